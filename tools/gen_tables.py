@@ -1,0 +1,217 @@
+#!/usr/bin/env python3
+"""Generate misti_b200/csrc/misti_tables.h: the constant structure tables of the lineage chains.
+
+Derivation is index-arithmetic on the state layout documented in SURVEY.md section 8(a) (which
+restates TwoPopulations.MapStateToInd/MapIndToState, TwoPopulations.py:99-186, and
+OnePopulation.py:64-107) -- deliberately a different construction from oracle/misti_oracle.py
+(which closes the state space by breadth-first search), so that tests/test_tables.py can
+cross-check the two and both against tests/golden/tables.json (reference output).
+
+A state is a multiset of lineages; a lineage is (d0, d1, deme) = (#genome-1 samples below it,
+#genome-2 samples below it, deme it sits in).
+
+Emitted tables
+  MISTI_GEN_*     off-diagonal generator entries (row, col, kind, count); kind 0/1 = coalescence
+                  in deme 0/1 (rate la[kind]), 2/3 = migration out of deme 0/1 (rate mu[kind-2]);
+                  MISTI_GEN_DIAG[col][kind] = multiplicity on the diagonal (entered with minus).
+  MISTI_ELL       the same off-diagonal entries grouped by row, 4 slots {col, kind, count} per row.
+  MISTI_W44/W8    branch-type counts per state (StateToJAF).
+  MISTI_PULSE_*   pulse map entries (row, col, a, b): value (1-r)^a r^b, per source deme.
+  MISTI_ANC_*     ancient-sample reset masks (AncientSampleP0).
+  MISTI_COLLAPSE  44 -> 8 block index (CollapsePops).
+  MISTI_WG*       W8 * G_k for the three spectral projectors of the one-population generator
+                  L8 (eigenvalues -6, -3, -1), and L8 itself.
+"""
+import itertools
+import os
+from fractions import Fraction
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+OUT = os.path.join(HERE, "..", "misti_b200", "csrc", "misti_tables.h")
+
+# ---- lineage "types" by descendant counts
+TYPES_BY_COUNT = {
+    4: [[(1, 0), (1, 0), (0, 1), (0, 1)]],
+    3: [[(2, 0), (0, 1), (0, 1)], [(1, 1), (1, 0), (0, 1)], [(0, 2), (1, 0), (1, 0)]],
+    2: [[(2, 1), (0, 1)], [(1, 2), (1, 0)], [(2, 0), (0, 2)], [(1, 1), (1, 1)]],
+}
+CONFIGS = TYPES_BY_COUNT[4] + TYPES_BY_COUNT[3] + TYPES_BY_COUNT[2]  # == one-population state order
+BASE = [0, 9, 15, 23, 29, 33, 37, 41, 44]
+
+
+def key(state):
+    return tuple(sorted(state))
+
+
+def build_states():
+    """index -> canonical multiset of (d0, d1, deme), following the layout formulas."""
+    idx = {}
+    for cfg_i, cfg in enumerate(CONFIGS):
+        for demes in itertools.product((0, 1), repeat=len(cfg)):
+            st = [(d0, d1, p) for (d0, d1), p in zip(cfg, demes)]
+            if cfg_i == 0:
+                j = demes[0] + demes[1]
+                i = demes[2] + demes[3]
+                ind = i + 3 * j
+            elif cfg_i in (1, 3):
+                ind = BASE[cfg_i] + 3 * demes[0] + demes[1] + demes[2]
+            elif cfg_i == 2:
+                ind = BASE[cfg_i] + 4 * demes[0] + 2 * demes[1] + demes[2]
+            elif cfg_i in (4, 5, 6):
+                ind = BASE[cfg_i] + 2 * demes[0] + demes[1]
+            else:
+                ind = BASE[cfg_i] + demes[0] + demes[1]
+            k = key(st)
+            if k in idx:
+                assert idx[k] == ind
+            idx[k] = ind
+    assert sorted(idx.values()) == list(range(44))
+    inv = {v: list(k) for k, v in idx.items()}
+    return idx, [inv[i] for i in range(44)]
+
+
+IDX, STATES = build_states()
+SLOT = {(1, 0): 0, (2, 0): 1, (0, 1): 2, (1, 1): 3, (2, 1): 4, (0, 2): 5, (1, 2): 6}
+
+
+def generator_entries():
+    off = {}
+    diag = [[0, 0, 0, 0] for _ in range(44)]
+    for col, st in enumerate(STATES):
+        n = len(st)
+        for i in range(n):
+            d0, d1, p = st[i]
+            moved = list(st)
+            moved[i] = (d0, d1, 1 - p)
+            row = IDX[key(moved)]
+            off[(row, col, 2 + p)] = off.get((row, col, 2 + p), 0) + 1
+            diag[col][2 + p] += 1
+            for j in range(i + 1, n):
+                if st[j][2] != p:
+                    continue
+                rest = [st[k] for k in range(n) if k not in (i, j)]
+                rest.append((d0 + st[j][0], d1 + st[j][1], p))
+                diag[col][p] += 1
+                if len(rest) >= 2:
+                    row = IDX[key(rest)]
+                    off[(row, col, p)] = off.get((row, col, p), 0) + 1
+    pos = {}
+    for (r, c, k) in off:
+        assert (r, c) not in pos, "two rate kinds on one off-diagonal entry"
+        pos[(r, c)] = k
+    ent = sorted((r, c, k, cnt) for (r, c, k), cnt in off.items())
+    return ent, diag
+
+
+def pulse_entries(src):
+    ent = {}
+    for col, st in enumerate(STATES):
+        movers = [k for k, l in enumerate(st) if l[2] == src]
+        for mask in range(1 << len(movers)):
+            new = list(st)
+            a = b = 0
+            for bit, k in enumerate(movers):
+                if mask >> bit & 1:
+                    new[k] = (st[k][0], st[k][1], 1 - src)
+                    b += 1
+                else:
+                    a += 1
+            row = IDX[key(new)]
+            ent.setdefault((row, col, a, b), 0)
+            ent[(row, col, a, b)] += 1
+    return sorted((r, c, a, b, m) for (r, c, a, b), m in ent.items())
+
+
+def onepop():
+    cfg_index = {tuple(sorted(c)): i for i, c in enumerate(CONFIGS)}
+    L = [[Fraction(0)] * 8 for _ in range(8)]
+    for col, cfg in enumerate(CONFIGS):
+        n = len(cfg)
+        for i in range(n):
+            for j in range(i + 1, n):
+                rest = [cfg[k] for k in range(n) if k not in (i, j)]
+                rest.append((cfg[i][0] + cfg[j][0], cfg[i][1] + cfg[j][1]))
+                L[col][col] -= 1
+                if len(rest) >= 2:
+                    L[cfg_index[tuple(sorted(rest))]][col] += 1
+    return L
+
+
+def matmul(A, B):
+    n, m, p = len(A), len(B), len(B[0])
+    return [[sum(A[i][k] * B[k][j] for k in range(m)) for j in range(p)] for i in range(n)]
+
+
+def shifted(L, s):
+    return [[L[i][j] + (s if i == j else 0) for j in range(8)] for i in range(8)]
+
+
+def fmt(v):
+    return repr(float(v))
+
+
+def main():
+    ent, diag = generator_entries()
+    W44 = [[0] * 44 for _ in range(7)]
+    for i, st in enumerate(STATES):
+        for (d0, d1, _p) in st:
+            W44[SLOT[(d0, d1)]][i] += 1
+    W8 = [[0] * 8 for _ in range(7)]
+    for i, cfg in enumerate(CONFIGS):
+        for d in cfg:
+            W8[SLOT[d]][i] += 1
+    collapse = [max(b for b in range(8) if BASE[b] <= i) for i in range(44)]
+    anc2 = [int(sum(1 for l in st if l == (1, 0, 0)) == 2) for st in STATES]
+    anc11 = [int(sum(1 for l in st if l == (2, 0, 0)) == 1) for st in STATES]
+    stationary = [i for i, st in enumerate(STATES) if len(st) == 2 and st[0][2] != st[1][2]]
+    L = onepop()
+    # spectral projectors of L8: eigenvalues -6, -3, -1 (diagonal blocks are scalar => diagonalisable)
+    G6 = [[v / 15 for v in row] for row in matmul(shifted(L, 3), shifted(L, 1))]
+    G3 = [[v / -6 for v in row] for row in matmul(shifted(L, 6), shifted(L, 1))]
+    G1 = [[v / 10 for v in row] for row in matmul(shifted(L, 6), shifted(L, 3))]
+    for i in range(8):
+        for j in range(8):
+            assert G6[i][j] + G3[i][j] + G1[i][j] == (1 if i == j else 0)
+            assert -6 * G6[i][j] - 3 * G3[i][j] - G1[i][j] == L[i][j]
+    W8f = [[Fraction(v) for v in row] for row in W8]
+    WG = [matmul(W8f, G) for G in (G6, G3, G1)]
+    pulses = [pulse_entries(0), pulse_entries(1)]
+
+    o = []
+    o.append("// GENERATED by tools/gen_tables.py -- do not edit.  See that file for the derivation.")
+    o.append("#pragma once")
+    o.append("#define MISTI_NSTATE2 44")
+    o.append("#define MISTI_NSTATE1 8")
+    o.append("#define MISTI_GEN_NNZ %d" % len(ent))
+    o.append("// {row, col, kind, count}")
+    o.append("#define MISTI_GEN_ENTRIES_INIT { %s }" % ", ".join("{%d,%d,%d,%d}" % e for e in ent))
+    o.append("#define MISTI_GEN_DIAG_INIT { %s }" % ", ".join("{%d,%d,%d,%d}" % tuple(d) for d in diag))
+    # row-oriented (ELL) copy of the off-diagonal entries: 4 slots per row, {col, kind, count}, padded with count 0
+    ell = [[e[1:] for e in ent if e[0] == r] for r in range(44)]
+    assert max(len(r) for r in ell) == 4
+    o.append("#define MISTI_ELL_WIDTH 4")
+    o.append("#define MISTI_ELL_INIT { %s }" % ", ".join(
+        "{" + ",".join("{%d,%d,%d}" % e for e in (row + [(r, 0, 0)] * (4 - len(row)))) + "}" for r, row in enumerate(ell)))
+    o.append("#define MISTI_W44_INIT { %s }" % ", ".join("{" + ",".join(str(v) for v in row) + "}" for row in W44))
+    o.append("#define MISTI_W8_INIT { %s }" % ", ".join("{" + ",".join(str(v) for v in row) + "}" for row in W8))
+    o.append("#define MISTI_COLLAPSE_INIT { %s }" % ",".join(str(v) for v in collapse))
+    o.append("#define MISTI_ANC2_INIT { %s }" % ",".join(str(v) for v in anc2))
+    o.append("#define MISTI_ANC11_INIT { %s }" % ",".join(str(v) for v in anc11))
+    o.append("#define MISTI_NSTATIONARY %d" % len(stationary))
+    o.append("#define MISTI_STATIONARY_INIT { %s }" % ",".join(str(v) for v in stationary))
+    for s in (0, 1):
+        o.append("#define MISTI_PULSE%d_NNZ %d" % (s, len(pulses[s])))
+        o.append("// {row, col, a, b, multiplicity}: value = multiplicity * (1-r)^a * r^b")
+        o.append("#define MISTI_PULSE%d_INIT { %s }" % (s, ", ".join("{%d,%d,%d,%d,%d}" % e for e in pulses[s])))
+        rowptr = [sum(1 for e in pulses[s] if e[0] < r) for r in range(45)]
+        o.append("#define MISTI_PULSE%d_ROWPTR_INIT { %s }" % (s, ",".join(str(v) for v in rowptr)))
+    o.append("#define MISTI_L8_INIT { %s }" % ", ".join("{" + ",".join(fmt(v) for v in row) + "}" for row in L))
+    for name, M in zip(("WG6", "WG3", "WG1"), WG):
+        o.append("#define MISTI_%s_INIT { %s }" % (name, ", ".join("{" + ",".join(fmt(v) for v in row) + "}" for row in M)))
+    with open(OUT, "w") as f:
+        f.write("\n".join(o) + "\n")
+    print("wrote", OUT, "gen nnz", len(ent), "pulse nnz", len(pulses[0]), len(pulses[1]), "stationary", stationary)
+
+
+if __name__ == "__main__":
+    main()
