@@ -1,0 +1,148 @@
+/* misti_b200.h -- C ABI of libmisti_b200.so: batched MiSTI model evaluation on one B200 (sm_100a).
+ *
+ * The reference (Genomics-HSE/MiSTI) is pure Python and has no FFI layer; the boundary a replacement
+ * has to honour is the Python class API.  This header declares the C entry
+ * points the Python host in misti_b200/ binds with ctypes and which a maintainer of the reference
+ * would bind in the same way (INTEGRATION.md shows the stub).  Each entry point cites the reference
+ * interface it replaces.  Plain pointers and sizes only; no torch / numpy types.
+ *
+ * There is NO CPU path behind these functions: every evaluation runs in the CUDA kernels of
+ * misti_b200/csrc/misti_kernels.cu, and misti_ctx_create fails when no CUDA device is usable.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative MISTI_E_* code on API misuse or CUDA failure
+ *     (text via misti_last_error); numerical outcomes are reported PER ITEM in status[] with the
+ *     reference's conventions (llh = -inf where MigrationInference.JAFSLikelihood returns -inf).
+ *   - the caller owns every buffer it passes; inputs are copied at call time.
+ *   - a context is bound to one device and one stream; calls on one context must be serialised by
+ *     the caller (the reference is single-threaded: MiSTI.py:23-25).  One context per process per GPU.
+ */
+#ifndef MISTI_B200_H
+#define MISTI_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MISTI_ABI_VERSION 1
+
+/* error codes (function return values) */
+#define MISTI_E_ARG (-1)     /* invalid argument / unknown id / capacity exceeded */
+#define MISTI_E_CUDA (-2)    /* CUDA runtime failure (see misti_last_error)       */
+#define MISTI_E_NODEV (-3)   /* no usable CUDA device: there is no CPU fallback   */
+
+/* evaluation flags = the MigrationInference keyword arguments (MigrationInference.py:41-200) */
+#define MISTI_FLAG_CORRECT 1u  /* not trueEPS: run the coalescence-rate correction (CorrectLambdas) */
+#define MISTI_FLAG_CPFIT 2u    /* cpfit=True: fit non-coalescence probabilities                     */
+#define MISTI_FLAG_SMOOTH 4u   /* smooth=True: SmoothConst over runs of equal PSMC rates            */
+#define MISTI_FLAG_UNFOLDED 8u /* unfolded=True: 7-bin likelihood, else 4 folded bins               */
+#define MISTI_FLAG_DEVICE_PTRS 256u /* params/model_ids/lc_inject/llh/jafs/status are DEVICE pointers; the call is
+                                       asynchronous on the context's stream (no host synchronisation)  */
+
+/* per-item status codes */
+#define MISTI_OK 0
+#define MISTI_NEGATIVE_PARAM 1     /* "Hit negative value of migration rate" (MigrationInference.py:569-572)  */
+#define MISTI_CORRECTION_FAILED 2  /* "Lambda correction failed" (MigrationInference.py:575-578)              */
+#define MISTI_NONFINITE 3          /* the reference would have raised or produced NaN                         */
+#define MISTI_INFINITE_COAL_TIME 4 /* last interval before the split without migration (:475-476, ref. exits)  */
+
+#define MISTI_MAX_BANDS 8
+#define MISTI_MAX_PULSES 8
+#define MISTI_MAX_PARAMS 16
+
+typedef struct misti_ctx misti_ctx;
+
+/* One model layout = what MigrationInference.__init__ + SetModel hold (MigrationInference.py:41-200,
+ * 229-289): the split interval, the sampling date of genome 2, migration bands [start, end) per
+ * source deme and pulses, each either fixed (opt = -1) or bound to optimiser parameter `opt`
+ * (MapParameters, :291-298: bands first, then pulses, in the order given).  pop is 0-based. */
+typedef struct misti_model_desc {
+    int32_t grid_id;     /* time grid registered with misti_add_grid                    */
+    int32_t split_t;     /* first one-population interval (0 .. numT)                   */
+    int32_t sample_date; /* interval index at which genome 2 was sampled (0 = present)  */
+    int32_t n_bands;
+    int32_t n_pulses;
+    int32_t n_params;    /* number of optimiser parameters this model consumes          */
+    int32_t band_pop[MISTI_MAX_BANDS], band_start[MISTI_MAX_BANDS], band_end[MISTI_MAX_BANDS], band_opt[MISTI_MAX_BANDS];
+    int32_t pulse_pop[MISTI_MAX_PULSES], pulse_time[MISTI_MAX_PULSES], pulse_opt[MISTI_MAX_PULSES];
+    double band_val[MISTI_MAX_BANDS];
+    double pulse_val[MISTI_MAX_PULSES];
+} misti_model_desc;
+
+/* Optional outputs / inputs of misti_eval_batch; any pointer may be NULL.  Host or device pointers
+ * according to MISTI_FLAG_DEVICE_PTRS.  numT_max = largest numT over the registered grids. */
+typedef struct misti_eval_io {
+    const double* lc_inject; /* [B][numT_max][2] corrected rates to use instead of running the correction   */
+    double* jafs;            /* [B][7]  normalised expected JSFS (MigrationInference.JAFS)                  */
+    double* jafs_raw;        /* [B][7]  JAFSpectrum() before normalisation                                  */
+    double* lc_out;          /* [B][numT_max][2] corrected rates (MigrationInference.lc)                    */
+    double* pr_out;          /* [B][numT_max+1][3][2] 3-state trajectories (MigrationInference.Pr)          */
+    int32_t* status;         /* [B]                                                                        */
+    int32_t* nfev;           /* [B] residual evaluations spent in the correction (least_squares nfev sum)  */
+    int32_t* terms;          /* [B] sparse mat-vecs spent in the JSFS stage                                 */
+} misti_eval_io;
+
+int misti_abi_version(void);
+
+/* Create a context on CUDA device `device`.  `stream` is a cudaStream_t to launch on (e.g. the
+ * caller's torch stream) or NULL for a private stream.  Replaces: construction of the model
+ * objects in MiSTI.py:213. */
+int misti_ctx_create(int device, void* stream, misti_ctx** out);
+void misti_ctx_destroy(misti_ctx* ctx);
+const char* misti_last_error(const misti_ctx* ctx);
+int misti_ctx_set_stream(misti_ctx* ctx, void* stream);
+int misti_ctx_synchronize(misti_ctx* ctx);
+
+/* Register a merged PSMC time grid: times[numT-1] interval lengths and lh[numT][2] apparent
+ * coalescence rates of the two genomes (InputData.times / .lambdas from migrationIO.ReadPSMC,
+ * migrationIO.py:224-295, after the constructor's fractional-split surgery, MigrationInference.py:89-99). */
+int misti_add_grid(misti_ctx* ctx, int32_t numT, const double* times, const double* lh, int32_t* grid_id);
+
+/* Register a model layout (MigrationInference.SetModel, MigrationInference.py:229-289). */
+int misti_add_model(misti_ctx* ctx, const misti_model_desc* desc, int32_t* model_id);
+/* Drop all grids and models (data rows are kept). */
+int misti_clear_models(misti_ctx* ctx);
+
+/* Observed spectra: sfs[R][8] = [total sites, 7 counts] rows as read by MiSTI.py:172-178 (row 0 =
+ * data, further rows = bootstrap replicates).  llh_const[R] = lnGamma(n+1) - sum lnGamma(k_i+1)
+ * over the 7 (unfolded) or 4 folded bins (MigrationInference.SetJAFS, :202-227); NULL = computed
+ * here with lgamma().  `unfolded` selects the binning. */
+int misti_set_data(misti_ctx* ctx, int32_t R, const double* sfs, const double* llh_const, int32_t unfolded);
+
+/* Evaluate B items.  Item b uses model model_ids[b] (or `model_default` when model_ids is NULL)
+ * and the optimiser vector params[b*P .. b*P+P) (P >= that model's n_params, P <= MISTI_MAX_PARAMS).
+ * llh[b*R + r] = composite log-likelihood of item b against data row r (MigrationInference
+ * .JAFSLikelihood, MigrationInference.py:566-614); -inf where the reference returns -inf.
+ * Replaces: one MigrationInference.JAFSLikelihood call per item per data row. */
+int misti_eval_batch(misti_ctx* ctx, int32_t B, int32_t P, const double* params, const int32_t* model_ids,
+                     int32_t model_default, uint32_t flags, double mixture_th, double* llh, const misti_eval_io* io);
+
+/* Score B given spectra (7 non-negative weights each, normalised on the device) against every data
+ * row: llh[b*R + r].  Host pointers.  Replaces the likelihood tail used on its own, e.g.
+ * MigrationInference.MaximumLLHFunction (MigrationInference.py:696-711) with the data spectrum. */
+int misti_score_spectra(misti_ctx* ctx, int32_t B, const double* spectra, double* llh);
+
+/* Device time in milliseconds of the two kernels of the last misti_eval_batch on this context
+ * (CUDA events on the context's stream): out[0] = correction kernel, out[1] = JSFS+likelihood kernel.
+ * Synchronises with the stream. */
+int misti_last_kernel_ms(misti_ctx* ctx, float* out2);
+/* Number of kernel launches issued by this context so far. */
+int64_t misti_launch_count(const misti_ctx* ctx);
+
+/* Structure tables of the lineage chains, produced ON THE DEVICE from the same tables the kernels use
+ * (for the TwoPopulations / OnePopulation mirror classes).  generator: 44x44 row-major
+ * (TwoPopulations.SetMatrix before the stationary states are deleted, TwoPopulations.py:231-238);
+ * which = 1: one-population 8x8 generator for rate l1 (OnePopulation.SetMatrix, OnePopulation.py:153-158). */
+int misti_generator(misti_ctx* ctx, int32_t which, double l1, double l2, double m1, double m2, double* out);
+/* PulseMigration (TwoPopulations.py:361-377) and AncientSampleP0 (:246-262) applied to P0[44]. */
+int misti_pulse(misti_ctx* ctx, const double* P0, double rate, int32_t src_pop, double* P1);
+int misti_ancient_reset(misti_ctx* ctx, const double* P0, double* P1);
+/* StateToJAF for all states: out[44][7] (which = 0) or out[8][7] (which = 1). */
+int misti_state_to_jaf(misti_ctx* ctx, int32_t which, int32_t* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MISTI_B200_H */

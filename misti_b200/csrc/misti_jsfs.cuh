@@ -42,12 +42,16 @@ struct PulseEntry { unsigned char row, col, a, b, mult; };
     SPEC double PFX##wg3[7][8] = MISTI_WG3_INIT;                                \
     SPEC double PFX##wg1[7][8] = MISTI_WG1_INIT;
 
+// Under nvcc the table users are device-only functions reading __device__ copies; the test-only
+// host build (g++) reads plain static copies.
 #if defined(__CUDACC__)
 MISTI_DEFINE_TABLES(static __device__ const, d_)
 #define MISTI_TAB(name) d_##name
+#define MISTI_D __device__
 #else
 MISTI_DEFINE_TABLES(static const, h_)
 #define MISTI_TAB(name) h_##name
+#define MISTI_D
 #endif
 
 // ---- lane groups ------------------------------------------------------------------------------
@@ -109,7 +113,7 @@ MISTI_HD inline void post_split_coeffs(const ModelDesc& md, const double* times,
 // 2*44 doubles shared by the group.  On return every lane holds the UNNORMALISED spectrum in
 // jafs[0..6] (MigrationInference.JAFSpectrum's return value) and the number of mat-vecs in *terms.
 template <class G>
-MISTI_HD inline int jsfs_item(const G& g, const ModelDesc& md, const double* times, const double* params, const double* lc,
+MISTI_D inline int jsfs_item(const G& g, const ModelDesc& md, const double* times, const double* params, const double* lc,
                               long stride, const double* cpost, double* ysm, double* jafs, int* terms) {
     constexpr int RPL = (44 + G::LANES - 1) / G::LANES;
     const int lane = g.lane();

@@ -1,0 +1,706 @@
+// misti_kernels.cu -- CUDA kernels (sm_100a) and the C ABI of libmisti_b200.so.
+//
+// Two kernels make one batched evaluation:
+//   misti_correct_kernel   one THREAD per item: parameter mapping, negative-parameter test, the
+//                          sequential coalescence-rate correction chain (CorrectLambdas / CorrectLambda /
+//                          Smooth, incl. an iterate-faithful trust-region-reflective least-squares
+//                          solver), and the post-split closed-form coefficients.
+//   misti_jsfs_kernel      one WARP per item: generator assembly from (lc, mi), uniformised
+//                          propagation + branch-length integrals on the 44-state chain, pulses,
+//                          ancient-sample reset, collapse, closed-form one-population tail, the
+//                          7x44 / 7x8 JSFS contraction, normalisation, and -- fused -- the multinomial
+//                          composite log-likelihood against every data row (bootstrap replicates),
+//                          reduced with warp shuffles.
+// There is no CPU path: every entry point below launches on the device or fails.
+#include <cuda_runtime.h>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "misti_jsfs.cuh"
+
+namespace {
+
+using misti::ModelDesc;
+
+constexpr int kCorrectThreads = 64;
+constexpr int kJsfsWarps = 4;
+constexpr int kMaxChunk = 1 << 20;
+
+static __device__ const double d_l8[8][8] = MISTI_L8_INIT;
+static __device__ const unsigned char d_w8[7][8] = MISTI_W8_INIT;
+
+// ------------------------------------------------------------------------------------------------
+// K1: correction chain, one thread per item
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kCorrectThreads)
+misti_correct_kernel(int B, int P, const double* __restrict__ params, const int* __restrict__ model_ids, int model_default,
+                     const ModelDesc* __restrict__ models, const double* __restrict__ times, const double* __restrict__ lh,
+                     unsigned flags, double mixtureTH, const double* __restrict__ lc_inject, int numT_max, double* lc,
+                     long stride, double* __restrict__ cpost, double* pr_out, int* __restrict__ status, int* __restrict__ nfev) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const ModelDesc& md = models[model_ids ? model_ids[b] : model_default];
+    const double* tt = times + md.grid_off;
+    const double* ll = lh + 2 * md.grid_off;
+    const double* par = params + (long)b * P;
+    double* lcb = lc + b;
+    int st = MISTI_OK, nf = 0;
+    if (lc_inject) {
+        for (int i = 0; i < md.n_params; ++i)
+            if (par[i] < 0) st = MISTI_NEGATIVE_PARAM;
+        const double* src = lc_inject + (long)b * 2 * numT_max;
+        for (int j = 0; j < 2 * md.numT; ++j) lcb[j * stride] = src[j];
+    } else {
+        double* pr = pr_out ? pr_out + (long)b * (numT_max + 1) * 6 : nullptr;
+        st = misti::correct_lambdas_item(md, tt, ll, par, flags, mixtureTH, lcb, stride, pr, &nf);
+    }
+    double cp[3] = {0.0, 0.0, 0.0};
+    if (st == MISTI_OK) misti::post_split_coeffs(md, tt, lcb, stride, cp);
+    cpost[b] = cp[0];
+    cpost[stride + b] = cp[1];
+    cpost[2 * stride + b] = cp[2];
+    status[b] = st;
+    nfev[b] = nf;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2: expected JSFS + composite log-likelihood, one warp per item
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kJsfsWarps * 32)
+misti_jsfs_kernel(int B, int P, const double* __restrict__ params, const int* __restrict__ model_ids, int model_default,
+                  const ModelDesc* __restrict__ models, const double* __restrict__ times, const double* __restrict__ lc,
+                  long stride, const double* __restrict__ cpost, const double* __restrict__ data, int R, int unfolded,
+                  double* __restrict__ llh, double* __restrict__ jafs, double* __restrict__ jafs_raw, int* __restrict__ status,
+                  int* __restrict__ terms) {
+    __shared__ double ysm_all[kJsfsWarps][88];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double* ysm = ysm_all[warp];
+    const misti::WarpLanes g;
+    const int nwarps = gridDim.x * kJsfsWarps;
+    for (int b = blockIdx.x * kJsfsWarps + warp; b < B; b += nwarps) {
+        const ModelDesc& md = models[model_ids ? model_ids[b] : model_default];
+        int st = status[b];
+        double raw[7], jn[7], logj[7];
+        int nt = 0;
+        if (st == MISTI_OK) {
+            const double cp[3] = {cpost[b], cpost[stride + b], cpost[2 * stride + b]};
+            st = misti::jsfs_item(g, md, times + md.grid_off, params + (long)b * P, lc + b, stride, cp, ysm, raw, &nt);
+        }
+        if (st == MISTI_OK && !misti::jafs_normalise_logs(raw, unfolded != 0, jn, logj)) st = MISTI_NONFINITE;
+        if (st != MISTI_OK)
+            for (int c = 0; c < 7; ++c) raw[c] = jn[c] = nan("");
+        if (lane == 0) {
+            status[b] = st;
+            if (terms) terms[b] = nt;
+        }
+        if (lane < 7) {
+            double v = jn[0], w = raw[0];
+#pragma unroll
+            for (int c = 1; c < 7; ++c)
+                if (lane == c) { v = jn[c]; w = raw[c]; }
+            if (jafs) jafs[(long)b * 7 + lane] = v;
+            if (jafs_raw) jafs_raw[(long)b * 7 + lane] = w;
+        }
+        // fused composite likelihood over all data rows (bootstrap replicates): lanes stride the rows
+        const double bad = (st == MISTI_NEGATIVE_PARAM || st == MISTI_CORRECTION_FAILED) ? -misti::kInf : nan("");
+        for (int r = lane; r < R; r += 32)
+            llh[(long)b * R + r] = st == MISTI_OK ? misti::score_row(data + 8 * (long)r, logj) : bad;
+    }
+}
+
+// likelihood tail alone: one warp per spectrum, lanes stride the data rows
+__global__ void __launch_bounds__(128)
+misti_score_kernel(int B, const double* __restrict__ spectra, const double* __restrict__ data, int R, int unfolded,
+                   double* __restrict__ llh) {
+    const int lane = threadIdx.x & 31;
+    const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (b >= B) return;
+    double raw[7], jn[7], logj[7];
+    for (int c = 0; c < 7; ++c) raw[c] = spectra[(long)b * 7 + c];
+    const bool ok = misti::jafs_normalise_logs(raw, unfolded != 0, jn, logj);
+    for (int r = lane; r < R; r += 32) llh[(long)b * R + r] = ok ? misti::score_row(data + 8 * (long)r, logj) : nan("");
+}
+
+// lc[(2t+g)*stride + b]  ->  out[b][numT_max][2]
+__global__ void misti_gather_lc_kernel(int B, int numT_max, const int* __restrict__ model_ids, int model_default,
+                                       const ModelDesc* __restrict__ models, const double* __restrict__ lc, long stride,
+                                       double* __restrict__ out) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long n = (long)B * 2 * numT_max;
+    if (i >= n) return;
+    const int b = (int)(i / (2 * numT_max)), j = (int)(i % (2 * numT_max));
+    const ModelDesc& md = models[model_ids ? model_ids[b] : model_default];
+    out[i] = j < 2 * md.numT ? lc[j * stride + b] : 0.0;
+}
+
+// ---- structure-table export kernels (TwoPopulations / OnePopulation mirror classes) ---------------
+__global__ void misti_generator_kernel(int which, double l1, double l2, double m1, double m2, double* out) {
+    const int r = threadIdx.x;
+    if (which == 1) {
+        if (r < 8)
+            for (int c = 0; c < 8; ++c) out[r * 8 + c] = l1 * d_l8[r][c];
+        return;
+    }
+    if (r >= 44) return;
+    const double rate[4] = {l1, l2, m1, m2};
+    for (int c = 0; c < 44; ++c) out[r * 44 + c] = 0.0;
+    double d = 0.0;
+    for (int k = 0; k < 4; ++k) d += (double)misti::d_diag[r][k] * rate[k];
+    out[r * 44 + r] = -d;
+    for (int e = 0; e < MISTI_ELL_WIDTH; ++e) {
+        const misti::EllEntry en = misti::d_ell[r][e];
+        if (en.cnt) out[r * 44 + en.col] += (double)en.cnt * rate[en.kind];
+    }
+}
+
+__global__ void misti_pulse_kernel(const double* P0, double rate, int src, double* P1) {
+    const int r = threadIdx.x;
+    if (r >= 44) return;
+    const misti::PulseEntry* ent = src == 0 ? misti::d_pulse0 : misti::d_pulse1;
+    const unsigned char* rp = src == 0 ? misti::d_pulse0_rowptr : misti::d_pulse1_rowptr;
+    double acc = 0.0;
+    for (int e = rp[r]; e < rp[r + 1]; ++e) {
+        const misti::PulseEntry pe = ent[e];
+        acc += (double)pe.mult * pow(1.0 - rate, (double)pe.a) * pow(rate, (double)pe.b) * P0[pe.col];
+    }
+    P1[r] = acc;
+}
+
+__global__ void misti_ancient_kernel(const double* P0, double* P1) {
+    const int r = threadIdx.x;
+    if (r >= 44) return;
+    double v = 0.0;
+    if (r == 2) {
+        for (int i = 0; i < 44; ++i)
+            if (misti::d_anc2[i]) v += P0[i];
+    } else if (r == 11) {
+        for (int i = 0; i < 44; ++i)
+            if (misti::d_anc11[i]) v += P0[i];
+    }
+    P1[r] = v;
+}
+
+__global__ void misti_state_to_jaf_kernel(int which, int* out) {
+    const int r = threadIdx.x;
+    if (which == 1) {
+        if (r < 8)
+            for (int c = 0; c < 7; ++c) out[r * 7 + c] = d_w8[c][r];
+    } else if (r < 44) {
+        for (int c = 0; c < 7; ++c) out[r * 7 + c] = misti::d_w44[c][r];
+    }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// Context
+// ------------------------------------------------------------------------------------------------
+struct misti_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::string err;
+    int sm_count = 148;
+    // grids (pooled: grid g occupies intervals [grid_off[g], grid_off[g] + numT[g]); times padded with one 0)
+    std::vector<int> grid_numT, grid_off;
+    std::vector<double> h_times, h_lh;
+    int numT_max = 0;
+    double *d_times = nullptr, *d_lh = nullptr;
+    size_t d_grid_cap = 0;
+    bool grids_dirty = false;
+    // models
+    std::vector<ModelDesc> h_models;
+    ModelDesc* d_models = nullptr;
+    size_t d_models_cap = 0;
+    bool models_dirty = false;
+    // data rows
+    int R = 0, unfolded = 1;
+    double* d_data = nullptr;
+    size_t d_data_cap = 0;
+    // batch buffers
+    size_t cap = 0;
+    int cap_numT = 0;
+    double *d_lc = nullptr, *d_cpost = nullptr;
+    int *d_status = nullptr, *d_nfev = nullptr;
+    // staging for host-pointer calls
+    size_t st_cap = 0, st_capR = 0, st_capP = 0;
+    int st_numT = 0;
+    double *s_params = nullptr, *s_llh = nullptr, *s_jafs = nullptr, *s_jafs_raw = nullptr;
+    int *s_model_ids = nullptr, *s_terms = nullptr;
+    double *s_lc_io = nullptr, *s_pr = nullptr;
+    size_t s_lc_io_cap = 0, s_pr_cap = 0;
+    double* d_small = nullptr;  // 44*44 + 2*44 doubles for the table export kernels
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    bool ev_valid = false;
+    int64_t launches = 0;
+};
+
+namespace {
+
+int fail(misti_ctx* ctx, int code, const std::string& msg) {
+    if (ctx) ctx->err = msg;
+    return code;
+}
+
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess)                                                                           \
+            return fail(ctx, MISTI_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));          \
+    } while (0)
+
+template <class T>
+int ensure(misti_ctx* ctx, T** p, size_t* cap, size_t need) {
+    if (need <= *cap && *p) return 0;
+    size_t ncap = *cap ? *cap : 1;
+    while (ncap < need) ncap *= 2;
+    if (*p) CK(cudaFree(*p));
+    *p = nullptr;
+    CK(cudaMalloc((void**)p, ncap * sizeof(T)));
+    *cap = ncap;
+    return 0;
+}
+
+template <class T>
+int realloc_exact(misti_ctx* ctx, T** p, size_t n) {
+    if (*p) CK(cudaFree(*p));
+    *p = nullptr;
+    if (n) CK(cudaMalloc((void**)p, n * sizeof(T)));
+    return 0;
+}
+
+int sync_tables(misti_ctx* ctx) {
+    if (ctx->grids_dirty) {
+        size_t need = ctx->h_times.size();
+        if (need > ctx->d_grid_cap) {
+            size_t ncap = ctx->d_grid_cap ? ctx->d_grid_cap : 256;
+            while (ncap < need) ncap *= 2;
+            if (ctx->d_times) CK(cudaFree(ctx->d_times));
+            if (ctx->d_lh) CK(cudaFree(ctx->d_lh));
+            ctx->d_times = ctx->d_lh = nullptr;
+            CK(cudaMalloc((void**)&ctx->d_times, ncap * sizeof(double)));
+            CK(cudaMalloc((void**)&ctx->d_lh, 2 * ncap * sizeof(double)));
+            ctx->d_grid_cap = ncap;
+        }
+        // the previous launches may still read the old tables: copies are stream-ordered behind them
+        CK(cudaMemcpyAsync(ctx->d_times, ctx->h_times.data(), need * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->d_lh, ctx->h_lh.data(), 2 * need * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        ctx->grids_dirty = false;
+    }
+    if (ctx->models_dirty) {
+        size_t need = ctx->h_models.size();
+        if (need > ctx->d_models_cap) {
+            size_t ncap = ctx->d_models_cap ? ctx->d_models_cap : 16;
+            while (ncap < need) ncap *= 2;
+            if (ctx->d_models) CK(cudaFree(ctx->d_models));
+            ctx->d_models = nullptr;
+            CK(cudaMalloc((void**)&ctx->d_models, ncap * sizeof(ModelDesc)));
+            ctx->d_models_cap = ncap;
+        }
+        CK(cudaMemcpyAsync(ctx->d_models, ctx->h_models.data(), need * sizeof(ModelDesc), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        ctx->models_dirty = false;
+    }
+    return 0;
+}
+
+int ensure_batch(misti_ctx* ctx, size_t B) {
+    if (B <= ctx->cap && ctx->cap_numT >= ctx->numT_max) return 0;
+    size_t ncap = ctx->cap ? ctx->cap : 1024;
+    while (ncap < B) ncap *= 2;
+    int rc;
+    if ((rc = realloc_exact(ctx, &ctx->d_lc, ncap * 2 * (size_t)ctx->numT_max))) return rc;
+    if ((rc = realloc_exact(ctx, &ctx->d_cpost, ncap * 3))) return rc;
+    if ((rc = realloc_exact(ctx, &ctx->d_status, ncap))) return rc;
+    if ((rc = realloc_exact(ctx, &ctx->d_nfev, ncap))) return rc;
+    ctx->cap = ncap;
+    ctx->cap_numT = ctx->numT_max;
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int misti_abi_version(void) { return MISTI_ABI_VERSION; }
+
+int misti_ctx_create(int device, void* stream, misti_ctx** out) {
+    if (!out) return MISTI_E_ARG;
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0 || device < 0 || device >= n) return MISTI_E_NODEV;
+    misti_ctx* ctx = new (std::nothrow) misti_ctx();
+    if (!ctx) return MISTI_E_ARG;
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return MISTI_E_NODEV; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+    if (stream) {
+        ctx->stream = (cudaStream_t)stream;
+    } else {
+        if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return MISTI_E_CUDA; }
+        ctx->own_stream = true;
+    }
+    for (int i = 0; i < 3; ++i)
+        if (cudaEventCreate(&ctx->ev[i]) != cudaSuccess) { delete ctx; return MISTI_E_CUDA; }
+    if (cudaMalloc((void**)&ctx->d_small, (44 * 44 + 2 * 44) * sizeof(double)) != cudaSuccess) { delete ctx; return MISTI_E_CUDA; }
+    *out = ctx;
+    return 0;
+}
+
+void misti_ctx_destroy(misti_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    void* ptrs[] = {ctx->d_times, ctx->d_lh, ctx->d_models, ctx->d_data, ctx->d_lc, ctx->d_cpost, ctx->d_status, ctx->d_nfev,
+                    ctx->s_params, ctx->s_llh, ctx->s_jafs, ctx->s_jafs_raw, ctx->s_model_ids, ctx->s_terms, ctx->s_lc_io,
+                    ctx->s_pr, ctx->d_small};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    for (int i = 0; i < 3; ++i)
+        if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* misti_last_error(const misti_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int misti_ctx_set_stream(misti_ctx* ctx, void* stream) {
+    if (!ctx) return MISTI_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->own_stream) { cudaStreamDestroy(ctx->stream); ctx->own_stream = false; }
+    if (stream) {
+        ctx->stream = (cudaStream_t)stream;
+    } else {
+        CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        ctx->own_stream = true;
+    }
+    ctx->ev_valid = false;
+    return 0;
+}
+
+int misti_ctx_synchronize(misti_ctx* ctx) {
+    if (!ctx) return MISTI_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int misti_add_grid(misti_ctx* ctx, int32_t numT, const double* times, const double* lh, int32_t* grid_id) {
+    if (!ctx) return MISTI_E_ARG;
+    if (numT < 1 || !lh || (numT > 1 && !times) || !grid_id) return fail(ctx, MISTI_E_ARG, "misti_add_grid: bad arguments");
+    for (int i = 0; i < 2 * numT; ++i)
+        if (!(lh[i] == lh[i])) return fail(ctx, MISTI_E_ARG, "misti_add_grid: NaN rate");
+    const int off = (int)ctx->h_times.size();
+    ctx->grid_numT.push_back(numT);
+    ctx->grid_off.push_back(off);
+    for (int i = 0; i < numT - 1; ++i) ctx->h_times.push_back(times[i]);
+    ctx->h_times.push_back(0.0);  // padding: the last interval is infinite and has no length entry
+    for (int i = 0; i < 2 * numT; ++i) ctx->h_lh.push_back(lh[i]);
+    if (numT > ctx->numT_max) ctx->numT_max = numT;
+    ctx->grids_dirty = true;
+    *grid_id = (int32_t)ctx->grid_numT.size() - 1;
+    return 0;
+}
+
+int misti_add_model(misti_ctx* ctx, const misti_model_desc* d, int32_t* model_id) {
+    if (!ctx) return MISTI_E_ARG;
+    if (!d || !model_id) return fail(ctx, MISTI_E_ARG, "misti_add_model: null argument");
+    if (d->grid_id < 0 || d->grid_id >= (int)ctx->grid_numT.size()) return fail(ctx, MISTI_E_ARG, "misti_add_model: unknown grid");
+    const int numT = ctx->grid_numT[d->grid_id];
+    if (d->split_t < 0 || d->split_t > numT) return fail(ctx, MISTI_E_ARG, "misti_add_model: split time outside the grid");
+    if (d->sample_date < 0 || d->sample_date > d->split_t)
+        return fail(ctx, MISTI_E_ARG, "misti_add_model: split time more recent than sample date");
+    if (d->n_bands < 0 || d->n_bands > MISTI_MAX_BANDS || d->n_pulses < 0 || d->n_pulses > MISTI_MAX_PULSES ||
+        d->n_params < 0 || d->n_params > MISTI_MAX_PARAMS)
+        return fail(ctx, MISTI_E_ARG, "misti_add_model: too many bands / pulses / parameters");
+    ModelDesc md;
+    std::memset(&md, 0, sizeof(md));
+    md.numT = numT; md.splitT = d->split_t; md.sampleDate = d->sample_date;
+    md.n_bands = d->n_bands; md.n_pulses = d->n_pulses; md.n_params = d->n_params;
+    md.grid_off = ctx->grid_off[d->grid_id];
+    for (int b = 0; b < d->n_bands; ++b) {
+        if ((d->band_pop[b] != 0 && d->band_pop[b] != 1) || d->band_start[b] < 0 || d->band_end[b] <= d->band_start[b] ||
+            d->band_end[b] > numT || d->band_opt[b] >= d->n_params || !(d->band_val[b] == d->band_val[b]))
+            return fail(ctx, MISTI_E_ARG, "misti_add_model: invalid migration band");
+        md.band_pop[b] = d->band_pop[b]; md.band_start[b] = d->band_start[b]; md.band_end[b] = d->band_end[b];
+        md.band_opt[b] = d->band_opt[b] < 0 ? -1 : d->band_opt[b]; md.band_val[b] = d->band_val[b];
+    }
+    for (int b = 0; b < d->n_pulses; ++b) {
+        if ((d->pulse_pop[b] != 0 && d->pulse_pop[b] != 1) || d->pulse_time[b] < 0 || d->pulse_time[b] >= numT ||
+            d->pulse_opt[b] >= d->n_params || !(d->pulse_val[b] == d->pulse_val[b]))
+            return fail(ctx, MISTI_E_ARG, "misti_add_model: invalid pulse");
+        md.pulse_pop[b] = d->pulse_pop[b]; md.pulse_time[b] = d->pulse_time[b];
+        md.pulse_opt[b] = d->pulse_opt[b] < 0 ? -1 : d->pulse_opt[b]; md.pulse_val[b] = d->pulse_val[b];
+    }
+    ctx->h_models.push_back(md);
+    ctx->models_dirty = true;
+    *model_id = (int32_t)ctx->h_models.size() - 1;
+    return 0;
+}
+
+int misti_clear_models(misti_ctx* ctx) {
+    if (!ctx) return MISTI_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->grid_numT.clear(); ctx->grid_off.clear(); ctx->h_times.clear(); ctx->h_lh.clear(); ctx->h_models.clear();
+    ctx->numT_max = 0;
+    ctx->grids_dirty = ctx->models_dirty = false;
+    return 0;
+}
+
+int misti_set_data(misti_ctx* ctx, int32_t R, const double* sfs, const double* llh_const, int32_t unfolded) {
+    if (!ctx) return MISTI_E_ARG;
+    if (R < 1 || !sfs) return fail(ctx, MISTI_E_ARG, "misti_set_data: need at least one data row");
+    CK(cudaSetDevice(ctx->device));
+    std::vector<double> rows((size_t)R * 8);
+    for (int r = 0; r < R; ++r) {
+        const double* d = sfs + 8 * (size_t)r + 1;
+        double* o = rows.data() + 8 * (size_t)r;
+        double snps = 0.0;
+        for (int i = 0; i < 7; ++i) snps += d[i];
+        double c;
+        if (unfolded) {
+            for (int i = 0; i < 7; ++i) o[i] = d[i];
+            c = lgamma(snps + 1.0);
+            for (int i = 0; i < 7; ++i) c -= lgamma(d[i] + 1.0);
+        } else {
+            o[0] = d[0] + d[6]; o[1] = d[1] + d[5]; o[2] = d[2] + d[4]; o[3] = d[3];
+            o[4] = o[5] = o[6] = 0.0;
+            c = lgamma(snps + 1.0);
+            c -= lgamma(o[0] + 1.0) + lgamma(o[1] + 1.0) + lgamma(o[2] + 1.0) + lgamma(o[3] + 1.0);
+        }
+        o[7] = llh_const ? llh_const[r] : c;
+    }
+    int rc;
+    if ((rc = ensure(ctx, &ctx->d_data, &ctx->d_data_cap, rows.size()))) return rc;
+    CK(cudaMemcpyAsync(ctx->d_data, rows.data(), rows.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->R = R;
+    ctx->unfolded = unfolded ? 1 : 0;
+    return 0;
+}
+
+static int eval_chunk(misti_ctx* ctx, int B, int P, const double* d_params, const int* d_model_ids, int model_default,
+                      unsigned flags, double mixture_th, const double* d_lc_inject, double* d_llh, double* d_jafs,
+                      double* d_jafs_raw, double* d_lc_out, double* d_pr, int* d_status_out, int* d_nfev_out, int* d_terms) {
+    int rc;
+    if ((rc = ensure_batch(ctx, (size_t)B))) return rc;
+    const long stride = (long)ctx->cap;
+    const int numT_max = ctx->numT_max;
+    CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+    misti_correct_kernel<<<(B + kCorrectThreads - 1) / kCorrectThreads, kCorrectThreads, 0, ctx->stream>>>(
+        B, P, d_params, d_model_ids, model_default, ctx->d_models, ctx->d_times, ctx->d_lh, flags, mixture_th, d_lc_inject,
+        numT_max, ctx->d_lc, stride, ctx->d_cpost, d_pr, ctx->d_status, ctx->d_nfev);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+    int blocks = (B + kJsfsWarps - 1) / kJsfsWarps;
+    const int max_blocks = ctx->sm_count * 16;
+    if (blocks > max_blocks) blocks = max_blocks;
+    misti_jsfs_kernel<<<blocks, kJsfsWarps * 32, 0, ctx->stream>>>(B, P, d_params, d_model_ids, model_default, ctx->d_models,
+                                                                   ctx->d_times, ctx->d_lc, stride, ctx->d_cpost, ctx->d_data,
+                                                                   ctx->R, ctx->unfolded, d_llh, d_jafs, d_jafs_raw,
+                                                                   ctx->d_status, d_terms);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(ctx->ev[2], ctx->stream));
+    ctx->ev_valid = true;
+    ctx->launches += 2;
+    if (d_lc_out) {
+        const long n = (long)B * 2 * numT_max;
+        misti_gather_lc_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(B, numT_max, d_model_ids, model_default,
+                                                                                     ctx->d_models, ctx->d_lc, stride, d_lc_out);
+        CK(cudaGetLastError());
+        ctx->launches += 1;
+    }
+    if (d_status_out) CK(cudaMemcpyAsync(d_status_out, ctx->d_status, (size_t)B * sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
+    if (d_nfev_out) CK(cudaMemcpyAsync(d_nfev_out, ctx->d_nfev, (size_t)B * sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
+    return 0;
+}
+
+int misti_eval_batch(misti_ctx* ctx, int32_t B, int32_t P, const double* params, const int32_t* model_ids, int32_t model_default,
+                     uint32_t flags, double mixture_th, double* llh, const misti_eval_io* io) {
+    if (!ctx) return MISTI_E_ARG;
+    if (B < 0 || P < 0 || P > MISTI_MAX_PARAMS || !llh) return fail(ctx, MISTI_E_ARG, "misti_eval_batch: bad arguments");
+    if (B == 0) return 0;
+    if (P > 0 && !params) return fail(ctx, MISTI_E_ARG, "misti_eval_batch: params is null");
+    if (ctx->h_models.empty()) return fail(ctx, MISTI_E_ARG, "misti_eval_batch: no model registered");
+    if (ctx->R < 1) return fail(ctx, MISTI_E_ARG, "misti_eval_batch: no data rows (misti_set_data)");
+    const int n_models = (int)ctx->h_models.size();
+    if (!model_ids) {
+        if (model_default < 0 || model_default >= n_models) return fail(ctx, MISTI_E_ARG, "misti_eval_batch: unknown model");
+        if (ctx->h_models[model_default].n_params > P) return fail(ctx, MISTI_E_ARG, "misti_eval_batch: incorrect number of parameters");
+    } else {
+        for (const ModelDesc& md : ctx->h_models)
+            if (md.n_params > P) return fail(ctx, MISTI_E_ARG, "misti_eval_batch: incorrect number of parameters");
+    }
+    CK(cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = sync_tables(ctx))) return rc;
+    misti_eval_io none;
+    std::memset(&none, 0, sizeof(none));
+    if (!io) io = &none;
+    const int numT_max = ctx->numT_max, R = ctx->R;
+    const int Pe = P > 0 ? P : 1;
+    static const double dummy_param = 0.0;
+    (void)dummy_param;
+
+    if (flags & MISTI_FLAG_DEVICE_PTRS) {
+        // asynchronous, everything already resident; chunks only bound the scratch size
+        for (long off = 0; off < B; off += kMaxChunk) {
+            const int n = (int)((B - off) < kMaxChunk ? (B - off) : kMaxChunk);
+            rc = eval_chunk(ctx, n, P, params ? params + off * P : nullptr, model_ids ? model_ids + off : nullptr, model_default,
+                            flags, mixture_th, io->lc_inject ? io->lc_inject + off * 2 * numT_max : nullptr, llh + off * R,
+                            io->jafs ? io->jafs + off * 7 : nullptr, io->jafs_raw ? io->jafs_raw + off * 7 : nullptr,
+                            io->lc_out ? io->lc_out + off * 2 * numT_max : nullptr,
+                            io->pr_out ? io->pr_out + off * (numT_max + 1) * 6 : nullptr, io->status ? io->status + off : nullptr,
+                            io->nfev ? io->nfev + off : nullptr, io->terms ? io->terms + off : nullptr);
+            if (rc) return rc;
+        }
+        return 0;
+    }
+
+    // host pointers: stage through context-owned device buffers, synchronous
+    if (model_ids)
+        for (int b = 0; b < B; ++b)
+            if (model_ids[b] < 0 || model_ids[b] >= n_models) return fail(ctx, MISTI_E_ARG, "misti_eval_batch: unknown model id");
+    for (long off = 0; off < B; off += kMaxChunk) {
+        const int n = (int)((B - off) < kMaxChunk ? (B - off) : kMaxChunk);
+        if ((size_t)n > ctx->st_cap || (size_t)R > ctx->st_capR || (size_t)Pe > ctx->st_capP || numT_max > ctx->st_numT) {
+            size_t ncap = ctx->st_cap ? ctx->st_cap : 1024;
+            while (ncap < (size_t)n) ncap *= 2;
+            const size_t nR = (size_t)R > ctx->st_capR ? (size_t)R : ctx->st_capR;
+            const size_t nP = (size_t)Pe > ctx->st_capP ? (size_t)Pe : ctx->st_capP;
+            if ((rc = realloc_exact(ctx, &ctx->s_params, ncap * nP))) return rc;
+            if ((rc = realloc_exact(ctx, &ctx->s_llh, ncap * nR))) return rc;
+            if ((rc = realloc_exact(ctx, &ctx->s_jafs, ncap * 7))) return rc;
+            if ((rc = realloc_exact(ctx, &ctx->s_jafs_raw, ncap * 7))) return rc;
+            if ((rc = realloc_exact(ctx, &ctx->s_model_ids, ncap))) return rc;
+            if ((rc = realloc_exact(ctx, &ctx->s_terms, ncap))) return rc;
+            ctx->st_cap = ncap; ctx->st_capR = nR; ctx->st_capP = nP; ctx->st_numT = numT_max;
+        }
+        const bool need_lc_io = io->lc_inject || io->lc_out;
+        if (need_lc_io && (rc = ensure(ctx, &ctx->s_lc_io, &ctx->s_lc_io_cap, (size_t)n * 2 * numT_max))) return rc;
+        if (io->pr_out && (rc = ensure(ctx, &ctx->s_pr, &ctx->s_pr_cap, (size_t)n * (numT_max + 1) * 6))) return rc;
+        if (P > 0)
+            CK(cudaMemcpyAsync(ctx->s_params, params + off * P, (size_t)n * P * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        if (model_ids)
+            CK(cudaMemcpyAsync(ctx->s_model_ids, model_ids + off, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        if (io->lc_inject)
+            CK(cudaMemcpyAsync(ctx->s_lc_io, io->lc_inject + off * 2 * numT_max, (size_t)n * 2 * numT_max * sizeof(double),
+                               cudaMemcpyHostToDevice, ctx->stream));
+        if (io->pr_out) CK(cudaMemsetAsync(ctx->s_pr, 0, (size_t)n * (numT_max + 1) * 6 * sizeof(double), ctx->stream));
+        // lc_inject and lc_out share one staging buffer: the inject copy is consumed by K1 before the gather writes
+        rc = eval_chunk(ctx, n, P, ctx->s_params, model_ids ? ctx->s_model_ids : nullptr, model_default, flags, mixture_th,
+                        io->lc_inject ? ctx->s_lc_io : nullptr, ctx->s_llh, ctx->s_jafs, ctx->s_jafs_raw,
+                        io->lc_out ? ctx->s_lc_io : nullptr, io->pr_out ? ctx->s_pr : nullptr, nullptr, nullptr, ctx->s_terms);
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(llh + off * R, ctx->s_llh, (size_t)n * R * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        if (io->jafs) CK(cudaMemcpyAsync(io->jafs + off * 7, ctx->s_jafs, (size_t)n * 7 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        if (io->jafs_raw)
+            CK(cudaMemcpyAsync(io->jafs_raw + off * 7, ctx->s_jafs_raw, (size_t)n * 7 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        if (io->lc_out)
+            CK(cudaMemcpyAsync(io->lc_out + off * 2 * numT_max, ctx->s_lc_io, (size_t)n * 2 * numT_max * sizeof(double),
+                               cudaMemcpyDeviceToHost, ctx->stream));
+        if (io->pr_out)
+            CK(cudaMemcpyAsync(io->pr_out + off * (numT_max + 1) * 6, ctx->s_pr, (size_t)n * (numT_max + 1) * 6 * sizeof(double),
+                               cudaMemcpyDeviceToHost, ctx->stream));
+        if (io->status) CK(cudaMemcpyAsync(io->status + off, ctx->d_status, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        if (io->nfev) CK(cudaMemcpyAsync(io->nfev + off, ctx->d_nfev, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        if (io->terms) CK(cudaMemcpyAsync(io->terms + off, ctx->s_terms, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    return 0;
+}
+
+int misti_score_spectra(misti_ctx* ctx, int32_t B, const double* spectra, double* llh) {
+    if (!ctx) return MISTI_E_ARG;
+    if (B < 0 || !spectra || !llh) return fail(ctx, MISTI_E_ARG, "misti_score_spectra: bad arguments");
+    if (ctx->R < 1) return fail(ctx, MISTI_E_ARG, "misti_score_spectra: no data rows (misti_set_data)");
+    if (B == 0) return 0;
+    CK(cudaSetDevice(ctx->device));
+    double *d_sp = nullptr, *d_out = nullptr;
+    CK(cudaMalloc((void**)&d_sp, (size_t)B * 7 * sizeof(double)));
+    cudaError_t e = cudaMalloc((void**)&d_out, (size_t)B * ctx->R * sizeof(double));
+    if (e != cudaSuccess) { cudaFree(d_sp); return fail(ctx, MISTI_E_CUDA, cudaGetErrorString(e)); }
+    e = cudaMemcpyAsync(d_sp, spectra, (size_t)B * 7 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) {
+        misti_score_kernel<<<(B + 3) / 4, 128, 0, ctx->stream>>>(B, d_sp, ctx->d_data, ctx->R, ctx->unfolded, d_out);
+        e = cudaGetLastError();
+        ctx->launches += 1;
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(llh, d_out, (size_t)B * ctx->R * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_sp);
+    cudaFree(d_out);
+    if (e != cudaSuccess) return fail(ctx, MISTI_E_CUDA, std::string("misti_score_spectra: ") + cudaGetErrorString(e));
+    return 0;
+}
+
+int misti_last_kernel_ms(misti_ctx* ctx, float* out2) {
+    if (!ctx || !out2) return MISTI_E_ARG;
+    if (!ctx->ev_valid) return fail(ctx, MISTI_E_ARG, "misti_last_kernel_ms: no evaluation recorded");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaEventSynchronize(ctx->ev[2]));
+    CK(cudaEventElapsedTime(&out2[0], ctx->ev[0], ctx->ev[1]));
+    CK(cudaEventElapsedTime(&out2[1], ctx->ev[1], ctx->ev[2]));
+    return 0;
+}
+
+int64_t misti_launch_count(const misti_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int misti_generator(misti_ctx* ctx, int32_t which, double l1, double l2, double m1, double m2, double* out) {
+    if (!ctx || !out || (which != 0 && which != 1)) return MISTI_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    const int n = which == 1 ? 8 : 44;
+    misti_generator_kernel<<<1, 64, 0, ctx->stream>>>(which, l1, l2, m1, m2, ctx->d_small);
+    CK(cudaGetLastError());
+    ctx->launches += 1;
+    CK(cudaMemcpyAsync(out, ctx->d_small, (size_t)n * n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int misti_pulse(misti_ctx* ctx, const double* P0, double rate, int32_t src_pop, double* P1) {
+    if (!ctx || !P0 || !P1 || (src_pop != 0 && src_pop != 1)) return MISTI_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(ctx->d_small, P0, 44 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    misti_pulse_kernel<<<1, 64, 0, ctx->stream>>>(ctx->d_small, rate, src_pop, ctx->d_small + 44);
+    CK(cudaGetLastError());
+    ctx->launches += 1;
+    CK(cudaMemcpyAsync(P1, ctx->d_small + 44, 44 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int misti_ancient_reset(misti_ctx* ctx, const double* P0, double* P1) {
+    if (!ctx || !P0 || !P1) return MISTI_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(ctx->d_small, P0, 44 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    misti_ancient_kernel<<<1, 64, 0, ctx->stream>>>(ctx->d_small, ctx->d_small + 44);
+    CK(cudaGetLastError());
+    ctx->launches += 1;
+    CK(cudaMemcpyAsync(P1, ctx->d_small + 44, 44 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int misti_state_to_jaf(misti_ctx* ctx, int32_t which, int32_t* out) {
+    if (!ctx || !out || (which != 0 && which != 1)) return MISTI_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    const int n = which == 1 ? 8 : 44;
+    misti_state_to_jaf_kernel<<<1, 64, 0, ctx->stream>>>(which, (int*)ctx->d_small);
+    CK(cudaGetLastError());
+    ctx->launches += 1;
+    CK(cudaMemcpyAsync(out, ctx->d_small, (size_t)n * 7 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+}  // extern "C"

@@ -167,14 +167,13 @@ MISTI_HD inline void mat3_expm(const double* Ain, double* E) {
 // ------------------------------------------------------------------------------------------
 template <int N, int MR>
 MISTI_HD inline void thin_svd(const double* B, int m, const double* f, double* s, double* V, double* uf) {
-    if (N == 1) {
+    if constexpr (N == 1) {
         double n2 = 0, d = 0;
         for (int r = 0; r < m; ++r) { n2 += B[r] * B[r]; d += B[r] * f[r]; }
         s[0] = sqrt(n2);
         V[0] = 1.0;
         uf[0] = s[0] > 0 ? d / s[0] : 0.0;
-        return;
-    }
+    } else {
     double c1[MR], c2[MR];
     for (int r = 0; r < m; ++r) { c1[r] = B[r]; c2[r] = B[MR + r]; }
     double v00 = 1, v01 = 0, v10 = 0, v11 = 1;  // V columns: (v00,v10) and (v01,v11)
@@ -205,6 +204,7 @@ MISTI_HD inline void thin_svd(const double* B, int m, const double* f, double* s
         s[0] = n2; s[1] = n1;
         V[0] = v01; V[2] = v11; V[1] = v00; V[3] = v10;
         uf[0] = n2 > 0 ? d2 / n2 : 0.0; uf[1] = n1 > 0 ? d1 / n1 : 0.0;
+    }
     }
 }
 

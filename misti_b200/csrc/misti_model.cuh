@@ -6,22 +6,7 @@
 #pragma once
 #include "misti_math.cuh"
 
-#define MISTI_MAX_BANDS 8
-#define MISTI_MAX_PULSES 8
-#define MISTI_MAX_PARAMS 16
-
-// evaluation flags (bit field), same meaning as the MigrationInference keyword arguments
-#define MISTI_FLAG_CORRECT 1u   // not trueEPS
-#define MISTI_FLAG_CPFIT 2u
-#define MISTI_FLAG_SMOOTH 4u
-#define MISTI_FLAG_UNFOLDED 8u
-
-// per-item status codes
-#define MISTI_OK 0
-#define MISTI_NEGATIVE_PARAM 1      // "Hit negative value of migration rate"  -> llh = -inf
-#define MISTI_CORRECTION_FAILED 2   // "Lambda correction failed"               -> llh = -inf
-#define MISTI_NONFINITE 3           // the reference would have raised / produced NaN
-#define MISTI_INFINITE_COAL_TIME 4  // last interval before the split without migration (reference exits)
+#include "../../include/misti_b200.h"  // flags, status codes and capacity limits are part of the C ABI
 
 namespace misti {
 
