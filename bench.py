@@ -134,27 +134,29 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.QUERY,
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append([time.monotonic()] + [c.strip() for c in line.split(",")])
 
-    def stop(self):
+    def stop(self, t0, t1):
+        """median SM clock over the samples taken inside [t0, t1] (the timed regions)"""
         if self.proc is not None:
             self.proc.terminate()
             try:
                 self.proc.wait(timeout=5)
             except Exception:
                 pass
-        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        rows = [r[1:] for r in self.rows if t0 <= r[0] <= t1 + 0.05]
+        sm = [float(r[1]) for r in rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
         reasons = set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in rows:
             if len(r) >= 9:
                 for name, v in zip(names, r[5:9]):
                     if v.lower().startswith("active"):
@@ -177,7 +179,8 @@ def run_gpu(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    stream = torch.cuda.current_stream(dev)
+    stream = torch.cuda.Stream(dev)  # a real (non-NULL) stream shared by torch events and the engine's launches
+    torch.cuda.set_stream(stream)
     eng = misti_b200.Engine(local, stream=stream.cuda_stream)
 
     ds = load_dataset()
@@ -206,17 +209,18 @@ def run_gpu(args):
                             status_ptr=status_d.data_ptr(), terms_ptr=terms_d.data_ptr())
 
     # ---- device-resident throughput -----------------------------------------------------------
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     for _ in range(args.warmup):
         flush.zero_()
         step_device()
     barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     launches0 = eng.launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     k1_ms, k2_ms = [], []
     barrier()
+    t_load0 = time.monotonic()
     for s in range(args.steps):
         flush.zero_()  # L2 flush between timed iterations (outside the per-step events)
         ev[s][0].record(stream)
@@ -245,7 +249,7 @@ def run_gpu(args):
         ee[s][1].record(stream)
     barrier()
     e2e_ms = sum(e0.elapsed_time(e1) for e0, e1 in ee)
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_load0, time.monotonic()) if rank == 0 else None
 
     ok_frac = float((status_d == 0).float().mean().item())
     terms_mean = float(terms_d.double().mean().item())
@@ -284,7 +288,7 @@ def run_gpu(args):
     cpu = None
     if world == 1:
         cores = os.cpu_count() or 1
-        n = 8 * cores
+        n = 128 * cores
         rate, dt = cpu_rate(n, cores)
         cpu = {"value": rate, "unit": "evals/s", "cores": cores, "kind": "port",
                "sample": "%d of the batch's parameter vectors through oracle/misti_oracle.py (numpy/scipy port of the reference "
@@ -305,7 +309,7 @@ def run_gpu(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=65536, help="parameter vectors per GPU per step")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
