@@ -286,7 +286,7 @@ def run_gpu(args):
                                "%.1f TFLOP/s; MEASURED_PEAKS.json has no FP64 entry)" % (peaks["dfma_tflops"], peaks["dmma_tflops"],
                                                                                           peaks["cublas_dgemm_tflops"])}
     cpu = None
-    if world == 1:
+    if world == 1 and not args.skip_cpu:
         cores = os.cpu_count() or 1
         n = 128 * cores
         rate, dt = cpu_rate(n, cores)
@@ -313,6 +313,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=65536, help="parameter vectors per GPU per step")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--skip-cpu", action="store_true", help="omit the cpu_baseline leg (profiling runs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -47,6 +47,8 @@ extern "C" {
 #define MISTI_CORRECTION_FAILED 2  /* "Lambda correction failed" (MigrationInference.py:575-578)              */
 #define MISTI_NONFINITE 3          /* the reference would have raised or produced NaN                         */
 #define MISTI_INFINITE_COAL_TIME 4 /* last interval before the split without migration (:475-476, ref. exits)  */
+#define MISTI_STIFF 5              /* an interval with rate*length > 131072 (only seen after a run-away correction);
+                                      llh = NaN instead of spending seconds on one item                          */
 
 #define MISTI_MAX_BANDS 8
 #define MISTI_MAX_PULSES 8

@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(HERE, "libmisti_b200.so")
 MAX_BANDS, MAX_PULSES, MAX_PARAMS = 8, 8, 16
 
 FLAG_CORRECT, FLAG_CPFIT, FLAG_SMOOTH, FLAG_UNFOLDED, FLAG_DEVICE_PTRS = 1, 2, 4, 8, 256
-OK, NEGATIVE_PARAM, CORRECTION_FAILED, NONFINITE, INFINITE_COAL_TIME = 0, 1, 2, 3, 4
+OK, NEGATIVE_PARAM, CORRECTION_FAILED, NONFINITE, INFINITE_COAL_TIME, STIFF = 0, 1, 2, 3, 4, 5
 E_ARG, E_CUDA, E_NODEV = -1, -2, -3
 
 c_double_p = ctypes.POINTER(ctypes.c_double)

@@ -55,32 +55,63 @@ MISTI_DEFINE_TABLES(static const, h_)
 #endif
 
 // ---- lane groups ------------------------------------------------------------------------------
+// A group = the lanes that share one item.  Several groups may share a warp; they then run in LOCK
+// STEP: every loop bound and branch in jsfs_item is made warp-uniform with wmax / any / all, and a
+// group that has nothing left to do keeps executing on a zero-length interval (an exact no-op).
 struct SingleLane {  // test-only host build: one lane owns all 44 rows
     static constexpr int LANES = 1;
     MISTI_HD int lane() const { return 0; }
     MISTI_HD void sync() const {}
     MISTI_HD double max(double v) const { return v; }
     MISTI_HD double sum(double v) const { return v; }
+    MISTI_HD int wmax(int v) const { return v; }
+    MISTI_HD bool any(bool v) const { return v; }
+    MISTI_HD bool all(bool v) const { return v; }
 };
 
 #if defined(__CUDACC__)
-struct WarpLanes {  // one warp per item: lane l owns rows l and l + 32
-    static constexpr int LANES = 32;
-    __device__ int lane() const { return threadIdx.x & 31; }
+struct HalfWarpLanes {  // two items per warp: lane l of each 16-lane half owns rows l, l + 16, l + 32
+    static constexpr int LANES = 16;
+    __device__ int lane() const { return threadIdx.x & 15; }
     __device__ void sync() const { __syncwarp(); }
-    __device__ double max(double v) const {
-        for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    __device__ double max(double v) const {  // within the half
+        for (int o = 8; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
         return v;
     }
-    __device__ double sum(double v) const {
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __device__ double sum(double v) const {  // within the half
+        for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
         return v;
+    }
+    __device__ int wmax(int v) const {  // over the whole warp (both items); v is uniform within a half
+        const int o = __shfl_xor_sync(0xffffffffu, v, 16);
+        return v > o ? v : o;
+    }
+    __device__ bool any(bool v) const { return __any_sync(0xffffffffu, v); }
+    __device__ bool all(bool v) const { return __all_sync(0xffffffffu, v); }
+};
+#endif
+
+// 1/k for the Poisson weight recursion p_k = p_(k-1) * lam / k (a table lookup instead of a division per term)
+#define MISTI_RECIP_N 512
+struct RecipTable {
+    double v[MISTI_RECIP_N];
+    constexpr RecipTable() : v() {
+        v[0] = 0.0;
+        for (int k = 1; k < MISTI_RECIP_N; ++k) v[k] = 1.0 / k;
     }
 };
+#if defined(__CUDACC__)
+static __constant__ RecipTable c_recip = RecipTable();
+#define MISTI_RECIP(k) c_recip.v[k]
+#else
+static const RecipTable h_recip = RecipTable();
+#define MISTI_RECIP(k) h_recip.v[k]
 #endif
 
 constexpr double kUnifMaxStep = 32.0;           // largest q*T handled in one uniformisation sweep
 constexpr double kUnifTol = 1.3877787807814457e-17;  // 2^-56: truncation of the Poisson tail
+constexpr double kUnifMaxStiff = 131072.0;       // q*T beyond this is reported as MISTI_STIFF (4096 sweeps)
+constexpr int kUnifMaxTerms = MISTI_RECIP_N - 4;     // never reached for q*T <= 32 (about 110 terms)
 
 // Post-split coefficients (run by ONE thread; lc addressed like in correct_lambdas_item):
 //   cpost[k] = sum_{i>=splitT} exp(-a_k x_i) (1 - exp(-a_k lam_i T_i)) / (a_k lam_i),  x_i = sum_{j<i} lam_j T_j,
@@ -109,232 +140,320 @@ MISTI_HD inline void post_split_coeffs(const ModelDesc& md, const double* times,
     cpost[0] = c6; cpost[1] = c3; cpost[2] = c1;
 }
 
-// Expected JSFS of one item.  All lanes of the group call this together; `ysm` is a scratch area of
-// 2*44 doubles shared by the group.  On return every lane holds the UNNORMALISED spectrum in
-// jafs[0..6] (MigrationInference.JAFSpectrum's return value) and the number of mat-vecs in *terms.
+// Expected JSFS of one item.  ALL lanes of the warp call this together (each group with its own item;
+// `active` = false for a group without work); `ysm` is a scratch area of 2*44 doubles private to the
+// group.  On return every lane of the group holds the UNNORMALISED spectrum in jafs[0..6]
+// (MigrationInference.JAFSpectrum's return value) and the number of mat-vecs in *terms.
 template <class G>
-MISTI_D inline int jsfs_item(const G& g, const ModelDesc& md, const double* times, const double* params, const double* lc,
-                              long stride, const double* cpost, double* ysm, double* jafs, int* terms) {
+MISTI_D inline int jsfs_item(const G& g, const ModelDesc& md, bool active, const double* times, const double* params,
+                             const double* lc, long stride, const double* cpost, double* ysm, double* jafs, int* terms) {
     constexpr int RPL = (44 + G::LANES - 1) / G::LANES;
+    constexpr int W = MISTI_ELL_WIDTH;
     const int lane = g.lane();
-    int row[RPL];
     bool valid[RPL];
-    unsigned code[RPL][MISTI_ELL_WIDTH];  // col | kind << 8 | cnt << 16
-    unsigned dcode[RPL];                  // diagonal multiplicities, 8 bits per rate kind
-    unsigned wcode[RPL];                  // W44 column, 2 bits per SFS category
-    double P[RPL];
-    double jl[7];
-    for (int c = 0; c < 7; ++c) jl[c] = 0.0;
+    // per row, packed: ELL slot e -> kind (2 bits) | count (3 bits) at bit 5e; diagonal multiplicity of rate kind k at bit 20+3k
+    unsigned rc[RPL];
+    const double* yp[RPL][W];  // where this lane reads y[col] for each ELL slot (buffer 0; buffer 1 is +44)
+    double* const wb = ysm + lane;  // this lane writes y[row] at wb[s * LANES] (+44 for buffer 1)
+    double P[RPL];            // state probabilities at the start of the current interval (rows owned by this lane)
+    double Ia[RPL], Ib[RPL];  // occupancy integrals summed over the intervals before / from the sampling date
 #pragma unroll
     for (int s = 0; s < RPL; ++s) {
         const int r = lane + s * G::LANES;
         valid[s] = r < 44;
-        row[s] = valid[s] ? r : 0;
-        dcode[s] = 0; wcode[s] = 0;
-        for (int e = 0; e < MISTI_ELL_WIDTH; ++e) {
-            const EllEntry en = MISTI_TAB(ell)[row[s]][e];
-            code[s][e] = valid[s] ? (en.col | (en.kind << 8) | (en.cnt << 16)) : 0u;
+        const int rr = valid[s] ? r : 0;
+        rc[s] = 0;
+#pragma unroll
+        for (int e = 0; e < W; ++e) {
+            const EllEntry en = MISTI_TAB(ell)[rr][e];
+            if (valid[s]) rc[s] |= ((unsigned)en.kind | ((unsigned)en.cnt << 2)) << (5 * e);
+            yp[s][e] = ysm + (valid[s] ? en.col : 0);
         }
-        if (valid[s]) {
-            for (int k = 0; k < 4; ++k) dcode[s] |= (unsigned)MISTI_TAB(diag)[r][k] << (8 * k);
-            for (int c = 0; c < 7; ++c) wcode[s] |= (unsigned)MISTI_TAB(w44)[c][r] << (2 * c);
-        }
+        if (valid[s])
+            for (int k = 0; k < 4; ++k) rc[s] |= (unsigned)MISTI_TAB(diag)[r][k] << (20 + 3 * k);
         P[s] = (valid[s] && r == 2) ? 1.0 : 0.0;  // both genome-1 lineages in deme 0, genome-2 in deme 1 (:469-471)
+        Ia[s] = 0.0; Ib[s] = 0.0;
     }
     int nterms = 0;
     int status = MISTI_OK;
     const int numT = md.numT;
-    const int n2 = md.splitT < numT ? md.splitT : numT;  // number of two-population intervals
-    for (int it = 0; it < n2; ++it) {
-        if (it == md.sampleDate && it > 0) {  // AncientSampleP0 (TwoPopulations.py:246-262); identity on the start vector
+    const int n2 = !active ? 0 : (md.splitT < numT ? md.splitT : numT);  // two-population intervals of this item
+    const bool inf_last = active && md.splitT >= numT;                    // ... the last of which is then infinite
+    const int n_fin = inf_last ? n2 - 1 : n2;
+    const bool has_pulses = md.n_pulses > 0;
+
+    // AncientSampleP0 (TwoPopulations.py:246-262) at it == sampleDate, then PulseMigration (:361-377)
+    auto reset_and_pulse = [&](int it, bool act) {
+        const bool do_reset = act && it == md.sampleDate && it > 0;  // identity on the start vector
+        if (g.any(do_reset)) {
             double a2 = 0.0, a11 = 0.0;
 #pragma unroll
             for (int s = 0; s < RPL; ++s)
                 if (valid[s]) {
-                    if (MISTI_TAB(anc2)[row[s]]) a2 += P[s];
-                    if (MISTI_TAB(anc11)[row[s]]) a11 += P[s];
+                    if (MISTI_TAB(anc2)[lane + s * G::LANES]) a2 += P[s];
+                    if (MISTI_TAB(anc11)[lane + s * G::LANES]) a11 += P[s];
                 }
             a2 = g.sum(a2); a11 = g.sum(a11);
+            if (do_reset) {
 #pragma unroll
-            for (int s = 0; s < RPL; ++s) P[s] = !valid[s] ? 0.0 : (row[s] == 2 ? a2 : (row[s] == 11 ? a11 : 0.0));
+                for (int s = 0; s < RPL; ++s) {
+                    const int r = lane + s * G::LANES;
+                    P[s] = r == 2 ? a2 : (r == 11 ? a11 : 0.0);
+                }
+            }
         }
-        const double pu0 = pulse_rate(md, params, it, 0), pu1 = pulse_rate(md, params, it, 1);
-        if (pu0 + pu1 > 0) {  // PulseMigration (TwoPopulations.py:361-377)
-            const double r = pu0 + pu1, om = 1.0 - r;
-            const int src = pu0 > 0 ? 0 : 1;
+        double pr = 0.0;
+        int src = 0;
+        if (has_pulses && act) {
+            const double pu0 = pulse_rate(md, params, it, 0), pu1 = pulse_rate(md, params, it, 1);
+            pr = pu0 + pu1;
+            src = pu0 > 0 ? 0 : 1;
+        }
+        if (g.any(pr > 0)) {  // a group without a pulse here applies the map with rate 0 = the identity
+            const double om = 1.0 - pr;
             const PulseEntry* ent = src == 0 ? MISTI_TAB(pulse0) : MISTI_TAB(pulse1);
             const unsigned char* rp = src == 0 ? MISTI_TAB(pulse0_rowptr) : MISTI_TAB(pulse1_rowptr);
             g.sync();
 #pragma unroll
             for (int s = 0; s < RPL; ++s)
-                if (valid[s]) ysm[row[s]] = P[s];
+                if (valid[s]) wb[s * G::LANES] = P[s];
             g.sync();
             double pw_om[5], pw_r[5];
             pw_om[0] = 1.0; pw_r[0] = 1.0;
-            for (int k = 1; k < 5; ++k) { pw_om[k] = pw_om[k - 1] * om; pw_r[k] = pw_r[k - 1] * r; }
+            for (int k = 1; k < 5; ++k) { pw_om[k] = pw_om[k - 1] * om; pw_r[k] = pw_r[k - 1] * pr; }
 #pragma unroll
             for (int s = 0; s < RPL; ++s) {
                 double acc = 0.0;
-                if (valid[s])
-                    for (int e = rp[row[s]]; e < rp[row[s] + 1]; ++e) {
+                if (valid[s]) {
+                    const int r = lane + s * G::LANES;
+                    for (int e = rp[r]; e < rp[r + 1]; ++e) {
                         const PulseEntry pe = ent[e];
-                        acc += (double)pe.mult * pw_om[pe.a] * pw_r[pe.b] * ysm[pe.col];
+                        double w = (double)pe.mult;
+                        for (int k = 0; k < 5; ++k) {
+                            if (k == pe.a) w *= pw_om[k];
+                            if (k == pe.b) w *= pw_r[k];
+                        }
+                        acc += w * ysm[pe.col];
                     }
+                }
                 P[s] = acc;
             }
             g.sync();
         }
-        const double la0 = lc[(2 * it) * stride], la1 = lc[(2 * it + 1) * stride];
-        const double m0 = band_rate(md, params, it, 0), m1 = band_rate(md, params, it, 1);
-        const double rate[4] = {la0, la1, m0, m1};
+    };
+
+    // generator of interval `it` in uniformised form: A = I + M/q with q = max |M_cc| (per group)
+    double adiag[RPL], coef[RPL][W], qinv = 1.0, q = 1.0;
+    bool mig = false;
+    auto set_generator = [&](int it, bool act) {
+        double la0 = 1.0, la1 = 1.0, m0 = 0.0, m1 = 0.0;
+        if (act) {
+            la0 = lc[(2 * it) * stride]; la1 = lc[(2 * it + 1) * stride];
+            m0 = band_rate(md, params, it, 0); m1 = band_rate(md, params, it, 1);
+            if (!(la0 >= 0.0 && la0 <= DBL_MAX && la1 >= 0.0 && la1 <= DBL_MAX && m0 >= 0.0 && m0 <= DBL_MAX && m1 >= 0.0 &&
+                  m1 <= DBL_MAX)) {
+                status = MISTI_NONFINITE;
+                la0 = la1 = 1.0; m0 = m1 = 0.0;
+            }
+        }
+        mig = m0 + m1 != 0.0;
         double d[RPL], dmax = 0.0;
 #pragma unroll
         for (int s = 0; s < RPL; ++s) {
-            d[s] = (double)(dcode[s] & 255u) * la0 + (double)((dcode[s] >> 8) & 255u) * la1 +
-                   (double)((dcode[s] >> 16) & 255u) * m0 + (double)((dcode[s] >> 24) & 255u) * m1;
+            d[s] = (double)((rc[s] >> 20) & 7u) * la0 + (double)((rc[s] >> 23) & 7u) * la1 +
+                   (double)((rc[s] >> 26) & 7u) * m0 + (double)((rc[s] >> 29) & 7u) * m1;
             dmax = d[s] > dmax ? d[s] : dmax;
         }
-        const double q = g.max(dmax);
-        if (!(q > 0.0) || !(q <= DBL_MAX)) { status = MISTI_NONFINITE; break; }
-        const double qinv = 1.0 / q;
-        double adiag[RPL], coef[RPL][MISTI_ELL_WIDTH];
+        q = g.max(dmax);
+        if (!(q > 0.0)) q = 1.0;  // no event possible at all: A = I
+        qinv = 1.0 / q;
+        const double rq0 = la0 * qinv, rq1 = la1 * qinv, rq2 = m0 * qinv, rq3 = m1 * qinv;
 #pragma unroll
         for (int s = 0; s < RPL; ++s) {
             adiag[s] = (q - d[s]) * qinv;
 #pragma unroll
-            for (int e = 0; e < MISTI_ELL_WIDTH; ++e)
-                coef[s][e] = (double)(code[s][e] >> 16) * rate[(code[s][e] >> 8) & 3u] * qinv;
-        }
-        double Iacc[RPL];
-#pragma unroll
-        for (int s = 0; s < RPL; ++s) Iacc[s] = 0.0;
-        const bool last = it == numT - 1;
-        if (!last) {
-            const double qT = q * times[it];
-            int nsub = 1;
-            if (qT > kUnifMaxStep) nsub = (int)ceil(qT / kUnifMaxStep);
-            const double lam = qT / nsub;
-            const double p0 = exp(-lam);
-            for (int sub = 0; sub < nsub; ++sub) {
-                double yk[RPL], S[RPL], P1[RPL], I[RPL];
-                int cur = 0;
-                g.sync();
-#pragma unroll
-                for (int s = 0; s < RPL; ++s) {
-                    yk[s] = P[s]; S[s] = 0.0; P1[s] = p0 * P[s]; I[s] = 0.0;
-                    if (valid[s]) ysm[row[s]] = P[s];
-                }
-                double p = p0;
-                int k = 0;
-                while (true) {
-                    g.sync();
-                    const double* yr = ysm + 44 * cur;
-                    double* yw = ysm + 44 * (cur ^ 1);
-                    ++k;
-                    p *= lam / k;
-#pragma unroll
-                    for (int s = 0; s < RPL; ++s) {
-                        double acc = adiag[s] * yk[s];
-#pragma unroll
-                        for (int e = 0; e < MISTI_ELL_WIDTH; ++e) acc += coef[s][e] * yr[code[s][e] & 255u];
-                        S[s] += yk[s];
-                        yk[s] = acc;
-                        if (valid[s]) yw[row[s]] = acc;
-                        P1[s] += p * acc;
-                        I[s] += p * S[s];
-                    }
-                    cur ^= 1;
-                    if (k + 1 > lam && p * (k + 1) < kUnifTol * (k + 1 - lam)) break;
-                    if (k > 4096) { status = MISTI_NONFINITE; break; }
-                }
-                nterms += k;
-#pragma unroll
-                for (int s = 0; s < RPL; ++s) { P[s] = P1[s]; Iacc[s] += I[s]; }
-                if (status != MISTI_OK) break;
+            for (int e = 0; e < W; ++e) {
+                const unsigned ke = rc[s] >> (5 * e);
+                const unsigned kind = ke & 3u;
+                const double rk = kind == 0 ? rq0 : (kind == 1 ? rq1 : (kind == 2 ? rq2 : rq3));
+                coef[s][e] = (double)((ke >> 2) & 7u) * rk;
             }
+        }
+    };
+
+    const int n_loop = g.wmax(n_fin);
+    for (int it = 0; it < n_loop; ++it) {
+        const bool act = it < n_fin;  // a group past its own last interval idles on a zero-length interval
+        reset_and_pulse(it, act);
+        set_generator(it, act);
+        double T = act ? times[it] : 0.0;
+        if (!(T >= 0.0 && T <= DBL_MAX)) { status = MISTI_NONFINITE; T = 0.0; }
+        // rates of 1e5 and more per unit of interval length only come out of a run-away correction; the
+        // sweep count is bounded rather than letting one item stall its warp for seconds
+        if (q * T > kUnifMaxStiff) { status = MISTI_STIFF; T = 0.0; }
+        const double qT = q * T;
+        const int nsub = g.wmax(qT > kUnifMaxStep ? (int)ceil(qT / kUnifMaxStep) : 1);
+        const double lam = qT / nsub;
+        const double p0 = exp(-lam);
+        double Iint[RPL];
 #pragma unroll
-            for (int s = 0; s < RPL; ++s) Iacc[s] *= qinv;
-        } else {
-            // infinite last interval before any split (MigrationInference.py:475-476, 535-538):
-            // integralP = -inv(M) P0 = (1/q) sum_k A^k P0; needs migration to be finite.
-            if (m0 + m1 == 0.0) { status = MISTI_INFINITE_COAL_TIME; break; }
-            double yk[RPL];
-            int cur = 0;
+        for (int s = 0; s < RPL; ++s) Iint[s] = 0.0;
+        for (int sub = 0; sub < nsub; ++sub) {
+            double yk[RPL], S[RPL], P1[RPL];
             g.sync();
 #pragma unroll
             for (int s = 0; s < RPL; ++s) {
-                yk[s] = P[s];
-                Iacc[s] = P[s];
-                if (valid[s]) ysm[row[s]] = P[s];
+                yk[s] = P[s]; S[s] = 0.0; P1[s] = p0 * P[s];
+                if (valid[s]) wb[s * G::LANES] = P[s];
             }
-            double nprev = 0.0, itot = 0.0;
-#pragma unroll
-            for (int s = 0; s < RPL; ++s) nprev += yk[s];
-            nprev = g.sum(nprev);
-            itot = nprev;
+            double p = p0;
+            double r = lam;  // lam / (k + 1): ratio of consecutive Poisson weights
             int k = 0;
-            while (nprev > 0.0) {
+            // one term: y <- A y (read buffer RO, write buffer WO), S += y_old, P1 += p y, I += p S.
+            // Returns true when this group's Poisson tail beyond the term is below kUnifTol.
+            auto term = [&](const int RO, const int WO) -> bool {
                 g.sync();
-                const double* yr = ysm + 44 * cur;
-                double* yw = ysm + 44 * (cur ^ 1);
-                double nk = 0.0;
+                ++k;
+                p *= r;
+                r = lam * MISTI_RECIP(k + 1);
 #pragma unroll
                 for (int s = 0; s < RPL; ++s) {
-                    double acc = adiag[s] * yk[s];
-#pragma unroll
-                    for (int e = 0; e < MISTI_ELL_WIDTH; ++e) acc += coef[s][e] * yr[code[s][e] & 255u];
+                    // two short FMA chains per row instead of one long one
+                    const double u = fma(coef[s][1], yp[s][1][RO], fma(coef[s][0], yp[s][0][RO], adiag[s] * yk[s]));
+                    const double v = fma(coef[s][3], yp[s][3][RO], coef[s][2] * yp[s][2][RO]);
+                    const double acc = u + v;
+                    S[s] += yk[s];
                     yk[s] = acc;
-                    if (valid[s]) yw[row[s]] = acc;
-                    Iacc[s] += acc;
-                    nk += acc;
+                    if (valid[s]) wb[WO + s * G::LANES] = acc;
+                    P1[s] = fma(p, acc, P1[s]);
+                    Iint[s] = fma(p, S[s], Iint[s]);
                 }
-                cur ^= 1;
-                ++k;
-                nk = g.sum(nk);
-                itot += nk;
-                const double rho = nk / nprev;  // contraction of the remaining mass
-                nprev = nk;
-                if (rho < 1.0 && nk * rho < kUnifTol * itot * (1.0 - rho)) break;
-                if (k > 2000000) { status = MISTI_NONFINITE; break; }
+                return r < 1.0 && p < kUnifTol * (1.0 - r);
+            };
+            while (true) {  // the two halves of the ping-pong buffer get compile-time offsets
+                if (g.all(term(0, 44))) break;
+                if (g.all(term(44, 0))) break;
+                if (k >= kUnifMaxTerms) { status = MISTI_NONFINITE; break; }
             }
-            nterms += k;
+            if (act) nterms += k;
 #pragma unroll
-            for (int s = 0; s < RPL; ++s) { Iacc[s] *= qinv; P[s] = 0.0; }
-            if (status != MISTI_OK) break;
+            for (int s = 0; s < RPL; ++s) P[s] = P1[s];
         }
-        // JAFS += StateToJAF . integralP; categories 2..6 are muted before the sampling date (:501-506)
-        const int cmax = it < md.sampleDate ? 2 : 7;
+        // integralP of this interval joins the running sums; categories 2..6 are muted before the sampling
+        // date (:501-506), hence the two accumulators
+        if (it < md.sampleDate) {
 #pragma unroll
-        for (int s = 0; s < RPL; ++s)
+            for (int s = 0; s < RPL; ++s) Ia[s] = fma(Iint[s], qinv, Ia[s]);
+        } else {
 #pragma unroll
-            for (int c = 0; c < 7; ++c)
-                if (c < cmax) jl[c] += (double)((wcode[s] >> (2 * c)) & 3u) * Iacc[s];
+            for (int s = 0; s < RPL; ++s) Ib[s] = fma(Iint[s], qinv, Ib[s]);
+        }
     }
-    if (status == MISTI_OK && md.splitT < numT) {
-        if (md.splitT == md.sampleDate && md.splitT > 0) {  // the reset precedes the collapse (:480-494)
+    if (g.any(inf_last)) {
+        // no split inside the grid: the last two-population interval is infinite (MigrationInference.py:475-476,
+        // 535-538): P1 = 0, integralP = -inv(M) P0 = (1/q) sum_k A^k P0, finite only with migration.
+        const int it = numT - 1;
+        reset_and_pulse(it, inf_last);
+        set_generator(it, inf_last);
+        if (inf_last && !mig && status == MISTI_OK) status = MISTI_INFINITE_COAL_TIME;
+        const bool run = inf_last && mig;
+        double yk[RPL], Iint[RPL];
+        g.sync();
+#pragma unroll
+        for (int s = 0; s < RPL; ++s) {
+            yk[s] = run ? P[s] : 0.0;
+            Iint[s] = yk[s];
+            if (valid[s]) wb[s * G::LANES] = yk[s];
+        }
+        double nprev = 0.0;
+#pragma unroll
+        for (int s = 0; s < RPL; ++s) nprev += yk[s];
+        nprev = g.sum(nprev);
+        double itot = nprev;
+        bool done = !(nprev > 0.0);
+        int k = 0, cur = 0;
+        while (!g.all(done)) {
+            g.sync();
+            const int ro = 44 * cur, wo = 44 * (cur ^ 1);
+            double nk = 0.0;
+#pragma unroll
+            for (int s = 0; s < RPL; ++s) {
+                double acc = adiag[s] * yk[s];
+#pragma unroll
+                for (int e = 0; e < W; ++e) acc += coef[s][e] * yp[s][e][ro];
+                yk[s] = acc;
+                if (valid[s]) wb[wo + s * G::LANES] = acc;
+                Iint[s] += acc;
+                nk += acc;
+            }
+            cur ^= 1;
+            ++k;
+            nk = g.sum(nk);
+            itot += nk;
+            const double rho = nprev > 0.0 ? nk / nprev : 0.0;  // contraction of the remaining mass
+            nprev = nk;
+            if (!(nk > 0.0) || (rho < 1.0 && nk * rho < kUnifTol * itot * (1.0 - rho))) done = true;
+            if (k > 2000000) { if (!done) status = MISTI_NONFINITE; break; }
+        }
+        if (run) {
+            nterms += k;
+            const bool pre = it < md.sampleDate;
+#pragma unroll
+            for (int s = 0; s < RPL; ++s) {
+                if (pre) Ia[s] = fma(Iint[s], qinv, Ia[s]);
+                else Ib[s] = fma(Iint[s], qinv, Ib[s]);
+                P[s] = 0.0;
+            }
+        }
+    }
+    // JAFS = StateToJAF . (sum of the interval integrals) (:501-506)
+    double jl[7];
+#pragma unroll
+    for (int c = 0; c < 7; ++c) jl[c] = 0.0;
+#pragma unroll
+    for (int s = 0; s < RPL; ++s)
+        if (valid[s]) {
+#pragma unroll
+            for (int c = 0; c < 7; ++c) {
+                const double w = (double)MISTI_TAB(w44)[c][lane + s * G::LANES];
+                jl[c] += w * (c < 2 ? Ia[s] + Ib[s] : Ib[s]);
+            }
+        }
+    const bool post = active && md.splitT < numT;
+    if (g.any(post)) {
+        const bool do_reset = post && md.splitT == md.sampleDate && md.splitT > 0;  // the reset precedes the collapse (:480-494)
+        if (g.any(do_reset)) {
             double a2 = 0.0, a11 = 0.0;
 #pragma unroll
             for (int s = 0; s < RPL; ++s)
                 if (valid[s]) {
-                    if (MISTI_TAB(anc2)[row[s]]) a2 += P[s];
-                    if (MISTI_TAB(anc11)[row[s]]) a11 += P[s];
+                    if (MISTI_TAB(anc2)[lane + s * G::LANES]) a2 += P[s];
+                    if (MISTI_TAB(anc11)[lane + s * G::LANES]) a11 += P[s];
                 }
             a2 = g.sum(a2); a11 = g.sum(a11);
+            if (do_reset) {
 #pragma unroll
-            for (int s = 0; s < RPL; ++s) P[s] = !valid[s] ? 0.0 : (row[s] == 2 ? a2 : (row[s] == 11 ? a11 : 0.0));
+                for (int s = 0; s < RPL; ++s) {
+                    const int r = lane + s * G::LANES;
+                    P[s] = r == 2 ? a2 : (r == 11 ? a11 : 0.0);
+                }
+            }
         }
         // CollapsePops (:518-528): 44 -> 8 block sums
         double P8[8];
+#pragma unroll
         for (int b = 0; b < 8; ++b) {
             double v = 0.0;
 #pragma unroll
             for (int s = 0; s < RPL; ++s)
-                if (valid[s] && MISTI_TAB(collapse)[row[s]] == b) v += P[s];
+                if (valid[s] && MISTI_TAB(collapse)[lane + s * G::LANES] == b) v += P[s];
             P8[b] = g.sum(v);
         }
-        const double c6 = cpost[0], c3 = cpost[1], c1 = cpost[2];
+        const double c6 = post ? cpost[0] : 0.0, c3 = post ? cpost[1] : 0.0, c1 = post ? cpost[2] : 0.0;
+#pragma unroll
         for (int c = 0; c < 7; ++c) {
             double a6 = 0.0, a3 = 0.0, a1 = 0.0;
+#pragma unroll
             for (int b = 0; b < 8; ++b) {
                 a6 += MISTI_TAB(wg6)[c][b] * P8[b];
                 a3 += MISTI_TAB(wg3)[c][b] * P8[b];
@@ -343,6 +462,7 @@ MISTI_D inline int jsfs_item(const G& g, const ModelDesc& md, const double* time
             jafs[c] = g.sum(jl[c]) + ((c6 * a6 + c3 * a3) + c1 * a1);
         }
     } else {
+#pragma unroll
         for (int c = 0; c < 7; ++c) jafs[c] = g.sum(jl[c]);
     }
     *terms = nterms;

@@ -5,7 +5,7 @@
 //                          sequential coalescence-rate correction chain (CorrectLambdas / CorrectLambda /
 //                          Smooth, incl. an iterate-faithful trust-region-reflective least-squares
 //                          solver), and the post-split closed-form coefficients.
-//   misti_jsfs_kernel      one WARP per item: generator assembly from (lc, mi), uniformised
+//   misti_jsfs_kernel      one HALF WARP per item (3 chain states per lane, two items per warp): generator assembly from (lc, mi), uniformised
 //                          propagation + branch-length integrals on the 44-state chain, pulses,
 //                          ancient-sample reset, collapse, closed-form one-population tail, the
 //                          7x44 / 7x8 JSFS contraction, normalisation, and -- fused -- the multinomial
@@ -15,6 +15,7 @@
 #include <cuda_runtime.h>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -27,7 +28,8 @@ namespace {
 using misti::ModelDesc;
 
 constexpr int kCorrectThreads = 64;
-constexpr int kJsfsWarps = 4;
+constexpr int kJsfsWarps = 4;      // warps per block of the JSFS kernel (8 items per block)
+constexpr int kJsfsMinBlocks = 4;  // occupancy target: caps the kernel at 128 registers per thread
 constexpr int kMaxChunk = 1 << 20;
 
 static __device__ const double d_l8[8][8] = MISTI_L8_INIT;
@@ -70,26 +72,32 @@ misti_correct_kernel(int B, int P, const double* __restrict__ params, const int*
 // ------------------------------------------------------------------------------------------------
 // K2: expected JSFS + composite log-likelihood, one warp per item
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kJsfsWarps * 32)
+template <int MINB>
+__global__ void __launch_bounds__(kJsfsWarps * 32, MINB)
 misti_jsfs_kernel(int B, int P, const double* __restrict__ params, const int* __restrict__ model_ids, int model_default,
                   const ModelDesc* __restrict__ models, const double* __restrict__ times, const double* __restrict__ lc,
                   long stride, const double* __restrict__ cpost, const double* __restrict__ data, int R, int unfolded,
                   double* __restrict__ llh, double* __restrict__ jafs, double* __restrict__ jafs_raw, int* __restrict__ status,
                   int* __restrict__ terms) {
-    __shared__ double ysm_all[kJsfsWarps][88];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    double* ysm = ysm_all[warp];
-    const misti::WarpLanes g;
-    const int nwarps = gridDim.x * kJsfsWarps;
-    for (int b = blockIdx.x * kJsfsWarps + warp; b < B; b += nwarps) {
+    // one item per 16-lane half warp (3 of the 44 chain states per lane), two items per warp
+    __shared__ double ysm_all[kJsfsWarps * 2][88];
+    const int half = threadIdx.x >> 4, lane = threadIdx.x & 15;
+    double* ysm = ysm_all[half];
+    const misti::HalfWarpLanes g;
+    const int ngroups = gridDim.x * kJsfsWarps * 2;
+    // both halves of a warp walk the item list together (lock step); the odd one out re-reads the last item
+    for (int b0 = blockIdx.x * kJsfsWarps * 2 + (half & ~1); b0 < B; b0 += ngroups) {
+        const bool has = b0 + (half & 1) < B;
+        const int b = has ? b0 + (half & 1) : B - 1;
         const ModelDesc& md = models[model_ids ? model_ids[b] : model_default];
         int st = status[b];
         double raw[7], jn[7], logj[7];
         int nt = 0;
-        if (st == MISTI_OK) {
-            const double cp[3] = {cpost[b], cpost[stride + b], cpost[2 * stride + b]};
-            st = misti::jsfs_item(g, md, times + md.grid_off, params + (long)b * P, lc + b, stride, cp, ysm, raw, &nt);
-        }
+        const double cp[3] = {cpost[b], cpost[stride + b], cpost[2 * stride + b]};
+        const int js = misti::jsfs_item(g, md, has && st == MISTI_OK, times + md.grid_off, params + (long)b * P, lc + b, stride,
+                                        cp, ysm, raw, &nt);
+        if (!has) continue;
+        if (st == MISTI_OK) st = js;
         if (st == MISTI_OK && !misti::jafs_normalise_logs(raw, unfolded != 0, jn, logj)) st = MISTI_NONFINITE;
         if (st != MISTI_OK)
             for (int c = 0; c < 7; ++c) raw[c] = jn[c] = nan("");
@@ -107,7 +115,7 @@ misti_jsfs_kernel(int B, int P, const double* __restrict__ params, const int* __
         }
         // fused composite likelihood over all data rows (bootstrap replicates): lanes stride the rows
         const double bad = (st == MISTI_NEGATIVE_PARAM || st == MISTI_CORRECTION_FAILED) ? -misti::kInf : nan("");
-        for (int r = lane; r < R; r += 32)
+        for (int r = lane; r < R; r += 16)
             llh[(long)b * R + r] = st == MISTI_OK ? misti::score_row(data + 8 * (long)r, logj) : bad;
     }
 }
@@ -237,6 +245,7 @@ struct misti_ctx {
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
     bool ev_valid = false;
     int64_t launches = 0;
+    int jsfs_minb = kJsfsMinBlocks;
 };
 
 namespace {
@@ -347,6 +356,7 @@ int misti_ctx_create(int device, void* stream, misti_ctx** out) {
         if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return MISTI_E_CUDA; }
         ctx->own_stream = true;
     }
+    if (const char* e = getenv("MISTI_JSFS_MINB")) ctx->jsfs_minb = atoi(e);
     for (int i = 0; i < 3; ++i)
         if (cudaEventCreate(&ctx->ev[i]) != cudaSuccess) { delete ctx; return MISTI_E_CUDA; }
     if (cudaMalloc((void**)&ctx->d_small, (44 * 44 + 2 * 44) * sizeof(double)) != cudaSuccess) { delete ctx; return MISTI_E_CUDA; }
@@ -501,13 +511,20 @@ static int eval_chunk(misti_ctx* ctx, int B, int P, const double* d_params, cons
         numT_max, ctx->d_lc, stride, ctx->d_cpost, d_pr, ctx->d_status, ctx->d_nfev);
     CK(cudaGetLastError());
     CK(cudaEventRecord(ctx->ev[1], ctx->stream));
-    int blocks = (B + kJsfsWarps - 1) / kJsfsWarps;
+    int blocks = (B + 2 * kJsfsWarps - 1) / (2 * kJsfsWarps);
     const int max_blocks = ctx->sm_count * 16;
     if (blocks > max_blocks) blocks = max_blocks;
-    misti_jsfs_kernel<<<blocks, kJsfsWarps * 32, 0, ctx->stream>>>(B, P, d_params, d_model_ids, model_default, ctx->d_models,
-                                                                   ctx->d_times, ctx->d_lc, stride, ctx->d_cpost, ctx->d_data,
-                                                                   ctx->R, ctx->unfolded, d_llh, d_jafs, d_jafs_raw,
-                                                                   ctx->d_status, d_terms);
+#define MISTI_LAUNCH_JSFS(MINB)                                                                                          \
+    misti_jsfs_kernel<MINB><<<blocks, kJsfsWarps * 32, 0, ctx->stream>>>(                                                 \
+        B, P, d_params, d_model_ids, model_default, ctx->d_models, ctx->d_times, ctx->d_lc, stride, ctx->d_cpost, ctx->d_data, \
+        ctx->R, ctx->unfolded, d_llh, d_jafs, d_jafs_raw, ctx->d_status, d_terms)
+    switch (ctx->jsfs_minb) {  // register budget per thread: 2 -> 255, 3 -> 168, 4 -> 128, 5 -> 96 (tuning knob MISTI_JSFS_MINB)
+        case 2: MISTI_LAUNCH_JSFS(2); break;
+        case 3: MISTI_LAUNCH_JSFS(3); break;
+        case 5: MISTI_LAUNCH_JSFS(5); break;
+        default: MISTI_LAUNCH_JSFS(kJsfsMinBlocks); break;
+    }
+#undef MISTI_LAUNCH_JSFS
     CK(cudaGetLastError());
     CK(cudaEventRecord(ctx->ev[2], ctx->stream));
     ctx->ev_valid = true;

@@ -17,6 +17,7 @@ STATUS_TEXT = {
     _lib.CORRECTION_FAILED: "lambda correction failed",
     _lib.NONFINITE: "non-finite result",
     _lib.INFINITE_COAL_TIME: "infinite coalescent time, no migration",
+    _lib.STIFF: "interval too stiff (run-away corrected rate)",
 }
 
 

@@ -55,7 +55,7 @@ int hs_jsfs(int numT, int splitT, int sampleDate, const double* times, int n_ban
     double cpost[3], ysm[88], logj[7];
     misti::post_split_coeffs(md, times, lc, 1, cpost);
     misti::SingleLane g;
-    const int st = misti::jsfs_item(g, md, times, params, lc, 1, cpost, ysm, raw, terms);
+    const int st = misti::jsfs_item(g, md, true, times, params, lc, 1, cpost, ysm, raw, terms);
     if (st != MISTI_OK) return st;
     if (!misti::jafs_normalise_logs(raw, unfolded != 0, jn, logj)) return MISTI_NONFINITE;
     *llh = misti::score_row(drow, logj);

@@ -186,7 +186,7 @@ def test_drop_in_class(golden_datasets, golden_cases):
         assert relerr(M.JAFS, exp["JAFS"]) < TOL
         assert relerr(M.lc, exp["lc"]) < 1e-8
         assert relerr(M.llh_const, exp["llh_const"]) < 1e-15
-        assert relerr(M.MaximumLLHFunction(), exp["max_llh"]) < 1e-12
+        assert relerr(M.MaximumLLHFunction(), exp["max_llh"]) < TOL
         assert relerr(np.array(M.Pr) + 1.0, np.array(exp["Pr"]) + 1.0) < 1e-9
         assert M.numT == exp["numT"] and M.splitT == exp["splitT_int"]
 
