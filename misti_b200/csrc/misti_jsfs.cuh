@@ -67,6 +67,11 @@ struct SingleLane {  // test-only host build: one lane owns all 44 rows
     MISTI_HD int wmax(int v) const { return v; }
     MISTI_HD bool any(bool v) const { return v; }
     MISTI_HD bool all(bool v) const { return v; }
+    // coefficient table: entry c < 12 is 2^(c >> 2) * rq[c & 3], entries 12.. are 0
+    MISTI_HD double table_entry(const double*) const { return 0.0; }
+    MISTI_HD double table_get(double, unsigned c, const double* rq) const {
+        return c >= 12u ? 0.0 : (double)(1u << (c >> 2)) * rq[c & 3u];
+    }
 };
 
 #if defined(__CUDACC__)
@@ -88,6 +93,15 @@ struct HalfWarpLanes {  // two items per warp: lane l of each 16-lane half owns 
     }
     __device__ bool any(bool v) const { return __any_sync(0xffffffffu, v); }
     __device__ bool all(bool v) const { return __all_sync(0xffffffffu, v); }
+    // coefficient table spread over the 16 lanes of the group: lane c < 12 holds 2^(c >> 2) * rq[c & 3],
+    // lanes 12.. hold 0; table_get fetches entry (c & 15) with one shuffle instead of a select chain
+    __device__ double table_entry(const double* rq) const {
+        const unsigned c = threadIdx.x & 15u;
+        const unsigned kind = c & 3u;
+        const double base = kind == 0 ? rq[0] : (kind == 1 ? rq[1] : (kind == 2 ? rq[2] : rq[3]));
+        return c >= 12u ? 0.0 : (double)(1u << (c >> 2)) * base;
+    }
+    __device__ double table_get(double mine, unsigned c, const double*) const { return __shfl_sync(0xffffffffu, mine, c, 16); }
 };
 #endif
 
@@ -108,6 +122,7 @@ static const RecipTable h_recip = RecipTable();
 #define MISTI_RECIP(k) h_recip.v[k]
 #endif
 
+constexpr int kYStride = 48;                    // doubles per ping-pong buffer (44 states + pad rows)
 constexpr double kUnifMaxStep = 32.0;           // largest q*T handled in one uniformisation sweep
 constexpr double kUnifTol = 1.3877787807814457e-17;  // 2^-56: truncation of the Poisson tail
 constexpr double kUnifMaxStiff = 131072.0;       // q*T beyond this is reported as MISTI_STIFF (4096 sweeps)
@@ -116,11 +131,12 @@ constexpr int kUnifMaxTerms = MISTI_RECIP_N - 4;     // never reached for q*T <=
 // Post-split coefficients (run by ONE thread; lc addressed like in correct_lambdas_item):
 //   cpost[k] = sum_{i>=splitT} exp(-a_k x_i) (1 - exp(-a_k lam_i T_i)) / (a_k lam_i),  x_i = sum_{j<i} lam_j T_j,
 // with the last interval infinite (MigrationInference.py:530-540: P1 = 0 there), a = (6, 3, 1).
-MISTI_HD inline void post_split_coeffs(const ModelDesc& md, const double* times, const double* lc, long stride, double* cpost) {
+MISTI_HD inline void post_split_coeffs(const ModelDesc& md, const double* times, const double* lc, int pitch, long stride,
+                                       double* cpost) {
     double c6 = 0, c3 = 0, c1 = 0;
     double e1 = 1.0;  // exp(-x)
     for (int t = md.splitT; t < md.numT; ++t) {
-        const double lam = lc[(2 * t) * stride];
+        const double lam = lc[(pitch * t) * stride];
         const double e3 = e1 * e1 * e1, e6 = e3 * e3;
         if (t < md.numT - 1) {
             const double z = lam * times[t];
@@ -140,21 +156,25 @@ MISTI_HD inline void post_split_coeffs(const ModelDesc& md, const double* times,
     cpost[0] = c6; cpost[1] = c3; cpost[2] = c1;
 }
 
+// Rates are read as lc[(PITCH*t + j)*stride]: j = 0, 1 the corrected coalescence rates and, when PITCH == 4, j = 2, 3
+// the migration rates of the interval (written by the correction kernel; with PITCH == 2 they are re-derived from the
+// band list).
 // Expected JSFS of one item.  ALL lanes of the warp call this together (each group with its own item;
-// `active` = false for a group without work); `ysm` is a scratch area of 2*44 doubles private to the
-// group.  On return every lane of the group holds the UNNORMALISED spectrum in jafs[0..6]
+// `active` = false for a group without work); `ysm` is a scratch area of 2*kYStride doubles private to the
+// group (two ping-pong copies of the 44-vector, padded to 48 so that every lane has a slot to write).  On return every lane of the group holds the UNNORMALISED spectrum in jafs[0..6]
 // (MigrationInference.JAFSpectrum's return value) and the number of mat-vecs in *terms.
-template <class G>
+template <class G, int PITCH>
 MISTI_D inline int jsfs_item(const G& g, const ModelDesc& md, bool active, const double* times, const double* params,
                              const double* lc, long stride, const double* cpost, double* ysm, double* jafs, int* terms) {
     constexpr int RPL = (44 + G::LANES - 1) / G::LANES;
     constexpr int W = MISTI_ELL_WIDTH;
     const int lane = g.lane();
     bool valid[RPL];
-    // per row, packed: ELL slot e -> kind (2 bits) | count (3 bits) at bit 5e; diagonal multiplicity of rate kind k at bit 20+3k
+    // per row, packed: ELL slot e -> coefficient-table code (kind + 4 log2(count), 12 = empty) at bit 4e;
+    // diagonal multiplicity of rate kind k at bit 16+3k
     unsigned rc[RPL];
-    const double* yp[RPL][W];  // where this lane reads y[col] for each ELL slot (buffer 0; buffer 1 is +44)
-    double* const wb = ysm + lane;  // this lane writes y[row] at wb[s * LANES] (+44 for buffer 1)
+    const double* yp[RPL][W];  // where this lane reads y[col] for each ELL slot (buffer 0; buffer 1 is +kYStride)
+    double* const wb = ysm + lane;  // this lane writes y[row] at wb[s * LANES] (+kYStride for buffer 1); rows 44.. are pad
     double P[RPL];            // state probabilities at the start of the current interval (rows owned by this lane)
     double Ia[RPL], Ib[RPL];  // occupancy integrals summed over the intervals before / from the sampling date
 #pragma unroll
@@ -166,11 +186,12 @@ MISTI_D inline int jsfs_item(const G& g, const ModelDesc& md, bool active, const
 #pragma unroll
         for (int e = 0; e < W; ++e) {
             const EllEntry en = MISTI_TAB(ell)[rr][e];
-            if (valid[s]) rc[s] |= ((unsigned)en.kind | ((unsigned)en.cnt << 2)) << (5 * e);
+            const unsigned cde = (!valid[s] || en.cnt == 0) ? 12u : (unsigned)en.kind + (en.cnt == 1 ? 0u : (en.cnt == 2 ? 4u : 8u));
+            rc[s] |= cde << (4 * e);
             yp[s][e] = ysm + (valid[s] ? en.col : 0);
         }
         if (valid[s])
-            for (int k = 0; k < 4; ++k) rc[s] |= (unsigned)MISTI_TAB(diag)[r][k] << (20 + 3 * k);
+            for (int k = 0; k < 4; ++k) rc[s] |= (unsigned)MISTI_TAB(diag)[r][k] << (16 + 3 * k);
         P[s] = (valid[s] && r == 2) ? 1.0 : 0.0;  // both genome-1 lineages in deme 0, genome-2 in deme 1 (:469-471)
         Ia[s] = 0.0; Ib[s] = 0.0;
     }
@@ -216,7 +237,7 @@ MISTI_D inline int jsfs_item(const G& g, const ModelDesc& md, bool active, const
             g.sync();
 #pragma unroll
             for (int s = 0; s < RPL; ++s)
-                if (valid[s]) wb[s * G::LANES] = P[s];
+                wb[s * G::LANES] = P[s];
             g.sync();
             double pw_om[5], pw_r[5];
             pw_om[0] = 1.0; pw_r[0] = 1.0;
@@ -248,8 +269,12 @@ MISTI_D inline int jsfs_item(const G& g, const ModelDesc& md, bool active, const
     auto set_generator = [&](int it, bool act) {
         double la0 = 1.0, la1 = 1.0, m0 = 0.0, m1 = 0.0;
         if (act) {
-            la0 = lc[(2 * it) * stride]; la1 = lc[(2 * it + 1) * stride];
-            m0 = band_rate(md, params, it, 0); m1 = band_rate(md, params, it, 1);
+            la0 = lc[(PITCH * it) * stride]; la1 = lc[(PITCH * it + 1) * stride];
+            if (PITCH == 4) {
+                m0 = lc[(PITCH * it + 2) * stride]; m1 = lc[(PITCH * it + 3) * stride];
+            } else {
+                m0 = band_rate(md, params, it, 0); m1 = band_rate(md, params, it, 1);
+            }
             if (!(la0 >= 0.0 && la0 <= DBL_MAX && la1 >= 0.0 && la1 <= DBL_MAX && m0 >= 0.0 && m0 <= DBL_MAX && m1 >= 0.0 &&
                   m1 <= DBL_MAX)) {
                 status = MISTI_NONFINITE;
@@ -260,24 +285,20 @@ MISTI_D inline int jsfs_item(const G& g, const ModelDesc& md, bool active, const
         double d[RPL], dmax = 0.0;
 #pragma unroll
         for (int s = 0; s < RPL; ++s) {
-            d[s] = (double)((rc[s] >> 20) & 7u) * la0 + (double)((rc[s] >> 23) & 7u) * la1 +
-                   (double)((rc[s] >> 26) & 7u) * m0 + (double)((rc[s] >> 29) & 7u) * m1;
+            d[s] = (double)((rc[s] >> 16) & 7u) * la0 + (double)((rc[s] >> 19) & 7u) * la1 +
+                   (double)((rc[s] >> 22) & 7u) * m0 + (double)((rc[s] >> 25) & 7u) * m1;
             dmax = d[s] > dmax ? d[s] : dmax;
         }
         q = g.max(dmax);
         if (!(q > 0.0)) q = 1.0;  // no event possible at all: A = I
         qinv = 1.0 / q;
-        const double rq0 = la0 * qinv, rq1 = la1 * qinv, rq2 = m0 * qinv, rq3 = m1 * qinv;
+        const double rq[4] = {la0 * qinv, la1 * qinv, m0 * qinv, m1 * qinv};
+        const double mine = g.table_entry(rq);
 #pragma unroll
         for (int s = 0; s < RPL; ++s) {
             adiag[s] = (q - d[s]) * qinv;
 #pragma unroll
-            for (int e = 0; e < W; ++e) {
-                const unsigned ke = rc[s] >> (5 * e);
-                const unsigned kind = ke & 3u;
-                const double rk = kind == 0 ? rq0 : (kind == 1 ? rq1 : (kind == 2 ? rq2 : rq3));
-                coef[s][e] = (double)((ke >> 2) & 7u) * rk;
-            }
+            for (int e = 0; e < W; ++e) coef[s][e] = g.table_get(mine, (rc[s] >> (4 * e)) & 15u, rq);
         }
     };
 
@@ -293,23 +314,24 @@ MISTI_D inline int jsfs_item(const G& g, const ModelDesc& md, bool active, const
         if (q * T > kUnifMaxStiff) { status = MISTI_STIFF; T = 0.0; }
         const double qT = q * T;
         const int nsub = g.wmax(qT > kUnifMaxStep ? (int)ceil(qT / kUnifMaxStep) : 1);
-        const double lam = qT / nsub;
-        const double p0 = exp(-lam);
+        const double lam = nsub == 1 ? qT : qT / nsub;
+        const double p0 = exp(-lam), t0 = -expm1(-lam);  // Poisson P(N = 0) and P(N > 0)
         double Iint[RPL];
 #pragma unroll
         for (int s = 0; s < RPL; ++s) Iint[s] = 0.0;
         for (int sub = 0; sub < nsub; ++sub) {
-            double yk[RPL], S[RPL], P1[RPL];
+            double yk[RPL], P1[RPL];
             g.sync();
 #pragma unroll
             for (int s = 0; s < RPL; ++s) {
-                yk[s] = P[s]; S[s] = 0.0; P1[s] = p0 * P[s];
-                if (valid[s]) wb[s * G::LANES] = P[s];
+                yk[s] = P[s]; P1[s] = p0 * P[s];
+                wb[s * G::LANES] = P[s];
             }
-            double p = p0;
-            double r = lam;  // lam / (k + 1): ratio of consecutive Poisson weights
+            double p = p0;     // Pois(k; lam)
+            double tail = t0;  // P(N > k)
+            double r = lam;    // lam / (k + 1): ratio of consecutive Poisson weights
             int k = 0;
-            // one term: y <- A y (read buffer RO, write buffer WO), S += y_old, P1 += p y, I += p S.
+            // one term: I += P(N > k-1) y_(k-1);  y_k <- A y_(k-1) (read buffer RO, write buffer WO);  P1 += Pois(k) y_k.
             // Returns true when this group's Poisson tail beyond the term is below kUnifTol.
             auto term = [&](const int RO, const int WO) -> bool {
                 g.sync();
@@ -322,17 +344,17 @@ MISTI_D inline int jsfs_item(const G& g, const ModelDesc& md, bool active, const
                     const double u = fma(coef[s][1], yp[s][1][RO], fma(coef[s][0], yp[s][0][RO], adiag[s] * yk[s]));
                     const double v = fma(coef[s][3], yp[s][3][RO], coef[s][2] * yp[s][2][RO]);
                     const double acc = u + v;
-                    S[s] += yk[s];
+                    Iint[s] = fma(tail, yk[s], Iint[s]);
                     yk[s] = acc;
-                    if (valid[s]) wb[WO + s * G::LANES] = acc;
+                    wb[WO + s * G::LANES] = acc;
                     P1[s] = fma(p, acc, P1[s]);
-                    Iint[s] = fma(p, S[s], Iint[s]);
                 }
+                tail -= p;
                 return r < 1.0 && p < kUnifTol * (1.0 - r);
             };
             while (true) {  // the two halves of the ping-pong buffer get compile-time offsets
-                if (g.all(term(0, 44))) break;
-                if (g.all(term(44, 0))) break;
+                if (g.all(term(0, kYStride))) break;
+                if (g.all(term(kYStride, 0))) break;
                 if (k >= kUnifMaxTerms) { status = MISTI_NONFINITE; break; }
             }
             if (act) nterms += k;
@@ -363,7 +385,7 @@ MISTI_D inline int jsfs_item(const G& g, const ModelDesc& md, bool active, const
         for (int s = 0; s < RPL; ++s) {
             yk[s] = run ? P[s] : 0.0;
             Iint[s] = yk[s];
-            if (valid[s]) wb[s * G::LANES] = yk[s];
+            wb[s * G::LANES] = yk[s];
         }
         double nprev = 0.0;
 #pragma unroll
@@ -374,7 +396,7 @@ MISTI_D inline int jsfs_item(const G& g, const ModelDesc& md, bool active, const
         int k = 0, cur = 0;
         while (!g.all(done)) {
             g.sync();
-            const int ro = 44 * cur, wo = 44 * (cur ^ 1);
+            const int ro = kYStride * cur, wo = kYStride * (cur ^ 1);
             double nk = 0.0;
 #pragma unroll
             for (int s = 0; s < RPL; ++s) {
@@ -382,7 +404,7 @@ MISTI_D inline int jsfs_item(const G& g, const ModelDesc& md, bool active, const
 #pragma unroll
                 for (int e = 0; e < W; ++e) acc += coef[s][e] * yp[s][e][ro];
                 yk[s] = acc;
-                if (valid[s]) wb[wo + s * G::LANES] = acc;
+                wb[wo + s * G::LANES] = acc;
                 Iint[s] += acc;
                 nk += acc;
             }

@@ -31,6 +31,7 @@ constexpr int kCorrectThreads = 64;
 constexpr int kJsfsWarps = 4;      // warps per block of the JSFS kernel (8 items per block)
 constexpr int kJsfsMinBlocks = 4;  // occupancy target: caps the kernel at 128 registers per thread
 constexpr int kMaxChunk = 1 << 20;
+constexpr int kPitch = 4;  // per interval and item the rate buffer holds la0, la1, m0, m1
 
 static __device__ const double d_l8[8][8] = MISTI_L8_INIT;
 static __device__ const unsigned char d_w8[7][8] = MISTI_W8_INIT;
@@ -55,13 +56,23 @@ misti_correct_kernel(int B, int P, const double* __restrict__ params, const int*
         for (int i = 0; i < md.n_params; ++i)
             if (par[i] < 0) st = MISTI_NEGATIVE_PARAM;
         const double* src = lc_inject + (long)b * 2 * numT_max;
-        for (int j = 0; j < 2 * md.numT; ++j) lcb[j * stride] = src[j];
+        for (int t = 0; t < md.numT; ++t) {
+            lcb[(kPitch * t) * stride] = src[2 * t];
+            lcb[(kPitch * t + 1) * stride] = src[2 * t + 1];
+        }
     } else {
         double* pr = pr_out ? pr_out + (long)b * (numT_max + 1) * 6 : nullptr;
-        st = misti::correct_lambdas_item(md, tt, ll, par, flags, mixtureTH, lcb, stride, pr, &nf);
+        st = misti::correct_lambdas_item(md, tt, ll, par, flags, mixtureTH, lcb, kPitch, stride, pr, &nf);
     }
     double cp[3] = {0.0, 0.0, 0.0};
-    if (st == MISTI_OK) misti::post_split_coeffs(md, tt, lcb, stride, cp);
+    if (st == MISTI_OK) {
+        misti::post_split_coeffs(md, tt, lcb, kPitch, stride, cp);
+        const int n2 = md.splitT < md.numT ? md.splitT : md.numT;
+        for (int t = 0; t < n2; ++t) {  // migration rates of the two-population intervals, for the JSFS kernel
+            lcb[(kPitch * t + 2) * stride] = misti::band_rate(md, par, t, 0);
+            lcb[(kPitch * t + 3) * stride] = misti::band_rate(md, par, t, 1);
+        }
+    }
     cpost[b] = cp[0];
     cpost[stride + b] = cp[1];
     cpost[2 * stride + b] = cp[2];
@@ -80,7 +91,7 @@ misti_jsfs_kernel(int B, int P, const double* __restrict__ params, const int* __
                   double* __restrict__ llh, double* __restrict__ jafs, double* __restrict__ jafs_raw, int* __restrict__ status,
                   int* __restrict__ terms) {
     // one item per 16-lane half warp (3 of the 44 chain states per lane), two items per warp
-    __shared__ double ysm_all[kJsfsWarps * 2][88];
+    __shared__ double ysm_all[kJsfsWarps * 2][2 * misti::kYStride];
     const int half = threadIdx.x >> 4, lane = threadIdx.x & 15;
     double* ysm = ysm_all[half];
     const misti::HalfWarpLanes g;
@@ -94,7 +105,7 @@ misti_jsfs_kernel(int B, int P, const double* __restrict__ params, const int* __
         double raw[7], jn[7], logj[7];
         int nt = 0;
         const double cp[3] = {cpost[b], cpost[stride + b], cpost[2 * stride + b]};
-        const int js = misti::jsfs_item(g, md, has && st == MISTI_OK, times + md.grid_off, params + (long)b * P, lc + b, stride,
+        const int js = misti::jsfs_item<misti::HalfWarpLanes, kPitch>(g, md, has && st == MISTI_OK, times + md.grid_off, params + (long)b * P, lc + b, stride,
                                         cp, ysm, raw, &nt);
         if (!has) continue;
         if (st == MISTI_OK) st = js;
@@ -142,7 +153,7 @@ __global__ void misti_gather_lc_kernel(int B, int numT_max, const int* __restric
     if (i >= n) return;
     const int b = (int)(i / (2 * numT_max)), j = (int)(i % (2 * numT_max));
     const ModelDesc& md = models[model_ids ? model_ids[b] : model_default];
-    out[i] = j < 2 * md.numT ? lc[j * stride + b] : 0.0;
+    out[i] = j < 2 * md.numT ? lc[(kPitch * (j >> 1) + (j & 1)) * stride + b] : 0.0;
 }
 
 // ---- structure-table export kernels (TwoPopulations / OnePopulation mirror classes) ---------------
@@ -323,7 +334,7 @@ int ensure_batch(misti_ctx* ctx, size_t B) {
     size_t ncap = ctx->cap ? ctx->cap : 1024;
     while (ncap < B) ncap *= 2;
     int rc;
-    if ((rc = realloc_exact(ctx, &ctx->d_lc, ncap * 2 * (size_t)ctx->numT_max))) return rc;
+    if ((rc = realloc_exact(ctx, &ctx->d_lc, ncap * kPitch * (size_t)ctx->numT_max))) return rc;
     if ((rc = realloc_exact(ctx, &ctx->d_cpost, ncap * 3))) return rc;
     if ((rc = realloc_exact(ctx, &ctx->d_status, ncap))) return rc;
     if ((rc = realloc_exact(ctx, &ctx->d_nfev, ncap))) return rc;

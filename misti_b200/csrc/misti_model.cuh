@@ -42,10 +42,11 @@ MISTI_HD inline double pulse_rate(const ModelDesc& md, const double* params, int
     return v;
 }
 
-// lc is addressed as lc[(2*t+g)*stride]; times[numT-1]; lh[numT][2].
+// lc is addressed as lc[(pitch*t+g)*stride] (pitch >= 2 values per interval); times[numT-1]; lh[numT][2].
 // Pr (nullable): [splitT+1][3][2] trajectory of the 3-state chains (MigrationInference.py:309,350).
 MISTI_HD inline int correct_lambdas_item(const ModelDesc& md, const double* times, const double* lh, const double* params,
-                                         unsigned flags, double mixtureTH, double* lc, long stride, double* Pr, int* nfev_out) {
+                                         unsigned flags, double mixtureTH, double* lc, int pitch, long stride, double* Pr,
+                                         int* nfev_out) {
     const bool correct = flags & MISTI_FLAG_CORRECT, cpfit = flags & MISTI_FLAG_CPFIT;
     int nfev = 0;
     for (int i = 0; i < md.n_params; ++i)
@@ -71,16 +72,16 @@ MISTI_HD inline int correct_lambdas_item(const ModelDesc& md, const double* time
             }
         }
         if (!correct) {
-            lc[(2 * t) * stride] = lh[2 * t];
-            lc[(2 * t + 1) * stride] = lh[2 * t + 1];
+            lc[(pitch * t) * stride] = lh[2 * t];
+            lc[(pitch * t + 1) * stride] = lh[2 * t + 1];
         } else {
             st.lh[0] = lh[2 * t]; st.lh[1] = lh[2 * t + 1];
             st.T = times[t];
             st.mu[0] = band_rate(md, params, t, 0); st.mu[1] = band_rate(md, params, t, 1);
             double l[2];
             const bool ok = solve_interval(&st, cpfit, mixtureTH, l, &nfev);
-            lc[(2 * t) * stride] = l[0];
-            lc[(2 * t + 1) * stride] = l[1];
+            lc[(pitch * t) * stride] = l[0];
+            lc[(pitch * t + 1) * stride] = l[1];
             if (!ok) { *nfev_out = nfev; return MISTI_CORRECTION_FAILED; }
         }
         if (Pr) {
@@ -92,7 +93,7 @@ MISTI_HD inline int correct_lambdas_item(const ModelDesc& md, const double* time
     }
     for (int t = splitT; t < numT - 1; ++t) {
         const double T = times[t];
-        if (T == 0) { lc[(2 * t) * stride] = 1; lc[(2 * t + 1) * stride] = 1; continue; }
+        if (T == 0) { lc[(pitch * t) * stride] = 1; lc[(pitch * t + 1) * stride] = 1; continue; }
         double lam;
         if (!cpfit) {
             if (!fit_single_pop(lh + 2 * t, T, nc0, nc1, &lam, &nfev)) { *nfev_out = nfev; return MISTI_NONFINITE; }
@@ -100,8 +101,8 @@ MISTI_HD inline int correct_lambdas_item(const ModelDesc& md, const double* time
             const double pnc = (exp(-T * lh[2 * t]) + exp((nc1 - nc0) - T * lh[2 * t + 1])) / (1 + exp(nc1 - nc0));
             lam = -log(pnc) / T;
         }
-        lc[(2 * t) * stride] = lam;
-        lc[(2 * t + 1) * stride] = lam;
+        lc[(pitch * t) * stride] = lam;
+        lc[(pitch * t + 1) * stride] = lam;
         nc0 += -T * lam;
         nc1 += -T * lam;
     }
@@ -109,8 +110,8 @@ MISTI_HD inline int correct_lambdas_item(const ModelDesc& md, const double* time
         const int t = numT - 1;
         const double pr0 = exp(nc0), pr1 = exp(nc1);
         const double lam = (pr0 + pr1) / (pr0 / lh[2 * t] + pr1 / lh[2 * t + 1]);
-        lc[(2 * t) * stride] = lam;
-        lc[(2 * t + 1) * stride] = lam;
+        lc[(pitch * t) * stride] = lam;
+        lc[(pitch * t + 1) * stride] = lam;
     }
     if (flags & MISTI_FLAG_SMOOTH) {  // SmoothConst for both genomes (:380-405)
         for (int g = 0; g < 2; ++g) {
@@ -120,14 +121,14 @@ MISTI_HD inline int correct_lambdas_item(const ModelDesc& md, const double* time
             while (k < splitT) {
                 int j = k;
                 while (fabs(lh[2 * j + g] - lam) < 1e-10 && j < numT - 1) {
-                    nc += lc[(2 * j + g) * stride] * times[j];
+                    nc += lc[(pitch * j + g) * stride] * times[j];
                     time += times[j];
                     ++j;
                     if (j == splitT) break;
                 }
                 if (j == k) break;  // splitT == numT: the reference loops forever here; we stop
                 const double avg = nc / time;
-                for (int i = k; i < j; ++i) lc[(2 * i + g) * stride] = avg;
+                for (int i = k; i < j; ++i) lc[(pitch * i + g) * stride] = avg;
                 lam = lh[2 * j + g];
                 nc = 0.0; time = 0.0;
                 k = j;

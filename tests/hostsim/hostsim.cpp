@@ -28,7 +28,7 @@ int hs_correct_lambdas(int numT, int splitT, int sampleDate, const double* times
         md.pulse_pop[b] = (int)pulses[4 * b]; md.pulse_time[b] = (int)pulses[4 * b + 1];
         md.pulse_val[b] = pulses[4 * b + 2]; md.pulse_opt[b] = (int)pulses[4 * b + 3];
     }
-    return misti::correct_lambdas_item(md, times, lh, params, flags, mixtureTH, lc, 1, Pr, nfev);
+    return misti::correct_lambdas_item(md, times, lh, params, flags, mixtureTH, lc, 2, 1, Pr, nfev);
 }
 
 static void fill_model(misti::ModelDesc& md, int numT, int splitT, int sampleDate, int n_bands, const double* bands,
@@ -52,10 +52,10 @@ int hs_jsfs(int numT, int splitT, int sampleDate, const double* times, int n_ban
             const double* drow /* 7 + const */, double* raw, double* jn, double* llh, int* terms) {
     misti::ModelDesc md;
     fill_model(md, numT, splitT, sampleDate, n_bands, bands, n_pulses, pulses, n_params);
-    double cpost[3], ysm[88], logj[7];
-    misti::post_split_coeffs(md, times, lc, 1, cpost);
+    double cpost[3], ysm[2 * misti::kYStride], logj[7];
+    misti::post_split_coeffs(md, times, lc, 2, 1, cpost);
     misti::SingleLane g;
-    const int st = misti::jsfs_item(g, md, true, times, params, lc, 1, cpost, ysm, raw, terms);
+    const int st = misti::jsfs_item<misti::SingleLane, 2>(g, md, true, times, params, lc, 1, cpost, ysm, raw, terms);
     if (st != MISTI_OK) return st;
     if (!misti::jafs_normalise_logs(raw, unfolded != 0, jn, logj)) return MISTI_NONFINITE;
     *llh = misti::score_row(drow, logj);
