@@ -28,6 +28,7 @@ namespace {
 using misti::ModelDesc;
 
 constexpr int kCorrectThreads = 64;
+constexpr int kCorrectMinBlocks = 8;
 constexpr int kJsfsWarps = 4;      // warps per block of the JSFS kernel (8 items per block)
 constexpr int kJsfsMinBlocks = 4;  // occupancy target: caps the kernel at 128 registers per thread
 constexpr int kMaxChunk = 1 << 20;
@@ -39,7 +40,8 @@ static __device__ const unsigned char d_w8[7][8] = MISTI_W8_INIT;
 // ------------------------------------------------------------------------------------------------
 // K1: correction chain, one thread per item
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kCorrectThreads)
+template <int MINB>
+__global__ void __launch_bounds__(kCorrectThreads, MINB)
 misti_correct_kernel(int B, int P, const double* __restrict__ params, const int* __restrict__ model_ids, int model_default,
                      const ModelDesc* __restrict__ models, const double* __restrict__ times, const double* __restrict__ lh,
                      unsigned flags, double mixtureTH, const double* __restrict__ lc_inject, int numT_max, double* lc,
@@ -257,6 +259,7 @@ struct misti_ctx {
     bool ev_valid = false;
     int64_t launches = 0;
     int jsfs_minb = kJsfsMinBlocks;
+    int correct_minb = kCorrectMinBlocks;
 };
 
 namespace {
@@ -368,6 +371,7 @@ int misti_ctx_create(int device, void* stream, misti_ctx** out) {
         ctx->own_stream = true;
     }
     if (const char* e = getenv("MISTI_JSFS_MINB")) ctx->jsfs_minb = atoi(e);
+    if (const char* e = getenv("MISTI_CORRECT_MINB")) ctx->correct_minb = atoi(e);
     for (int i = 0; i < 3; ++i)
         if (cudaEventCreate(&ctx->ev[i]) != cudaSuccess) { delete ctx; return MISTI_E_CUDA; }
     if (cudaMalloc((void**)&ctx->d_small, (44 * 44 + 2 * 44) * sizeof(double)) != cudaSuccess) { delete ctx; return MISTI_E_CUDA; }
@@ -517,9 +521,16 @@ static int eval_chunk(misti_ctx* ctx, int B, int P, const double* d_params, cons
     const long stride = (long)ctx->cap;
     const int numT_max = ctx->numT_max;
     CK(cudaEventRecord(ctx->ev[0], ctx->stream));
-    misti_correct_kernel<<<(B + kCorrectThreads - 1) / kCorrectThreads, kCorrectThreads, 0, ctx->stream>>>(
-        B, P, d_params, d_model_ids, model_default, ctx->d_models, ctx->d_times, ctx->d_lh, flags, mixture_th, d_lc_inject,
-        numT_max, ctx->d_lc, stride, ctx->d_cpost, d_pr, ctx->d_status, ctx->d_nfev);
+#define MISTI_LAUNCH_CORRECT(MINB)                                                                                       \
+    misti_correct_kernel<MINB><<<(B + kCorrectThreads - 1) / kCorrectThreads, kCorrectThreads, 0, ctx->stream>>>(          \
+        B, P, d_params, d_model_ids, model_default, ctx->d_models, ctx->d_times, ctx->d_lh, flags, mixture_th, d_lc_inject, \
+        numT_max, ctx->d_lc, stride, ctx->d_cpost, d_pr, ctx->d_status, ctx->d_nfev)
+    switch (ctx->correct_minb) {  // register budget per thread: 4 -> 255, 8 -> 128, 12 -> 80 (tuning knob MISTI_CORRECT_MINB)
+        case 4: MISTI_LAUNCH_CORRECT(4); break;
+        case 12: MISTI_LAUNCH_CORRECT(12); break;
+        default: MISTI_LAUNCH_CORRECT(kCorrectMinBlocks); break;
+    }
+#undef MISTI_LAUNCH_CORRECT
     CK(cudaGetLastError());
     CK(cudaEventRecord(ctx->ev[1], ctx->stream));
     int blocks = (B + 2 * kJsfsWarps - 1) / (2 * kJsfsWarps);
