@@ -1,0 +1,143 @@
+"""Device numerics, compiled for the HOST (tests/hostsim, test-only): the very headers the CUDA kernels
+include -- trust-region least squares, 3x3 expm, correction chain, uniformised JSFS stage, likelihood
+tail -- checked against the golden vectors of the reference without a GPU."""
+import ctypes
+
+import numpy as np
+
+from _cases import RUNAWAY, bands_pulses, end_to_end_gated, flags_of, grid_of, relerr, sfs_of
+from misti_b200.engine import llh_constants
+
+dp = ctypes.POINTER(ctypes.c_double)
+
+
+def _arr(x):
+    return np.ascontiguousarray(x, dtype=np.float64)
+
+
+def _p(a):
+    return a.ctypes.data_as(dp)
+
+
+def _chain(lib, ds, case):
+    times, lam, st, sd = grid_of(ds, case)
+    bands, pulses = bands_pulses(case)
+    numT = len(lam)
+    T, L = _arr(times), _arr(lam)
+    Bn = _arr([[b[0], b[1], b[2], b[3], b[4]] for b in bands] or [[0] * 5])
+    Pu = _arr([[p[0], p[1], p[2], p[3]] for p in pulses] or [[0] * 4])
+    par = _arr(case["params"] or [0.0])
+    lc, Pr, nfev = np.zeros((numT, 2)), np.zeros((numT + 1, 3, 2)), ctypes.c_int(0)
+    rc = lib.hs_correct_lambdas(numT, st, sd, _p(T), _p(L), len(bands), _p(Bn), len(pulses), _p(Pu), len(case["params"]), _p(par),
+                                flags_of(case), ctypes.c_double(0.0), _p(lc), _p(Pr), ctypes.byref(nfev))
+    return rc, lc, Pr, nfev.value
+
+
+def _jsfs(lib, ds, case, lc):
+    times, lam, st, sd = grid_of(ds, case)
+    bands, pulses = bands_pulses(case)
+    T = _arr(times)
+    Bn = _arr([[b[0], b[1], b[2], b[3], b[4]] for b in bands] or [[0] * 5])
+    Pu = _arr([[p[0], p[1], p[2], p[3]] for p in pulses] or [[0] * 4])
+    par = _arr(case["params"] or [0.0])
+    uf = case["flags"]["unfolded"]
+    row = _arr(sfs_of(ds, case))
+    d = row[1:]
+    drow = _arr(list(d) + [0.0]) if uf else _arr([d[0] + d[6], d[1] + d[5], d[2] + d[4], d[3], 0, 0, 0, 0.0])
+    drow[7] = llh_constants([row], uf)[0]
+    raw, jn, llh, terms = np.zeros(7), np.zeros(7), ctypes.c_double(0), ctypes.c_int(0)
+    lc = _arr(lc)
+    rc = lib.hs_jsfs(len(lam), st, sd, _p(T), len(bands), _p(Bn), len(pulses), _p(Pu), len(case["params"]), _p(par), _p(lc), int(uf),
+                     _p(drow), _p(raw), _p(jn), ctypes.byref(llh), ctypes.byref(terms))
+    return rc, raw, jn, llh.value, terms.value
+
+
+def test_expm3_and_inverse(hostsim):
+    """3x3 expm / inverse on matrices of the shape the correction uses (CorrectLambda.SetMatrix, CorrectLambda.py:55-56)."""
+    from scipy.linalg import expm, inv
+    rng = np.random.default_rng(0)
+    for T in (1e-3, 0.05, 0.5, 1.0, 4.0, 30.0):
+        for _ in range(20):
+            l0, l1, m0, m1 = rng.uniform(0.0, 5.0, 4)
+            M = _arr([[-2 * m0 - l0, 0, m1], [0, -2 * m1 - l1, m0], [2 * m0, 2 * m1, -m0 - m1]])
+            A = _arr(M * T)
+            E = np.zeros((3, 3))
+            hostsim.hs_expm3(_p(A), _p(E))
+            assert np.max(np.abs(E - expm(A))) <= 5e-15 * max(1.0, np.abs(A).sum(axis=0).max())
+            Mi = np.zeros((3, 3))
+            assert hostsim.hs_inv3(_p(M), _p(Mi)) == 1
+            ref = inv(M)
+            assert np.max(np.abs(Mi - ref)) <= 1e-13 * np.linalg.cond(M) * np.max(np.abs(ref))
+
+
+def test_correction_chain_matches_reference(hostsim, golden_datasets, golden_cases):
+    exact = 0
+    for case in golden_cases:
+        rc, lc, Pr, nfev = _chain(hostsim, golden_datasets, case)
+        exp = case["expect"]
+        if not exp["ok"]:
+            assert rc in (1, 2), case["name"]
+            continue
+        if not end_to_end_gated(case):
+            continue
+        assert rc == 0, case["name"]
+        err = relerr(lc, exp["lc"])
+        assert err < 1e-9, (case["name"], err)
+        exact += err == 0.0
+        n = len(exp["Pr"])
+        assert relerr(Pr[:n] + 1.0, np.array(exp["Pr"]) + 1.0) < 1e-10, case["name"]
+    # the trust-region port is iterate-faithful: every no-migration case reproduces the rates bit for bit
+    assert exact >= 20
+
+
+def test_jsfs_stage_matches_reference_given_rates(hostsim, golden_datasets, golden_cases):
+    for case in golden_cases:
+        exp = case["expect"]
+        if not exp["ok"] or case["name"] in RUNAWAY:
+            continue
+        rc, raw, jn, llh, terms = _jsfs(hostsim, golden_datasets, case, exp["lc"])
+        assert rc == 0, case["name"]
+        assert relerr(jn, exp["JAFS"]) < 1e-12, case["name"]
+        assert relerr(llh, exp["llh"]) < 1e-10, case["name"]
+        assert abs(raw.sum() / jn.sum() - raw.sum()) < 1e-9 * raw.sum()
+
+
+def test_end_to_end_host_build(hostsim, golden_datasets, golden_cases):
+    for case in golden_cases:
+        exp = case["expect"]
+        if not exp["ok"] or not end_to_end_gated(case):
+            continue
+        rc, lc, _, _ = _chain(hostsim, golden_datasets, case)
+        assert rc == 0
+        rc, raw, jn, llh, terms = _jsfs(hostsim, golden_datasets, case, lc)
+        assert rc == 0
+        assert relerr(jn, exp["JAFS"]) < 1e-9, case["name"]
+        assert relerr(llh, exp["llh"]) < 1e-9, case["name"]
+
+
+def test_runaway_rates_are_flagged_stiff(hostsim, golden_datasets, golden_cases):
+    """where the reference's own least-squares solve runs away to rates ~1e7 the uniformisation would need
+    millions of sweeps; the kernel reports MISTI_STIFF (5) instead."""
+    for case in golden_cases:
+        if case["name"] in RUNAWAY:
+            rc, *_ = _jsfs(hostsim, golden_datasets, case, case["expect"]["lc"])
+            assert rc == 5
+
+
+def test_no_split_inside_grid(hostsim, golden_datasets):
+    """splitT == numT: the last two-population interval is infinite; needs migration there."""
+    from oracle.misti_oracle import OracleModel
+    d = golden_datasets["ms_two_bands"]
+    numT = len(d["lambdas"])
+    mi = [[1, 0, numT, 0.7, 0], [2, 0, numT, 0.4, 0]]
+    case = {"dataset": "ms_two_bands", "splitT": numT, "mi": mi, "pu": [], "params": [],
+            "flags": dict(trueEPS=True, cpfit=False, smooth=False, unfolded=True), "bs": -1}
+    om = OracleModel(d["times"], d["lambdas"], d["sfs"], numT, mi, [], trueEPS=True, unfolded=True)
+    ref = om.likelihood([])
+    rc, raw, jn, llh, terms = _jsfs(hostsim, golden_datasets, case, d["lambdas"])
+    assert rc == 0
+    assert relerr(jn, om.JAFS) < 1e-10
+    assert relerr(llh, ref) < 1e-10
+    case["mi"] = []
+    rc, *_ = _jsfs(hostsim, golden_datasets, case, d["lambdas"])
+    assert rc == 4  # infinite coalescent time, no migration

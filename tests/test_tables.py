@@ -1,0 +1,106 @@
+"""Structure tables: the generated header (tools/gen_tables.py, index arithmetic) against the oracle's
+independently built tables (breadth-first enumeration) and the reference outputs.  CPU only."""
+import importlib.util
+import os
+import re
+
+import numpy as np
+
+from oracle import misti_oracle as mo
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = open(os.path.join(ROOT, "misti_b200", "csrc", "misti_tables.h")).read()
+
+
+def _macro(name):
+    m = re.search(r"#define %s (.*)" % name, HEADER)
+    body = m.group(1).replace("{", "[").replace("}", "]")
+    return eval(body)
+
+
+def test_header_is_up_to_date():
+    spec = importlib.util.spec_from_file_location("gen_tables", os.path.join(ROOT, "tools", "gen_tables.py"))
+    gt = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gt)
+    ent, diag = gt.generator_entries()
+    assert [list(e) for e in ent] == _macro("MISTI_GEN_ENTRIES_INIT")
+    assert [list(d) for d in diag] == _macro("MISTI_GEN_DIAG_INIT")
+    # the two state enumerations agree
+    for i, st in enumerate(gt.STATES):
+        assert sorted(st) == sorted(mo.STATES2[i])
+
+
+def test_generator_tables_match_oracle():
+    ent, diag = _macro("MISTI_GEN_ENTRIES_INIT"), _macro("MISTI_GEN_DIAG_INIT")
+    rng = np.random.default_rng(3)
+    for _ in range(5):
+        rate = rng.uniform(0.1, 3.0, 4)
+        M = np.zeros((44, 44))
+        for r, c, k, n in ent:
+            M[r, c] += n * rate[k]
+        for c in range(44):
+            M[c, c] -= sum(diag[c][k] * rate[k] for k in range(4))
+        assert np.max(np.abs(M - mo.generator_two_pop(*rate))) < 1e-13
+    ell = _macro("MISTI_ELL_INIT")
+    from_ell = sorted([r, c, k, n] for r in range(44) for (c, k, n) in ell[r] if n)
+    assert from_ell == sorted(ent)
+    assert all(len(row) == 4 for row in ell)
+
+
+def test_branch_counts_collapse_ancient():
+    assert np.array_equal(np.array(_macro("MISTI_W44_INIT")), mo.W44.astype(int))
+    assert np.array_equal(np.array(_macro("MISTI_W8_INIT")), mo.W8.astype(int))
+    col = _macro("MISTI_COLLAPSE_INIT")
+    b = mo.COLLAPSE_BOUNDS
+    assert col == [max(k for k in range(8) if b[k] <= i) for i in range(44)]
+    assert _macro("MISTI_STATIONARY_INIT") == mo.STATIONARY
+    P0 = np.random.default_rng(5).uniform(0, 1, 44)
+    out = np.zeros(44)
+    out[2] = sum(P0[i] for i in range(44) if _macro("MISTI_ANC2_INIT")[i])
+    out[11] = sum(P0[i] for i in range(44) if _macro("MISTI_ANC11_INIT")[i])
+    assert np.allclose(out, mo.ancient_sample_reset(P0), atol=1e-15)
+
+
+def test_pulse_tables():
+    for src in (0, 1):
+        ent = _macro("MISTI_PULSE%d_INIT" % src)
+        rp = _macro("MISTI_PULSE%d_ROWPTR_INIT" % src)
+        assert rp[0] == 0 and rp[44] == len(ent)
+        for r in (0.0, 0.05, 0.6, 1.0):
+            Pm = np.zeros((44, 44))
+            for row in range(44):
+                for e in ent[rp[row]:rp[row + 1]]:
+                    assert e[0] == row
+                    Pm[row, e[1]] += e[4] * (1 - r) ** e[2] * r ** e[3]
+            assert np.max(np.abs(Pm - mo.pulse_matrix(r, src))) < 1e-14
+            assert np.allclose(Pm.sum(axis=0), 1.0)
+
+
+def test_one_population_spectral_tables():
+    L = np.array(_macro("MISTI_L8_INIT"))
+    assert np.array_equal(L, mo.L8)
+    WG = [np.array(_macro("MISTI_WG%d_INIT" % a)) for a in (6, 3, 1)]
+    # W8 exp(x L8) P = sum_k exp(-a_k x) WG_k P
+    from scipy.linalg import expm
+    rng = np.random.default_rng(11)
+    for x in (0.0, 0.3, 2.5):
+        P = rng.uniform(0, 1, 8)
+        lhs = mo.W8 @ expm(x * L) @ P
+        rhs = sum(np.exp(-a * x) * (G @ P) for a, G in zip((6, 3, 1), WG))
+        assert np.max(np.abs(lhs - rhs)) < 1e-13
+
+
+def test_mirror_state_maps():
+    """misti_b200.populations.MapIndToState (host bookkeeping, no device call) enumerates the same states."""
+    from misti_b200.populations import OnePopulation, TwoPopulations
+    tp = TwoPopulations.__new__(TwoPopulations)
+    tp.Msize = 44
+    for i in range(44):
+        st = tp.MapIndToState(i)
+        assert sorted((l.d0, l.d1, l.pop) for l in st) == sorted(mo.STATES2[i])
+        assert tp.MapStateToInd(st) == i
+    op = OnePopulation.__new__(OnePopulation)
+    op.Msize = 8
+    for i in range(8):
+        assert sorted((l.d0, l.d1) for l in op.MapIndToState(i)) == sorted(mo.STATES1[i])
+        assert op.MapStateToInd(op.MapIndToState(i)) == i
