@@ -84,6 +84,8 @@ typedef struct misti_eval_io {
     int32_t* status;         /* [B]                                                                        */
     int32_t* nfev;           /* [B] residual evaluations spent in the correction (least_squares nfev sum)  */
     int32_t* terms;          /* [B] sparse mat-vecs spent in the JSFS stage                                 */
+    const int32_t* row_ids;  /* [B] score item b against data row row_ids[b] ONLY; llh is then [B] instead of
+                                [B][R] (one optimiser simplex per (bootstrap row, split time) pair)         */
 } misti_eval_io;
 
 int misti_abi_version(void);

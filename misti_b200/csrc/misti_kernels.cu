@@ -91,7 +91,7 @@ misti_jsfs_kernel(int B, int P, const double* __restrict__ params, const int* __
                   const ModelDesc* __restrict__ models, const double* __restrict__ times, const double* __restrict__ lc,
                   long stride, const double* __restrict__ cpost, const double* __restrict__ data, int R, int unfolded,
                   double* __restrict__ llh, double* __restrict__ jafs, double* __restrict__ jafs_raw, int* __restrict__ status,
-                  int* __restrict__ terms) {
+                  int* __restrict__ terms, const int* __restrict__ row_ids) {
     // one item per 16-lane half warp (3 of the 44 chain states per lane), two items per warp
     __shared__ double ysm_all[kJsfsWarps * 2][2 * misti::kYStride];
     const int half = threadIdx.x >> 4, lane = threadIdx.x & 15;
@@ -128,8 +128,13 @@ misti_jsfs_kernel(int B, int P, const double* __restrict__ params, const int* __
         }
         // fused composite likelihood over all data rows (bootstrap replicates): lanes stride the rows
         const double bad = (st == MISTI_NEGATIVE_PARAM || st == MISTI_CORRECTION_FAILED) ? -misti::kInf : nan("");
-        for (int r = lane; r < R; r += 16)
-            llh[(long)b * R + r] = st == MISTI_OK ? misti::score_row(data + 8 * (long)r, logj) : bad;
+        if (row_ids) {  // one data row per item
+            const int r = row_ids[b];
+            if (lane == 0) llh[b] = (st == MISTI_OK && r >= 0 && r < R) ? misti::score_row(data + 8 * (long)r, logj) : bad;
+        } else {
+            for (int r = lane; r < R; r += 16)
+                llh[(long)b * R + r] = st == MISTI_OK ? misti::score_row(data + 8 * (long)r, logj) : bad;
+        }
     }
 }
 
@@ -251,7 +256,7 @@ struct misti_ctx {
     size_t st_cap = 0, st_capR = 0, st_capP = 0;
     int st_numT = 0;
     double *s_params = nullptr, *s_llh = nullptr, *s_jafs = nullptr, *s_jafs_raw = nullptr;
-    int *s_model_ids = nullptr, *s_terms = nullptr;
+    int *s_model_ids = nullptr, *s_terms = nullptr, *s_row_ids = nullptr;
     double *s_lc_io = nullptr, *s_pr = nullptr;
     size_t s_lc_io_cap = 0, s_pr_cap = 0;
     double* d_small = nullptr;  // 44*44 + 2*44 doubles for the table export kernels
@@ -384,7 +389,7 @@ void misti_ctx_destroy(misti_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     void* ptrs[] = {ctx->d_times, ctx->d_lh, ctx->d_models, ctx->d_data, ctx->d_lc, ctx->d_cpost, ctx->d_status, ctx->d_nfev,
-                    ctx->s_params, ctx->s_llh, ctx->s_jafs, ctx->s_jafs_raw, ctx->s_model_ids, ctx->s_terms, ctx->s_lc_io,
+                    ctx->s_params, ctx->s_llh, ctx->s_jafs, ctx->s_jafs_raw, ctx->s_model_ids, ctx->s_terms, ctx->s_row_ids, ctx->s_lc_io,
                     ctx->s_pr, ctx->d_small};
     for (void* p : ptrs)
         if (p) cudaFree(p);
@@ -515,7 +520,8 @@ int misti_set_data(misti_ctx* ctx, int32_t R, const double* sfs, const double* l
 
 static int eval_chunk(misti_ctx* ctx, int B, int P, const double* d_params, const int* d_model_ids, int model_default,
                       unsigned flags, double mixture_th, const double* d_lc_inject, double* d_llh, double* d_jafs,
-                      double* d_jafs_raw, double* d_lc_out, double* d_pr, int* d_status_out, int* d_nfev_out, int* d_terms) {
+                      double* d_jafs_raw, double* d_lc_out, double* d_pr, int* d_status_out, int* d_nfev_out, int* d_terms,
+                      const int* d_row_ids) {
     int rc;
     if ((rc = ensure_batch(ctx, (size_t)B))) return rc;
     const long stride = (long)ctx->cap;
@@ -539,7 +545,7 @@ static int eval_chunk(misti_ctx* ctx, int B, int P, const double* d_params, cons
 #define MISTI_LAUNCH_JSFS(MINB)                                                                                          \
     misti_jsfs_kernel<MINB><<<blocks, kJsfsWarps * 32, 0, ctx->stream>>>(                                                 \
         B, P, d_params, d_model_ids, model_default, ctx->d_models, ctx->d_times, ctx->d_lc, stride, ctx->d_cpost, ctx->d_data, \
-        ctx->R, ctx->unfolded, d_llh, d_jafs, d_jafs_raw, ctx->d_status, d_terms)
+        ctx->R, ctx->unfolded, d_llh, d_jafs, d_jafs_raw, ctx->d_status, d_terms, d_row_ids)
     switch (ctx->jsfs_minb) {  // register budget per thread: 2 -> 255, 3 -> 168, 4 -> 128, 5 -> 96 (tuning knob MISTI_JSFS_MINB)
         case 2: MISTI_LAUNCH_JSFS(2); break;
         case 3: MISTI_LAUNCH_JSFS(3); break;
@@ -586,6 +592,7 @@ int misti_eval_batch(misti_ctx* ctx, int32_t B, int32_t P, const double* params,
     std::memset(&none, 0, sizeof(none));
     if (!io) io = &none;
     const int numT_max = ctx->numT_max, R = ctx->R;
+    const int Rl = io->row_ids ? 1 : R;  // llh entries per item
     const int Pe = P > 0 ? P : 1;
     static const double dummy_param = 0.0;
     (void)dummy_param;
@@ -595,11 +602,12 @@ int misti_eval_batch(misti_ctx* ctx, int32_t B, int32_t P, const double* params,
         for (long off = 0; off < B; off += kMaxChunk) {
             const int n = (int)((B - off) < kMaxChunk ? (B - off) : kMaxChunk);
             rc = eval_chunk(ctx, n, P, params ? params + off * P : nullptr, model_ids ? model_ids + off : nullptr, model_default,
-                            flags, mixture_th, io->lc_inject ? io->lc_inject + off * 2 * numT_max : nullptr, llh + off * R,
+                            flags, mixture_th, io->lc_inject ? io->lc_inject + off * 2 * numT_max : nullptr, llh + off * Rl,
                             io->jafs ? io->jafs + off * 7 : nullptr, io->jafs_raw ? io->jafs_raw + off * 7 : nullptr,
                             io->lc_out ? io->lc_out + off * 2 * numT_max : nullptr,
                             io->pr_out ? io->pr_out + off * (numT_max + 1) * 6 : nullptr, io->status ? io->status + off : nullptr,
-                            io->nfev ? io->nfev + off : nullptr, io->terms ? io->terms + off : nullptr);
+                            io->nfev ? io->nfev + off : nullptr, io->terms ? io->terms + off : nullptr,
+                            io->row_ids ? io->row_ids + off : nullptr);
             if (rc) return rc;
         }
         return 0;
@@ -622,6 +630,7 @@ int misti_eval_batch(misti_ctx* ctx, int32_t B, int32_t P, const double* params,
             if ((rc = realloc_exact(ctx, &ctx->s_jafs_raw, ncap * 7))) return rc;
             if ((rc = realloc_exact(ctx, &ctx->s_model_ids, ncap))) return rc;
             if ((rc = realloc_exact(ctx, &ctx->s_terms, ncap))) return rc;
+            if ((rc = realloc_exact(ctx, &ctx->s_row_ids, ncap))) return rc;
             ctx->st_cap = ncap; ctx->st_capR = nR; ctx->st_capP = nP; ctx->st_numT = numT_max;
         }
         const bool need_lc_io = io->lc_inject || io->lc_out;
@@ -631,6 +640,8 @@ int misti_eval_batch(misti_ctx* ctx, int32_t B, int32_t P, const double* params,
             CK(cudaMemcpyAsync(ctx->s_params, params + off * P, (size_t)n * P * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
         if (model_ids)
             CK(cudaMemcpyAsync(ctx->s_model_ids, model_ids + off, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        if (io->row_ids)
+            CK(cudaMemcpyAsync(ctx->s_row_ids, io->row_ids + off, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
         if (io->lc_inject)
             CK(cudaMemcpyAsync(ctx->s_lc_io, io->lc_inject + off * 2 * numT_max, (size_t)n * 2 * numT_max * sizeof(double),
                                cudaMemcpyHostToDevice, ctx->stream));
@@ -638,9 +649,10 @@ int misti_eval_batch(misti_ctx* ctx, int32_t B, int32_t P, const double* params,
         // lc_inject and lc_out share one staging buffer: the inject copy is consumed by K1 before the gather writes
         rc = eval_chunk(ctx, n, P, ctx->s_params, model_ids ? ctx->s_model_ids : nullptr, model_default, flags, mixture_th,
                         io->lc_inject ? ctx->s_lc_io : nullptr, ctx->s_llh, ctx->s_jafs, ctx->s_jafs_raw,
-                        io->lc_out ? ctx->s_lc_io : nullptr, io->pr_out ? ctx->s_pr : nullptr, nullptr, nullptr, ctx->s_terms);
+                        io->lc_out ? ctx->s_lc_io : nullptr, io->pr_out ? ctx->s_pr : nullptr, nullptr, nullptr, ctx->s_terms,
+                        io->row_ids ? ctx->s_row_ids : nullptr);
         if (rc) return rc;
-        CK(cudaMemcpyAsync(llh + off * R, ctx->s_llh, (size_t)n * R * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(llh + off * Rl, ctx->s_llh, (size_t)n * Rl * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
         if (io->jafs) CK(cudaMemcpyAsync(io->jafs + off * 7, ctx->s_jafs, (size_t)n * 7 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
         if (io->jafs_raw)
             CK(cudaMemcpyAsync(io->jafs_raw + off * 7, ctx->s_jafs_raw, (size_t)n * 7 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));

@@ -149,10 +149,11 @@ class Engine:
 
     # -- evaluation -----------------------------------------------------------------------------
     def evaluate(self, params, model=0, model_ids=None, flags=_lib.FLAG_CORRECT, mixtureTH=0.0, lc_inject=None,
-                 want=("jafs", "status"), buffers=None):
+                 want=("jafs", "status"), buffers=None, row_ids=None):
         """Host-buffer evaluation.  params: [B, P] (or [B] / [] for P = 0).  Returns a dict with
         'llh' [B, R] and the arrays named in `want` (jafs, jafs_raw, lc, pr, status, nfev, terms).
-        `buffers` may hold preallocated C-contiguous numpy arrays (e.g. views of pinned memory) to write into."""
+        `buffers` may hold preallocated C-contiguous numpy arrays (e.g. views of pinned memory) to write into.
+        With `row_ids` [B], item b is scored against data row row_ids[b] only and 'llh' is [B, 1]."""
         params = _as_f64(params)
         if params.ndim == 1:
             params = params.reshape(-1, 1) if params.size else params.reshape(1, 0)
@@ -173,8 +174,14 @@ class Engine:
             if a.dtype != dt or a.size != int(np.prod(shp)) or not a.flags["C_CONTIGUOUS"]:
                 raise ValueError("buffer %r has the wrong dtype/size/layout" % name)
             return a.reshape(shp)
-        out = {"llh": _buf("llh", (B, self.R), np.float64)}
         io = _lib.EvalIO()
+        rows = None
+        if row_ids is not None:
+            rows = np.ascontiguousarray(row_ids, dtype=np.int32).reshape(-1)
+            if rows.shape[0] != B or (B and (rows.min() < 0 or rows.max() >= self.R)):
+                raise ValueError("row_ids must hold one valid data row index per item")
+            io.row_ids = _ptr(rows)
+        out = {"llh": _buf("llh", (B, 1 if rows is not None else self.R), np.float64)}
         nT = self.numT_max
         if lc_inject is not None:
             inj = _as_f64(lc_inject).reshape(B, nT, 2)

@@ -202,6 +202,20 @@ class MigrationInference:
             f |= _lib.FLAG_UNFOLDED
         return f
 
+    def register_into(self, eng, grid_id=None):
+        """Register this object's grid (unless grid_id is given) and model layout in an Engine; returns
+        (grid_id, model_id).  Used by the object itself and by misti_b200.sweep for shared engines."""
+        gid = eng.add_grid(self.times, self.lh) if grid_id is None else grid_id
+        bands, pulses, k = [], [], 0
+        # optimiser index order = MapParameters order: optimised bands first, then optimised pulses
+        for pop, a, b, val, opt in self._bands:
+            bands.append((pop, a, min(b, self.numT), val, k if opt else -1))
+            k += 1 if opt else 0
+        for pop, t, val, opt in self._pulses:
+            pulses.append((pop, t, val, k if opt else -1))
+            k += 1 if opt else 0
+        return gid, eng.add_model(gid, self.splitT, self.sampleDate, bands, pulses)
+
     def _sync_engine(self):
         if self._engine is None:
             self._engine = Engine(self._device)
@@ -210,16 +224,7 @@ class MigrationInference:
             if not self._owns_engine:
                 raise RuntimeError("a shared Engine must be populated by its owner (use misti_b200.sweep)")
             eng.clear_models()
-            gid = eng.add_grid(self.times, self.lh)
-            bands, pulses, k = [], [], 0
-            # optimiser index order = MapParameters order: optimised bands first, then optimised pulses
-            for pop, a, b, val, opt in self._bands:
-                bands.append((pop, a, min(b, self.numT), val, k if opt else -1))
-                k += 1 if opt else 0
-            for pop, t, val, opt in self._pulses:
-                pulses.append((pop, t, val, k if opt else -1))
-                k += 1 if opt else 0
-            self._model_id = eng.add_model(gid, self.splitT, self.sampleDate, bands, pulses)
+            _, self._model_id = self.register_into(eng)
             self._registered = True
             self._data_dirty = True
         if self._data_dirty:

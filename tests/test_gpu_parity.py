@@ -204,3 +204,49 @@ def test_fit_matches_reference(golden_datasets, golden_fits):
     exp = fit["expect"]
     assert relerr(sol[0], exp["x"]) < 1e-6
     assert relerr(sol[1], exp["llh"]) < TOL
+
+
+def test_sweep_lockstep_fits(engine, golden_datasets, golden_fits):
+    """misti_b200.sweep: several (split time x data row) Nelder-Mead fits advanced in lock step reproduce the
+    reference's serial fits (golden fits: same x, llh and scipy evaluation count)."""
+    from misti_b200.sweep import Sweep
+    ds = golden_datasets["synthetic"]
+    rows = [ds["sfs"]] + ds["bs_rows"][:3]
+    sw = Sweep(ds["times"], ds["lambdas"], rows, unfolded=True, cpfit=True, smooth=True, engine=engine)
+    m_c2 = sw.add_model(40, [[2, 5, 12, 0.8, 1]])
+    m_c3 = sw.add_model(40, [[1, 2, 10, 0.3, 1], [2, 5, 12, 0.8, 1]], [[1, 7, 0.05, 1]])
+    m_fix = sw.add_model(40)
+    res = sw.solve(tol=1e-4)
+    assert len(res["llh"]) == 3 * len(rows)
+    by = {(int(m), int(r)): k for k, (m, r) in enumerate(zip(res["model"], res["row"]))}
+    for fit, m in ((golden_fits[0], m_c2), (golden_fits[2], m_c3)):
+        k = by[(m, 0)]
+        exp = fit["expect"]
+        P = len(exp["x"])
+        assert res["nfev"][k] == len(exp["calls"]), fit["name"]
+        assert np.allclose(res["x"][k][:P], exp["x"], rtol=1e-6, atol=1e-9), fit["name"]
+        assert relerr(res["llh"][k], exp["llh"]) < TOL, fit["name"]
+    # fixed model: plain evaluation per row; bootstrap rows give different likelihoods from the same spectrum
+    ks = [by[(m_fix, r)] for r in range(len(rows))]
+    assert len(set(np.round(res["llh"][ks], 3))) == len(rows)
+    line = sw.result_line(res, by[(m_c2, 0)])
+    assert line.startswith("bs_id = 0 \tsplitT = 40 \ttime = ") and "\tmigration rates optim = [" in line and "\tllh = " in line
+    # the two-phase (non-speculative) schedule takes the same decisions
+    res2 = sw.solve(pairs=[(m_c2, 0), (m_c2, 2)], tol=1e-4, speculative=False)
+    assert np.array_equal(res2["x"][0], res["x"][by[(m_c2, 0)]]) and res2["nfev"][1] == res["nfev"][by[(m_c2, 2)]]
+    assert res2["evaluations"] < res["evaluations"]
+
+
+def test_per_item_data_rows(engine, golden_datasets):
+    ds = golden_datasets["synthetic"]
+    rows = [ds["sfs"]] + ds["bs_rows"]
+    engine.clear_models()
+    gid = engine.add_grid(ds["times"], ds["lambdas"])
+    mid = engine.add_model(gid, 40, 0, bands=[(1, 5, 12, 0.8, 0)])
+    engine.set_data(rows, True)
+    params = np.linspace(0.1, 2.0, 9).reshape(-1, 1)
+    full = engine.evaluate(params, model=mid, flags=1 | 2 | 4)["llh"]
+    rid = np.arange(9) % len(rows)
+    one = engine.evaluate(params, model=mid, flags=1 | 2 | 4, row_ids=rid)["llh"]
+    assert one.shape == (9, 1)
+    assert np.array_equal(one[:, 0], full[np.arange(9), rid])
