@@ -211,7 +211,7 @@ def test_sweep_lockstep_fits(engine, golden_datasets, golden_fits):
     reference's serial fits (golden fits: same x, llh and scipy evaluation count)."""
     from misti_b200.sweep import Sweep
     ds = golden_datasets["synthetic"]
-    rows = [ds["sfs"]] + ds["bs_rows"][:3]
+    rows = [ds["sfs"]] + ds["bs_rows"][1:4]
     sw = Sweep(ds["times"], ds["lambdas"], rows, unfolded=True, cpfit=True, smooth=True, engine=engine)
     m_c2 = sw.add_model(40, [[2, 5, 12, 0.8, 1]])
     m_c3 = sw.add_model(40, [[1, 2, 10, 0.3, 1], [2, 5, 12, 0.8, 1]], [[1, 7, 0.05, 1]])
