@@ -125,7 +125,20 @@ static const RecipTable h_recip = RecipTable();
 constexpr int kYStride = 48;                    // doubles per ping-pong buffer (44 states + pad rows)
 constexpr double kUnifMaxStep = 32.0;           // largest q*T handled in one uniformisation sweep
 constexpr double kUnifTol = 1.3877787807814457e-17;  // 2^-56: truncation of the Poisson tail
-constexpr double kUnifMaxStiff = 131072.0;       // q*T beyond this is reported as MISTI_STIFF (4096 sweeps)
+constexpr double kUnifMaxStiff = 256.0;         // q*T beyond this (8 sweeps) goes to the dense scaling-and-squaring step
+
+// Continuation record of an item whose next two-population interval is too stiff for the uniformisation sweep
+// (rates ~1e5..1e8 after a run-away correction): the state at the START of interval `it` (before the ancient
+// reset / pulse of that interval).  misti_stiff_kernel advances it over the stiff interval(s) with a dense
+// scaling-and-squaring step; the JSFS kernel then resumes from it.
+struct Cont {
+    int it;
+    int nterms;
+    int pad_[2];
+    double P[48];
+    double Ia[48];
+    double Ib[48];
+};
 constexpr int kUnifMaxTerms = MISTI_RECIP_N - 4;     // never reached for q*T <= 32 (about 110 terms)
 
 // Post-split coefficients (run by ONE thread; lc addressed like in correct_lambdas_item):
@@ -163,9 +176,12 @@ MISTI_HD inline void post_split_coeffs(const ModelDesc& md, const double* times,
 // `active` = false for a group without work); `ysm` is a scratch area of 2*kYStride doubles private to the
 // group (two ping-pong copies of the 44-vector, padded to 48 so that every lane has a slot to write).  On return every lane of the group holds the UNNORMALISED spectrum in jafs[0..6]
 // (MigrationInference.JAFSpectrum's return value) and the number of mat-vecs in *terms.
+// `cont` (nullable): where to park the item when it meets a stiff interval (return value MISTI_STIFF = "pending");
+// `resume`: start from the record instead of from the sampling configuration.
 template <class G, int PITCH>
 MISTI_D inline int jsfs_item(const G& g, const ModelDesc& md, bool active, const double* times, const double* params,
-                             const double* lc, long stride, const double* cpost, double* ysm, double* jafs, int* terms) {
+                             const double* lc, long stride, const double* cpost, double* ysm, double* jafs, int* terms,
+                             Cont* cont = nullptr, bool resume = false) {
     constexpr int RPL = (44 + G::LANES - 1) / G::LANES;
     constexpr int W = MISTI_ELL_WIDTH;
     const int lane = g.lane();
@@ -197,6 +213,19 @@ MISTI_D inline int jsfs_item(const G& g, const ModelDesc& md, bool active, const
     }
     int nterms = 0;
     int status = MISTI_OK;
+    int it0 = 0;
+    if (resume && active && cont) {
+        it0 = cont->it;
+        nterms = cont->nterms;
+#pragma unroll
+        for (int s = 0; s < RPL; ++s) {
+            const int r = lane + s * G::LANES;
+            P[s] = valid[s] ? cont->P[r] : 0.0;
+            Ia[s] = valid[s] ? cont->Ia[r] : 0.0;
+            Ib[s] = valid[s] ? cont->Ib[r] : 0.0;
+        }
+    }
+    bool pending = false;
     const int numT = md.numT;
     const int n2 = !active ? 0 : (md.splitT < numT ? md.splitT : numT);  // two-population intervals of this item
     const bool inf_last = active && md.splitT >= numT;                    // ... the last of which is then infinite
@@ -302,16 +331,31 @@ MISTI_D inline int jsfs_item(const G& g, const ModelDesc& md, bool active, const
         }
     };
 
-    const int n_loop = g.wmax(n_fin);
-    for (int it = 0; it < n_loop; ++it) {
-        const bool act = it < n_fin;  // a group past its own last interval idles on a zero-length interval
-        reset_and_pulse(it, act);
+    const int n_loop = g.wmax(n_fin > it0 ? n_fin - it0 : 0);
+    for (int j = 0; j < n_loop; ++j) {
+        const int it = it0 + j;
+        bool act = !pending && it < n_fin;  // a group past its own last interval idles on a zero-length interval
         set_generator(it, act);
         double T = act ? times[it] : 0.0;
         if (!(T >= 0.0 && T <= DBL_MAX)) { status = MISTI_NONFINITE; T = 0.0; }
-        // rates of 1e5 and more per unit of interval length only come out of a run-away correction; the
-        // sweep count is bounded rather than letting one item stall its warp for seconds
-        if (q * T > kUnifMaxStiff) { status = MISTI_STIFF; T = 0.0; }
+        // rates of 1e5 and more per unit of interval length only come out of a run-away correction; such an interval
+        // is not swept here (it would stall the warp for millions of terms): the item is parked for the dense step
+        if (q * T > kUnifMaxStiff) {
+            if (cont) {
+                if (lane == 0) { cont->it = it; cont->nterms = nterms; }
+#pragma unroll
+                for (int s = 0; s < RPL; ++s) {
+                    const int r = lane + s * G::LANES;
+                    if (r < 48) { cont->P[r] = P[s]; cont->Ia[r] = Ia[s]; cont->Ib[r] = Ib[s]; }
+                }
+                pending = true;
+            } else {
+                status = MISTI_STIFF;
+            }
+            act = false;
+            T = 0.0;
+        }
+        reset_and_pulse(it, act);
         const double qT = q * T;
         const int nsub = g.wmax(qT > kUnifMaxStep ? (int)ceil(qT / kUnifMaxStep) : 1);
         const double lam = nsub == 1 ? qT : qT / nsub;
@@ -371,14 +415,15 @@ MISTI_D inline int jsfs_item(const G& g, const ModelDesc& md, bool active, const
             for (int s = 0; s < RPL; ++s) Ib[s] = fma(Iint[s], qinv, Ib[s]);
         }
     }
-    if (g.any(inf_last)) {
+    if (g.any(inf_last && !pending)) {
         // no split inside the grid: the last two-population interval is infinite (MigrationInference.py:475-476,
         // 535-538): P1 = 0, integralP = -inv(M) P0 = (1/q) sum_k A^k P0, finite only with migration.
         const int it = numT - 1;
-        reset_and_pulse(it, inf_last);
-        set_generator(it, inf_last);
-        if (inf_last && !mig && status == MISTI_OK) status = MISTI_INFINITE_COAL_TIME;
-        const bool run = inf_last && mig;
+        const bool inf_now = inf_last && !pending;
+        reset_and_pulse(it, inf_now);
+        set_generator(it, inf_now);
+        if (inf_now && !mig && status == MISTI_OK) status = MISTI_INFINITE_COAL_TIME;
+        const bool run = inf_now && mig;
         double yk[RPL], Iint[RPL];
         g.sync();
 #pragma unroll
@@ -488,7 +533,7 @@ MISTI_D inline int jsfs_item(const G& g, const ModelDesc& md, bool active, const
         for (int c = 0; c < 7; ++c) jafs[c] = g.sum(jl[c]);
     }
     *terms = nterms;
-    return status;
+    return pending ? MISTI_STIFF : status;
 }
 
 // Normalised spectrum -> log terms used by the composite likelihood (MigrationInference.py:583-613).

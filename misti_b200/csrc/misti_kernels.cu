@@ -91,26 +91,37 @@ misti_jsfs_kernel(int B, int P, const double* __restrict__ params, const int* __
                   const ModelDesc* __restrict__ models, const double* __restrict__ times, const double* __restrict__ lc,
                   long stride, const double* __restrict__ cpost, const double* __restrict__ data, int R, int unfolded,
                   double* __restrict__ llh, double* __restrict__ jafs, double* __restrict__ jafs_raw, int* __restrict__ status,
-                  int* __restrict__ terms, const int* __restrict__ row_ids) {
+                  int* __restrict__ terms, const int* __restrict__ row_ids, misti::Cont* __restrict__ conts,
+                  const int* __restrict__ item_list, const int* __restrict__ item_count, int* __restrict__ next_list,
+                  int* __restrict__ next_count) {
     // one item per 16-lane half warp (3 of the 44 chain states per lane), two items per warp
     __shared__ double ysm_all[kJsfsWarps * 2][2 * misti::kYStride];
     const int half = threadIdx.x >> 4, lane = threadIdx.x & 15;
     double* ysm = ysm_all[half];
     const misti::HalfWarpLanes g;
     const int ngroups = gridDim.x * kJsfsWarps * 2;
+    // first pass: all B items; resume pass: the items parked by the previous pass and advanced by misti_stiff_kernel
+    const bool resume = item_list != nullptr;
+    const int n_items = resume ? *item_count : B;
     // both halves of a warp walk the item list together (lock step); the odd one out re-reads the last item
-    for (int b0 = blockIdx.x * kJsfsWarps * 2 + (half & ~1); b0 < B; b0 += ngroups) {
-        const bool has = b0 + (half & 1) < B;
-        const int b = has ? b0 + (half & 1) : B - 1;
+    for (int i0 = blockIdx.x * kJsfsWarps * 2 + (half & ~1); i0 < n_items; i0 += ngroups) {
+        const bool has = i0 + (half & 1) < n_items;
+        const int i = has ? i0 + (half & 1) : n_items - 1;
+        const int b = resume ? item_list[i] : i;
         const ModelDesc& md = models[model_ids ? model_ids[b] : model_default];
         int st = status[b];
+        if (resume && st == MISTI_STIFF) st = MISTI_OK;  // parked by the previous pass, advanced by misti_stiff_kernel
         double raw[7], jn[7], logj[7];
         int nt = 0;
         const double cp[3] = {cpost[b], cpost[stride + b], cpost[2 * stride + b]};
-        const int js = misti::jsfs_item<misti::HalfWarpLanes, kPitch>(g, md, has && st == MISTI_OK, times + md.grid_off, params + (long)b * P, lc + b, stride,
-                                        cp, ysm, raw, &nt);
+        const int js = misti::jsfs_item<misti::HalfWarpLanes, kPitch>(g, md, has && st == MISTI_OK, times + md.grid_off,
+                                                                      params + (long)b * P, lc + b, stride, cp, ysm, raw, &nt,
+                                                                      conts ? conts + b : nullptr, resume);
         if (!has) continue;
         if (st == MISTI_OK) st = js;
+        if (st == MISTI_STIFF && conts && next_list) {  // parked: queue it for the dense step; results come from a later pass
+            if (lane == 0) next_list[atomicAdd(next_count, 1)] = b;
+        }
         if (st == MISTI_OK && !misti::jafs_normalise_logs(raw, unfolded != 0, jn, logj)) st = MISTI_NONFINITE;
         if (st != MISTI_OK)
             for (int c = 0; c < 7; ++c) raw[c] = jn[c] = nan("");
@@ -135,6 +146,218 @@ misti_jsfs_kernel(int B, int P, const double* __restrict__ params, const int* __
             for (int r = lane; r < R; r += 16)
                 llh[(long)b * R + r] = st == MISTI_OK ? misti::score_row(data + 8 * (long)r, logj) : bad;
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Dense step for stiff intervals: one BLOCK per parked item.  exp(M~ T) of the Van Loan augmented generator
+// M~ = [[M, P0], [0, 0]] (45x45, padded to 48) by scaling and squaring of the UNIFORMISED matrix: for
+// T' = T / 2^s with q T' <= 1/2 the series E = sum_k Pois(k; q T') A~^k (A~ = I + M~/q >= 0, sparse x dense
+// products) is summed in shared memory, then squared s times with FP64 tensor-core MMAs (mma.sync m8n8k4.f64,
+// "DMMA").  Every matrix stays non-negative, so the squarings are free of cancellation.  Then
+// P1 = E11 P0 and integralP = last column of E (MigrationInference.SolveDifEq, :530-540).
+// ------------------------------------------------------------------------------------------------
+constexpr int kStiffThreads = 128;
+constexpr int kStiffRounds = 2;    // an item may be parked (and resumed) this many times per evaluation
+constexpr int kLd = 50;  // leading dimension of the 48x48 matrices in shared memory (bank spread)
+
+constexpr int kStiffSmem = (3 * 48 * 50 + 192 + 192) * (int)sizeof(double);
+
+__device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+// C = A * A for 48x48 (ld = kLd) matrices in shared memory; 4 warps x 9 tiles of 8x8 each
+__device__ void dense_square(const double* __restrict__ A, double* __restrict__ C) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int gid = lane >> 2, tig = lane & 3;
+    for (int t = warp; t < 36; t += kStiffThreads / 32) {
+        const int ti = t / 6, tj = t % 6;
+        double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+        for (int kk = 0; kk < 12; ++kk) {
+            const double a = A[(8 * ti + gid) * kLd + 4 * kk + tig];
+            const double b = A[(4 * kk + tig) * kLd + 8 * tj + gid];
+            dmma_m8n8k4(c0, c1, a, b);
+        }
+        C[(8 * ti + gid) * kLd + 8 * tj + 2 * tig] = c0;
+        C[(8 * ti + gid) * kLd + 8 * tj + 2 * tig + 1] = c1;
+    }
+}
+
+__global__ void __launch_bounds__(kStiffThreads)
+misti_stiff_kernel(int P, const double* __restrict__ params, const int* __restrict__ model_ids, int model_default,
+                   const ModelDesc* __restrict__ models, const double* __restrict__ times, const double* __restrict__ lc,
+                   long stride, misti::Cont* __restrict__ conts, const int* __restrict__ item_list,
+                   const int* __restrict__ item_count, int* __restrict__ status) {
+    extern __shared__ double sm[];
+    double* E = sm;                      // [48][kLd]
+    double* Y = sm + 48 * kLd;           // [48][kLd]
+    double* Z = sm + 2 * 48 * kLd;       // [48][kLd]
+    double* vec = sm + 3 * 48 * kLd;     // P[48], tmp[48], adiag[48], aug[48], coef[48][4]
+    double* Pv = vec; double* tmp = vec + 48; double* adiag = vec + 96; double* aug = vec + 144; double* coef = vec + 192;
+    __shared__ double s_scal[4];
+    __shared__ int s_flag[2];
+    const int tid = threadIdx.x;
+    const int n_items = *item_count;
+    for (int i = blockIdx.x; i < n_items; i += gridDim.x) {
+        const int b = item_list[i];
+        const ModelDesc& md = models[model_ids ? model_ids[b] : model_default];
+        const double* par = params + (long)b * P;
+        const double* tt = times + md.grid_off;
+        misti::Cont* ct = conts + b;
+        const int numT = md.numT;
+        const int n2 = md.splitT < numT ? md.splitT : numT;
+        const int n_fin = md.splitT >= numT ? n2 - 1 : n2;
+        int it = ct->it;
+        int nterms = ct->nterms;
+        if (tid < 48) Pv[tid] = ct->P[tid];
+        __syncthreads();
+        int st = MISTI_OK;
+        while (it < n_fin) {
+            const double la0 = lc[(kPitch * it) * stride + b], la1 = lc[(kPitch * it + 1) * stride + b];
+            const double m0 = lc[(kPitch * it + 2) * stride + b], m1 = lc[(kPitch * it + 3) * stride + b];
+            const double T = tt[it];
+            const double rate[4] = {la0, la1, m0, m1};
+            // q = max |M_cc|
+            if (tid < 48) {
+                double d = 0.0;
+                if (tid < 44)
+                    for (int k = 0; k < 4; ++k) d += (double)misti::d_diag[tid][k] * rate[k];
+                tmp[tid] = d;
+            }
+            __syncthreads();
+            if (tid == 0) {
+                double q = 0.0;
+                for (int r = 0; r < 44; ++r) q = tmp[r] > q ? tmp[r] : q;
+                const bool bad = !(q > 0.0 && q <= DBL_MAX && T >= 0.0 && T <= DBL_MAX);
+                s_scal[0] = bad ? 1.0 : q;
+                s_flag[0] = bad ? 1 : 0;
+                s_flag[1] = (!bad && q * T > misti::kUnifMaxStiff) ? 1 : 0;  // still stiff?
+            }
+            __syncthreads();
+            if (s_flag[0]) { st = MISTI_NONFINITE; break; }
+            if (!s_flag[1]) break;  // an ordinary interval: back to the sweep kernel
+            const double q = s_scal[0], qinv = 1.0 / q;
+            // ancient-sample reset (TwoPopulations.py:246-262) and pulse (:361-377) of this interval
+            if (it == md.sampleDate && it > 0) {
+                if (tid == 0) {
+                    double a2 = 0.0, a11 = 0.0;
+                    for (int r = 0; r < 44; ++r) {
+                        if (misti::d_anc2[r]) a2 += Pv[r];
+                        if (misti::d_anc11[r]) a11 += Pv[r];
+                    }
+                    for (int r = 0; r < 44; ++r) Pv[r] = 0.0;
+                    Pv[2] = a2; Pv[11] = a11;
+                }
+                __syncthreads();
+            }
+            if (md.n_pulses > 0) {
+                const double pu0 = misti::pulse_rate(md, par, it, 0), pu1 = misti::pulse_rate(md, par, it, 1);
+                if (pu0 + pu1 > 0) {
+                    const double pr = pu0 + pu1;
+                    const int src = pu0 > 0 ? 0 : 1;
+                    const misti::PulseEntry* ent = src == 0 ? misti::d_pulse0 : misti::d_pulse1;
+                    const unsigned char* rp = src == 0 ? misti::d_pulse0_rowptr : misti::d_pulse1_rowptr;
+                    if (tid < 44) {
+                        double acc = 0.0;
+                        for (int e = rp[tid]; e < rp[tid + 1]; ++e) {
+                            const misti::PulseEntry pe = ent[e];
+                            acc += (double)pe.mult * pow(1.0 - pr, (double)pe.a) * pow(pr, (double)pe.b) * Pv[pe.col];
+                        }
+                        tmp[tid] = acc;
+                    }
+                    __syncthreads();
+                    if (tid < 44) Pv[tid] = tmp[tid];
+                    __syncthreads();
+                }
+            }
+            // uniformised augmented generator
+            if (tid < 48) {
+                double d = 0.0;
+                if (tid < 44)
+                    for (int k = 0; k < 4; ++k) d += (double)misti::d_diag[tid][k] * rate[k];
+                adiag[tid] = tid < 44 ? (q - d) * qinv : (tid == 44 ? 1.0 : 0.0);
+                aug[tid] = tid < 44 ? Pv[tid] * qinv : 0.0;
+                for (int e = 0; e < 4; ++e) {
+                    double c = 0.0;
+                    if (tid < 44) {
+                        const misti::EllEntry en = misti::d_ell[tid][e];
+                        c = (double)en.cnt * rate[en.kind] * qinv;
+                    }
+                    coef[tid * 4 + e] = c;
+                }
+            }
+            // scaling: q T / 2^s <= 1/2
+            const double qT = q * T;
+            int sq = 0;
+            double lam = qT;
+            while (lam > 0.5) { lam *= 0.5; ++sq; }
+            // E = sum_k Pois(k; lam) A~^k,  Y_k = A~ Y_(k-1), Y_0 = I
+            const double p0 = exp(-lam);
+            for (int idx = tid; idx < 48 * kLd; idx += kStiffThreads) {
+                const int r = idx / kLd, c = idx % kLd;
+                const double v = (r == c && r < 45) ? 1.0 : 0.0;
+                Y[idx] = v;
+                E[idx] = p0 * v;
+            }
+            __syncthreads();
+            double p = p0, rr = lam;
+            int k = 0;
+            double* Ya = Y; double* Yb = Z;
+            while (true) {
+                ++k;
+                p *= rr;
+                rr = lam / (k + 1);
+                for (int idx = tid; idx < 45 * 48; idx += kStiffThreads) {
+                    const int r = idx / 48, c = idx % 48;
+                    double acc;
+                    if (r < 44) {
+                        acc = adiag[r] * Ya[r * kLd + c];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) acc += coef[r * 4 + e] * Ya[misti::d_ell[r][e].col * kLd + c];
+                        acc += aug[r] * Ya[44 * kLd + c];
+                    } else {
+                        acc = Ya[44 * kLd + c];
+                    }
+                    Yb[r * kLd + c] = acc;
+                    E[r * kLd + c] += p * acc;
+                }
+                __syncthreads();
+                double* t = Ya; Ya = Yb; Yb = t;
+                if (rr < 1.0 && p < misti::kUnifTol * (1.0 - rr)) break;
+                if (k > 200) { st = MISTI_NONFINITE; break; }
+            }
+            nterms += k;
+            // squarings (DMMA): E <- E E, sq times
+            double* Ea = E; double* Eb = Ya;  // Ya is free now (Yb too)
+            for (int j = 0; j < sq; ++j) {
+                dense_square(Ea, Eb);
+                __syncthreads();
+                double* t = Ea; Ea = Eb; Eb = t;
+            }
+            // P1 = E11 P0, integral = E[:, 44]
+            if (tid < 44) {
+                double acc = 0.0;
+                for (int c = 0; c < 44; ++c) acc += Ea[tid * kLd + c] * Pv[c];
+                tmp[tid] = acc;
+                const double I = Ea[tid * kLd + 44];
+                if (it < md.sampleDate) ct->Ia[tid] += I;
+                else ct->Ib[tid] += I;
+            }
+            __syncthreads();
+            if (tid < 44) Pv[tid] = tmp[tid];
+            __syncthreads();
+            ++it;
+            if (st != MISTI_OK) break;
+        }
+        if (tid < 48) ct->P[tid] = tid < 44 ? Pv[tid] : 0.0;
+        if (tid == 0) {
+            ct->it = it;
+            ct->nterms = nterms;
+            if (st != MISTI_OK) { status[b] = st; ct->it = -1; }
+        }
+        __syncthreads();
     }
 }
 
@@ -252,6 +475,9 @@ struct misti_ctx {
     int cap_numT = 0;
     double *d_lc = nullptr, *d_cpost = nullptr;
     int *d_status = nullptr, *d_nfev = nullptr;
+    misti::Cont* d_conts = nullptr;       // continuation records of parked (stiff) items
+    int *d_queue[2] = {nullptr, nullptr}; // item lists of the stiff rounds
+    int* d_counts = nullptr;              // their lengths (one counter per round)
     // staging for host-pointer calls
     size_t st_cap = 0, st_capR = 0, st_capP = 0;
     int st_numT = 0;
@@ -346,6 +572,10 @@ int ensure_batch(misti_ctx* ctx, size_t B) {
     if ((rc = realloc_exact(ctx, &ctx->d_cpost, ncap * 3))) return rc;
     if ((rc = realloc_exact(ctx, &ctx->d_status, ncap))) return rc;
     if ((rc = realloc_exact(ctx, &ctx->d_nfev, ncap))) return rc;
+    if ((rc = realloc_exact(ctx, &ctx->d_conts, ncap))) return rc;
+    if ((rc = realloc_exact(ctx, &ctx->d_queue[0], ncap))) return rc;
+    if ((rc = realloc_exact(ctx, &ctx->d_queue[1], ncap))) return rc;
+    if (!ctx->d_counts && (rc = realloc_exact(ctx, &ctx->d_counts, (size_t)8))) return rc;
     ctx->cap = ncap;
     ctx->cap_numT = ctx->numT_max;
     return 0;
@@ -375,6 +605,10 @@ int misti_ctx_create(int device, void* stream, misti_ctx** out) {
         if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return MISTI_E_CUDA; }
         ctx->own_stream = true;
     }
+    if (cudaFuncSetAttribute(misti_stiff_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStiffSmem) != cudaSuccess) {
+        delete ctx;
+        return MISTI_E_CUDA;
+    }
     if (const char* e = getenv("MISTI_JSFS_MINB")) ctx->jsfs_minb = atoi(e);
     if (const char* e = getenv("MISTI_CORRECT_MINB")) ctx->correct_minb = atoi(e);
     for (int i = 0; i < 3; ++i)
@@ -388,7 +622,7 @@ void misti_ctx_destroy(misti_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    void* ptrs[] = {ctx->d_times, ctx->d_lh, ctx->d_models, ctx->d_data, ctx->d_lc, ctx->d_cpost, ctx->d_status, ctx->d_nfev,
+    void* ptrs[] = {ctx->d_times, ctx->d_lh, ctx->d_models, ctx->d_data, ctx->d_lc, ctx->d_cpost, ctx->d_status, ctx->d_nfev, ctx->d_conts, ctx->d_queue[0], ctx->d_queue[1], ctx->d_counts,
                     ctx->s_params, ctx->s_llh, ctx->s_jafs, ctx->s_jafs_raw, ctx->s_model_ids, ctx->s_terms, ctx->s_row_ids, ctx->s_lc_io,
                     ctx->s_pr, ctx->d_small};
     for (void* p : ptrs)
@@ -542,21 +776,40 @@ static int eval_chunk(misti_ctx* ctx, int B, int P, const double* d_params, cons
     int blocks = (B + 2 * kJsfsWarps - 1) / (2 * kJsfsWarps);
     const int max_blocks = ctx->sm_count * 16;
     if (blocks > max_blocks) blocks = max_blocks;
-#define MISTI_LAUNCH_JSFS(MINB)                                                                                          \
-    misti_jsfs_kernel<MINB><<<blocks, kJsfsWarps * 32, 0, ctx->stream>>>(                                                 \
+    CK(cudaMemsetAsync(ctx->d_counts, 0, 8 * sizeof(int), ctx->stream));
+#define MISTI_LAUNCH_JSFS(MINB, GRID, LIST, COUNT, NEXT, NEXTCOUNT)                                                       \
+    misti_jsfs_kernel<MINB><<<GRID, kJsfsWarps * 32, 0, ctx->stream>>>(                                                   \
         B, P, d_params, d_model_ids, model_default, ctx->d_models, ctx->d_times, ctx->d_lc, stride, ctx->d_cpost, ctx->d_data, \
-        ctx->R, ctx->unfolded, d_llh, d_jafs, d_jafs_raw, ctx->d_status, d_terms, d_row_ids)
-    switch (ctx->jsfs_minb) {  // register budget per thread: 2 -> 255, 3 -> 168, 4 -> 128, 5 -> 96 (tuning knob MISTI_JSFS_MINB)
-        case 2: MISTI_LAUNCH_JSFS(2); break;
-        case 3: MISTI_LAUNCH_JSFS(3); break;
-        case 5: MISTI_LAUNCH_JSFS(5); break;
-        default: MISTI_LAUNCH_JSFS(kJsfsMinBlocks); break;
+        ctx->R, ctx->unfolded, d_llh, d_jafs, d_jafs_raw, ctx->d_status, d_terms, d_row_ids, ctx->d_conts, LIST, COUNT, NEXT, \
+        NEXTCOUNT)
+#define MISTI_LAUNCH_JSFS_ANY(GRID, LIST, COUNT, NEXT, NEXTCOUNT)                                                          \
+    switch (ctx->jsfs_minb) { /* register budget: 2 -> 255, 3 -> 168, 4 -> 128, 5 -> 96 (tuning knob MISTI_JSFS_MINB) */   \
+        case 2: MISTI_LAUNCH_JSFS(2, GRID, LIST, COUNT, NEXT, NEXTCOUNT); break;                                           \
+        case 3: MISTI_LAUNCH_JSFS(3, GRID, LIST, COUNT, NEXT, NEXTCOUNT); break;                                           \
+        case 5: MISTI_LAUNCH_JSFS(5, GRID, LIST, COUNT, NEXT, NEXTCOUNT); break;                                           \
+        default: MISTI_LAUNCH_JSFS(kJsfsMinBlocks, GRID, LIST, COUNT, NEXT, NEXTCOUNT); break;                             \
     }
-#undef MISTI_LAUNCH_JSFS
+    // pass 0: every item; items that meet a stiff interval are parked in queue 0
+    MISTI_LAUNCH_JSFS_ANY(blocks, (const int*)nullptr, (const int*)nullptr, ctx->d_queue[0], ctx->d_counts);
     CK(cudaGetLastError());
+    ctx->launches += 1;
+    // stiff rounds: dense scaling-and-squaring step for the parked items, then resume the sweep for them.  The grids
+    // are fixed; with an empty queue (the usual case) both kernels return at once.
+    for (int r = 0; r < kStiffRounds; ++r) {
+        misti_stiff_kernel<<<ctx->sm_count, kStiffThreads, kStiffSmem, ctx->stream>>>(
+            P, d_params, d_model_ids, model_default, ctx->d_models, ctx->d_times, ctx->d_lc, stride, ctx->d_conts,
+            ctx->d_queue[r & 1], ctx->d_counts + r, ctx->d_status);
+        CK(cudaGetLastError());
+        MISTI_LAUNCH_JSFS_ANY(ctx->sm_count * 2, (const int*)ctx->d_queue[r & 1], (const int*)(ctx->d_counts + r),
+                              ctx->d_queue[(r + 1) & 1], ctx->d_counts + r + 1);
+        CK(cudaGetLastError());
+        ctx->launches += 2;
+    }
+#undef MISTI_LAUNCH_JSFS_ANY
+#undef MISTI_LAUNCH_JSFS
     CK(cudaEventRecord(ctx->ev[2], ctx->stream));
     ctx->ev_valid = true;
-    ctx->launches += 2;
+    ctx->launches += 1;
     if (d_lc_out) {
         const long n = (long)B * 2 * numT_max;
         misti_gather_lc_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(B, numT_max, d_model_ids, model_default,

@@ -250,3 +250,40 @@ def test_per_item_data_rows(engine, golden_datasets):
     one = engine.evaluate(params, model=mid, flags=1 | 2 | 4, row_ids=rid)["llh"]
     assert one.shape == (9, 1)
     assert np.array_equal(one[:, 0], full[np.arange(9), rid])
+
+
+def test_stiff_intervals_take_the_dense_step(engine, golden_datasets, golden_cases):
+    """rates ~1e7 (the reference's own run-away corrections): the item is parked by the sweep kernel, advanced by
+    the dense scaling-and-squaring kernel (FP64 MMA) and resumed; results agree with the reference's."""
+    n = 0
+    for case in golden_cases:
+        if case["name"] not in RUNAWAY:
+            continue
+        exp = case["expect"]
+        mid, numT = _register(engine, golden_datasets, case)
+        inj = np.zeros((1, engine.numT_max, 2))
+        inj[0, :numT] = np.array(exp["lc"])
+        assert inj.max() > 1e6
+        out = engine.evaluate(np.array([case["params"]]), model=mid, flags=flags_of(case), lc_inject=inj, want=("jafs", "status", "terms"))
+        assert out["status"][0] == 0, case["name"]
+        assert relerr(out["jafs"][0], exp["JAFS"]) < 1e-8, case["name"]
+        assert relerr(out["llh"][0, 0], exp["llh"]) < 1e-8, case["name"]
+        n += 1
+    assert n == 2
+    # a batch mixing stiff and ordinary items, odd count, both halves of a warp affected differently
+    case = [c for c in golden_cases if c["name"] == "c3_band_to_split"][0]
+    mid, numT = _register(engine, golden_datasets, case)
+    lc_ok = np.array([c for c in golden_cases if c["name"] == "c2_cpfit_m0"][0]["expect"]["lc"])
+    lc_stiff = np.array(case["expect"]["lc"])
+    B = 7
+    inj = np.zeros((B, engine.numT_max, 2))
+    for b in range(B):
+        inj[b, :numT] = lc_stiff if b % 3 == 1 else lc_ok
+    out = engine.evaluate(np.full((B, 1), case["params"][0]), model=mid, flags=flags_of(case), lc_inject=inj, want=("jafs", "status"))
+    assert (out["status"] == 0).all()
+    stiff, plain = [b for b in range(B) if b % 3 == 1], [b for b in range(B) if b % 3 != 1]
+    for b in stiff[1:]:
+        assert np.array_equal(out["jafs"][b], out["jafs"][stiff[0]])
+    for b in plain[1:]:
+        assert np.array_equal(out["jafs"][b], out["jafs"][plain[0]])
+    assert relerr(out["llh"][stiff[0], 0], case["expect"]["llh"]) < 1e-8
