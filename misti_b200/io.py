@@ -1,0 +1,235 @@
+"""Input / output either side of the hot path: PSMC pairs -> merged grid, joint SFS files, bootstrap rows,
+the `.mi` result file.  Host-side text handling only (runs once per process); nothing here is accelerated.
+
+Functional restatement of migrationIO.Units / ReadPSMCFile / ReadPSMC (migrationIO.py:100-176, 183-295),
+ReadJAFS (:557-656), BootstrapJAFS (:506-524), utils/generateJSFS_bs.py:39-48 and OutputMigration
+(:346-375), without the reference's process-global state: units are a value object (the reference mutates
+class statics), readers return fresh objects (the reference's JAFS() default list accumulates rows across
+calls, migrationIO.py:39), bootstrap resampling takes an explicit seed (the reference uses the unseeded
+global `random`).  Reference-named aliases (ReadPSMC, ReadJAFS, BootstrapJAFS, OutputMigration) are kept.
+"""
+import random
+import sys
+
+
+class Units:
+    """mutation rate per bp per generation, PSMC bin size, reference N0, generation time, heterozygosity loss."""
+
+    def __init__(self, mutRate=1.25e-8, binsize=100, N0=10000, genTime=1, hetloss=(0.0, 0.0)):
+        self.mutRate, self.binsize, self.N0, self.genTime = mutRate, binsize, N0, genTime
+        self.hetloss1, self.hetloss2 = 0.0, 0.0
+        self.SetHetLoss(hetloss)
+
+    @classmethod
+    def from_file(cls, fn, hetloss=(0.0, 0.0)):
+        """`name=value` lines (setunits.txt); unknown / unreadable entries keep their defaults."""
+        u = cls(hetloss=hetloss)
+        try:
+            with open(fn) as f:
+                for line in f:
+                    kv = line.split("=")
+                    if len(kv) == 2 and kv[0] in ("mutRate", "binsize", "N0", "genTime"):
+                        try:
+                            setattr(u, kv[0], float(kv[1]))
+                        except ValueError:
+                            print("Cannot read %s entry from file, using default or previous values" % kv[0])
+        except OSError:
+            print("Units input file not found, using default values.")
+        return u
+
+    def SetHetLoss(self, hl):
+        for k, v in enumerate(hl or ()):
+            if v is None:
+                continue
+            if not (0.0 <= v < 1.0):
+                sys.stderr.write("Hetloss should be between 0 and 1.\n")
+                sys.exit(0)
+            setattr(self, "hetloss%d" % (k + 1), v)
+
+    def PrintUnits(self):
+        print("Units: mutation rate =", self.mutRate, "\tbinsize =", self.binsize, "\tN0 =", self.N0, "\tgeneration time =", self.genTime)
+
+
+class InputData:
+    """What MiSTI.py hands to MigrationInference (migrationIO.InputData, migrationIO.py:46-63)."""
+
+    def __init__(self, times, lambdas, scaleTime, theta, divTime=-1, scaleEPS=1.0, rho=None, sampleDateDiscr=0, Tpsmc=None):
+        self.times, self.lambdas = times, lambdas
+        self.divergenceTime = divTime
+        self.scaleTime, self.theta, self.scaleEPS, self.rho = scaleTime, theta, scaleEPS, rho
+        self.sampleDateDiscr, self.Tpsmc = sampleDateDiscr, Tpsmc
+        self.mi, self.pu = None, None
+
+
+class JAFS:
+    def __init__(self, jafs=None, pop1=None, pop2=None):
+        self.jafs = [] if jafs is None else jafs
+        self.pop1, self.pop2 = pop1, pop2
+
+
+def read_psmc_file(fn, RD=-1):
+    """One PSMC output: interval start times t_k and relative sizes lambda_k of round RD (-1 = last),
+    theta and rho of that round (migrationIO.ReadPSMCFile, migrationIO.py:183-222)."""
+    with open(fn) as f:
+        lines = [ln.split() for ln in f if ln.split()]
+    rounds = [int(ln[1]) for ln in lines if ln[0] == "RD"]
+    if not rounds:
+        print("Corrupted or empty input file")
+        sys.exit(0)
+    if RD == -1 or RD > max(rounds):
+        RD = max(rounds)
+    Tk, Lk, th, rh = [], [], 0.0, 0.0
+    inside = False
+    for ln in lines:
+        if ln[0] == "RD":
+            if inside:
+                break
+            inside = int(ln[1]) == RD
+        elif inside:
+            if ln[0] == "TR":
+                th, rh = float(ln[1]), float(ln[2])
+            elif ln[0] == "RS":
+                Tk.append(float(ln[2]))
+                Lk.append(float(ln[3]))
+            elif ln[0] == "PA":
+                break
+    return [Tk, Lk, RD, th, rh]
+
+
+def read_psmc(fn1, fn2, sampleDate=0.0, RD=-1, units=None):
+    """Merge two PSMC trajectories onto one time grid (migrationIO.ReadPSMC, migrationIO.py:224-295):
+    each genome's times and sizes are rescaled by theta_g / theta (theta_g inflated by its heterozygosity loss),
+    genome 2 is shifted by the sampling date (with a dummy unit-rate interval before it), the union of the
+    breakpoints is the grid and each genome's rate 1/lambda is held piecewise constant on it."""
+    u = units if units is not None else Units()
+    d1, d2 = read_psmc_file(fn1, RD), read_psmc_file(fn2, RD)
+    d1[3] = d1[3] / (1.0 - u.hetloss1)
+    d2[3] = d2[3] / (1.0 - u.hetloss2)
+    theta = 4.0 * u.binsize * u.mutRate * u.N0
+    scaleTime = 2 * u.genTime * u.N0
+    for d in (d1, d2):
+        d[0] = [v * d[3] / theta for v in d[0]]
+        d[1] = [v * d[3] / theta for v in d[1]]
+    sdResc = sampleDate / 2 / u.N0 / u.genTime
+    if sdResc > 0:
+        d2[0] = [0.0] + [v + sdResc for v in d2[0]]
+        d2[1] = [1.0] + d2[1]
+    Tk = sorted(d1[0] + d2[0][1:])
+    if sdResc not in Tk:
+        sys.stderr.write("Unexpected error in ReadPSMC(). Get in touch with the author.\n")
+        sys.exit(0)
+    sampleDateDiscr = Tk.index(sdResc)
+    rates, Tpsmc = [], []
+    for d in (d1, d2):
+        L, marks, j = [], [0], 0
+        for i in range(len(d[0]) - 1):
+            while Tk[j] < d[0][i + 1]:
+                L.append(1.0 / d[1][i])
+                j += 1
+            marks.append(j)
+        L += [1.0 / d[1][-1]] * (len(Tk) - len(L))
+        marks.append(len(Tk))
+        rates.append(L)
+        Tpsmc.append(marks)
+    lambdas = [[a, b] for a, b in zip(rates[0], rates[1])]
+    times = [b - a for a, b in zip(Tk[:-1], Tk[1:])]
+    return InputData(times, lambdas, scaleTime, theta, scaleEPS=1, rho=d1[4] * theta / d1[3], sampleDateDiscr=sampleDateDiscr,
+                     Tpsmc=Tpsmc)
+
+
+def read_jafs(fn, silent_mode=True):
+    """Joint SFS file, format version >= 1 (migrationIO.ReadJAFS, migrationIO.py:557-614): header lines starting
+    with '#', an optional column line starting with 'total', then rows of 8 TAB-separated numbers
+    [total sites, 0100, 1100, 0001, 0101, 1101, 0011, 0111]."""
+    out = JAFS()
+    with open(fn) as f:
+        lines = [ln.rstrip("\n") for ln in f]
+    if not lines or not lines[0].startswith(("#MiSTI_JSFS", "#MiSTI_JAF", "#Migration_JAF")):
+        sys.stderr.write("Corrupted JSFS file header.\n")
+        sys.exit(0)
+    if float(lines[0].split(" ")[2]) < 1:
+        sys.stderr.write("The file version is not supported anymore.\n")
+        sys.exit(0)
+    for ln in lines[1:]:
+        if ln.startswith("#"):
+            if ln[1:5] in ("pop1", "pop2"):
+                pars = ln.split("\t")
+                if len(pars) != 2:
+                    sys.stderr.write("Corrupted JSFS file header.\n")
+                    sys.exit(0)
+                setattr(out, ln[1:5], pars[1])
+                if not silent_mode:
+                    print(ln[1:5] + "\t", pars[1])
+            continue
+        if ln.startswith("total") or ln == "":
+            continue
+        cols = ln.split("\t")
+        if len(cols) != 8:
+            sys.stderr.write("Unexpected line. Expected an entry for JSFS with eight TAB-separated columns.\n")
+            sys.exit(0)
+        out.jafs.append([float(v) for v in cols])
+    return out
+
+
+def column_sums(rows):
+    """The data spectrum MiSTI.py uses with -bs -1: the sum of all chunk rows (MiSTI.py:172-176)."""
+    s = [0 for _ in range(8)]
+    for r in rows:
+        s = [v + w for v, w in zip(s, r)]
+    return s
+
+
+def bootstrap_jafs(rows, rng, normalize=False):
+    """One bootstrap replicate: chunk rows drawn with replacement until the genome length is reached
+    (migrationIO.BootstrapJAFS, migrationIO.py:506-524).  rng: random.Random."""
+    for el in rows:
+        if len(el) != 8:
+            sys.stderr.write("Cannot use provided SFS for bootstrap.\n")
+            sys.exit(0)
+    genomeLen = sum(el[0] for el in rows)
+    seg = sum(sum(el[1:]) for el in rows)
+    sfs = [0 for _ in range(8)]
+    while sfs[0] < genomeLen:
+        pick = rows[rng.randint(0, len(rows) - 1)]
+        sfs = [a + b for a, b in zip(sfs, pick)]
+    if normalize:
+        k = seg / sum(sfs[1:])
+        sfs = [v * k for v in sfs]
+    return sfs
+
+
+def generate_bootstrap(rows, n, seed=0):
+    """Row 0 = the data total, rows 1..n = bootstrap replicates (utils/generateJSFS_bs.py:39-48), seeded."""
+    rng = random.Random(seed)
+    return [column_sums(rows)] + [bootstrap_jafs(rows, rng) for _ in range(n)]
+
+
+def output_migration(fout, mu, Migration, scaleTime=1, scaleEPS=1):
+    """The `.mi` result file, format "#MiSTI2 ver 0.4" (migrationIO.OutputMigration, migrationIO.py:346-375)."""
+    llh = Migration.llh if len(mu) == 0 else Migration.JAFSLikelihood(mu)
+    times = [sum(Migration.times[0:i]) for i in range(len(Migration.times) + 1)]
+    tot = sum(Migration.dataJAFS)
+    out = ["#MiSTI2 ver 0.4", "LK\t" + str(llh), "ST\t" + str(Migration.splitT), "SD\t" + str(Migration.sampleDate),
+           "TR\t" + str(Migration.thrh[0]) + "\t" + str(Migration.thrh[1]), "SFS\t" + "\t".join(map(str, Migration.JAFS)),
+           "DSF\t" + "\t".join(str(v / tot) for v in Migration.dataJAFS), "SCT\t" + str(scaleTime), "SCE\t" + str(scaleEPS)]
+    for i, t in enumerate(times):
+        row = ["RS", str(t), str(1.0 / Migration.lc[i][0]), str(1.0 / Migration.lc[i][1]), str(1.0 / Migration.lh[i][0]),
+               str(1.0 / Migration.lh[i][1]), str(Migration.mi[i][0]), str(Migration.mi[i][1])]
+        if i < Migration.splitT:
+            for val in Migration.Pr[i]:
+                row += [str(val[0]), str(val[1])]
+        out.append("\t".join(row))
+    text = "\n".join(out) + "\n"
+    if fout == "":
+        print(text)
+    else:
+        with open(fout, "w") as f:
+            f.write(text)
+
+
+# reference-named aliases
+ReadPSMCFile, ReadPSMC, ReadJAFS, OutputMigration = read_psmc_file, read_psmc, read_jafs, output_migration
+
+
+def BootstrapJAFS(Jafs, normalize=False, rng=None):
+    return bootstrap_jafs(Jafs.jafs, rng if rng is not None else random.Random(), normalize)

@@ -1,0 +1,74 @@
+"""Loaders either side of the path (misti_b200/io.py) against what the reference's migrationIO produced from the
+same files (tests/golden/datasets.json).  CPU only."""
+import os
+import random
+
+import numpy as np
+
+from misti_b200 import io as mio
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DATA = os.path.join(ROOT, "data", "synthetic")
+
+
+def test_read_psmc_plain_and_ancient(golden_datasets):
+    units = mio.Units.from_file(os.path.join(DATA, "setunits.txt"))
+    inp = mio.read_psmc(os.path.join(DATA, "m1.psmc"), os.path.join(DATA, "m2.psmc"), 0, -1, units)
+    g = golden_datasets["synthetic"]
+    assert inp.times == g["times"] and inp.lambdas == g["lambdas"]  # bit-identical: same arithmetic in the same order
+    assert inp.sampleDateDiscr == g["sampleDate"] and inp.theta == g["theta"] and inp.rho == g["rho"]
+    assert inp.scaleTime == g["scaleTime"] and len(inp.times) == len(inp.lambdas) - 1 == 126
+    g = golden_datasets["synthetic_ancient"]
+    units = mio.Units.from_file(os.path.join(DATA, "setunits.txt"), hetloss=g["hetloss"])
+    inp = mio.read_psmc(os.path.join(DATA, "m1.psmc"), os.path.join(DATA, "m2.psmc"), g["sdate"], -1, units)
+    assert inp.times == g["times"] and inp.lambdas == g["lambdas"] and inp.sampleDateDiscr == g["sampleDate"]
+    assert inp.theta == g["theta"] and inp.rho == g["rho"]
+
+
+def test_read_jafs_is_side_effect_free(golden_datasets):
+    a = mio.read_jafs(os.path.join(DATA, "m.sfs"))
+    b = mio.read_jafs(os.path.join(DATA, "m.sfs"))  # the reference would now hold 400 rows (mutable default list)
+    assert len(a.jafs) == len(b.jafs) == 200 and a.pop1 == "A" and a.pop2 == "B"
+    assert mio.column_sums(a.jafs) == golden_datasets["synthetic"]["sfs"]
+    bs = mio.read_jafs(os.path.join(DATA, "bs.sfs"))
+    assert bs.jafs[:6] == golden_datasets["synthetic"]["bs_rows"]
+
+
+def test_bootstrap_semantics():
+    rows = mio.read_jafs(os.path.join(DATA, "m.sfs")).jafs
+    total = mio.column_sums(rows)
+    out = mio.generate_bootstrap(rows, 5, seed=12345)
+    assert out[0] == total and len(out) == 6
+    for r in out[1:]:
+        assert total[0] <= r[0] < total[0] + max(x[0] for x in rows)  # drawn until the genome length is reached
+    assert out == mio.generate_bootstrap(rows, 5, seed=12345) and out != mio.generate_bootstrap(rows, 5, seed=1)
+    # identical to the reference's procedure driven by the same generator
+    rng = random.Random(12345)
+    sfs = [0] * 8
+    while sfs[0] < total[0]:
+        pick = rows[rng.randint(0, len(rows) - 1)]
+        sfs = [a + b for a, b in zip(sfs, pick)]
+    assert sfs == out[1]
+
+
+def test_units_file_and_hetloss(tmp_path):
+    p = tmp_path / "u.txt"
+    p.write_text("mutRate=2.5e-8\nbinsize=100\nN0=5000\ngenTime=25\njunk\n")
+    u = mio.Units.from_file(str(p), hetloss=(0.05, None))
+    assert (u.mutRate, u.N0, u.genTime, u.hetloss1, u.hetloss2) == (2.5e-8, 5000.0, 25.0, 0.05, 0.0)
+    assert mio.Units.from_file(str(tmp_path / "missing.txt")).N0 == 10000
+
+
+def test_mi_writer(tmp_path):
+    class M:
+        llh, splitT, sampleDate, thrh = -12.5, 1, 0, [0.05, 0.01]
+        times, JAFS, dataJAFS = [0.1, 0.2], [0.1] * 7, [1.0] * 7
+        lc, lh, mi = [[1, 2], [4, 4], [5, 5]], [[1, 1], [2, 2], [4, 4]], [[0.0, 0.5], [0, 0], [0, 0]]
+        Pr = [[[1.0, 0.0], [0.0, 1.0], [0.0, 0.0]], [[0.9, 0.0], [0.0, 0.8], [0.0, 0.1]]]
+    f = tmp_path / "o.mi"
+    mio.output_migration(str(f), [], M, 20000, 1)
+    lines = f.read_text().splitlines()
+    assert lines[0] == "#MiSTI2 ver 0.4" and lines[1] == "LK\t-12.5" and lines[2] == "ST\t1"
+    rs = [ln.split("\t") for ln in lines if ln.startswith("RS")]
+    assert len(rs) == 3 and rs[0][1:8] == ["0", "1.0", "0.5", "1.0", "1.0", "0.0", "0.5"] and len(rs[0]) == 14 and len(rs[1]) == 8
+    assert np.isclose(float(rs[2][1]), 0.3)
