@@ -19,9 +19,15 @@
 
 #if defined(__CUDACC__)
 #define MISTI_HD __host__ __device__
+#define MISTI_NOINLINE __noinline__
 #else
 #define MISTI_HD
+#define MISTI_NOINLINE __attribute__((noinline))
 #endif
+// The residual functors are NOT inlined: the finite-difference Jacobian subtracts two evaluations of the same
+// function, and scipy's result (an exactly zero column where the residual does not depend on a variable, which
+// then stays at its start value) is only reproduced if both evaluations run the very same instruction sequence --
+// inlined copies may be fused into FMAs differently at different call sites.
 
 namespace misti {
 
@@ -82,7 +88,7 @@ MISTI_HD inline bool mat3_inv(const double* A, double* Ainv) {
 
 // exp(A) for a 3x3 matrix: Pade [m/m] with m in {3,5,7,9,13} chosen from ||A||_1, scaling and
 // squaring (Higham 2005 thresholds; same algorithm family as scipy.linalg.expm).
-MISTI_HD inline void mat3_expm(const double* Ain, double* E) {
+MISTI_HD MISTI_NOINLINE inline void mat3_expm(const double* Ain, double* E) {
     double A[9];
     double nrm = 0.0;
     for (int j = 0; j < 3; ++j) {
@@ -659,7 +665,7 @@ MISTI_HD inline double one_pop_time_noncond(double lam, double T) {  // CorrectL
 // cpfit residuals: LambdaSystem1 / LambdaEquation (CorrectLambda.py:135-144,169-173)
 struct ResidualProb {
     const IntervalState* st;
-    MISTI_HD bool operator()(const double* l, double* out) const {
+    MISTI_HD MISTI_NOINLINE bool operator()(const double* l, double* out) const {
         double M[9], E[9];
         corr_matrix(l, st->mu, st->T, M);
         mat3_expm(M, E);
@@ -677,7 +683,7 @@ struct ResidualProb {
 // default-mode residuals: LambdaSystem / ExpectedCoalTimeTwoPop (CorrectLambda.py:94-110,151-157)
 struct ResidualTime {
     const IntervalState* st;
-    MISTI_HD bool operator()(const double* l, double* out) const {
+    MISTI_HD MISTI_NOINLINE bool operator()(const double* l, double* out) const {
         const double T = st->T;
         double M[9], MT[9], E[9], Minv[9];
         corr_matrix(l, st->mu, 1.0, M);
@@ -712,7 +718,7 @@ struct ResidualTime {
 struct ResidualNoMig {
     const IntervalState* st;
     double pr0[2][3];
-    MISTI_HD bool operator()(const double* l, double* out) const {
+    MISTI_HD MISTI_NOINLINE bool operator()(const double* l, double* out) const {
         const double T = st->T;
         for (int i = 0; i < 2; ++i) {
             const double pnc = (pr0[i][0] * exp(-l[0] * T) + pr0[i][1] * exp(-l[1] * T)) + pr0[i][2];
@@ -726,7 +732,7 @@ struct ResidualNoMig {
 // post-split single rate: EPSFromExpectedCoalTime (CorrectLambda.py:82-86)
 struct ResidualSingle {
     double T, Te;
-    MISTI_HD bool operator()(const double* lam, double* out) const {
+    MISTI_HD MISTI_NOINLINE bool operator()(const double* lam, double* out) const {
         out[0] = one_pop_time(lam[0], T) - Te;
         return true;
     }
