@@ -1,5 +1,5 @@
 // misti_jsfs.cuh -- expected joint SFS of one evaluation item, written for a cooperating GROUP of
-// lanes (a warp on the device; a single "lane" in the test-only host build tests/hostsim).
+// lanes (16 lanes of a warp on the device; a single "lane" in the test-only host build tests/hostsim).
 //
 // Reference path restated here: MigrationInference.JAFSpectrum / SolveDifEq / CollapsePops
 // (MigrationInference.py:467-540), TwoPopulations.SetMatrix / UpdateMatrixCol / PulseMigration /
@@ -7,18 +7,24 @@
 // (OnePopulation.py:153-178), and the likelihood tail (MigrationInference.py:583-613).
 //
 // What is different from the reference (same numbers, different algorithm):
-//   * P1 = expm(M T) P0 and integralP = inv(M)(P1 - P0) = int_0^T exp(M s) P0 ds are obtained
-//     together by UNIFORMISATION of the lineage chain: with q >= max |M_cc| the matrix
-//     A = I + M/q is non-negative, exp(M T) = sum_k Pois(k; qT) A^k, and
-//     int_0^T exp(M s) P0 ds = (1/q) sum_k Pois(k; qT) (P0 + A P0 + ... + A^(k-1) P0).
-//     Every term is non-negative (no cancellation), only sparse 44x44 mat-vecs are needed
-//     (152 off-diagonal entries), the zero-migration singular case of the reference
-//     (TwoPopulations.py:240-309, 7 stationary states removed and patched back) needs no special
-//     handling, and no inverse is formed.  Intervals with qT > 32 are cut into equal sub-steps.
-//   * after the split all generators are multiples of one constant 8x8 matrix L8 and commute, so
-//     the whole post-split contribution is  sum_k cpost[k] * (W8 G_k) P8  with the three spectral
-//     projectors G_k of L8 (eigenvalues -6, -3, -1); cpost[] is accumulated by post_split_coeffs().
+//   * intervals WITH migration: P1 = expm(M T) P0 and integralP = inv(M)(P1 - P0) = int_0^T exp(M s) P0 ds are
+//     obtained together by UNIFORMISATION of the lineage chain: with q = max |M_cc| the matrix A = I + M/q is
+//     non-negative, exp(M T) = sum_k Pois(k; qT) A^k, and int_0^T exp(M s) P0 ds = (1/q) sum_k P(N > k) A^k P0.
+//     Every term is non-negative (no cancellation) and only sparse 44x44 mat-vecs are needed (152 off-diagonal
+//     entries).  Intervals with qT > 32 are cut into equal sub-steps.
+//   * RUNS of consecutive intervals WITHOUT migration: M_i = la0_i C0 + la1_i C1 with two constant, commuting,
+//     diagonalisable matrices (eigenvalues 0, -1, -3, -6), so the whole run is ONE application of
+//     sum_ab coef_ab G0_a G1_b (8 non-zero projector products, 188 entries; tools/gen_tables.py) with scalar
+//     coefficients -- the reference's singular zero-migration case (TwoPopulations.py:240-309) in closed form.
+//   * after the split all generators are multiples of one constant 8x8 matrix L8 and commute, so the whole
+//     post-split contribution is sum_k cpost[k] (W8 G_k) P8 with the three spectral projectors of L8.
+//   * all SCALAR work per interval (q, 1/q, Poisson start weights, series length, run coefficients) is done once per
+//     item by the single thread that ran the correction chain (build_segments_item, called by kernel K1) and handed
+//     to the lane group as a list of 128-byte SEGMENT RECORDS; the lane group only does vector work.
 #pragma once
+#include <climits>
+#include <cstring>
+
 #include "misti_model.cuh"
 #include "misti_tables.h"
 
@@ -30,6 +36,7 @@ struct PulseEntry { unsigned char row, col, a, b, mult; };
 #define MISTI_DEFINE_TABLES(SPEC, PFX)                                          \
     SPEC EllEntry PFX##ell[44][MISTI_ELL_WIDTH] = MISTI_ELL_INIT;               \
     SPEC unsigned char PFX##diag[44][4] = MISTI_GEN_DIAG_INIT;                  \
+    SPEC unsigned char PFX##qdiag[MISTI_QDIAG_N][4] = MISTI_QDIAG_INIT;         \
     SPEC unsigned char PFX##w44[7][44] = MISTI_W44_INIT;                        \
     SPEC unsigned char PFX##collapse[44] = MISTI_COLLAPSE_INIT;                 \
     SPEC unsigned char PFX##anc2[44] = MISTI_ANC2_INIT;                         \
@@ -40,7 +47,14 @@ struct PulseEntry { unsigned char row, col, a, b, mult; };
     SPEC unsigned char PFX##pulse1_rowptr[45] = MISTI_PULSE1_ROWPTR_INIT;       \
     SPEC double PFX##wg6[7][8] = MISTI_WG6_INIT;                                \
     SPEC double PFX##wg3[7][8] = MISTI_WG3_INIT;                                \
-    SPEC double PFX##wg1[7][8] = MISTI_WG1_INIT;
+    SPEC double PFX##wg1[7][8] = MISTI_WG1_INIT;                                \
+    SPEC unsigned char PFX##l16_row[16][3] = MISTI_L16_ROW_INIT;                \
+    SPEC unsigned char PFX##l16_rem[16][3][3][2] = MISTI_L16_REM_INIT;          \
+    SPEC unsigned char PFX##l16_loc[16][3][2] = MISTI_L16_LOC_INIT;             \
+    SPEC unsigned char PFX##nm_rowptr[45] = MISTI_NM_ROWPTR_INIT;               \
+    SPEC unsigned char PFX##nm_col[MISTI_NM_NNZ] = MISTI_NM_COL_INIT;           \
+    SPEC unsigned char PFX##nm_ab[MISTI_NM_NNZ] = MISTI_NM_AB_INIT;             \
+    SPEC double PFX##nm_val[MISTI_NM_NNZ] = MISTI_NM_VAL_INIT;
 
 // Under nvcc the table users are device-only functions reading __device__ copies; the test-only
 // host build (g++) reads plain static copies.
@@ -52,57 +66,6 @@ MISTI_DEFINE_TABLES(static __device__ const, d_)
 MISTI_DEFINE_TABLES(static const, h_)
 #define MISTI_TAB(name) h_##name
 #define MISTI_D
-#endif
-
-// ---- lane groups ------------------------------------------------------------------------------
-// A group = the lanes that share one item.  Several groups may share a warp; they then run in LOCK
-// STEP: every loop bound and branch in jsfs_item is made warp-uniform with wmax / any / all, and a
-// group that has nothing left to do keeps executing on a zero-length interval (an exact no-op).
-struct SingleLane {  // test-only host build: one lane owns all 44 rows
-    static constexpr int LANES = 1;
-    MISTI_HD int lane() const { return 0; }
-    MISTI_HD void sync() const {}
-    MISTI_HD double max(double v) const { return v; }
-    MISTI_HD double sum(double v) const { return v; }
-    MISTI_HD int wmax(int v) const { return v; }
-    MISTI_HD bool any(bool v) const { return v; }
-    MISTI_HD bool all(bool v) const { return v; }
-    // coefficient table: entry c < 12 is 2^(c >> 2) * rq[c & 3], entries 12.. are 0
-    MISTI_HD double table_entry(const double*) const { return 0.0; }
-    MISTI_HD double table_get(double, unsigned c, const double* rq) const {
-        return c >= 12u ? 0.0 : (double)(1u << (c >> 2)) * rq[c & 3u];
-    }
-};
-
-#if defined(__CUDACC__)
-struct HalfWarpLanes {  // two items per warp: lane l of each 16-lane half owns rows l, l + 16, l + 32
-    static constexpr int LANES = 16;
-    __device__ int lane() const { return threadIdx.x & 15; }
-    __device__ void sync() const { __syncwarp(); }
-    __device__ double max(double v) const {  // within the half
-        for (int o = 8; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
-        return v;
-    }
-    __device__ double sum(double v) const {  // within the half
-        for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        return v;
-    }
-    __device__ int wmax(int v) const {  // over the whole warp (both items); v is uniform within a half
-        const int o = __shfl_xor_sync(0xffffffffu, v, 16);
-        return v > o ? v : o;
-    }
-    __device__ bool any(bool v) const { return __any_sync(0xffffffffu, v); }
-    __device__ bool all(bool v) const { return __all_sync(0xffffffffu, v); }
-    // coefficient table spread over the 16 lanes of the group: lane c < 12 holds 2^(c >> 2) * rq[c & 3],
-    // lanes 12.. hold 0; table_get fetches entry (c & 15) with one shuffle instead of a select chain
-    __device__ double table_entry(const double* rq) const {
-        const unsigned c = threadIdx.x & 15u;
-        const unsigned kind = c & 3u;
-        const double base = kind == 0 ? rq[0] : (kind == 1 ? rq[1] : (kind == 2 ? rq[2] : rq[3]));
-        return c >= 12u ? 0.0 : (double)(1u << (c >> 2)) * base;
-    }
-    __device__ double table_get(double mine, unsigned c, const double*) const { return __shfl_sync(0xffffffffu, mine, c, 16); }
-};
 #endif
 
 // 1/k for the Poisson weight recursion p_k = p_(k-1) * lam / k (a table lookup instead of a division per term)
@@ -124,22 +87,259 @@ static const RecipTable h_recip = RecipTable();
 
 constexpr int kYStride = 48;                    // doubles per ping-pong buffer (44 states + pad rows)
 constexpr double kUnifMaxStep = 32.0;           // largest q*T handled in one uniformisation sweep
-constexpr double kUnifTol = 1.3877787807814457e-17;  // 2^-56: truncation of the Poisson tail
+constexpr double kUnifTol = 8.881784197001252e-16;   // 2^-50: truncation of the Poisson tail (relative to the mass)
 constexpr double kUnifMaxStiff = 256.0;         // q*T beyond this (8 sweeps) goes to the dense scaling-and-squaring step
+constexpr int kUnifMaxTerms = MISTI_RECIP_N - 4;     // never reached for q*T <= 32 (about 110 terms)
 
-// Continuation record of an item whose next two-population interval is too stiff for the uniformisation sweep
-// (rates ~1e5..1e8 after a run-away correction): the state at the START of interval `it` (before the ancient
-// reset / pulse of that interval).  misti_stiff_kernel advances it over the stiff interval(s) with a dense
-// scaling-and-squaring step; the JSFS kernel then resumes from it.
+// ---- segment records ----------------------------------------------------------------------------
+// The two-population part of an item is a list of segments, 16 doubles (one 128-byte line) each:
+//   SEG_MIG    one interval with migration, to be swept by uniformisation.  Slots 0..9: coefficient table
+//              2^(c >> 2) * rate[c & 3] / q for code c = kind + 4 log2(count) (kinds: coalescence in deme 0 / 1,
+//              migration out of deme 0 / 1; codes 10, 11 do not occur), 10: 1/q, 11: lam = q T / nsub, 12: 0
+//              (code 12 = "no entry"), 13: Pois(0; lam), 14: P(N > 0), 15: meta.
+//   SEG_RUN    a run of intervals without migration.  Slots 0..7: c_ab = sum_i e_ab(i) phi_ab(i) (integral
+//              coefficients), 8..14: e_ab at the end of the run for ab = 1..7 (e_0 = 1), 15: meta.
+//   SEG_STIFF  one interval with migration and q T > kUnifMaxStiff: only meta (the item is parked for the dense step).
+//   SEG_INF    the infinite last interval when there is no split inside the grid: slots 0..9 table, 10: 1/q.
+// meta (the 64 bits of slot 15): bits 0-2 type, bit 3 ancient-sample reset before the segment, bit 4 pulse before
+// the segment, bit 5 segment lies before the sampling date, bits 8-19 first interval, bits 20-31 number of
+// intervals, bits 32-47 series length K, bits 48-62 number of sub-steps.
+constexpr int kRecSlots = 16;
+enum { SEG_NOP = 0, SEG_MIG = 1, SEG_RUN = 2, SEG_STIFF = 3, SEG_INF = 4 };
+constexpr unsigned long long kSegReset = 8, kSegPulse = 16, kSegPre = 32;
+
+MISTI_HD inline double seg_meta_pack(unsigned long long m) { double d; memcpy(&d, &m, 8); return d; }
+MISTI_HD inline unsigned long long seg_meta_bits(double d) { unsigned long long m; memcpy(&m, &d, 8); return m; }
+MISTI_HD inline int seg_type(unsigned long long m) { return (int)(m & 7ull); }
+MISTI_HD inline int seg_it(unsigned long long m) { return (int)((m >> 8) & 0xfffull); }
+MISTI_HD inline int seg_K(unsigned long long m) { return (int)((m >> 32) & 0xffffull); }
+MISTI_HD inline int seg_nsub(unsigned long long m) { return (int)((m >> 48) & 0x7fffull); }
+
+MISTI_HD inline bool finite_nonneg(double v) { return v >= 0.0 && v <= DBL_MAX; }
+
+// Segment list of one item (run by ONE thread, after the correction chain).  lc is addressed as
+// lc[(pitch*t + g)*stride]; rec has room for min(splitT, numT) records.  Returns MISTI_OK, MISTI_NONFINITE or
+// MISTI_INFINITE_COAL_TIME (no split inside the grid and no migration in the last interval, :475-476).
+MISTI_D inline int build_segments_item(const ModelDesc& md, const double* times, const double* params, const double* lc,
+                                       int pitch, long stride, double* rec, int* nseg_out) {
+    const int numT = md.numT;
+    const int n2 = md.splitT < numT ? md.splitT : numT;
+    const bool inf_last = md.splitT >= numT;
+    const int n_fin = inf_last ? n2 - 1 : n2;
+    int ns = 0;
+    bool open = false;
+    double c[8], u0 = 1.0, u1 = 1.0;
+    unsigned long long run_meta = 0;
+    int run_n = 0;
+    *nseg_out = 0;
+    auto put = [&](const double* slot) {
+        double* o = rec + (long)ns * kRecSlots;
+        for (int i = 0; i < kRecSlots; ++i) o[i] = slot[i];
+        ++ns;
+    };
+    auto close_run = [&]() {
+        double slot[kRecSlots];
+        for (int i = 0; i < 8; ++i) slot[i] = c[i];
+        const double u03 = u0 * u0 * u0, u13 = u1 * u1 * u1;
+        slot[8] = u0; slot[9] = u03; slot[10] = u03 * u03;
+        slot[11] = u1; slot[12] = u13; slot[13] = u13 * u13;
+        slot[14] = u0 * u1;
+        slot[15] = seg_meta_pack(run_meta | ((unsigned long long)run_n << 20));
+        put(slot);
+        open = false;
+    };
+    auto table = [&](double la0, double la1, double m0, double m1, double* slot, double* q_out) {
+        double q = 0.0;
+        for (int i = 0; i < MISTI_QDIAG_N; ++i) {
+            const double d = ((double)MISTI_TAB(qdiag)[i][0] * la0 + (double)MISTI_TAB(qdiag)[i][1] * la1) +
+                             ((double)MISTI_TAB(qdiag)[i][2] * m0 + (double)MISTI_TAB(qdiag)[i][3] * m1);
+            q = d > q ? d : q;
+        }
+        const double qinv = 1.0 / q;
+        const double rq[4] = {la0 * qinv, la1 * qinv, m0 * qinv, m1 * qinv};
+        for (int i = 0; i < kRecSlots; ++i) slot[i] = 0.0;
+        for (int k = 0; k < 4; ++k) { slot[k] = rq[k]; slot[4 + k] = 2.0 * rq[k]; }
+        slot[8] = 4.0 * rq[0]; slot[9] = 4.0 * rq[1];
+        slot[10] = qinv;
+        *q_out = q;
+    };
+    for (int it = 0; it <= n_fin; ++it) {
+        const bool last = it == n_fin;  // the infinite interval (only visited when inf_last)
+        if (last && !inf_last) break;
+        const int t = last ? numT - 1 : it;
+        const double la0 = lc[(pitch * t) * stride], la1 = lc[(pitch * t + 1) * stride];
+        const double m0 = band_rate(md, params, t, 0), m1 = band_rate(md, params, t, 1);
+        const double T = last ? 0.0 : times[t];
+        if (!(finite_nonneg(la0) && finite_nonneg(la1) && finite_nonneg(m0) && finite_nonneg(m1) && finite_nonneg(T)))
+            return MISTI_NONFINITE;
+        const bool reset = t == md.sampleDate && t > 0;
+        const bool pulse = md.n_pulses > 0 && pulse_rate(md, params, t, 0) + pulse_rate(md, params, t, 1) > 0;
+        const bool mig = m0 + m1 != 0.0;
+        if (open && (reset || pulse || mig || last)) close_run();
+        const unsigned long long flags = (reset ? kSegReset : 0) | (pulse ? kSegPulse : 0) | (t < md.sampleDate ? kSegPre : 0) |
+                                         ((unsigned long long)t << 8) | (1ull << 20);
+        if (last) {
+            if (!mig) return MISTI_INFINITE_COAL_TIME;
+            double slot[kRecSlots], q;
+            table(la0, la1, m0, m1, slot, &q);
+            if (!(q <= DBL_MAX)) return MISTI_NONFINITE;
+            slot[15] = seg_meta_pack(flags | SEG_INF);
+            put(slot);
+        } else if (mig) {
+            double slot[kRecSlots], q;
+            table(la0, la1, m0, m1, slot, &q);
+            const double qT = q * T;
+            if (!(qT <= DBL_MAX)) return MISTI_NONFINITE;
+            if (qT > kUnifMaxStiff) {
+                // rates of 1e5 and more per unit of interval length only come out of a run-away correction; such an
+                // interval is not swept (it would take millions of terms): the item is parked for the dense step
+                for (int i = 0; i < kRecSlots; ++i) slot[i] = 0.0;
+                slot[15] = seg_meta_pack(flags | SEG_STIFF);
+            } else {
+                const int nsub = qT > kUnifMaxStep ? (int)ceil(qT / kUnifMaxStep) : 1;
+                const double lam = nsub == 1 ? qT : qT / nsub;
+                const double p0 = exp(-lam), t0 = -expm1(-lam);  // Poisson P(N = 0) and P(N > 0)
+                // series length: the first k whose Poisson tail beyond the term is below kUnifTol
+                double p = p0, r = lam;
+                int k = 0;
+                do {
+                    ++k;
+                    p *= r;
+                    r = lam * MISTI_RECIP(k + 1);
+                } while (!(r < 1.0 && p < kUnifTol * (1.0 - r)) && k < kUnifMaxTerms);
+                if (k >= kUnifMaxTerms) return MISTI_NONFINITE;
+                slot[11] = lam; slot[13] = p0; slot[14] = t0;
+                slot[15] = seg_meta_pack(flags | SEG_MIG | ((unsigned long long)k << 32) | ((unsigned long long)nsub << 48));
+            }
+            put(slot);
+        } else {
+            if (!open) {
+                open = true;
+                u0 = 1.0; u1 = 1.0;
+                for (int i = 0; i < 8; ++i) c[i] = 0.0;
+                run_meta = (flags & ~(0xfffull << 20)) | SEG_RUN;
+                run_n = 0;
+            }
+            ++run_n;
+            // e_ab = exp(-a X0 - b X1) at the start of the interval; phi_ab = (1 - exp(-(a la0 + b la1) T)) / (a la0 + b la1);
+            // 1 - v^3 = (1 - v)(1 + v + v^2) and 1 - v0 v1 = (1 - v0) + v0 (1 - v1) keep every term positive
+            const double z0 = la0 * T, z1 = la1 * T;
+            const double v0 = exp(-z0), w0 = -expm1(-z0), v1 = exp(-z1), w1 = -expm1(-z1);
+            const double v03 = v0 * v0 * v0, v13 = v1 * v1 * v1;
+            const double w03 = w0 * (1.0 + v0 + v0 * v0), w13 = w1 * (1.0 + v1 + v1 * v1);
+            const double w06 = w03 * (1.0 + v03), w16 = w13 * (1.0 + v13);
+            const double u03 = u0 * u0 * u0, u13 = u1 * u1 * u1;
+            const double i0 = 1.0 / la0, i1 = 1.0 / la1, i01 = 1.0 / (la0 + la1);
+            c[0] += T;
+            c[1] += u0 * (la0 > 0.0 ? w0 * i0 : T);
+            c[2] += u03 * (la0 > 0.0 ? w03 * (i0 * (1.0 / 3.0)) : T);
+            c[3] += (u03 * u03) * (la0 > 0.0 ? w06 * (i0 * (1.0 / 6.0)) : T);
+            c[4] += u1 * (la1 > 0.0 ? w1 * i1 : T);
+            c[5] += u13 * (la1 > 0.0 ? w13 * (i1 * (1.0 / 3.0)) : T);
+            c[6] += (u13 * u13) * (la1 > 0.0 ? w16 * (i1 * (1.0 / 6.0)) : T);
+            c[7] += (u0 * u1) * (la0 + la1 > 0.0 ? (w0 + v0 * w1) * i01 : T);
+            u0 *= v0; u1 *= v1;
+        }
+    }
+    if (open) close_run();
+    *nseg_out = ns;
+    return MISTI_OK;
+}
+
+// ---- lane groups ------------------------------------------------------------------------------
+// A group = the lanes that share one item.  Several groups may share a warp; they then run in LOCK
+// STEP: every loop bound and branch in jsfs_item is made warp-uniform with wmax / wmin / any, and a
+// group that has nothing to do in a step executes it with neutral weights (an exact no-op), so that the
+// result of an item never depends on which item shares its warp.
+#if !defined(__CUDACC__)
+static const double kNeutralRec[kRecSlots] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1.0, 0, 0};
+
+struct SingleLane {  // test-only host build: one lane owns all 44 rows, every off-diagonal entry is "remote"
+    static constexpr int LANES = 1;
+    static constexpr int RPL = 44;    // rows per lane
+    static constexpr int NLOC = 0;    // entries served from the lane's own registers, per row
+    static constexpr int RWMAX = 4;   // entries read from the shared vector, per row (upper bound)
+    struct Rec {
+        const double* p;
+        MISTI_HD double get(int i) const { return p[i]; }
+    };
+    MISTI_D static int rw(int) { return 4; }
+    MISTI_D int row_of(int s) const { return s; }
+    MISTI_D void rem_of(int s, int e, int* col, unsigned* code) const {
+        const EllEntry en = MISTI_TAB(ell)[s][e];
+        *col = en.col;
+        *code = en.cnt == 0 ? 12u : (unsigned)en.kind + (en.cnt == 1 ? 0u : (en.cnt == 2 ? 4u : 8u));
+    }
+    MISTI_D unsigned loc_of(int, int) const { return 12u; }
+    MISTI_HD int lane() const { return 0; }
+    MISTI_HD void sync() const {}
+    MISTI_HD double sum(double v) const { return v; }
+    MISTI_HD int wmax(int v) const { return v; }
+    MISTI_HD int wmin(int v) const { return v; }
+    MISTI_HD bool any(bool v) const { return v; }
+    // record j of the item (all-zero = SEG_NOP when the group has none)
+    MISTI_HD Rec rec_load(const double* p, bool have) const { return Rec{have ? p : zero_rec()}; }
+    // the record itself, or the neutral sweep record (no events, P(N = 0) = 1)
+    MISTI_HD Rec rec_select(const Rec& r, bool is) const { return Rec{is ? r.p : kNeutralRec}; }
+    MISTI_HD void rec_store(const Rec& r, double* dst) const {
+        for (int i = 0; i < kRecSlots; ++i) dst[i] = r.p[i];
+    }
+    MISTI_HD static const double* zero_rec() {
+        static const double z[kRecSlots] = {0};
+        return z;
+    }
+};
+
+#else
+struct HalfWarpLanes {  // two items per warp; each lane of a 16-lane half owns three states (slots a, b, c) chosen so
+                        // that many off-diagonal entries have their column in the same lane (tools/gen_tables.py)
+    static constexpr int LANES = 16;
+    static constexpr int RPL = 3;
+    static constexpr int NLOC = 2;   // per row: one coefficient for each of the lane's other two rows (registers)
+    static constexpr int RWMAX = 3;  // per row: at most 3 / 2 / 3 entries read from shared memory (slots a / b / c)
+    struct Rec {  // lane l of the group holds slot l; get() is one shuffle
+        double v;
+        __device__ double get(int i) const { return __shfl_sync(0xffffffffu, v, i, 16); }
+    };
+    __device__ static int rw(int s) { return s == 1 ? 2 : 3; }
+    __device__ int row_of(int s) const { return d_l16_row[threadIdx.x & 15][s]; }
+    __device__ void rem_of(int s, int e, int* col, unsigned* code) const {
+        *col = d_l16_rem[threadIdx.x & 15][s][e][0];
+        *code = d_l16_rem[threadIdx.x & 15][s][e][1];
+    }
+    __device__ unsigned loc_of(int s, int j) const { return d_l16_loc[threadIdx.x & 15][s][j]; }
+    __device__ int lane() const { return threadIdx.x & 15; }
+    __device__ void sync() const { __syncwarp(); }
+    __device__ double sum(double v) const {  // within the half
+        for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        return v;
+    }
+    __device__ int wmax(int v) const {  // over the whole warp (both items); v is uniform within a half
+        const int o = __shfl_xor_sync(0xffffffffu, v, 16);
+        return v > o ? v : o;
+    }
+    __device__ int wmin(int v) const {
+        const int o = __shfl_xor_sync(0xffffffffu, v, 16);
+        return v < o ? v : o;
+    }
+    __device__ bool any(bool v) const { return __any_sync(0xffffffffu, v); }
+    __device__ Rec rec_load(const double* p, bool have) const { return Rec{have ? p[threadIdx.x & 15] : 0.0}; }
+    __device__ Rec rec_select(const Rec& r, bool is) const { return Rec{is ? r.v : ((threadIdx.x & 15) == 13 ? 1.0 : 0.0)}; }
+    __device__ void rec_store(const Rec& r, double* dst) const { dst[threadIdx.x & 15] = r.v; }
+};
+#endif
+
+// Continuation record of an item whose next segment is a stiff interval (rates ~1e5..1e8 after a run-away
+// correction): the state at the START of that interval (before its ancient reset / pulse).  misti_stiff_kernel
+// advances it over the stiff segment(s) with a dense scaling-and-squaring step; the JSFS kernel then resumes from it.
 struct Cont {
-    int it;
+    int seg;
     int nterms;
     int pad_[2];
     double P[48];
     double Ia[48];
     double Ib[48];
 };
-constexpr int kUnifMaxTerms = MISTI_RECIP_N - 4;     // never reached for q*T <= 32 (about 110 terms)
 
 // Post-split coefficients (run by ONE thread; lc addressed like in correct_lambdas_item):
 //   cpost[k] = sum_{i>=splitT} exp(-a_k x_i) (1 - exp(-a_k lam_i T_i)) / (a_k lam_i),  x_i = sum_{j<i} lam_j T_j,
@@ -156,117 +356,112 @@ MISTI_HD inline void post_split_coeffs(const ModelDesc& md, const double* times,
             const double u = exp(-z), w1 = -expm1(-z);      // w1 = 1 - u
             const double w3 = w1 * (1.0 + u + u * u);         // 1 - u^3
             const double w6 = w3 * (1.0 + u * u * u);         // 1 - u^6
-            c1 += e1 * w1 / lam;
-            c3 += e3 * w3 / (3.0 * lam);
-            c6 += e6 * w6 / (6.0 * lam);
+            const double il = 1.0 / lam;
+            c1 += e1 * w1 * il;
+            c3 += e3 * w3 * (il * (1.0 / 3.0));
+            c6 += e6 * w6 * (il * (1.0 / 6.0));
             e1 *= u;
         } else {
-            c1 += e1 / lam;
-            c3 += e3 / (3.0 * lam);
-            c6 += e6 / (6.0 * lam);
+            const double il = 1.0 / lam;
+            c1 += e1 * il;
+            c3 += e3 * (il * (1.0 / 3.0));
+            c6 += e6 * (il * (1.0 / 6.0));
         }
     }
     cpost[0] = c6; cpost[1] = c3; cpost[2] = c1;
 }
 
-// Rates are read as lc[(PITCH*t + j)*stride]: j = 0, 1 the corrected coalescence rates and, when PITCH == 4, j = 2, 3
-// the migration rates of the interval (written by the correction kernel; with PITCH == 2 they are re-derived from the
-// band list).
 // Expected JSFS of one item.  ALL lanes of the warp call this together (each group with its own item;
-// `active` = false for a group without work); `ysm` is a scratch area of 2*kYStride doubles private to the
-// group (two ping-pong copies of the 44-vector, padded to 48 so that every lane has a slot to write).  On return every lane of the group holds the UNNORMALISED spectrum in jafs[0..6]
-// (MigrationInference.JAFSpectrum's return value) and the number of mat-vecs in *terms.
-// `cont` (nullable): where to park the item when it meets a stiff interval (return value MISTI_STIFF = "pending");
+// `active` = false for a group without work); `rec` / `nseg` = the item's segment records (build_segments_item);
+// `ysm` is a scratch area of 2*kYStride doubles private to the group (two ping-pong copies of the 44-vector, padded
+// to 48 so that every lane has a slot to write).  On return every lane of the group holds the UNNORMALISED spectrum
+// in jafs[0..6] (MigrationInference.JAFSpectrum's return value) and the number of mat-vecs in *terms.
+// `cont` (nullable): where to park the item when it meets a stiff segment (return value MISTI_STIFF = "pending");
 // `resume`: start from the record instead of from the sampling configuration.
-template <class G, int PITCH>
-MISTI_D inline int jsfs_item(const G& g, const ModelDesc& md, bool active, const double* times, const double* params,
-                             const double* lc, long stride, const double* cpost, double* ysm, double* jafs, int* terms,
-                             Cont* cont = nullptr, bool resume = false) {
-    constexpr int RPL = (44 + G::LANES - 1) / G::LANES;
-    constexpr int W = MISTI_ELL_WIDTH;
+template <class G>
+MISTI_D inline int jsfs_item(const G& g, const ModelDesc& md, bool active, const double* params, const double* rec, int nseg,
+                             const double* cpost, double* ysm, double* jafs, int* terms, Cont* cont = nullptr,
+                             bool resume = false) {
+    constexpr int RPL = G::RPL, NLOC = G::NLOC, RW = G::RWMAX;
+    typedef typename G::Rec Rec;
     const int lane = g.lane();
+    int row[RPL];     // the states owned by this lane (44..47 = pad rows of empty slots)
     bool valid[RPL];
-    // per row, packed: ELL slot e -> coefficient-table code (kind + 4 log2(count), 12 = empty) at bit 4e;
-    // diagonal multiplicity of rate kind k at bit 16+3k
-    unsigned rc[RPL];
-    const double* yp[RPL][W];  // where this lane reads y[col] for each ELL slot (buffer 0; buffer 1 is +kYStride)
-    double* const wb = ysm + lane;  // this lane writes y[row] at wb[s * LANES] (+kYStride for buffer 1); rows 44.. are pad
-    double P[RPL];            // state probabilities at the start of the current interval (rows owned by this lane)
+    unsigned rc[RPL];  // packed coefficient-table codes (kind + 4 log2(count), 12 = none): remote slot e at bit 4e, local slot j at bit 16+4j
+    unsigned dg[RPL];  // diagonal multiplicity of rate kind k at bit 3k
+    const double* yp[RPL][RW];  // where this lane reads y[col] of each remote entry (buffer 0; buffer 1 is +kYStride)
+    double* wp[RPL];            // where it writes y[row]
+    double P[RPL];            // state probabilities at the start of the current segment (rows owned by this lane)
     double Ia[RPL], Ib[RPL];  // occupancy integrals summed over the intervals before / from the sampling date
 #pragma unroll
     for (int s = 0; s < RPL; ++s) {
-        const int r = lane + s * G::LANES;
-        valid[s] = r < 44;
-        const int rr = valid[s] ? r : 0;
-        rc[s] = 0;
+        row[s] = g.row_of(s);
+        valid[s] = row[s] < 44;
+        wp[s] = ysm + row[s];
+        rc[s] = 0; dg[s] = 0;
 #pragma unroll
-        for (int e = 0; e < W; ++e) {
-            const EllEntry en = MISTI_TAB(ell)[rr][e];
-            const unsigned cde = (!valid[s] || en.cnt == 0) ? 12u : (unsigned)en.kind + (en.cnt == 1 ? 0u : (en.cnt == 2 ? 4u : 8u));
+        for (int e = 0; e < RW; ++e) {
+            int col = 0;
+            unsigned cde = 12u;
+            if (valid[s] && e < G::rw(s)) g.rem_of(s, e, &col, &cde);
             rc[s] |= cde << (4 * e);
-            yp[s][e] = ysm + (valid[s] ? en.col : 0);
+            yp[s][e] = ysm + col;
         }
+#pragma unroll
+        for (int j = 0; j < NLOC; ++j) rc[s] |= (valid[s] ? g.loc_of(s, j) : 12u) << (16 + 4 * j);
         if (valid[s])
-            for (int k = 0; k < 4; ++k) rc[s] |= (unsigned)MISTI_TAB(diag)[r][k] << (16 + 3 * k);
-        P[s] = (valid[s] && r == 2) ? 1.0 : 0.0;  // both genome-1 lineages in deme 0, genome-2 in deme 1 (:469-471)
+            for (int k = 0; k < 4; ++k) dg[s] |= (unsigned)MISTI_TAB(diag)[row[s]][k] << (3 * k);
+        P[s] = row[s] == 2 ? 1.0 : 0.0;  // both genome-1 lineages in deme 0, genome-2 in deme 1 (:469-471)
         Ia[s] = 0.0; Ib[s] = 0.0;
     }
     int nterms = 0;
     int status = MISTI_OK;
-    int it0 = 0;
+    int seg0 = 0;
     if (resume && active && cont) {
-        it0 = cont->it;
+        seg0 = cont->seg;
         nterms = cont->nterms;
 #pragma unroll
         for (int s = 0; s < RPL; ++s) {
-            const int r = lane + s * G::LANES;
-            P[s] = valid[s] ? cont->P[r] : 0.0;
-            Ia[s] = valid[s] ? cont->Ia[r] : 0.0;
-            Ib[s] = valid[s] ? cont->Ib[r] : 0.0;
+            P[s] = valid[s] ? cont->P[row[s]] : 0.0;
+            Ia[s] = valid[s] ? cont->Ia[row[s]] : 0.0;
+            Ib[s] = valid[s] ? cont->Ib[row[s]] : 0.0;
         }
     }
     bool pending = false;
     const int numT = md.numT;
-    const int n2 = !active ? 0 : (md.splitT < numT ? md.splitT : numT);  // two-population intervals of this item
-    const bool inf_last = active && md.splitT >= numT;                    // ... the last of which is then infinite
-    const int n_fin = inf_last ? n2 - 1 : n2;
-    const bool has_pulses = md.n_pulses > 0;
+    const int nown = active ? nseg : 0;
 
-    // AncientSampleP0 (TwoPopulations.py:246-262) at it == sampleDate, then PulseMigration (:361-377)
-    auto reset_and_pulse = [&](int it, bool act) {
-        const bool do_reset = act && it == md.sampleDate && it > 0;  // identity on the start vector
+    // AncientSampleP0 (TwoPopulations.py:246-262), then PulseMigration (:361-377), before interval `it`
+    auto reset_and_pulse = [&](int it, bool do_reset, bool do_pulse) {
         if (g.any(do_reset)) {
             double a2 = 0.0, a11 = 0.0;
 #pragma unroll
             for (int s = 0; s < RPL; ++s)
                 if (valid[s]) {
-                    if (MISTI_TAB(anc2)[lane + s * G::LANES]) a2 += P[s];
-                    if (MISTI_TAB(anc11)[lane + s * G::LANES]) a11 += P[s];
+                    if (MISTI_TAB(anc2)[row[s]]) a2 += P[s];
+                    if (MISTI_TAB(anc11)[row[s]]) a11 += P[s];
                 }
             a2 = g.sum(a2); a11 = g.sum(a11);
             if (do_reset) {
 #pragma unroll
-                for (int s = 0; s < RPL; ++s) {
-                    const int r = lane + s * G::LANES;
-                    P[s] = r == 2 ? a2 : (r == 11 ? a11 : 0.0);
-                }
+                for (int s = 0; s < RPL; ++s) P[s] = row[s] == 2 ? a2 : (row[s] == 11 ? a11 : 0.0);
             }
         }
-        double pr = 0.0;
-        int src = 0;
-        if (has_pulses && act) {
-            const double pu0 = pulse_rate(md, params, it, 0), pu1 = pulse_rate(md, params, it, 1);
-            pr = pu0 + pu1;
-            src = pu0 > 0 ? 0 : 1;
-        }
-        if (g.any(pr > 0)) {  // a group without a pulse here applies the map with rate 0 = the identity
+        if (g.any(do_pulse)) {  // a group without a pulse here applies the map with rate 0 = the identity
+            double pr = 0.0;
+            int src = 0;
+            if (do_pulse) {
+                const double pu0 = pulse_rate(md, params, it, 0), pu1 = pulse_rate(md, params, it, 1);
+                pr = pu0 + pu1;
+                src = pu0 > 0 ? 0 : 1;
+            }
             const double om = 1.0 - pr;
             const PulseEntry* ent = src == 0 ? MISTI_TAB(pulse0) : MISTI_TAB(pulse1);
             const unsigned char* rp = src == 0 ? MISTI_TAB(pulse0_rowptr) : MISTI_TAB(pulse1_rowptr);
             g.sync();
 #pragma unroll
             for (int s = 0; s < RPL; ++s)
-                wb[s * G::LANES] = P[s];
+                wp[s][0] = P[s];
             g.sync();
             double pw_om[5], pw_r[5];
             pw_om[0] = 1.0; pw_r[0] = 1.0;
@@ -275,7 +470,7 @@ MISTI_D inline int jsfs_item(const G& g, const ModelDesc& md, bool active, const
             for (int s = 0; s < RPL; ++s) {
                 double acc = 0.0;
                 if (valid[s]) {
-                    const int r = lane + s * G::LANES;
+                    const int r = row[s];
                     for (int e = rp[r]; e < rp[r + 1]; ++e) {
                         const PulseEntry pe = ent[e];
                         double w = (double)pe.mult;
@@ -292,145 +487,152 @@ MISTI_D inline int jsfs_item(const G& g, const ModelDesc& md, bool active, const
         }
     };
 
-    // generator of interval `it` in uniformised form: A = I + M/q with q = max |M_cc| (per group)
-    double adiag[RPL], coef[RPL][W], qinv = 1.0, q = 1.0;
-    bool mig = false;
-    auto set_generator = [&](int it, bool act) {
-        double la0 = 1.0, la1 = 1.0, m0 = 0.0, m1 = 0.0;
-        if (act) {
-            la0 = lc[(PITCH * it) * stride]; la1 = lc[(PITCH * it + 1) * stride];
-            if (PITCH == 4) {
-                m0 = lc[(PITCH * it + 2) * stride]; m1 = lc[(PITCH * it + 3) * stride];
-            } else {
-                m0 = band_rate(md, params, it, 0); m1 = band_rate(md, params, it, 1);
-            }
-            if (!(la0 >= 0.0 && la0 <= DBL_MAX && la1 >= 0.0 && la1 <= DBL_MAX && m0 >= 0.0 && m0 <= DBL_MAX && m1 >= 0.0 &&
-                  m1 <= DBL_MAX)) {
-                status = MISTI_NONFINITE;
-                la0 = la1 = 1.0; m0 = m1 = 0.0;
-            }
-        }
-        mig = m0 + m1 != 0.0;
-        double d[RPL], dmax = 0.0;
+    // generator in uniformised form, A = I + M/q, from the coefficient table of a record
+    double adiag[RPL], coef[RPL][RW], cloc[RPL][NLOC > 0 ? NLOC : 1];
+    auto load_generator = [&](const Rec& sw) {
+        const double rq0 = sw.get(0), rq1 = sw.get(1), rq2 = sw.get(2), rq3 = sw.get(3);
 #pragma unroll
         for (int s = 0; s < RPL; ++s) {
-            d[s] = (double)((rc[s] >> 16) & 7u) * la0 + (double)((rc[s] >> 19) & 7u) * la1 +
-                   (double)((rc[s] >> 22) & 7u) * m0 + (double)((rc[s] >> 25) & 7u) * m1;
-            dmax = d[s] > dmax ? d[s] : dmax;
+            const double d = ((double)(dg[s] & 7u) * rq0 + (double)((dg[s] >> 3) & 7u) * rq1) +
+                             ((double)((dg[s] >> 6) & 7u) * rq2 + (double)((dg[s] >> 9) & 7u) * rq3);
+            adiag[s] = d < 1.0 ? 1.0 - d : 0.0;
+#pragma unroll
+            for (int e = 0; e < RW; ++e) coef[s][e] = sw.get((rc[s] >> (4 * e)) & 15u);
+#pragma unroll
+            for (int j = 0; j < NLOC; ++j) cloc[s][j] = sw.get((rc[s] >> (16 + 4 * j)) & 15u);
         }
-        q = g.max(dmax);
-        if (!(q > 0.0)) q = 1.0;  // no event possible at all: A = I
-        qinv = 1.0 / q;
-        const double rq[4] = {la0 * qinv, la1 * qinv, m0 * qinv, m1 * qinv};
-        const double mine = g.table_entry(rq);
+    };
+    // y_new[row] = (A y)[row] for the rows of this lane: diagonal and same-lane entries from registers (yk), the rest
+    // from the shared copy of y at offset RO
+    auto matvec = [&](const double* yk, const int RO, double* acc) {
 #pragma unroll
         for (int s = 0; s < RPL; ++s) {
-            adiag[s] = (q - d[s]) * qinv;
+            double a = adiag[s] * yk[s];
+            if (NLOC == 2) {
+                a = fma(cloc[s][0], yk[(s + 1) % RPL], a);
+                a = fma(cloc[s][NLOC - 1], yk[(s + 2) % RPL], a);
+            }
 #pragma unroll
-            for (int e = 0; e < W; ++e) coef[s][e] = g.table_get(mine, (rc[s] >> (4 * e)) & 15u, rq);
+            for (int e = 0; e < RW; ++e)
+                if (e < G::rw(s)) a = fma(coef[s][e], yp[s][e][RO], a);
+            acc[s] = a;
         }
     };
 
-    const int n_loop = g.wmax(n_fin > it0 ? n_fin - it0 : 0);
-    for (int j = 0; j < n_loop; ++j) {
-        const int it = it0 + j;
-        bool act = !pending && it < n_fin;  // a group past its own last interval idles on a zero-length interval
-        set_generator(it, act);
-        double T = act ? times[it] : 0.0;
-        if (!(T >= 0.0 && T <= DBL_MAX)) { status = MISTI_NONFINITE; T = 0.0; }
-        // rates of 1e5 and more per unit of interval length only come out of a run-away correction; such an interval
-        // is not swept here (it would stall the warp for millions of terms): the item is parked for the dense step
-        if (q * T > kUnifMaxStiff) {
-            if (cont) {
-                if (lane == 0) { cont->it = it; cont->nterms = nterms; }
-#pragma unroll
-                for (int s = 0; s < RPL; ++s) {
-                    const int r = lane + s * G::LANES;
-                    if (r < 48) { cont->P[r] = P[s]; cont->Ia[r] = Ia[s]; cont->Ib[r] = Ib[s]; }
-                }
-                pending = true;
-            } else {
-                status = MISTI_STIFF;
-            }
-            act = false;
-            T = 0.0;
-        }
-        reset_and_pulse(it, act);
-        const double qT = q * T;
-        const int nsub = g.wmax(qT > kUnifMaxStep ? (int)ceil(qT / kUnifMaxStep) : 1);
-        const double lam = nsub == 1 ? qT : qT / nsub;
-        const double p0 = exp(-lam), t0 = -expm1(-lam);  // Poisson P(N = 0) and P(N > 0)
+    // one interval with migration: uniformisation sweep(s)
+    auto sweep = [&](const Rec& rv, bool is, unsigned long long meta) {
+        const Rec sw = g.rec_select(rv, is);
+        load_generator(sw);
+        const double qinv = sw.get(10), lam_own = sw.get(11), p0_own = sw.get(13), t0_own = sw.get(14);
+        const int K_own = is ? seg_K(meta) : 0, nsub_own = is ? seg_nsub(meta) : 0;
+        const int nsub = g.wmax(nsub_own);
         double Iint[RPL];
 #pragma unroll
         for (int s = 0; s < RPL; ++s) Iint[s] = 0.0;
         for (int sub = 0; sub < nsub; ++sub) {
+            const bool live = sub < nsub_own;
+            double lam = live ? lam_own : 0.0;
+            const double p0 = live ? p0_own : 1.0, t0 = live ? t0_own : 0.0;
+            const int Ks = live ? K_own : 0;
+            const int Kmin = g.wmin(live ? Ks : INT_MAX);  // some group is live in every sub-step
+            const int Kmax = g.wmax(Ks);
             double yk[RPL], P1[RPL];
             g.sync();
 #pragma unroll
             for (int s = 0; s < RPL; ++s) {
                 yk[s] = P[s]; P1[s] = p0 * P[s];
-                wb[s * G::LANES] = P[s];
+                wp[s][0] = P[s];
             }
             double p = p0;     // Pois(k; lam)
             double tail = t0;  // P(N > k)
             double r = lam;    // lam / (k + 1): ratio of consecutive Poisson weights
             int k = 0;
-            // one term: I += P(N > k-1) y_(k-1);  y_k <- A y_(k-1) (read buffer RO, write buffer WO);  P1 += Pois(k) y_k.
-            // Returns true when this group's Poisson tail beyond the term is below kUnifTol.
-            auto term = [&](const int RO, const int WO) -> bool {
+            // one term: I += P(N > k-1) y_(k-1);  y_k <- A y_(k-1) (read buffer RO, write buffer WO);  P1 += Pois(k) y_k
+            auto term = [&](const int RO, const int WO) {
                 g.sync();
                 ++k;
                 p *= r;
                 r = lam * MISTI_RECIP(k + 1);
+                double acc[RPL];
+                matvec(yk, RO, acc);
 #pragma unroll
                 for (int s = 0; s < RPL; ++s) {
-                    // two short FMA chains per row instead of one long one
-                    const double u = fma(coef[s][1], yp[s][1][RO], fma(coef[s][0], yp[s][0][RO], adiag[s] * yk[s]));
-                    const double v = fma(coef[s][3], yp[s][3][RO], coef[s][2] * yp[s][2][RO]);
-                    const double acc = u + v;
                     Iint[s] = fma(tail, yk[s], Iint[s]);
-                    yk[s] = acc;
-                    wb[WO + s * G::LANES] = acc;
-                    P1[s] = fma(p, acc, P1[s]);
+                    yk[s] = acc[s];
+                    wp[s][WO] = acc[s];
+                    P1[s] = fma(p, acc[s], P1[s]);
                 }
                 tail -= p;
-                return r < 1.0 && p < kUnifTol * (1.0 - r);
             };
-            while (true) {  // the two halves of the ping-pong buffer get compile-time offsets
-                if (g.all(term(0, kYStride))) break;
-                if (g.all(term(kYStride, 0))) break;
-                if (k >= kUnifMaxTerms) { status = MISTI_NONFINITE; break; }
+            // the terms every group needs: the two halves of the ping-pong buffer get compile-time offsets
+            while (k + 2 <= Kmin) {
+                term(0, kYStride);
+                term(kYStride, 0);
             }
-            if (act) nterms += k;
+            int cur = 0;
+            if (k < Kmin) { term(0, kYStride); cur = kYStride; }
+            // the rest: a group whose own series has ended goes on with zero weights (exact no-op)
+            while (k < Kmax) {
+                if (k >= Ks) { lam = 0.0; r = 0.0; tail = 0.0; }
+                term(cur, kYStride - cur);
+                cur = kYStride - cur;
+            }
+            if (live) nterms += Ks;
 #pragma unroll
             for (int s = 0; s < RPL; ++s) P[s] = P1[s];
         }
         // integralP of this interval joins the running sums; categories 2..6 are muted before the sampling
         // date (:501-506), hence the two accumulators
-        if (it < md.sampleDate) {
+        const bool pre = (meta & kSegPre) != 0;
+        const double qa = pre ? qinv : 0.0, qb = pre ? 0.0 : qinv;
 #pragma unroll
-            for (int s = 0; s < RPL; ++s) Ia[s] = fma(Iint[s], qinv, Ia[s]);
-        } else {
-#pragma unroll
-            for (int s = 0; s < RPL; ++s) Ib[s] = fma(Iint[s], qinv, Ib[s]);
+        for (int s = 0; s < RPL; ++s) {
+            Ia[s] = fma(Iint[s], qa, Ia[s]);
+            Ib[s] = fma(Iint[s], qb, Ib[s]);
         }
-    }
-    if (g.any(inf_last && !pending)) {
-        // no split inside the grid: the last two-population interval is infinite (MigrationInference.py:475-476,
-        // 535-538): P1 = 0, integralP = -inv(M) P0 = (1/q) sum_k A^k P0, finite only with migration.
-        const int it = numT - 1;
-        const bool inf_now = inf_last && !pending;
-        reset_and_pulse(it, inf_now);
-        set_generator(it, inf_now);
-        if (inf_now && !mig && status == MISTI_OK) status = MISTI_INFINITE_COAL_TIME;
-        const bool run = inf_now && mig;
+    };
+
+    // a run of intervals without migration: P <- sum_ab e_ab G_ab P, integral += sum_ab c_ab G_ab P
+    auto runop = [&](const Rec& rv, bool is, unsigned long long meta) {
+        g.sync();
+#pragma unroll
+        for (int s = 0; s < RPL; ++s) wp[s][0] = P[s];
+        g.rec_store(rv, ysm + kYStride);
+        g.sync();
+        if (is) {
+            const double* cc = ysm + kYStride;
+            const bool pre = (meta & kSegPre) != 0;
+#pragma unroll
+            for (int s = 0; s < RPL; ++s)
+                if (valid[s]) {
+                    double pe = 0.0, ir = 0.0;
+                    for (int e = MISTI_TAB(nm_rowptr)[row[s]]; e < MISTI_TAB(nm_rowptr)[row[s] + 1]; ++e) {
+                        const int ab = MISTI_TAB(nm_ab)[e];
+                        const double t = MISTI_TAB(nm_val)[e] * ysm[MISTI_TAB(nm_col)[e]];
+                        ir = fma(cc[ab], t, ir);
+                        pe = fma(ab == 0 ? 1.0 : cc[7 + ab], t, pe);
+                    }
+                    P[s] = pe;
+                    if (pre) Ia[s] += ir;
+                    else Ib[s] += ir;
+                }
+            nterms += 1;
+        }
+    };
+
+    // no split inside the grid: the last two-population interval is infinite (MigrationInference.py:475-476,
+    // 535-538): P1 = 0, integralP = -inv(M) P0 = (1/q) sum_k A^k P0 (finite only with migration)
+    auto infsum = [&](const Rec& rv, bool is, unsigned long long meta) {
+        const Rec sw = g.rec_select(rv, is);
+        load_generator(sw);
+        const double qinv = sw.get(10);
         double yk[RPL], Iint[RPL];
         g.sync();
 #pragma unroll
         for (int s = 0; s < RPL; ++s) {
-            yk[s] = run ? P[s] : 0.0;
+            yk[s] = is ? P[s] : 0.0;
             Iint[s] = yk[s];
-            wb[s * G::LANES] = yk[s];
+            wp[s][0] = yk[s];
         }
         double nprev = 0.0;
 #pragma unroll
@@ -439,19 +641,18 @@ MISTI_D inline int jsfs_item(const G& g, const ModelDesc& md, bool active, const
         double itot = nprev;
         bool done = !(nprev > 0.0);
         int k = 0, cur = 0;
-        while (!g.all(done)) {
+        while (g.any(!done)) {
             g.sync();
             const int ro = kYStride * cur, wo = kYStride * (cur ^ 1);
-            double nk = 0.0;
+            double nk = 0.0, acc[RPL];
+            matvec(yk, ro, acc);
 #pragma unroll
             for (int s = 0; s < RPL; ++s) {
-                double acc = adiag[s] * yk[s];
-#pragma unroll
-                for (int e = 0; e < W; ++e) acc += coef[s][e] * yp[s][e][ro];
-                yk[s] = acc;
-                wb[wo + s * G::LANES] = acc;
-                Iint[s] += acc;
-                nk += acc;
+                if (done) acc[s] = 0.0;  // this group's series has ended: keep its sums as they are
+                yk[s] = acc[s];
+                wp[s][wo] = acc[s];
+                Iint[s] += acc[s];
+                nk += acc[s];
             }
             cur ^= 1;
             ++k;
@@ -459,12 +660,17 @@ MISTI_D inline int jsfs_item(const G& g, const ModelDesc& md, bool active, const
             itot += nk;
             const double rho = nprev > 0.0 ? nk / nprev : 0.0;  // contraction of the remaining mass
             nprev = nk;
-            if (!(nk > 0.0) || (rho < 1.0 && nk * rho < kUnifTol * itot * (1.0 - rho))) done = true;
-            if (k > 2000000) { if (!done) status = MISTI_NONFINITE; break; }
+            if (!done && (!(nk > 0.0) || (rho < 1.0 && nk * rho < kUnifTol * itot * (1.0 - rho)))) {
+                done = true;
+                if (is) nterms += k;
+            }
+            if (k > 2000000) {
+                if (!done) status = MISTI_NONFINITE;
+                break;
+            }
         }
-        if (run) {
-            nterms += k;
-            const bool pre = it < md.sampleDate;
+        if (is) {
+            const bool pre = (meta & kSegPre) != 0;
 #pragma unroll
             for (int s = 0; s < RPL; ++s) {
                 if (pre) Ia[s] = fma(Iint[s], qinv, Ia[s]);
@@ -472,6 +678,33 @@ MISTI_D inline int jsfs_item(const G& g, const ModelDesc& md, bool active, const
                 P[s] = 0.0;
             }
         }
+    };
+
+    const int n_loop = g.wmax(nown > seg0 ? nown - seg0 : 0);
+    for (int j = 0; j < n_loop; ++j) {
+        const int sg = seg0 + j;
+        const bool have = !pending && sg < nown;  // a group past its own last segment idles
+        const Rec rv = g.rec_load(rec + (long)sg * kRecSlots, have);
+        const double mslot = rv.get(15);
+        const unsigned long long meta = have ? seg_meta_bits(mslot) : 0ull;
+        int type = seg_type(meta);
+        const int it = seg_it(meta);
+        if (type == SEG_STIFF) {
+            if (cont) {
+                if (lane == 0) { cont->seg = sg; cont->nterms = nterms; }
+#pragma unroll
+                for (int s = 0; s < RPL; ++s) { cont->P[row[s]] = P[s]; cont->Ia[row[s]] = Ia[s]; cont->Ib[row[s]] = Ib[s]; }
+                pending = true;
+            } else {
+                status = MISTI_STIFF;
+            }
+            type = SEG_NOP;
+        }
+        const bool do_reset = type != SEG_NOP && (meta & kSegReset) != 0, do_pulse = type != SEG_NOP && (meta & kSegPulse) != 0;
+        if (g.any(do_reset || do_pulse)) reset_and_pulse(it, do_reset, do_pulse);
+        if (g.any(type == SEG_MIG)) sweep(rv, type == SEG_MIG, meta);
+        if (g.any(type == SEG_RUN)) runop(rv, type == SEG_RUN, meta);
+        if (g.any(type == SEG_INF)) infsum(rv, type == SEG_INF, meta);
     }
     // JAFS = StateToJAF . (sum of the interval integrals) (:501-506)
     double jl[7];
@@ -482,7 +715,7 @@ MISTI_D inline int jsfs_item(const G& g, const ModelDesc& md, bool active, const
         if (valid[s]) {
 #pragma unroll
             for (int c = 0; c < 7; ++c) {
-                const double w = (double)MISTI_TAB(w44)[c][lane + s * G::LANES];
+                const double w = (double)MISTI_TAB(w44)[c][row[s]];
                 jl[c] += w * (c < 2 ? Ia[s] + Ib[s] : Ib[s]);
             }
         }
@@ -494,16 +727,13 @@ MISTI_D inline int jsfs_item(const G& g, const ModelDesc& md, bool active, const
 #pragma unroll
             for (int s = 0; s < RPL; ++s)
                 if (valid[s]) {
-                    if (MISTI_TAB(anc2)[lane + s * G::LANES]) a2 += P[s];
-                    if (MISTI_TAB(anc11)[lane + s * G::LANES]) a11 += P[s];
+                    if (MISTI_TAB(anc2)[row[s]]) a2 += P[s];
+                    if (MISTI_TAB(anc11)[row[s]]) a11 += P[s];
                 }
             a2 = g.sum(a2); a11 = g.sum(a11);
             if (do_reset) {
 #pragma unroll
-                for (int s = 0; s < RPL; ++s) {
-                    const int r = lane + s * G::LANES;
-                    P[s] = r == 2 ? a2 : (r == 11 ? a11 : 0.0);
-                }
+                for (int s = 0; s < RPL; ++s) P[s] = row[s] == 2 ? a2 : (row[s] == 11 ? a11 : 0.0);
             }
         }
         // CollapsePops (:518-528): 44 -> 8 block sums
@@ -513,7 +743,7 @@ MISTI_D inline int jsfs_item(const G& g, const ModelDesc& md, bool active, const
             double v = 0.0;
 #pragma unroll
             for (int s = 0; s < RPL; ++s)
-                if (valid[s] && MISTI_TAB(collapse)[lane + s * G::LANES] == b) v += P[s];
+                if (valid[s] && MISTI_TAB(collapse)[row[s]] == b) v += P[s];
             P8[b] = g.sum(v);
         }
         const double c6 = post ? cpost[0] : 0.0, c3 = post ? cpost[1] : 0.0, c1 = post ? cpost[2] : 0.0;

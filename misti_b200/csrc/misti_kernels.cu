@@ -32,7 +32,7 @@ constexpr int kCorrectMinBlocks = 8;
 constexpr int kJsfsWarps = 4;      // warps per block of the JSFS kernel (8 items per block)
 constexpr int kJsfsMinBlocks = 4;  // occupancy target: caps the kernel at 128 registers per thread
 constexpr int kMaxChunk = 1 << 20;
-constexpr int kPitch = 4;  // per interval and item the rate buffer holds la0, la1, m0, m1
+constexpr int kPitch = 2;  // per interval and item the rate buffer holds la0, la1
 
 static __device__ const double d_l8[8][8] = MISTI_L8_INIT;
 static __device__ const unsigned char d_w8[7][8] = MISTI_W8_INIT;
@@ -45,7 +45,8 @@ __global__ void __launch_bounds__(kCorrectThreads, MINB)
 misti_correct_kernel(int B, int P, const double* __restrict__ params, const int* __restrict__ model_ids, int model_default,
                      const ModelDesc* __restrict__ models, const double* __restrict__ times, const double* __restrict__ lh,
                      unsigned flags, double mixtureTH, const double* __restrict__ lc_inject, int numT_max, double* lc,
-                     long stride, double* __restrict__ cpost, double* pr_out, int* __restrict__ status, int* __restrict__ nfev) {
+                     long stride, double* __restrict__ cpost, double* pr_out, int* __restrict__ status, int* __restrict__ nfev,
+                     double* __restrict__ rec, int seg_cap, int* __restrict__ nseg) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     const ModelDesc& md = models[model_ids ? model_ids[b] : model_default];
@@ -67,14 +68,13 @@ misti_correct_kernel(int B, int P, const double* __restrict__ params, const int*
         st = misti::correct_lambdas_item(md, tt, ll, par, flags, mixtureTH, lcb, kPitch, stride, pr, &nf);
     }
     double cp[3] = {0.0, 0.0, 0.0};
+    int ns = 0;
     if (st == MISTI_OK) {
         misti::post_split_coeffs(md, tt, lcb, kPitch, stride, cp);
-        const int n2 = md.splitT < md.numT ? md.splitT : md.numT;
-        for (int t = 0; t < n2; ++t) {  // migration rates of the two-population intervals, for the JSFS kernel
-            lcb[(kPitch * t + 2) * stride] = misti::band_rate(md, par, t, 0);
-            lcb[(kPitch * t + 3) * stride] = misti::band_rate(md, par, t, 1);
-        }
+        // all per-interval scalar work of the JSFS stage: the item's segment records
+        st = misti::build_segments_item(md, tt, par, lcb, kPitch, stride, rec + (long)b * seg_cap * misti::kRecSlots, &ns);
     }
+    nseg[b] = ns;
     cpost[b] = cp[0];
     cpost[stride + b] = cp[1];
     cpost[2 * stride + b] = cp[2];
@@ -88,7 +88,7 @@ misti_correct_kernel(int B, int P, const double* __restrict__ params, const int*
 template <int MINB>
 __global__ void __launch_bounds__(kJsfsWarps * 32, MINB)
 misti_jsfs_kernel(int B, int P, const double* __restrict__ params, const int* __restrict__ model_ids, int model_default,
-                  const ModelDesc* __restrict__ models, const double* __restrict__ times, const double* __restrict__ lc,
+                  const ModelDesc* __restrict__ models, const double* __restrict__ rec, int seg_cap, const int* __restrict__ nseg,
                   long stride, const double* __restrict__ cpost, const double* __restrict__ data, int R, int unfolded,
                   double* __restrict__ llh, double* __restrict__ jafs, double* __restrict__ jafs_raw, int* __restrict__ status,
                   int* __restrict__ terms, const int* __restrict__ row_ids, misti::Cont* __restrict__ conts,
@@ -114,9 +114,9 @@ misti_jsfs_kernel(int B, int P, const double* __restrict__ params, const int* __
         double raw[7], jn[7], logj[7];
         int nt = 0;
         const double cp[3] = {cpost[b], cpost[stride + b], cpost[2 * stride + b]};
-        const int js = misti::jsfs_item<misti::HalfWarpLanes, kPitch>(g, md, has && st == MISTI_OK, times + md.grid_off,
-                                                                      params + (long)b * P, lc + b, stride, cp, ysm, raw, &nt,
-                                                                      conts ? conts + b : nullptr, resume);
+        const int js = misti::jsfs_item<misti::HalfWarpLanes>(g, md, has && st == MISTI_OK, params + (long)b * P,
+                                                              rec + (long)b * seg_cap * misti::kRecSlots, nseg[b], cp, ysm, raw, &nt,
+                                                              conts ? conts + b : nullptr, resume);
         if (!has) continue;
         if (st == MISTI_OK) st = js;
         if (st == MISTI_STIFF && conts && next_list) {  // parked: queue it for the dense step; results come from a later pass
@@ -188,8 +188,9 @@ __device__ void dense_square(const double* __restrict__ A, double* __restrict__ 
 __global__ void __launch_bounds__(kStiffThreads)
 misti_stiff_kernel(int P, const double* __restrict__ params, const int* __restrict__ model_ids, int model_default,
                    const ModelDesc* __restrict__ models, const double* __restrict__ times, const double* __restrict__ lc,
-                   long stride, misti::Cont* __restrict__ conts, const int* __restrict__ item_list,
-                   const int* __restrict__ item_count, int* __restrict__ status) {
+                   long stride, const double* __restrict__ rec, int seg_cap, const int* __restrict__ nseg,
+                   misti::Cont* __restrict__ conts, const int* __restrict__ item_list, const int* __restrict__ item_count,
+                   int* __restrict__ status) {
     extern __shared__ double sm[];
     double* E = sm;                      // [48][kLd]
     double* Y = sm + 48 * kLd;           // [48][kLd]
@@ -198,6 +199,7 @@ misti_stiff_kernel(int P, const double* __restrict__ params, const int* __restri
     double* Pv = vec; double* tmp = vec + 48; double* adiag = vec + 96; double* aug = vec + 144; double* coef = vec + 192;
     __shared__ double s_scal[4];
     __shared__ int s_flag[2];
+    (void)s_scal;
     const int tid = threadIdx.x;
     const int n_items = *item_count;
     for (int i = blockIdx.x; i < n_items; i += gridDim.x) {
@@ -206,17 +208,19 @@ misti_stiff_kernel(int P, const double* __restrict__ params, const int* __restri
         const double* par = params + (long)b * P;
         const double* tt = times + md.grid_off;
         misti::Cont* ct = conts + b;
-        const int numT = md.numT;
-        const int n2 = md.splitT < numT ? md.splitT : numT;
-        const int n_fin = md.splitT >= numT ? n2 - 1 : n2;
-        int it = ct->it;
+        const double* rb = rec + (long)b * seg_cap * misti::kRecSlots;
+        const int ns = nseg[b];
+        int seg = ct->seg;
         int nterms = ct->nterms;
         if (tid < 48) Pv[tid] = ct->P[tid];
         __syncthreads();
         int st = MISTI_OK;
-        while (it < n_fin) {
+        while (seg < ns) {  // the stiff segment the item was parked at, and any that follow it directly
+            const unsigned long long meta = misti::seg_meta_bits(rb[seg * misti::kRecSlots + 15]);
+            if (misti::seg_type(meta) != misti::SEG_STIFF) break;  // an ordinary segment: back to the sweep kernel
+            const int it = misti::seg_it(meta);
             const double la0 = lc[(kPitch * it) * stride + b], la1 = lc[(kPitch * it + 1) * stride + b];
-            const double m0 = lc[(kPitch * it + 2) * stride + b], m1 = lc[(kPitch * it + 3) * stride + b];
+            const double m0 = misti::band_rate(md, par, it, 0), m1 = misti::band_rate(md, par, it, 1);
             const double T = tt[it];
             const double rate[4] = {la0, la1, m0, m1};
             // q = max |M_cc|
@@ -233,11 +237,9 @@ misti_stiff_kernel(int P, const double* __restrict__ params, const int* __restri
                 const bool bad = !(q > 0.0 && q <= DBL_MAX && T >= 0.0 && T <= DBL_MAX);
                 s_scal[0] = bad ? 1.0 : q;
                 s_flag[0] = bad ? 1 : 0;
-                s_flag[1] = (!bad && q * T > misti::kUnifMaxStiff) ? 1 : 0;  // still stiff?
             }
             __syncthreads();
             if (s_flag[0]) { st = MISTI_NONFINITE; break; }
-            if (!s_flag[1]) break;  // an ordinary interval: back to the sweep kernel
             const double q = s_scal[0], qinv = 1.0 / q;
             // ancient-sample reset (TwoPopulations.py:246-262) and pulse (:361-377) of this interval
             if (it == md.sampleDate && it > 0) {
@@ -348,14 +350,14 @@ misti_stiff_kernel(int P, const double* __restrict__ params, const int* __restri
             __syncthreads();
             if (tid < 44) Pv[tid] = tmp[tid];
             __syncthreads();
-            ++it;
+            ++seg;
             if (st != MISTI_OK) break;
         }
         if (tid < 48) ct->P[tid] = tid < 44 ? Pv[tid] : 0.0;
         if (tid == 0) {
-            ct->it = it;
+            ct->seg = seg;
             ct->nterms = nterms;
-            if (st != MISTI_OK) { status[b] = st; ct->it = -1; }
+            if (st != MISTI_OK) status[b] = st;
         }
         __syncthreads();
     }
@@ -473,7 +475,10 @@ struct misti_ctx {
     // batch buffers
     size_t cap = 0;
     int cap_numT = 0;
+    int cap_seg = 0;
     double *d_lc = nullptr, *d_cpost = nullptr;
+    double* d_rec = nullptr;  // segment records [cap][cap_seg][16]
+    int* d_nseg = nullptr;
     int *d_status = nullptr, *d_nfev = nullptr;
     misti::Cont* d_conts = nullptr;       // continuation records of parked (stiff) items
     int *d_queue[2] = {nullptr, nullptr}; // item lists of the stiff rounds
@@ -563,12 +568,27 @@ int sync_tables(misti_ctx* ctx) {
     return 0;
 }
 
+// most two-population segments any registered model can have
+int max_segments(const misti_ctx* ctx) {
+    int m = 1;
+    for (const ModelDesc& md : ctx->h_models) {
+        const int n2 = md.splitT < md.numT ? md.splitT : md.numT;
+        if (n2 > m) m = n2;
+    }
+    return m;
+}
+
 int ensure_batch(misti_ctx* ctx, size_t B) {
-    if (B <= ctx->cap && ctx->cap_numT >= ctx->numT_max) return 0;
+    const int seg_need = max_segments(ctx);
+    if (B <= ctx->cap && ctx->cap_numT >= ctx->numT_max && ctx->cap_seg >= seg_need) return 0;
     size_t ncap = ctx->cap ? ctx->cap : 1024;
     while (ncap < B) ncap *= 2;
     int rc;
+    CK(cudaStreamSynchronize(ctx->stream));  // the previous launches may still use the buffers
     if ((rc = realloc_exact(ctx, &ctx->d_lc, ncap * kPitch * (size_t)ctx->numT_max))) return rc;
+    if ((rc = realloc_exact(ctx, &ctx->d_rec, ncap * (size_t)seg_need * misti::kRecSlots))) return rc;
+    if ((rc = realloc_exact(ctx, &ctx->d_nseg, ncap))) return rc;
+    ctx->cap_seg = seg_need;
     if ((rc = realloc_exact(ctx, &ctx->d_cpost, ncap * 3))) return rc;
     if ((rc = realloc_exact(ctx, &ctx->d_status, ncap))) return rc;
     if ((rc = realloc_exact(ctx, &ctx->d_nfev, ncap))) return rc;
@@ -623,7 +643,7 @@ void misti_ctx_destroy(misti_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     void* ptrs[] = {ctx->d_times, ctx->d_lh, ctx->d_models, ctx->d_data, ctx->d_lc, ctx->d_cpost, ctx->d_status, ctx->d_nfev, ctx->d_conts, ctx->d_queue[0], ctx->d_queue[1], ctx->d_counts,
-                    ctx->s_params, ctx->s_llh, ctx->s_jafs, ctx->s_jafs_raw, ctx->s_model_ids, ctx->s_terms, ctx->s_row_ids, ctx->s_lc_io,
+                    ctx->d_rec, ctx->d_nseg, ctx->s_params, ctx->s_llh, ctx->s_jafs, ctx->s_jafs_raw, ctx->s_model_ids, ctx->s_terms, ctx->s_row_ids, ctx->s_lc_io,
                     ctx->s_pr, ctx->d_small};
     for (void* p : ptrs)
         if (p) cudaFree(p);
@@ -764,7 +784,7 @@ static int eval_chunk(misti_ctx* ctx, int B, int P, const double* d_params, cons
 #define MISTI_LAUNCH_CORRECT(MINB)                                                                                       \
     misti_correct_kernel<MINB><<<(B + kCorrectThreads - 1) / kCorrectThreads, kCorrectThreads, 0, ctx->stream>>>(          \
         B, P, d_params, d_model_ids, model_default, ctx->d_models, ctx->d_times, ctx->d_lh, flags, mixture_th, d_lc_inject, \
-        numT_max, ctx->d_lc, stride, ctx->d_cpost, d_pr, ctx->d_status, ctx->d_nfev)
+        numT_max, ctx->d_lc, stride, ctx->d_cpost, d_pr, ctx->d_status, ctx->d_nfev, ctx->d_rec, ctx->cap_seg, ctx->d_nseg)
     switch (ctx->correct_minb) {  // register budget per thread: 4 -> 255, 8 -> 128, 12 -> 80 (tuning knob MISTI_CORRECT_MINB)
         case 4: MISTI_LAUNCH_CORRECT(4); break;
         case 12: MISTI_LAUNCH_CORRECT(12); break;
@@ -779,7 +799,8 @@ static int eval_chunk(misti_ctx* ctx, int B, int P, const double* d_params, cons
     CK(cudaMemsetAsync(ctx->d_counts, 0, 8 * sizeof(int), ctx->stream));
 #define MISTI_LAUNCH_JSFS(MINB, GRID, LIST, COUNT, NEXT, NEXTCOUNT)                                                       \
     misti_jsfs_kernel<MINB><<<GRID, kJsfsWarps * 32, 0, ctx->stream>>>(                                                   \
-        B, P, d_params, d_model_ids, model_default, ctx->d_models, ctx->d_times, ctx->d_lc, stride, ctx->d_cpost, ctx->d_data, \
+        B, P, d_params, d_model_ids, model_default, ctx->d_models, ctx->d_rec, ctx->cap_seg, ctx->d_nseg, stride, ctx->d_cpost, \
+        ctx->d_data, \
         ctx->R, ctx->unfolded, d_llh, d_jafs, d_jafs_raw, ctx->d_status, d_terms, d_row_ids, ctx->d_conts, LIST, COUNT, NEXT, \
         NEXTCOUNT)
 #define MISTI_LAUNCH_JSFS_ANY(GRID, LIST, COUNT, NEXT, NEXTCOUNT)                                                          \
@@ -797,8 +818,8 @@ static int eval_chunk(misti_ctx* ctx, int B, int P, const double* d_params, cons
     // are fixed; with an empty queue (the usual case) both kernels return at once.
     for (int r = 0; r < kStiffRounds; ++r) {
         misti_stiff_kernel<<<ctx->sm_count, kStiffThreads, kStiffSmem, ctx->stream>>>(
-            P, d_params, d_model_ids, model_default, ctx->d_models, ctx->d_times, ctx->d_lc, stride, ctx->d_conts,
-            ctx->d_queue[r & 1], ctx->d_counts + r, ctx->d_status);
+            P, d_params, d_model_ids, model_default, ctx->d_models, ctx->d_times, ctx->d_lc, stride, ctx->d_rec, ctx->cap_seg,
+            ctx->d_nseg, ctx->d_conts, ctx->d_queue[r & 1], ctx->d_counts + r, ctx->d_status);
         CK(cudaGetLastError());
         MISTI_LAUNCH_JSFS_ANY(ctx->sm_count * 2, (const int*)ctx->d_queue[r & 1], (const int*)(ctx->d_counts + r),
                               ctx->d_queue[(r + 1) & 1], ctx->d_counts + r + 1);

@@ -3,6 +3,7 @@
 // can be unit-tested against the oracle in a container without a GPU.  It is NOT part of the
 // product: libmisti_b200.so has no CPU path and nothing under misti_b200/ loads this library.
 #include <cstring>
+#include <vector>
 #include "../../misti_b200/csrc/misti_model.cuh"
 #include "../../misti_b200/csrc/misti_jsfs.cuh"
 
@@ -46,6 +47,16 @@ static void fill_model(misti::ModelDesc& md, int numT, int splitT, int sampleDat
     }
 }
 
+static int hs_types_buf[256];
+static int* hs_last_types = hs_types_buf;
+static int hs_last_nseg = 0;
+
+// segment types of the last hs_jsfs call (1 = swept interval, 2 = closed-form run, 3 = stiff, 4 = infinite)
+int hs_segment_types(int* out, int cap) {
+    for (int i = 0; i < hs_last_nseg && i < cap; ++i) out[i] = hs_types_buf[i];
+    return hs_last_nseg;
+}
+
 // expected JSFS (unnormalised raw[7], normalised jn[7]) and llh for one data row, given lc[numT][2]
 int hs_jsfs(int numT, int splitT, int sampleDate, const double* times, int n_bands, const double* bands, int n_pulses,
             const double* pulses, int n_params, const double* params, const double* lc, int unfolded,
@@ -54,8 +65,16 @@ int hs_jsfs(int numT, int splitT, int sampleDate, const double* times, int n_ban
     fill_model(md, numT, splitT, sampleDate, n_bands, bands, n_pulses, pulses, n_params);
     double cpost[3], ysm[2 * misti::kYStride], logj[7];
     misti::post_split_coeffs(md, times, lc, 2, 1, cpost);
+    std::vector<double> rec((size_t)(numT + 1) * misti::kRecSlots);
+    int nseg = 0;
+    int st = misti::build_segments_item(md, times, params, lc, 2, 1, rec.data(), &nseg);
+    if (st != MISTI_OK) return st;
+    if (hs_last_types) {
+        for (int i = 0; i < nseg && i < 256; ++i) hs_last_types[i] = misti::seg_type(misti::seg_meta_bits(rec[i * misti::kRecSlots + 15]));
+        hs_last_nseg = nseg;
+    }
     misti::SingleLane g;
-    const int st = misti::jsfs_item<misti::SingleLane, 2>(g, md, true, times, params, lc, 1, cpost, ysm, raw, terms);
+    st = misti::jsfs_item<misti::SingleLane>(g, md, true, params, rec.data(), nseg, cpost, ysm, raw, terms);
     if (st != MISTI_OK) return st;
     if (!misti::jafs_normalise_logs(raw, unfolded != 0, jn, logj)) return MISTI_NONFINITE;
     *llh = misti::score_row(drow, logj);

@@ -164,6 +164,92 @@ def main():
     anc2 = [int(sum(1 for l in st if l == (1, 0, 0)) == 2) for st in STATES]
     anc11 = [int(sum(1 for l in st if l == (2, 0, 0)) == 1) for st in STATES]
     stationary = [i for i, st in enumerate(STATES) if len(st) == 2 and st[0][2] != st[1][2]]
+    # ---- state -> (lane, slot) map of the 16-lane device kernel.  Each lane owns three states (a, b, c); an
+    # off-diagonal entry whose column is owned by the same lane is served from registers ("local"), the others
+    # ("remote") are read from shared memory: at most 3 / 2 / 3 remote entries for slot a / b / c.  Lanes are
+    # paths a - b - c of the migration graph (b in the middle) or adjacent pairs (a, c) with a two-entry state
+    # (or nothing) in slot b; slots left empty write to the pad rows 44..47.
+    ell = [[e[1:] for e in ent if e[0] == r] for r in range(44)]
+    lanes16 = [[3, 4, 5], [1, None, 7], [9, 10, 11], [12, 13, 14], [23, 24, 25], [26, 27, 28], [15, 16, 18], [17, 21, 22],
+               [41, 42, 43], [29, 0, 30], [31, 2, 32], [33, 6, 34], [35, 8, 36], [37, None, 38], [39, None, 40], [19, None, 20]]
+    assert sorted(v for ln in lanes16 for v in ln if v is not None) == list(range(44))
+    RW = (3, 2, 3)
+
+    def code_of(kind, cnt):
+        return kind + {1: 0, 2: 4, 4: 8}[cnt]
+    l16_row, l16_rem, l16_loc, pad = [], [], [], 44
+    for ln in lanes16:
+        rows, rems, locs = [], [], []
+        for sl, r in enumerate(ln):
+            if r is None:
+                rows.append(pad)
+                pad += 1
+                rems.append([(0, 12)] * 3)
+                locs.append([12, 12])
+                continue
+            rows.append(r)
+            others = [ln[(sl + 1) % 3], ln[(sl + 2) % 3]]
+            loc, rem = [12, 12], []
+            for (c, k, n) in ell[r]:
+                if c in others:
+                    loc[others.index(c)] = code_of(k, n)
+                else:
+                    rem.append((c, code_of(k, n)))
+            assert len(rem) <= RW[sl], (r, rem)
+            rems.append(rem + [(r, 12)] * (3 - len(rem)))
+            locs.append(loc)
+        l16_row.append(rows)
+        l16_rem.append(rems)
+        l16_loc.append(locs)
+    assert pad <= 48
+    # ---- q = max |M_cc| needs only the Pareto-maximal diagonal multiplicity tuples (all rates are >= 0)
+    tuples = sorted(set(tuple(d) for d in diag))
+    qdiag = [t for t in tuples if not any(o != t and all(o[k] >= t[k] for k in range(4)) for o in tuples)]
+    # ---- zero-migration runs in closed form.  Without migration M = la0 C0 + la1 C1 with C0, C1 the coalescence
+    # generators of deme 0 / deme 1; they commute (lineages never change deme, so the two demes evolve independently) and
+    # are diagonalisable with eigenvalues 0, -1, -3, -6 (minus the number of pairs among 0/1, 2, 3, 4 lineages; blocks of
+    # equal diagonal are scalar).  Hence exp(sum_i M_i T_i) = sum_ab exp(-a X0 - b X1) G0_a G1_b, X = sum la T, and only
+    # the 8 products with a "lineage budget" of at most four are non-zero.
+    def cmat(kind):
+        M = [[Fraction(0)] * 44 for _ in range(44)]
+        for (r, c, k, n) in ent:
+            if k == kind:
+                M[r][c] += n
+        for c in range(44):
+            M[c][c] -= diag[c][kind]
+        return M
+
+    def mm44(A, B):
+        return [[sum(A[i][k] * B[k][j] for k in range(44) if A[i][k] != 0) for j in range(44)] for i in range(44)]
+    C0, C1 = cmat(0), cmat(1)
+    assert mm44(C0, C1) == mm44(C1, C0)
+    I44 = [[Fraction(int(i == j)) for j in range(44)] for i in range(44)]
+    EV = (0, 1, 3, 6)
+
+    def projector(C, ev):
+        Pm = I44
+        for o in EV:
+            if o != ev:
+                Pm = mm44(Pm, [[(C[i][j] + (o if i == j else 0)) / Fraction(o - ev) for j in range(44)] for i in range(44)])
+        return Pm
+    G0 = {a: projector(C0, a) for a in EV}
+    G1 = {a: projector(C1, a) for a in EV}
+    for C, G in ((C0, G0), (C1, G1)):
+        assert [[sum(G[a][i][j] for a in EV) for j in range(44)] for i in range(44)] == I44
+        for a in EV:
+            assert mm44(C, G[a]) == [[-a * x for x in row] for row in G[a]]
+    NM_AB = [(0, 0), (1, 0), (3, 0), (6, 0), (0, 1), (0, 3), (0, 6), (1, 1)]
+    nm = []  # (row, col, ab index, value)
+    for a in EV:
+        for b in EV:
+            Gab = mm44(G0[a], G1[b])
+            nz = [(r, c, Gab[r][c]) for r in range(44) for c in range(44) if Gab[r][c] != 0]
+            if (a, b) in NM_AB:
+                nm += [(r, c, NM_AB.index((a, b)), v) for (r, c, v) in nz]
+            else:
+                assert not nz
+    nm.sort()
+    nm_rowptr = [sum(1 for e in nm if e[0] < r) for r in range(45)]
     L = onepop()
     # spectral projectors of L8: eigenvalues -6, -3, -1 (diagonal blocks are scalar => diagonalisable)
     G6 = [[v / 15 for v in row] for row in matmul(shifted(L, 3), shifted(L, 1))]
@@ -192,6 +278,23 @@ def main():
     o.append("#define MISTI_ELL_WIDTH 4")
     o.append("#define MISTI_ELL_INIT { %s }" % ", ".join(
         "{" + ",".join("{%d,%d,%d}" % e for e in (row + [(r, 0, 0)] * (4 - len(row)))) + "}" for r, row in enumerate(ell)))
+    o.append("// 16-lane layout: state (or pad row 44..47) per lane and slot; remote entries {col, code} per slot (3 each,")
+    o.append("// slot b uses 2); local coefficient codes {from slot (s+1)%3, from slot (s+2)%3}; code = kind + 4 log2(count), 12 = none")
+    o.append("#define MISTI_L16_ROW_INIT { %s }" % ", ".join("{" + ",".join(str(v) for v in r) + "}" for r in l16_row))
+    o.append("#define MISTI_L16_REM_INIT { %s }" % ", ".join(
+        "{" + ",".join("{" + ",".join("{%d,%d}" % e for e in slot) + "}" for slot in lane) + "}" for lane in l16_rem))
+    o.append("#define MISTI_L16_LOC_INIT { %s }" % ", ".join(
+        "{" + ",".join("{%d,%d}" % tuple(slot) for slot in lane) + "}" for lane in l16_loc))
+    o.append("// Pareto-maximal rows of MISTI_GEN_DIAG: max_c |M_cc| is attained on one of them")
+    o.append("#define MISTI_QDIAG_N %d" % len(qdiag))
+    o.append("#define MISTI_QDIAG_INIT { %s }" % ", ".join("{%d,%d,%d,%d}" % t for t in qdiag))
+    o.append("// zero-migration runs: non-zero entries of the spectral projector products G0_a G1_b, row-major;")
+    o.append("// ab index -> (a, b): 0 (0,0), 1 (1,0), 2 (3,0), 3 (6,0), 4 (0,1), 5 (0,3), 6 (0,6), 7 (1,1)")
+    o.append("#define MISTI_NM_NNZ %d" % len(nm))
+    o.append("#define MISTI_NM_ROWPTR_INIT { %s }" % ",".join(str(v) for v in nm_rowptr))
+    o.append("#define MISTI_NM_COL_INIT { %s }" % ",".join(str(e[1]) for e in nm))
+    o.append("#define MISTI_NM_AB_INIT { %s }" % ",".join(str(e[2]) for e in nm))
+    o.append("#define MISTI_NM_VAL_INIT { %s }" % ",".join(fmt(e[3]) for e in nm))
     o.append("#define MISTI_W44_INIT { %s }" % ", ".join("{" + ",".join(str(v) for v in row) + "}" for row in W44))
     o.append("#define MISTI_W8_INIT { %s }" % ", ".join("{" + ",".join(str(v) for v in row) + "}" for row in W8))
     o.append("#define MISTI_COLLAPSE_INIT { %s }" % ",".join(str(v) for v in collapse))
