@@ -48,6 +48,7 @@ struct PulseEntry { unsigned char row, col, a, b, mult; };
     SPEC double PFX##wg6[7][8] = MISTI_WG6_INIT;                                \
     SPEC double PFX##wg3[7][8] = MISTI_WG3_INIT;                                \
     SPEC double PFX##wg1[7][8] = MISTI_WG1_INIT;                                \
+    SPEC unsigned char PFX##l16_pos[48] = MISTI_L16_POS_INIT;                   \
     SPEC unsigned char PFX##l16_row[16][3] = MISTI_L16_ROW_INIT;                \
     SPEC unsigned char PFX##l16_rem[16][3][3][2] = MISTI_L16_REM_INIT;          \
     SPEC unsigned char PFX##l16_loc[16][3][2] = MISTI_L16_LOC_INIT;             \
@@ -86,6 +87,7 @@ static const RecipTable h_recip = RecipTable();
 #endif
 
 constexpr int kYStride = 48;                    // doubles per ping-pong buffer (44 states + pad rows)
+constexpr int kGroupScratch = 128;              // doubles of scratch per lane group: two ping-pong buffers + 32
 constexpr double kUnifMaxStep = 32.0;           // largest q*T handled in one uniformisation sweep
 constexpr double kUnifTol = 8.881784197001252e-16;   // 2^-50: truncation of the Poisson tail (relative to the mass)
 constexpr double kUnifMaxStiff = 256.0;         // q*T beyond this (8 sweeps) goes to the dense scaling-and-squaring step
@@ -265,6 +267,7 @@ struct SingleLane {  // test-only host build: one lane owns all 44 rows, every o
     };
     MISTI_D static int rw(int) { return 4; }
     MISTI_D int row_of(int s) const { return s; }
+    MISTI_D static int pos_of(int row) { return row; }
     MISTI_D void rem_of(int s, int e, int* col, unsigned* code) const {
         const EllEntry en = MISTI_TAB(ell)[s][e];
         *col = en.col;
@@ -277,12 +280,14 @@ struct SingleLane {  // test-only host build: one lane owns all 44 rows, every o
     MISTI_HD int wmax(int v) const { return v; }
     MISTI_HD int wmin(int v) const { return v; }
     MISTI_HD bool any(bool v) const { return v; }
+    MISTI_HD bool any_in_group(bool v) const { return v; }
     // record j of the item (all-zero = SEG_NOP when the group has none)
     MISTI_HD Rec rec_load(const double* p, bool have) const { return Rec{have ? p : zero_rec()}; }
     // the record itself, or the neutral sweep record (no events, P(N = 0) = 1)
     MISTI_HD Rec rec_select(const Rec& r, bool is) const { return Rec{is ? r.p : kNeutralRec}; }
-    MISTI_HD void rec_store(const Rec& r, double* dst) const {
+    MISTI_HD void rec_store(const Rec& r, double* dst) const {  // 16 slots and the constant 1 behind them
         for (int i = 0; i < kRecSlots; ++i) dst[i] = r.p[i];
+        dst[kRecSlots] = 1.0;
     }
     MISTI_HD static const double* zero_rec() {
         static const double z[kRecSlots] = {0};
@@ -303,6 +308,7 @@ struct HalfWarpLanes {  // two items per warp; each lane of a 16-lane half owns 
     };
     __device__ static int rw(int s) { return s == 1 ? 2 : 3; }
     __device__ int row_of(int s) const { return d_l16_row[threadIdx.x & 15][s]; }
+    __device__ static int pos_of(int row) { return d_l16_pos[row]; }  // shared-memory word of a state: 16 * slot + lane
     __device__ void rem_of(int s, int e, int* col, unsigned* code) const {
         *col = d_l16_rem[threadIdx.x & 15][s][e][0];
         *code = d_l16_rem[threadIdx.x & 15][s][e][1];
@@ -323,9 +329,13 @@ struct HalfWarpLanes {  // two items per warp; each lane of a 16-lane half owns 
         return v < o ? v : o;
     }
     __device__ bool any(bool v) const { return __any_sync(0xffffffffu, v); }
+    __device__ bool any_in_group(bool v) const { return (__ballot_sync(0xffffffffu, v) & (0xffffu << (threadIdx.x & 16u))) != 0; }
     __device__ Rec rec_load(const double* p, bool have) const { return Rec{have ? p[threadIdx.x & 15] : 0.0}; }
     __device__ Rec rec_select(const Rec& r, bool is) const { return Rec{is ? r.v : ((threadIdx.x & 15) == 13 ? 1.0 : 0.0)}; }
-    __device__ void rec_store(const Rec& r, double* dst) const { dst[threadIdx.x & 15] = r.v; }
+    __device__ void rec_store(const Rec& r, double* dst) const {
+        dst[threadIdx.x & 15] = r.v;
+        if ((threadIdx.x & 15) == 15) dst[kRecSlots] = 1.0;
+    }
 };
 #endif
 
@@ -371,47 +381,88 @@ MISTI_HD inline void post_split_coeffs(const ModelDesc& md, const double* times,
     cpost[0] = c6; cpost[1] = c3; cpost[2] = c1;
 }
 
+// Entry of the zero-migration run table as the lane groups use it: G_ab[row][col] with the shared-memory word of
+// `col` and the slots of c_ab / e_ab in the staged record (e_0 = 1 sits behind the record, slot 16).
+struct RunEnt {
+    double val;
+    int ypos;
+    int ce;  // low half: slot of c_ab, high half: slot of e_ab
+};
+template <class G>
+MISTI_D inline void fill_run_entry(int e, RunEnt* out) {
+    const int ab = MISTI_TAB(nm_ab)[e];
+    out->val = MISTI_TAB(nm_val)[e];
+    out->ypos = G::pos_of(MISTI_TAB(nm_col)[e]);
+    out->ce = ab | ((ab == 0 ? kRecSlots : 7 + ab) << 16);
+}
+
+// What a lane knows about its rows, independent of the item: built once per thread.
+template <class G>
+struct LaneCtx {
+    static constexpr int RPL = G::RPL, NLOC = G::NLOC, RW = G::RWMAX;
+    int row[RPL];        // the states owned by this lane (44..47 = pad rows of empty slots)
+    unsigned rc[RPL];    // coefficient-table codes (kind + 4 log2(count), 12 = none): remote entry e at bit 4e, local entry j at bit 16+4j
+    unsigned rk[RPL];    // diagonal multiplicity of rate kind k at bit 3k; StateToJAF count of category c at bit 12+2c;
+                         // collapse block at bit 26; ancient-reset masks at bits 29, 30; valid at bit 31
+    unsigned run[RPL];   // entries [lo, hi) of the zero-migration run table: lo | hi << 8
+    const double* yp[RPL][RW];  // where this lane reads y[col] of each remote entry (buffer 0; buffer 1 is +kYStride)
+    double* wp[RPL];            // where it writes y[row]
+    double* scratch;            // the group's scratch area (kGroupScratch doubles)
+    const RunEnt* runtab;
+
+    MISTI_D void init(const G& g, double* ysm, const RunEnt* rt) {
+        scratch = ysm;
+        runtab = rt;
+#pragma unroll
+        for (int s = 0; s < RPL; ++s) {
+            row[s] = g.row_of(s);
+            const bool valid = row[s] < 44;
+            wp[s] = ysm + G::pos_of(row[s]);
+            rc[s] = 0; rk[s] = 0; run[s] = 0;
+#pragma unroll
+            for (int e = 0; e < RW; ++e) {
+                int col = row[s];
+                unsigned cde = 12u;
+                if (valid && e < G::rw(s)) g.rem_of(s, e, &col, &cde);
+                rc[s] |= cde << (4 * e);
+                yp[s][e] = ysm + G::pos_of(col);
+            }
+#pragma unroll
+            for (int j = 0; j < NLOC; ++j) rc[s] |= (valid ? g.loc_of(s, j) : 12u) << (16 + 4 * j);
+            if (valid) {
+                const int r = row[s];
+                for (int k = 0; k < 4; ++k) rk[s] |= (unsigned)MISTI_TAB(diag)[r][k] << (3 * k);
+                for (int c = 0; c < 7; ++c) rk[s] |= (unsigned)MISTI_TAB(w44)[c][r] << (12 + 2 * c);
+                rk[s] |= (unsigned)MISTI_TAB(collapse)[r] << 26;
+                rk[s] |= (unsigned)MISTI_TAB(anc2)[r] << 29;
+                rk[s] |= (unsigned)MISTI_TAB(anc11)[r] << 30;
+                rk[s] |= 1u << 31;
+                run[s] = (unsigned)MISTI_TAB(nm_rowptr)[r] | ((unsigned)MISTI_TAB(nm_rowptr)[r + 1] << 8);
+            }
+        }
+    }
+};
+
 // Expected JSFS of one item.  ALL lanes of the warp call this together (each group with its own item;
 // `active` = false for a group without work); `rec` / `nseg` = the item's segment records (build_segments_item);
-// `ysm` is a scratch area of 2*kYStride doubles private to the group (two ping-pong copies of the 44-vector, padded
-// to 48 so that every lane has a slot to write).  On return every lane of the group holds the UNNORMALISED spectrum
-// in jafs[0..6] (MigrationInference.JAFSpectrum's return value) and the number of mat-vecs in *terms.
+// L.scratch is private to the group.  On return lane c (and, with 16 lanes, c + 8) of the group holds the
+// UNNORMALISED spectrum entry c in *jafs_c (MigrationInference.JAFSpectrum's return value; lanes 7 and 15 hold 0;
+// a single lane gets all of them in jafs_c[0..6]) and every lane the number of mat-vecs in *terms.
 // `cont` (nullable): where to park the item when it meets a stiff segment (return value MISTI_STIFF = "pending");
 // `resume`: start from the record instead of from the sampling configuration.
 template <class G>
-MISTI_D inline int jsfs_item(const G& g, const ModelDesc& md, bool active, const double* params, const double* rec, int nseg,
-                             const double* cpost, double* ysm, double* jafs, int* terms, Cont* cont = nullptr,
-                             bool resume = false) {
+MISTI_D inline int jsfs_item(const G& g, const LaneCtx<G>& L, const ModelDesc& md, bool active, const double* params,
+                             const double* rec, int nseg, const double* cpost, double* jafs_c, int* terms,
+                             Cont* cont = nullptr, bool resume = false) {
     constexpr int RPL = G::RPL, NLOC = G::NLOC, RW = G::RWMAX;
     typedef typename G::Rec Rec;
     const int lane = g.lane();
-    int row[RPL];     // the states owned by this lane (44..47 = pad rows of empty slots)
-    bool valid[RPL];
-    unsigned rc[RPL];  // packed coefficient-table codes (kind + 4 log2(count), 12 = none): remote slot e at bit 4e, local slot j at bit 16+4j
-    unsigned dg[RPL];  // diagonal multiplicity of rate kind k at bit 3k
-    const double* yp[RPL][RW];  // where this lane reads y[col] of each remote entry (buffer 0; buffer 1 is +kYStride)
-    double* wp[RPL];            // where it writes y[row]
+    double* const ysm = L.scratch;
     double P[RPL];            // state probabilities at the start of the current segment (rows owned by this lane)
     double Ia[RPL], Ib[RPL];  // occupancy integrals summed over the intervals before / from the sampling date
 #pragma unroll
     for (int s = 0; s < RPL; ++s) {
-        row[s] = g.row_of(s);
-        valid[s] = row[s] < 44;
-        wp[s] = ysm + row[s];
-        rc[s] = 0; dg[s] = 0;
-#pragma unroll
-        for (int e = 0; e < RW; ++e) {
-            int col = 0;
-            unsigned cde = 12u;
-            if (valid[s] && e < G::rw(s)) g.rem_of(s, e, &col, &cde);
-            rc[s] |= cde << (4 * e);
-            yp[s][e] = ysm + col;
-        }
-#pragma unroll
-        for (int j = 0; j < NLOC; ++j) rc[s] |= (valid[s] ? g.loc_of(s, j) : 12u) << (16 + 4 * j);
-        if (valid[s])
-            for (int k = 0; k < 4; ++k) dg[s] |= (unsigned)MISTI_TAB(diag)[row[s]][k] << (3 * k);
-        P[s] = row[s] == 2 ? 1.0 : 0.0;  // both genome-1 lineages in deme 0, genome-2 in deme 1 (:469-471)
+        P[s] = L.row[s] == 2 ? 1.0 : 0.0;  // both genome-1 lineages in deme 0, genome-2 in deme 1 (:469-471)
         Ia[s] = 0.0; Ib[s] = 0.0;
     }
     int nterms = 0;
@@ -422,31 +473,34 @@ MISTI_D inline int jsfs_item(const G& g, const ModelDesc& md, bool active, const
         nterms = cont->nterms;
 #pragma unroll
         for (int s = 0; s < RPL; ++s) {
-            P[s] = valid[s] ? cont->P[row[s]] : 0.0;
-            Ia[s] = valid[s] ? cont->Ia[row[s]] : 0.0;
-            Ib[s] = valid[s] ? cont->Ib[row[s]] : 0.0;
+            const bool valid = (L.rk[s] >> 31) != 0;
+            P[s] = valid ? cont->P[L.row[s]] : 0.0;
+            Ia[s] = valid ? cont->Ia[L.row[s]] : 0.0;
+            Ib[s] = valid ? cont->Ib[L.row[s]] : 0.0;
         }
     }
     bool pending = false;
     const int numT = md.numT;
     const int nown = active ? nseg : 0;
 
-    // AncientSampleP0 (TwoPopulations.py:246-262), then PulseMigration (:361-377), before interval `it`
-    auto reset_and_pulse = [&](int it, bool do_reset, bool do_pulse) {
-        if (g.any(do_reset)) {
-            double a2 = 0.0, a11 = 0.0;
+    // AncientSampleP0 (TwoPopulations.py:246-262): mass of the states with both genome-1 singletons in deme 0 -> state 2,
+    // with a (2,0) lineage in deme 0 -> state 11, the rest is dropped
+    auto ancient_reset = [&](bool do_reset) {
+        double a2 = 0.0, a11 = 0.0;
 #pragma unroll
-            for (int s = 0; s < RPL; ++s)
-                if (valid[s]) {
-                    if (MISTI_TAB(anc2)[row[s]]) a2 += P[s];
-                    if (MISTI_TAB(anc11)[row[s]]) a11 += P[s];
-                }
-            a2 = g.sum(a2); a11 = g.sum(a11);
-            if (do_reset) {
-#pragma unroll
-                for (int s = 0; s < RPL; ++s) P[s] = row[s] == 2 ? a2 : (row[s] == 11 ? a11 : 0.0);
-            }
+        for (int s = 0; s < RPL; ++s) {
+            if ((L.rk[s] >> 29) & 1u) a2 += P[s];
+            if ((L.rk[s] >> 30) & 1u) a11 += P[s];
         }
+        a2 = g.sum(a2); a11 = g.sum(a11);
+        if (do_reset) {
+#pragma unroll
+            for (int s = 0; s < RPL; ++s) P[s] = L.row[s] == 2 ? a2 : (L.row[s] == 11 ? a11 : 0.0);
+        }
+    };
+    // the reset, then PulseMigration (:361-377), before interval `it`
+    auto reset_and_pulse = [&](int it, bool do_reset, bool do_pulse) {
+        if (g.any(do_reset)) ancient_reset(do_reset);
         if (g.any(do_pulse)) {  // a group without a pulse here applies the map with rate 0 = the identity
             double pr = 0.0;
             int src = 0;
@@ -460,8 +514,7 @@ MISTI_D inline int jsfs_item(const G& g, const ModelDesc& md, bool active, const
             const unsigned char* rp = src == 0 ? MISTI_TAB(pulse0_rowptr) : MISTI_TAB(pulse1_rowptr);
             g.sync();
 #pragma unroll
-            for (int s = 0; s < RPL; ++s)
-                wp[s][0] = P[s];
+            for (int s = 0; s < RPL; ++s) L.wp[s][0] = P[s];
             g.sync();
             double pw_om[5], pw_r[5];
             pw_om[0] = 1.0; pw_r[0] = 1.0;
@@ -469,8 +522,8 @@ MISTI_D inline int jsfs_item(const G& g, const ModelDesc& md, bool active, const
 #pragma unroll
             for (int s = 0; s < RPL; ++s) {
                 double acc = 0.0;
-                if (valid[s]) {
-                    const int r = row[s];
+                if (L.rk[s] >> 31) {
+                    const int r = L.row[s];
                     for (int e = rp[r]; e < rp[r + 1]; ++e) {
                         const PulseEntry pe = ent[e];
                         double w = (double)pe.mult;
@@ -478,7 +531,7 @@ MISTI_D inline int jsfs_item(const G& g, const ModelDesc& md, bool active, const
                             if (k == pe.a) w *= pw_om[k];
                             if (k == pe.b) w *= pw_r[k];
                         }
-                        acc += w * ysm[pe.col];
+                        acc += w * ysm[G::pos_of(pe.col)];
                     }
                 }
                 P[s] = acc;
@@ -493,13 +546,14 @@ MISTI_D inline int jsfs_item(const G& g, const ModelDesc& md, bool active, const
         const double rq0 = sw.get(0), rq1 = sw.get(1), rq2 = sw.get(2), rq3 = sw.get(3);
 #pragma unroll
         for (int s = 0; s < RPL; ++s) {
-            const double d = ((double)(dg[s] & 7u) * rq0 + (double)((dg[s] >> 3) & 7u) * rq1) +
-                             ((double)((dg[s] >> 6) & 7u) * rq2 + (double)((dg[s] >> 9) & 7u) * rq3);
+            const unsigned dg = L.rk[s];
+            const double d = ((double)(dg & 7u) * rq0 + (double)((dg >> 3) & 7u) * rq1) +
+                             ((double)((dg >> 6) & 7u) * rq2 + (double)((dg >> 9) & 7u) * rq3);
             adiag[s] = d < 1.0 ? 1.0 - d : 0.0;
 #pragma unroll
-            for (int e = 0; e < RW; ++e) coef[s][e] = sw.get((rc[s] >> (4 * e)) & 15u);
+            for (int e = 0; e < RW; ++e) coef[s][e] = sw.get((L.rc[s] >> (4 * e)) & 15u);
 #pragma unroll
-            for (int j = 0; j < NLOC; ++j) cloc[s][j] = sw.get((rc[s] >> (16 + 4 * j)) & 15u);
+            for (int j = 0; j < NLOC; ++j) cloc[s][j] = sw.get((L.rc[s] >> (16 + 4 * j)) & 15u);
         }
     };
     // y_new[row] = (A y)[row] for the rows of this lane: diagonal and same-lane entries from registers (yk), the rest
@@ -514,7 +568,7 @@ MISTI_D inline int jsfs_item(const G& g, const ModelDesc& md, bool active, const
             }
 #pragma unroll
             for (int e = 0; e < RW; ++e)
-                if (e < G::rw(s)) a = fma(coef[s][e], yp[s][e][RO], a);
+                if (e < G::rw(s)) a = fma(coef[s][e], L.yp[s][e][RO], a);
             acc[s] = a;
         }
     };
@@ -541,7 +595,7 @@ MISTI_D inline int jsfs_item(const G& g, const ModelDesc& md, bool active, const
 #pragma unroll
             for (int s = 0; s < RPL; ++s) {
                 yk[s] = P[s]; P1[s] = p0 * P[s];
-                wp[s][0] = P[s];
+                L.wp[s][0] = P[s];
             }
             double p = p0;     // Pois(k; lam)
             double tail = t0;  // P(N > k)
@@ -559,7 +613,7 @@ MISTI_D inline int jsfs_item(const G& g, const ModelDesc& md, bool active, const
                 for (int s = 0; s < RPL; ++s) {
                     Iint[s] = fma(tail, yk[s], Iint[s]);
                     yk[s] = acc[s];
-                    wp[s][WO] = acc[s];
+                    L.wp[s][WO] = acc[s];
                     P1[s] = fma(p, acc[s], P1[s]);
                 }
                 tail -= p;
@@ -596,7 +650,7 @@ MISTI_D inline int jsfs_item(const G& g, const ModelDesc& md, bool active, const
     auto runop = [&](const Rec& rv, bool is, unsigned long long meta) {
         g.sync();
 #pragma unroll
-        for (int s = 0; s < RPL; ++s) wp[s][0] = P[s];
+        for (int s = 0; s < RPL; ++s) L.wp[s][0] = P[s];
         g.rec_store(rv, ysm + kYStride);
         g.sync();
         if (is) {
@@ -604,13 +658,14 @@ MISTI_D inline int jsfs_item(const G& g, const ModelDesc& md, bool active, const
             const bool pre = (meta & kSegPre) != 0;
 #pragma unroll
             for (int s = 0; s < RPL; ++s)
-                if (valid[s]) {
+                if (L.rk[s] >> 31) {
                     double pe = 0.0, ir = 0.0;
-                    for (int e = MISTI_TAB(nm_rowptr)[row[s]]; e < MISTI_TAB(nm_rowptr)[row[s] + 1]; ++e) {
-                        const int ab = MISTI_TAB(nm_ab)[e];
-                        const double t = MISTI_TAB(nm_val)[e] * ysm[MISTI_TAB(nm_col)[e]];
-                        ir = fma(cc[ab], t, ir);
-                        pe = fma(ab == 0 ? 1.0 : cc[7 + ab], t, pe);
+                    const int hi = (int)(L.run[s] >> 8);
+                    for (int e = (int)(L.run[s] & 255u); e < hi; ++e) {
+                        const RunEnt en = L.runtab[e];
+                        const double t = en.val * ysm[en.ypos];
+                        ir = fma(cc[en.ce & 0xffff], t, ir);
+                        pe = fma(cc[en.ce >> 16], t, pe);
                     }
                     P[s] = pe;
                     if (pre) Ia[s] += ir;
@@ -632,7 +687,7 @@ MISTI_D inline int jsfs_item(const G& g, const ModelDesc& md, bool active, const
         for (int s = 0; s < RPL; ++s) {
             yk[s] = is ? P[s] : 0.0;
             Iint[s] = yk[s];
-            wp[s][0] = yk[s];
+            L.wp[s][0] = yk[s];
         }
         double nprev = 0.0;
 #pragma unroll
@@ -650,7 +705,7 @@ MISTI_D inline int jsfs_item(const G& g, const ModelDesc& md, bool active, const
             for (int s = 0; s < RPL; ++s) {
                 if (done) acc[s] = 0.0;  // this group's series has ended: keep its sums as they are
                 yk[s] = acc[s];
-                wp[s][wo] = acc[s];
+                L.wp[s][wo] = acc[s];
                 Iint[s] += acc[s];
                 nk += acc[s];
             }
@@ -681,10 +736,12 @@ MISTI_D inline int jsfs_item(const G& g, const ModelDesc& md, bool active, const
     };
 
     const int n_loop = g.wmax(nown > seg0 ? nown - seg0 : 0);
+    Rec nxt = g.rec_load(rec + (long)seg0 * kRecSlots, seg0 < nown);
     for (int j = 0; j < n_loop; ++j) {
         const int sg = seg0 + j;
         const bool have = !pending && sg < nown;  // a group past its own last segment idles
-        const Rec rv = g.rec_load(rec + (long)sg * kRecSlots, have);
+        const Rec rv = nxt;
+        nxt = g.rec_load(rec + (long)(sg + 1) * kRecSlots, sg + 1 < nown);  // in flight while this segment is processed
         const double mslot = rv.get(15);
         const unsigned long long meta = have ? seg_meta_bits(mslot) : 0ull;
         int type = seg_type(meta);
@@ -693,7 +750,7 @@ MISTI_D inline int jsfs_item(const G& g, const ModelDesc& md, bool active, const
             if (cont) {
                 if (lane == 0) { cont->seg = sg; cont->nterms = nterms; }
 #pragma unroll
-                for (int s = 0; s < RPL; ++s) { cont->P[row[s]] = P[s]; cont->Ia[row[s]] = Ia[s]; cont->Ib[row[s]] = Ib[s]; }
+                for (int s = 0; s < RPL; ++s) { cont->P[L.row[s]] = P[s]; cont->Ia[L.row[s]] = Ia[s]; cont->Ib[L.row[s]] = Ib[s]; }
                 pending = true;
             } else {
                 status = MISTI_STIFF;
@@ -706,65 +763,62 @@ MISTI_D inline int jsfs_item(const G& g, const ModelDesc& md, bool active, const
         if (g.any(type == SEG_RUN)) runop(rv, type == SEG_RUN, meta);
         if (g.any(type == SEG_INF)) infsum(rv, type == SEG_INF, meta);
     }
-    // JAFS = StateToJAF . (sum of the interval integrals) (:501-506)
+
+    // JAFS = StateToJAF . (sum of the interval integrals) (:501-506) + the one-population tail after the split: with
+    // P8 = CollapsePops(P) (:518-528) that is sum_b V[c][b] P8[b], V = c6 WG6 + c3 WG3 + c1 WG1, folded here into
+    // per-row weights V[c][block(row)] so that one reduction per category does both parts.
+    const bool post = active && md.splitT < numT;
+    const bool any_post = g.any(post);
+    if (any_post) {
+        const bool do_reset = post && md.splitT == md.sampleDate && md.splitT > 0;  // the reset precedes the collapse (:480-494)
+        if (g.any(do_reset)) ancient_reset(do_reset);
+        const double c6 = post ? cpost[0] : 0.0, c3 = post ? cpost[1] : 0.0, c1 = post ? cpost[2] : 0.0;
+        g.sync();
+        for (int idx = lane; idx < 56; idx += G::LANES) {
+            const int c = idx >> 3, b = idx & 7;
+            ysm[idx] = (c6 * MISTI_TAB(wg6)[c][b] + c3 * MISTI_TAB(wg3)[c][b]) + c1 * MISTI_TAB(wg1)[c][b];
+        }
+        g.sync();
+    }
     double jl[7];
 #pragma unroll
     for (int c = 0; c < 7; ++c) jl[c] = 0.0;
 #pragma unroll
     for (int s = 0; s < RPL; ++s)
-        if (valid[s]) {
+        if (L.rk[s] >> 31) {
+            const double iab = Ia[s] + Ib[s];
+            const int blk = (int)((L.rk[s] >> 26) & 7u);
 #pragma unroll
             for (int c = 0; c < 7; ++c) {
-                const double w = (double)MISTI_TAB(w44)[c][row[s]];
-                jl[c] += w * (c < 2 ? Ia[s] + Ib[s] : Ib[s]);
+                const double w = (double)((L.rk[s] >> (12 + 2 * c)) & 3u);
+                jl[c] = fma(w, c < 2 ? iab : Ib[s], jl[c]);
+                if (any_post) jl[c] = fma(ysm[c * 8 + blk], P[s], jl[c]);
             }
         }
-    const bool post = active && md.splitT < numT;
-    if (g.any(post)) {
-        const bool do_reset = post && md.splitT == md.sampleDate && md.splitT > 0;  // the reset precedes the collapse (:480-494)
-        if (g.any(do_reset)) {
-            double a2 = 0.0, a11 = 0.0;
+    // transposed reduction through the scratch area: lane l parks its 7 partial sums, lane c adds up category c
+    g.sync();
 #pragma unroll
-            for (int s = 0; s < RPL; ++s)
-                if (valid[s]) {
-                    if (MISTI_TAB(anc2)[row[s]]) a2 += P[s];
-                    if (MISTI_TAB(anc11)[row[s]]) a11 += P[s];
-                }
-            a2 = g.sum(a2); a11 = g.sum(a11);
-            if (do_reset) {
-#pragma unroll
-                for (int s = 0; s < RPL; ++s) P[s] = row[s] == 2 ? a2 : (row[s] == 11 ? a11 : 0.0);
-            }
-        }
-        // CollapsePops (:518-528): 44 -> 8 block sums
-        double P8[8];
-#pragma unroll
-        for (int b = 0; b < 8; ++b) {
-            double v = 0.0;
-#pragma unroll
-            for (int s = 0; s < RPL; ++s)
-                if (valid[s] && MISTI_TAB(collapse)[row[s]] == b) v += P[s];
-            P8[b] = g.sum(v);
-        }
-        const double c6 = post ? cpost[0] : 0.0, c3 = post ? cpost[1] : 0.0, c1 = post ? cpost[2] : 0.0;
-#pragma unroll
-        for (int c = 0; c < 7; ++c) {
-            double a6 = 0.0, a3 = 0.0, a1 = 0.0;
-#pragma unroll
-            for (int b = 0; b < 8; ++b) {
-                a6 += MISTI_TAB(wg6)[c][b] * P8[b];
-                a3 += MISTI_TAB(wg3)[c][b] * P8[b];
-                a1 += MISTI_TAB(wg1)[c][b] * P8[b];
-            }
-            jafs[c] = g.sum(jl[c]) + ((c6 * a6 + c3 * a3) + c1 * a1);
-        }
+    for (int c = 0; c < 7; ++c) ysm[c * G::LANES + lane] = jl[c];
+    g.sync();
+    if (G::LANES == 1) {
+        for (int c = 0; c < 7; ++c) jafs_c[c] = ysm[c];
     } else {
+        const int c = lane & 7;
+        double v = 0.0;
+        if (c < 7) {
 #pragma unroll
-        for (int c = 0; c < 7; ++c) jafs[c] = g.sum(jl[c]);
+            for (int j = 0; j < G::LANES; ++j) v += ysm[c * G::LANES + ((j + c) & (G::LANES - 1))];  // rotated: no bank conflict
+        }
+        jafs_c[0] = v;
     }
     *terms = nterms;
     return pending ? MISTI_STIFF : status;
 }
+
+// Group-cooperative tail: normalise the spectrum, take the logs (lane c handles category c), and leave
+// raw[7] / jn[7] / logj[7] in the group's scratch area at offsets kTailRaw / kTailJn / kTailLog for every lane to read.
+// Returns false if a required log is not finite.  (MigrationInference.py:583-613)
+constexpr int kTailRaw = 96, kTailJn = 104, kTailLog = 112;
 
 // Normalised spectrum -> log terms used by the composite likelihood (MigrationInference.py:583-613).
 // Folded: bins (0+6), (1+5), (2+4), 3; the data vector is folded the same way by the host, so
@@ -793,6 +847,38 @@ MISTI_HD inline double score_row(const double* drow /* 7 counts (folded by the h
     double llh = drow[7];
     for (int c = 0; c < 7; ++c) llh += drow[c] * logj[c];
     return llh;
+}
+
+// Group-cooperative version of the two functions above: lane c normalises and takes the log of category c
+// (jafs_c as returned by jsfs_item); raw[7], jn[7], logj[7] are left in the scratch area for every lane to read, and
+// *jn_c is this lane's normalised entry.
+template <class G>
+MISTI_D inline bool jafs_finish(const G& g, double* ysm, const double* jafs_c, bool unfolded, double* jn_c) {
+    if (G::LANES == 1) {
+        double jn[7], logj[7];
+        const bool ok = jafs_normalise_logs(jafs_c, unfolded, jn, logj);
+        for (int c = 0; c < 7; ++c) { ysm[kTailRaw + c] = jafs_c[c]; ysm[kTailJn + c] = jn[c]; ysm[kTailLog + c] = logj[c]; }
+        *jn_c = jn[0];
+        return ok;
+    }
+    const int lane = g.lane(), c = lane & 7;
+    const bool mine = lane < 7;
+    const double raw = jafs_c[0];
+    const double tot = g.sum(mine ? raw : 0.0);
+    const double jn = raw / tot;
+    g.sync();  // the partial sums of jsfs_item have been read
+    if (mine) { ysm[kTailRaw + c] = raw; ysm[kTailJn + c] = jn; }
+    g.sync();
+    double lj = 0.0;
+    if (mine) {
+        if (unfolded || c == 3) lj = log(jn);
+        else if (c < 3) lj = log(jn + ysm[kTailJn + 6 - c]);
+        ysm[kTailLog + c] = lj;
+    }
+    const bool bad = mine && !(fabs(lj) <= DBL_MAX);
+    g.sync();
+    *jn_c = jn;
+    return !g.any_in_group(bad);
 }
 
 }  // namespace misti

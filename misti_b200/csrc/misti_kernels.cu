@@ -30,7 +30,7 @@ using misti::ModelDesc;
 constexpr int kCorrectThreads = 64;
 constexpr int kCorrectMinBlocks = 8;
 constexpr int kJsfsWarps = 4;      // warps per block of the JSFS kernel (8 items per block)
-constexpr int kJsfsMinBlocks = 4;  // occupancy target: caps the kernel at 128 registers per thread
+constexpr int kJsfsMinBlocks = 3;  // occupancy target: caps the kernel at 168 registers per thread (12 warps per SM)
 constexpr int kMaxChunk = 1 << 20;
 constexpr int kPitch = 2;  // per interval and item the rate buffer holds la0, la1
 
@@ -95,10 +95,15 @@ misti_jsfs_kernel(int B, int P, const double* __restrict__ params, const int* __
                   const int* __restrict__ item_list, const int* __restrict__ item_count, int* __restrict__ next_list,
                   int* __restrict__ next_count) {
     // one item per 16-lane half warp (3 of the 44 chain states per lane), two items per warp
-    __shared__ double ysm_all[kJsfsWarps * 2][2 * misti::kYStride];
+    __shared__ double ysm_all[kJsfsWarps * 2][misti::kGroupScratch];
+    __shared__ misti::RunEnt runtab[MISTI_NM_NNZ];
+    for (int e = threadIdx.x; e < MISTI_NM_NNZ; e += blockDim.x) misti::fill_run_entry<misti::HalfWarpLanes>(e, &runtab[e]);
+    __syncthreads();
     const int half = threadIdx.x >> 4, lane = threadIdx.x & 15;
     double* ysm = ysm_all[half];
     const misti::HalfWarpLanes g;
+    misti::LaneCtx<misti::HalfWarpLanes> L;
+    L.init(g, ysm, runtab);
     const int ngroups = gridDim.x * kJsfsWarps * 2;
     // first pass: all B items; resume pass: the items parked by the previous pass and advanced by misti_stiff_kernel
     const bool resume = item_list != nullptr;
@@ -111,34 +116,30 @@ misti_jsfs_kernel(int B, int P, const double* __restrict__ params, const int* __
         const ModelDesc& md = models[model_ids ? model_ids[b] : model_default];
         int st = status[b];
         if (resume && st == MISTI_STIFF) st = MISTI_OK;  // parked by the previous pass, advanced by misti_stiff_kernel
-        double raw[7], jn[7], logj[7];
+        double raw_c, jn_c;
         int nt = 0;
         const double cp[3] = {cpost[b], cpost[stride + b], cpost[2 * stride + b]};
-        const int js = misti::jsfs_item<misti::HalfWarpLanes>(g, md, has && st == MISTI_OK, params + (long)b * P,
-                                                              rec + (long)b * seg_cap * misti::kRecSlots, nseg[b], cp, ysm, raw, &nt,
+        const int js = misti::jsfs_item<misti::HalfWarpLanes>(g, L, md, has && st == MISTI_OK, params + (long)b * P,
+                                                              rec + (long)b * seg_cap * misti::kRecSlots, nseg[b], cp, &raw_c, &nt,
                                                               conts ? conts + b : nullptr, resume);
+        const bool fin = misti::jafs_finish(g, ysm, &raw_c, unfolded != 0, &jn_c);  // all lanes, also of a group without an item
         if (!has) continue;
         if (st == MISTI_OK) st = js;
         if (st == MISTI_STIFF && conts && next_list) {  // parked: queue it for the dense step; results come from a later pass
             if (lane == 0) next_list[atomicAdd(next_count, 1)] = b;
         }
-        if (st == MISTI_OK && !misti::jafs_normalise_logs(raw, unfolded != 0, jn, logj)) st = MISTI_NONFINITE;
-        if (st != MISTI_OK)
-            for (int c = 0; c < 7; ++c) raw[c] = jn[c] = nan("");
+        if (st == MISTI_OK && !fin) st = MISTI_NONFINITE;
         if (lane == 0) {
             status[b] = st;
             if (terms) terms[b] = nt;
         }
         if (lane < 7) {
-            double v = jn[0], w = raw[0];
-#pragma unroll
-            for (int c = 1; c < 7; ++c)
-                if (lane == c) { v = jn[c]; w = raw[c]; }
-            if (jafs) jafs[(long)b * 7 + lane] = v;
-            if (jafs_raw) jafs_raw[(long)b * 7 + lane] = w;
+            if (jafs) jafs[(long)b * 7 + lane] = st == MISTI_OK ? jn_c : nan("");
+            if (jafs_raw) jafs_raw[(long)b * 7 + lane] = st == MISTI_OK ? raw_c : nan("");
         }
         // fused composite likelihood over all data rows (bootstrap replicates): lanes stride the rows
         const double bad = (st == MISTI_NEGATIVE_PARAM || st == MISTI_CORRECTION_FAILED) ? -misti::kInf : nan("");
+        const double* logj = ysm + misti::kTailLog;
         if (row_ids) {  // one data row per item
             const int r = row_ids[b];
             if (lane == 0) llh[b] = (st == MISTI_OK && r >= 0 && r < R) ? misti::score_row(data + 8 * (long)r, logj) : bad;

@@ -63,7 +63,7 @@ int hs_jsfs(int numT, int splitT, int sampleDate, const double* times, int n_ban
             const double* drow /* 7 + const */, double* raw, double* jn, double* llh, int* terms) {
     misti::ModelDesc md;
     fill_model(md, numT, splitT, sampleDate, n_bands, bands, n_pulses, pulses, n_params);
-    double cpost[3], ysm[2 * misti::kYStride], logj[7];
+    double cpost[3], ysm[misti::kGroupScratch], logj[7];
     misti::post_split_coeffs(md, times, lc, 2, 1, cpost);
     std::vector<double> rec((size_t)(numT + 1) * misti::kRecSlots);
     int nseg = 0;
@@ -74,9 +74,15 @@ int hs_jsfs(int numT, int splitT, int sampleDate, const double* times, int n_ban
         hs_last_nseg = nseg;
     }
     misti::SingleLane g;
-    st = misti::jsfs_item<misti::SingleLane>(g, md, true, params, rec.data(), nseg, cpost, ysm, raw, terms);
+    static misti::RunEnt runtab[MISTI_NM_NNZ];
+    for (int e = 0; e < MISTI_NM_NNZ; ++e) misti::fill_run_entry<misti::SingleLane>(e, &runtab[e]);
+    misti::LaneCtx<misti::SingleLane> L;
+    L.init(g, ysm, runtab);
+    st = misti::jsfs_item<misti::SingleLane>(g, L, md, true, params, rec.data(), nseg, cpost, raw, terms);
     if (st != MISTI_OK) return st;
-    if (!misti::jafs_normalise_logs(raw, unfolded != 0, jn, logj)) return MISTI_NONFINITE;
+    double jn0;
+    if (!misti::jafs_finish(g, ysm, raw, unfolded != 0, &jn0)) return MISTI_NONFINITE;
+    for (int c = 0; c < 7; ++c) { jn[c] = ysm[misti::kTailJn + c]; logj[c] = ysm[misti::kTailLog + c]; }
     *llh = misti::score_row(drow, logj);
     return MISTI_OK;
 }

@@ -177,14 +177,14 @@ def main():
 
     def code_of(kind, cnt):
         return kind + {1: 0, 2: 4, 4: 8}[cnt]
-    l16_row, l16_rem, l16_loc, pad = [], [], [], 44
+    l16_row, l16_loc, rem_sets, pad = [], [], [], 44
     for ln in lanes16:
         rows, rems, locs = [], [], []
         for sl, r in enumerate(ln):
             if r is None:
                 rows.append(pad)
                 pad += 1
-                rems.append([(0, 12)] * 3)
+                rems.append([])
                 locs.append([12, 12])
                 continue
             rows.append(r)
@@ -196,12 +196,59 @@ def main():
                 else:
                     rem.append((c, code_of(k, n)))
             assert len(rem) <= RW[sl], (r, rem)
-            rems.append(rem + [(r, 12)] * (3 - len(rem)))
+            rems.append(rem)
             locs.append(loc)
         l16_row.append(rows)
-        l16_rem.append(rems)
+        rem_sets.append(rems)
         l16_loc.append(locs)
     assert pad <= 48
+    # shared-memory position of a state: 16 * slot + lane, so that the 16 lanes of a group store one slot without a bank
+    # conflict (8-byte words: bank pair = position mod 16 = owning lane).  The remote loads conflict when two lanes of
+    # the group read different words owned by the same lane in the same load instruction; the ORDER of a lane's remote
+    # entries and the address of its padding entries (coefficient 0: any word will do) are chosen by a seeded local
+    # search to minimise the wavefronts per mat-vec.
+    l16_pos = [0] * 48
+    for ln, rows in enumerate(l16_row):
+        for sl, r in enumerate(rows):
+            l16_pos[r] = 16 * sl + ln
+
+    def wavefronts(addrs):
+        banks = {}
+        for a in addrs:
+            banks.setdefault(a % 16, set()).add(a)
+        return max(len(v) for v in banks.values())
+
+    def layout_cost(lay):
+        tot = 0
+        for sl in range(3):
+            for e in range(RW[sl]):
+                tot += wavefronts([l16_pos[lay[ln][sl][e][0]] for ln in range(16)])
+        return tot
+    import random
+    rnd = random.Random(20261018)
+    lay = [[rem_sets[ln][sl] + [(l16_row[ln][sl], 12)] * (3 - len(rem_sets[ln][sl])) for sl in range(3)] for ln in range(16)]
+    best = layout_cost(lay)
+    for _ in range(60000):
+        ln, sl = rnd.randrange(16), rnd.randrange(3)
+        cand = list(lay[ln][sl])
+        if rnd.random() < 0.5:
+            head = cand[:RW[sl]]
+            rnd.shuffle(head)
+            cand = head + cand[RW[sl]:]
+        else:
+            pads = [i for i in range(RW[sl]) if cand[i][1] == 12]
+            if not pads:
+                continue
+            cand[rnd.choice(pads)] = (rnd.randrange(48), 12)
+        old = lay[ln][sl]
+        lay[ln][sl] = cand
+        c = layout_cost(lay)
+        if c <= best:
+            best = c
+        else:
+            lay[ln][sl] = old
+    l16_rem = lay
+    l16_wavefronts = best + 3
     # ---- q = max |M_cc| needs only the Pareto-maximal diagonal multiplicity tuples (all rates are >= 0)
     tuples = sorted(set(tuple(d) for d in diag))
     qdiag = [t for t in tuples if not any(o != t and all(o[k] >= t[k] for k in range(4)) for o in tuples)]
@@ -280,6 +327,8 @@ def main():
         "{" + ",".join("{%d,%d,%d}" % e for e in (row + [(r, 0, 0)] * (4 - len(row)))) + "}" for r, row in enumerate(ell)))
     o.append("// 16-lane layout: state (or pad row 44..47) per lane and slot; remote entries {col, code} per slot (3 each,")
     o.append("// slot b uses 2); local coefficient codes {from slot (s+1)%3, from slot (s+2)%3}; code = kind + 4 log2(count), 12 = none")
+    o.append("// shared-memory position of each state in the 16-lane layout (16 * slot + lane); %d wavefronts per mat-vec and group" % l16_wavefronts)
+    o.append("#define MISTI_L16_POS_INIT { %s }" % ",".join(str(v) for v in l16_pos))
     o.append("#define MISTI_L16_ROW_INIT { %s }" % ", ".join("{" + ",".join(str(v) for v in r) + "}" for r in l16_row))
     o.append("#define MISTI_L16_REM_INIT { %s }" % ", ".join(
         "{" + ",".join("{" + ",".join("{%d,%d}" % e for e in slot) + "}" for slot in lane) + "}" for lane in l16_rem))

@@ -85,6 +85,12 @@ def main():
         w.writerow(["file", "line", "pct_instructions", "pct_stall_samples", "source"])
         for l in sorted(lines, key=lambda x: -x[3])[:40]:
             w.writerow([l[0], l[1], round(100 * l[3] / tot_i, 2), round(100 * l[4] / tot_s, 2), l[2][:110]])
+    if len(sys.argv) > 3:  # optional: every source line, for aggregation by function
+        with open(sys.argv[3], "w", newline="") as f:
+            w = csv.writer(f)
+            w.writerow(["file", "line", "instructions", "stall_samples"])
+            for l in lines:
+                w.writerow([l[0], l[1], l[3], l[4]])
     print(json.dumps(summary["metrics"], indent=1))
     print(summary["stall_samples_pct"])
     print(summary["instruction_mix_pct"])
