@@ -287,3 +287,33 @@ def test_stiff_intervals_take_the_dense_step(engine, golden_datasets, golden_cas
     for b in plain[1:]:
         assert np.array_equal(out["jafs"][b], out["jafs"][plain[0]])
     assert relerr(out["llh"][stiff[0], 0], case["expect"]["llh"]) < 1e-8
+
+
+def test_results_do_not_depend_on_the_warp_partner(engine, golden_datasets, golden_cases):
+    """two items share a warp and run in lock step (series lengths, sub-steps and segment types of the partner differ):
+    every item must come out bit-identical to its evaluation alone."""
+    rng = np.random.default_rng(99)
+    ds = golden_datasets["synthetic"]
+    engine.clear_models()
+    gid = engine.add_grid(ds["times"], ds["lambdas"])
+    m_band = engine.add_model(gid, 40, 0, bands=[(1, 5, 12, 0.8, 0)])
+    m_long = engine.add_model(gid, 40, 0, bands=[(0, 4, 40, 3.0, 0)])
+    m_none = engine.add_model(gid, 38, 0)
+    m_two = engine.add_model(gid, 40, 0, bands=[(0, 2, 10, 0.3, 0), (1, 5, 12, 0.8, 1)], pulses=[(0, 7, 0.05, 2)])
+    engine.set_data([ds["sfs"]], True)
+    import misti_b200
+    flags = misti_b200.FLAG_CORRECT | misti_b200.FLAG_CPFIT | misti_b200.FLAG_SMOOTH | misti_b200.FLAG_UNFOLDED
+    B = 37
+    params = np.zeros((B, 3))
+    params[:, 0] = 10 ** rng.uniform(-4, 0.7, B)   # migration rates over five decades: very different series lengths
+    params[:, 1] = rng.uniform(0, 3, B)
+    params[:, 2] = rng.uniform(0, 0.3, B)
+    models = rng.choice([m_band, m_long, m_none, m_two], B).astype(np.int32)
+    out = engine.evaluate(params, model_ids=models, flags=flags, want=("jafs", "status", "terms"))
+    assert (out["status"] == 0).sum() >= B - 4
+    for b in range(B):
+        one = engine.evaluate(params[b:b + 1], model_ids=models[b:b + 1], flags=flags, want=("jafs", "status", "terms"))
+        assert one["status"][0] == out["status"][b]
+        assert one["terms"][0] == out["terms"][b]
+        assert np.array_equal(one["llh"][0], out["llh"][b], equal_nan=True), b
+        assert np.array_equal(one["jafs"][0], out["jafs"][b], equal_nan=True), b

@@ -141,3 +141,30 @@ def test_no_split_inside_grid(hostsim, golden_datasets):
     case["mi"] = []
     rc, *_ = _jsfs(hostsim, golden_datasets, case, d["lambdas"])
     assert rc == 4  # infinite coalescent time, no migration
+
+
+def test_segment_lists(hostsim, golden_datasets, golden_cases):
+    """the per-item scalar pre-pass: zero-migration intervals merge into closed-form runs (type 2), broken by migration
+    intervals (type 1, one segment each), the sampling date and pulses"""
+    def types_of(case):
+        rc, *_ = _jsfs(hostsim, golden_datasets, case, case["expect"]["lc"])
+        assert rc == 0
+        buf = (ctypes.c_int * 256)()
+        n = hostsim.hs_segment_types(buf, 256)
+        return list(buf[:n])
+    by_name = {c["name"]: c for c in golden_cases}
+    assert types_of(by_name["c1_st36_uf"]) == [2]                       # no migration at all: one run up to the split
+    assert types_of(by_name["c2_cpfit_m0"]) == [2]                      # a band with rate 0 is no migration either
+    assert types_of(by_name["c2_cpfit_m0.8"]) == [2] + [1] * 7 + [2]    # band over intervals 5..11 of 40
+    assert types_of(by_name["c4_cpfit_band"]) == [2, 2] + [1] * 6 + [2]  # sampling date at 12, band 14..19
+    for case in golden_cases:
+        if not case["expect"]["ok"] or case["name"] in RUNAWAY:
+            continue
+        ty = types_of(case)
+        times, lam, st, sd = grid_of(golden_datasets, case)
+        n_mig = sum(1 for t in ty if t == 1)
+        assert all(t in (1, 2, 4) for t in ty) and n_mig <= min(st, len(lam))
+        if not case["mi"] and not case["flags"].get("trueEPS"):
+            assert n_mig == 0
+            # runs are broken only by the sampling date and by pulses
+            assert len(ty) <= 1 + (1 if 0 < sd < st else 0) + len(case["pu"])

@@ -104,3 +104,79 @@ def test_mirror_state_maps():
     for i in range(8):
         assert sorted((l.d0, l.d1) for l in op.MapIndToState(i)) == sorted(mo.STATES1[i])
         assert op.MapStateToInd(op.MapIndToState(i)) == i
+
+
+def test_uniformisation_rate_table():
+    """max_c |M_cc| is attained on one of the Pareto-maximal diagonal rows (MISTI_QDIAG)."""
+    diag, qd = np.array(_macro("MISTI_GEN_DIAG_INIT")), np.array(_macro("MISTI_QDIAG_INIT"))
+    assert len(qd) == _macro("MISTI_QDIAG_N")
+    rng = np.random.default_rng(17)
+    for _ in range(200):
+        rate = rng.uniform(0.0, 1.0, 4) ** rng.integers(1, 6) * 10 ** rng.uniform(-3, 3)
+        if rng.random() < 0.3:
+            rate[rng.integers(0, 4)] = 0.0
+        assert (qd @ rate).max() == (diag @ rate).max()
+
+
+def test_zero_migration_projector_table():
+    """sum_ab coef_ab G0_a G1_b reproduces expm over a run of zero-migration intervals and its time integral."""
+    from scipy.linalg import expm
+    rp, col, ab, val = (_macro("MISTI_NM_%s_INIT" % n) for n in ("ROWPTR", "COL", "AB", "VAL"))
+    assert rp[0] == 0 and rp[44] == _macro("MISTI_NM_NNZ") == len(col) == len(ab) == len(val)
+    G = np.zeros((8, 44, 44))
+    for r in range(44):
+        for e in range(rp[r], rp[r + 1]):
+            G[ab[e], r, col[e]] = val[e]
+    assert np.allclose(G.sum(axis=0), np.eye(44), atol=1e-15)
+    AB = [(0, 0), (1, 0), (3, 0), (6, 0), (0, 1), (0, 3), (0, 6), (1, 1)]
+    rng = np.random.default_rng(23)
+    for trial in range(4):
+        n = 5
+        la0, la1, T = rng.uniform(0.2, 4.0, n), rng.uniform(0.2, 4.0, n), rng.uniform(1e-3, 0.6, n)
+        P0 = rng.uniform(0, 1, 44)
+        P0 /= P0.sum()
+        P, I = P0.copy(), np.zeros(44)
+        for i in range(n):  # reference: Van Loan augmented exponential per interval
+            aug = np.zeros((45, 45))
+            aug[:44, :44] = mo.generator_two_pop(la0[i], la1[i], 0.0, 0.0) * T[i]
+            aug[:44, 44] = P * T[i]
+            E = expm(aug)
+            I += E[:44, 44]
+            P = E[:44, :44] @ P
+        X0, X1, c = 0.0, 0.0, np.zeros(8)
+        for i in range(n):
+            for k, (a, b) in enumerate(AB):
+                z = a * la0[i] + b * la1[i]
+                c[k] += np.exp(-a * X0 - b * X1) * (T[i] if z == 0 else -np.expm1(-z * T[i]) / z)
+            X0 += la0[i] * T[i]
+            X1 += la1[i] * T[i]
+        e = [np.exp(-a * X0 - b * X1) for a, b in AB]
+        assert np.max(np.abs(sum(e[k] * (G[k] @ P0) for k in range(8)) - P)) < 1e-14
+        assert np.max(np.abs(sum(c[k] * (G[k] @ P0) for k in range(8)) - I)) < 1e-14
+
+
+def test_sixteen_lane_layout():
+    """every state is owned by exactly one (lane, slot); local + remote entries of a row are exactly its generator
+    entries; a slot's 16 words sit in 16 different bank pairs."""
+    row, rem, loc, pos = (_macro("MISTI_L16_%s_INIT" % n) for n in ("ROW", "REM", "LOC", "POS"))
+    ell = _macro("MISTI_ELL_INIT")
+    assert sorted(r for ln in row for r in ln) == list(range(48))
+    assert sorted(pos) == list(range(48))
+    rw = (3, 2, 3)
+    for ln in range(16):
+        for sl in range(3):
+            r = row[ln][sl]
+            assert pos[r] == 16 * sl + ln
+            got = []
+            for e in range(rw[sl]):
+                c, code = rem[ln][sl][e]
+                if code != 12:
+                    got.append([c, code & 3, 1 << (code >> 2)])
+            assert all(code == 12 for (_c, code) in rem[ln][sl][rw[sl]:])
+            for j in range(2):
+                if loc[ln][sl][j] != 12:
+                    got.append([row[ln][(sl + 1 + j) % 3], loc[ln][sl][j] & 3, 1 << (loc[ln][sl][j] >> 2)])
+            want = [list(e) for e in ell[r] if e[2]] if r < 44 else []
+            assert sorted(got) == sorted(want), (ln, sl)
+    codes = {c for ln in rem for sl in ln for (_x, c) in sl} | {c for ln in loc for sl in ln for c in sl}
+    assert codes <= set(range(10)) | {12}  # the record's table slots 10, 11 are free for 1/q and lam

@@ -40,6 +40,10 @@ def main():
     sw = Sweep(inp.times, inp.lambdas, [data], unfolded=True, cpfit=True, engine=eng)
     sw.add_model(40, [[2, 5, 12, 0.8, 1]])
     sw.solve()
+    for cp in (False, True):  # one-time costs of the other kernel variants / host imports (lgamma) outside the timed regions
+        sw = Sweep(inp.times, inp.lambdas, bs[:2], unfolded=cp, cpfit=cp, smooth=True, engine=eng)
+        sw.add_model(40)
+        sw.evaluate_grid()
 
     t = time.perf_counter()
     sw = Sweep(inp.times, inp.lambdas, [data], unfolded=True, cpfit=True, engine=eng)
