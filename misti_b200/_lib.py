@@ -7,7 +7,7 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libmisti_b200.so")
+LIB_PATH = os.environ.get("MISTI_B200_LIB") or os.path.join(HERE, "libmisti_b200.so")  # the variable is a development knob
 
 MAX_BANDS, MAX_PULSES, MAX_PARAMS = 8, 8, 16
 

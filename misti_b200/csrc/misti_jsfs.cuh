@@ -226,7 +226,8 @@ MISTI_D inline int build_segments_item(const ModelDesc& md, const double* times,
             // e_ab = exp(-a X0 - b X1) at the start of the interval; phi_ab = (1 - exp(-(a la0 + b la1) T)) / (a la0 + b la1);
             // 1 - v^3 = (1 - v)(1 + v + v^2) and 1 - v0 v1 = (1 - v0) + v0 (1 - v1) keep every term positive
             const double z0 = la0 * T, z1 = la1 * T;
-            const double v0 = exp(-z0), w0 = -expm1(-z0), v1 = exp(-z1), w1 = -expm1(-z1);
+            // v = exp(-z) as 1 - w: the absolute error (1e-16) is what matters for a survival factor
+            const double w0 = -expm1(-z0), w1 = -expm1(-z1), v0 = 1.0 - w0, v1 = 1.0 - w1;
             const double v03 = v0 * v0 * v0, v13 = v1 * v1 * v1;
             const double w03 = w0 * (1.0 + v0 + v0 * v0), w13 = w1 * (1.0 + v1 + v1 * v1);
             const double w06 = w03 * (1.0 + v03), w16 = w13 * (1.0 + v13);

@@ -44,17 +44,28 @@ template <int MINB>
 __global__ void __launch_bounds__(kCorrectThreads, MINB)
 misti_correct_kernel(int B, int P, const double* __restrict__ params, const int* __restrict__ model_ids, int model_default,
                      const ModelDesc* __restrict__ models, const double* __restrict__ times, const double* __restrict__ lh,
-                     unsigned flags, double mixtureTH, const double* __restrict__ lc_inject, int numT_max, double* lc,
+                     const double* __restrict__ gaux, unsigned flags, double mixtureTH, const double* __restrict__ lc_inject, int numT_max, double* lc,
                      long stride, double* __restrict__ cpost, double* pr_out, int* __restrict__ status, int* __restrict__ nfev,
                      double* __restrict__ rec, int seg_cap, int* __restrict__ nseg) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    // one model for the whole batch (the usual case): its descriptor is staged in shared memory once per block
+    __shared__ ModelDesc smd;
+    if (!model_ids) {
+        const int* src = reinterpret_cast<const int*>(models + model_default);
+        int* dst = reinterpret_cast<int*>(&smd);
+        for (int i = threadIdx.x; i < (int)(sizeof(ModelDesc) / sizeof(int)); i += blockDim.x) dst[i] = src[i];
+        __syncthreads();
+    }
     if (b >= B) return;
-    const ModelDesc& md = models[model_ids ? model_ids[b] : model_default];
+    const ModelDesc& md = model_ids ? models[model_ids[b]] : smd;
     const double* tt = times + md.grid_off;
     const double* ll = lh + 2 * md.grid_off;
+    const double* ga = gaux + misti::kGridAux * md.grid_off;
     const double* par = params + (long)b * P;
     double* lcb = lc + b;
     int st = MISTI_OK, nf = 0;
+    double cp[3] = {0.0, 0.0, 0.0};
+    bool cp_done = false;
     if (lc_inject) {
         for (int i = 0; i < md.n_params; ++i)
             if (par[i] < 0) st = MISTI_NEGATIVE_PARAM;
@@ -65,12 +76,11 @@ misti_correct_kernel(int B, int P, const double* __restrict__ params, const int*
         }
     } else {
         double* pr = pr_out ? pr_out + (long)b * (numT_max + 1) * 6 : nullptr;
-        st = misti::correct_lambdas_item(md, tt, ll, par, flags, mixtureTH, lcb, kPitch, stride, pr, &nf);
+        st = misti::correct_lambdas_item(md, tt, ll, par, flags, mixtureTH, lcb, kPitch, stride, pr, &nf, ga, cp, &cp_done);
     }
-    double cp[3] = {0.0, 0.0, 0.0};
     int ns = 0;
     if (st == MISTI_OK) {
-        misti::post_split_coeffs(md, tt, lcb, kPitch, stride, cp);
+        if (!cp_done) misti::post_split_coeffs(md, tt, lcb, kPitch, stride, cp);
         // all per-interval scalar work of the JSFS stage: the item's segment records
         st = misti::build_segments_item(md, tt, par, lcb, kPitch, stride, rec + (long)b * seg_cap * misti::kRecSlots, &ns);
     }
@@ -459,9 +469,9 @@ struct misti_ctx {
     int sm_count = 148;
     // grids (pooled: grid g occupies intervals [grid_off[g], grid_off[g] + numT[g]); times padded with one 0)
     std::vector<int> grid_numT, grid_off;
-    std::vector<double> h_times, h_lh;
+    std::vector<double> h_times, h_lh, h_gaux;  // h_gaux: misti::grid_aux_row per interval
     int numT_max = 0;
-    double *d_times = nullptr, *d_lh = nullptr;
+    double *d_times = nullptr, *d_lh = nullptr, *d_gaux = nullptr;
     size_t d_grid_cap = 0;
     bool grids_dirty = false;
     // models
@@ -541,14 +551,17 @@ int sync_tables(misti_ctx* ctx) {
             while (ncap < need) ncap *= 2;
             if (ctx->d_times) CK(cudaFree(ctx->d_times));
             if (ctx->d_lh) CK(cudaFree(ctx->d_lh));
-            ctx->d_times = ctx->d_lh = nullptr;
+            if (ctx->d_gaux) CK(cudaFree(ctx->d_gaux));
+            ctx->d_times = ctx->d_lh = ctx->d_gaux = nullptr;
             CK(cudaMalloc((void**)&ctx->d_times, ncap * sizeof(double)));
             CK(cudaMalloc((void**)&ctx->d_lh, 2 * ncap * sizeof(double)));
+            CK(cudaMalloc((void**)&ctx->d_gaux, misti::kGridAux * ncap * sizeof(double)));
             ctx->d_grid_cap = ncap;
         }
         // the previous launches may still read the old tables: copies are stream-ordered behind them
         CK(cudaMemcpyAsync(ctx->d_times, ctx->h_times.data(), need * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaMemcpyAsync(ctx->d_lh, ctx->h_lh.data(), 2 * need * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->d_gaux, ctx->h_gaux.data(), misti::kGridAux * need * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
         ctx->grids_dirty = false;
     }
@@ -643,7 +656,7 @@ void misti_ctx_destroy(misti_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    void* ptrs[] = {ctx->d_times, ctx->d_lh, ctx->d_models, ctx->d_data, ctx->d_lc, ctx->d_cpost, ctx->d_status, ctx->d_nfev, ctx->d_conts, ctx->d_queue[0], ctx->d_queue[1], ctx->d_counts,
+    void* ptrs[] = {ctx->d_times, ctx->d_lh, ctx->d_gaux, ctx->d_models, ctx->d_data, ctx->d_lc, ctx->d_cpost, ctx->d_status, ctx->d_nfev, ctx->d_conts, ctx->d_queue[0], ctx->d_queue[1], ctx->d_counts,
                     ctx->d_rec, ctx->d_nseg, ctx->s_params, ctx->s_llh, ctx->s_jafs, ctx->s_jafs_raw, ctx->s_model_ids, ctx->s_terms, ctx->s_row_ids, ctx->s_lc_io,
                     ctx->s_pr, ctx->d_small};
     for (void* p : ptrs)
@@ -689,6 +702,11 @@ int misti_add_grid(misti_ctx* ctx, int32_t numT, const double* times, const doub
     for (int i = 0; i < numT - 1; ++i) ctx->h_times.push_back(times[i]);
     ctx->h_times.push_back(0.0);  // padding: the last interval is infinite and has no length entry
     for (int i = 0; i < 2 * numT; ++i) ctx->h_lh.push_back(lh[i]);
+    for (int i = 0; i < numT; ++i) {
+        double row[misti::kGridAux];
+        misti::grid_aux_row(lh + 2 * i, ctx->h_times[off + i], row);
+        for (int j = 0; j < misti::kGridAux; ++j) ctx->h_gaux.push_back(row[j]);
+    }
     if (numT > ctx->numT_max) ctx->numT_max = numT;
     ctx->grids_dirty = true;
     *grid_id = (int32_t)ctx->grid_numT.size() - 1;
@@ -735,7 +753,7 @@ int misti_clear_models(misti_ctx* ctx) {
     if (!ctx) return MISTI_E_ARG;
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
-    ctx->grid_numT.clear(); ctx->grid_off.clear(); ctx->h_times.clear(); ctx->h_lh.clear(); ctx->h_models.clear();
+    ctx->grid_numT.clear(); ctx->grid_off.clear(); ctx->h_times.clear(); ctx->h_lh.clear(); ctx->h_gaux.clear(); ctx->h_models.clear();
     ctx->numT_max = 0;
     ctx->grids_dirty = ctx->models_dirty = false;
     return 0;
@@ -784,7 +802,8 @@ static int eval_chunk(misti_ctx* ctx, int B, int P, const double* d_params, cons
     CK(cudaEventRecord(ctx->ev[0], ctx->stream));
 #define MISTI_LAUNCH_CORRECT(MINB)                                                                                       \
     misti_correct_kernel<MINB><<<(B + kCorrectThreads - 1) / kCorrectThreads, kCorrectThreads, 0, ctx->stream>>>(          \
-        B, P, d_params, d_model_ids, model_default, ctx->d_models, ctx->d_times, ctx->d_lh, flags, mixture_th, d_lc_inject, \
+        B, P, d_params, d_model_ids, model_default, ctx->d_models, ctx->d_times, ctx->d_lh, ctx->d_gaux, flags, mixture_th, \
+        d_lc_inject, \
         numT_max, ctx->d_lc, stride, ctx->d_cpost, d_pr, ctx->d_status, ctx->d_nfev, ctx->d_rec, ctx->cap_seg, ctx->d_nseg)
     switch (ctx->correct_minb) {  // register budget per thread: 4 -> 255, 8 -> 128, 12 -> 80 (tuning knob MISTI_CORRECT_MINB)
         case 4: MISTI_LAUNCH_CORRECT(4); break;

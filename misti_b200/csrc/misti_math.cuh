@@ -88,7 +88,8 @@ MISTI_HD inline bool mat3_inv(const double* A, double* Ainv) {
 
 // exp(A) for a 3x3 matrix: Pade [m/m] with m in {3,5,7,9,13} chosen from ||A||_1, scaling and
 // squaring (Higham 2005 thresholds; same algorithm family as scipy.linalg.expm).
-MISTI_HD MISTI_NOINLINE inline void mat3_expm(const double* Ain, double* E) {
+// (inlined into its three callers: the 9-element arrays then live in registers instead of going through the stack)
+MISTI_HD inline void mat3_expm(const double* Ain, double* E) {
     double A[9];
     double nrm = 0.0;
     for (int j = 0; j < 3; ++j) {
@@ -738,37 +739,55 @@ struct ResidualSingle {
     }
 };
 
+// Per-interval constants of a grid, shared by every item that uses the grid (computed once on the host when the grid
+// is registered): exp(-lh_g T), 1 - exp(-lh_g T) for the two genomes, and 1/T.
+constexpr int kGridAux = 5;
+MISTI_HD inline void grid_aux_row(const double* lh2, double T, double* out) {
+    out[0] = exp(-lh2[0] * T); out[1] = exp(-lh2[1] * T);
+    out[2] = -expm1(-lh2[0] * T); out[3] = -expm1(-lh2[1] * T);
+    out[4] = 1.0 / T;
+}
+
 // SolveLambdaSystem (CorrectLambda.py:266-317).  On return lc[2] and st->P0 (advanced through the
 // interval).  Returns false when the reference would report a failed correction or crash.
-MISTI_HD inline bool solve_interval(IntervalState* st, bool cpfit, double mixtureTH, double* lc, int* nfev) {
+// `ga` (nullable): grid_aux_row of this interval.
+MISTI_HD inline bool solve_interval(IntervalState* st, bool cpfit, double mixtureTH, double* lc, int* nfev, const double* ga = nullptr) {
     const double T = st->T;
     double (*P0)[3] = st->P0;
     const double s0 = (P0[0][0] + P0[0][1]) + P0[0][2], s1 = (P0[1][0] + P0[1][1]) + P0[1][2];
-    double mix = 0;
-    for (int i = 0; i < 3; ++i) { const double d = P0[0][i] / s0 - P0[1][i] / s1; mix += d * d; }
-    if (sqrt(mix) < mixtureTH) { lc[0] = lc[1] = -1; return false; }
+    if (mixtureTH > 0) {  // sqrt(mix) >= 0: the test can only fire for a positive threshold
+        double mix = 0;
+        for (int i = 0; i < 3; ++i) { const double d = P0[0][i] / s0 - P0[1][i] / s1; mix += d * d; }
+        if (sqrt(mix) < mixtureTH) { lc[0] = lc[1] = -1; return false; }
+    }
     if (st->mu[0] + st->mu[1] < 1e-10) {
-        if (cpfit) {  // SolveNoMigration1 (:213-235)
-            const double A1 = P0[0][0] / s0, A2 = P0[0][1] / s0, A3 = P0[1][0] / s1, A4 = P0[1][1] / s1;
-            const double C1 = P0[0][2] / s0, C2 = P0[1][2] / s1;
-            const double D = A1 * A4 - A2 * A3;
-            const double B1 = A4 / D, B2 = -A2 / D, B3 = -A3 / D, B4 = A1 / D;
-            const double X1 = exp(-st->lh[0] * T) - C1, X2 = exp(-st->lh[1] * T) - C2;
-            const double a0 = B1 * X1 + B2 * X2, a1 = B3 * X1 + B4 * X2;
-            if (a0 > 0 && a1 > 0) { lc[0] = -log(a0) / T; lc[1] = -log(a1) / T; }
-            else { lc[0] = lc[1] = -1; return false; }
-        } else {      // SolveNoMigration (:253-264)
-            ResidualNoMig fun;
-            fun.st = st;
-            for (int i = 0; i < 3; ++i) { fun.pr0[0][i] = P0[0][i] / s0; fun.pr0[1][i] = P0[1][i] / s1; }
-            const double lb = 0.01 * (st->lh[0] < st->lh[1] ? st->lh[0] : st->lh[1]);
-            double x[2] = {st->lh[0], st->lh[1]};
-            int nf = 0;
-            const int status = least_squares_trf<2>(fun, x, true, lb, &nf);
-            *nfev += nf;
-            if (status < 0) return false;
-            lc[0] = x[0]; lc[1] = x[1];
+        if (cpfit) {
+            // SolveNoMigration1 (:213-235): find (a0, a1) = (exp(-l0 T), exp(-l1 T)) with
+            //   P0[k][0] a0 + P0[k][1] a1 + P0[k][2] = exp(-lh_k T) s_k   for both genomes k.
+            // The reference normalises by s_k and inverts the 2x2 matrix entry by entry (12 divisions); this is the same
+            // linear system solved with one reciprocal, and the state is advanced with a0, a1 themselves.
+            const double E0 = ga ? ga[0] : exp(-st->lh[0] * T), E1 = ga ? ga[1] : exp(-st->lh[1] * T);
+            const double invT = ga ? ga[4] : 1.0 / T;
+            const double Y0 = E0 * s0 - P0[0][2], Y1 = E1 * s1 - P0[1][2];
+            const double det = P0[0][0] * P0[1][1] - P0[0][1] * P0[1][0];
+            const double rdet = 1.0 / det;
+            const double a0 = (P0[1][1] * Y0 - P0[0][1] * Y1) * rdet, a1 = (P0[0][0] * Y1 - P0[1][0] * Y0) * rdet;
+            if (!(a0 > 0 && a1 > 0)) { lc[0] = lc[1] = -1; return false; }
+            lc[0] = -log(a0) * invT; lc[1] = -log(a1) * invT;
+            for (int k = 0; k < 2; ++k) { P0[k][0] *= a0; P0[k][1] *= a1; }
+            return lc[0] > 0 && lc[1] > 0;
         }
+        // SolveNoMigration (:253-264)
+        ResidualNoMig fun;
+        fun.st = st;
+        for (int i = 0; i < 3; ++i) { fun.pr0[0][i] = P0[0][i] / s0; fun.pr0[1][i] = P0[1][i] / s1; }
+        const double lb = 0.01 * (st->lh[0] < st->lh[1] ? st->lh[0] : st->lh[1]);
+        double x[2] = {st->lh[0], st->lh[1]};
+        int nf = 0;
+        const int status = least_squares_trf<2>(fun, x, true, lb, &nf);
+        *nfev += nf;
+        if (status < 0) return false;
+        lc[0] = x[0]; lc[1] = x[1];
         const double e0 = exp(-lc[0] * T), e1 = exp(-lc[1] * T);
         for (int k = 0; k < 2; ++k) { P0[k][0] *= e0; P0[k][1] *= e1; }
         return lc[0] > 0 && lc[1] > 0;

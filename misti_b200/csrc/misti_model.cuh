@@ -44,9 +44,15 @@ MISTI_HD inline double pulse_rate(const ModelDesc& md, const double* params, int
 
 // lc is addressed as lc[(pitch*t+g)*stride] (pitch >= 2 values per interval); times[numT-1]; lh[numT][2].
 // Pr (nullable): [splitT+1][3][2] trajectory of the 3-state chains (MigrationInference.py:309,350).
+// gaux (nullable): [numT][kGridAux] per-interval constants of the grid (grid_aux_row).
+// cpost (nullable): in cpfit mode the post-split closed-form coefficients (see post_split_coeffs in misti_jsfs.cuh)
+// fall out of the post-split pass for free (exp(-lam T) is the fitted non-coalescence probability itself);
+// *cpost_done tells the caller whether they were written.
 MISTI_HD inline int correct_lambdas_item(const ModelDesc& md, const double* times, const double* lh, const double* params,
                                          unsigned flags, double mixtureTH, double* lc, int pitch, long stride, double* Pr,
-                                         int* nfev_out) {
+                                         int* nfev_out, const double* gaux = nullptr, double* cpost = nullptr,
+                                         bool* cpost_done = nullptr) {
+    if (cpost_done) *cpost_done = false;
     const bool correct = flags & MISTI_FLAG_CORRECT, cpfit = flags & MISTI_FLAG_CPFIT;
     int nfev = 0;
     for (int i = 0; i < md.n_params; ++i)
@@ -79,7 +85,7 @@ MISTI_HD inline int correct_lambdas_item(const ModelDesc& md, const double* time
             st.T = times[t];
             st.mu[0] = band_rate(md, params, t, 0); st.mu[1] = band_rate(md, params, t, 1);
             double l[2];
-            const bool ok = solve_interval(&st, cpfit, mixtureTH, l, &nfev);
+            const bool ok = solve_interval(&st, cpfit, mixtureTH, l, &nfev, gaux ? gaux + kGridAux * t : nullptr);
             lc[(pitch * t) * stride] = l[0];
             lc[(pitch * t + 1) * stride] = l[1];
             if (!ok) { *nfev_out = nfev; return MISTI_CORRECTION_FAILED; }
@@ -91,27 +97,63 @@ MISTI_HD inline int correct_lambdas_item(const ModelDesc& md, const double* time
         nc0 = (st.P0[0][0] + st.P0[0][1]) + st.P0[0][2];  // reference quirk: a probability used as a log (:353-354)
         nc1 = (st.P0[1][0] + st.P0[1][1]) + st.P0[1][2];
     }
-    for (int t = splitT; t < numT - 1; ++t) {
-        const double T = times[t];
-        if (T == 0) { lc[(pitch * t) * stride] = 1; lc[(pitch * t + 1) * stride] = 1; continue; }
-        double lam;
-        if (!cpfit) {
-            if (!fit_single_pop(lh + 2 * t, T, nc0, nc1, &lam, &nfev)) { *nfev_out = nfev; return MISTI_NONFINITE; }
-        } else {
-            const double pnc = (exp(-T * lh[2 * t]) + exp((nc1 - nc0) - T * lh[2 * t + 1])) / (1 + exp(nc1 - nc0));
-            lam = -log(pnc) / T;
+    if (cpfit && splitT < numT) {
+        // Post-split rates, cpfit mode (:356-374): pnc_t = (exp(-T lh0) + exp((nc1 - nc0) - T lh1)) / (1 + exp(nc1 - nc0)),
+        // lam_t = -log(pnc_t) / T, and nc0, nc1 both drop by T lam_t -- so d = nc1 - nc0 never changes and the intervals are
+        // independent of each other: pnc_t = (E0_t + e^d E1_t) / (1 + e^d) with the grid constants E_g = exp(-T lh_g).
+        // The last rate (pr0 + pr1) / (pr0 / lh0 + pr1 / lh1), pr_k = exp(nc_k), is (1 + e^d) / (1 / lh0 + e^d / lh1).
+        const double ed = exp(nc1 - nc0), wn = 1.0 / (1.0 + ed);
+        double c6 = 0, c3 = 0, c1 = 0, e1 = 1.0;  // e1 = exp(-sum of lam T so far)
+        for (int t = splitT; t < numT - 1; ++t) {
+            const double T = times[t];
+            if (T == 0) { lc[(pitch * t) * stride] = 1; lc[(pitch * t + 1) * stride] = 1; continue; }
+            double ga[kGridAux];
+            if (gaux) { for (int i = 0; i < kGridAux; ++i) ga[i] = gaux[kGridAux * t + i]; }
+            else grid_aux_row(lh + 2 * t, T, ga);
+            const double u = (ga[0] + ed * ga[1]) * wn;   // pnc = exp(-lam T)
+            const double q1 = (ga[2] + ed * ga[3]) * wn;  // 1 - pnc, free of cancellation
+            const double z = -log(u);
+            const double lam = z * ga[4];
+            lc[(pitch * t) * stride] = lam;
+            lc[(pitch * t + 1) * stride] = lam;
+            const double il = z > 0 ? T / z : 0.0;  // 1 / lam
+            const double e3 = e1 * e1 * e1;
+            const double q3 = q1 * (1.0 + u + u * u), q6 = q3 * (1.0 + u * u * u);  // 1 - u^3, 1 - u^6
+            c1 += z > 0 ? e1 * q1 * il : e1 * T;
+            c3 += z > 0 ? e3 * q3 * (il * (1.0 / 3.0)) : e3 * T;
+            c6 += z > 0 ? (e3 * e3) * q6 * (il * (1.0 / 6.0)) : (e3 * e3) * T;
+            e1 *= u;
         }
-        lc[(pitch * t) * stride] = lam;
-        lc[(pitch * t + 1) * stride] = lam;
-        nc0 += -T * lam;
-        nc1 += -T * lam;
-    }
-    {
-        const int t = numT - 1;
-        const double pr0 = exp(nc0), pr1 = exp(nc1);
-        const double lam = (pr0 + pr1) / (pr0 / lh[2 * t] + pr1 / lh[2 * t + 1]);
-        lc[(pitch * t) * stride] = lam;
-        lc[(pitch * t + 1) * stride] = lam;
+        {
+            const int t = numT - 1;
+            const double lam = (1.0 + ed) / (1.0 / lh[2 * t] + ed / lh[2 * t + 1]);
+            lc[(pitch * t) * stride] = lam;
+            lc[(pitch * t + 1) * stride] = lam;
+            const double il = 1.0 / lam, e3 = e1 * e1 * e1;
+            c1 += e1 * il; c3 += e3 * (il * (1.0 / 3.0)); c6 += (e3 * e3) * (il * (1.0 / 6.0));
+        }
+        if (cpost) {
+            cpost[0] = c6; cpost[1] = c3; cpost[2] = c1;
+            if (cpost_done) *cpost_done = true;
+        }
+    } else {
+        for (int t = splitT; t < numT - 1; ++t) {
+            const double T = times[t];
+            if (T == 0) { lc[(pitch * t) * stride] = 1; lc[(pitch * t + 1) * stride] = 1; continue; }
+            double lam;
+            if (!fit_single_pop(lh + 2 * t, T, nc0, nc1, &lam, &nfev)) { *nfev_out = nfev; return MISTI_NONFINITE; }
+            lc[(pitch * t) * stride] = lam;
+            lc[(pitch * t + 1) * stride] = lam;
+            nc0 += -T * lam;
+            nc1 += -T * lam;
+        }
+        {
+            const int t = numT - 1;
+            const double pr0 = exp(nc0), pr1 = exp(nc1);
+            const double lam = (pr0 + pr1) / (pr0 / lh[2 * t] + pr1 / lh[2 * t + 1]);
+            lc[(pitch * t) * stride] = lam;
+            lc[(pitch * t + 1) * stride] = lam;
+        }
     }
     if (flags & MISTI_FLAG_SMOOTH) {  // SmoothConst for both genomes (:380-405)
         for (int g = 0; g < 2; ++g) {
