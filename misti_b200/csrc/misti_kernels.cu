@@ -103,7 +103,7 @@ misti_jsfs_kernel(int B, int P, const double* __restrict__ params, const int* __
                   double* __restrict__ llh, double* __restrict__ jafs, double* __restrict__ jafs_raw, int* __restrict__ status,
                   int* __restrict__ terms, const int* __restrict__ row_ids, misti::Cont* __restrict__ conts,
                   const int* __restrict__ item_list, const int* __restrict__ item_count, int* __restrict__ next_list,
-                  int* __restrict__ next_count) {
+                  int* __restrict__ next_count, int* __restrict__ work_counter) {
     // one item per 16-lane half warp (3 of the 44 chain states per lane), two items per warp
     __shared__ double ysm_all[kJsfsWarps * 2][misti::kGroupScratch];
     __shared__ misti::RunEnt runtab[MISTI_NM_NNZ];
@@ -114,12 +114,17 @@ misti_jsfs_kernel(int B, int P, const double* __restrict__ params, const int* __
     const misti::HalfWarpLanes g;
     misti::LaneCtx<misti::HalfWarpLanes> L;
     L.init(g, ysm, runtab);
-    const int ngroups = gridDim.x * kJsfsWarps * 2;
     // first pass: all B items; resume pass: the items parked by the previous pass and advanced by misti_stiff_kernel
     const bool resume = item_list != nullptr;
     const int n_items = resume ? *item_count : B;
-    // both halves of a warp walk the item list together (lock step); the odd one out re-reads the last item
-    for (int i0 = blockIdx.x * kJsfsWarps * 2 + (half & ~1); i0 < n_items; i0 += ngroups) {
+    // The grid is persistent (as many blocks as fit on the device); every warp draws the next PAIR of items from a
+    // counter, so the load balances itself although items differ in cost.  The two halves of a warp work on items
+    // 2j and 2j + 1 in lock step; the odd one out re-reads the last item.
+    while (true) {
+        int i0 = 0;
+        if ((threadIdx.x & 31) == 0) i0 = atomicAdd(work_counter, 2);
+        i0 = __shfl_sync(0xffffffffu, i0, 0);
+        if (i0 >= n_items) break;
         const bool has = i0 + (half & 1) < n_items;
         const int i = has ? i0 + (half & 1) : n_items - 1;
         const int b = resume ? item_list[i] : i;
@@ -814,24 +819,26 @@ static int eval_chunk(misti_ctx* ctx, int B, int P, const double* d_params, cons
     CK(cudaGetLastError());
     CK(cudaEventRecord(ctx->ev[1], ctx->stream));
     int blocks = (B + 2 * kJsfsWarps - 1) / (2 * kJsfsWarps);
-    const int max_blocks = ctx->sm_count * 16;
+    const int per_sm = (ctx->jsfs_minb >= 2 && ctx->jsfs_minb <= 5 && ctx->jsfs_minb != 4) ? ctx->jsfs_minb
+                       : (ctx->jsfs_minb == 4 ? 4 : kJsfsMinBlocks);
+    const int max_blocks = ctx->sm_count * per_sm;  // persistent grid: exactly the blocks that are resident together
     if (blocks > max_blocks) blocks = max_blocks;
     CK(cudaMemsetAsync(ctx->d_counts, 0, 8 * sizeof(int), ctx->stream));
-#define MISTI_LAUNCH_JSFS(MINB, GRID, LIST, COUNT, NEXT, NEXTCOUNT)                                                       \
+#define MISTI_LAUNCH_JSFS(MINB, GRID, LIST, COUNT, NEXT, NEXTCOUNT, WORK)                                                       \
     misti_jsfs_kernel<MINB><<<GRID, kJsfsWarps * 32, 0, ctx->stream>>>(                                                   \
         B, P, d_params, d_model_ids, model_default, ctx->d_models, ctx->d_rec, ctx->cap_seg, ctx->d_nseg, stride, ctx->d_cpost, \
         ctx->d_data, \
         ctx->R, ctx->unfolded, d_llh, d_jafs, d_jafs_raw, ctx->d_status, d_terms, d_row_ids, ctx->d_conts, LIST, COUNT, NEXT, \
-        NEXTCOUNT)
-#define MISTI_LAUNCH_JSFS_ANY(GRID, LIST, COUNT, NEXT, NEXTCOUNT)                                                          \
+        NEXTCOUNT, WORK)
+#define MISTI_LAUNCH_JSFS_ANY(GRID, LIST, COUNT, NEXT, NEXTCOUNT, WORK)                                                          \
     switch (ctx->jsfs_minb) { /* register budget: 2 -> 255, 3 -> 168, 4 -> 128, 5 -> 96 (tuning knob MISTI_JSFS_MINB) */   \
-        case 2: MISTI_LAUNCH_JSFS(2, GRID, LIST, COUNT, NEXT, NEXTCOUNT); break;                                           \
-        case 3: MISTI_LAUNCH_JSFS(3, GRID, LIST, COUNT, NEXT, NEXTCOUNT); break;                                           \
-        case 5: MISTI_LAUNCH_JSFS(5, GRID, LIST, COUNT, NEXT, NEXTCOUNT); break;                                           \
-        default: MISTI_LAUNCH_JSFS(kJsfsMinBlocks, GRID, LIST, COUNT, NEXT, NEXTCOUNT); break;                             \
+        case 2: MISTI_LAUNCH_JSFS(2, GRID, LIST, COUNT, NEXT, NEXTCOUNT, WORK); break;                                           \
+        case 3: MISTI_LAUNCH_JSFS(3, GRID, LIST, COUNT, NEXT, NEXTCOUNT, WORK); break;                                           \
+        case 5: MISTI_LAUNCH_JSFS(5, GRID, LIST, COUNT, NEXT, NEXTCOUNT, WORK); break;                                           \
+        default: MISTI_LAUNCH_JSFS(kJsfsMinBlocks, GRID, LIST, COUNT, NEXT, NEXTCOUNT, WORK); break;                             \
     }
     // pass 0: every item; items that meet a stiff interval are parked in queue 0
-    MISTI_LAUNCH_JSFS_ANY(blocks, (const int*)nullptr, (const int*)nullptr, ctx->d_queue[0], ctx->d_counts);
+    MISTI_LAUNCH_JSFS_ANY(blocks, (const int*)nullptr, (const int*)nullptr, ctx->d_queue[0], ctx->d_counts, ctx->d_counts + 4);
     CK(cudaGetLastError());
     ctx->launches += 1;
     // stiff rounds: dense scaling-and-squaring step for the parked items, then resume the sweep for them.  The grids
@@ -842,7 +849,7 @@ static int eval_chunk(misti_ctx* ctx, int B, int P, const double* d_params, cons
             ctx->d_nseg, ctx->d_conts, ctx->d_queue[r & 1], ctx->d_counts + r, ctx->d_status);
         CK(cudaGetLastError());
         MISTI_LAUNCH_JSFS_ANY(ctx->sm_count * 2, (const int*)ctx->d_queue[r & 1], (const int*)(ctx->d_counts + r),
-                              ctx->d_queue[(r + 1) & 1], ctx->d_counts + r + 1);
+                              ctx->d_queue[(r + 1) & 1], ctx->d_counts + r + 1, ctx->d_counts + 5 + r);
         CK(cudaGetLastError());
         ctx->launches += 2;
     }
