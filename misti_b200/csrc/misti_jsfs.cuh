@@ -267,7 +267,9 @@ struct SingleLane {  // test-only host build: one lane owns all 44 rows, every o
         MISTI_HD double get(int i) const { return p[i]; }
     };
     MISTI_D static int rw(int) { return 4; }
+    static constexpr int RUNTAB = MISTI_NM_NNZ;  // entries of the run table as this group lays it out
     MISTI_D int row_of(int s) const { return s; }
+    MISTI_D static int row_of_lane(int, int s) { return s; }
     MISTI_D static int pos_of(int row) { return row; }
     MISTI_D void rem_of(int s, int e, int* col, unsigned* code) const {
         const EllEntry en = MISTI_TAB(ell)[s][e];
@@ -308,7 +310,9 @@ struct HalfWarpLanes {  // two items per warp; each lane of a 16-lane half owns 
         __device__ double get(int i) const { return __shfl_sync(0xffffffffu, v, i, 16); }
     };
     __device__ static int rw(int s) { return s == 1 ? 2 : 3; }
+    static constexpr int RUNTAB = MISTI_L16_RUNLEN * 16;
     __device__ int row_of(int s) const { return d_l16_row[threadIdx.x & 15][s]; }
+    __device__ static int row_of_lane(int lane, int s) { return d_l16_row[lane][s]; }
     __device__ static int pos_of(int row) { return d_l16_pos[row]; }  // shared-memory word of a state: 16 * slot + lane
     __device__ void rem_of(int s, int e, int* col, unsigned* code) const {
         *col = d_l16_rem[threadIdx.x & 15][s][e][0];
@@ -382,20 +386,28 @@ MISTI_HD inline void post_split_coeffs(const ModelDesc& md, const double* times,
     cpost[0] = c6; cpost[1] = c3; cpost[2] = c1;
 }
 
-// Entry of the zero-migration run table as the lane groups use it: G_ab[row][col] with the shared-memory word of
-// `col` and the slots of c_ab / e_ab in the staged record (e_0 = 1 sits behind the record, slot 16).
-struct RunEnt {
-    double val;
-    int ypos;
-    int ce;  // low half: slot of c_ab, high half: slot of e_ab
-};
+// The zero-migration run table as the lane groups use it: the entries G_ab[row][col] of the rows of lane l, in slot
+// order, sit at index (k * LANES + l), k = 0, 1, ... -- lane-interleaved, so that the lanes of a group walking their
+// own lists read consecutive words (no bank conflicts).  val = G_ab[row][col]; meta = shared-memory word of `col`
+// (bits 0-7), slot of c_ab (bits 8-15) and slot of e_ab (bits 16-23) in the staged record (e_0 = 1 sits behind the
+// record, slot 16).
 template <class G>
-MISTI_D inline void fill_run_entry(int e, RunEnt* out) {
-    const int ab = MISTI_TAB(nm_ab)[e];
-    out->val = MISTI_TAB(nm_val)[e];
-    out->ypos = G::pos_of(MISTI_TAB(nm_col)[e]);
-    out->ce = ab | ((ab == 0 ? kRecSlots : 7 + ab) << 16);
-}
+struct RunTable {
+    double val[G::RUNTAB];
+    unsigned meta[G::RUNTAB];
+    MISTI_D void fill_lane(int lane) {  // the part of one lane
+        int k = 0;
+        for (int s = 0; s < G::RPL; ++s) {
+            const int r = G::row_of_lane(lane, s);
+            if (r >= 44) continue;
+            for (int e = MISTI_TAB(nm_rowptr)[r]; e < MISTI_TAB(nm_rowptr)[r + 1]; ++e, ++k) {
+                const unsigned ab = MISTI_TAB(nm_ab)[e];
+                val[k * G::LANES + lane] = MISTI_TAB(nm_val)[e];
+                meta[k * G::LANES + lane] = (unsigned)G::pos_of(MISTI_TAB(nm_col)[e]) | (ab << 8) | ((ab == 0 ? (unsigned)kRecSlots : 7u + ab) << 16);
+            }
+        }
+    }
+};
 
 // What a lane knows about its rows, independent of the item: built once per thread.
 template <class G>
@@ -405,15 +417,16 @@ struct LaneCtx {
     unsigned rc[RPL];    // coefficient-table codes (kind + 4 log2(count), 12 = none): remote entry e at bit 4e, local entry j at bit 16+4j
     unsigned rk[RPL];    // diagonal multiplicity of rate kind k at bit 3k; StateToJAF count of category c at bit 12+2c;
                          // collapse block at bit 26; ancient-reset masks at bits 29, 30; valid at bit 31
-    unsigned run[RPL];   // entries [lo, hi) of the zero-migration run table: lo | hi << 8
+    unsigned run[RPL];   // this row's part of the lane's run-table list: first entry | number of entries << 16
     const double* yp[RPL][RW];  // where this lane reads y[col] of each remote entry (buffer 0; buffer 1 is +kYStride)
     double* wp[RPL];            // where it writes y[row]
     double* scratch;            // the group's scratch area (kGroupScratch doubles)
-    const RunEnt* runtab;
+    const RunTable<G>* runtab;
 
-    MISTI_D void init(const G& g, double* ysm, const RunEnt* rt) {
+    MISTI_D void init(const G& g, double* ysm, const RunTable<G>* rt) {
         scratch = ysm;
         runtab = rt;
+        unsigned run_base = 0;
 #pragma unroll
         for (int s = 0; s < RPL; ++s) {
             row[s] = g.row_of(s);
@@ -438,7 +451,9 @@ struct LaneCtx {
                 rk[s] |= (unsigned)MISTI_TAB(anc2)[r] << 29;
                 rk[s] |= (unsigned)MISTI_TAB(anc11)[r] << 30;
                 rk[s] |= 1u << 31;
-                run[s] = (unsigned)MISTI_TAB(nm_rowptr)[r] | ((unsigned)MISTI_TAB(nm_rowptr)[r + 1] << 8);
+                const unsigned n = (unsigned)MISTI_TAB(nm_rowptr)[r + 1] - (unsigned)MISTI_TAB(nm_rowptr)[r];
+                run[s] = run_base | (n << 16);
+                run_base += n;
             }
         }
     }
@@ -661,12 +676,13 @@ MISTI_D inline int jsfs_item(const G& g, const LaneCtx<G>& L, const ModelDesc& m
             for (int s = 0; s < RPL; ++s)
                 if (L.rk[s] >> 31) {
                     double pe = 0.0, ir = 0.0;
-                    const int hi = (int)(L.run[s] >> 8);
-                    for (int e = (int)(L.run[s] & 255u); e < hi; ++e) {
-                        const RunEnt en = L.runtab[e];
-                        const double t = en.val * ysm[en.ypos];
-                        ir = fma(cc[en.ce & 0xffff], t, ir);
-                        pe = fma(cc[en.ce >> 16], t, pe);
+                    const int n = (int)(L.run[s] >> 16);
+                    int idx = (int)(L.run[s] & 0xffffu) * G::LANES + lane;
+                    for (int i = 0; i < n; ++i, idx += G::LANES) {
+                        const unsigned m = L.runtab->meta[idx];
+                        const double t = L.runtab->val[idx] * ysm[m & 255u];
+                        ir = fma(cc[(m >> 8) & 255u], t, ir);
+                        pe = fma(cc[m >> 16], t, pe);
                     }
                     P[s] = pe;
                     if (pre) Ia[s] += ir;

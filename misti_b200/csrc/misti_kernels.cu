@@ -106,14 +106,14 @@ misti_jsfs_kernel(int B, int P, const double* __restrict__ params, const int* __
                   int* __restrict__ next_count, int* __restrict__ work_counter) {
     // one item per 16-lane half warp (3 of the 44 chain states per lane), two items per warp
     __shared__ double ysm_all[kJsfsWarps * 2][misti::kGroupScratch];
-    __shared__ misti::RunEnt runtab[MISTI_NM_NNZ];
-    for (int e = threadIdx.x; e < MISTI_NM_NNZ; e += blockDim.x) misti::fill_run_entry<misti::HalfWarpLanes>(e, &runtab[e]);
+    __shared__ misti::RunTable<misti::HalfWarpLanes> runtab;
+    if (threadIdx.x < 16) runtab.fill_lane(threadIdx.x);
     __syncthreads();
     const int half = threadIdx.x >> 4, lane = threadIdx.x & 15;
     double* ysm = ysm_all[half];
     const misti::HalfWarpLanes g;
     misti::LaneCtx<misti::HalfWarpLanes> L;
-    L.init(g, ysm, runtab);
+    L.init(g, ysm, &runtab);
     // first pass: all B items; resume pass: the items parked by the previous pass and advanced by misti_stiff_kernel
     const bool resume = item_list != nullptr;
     const int n_items = resume ? *item_count : B;

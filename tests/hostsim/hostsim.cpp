@@ -74,10 +74,10 @@ int hs_jsfs(int numT, int splitT, int sampleDate, const double* times, int n_ban
         hs_last_nseg = nseg;
     }
     misti::SingleLane g;
-    static misti::RunEnt runtab[MISTI_NM_NNZ];
-    for (int e = 0; e < MISTI_NM_NNZ; ++e) misti::fill_run_entry<misti::SingleLane>(e, &runtab[e]);
+    static misti::RunTable<misti::SingleLane> runtab;
+    runtab.fill_lane(0);
     misti::LaneCtx<misti::SingleLane> L;
-    L.init(g, ysm, runtab);
+    L.init(g, ysm, &runtab);
     st = misti::jsfs_item<misti::SingleLane>(g, L, md, true, params, rec.data(), nseg, cpost, raw, terms);
     if (st != MISTI_OK) return st;
     double jn0;

@@ -339,6 +339,9 @@ def main():
     o.append("#define MISTI_QDIAG_INIT { %s }" % ", ".join("{%d,%d,%d,%d}" % t for t in qdiag))
     o.append("// zero-migration runs: non-zero entries of the spectral projector products G0_a G1_b, row-major;")
     o.append("// ab index -> (a, b): 0 (0,0), 1 (1,0), 2 (3,0), 3 (6,0), 4 (0,1), 5 (0,3), 6 (0,6), 7 (1,1)")
+    runlen = max(sum(nm_rowptr[r + 1] - nm_rowptr[r] for r in rows if r < 44) for rows in l16_row)
+    o.append("// longest per-lane list of run-table entries in the 16-lane layout")
+    o.append("#define MISTI_L16_RUNLEN %d" % runlen)
     o.append("#define MISTI_NM_NNZ %d" % len(nm))
     o.append("#define MISTI_NM_ROWPTR_INIT { %s }" % ",".join(str(v) for v in nm_rowptr))
     o.append("#define MISTI_NM_COL_INIT { %s }" % ",".join(str(e[1]) for e in nm))
