@@ -339,6 +339,32 @@ def main():
     o.append("#define MISTI_QDIAG_INIT { %s }" % ", ".join("{%d,%d,%d,%d}" % t for t in qdiag))
     o.append("// zero-migration runs: non-zero entries of the spectral projector products G0_a G1_b, row-major;")
     o.append("// ab index -> (a, b): 0 (0,0), 1 (1,0), 2 (3,0), 3 (6,0), 4 (0,1), 5 (0,3), 6 (0,6), 7 (1,1)")
+    # order of the entries inside a row: free (it only fixes the order of a sum); chosen so that the 16 lanes of a group,
+    # each walking the list of its own row in step, gather y[col] with few bank conflicts in the 16-lane layout
+    by_row = [nm[nm_rowptr[r]:nm_rowptr[r + 1]] for r in range(44)]
+
+    def gather_cost(rows_entries):
+        tot = 0
+        for sl in range(3):
+            lists = [rows_entries[l16_row[ln][sl]] if l16_row[ln][sl] < 44 else [] for ln in range(16)]
+            for i in range(max(len(x) for x in lists)):
+                tot += wavefronts([l16_pos[x[i][1]] for x in lists if len(x) > i])
+        return tot
+    cost0 = gather_cost(by_row)
+    bestc = cost0
+    for _ in range(40000):
+        r = rnd.randrange(44)
+        if len(by_row[r]) < 2:
+            continue
+        i, j = rnd.sample(range(len(by_row[r])), 2)
+        by_row[r][i], by_row[r][j] = by_row[r][j], by_row[r][i]
+        c = gather_cost(by_row)
+        if c <= bestc:
+            bestc = c
+        else:
+            by_row[r][i], by_row[r][j] = by_row[r][j], by_row[r][i]
+    nm = [e for r in range(44) for e in by_row[r]]
+    print("run-table gather wavefronts per group: %d -> %d" % (cost0, bestc))
     runlen = max(sum(nm_rowptr[r + 1] - nm_rowptr[r] for r in rows if r < 44) for rows in l16_row)
     o.append("// longest per-lane list of run-table entries in the 16-lane layout")
     o.append("#define MISTI_L16_RUNLEN %d" % runlen)
