@@ -55,7 +55,9 @@ struct PulseEntry { unsigned char row, col, a, b, mult; };
     SPEC unsigned char PFX##nm_rowptr[45] = MISTI_NM_ROWPTR_INIT;               \
     SPEC unsigned char PFX##nm_col[MISTI_NM_NNZ] = MISTI_NM_COL_INIT;           \
     SPEC unsigned char PFX##nm_ab[MISTI_NM_NNZ] = MISTI_NM_AB_INIT;             \
-    SPEC double PFX##nm_val[MISTI_NM_NNZ] = MISTI_NM_VAL_INIT;
+    SPEC double PFX##nm_val[MISTI_NM_NNZ] = MISTI_NM_VAL_INIT;                  \
+    SPEC double PFX##r16_val[16 * MISTI_R16_LEN] = MISTI_R16_VAL_INIT;          \
+    SPEC unsigned PFX##r16_meta[16 * MISTI_R16_LEN] = MISTI_R16_META_INIT;
 
 // Under nvcc the table users are device-only functions reading __device__ copies; the test-only
 // host build (g++) reads plain static copies.
@@ -87,7 +89,8 @@ static const RecipTable h_recip = RecipTable();
 #endif
 
 constexpr int kYStride = 48;                    // doubles per ping-pong buffer (44 states + pad rows)
-constexpr int kGroupScratch = 128;              // doubles of scratch per lane group: two ping-pong buffers + 32
+constexpr int kGroupScratch = 168;              // doubles of scratch per lane group: two ping-pong buffers + 72
+constexpr int kRunOutP = 65, kRunOutI = 113;    // zero-migration run: where row results are parked (behind the staged record)
 constexpr double kUnifMaxStep = 32.0;           // largest q*T handled in one uniformisation sweep
 constexpr double kUnifTol = 8.881784197001252e-16;   // 2^-50: truncation of the Poisson tail (relative to the mass)
 constexpr double kUnifMaxStiff = 256.0;         // q*T beyond this (8 sweeps) goes to the dense scaling-and-squaring step
@@ -267,9 +270,8 @@ struct SingleLane {  // test-only host build: one lane owns all 44 rows, every o
         MISTI_HD double get(int i) const { return p[i]; }
     };
     MISTI_D static int rw(int) { return 4; }
-    static constexpr int RUNTAB = MISTI_NM_NNZ;  // entries of the run table as this group lays it out
+    static constexpr int RUNLEN = MISTI_NM_NNZ;  // entries of the run table per lane
     MISTI_D int row_of(int s) const { return s; }
-    MISTI_D static int row_of_lane(int, int s) { return s; }
     MISTI_D static int pos_of(int row) { return row; }
     MISTI_D void rem_of(int s, int e, int* col, unsigned* code) const {
         const EllEntry en = MISTI_TAB(ell)[s][e];
@@ -310,9 +312,8 @@ struct HalfWarpLanes {  // two items per warp; each lane of a 16-lane half owns 
         __device__ double get(int i) const { return __shfl_sync(0xffffffffu, v, i, 16); }
     };
     __device__ static int rw(int s) { return s == 1 ? 2 : 3; }
-    static constexpr int RUNTAB = MISTI_L16_RUNLEN * 16;
+    static constexpr int RUNLEN = MISTI_R16_LEN;
     __device__ int row_of(int s) const { return d_l16_row[threadIdx.x & 15][s]; }
-    __device__ static int row_of_lane(int lane, int s) { return d_l16_row[lane][s]; }
     __device__ static int pos_of(int row) { return d_l16_pos[row]; }  // shared-memory word of a state: 16 * slot + lane
     __device__ void rem_of(int s, int e, int* col, unsigned* code) const {
         *col = d_l16_rem[threadIdx.x & 15][s][e][0];
@@ -386,25 +387,28 @@ MISTI_HD inline void post_split_coeffs(const ModelDesc& md, const double* times,
     cpost[0] = c6; cpost[1] = c3; cpost[2] = c1;
 }
 
-// The zero-migration run table as the lane groups use it: the entries G_ab[row][col] of the rows of lane l, in slot
-// order, sit at index (k * LANES + l), k = 0, 1, ... -- lane-interleaved, so that the lanes of a group walking their
-// own lists read consecutive words (no bank conflicts).  val = G_ab[row][col]; meta = shared-memory word of `col`
-// (bits 0-7), slot of c_ab (bits 8-15) and slot of e_ab (bits 16-23) in the staged record (e_0 = 1 sits behind the
-// record, slot 16).
+// The zero-migration run table as the lane groups use it.  Any lane may compute any row (inputs and outputs go through
+// shared memory), so the 188 entries G_ab[row][col] are dealt into LANES lists of equal length, row by row; the lanes
+// walk their lists in lock step, entry k of lane l at index k * LANES + l (consecutive words: no bank conflicts).
+// meta = shared-memory word of `col` | slot of c_ab << 8 | slot of e_ab << 16 in the staged record (e_0 = 1 sits behind
+// the record, slot 16) | "last entry of its row" << 24 | shared-memory word of the row << 25.  For 16 lanes the table is
+// generated (tools/gen_tables.py: balanced lists, order chosen for few gather conflicts); a single lane takes the rows
+// in their natural order.
 template <class G>
 struct RunTable {
-    double val[G::RUNTAB];
-    unsigned meta[G::RUNTAB];
-    MISTI_D void fill_lane(int lane) {  // the part of one lane
-        int k = 0;
-        for (int s = 0; s < G::RPL; ++s) {
-            const int r = G::row_of_lane(lane, s);
-            if (r >= 44) continue;
-            for (int e = MISTI_TAB(nm_rowptr)[r]; e < MISTI_TAB(nm_rowptr)[r + 1]; ++e, ++k) {
-                const unsigned ab = MISTI_TAB(nm_ab)[e];
-                val[k * G::LANES + lane] = MISTI_TAB(nm_val)[e];
-                meta[k * G::LANES + lane] = (unsigned)G::pos_of(MISTI_TAB(nm_col)[e]) | (ab << 8) | ((ab == 0 ? (unsigned)kRecSlots : 7u + ab) << 16);
-            }
+    double val[G::RUNLEN * G::LANES];
+    unsigned meta[G::RUNLEN * G::LANES];
+    MISTI_D void fill(int tid, int nthreads) {
+        if (G::LANES == 16) {
+            for (int i = tid; i < G::RUNLEN * G::LANES; i += nthreads) { val[i] = MISTI_TAB(r16_val)[i]; meta[i] = MISTI_TAB(r16_meta)[i]; }
+        } else {
+            for (int r = tid; r < 44; r += nthreads)
+                for (int e = MISTI_TAB(nm_rowptr)[r]; e < MISTI_TAB(nm_rowptr)[r + 1]; ++e) {
+                    const unsigned ab = MISTI_TAB(nm_ab)[e], last = e + 1 == MISTI_TAB(nm_rowptr)[r + 1];
+                    val[e] = MISTI_TAB(nm_val)[e];
+                    meta[e] = (unsigned)MISTI_TAB(nm_col)[e] | (ab << 8) | ((ab == 0 ? (unsigned)kRecSlots : 7u + ab) << 16) | (last << 24) |
+                              ((unsigned)r << 25);
+                }
         }
     }
 };
@@ -417,7 +421,6 @@ struct LaneCtx {
     unsigned rc[RPL];    // coefficient-table codes (kind + 4 log2(count), 12 = none): remote entry e at bit 4e, local entry j at bit 16+4j
     unsigned rk[RPL];    // diagonal multiplicity of rate kind k at bit 3k; StateToJAF count of category c at bit 12+2c;
                          // collapse block at bit 26; ancient-reset masks at bits 29, 30; valid at bit 31
-    unsigned run[RPL];   // this row's part of the lane's run-table list: first entry | number of entries << 16
     const double* yp[RPL][RW];  // where this lane reads y[col] of each remote entry (buffer 0; buffer 1 is +kYStride)
     double* wp[RPL];            // where it writes y[row]
     double* scratch;            // the group's scratch area (kGroupScratch doubles)
@@ -426,13 +429,12 @@ struct LaneCtx {
     MISTI_D void init(const G& g, double* ysm, const RunTable<G>* rt) {
         scratch = ysm;
         runtab = rt;
-        unsigned run_base = 0;
 #pragma unroll
         for (int s = 0; s < RPL; ++s) {
             row[s] = g.row_of(s);
             const bool valid = row[s] < 44;
             wp[s] = ysm + G::pos_of(row[s]);
-            rc[s] = 0; rk[s] = 0; run[s] = 0;
+            rc[s] = 0; rk[s] = 0;
 #pragma unroll
             for (int e = 0; e < RW; ++e) {
                 int col = row[s];
@@ -451,9 +453,6 @@ struct LaneCtx {
                 rk[s] |= (unsigned)MISTI_TAB(anc2)[r] << 29;
                 rk[s] |= (unsigned)MISTI_TAB(anc11)[r] << 30;
                 rk[s] |= 1u << 31;
-                const unsigned n = (unsigned)MISTI_TAB(nm_rowptr)[r + 1] - (unsigned)MISTI_TAB(nm_rowptr)[r];
-                run[s] = run_base | (n << 16);
-                run_base += n;
             }
         }
     }
@@ -669,24 +668,31 @@ MISTI_D inline int jsfs_item(const G& g, const LaneCtx<G>& L, const ModelDesc& m
         for (int s = 0; s < RPL; ++s) L.wp[s][0] = P[s];
         g.rec_store(rv, ysm + kYStride);
         g.sync();
-        if (is) {
+        if (is) {  // this lane's share of the table; a row's sums are parked when its last entry has been added
             const double* cc = ysm + kYStride;
+            double pe = 0.0, ir = 0.0;
+#pragma unroll 4
+            for (int k = 0; k < G::RUNLEN; ++k) {
+                const unsigned m = L.runtab->meta[k * G::LANES + lane];
+                const double t = L.runtab->val[k * G::LANES + lane] * ysm[m & 255u];
+                ir = fma(cc[(m >> 8) & 255u], t, ir);
+                pe = fma(cc[(m >> 16) & 255u], t, pe);
+                if ((m >> 24) & 1u) {
+                    ysm[kRunOutP + (m >> 25)] = pe;
+                    ysm[kRunOutI + (m >> 25)] = ir;
+                    pe = 0.0; ir = 0.0;
+                }
+            }
+        }
+        g.sync();
+        if (is) {
             const bool pre = (meta & kSegPre) != 0;
 #pragma unroll
             for (int s = 0; s < RPL; ++s)
                 if (L.rk[s] >> 31) {
-                    double pe = 0.0, ir = 0.0;
-                    const int n = (int)(L.run[s] >> 16);
-                    int idx = (int)(L.run[s] & 0xffffu) * G::LANES + lane;
-                    for (int i = 0; i < n; ++i, idx += G::LANES) {
-                        const unsigned m = L.runtab->meta[idx];
-                        const double t = L.runtab->val[idx] * ysm[m & 255u];
-                        ir = fma(cc[(m >> 8) & 255u], t, ir);
-                        pe = fma(cc[m >> 16], t, pe);
-                    }
-                    P[s] = pe;
-                    if (pre) Ia[s] += ir;
-                    else Ib[s] += ir;
+                    P[s] = L.wp[s][kRunOutP];
+                    if (pre) Ia[s] += L.wp[s][kRunOutI];
+                    else Ib[s] += L.wp[s][kRunOutI];
                 }
             nterms += 1;
         }

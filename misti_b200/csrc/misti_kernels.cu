@@ -107,7 +107,7 @@ misti_jsfs_kernel(int B, int P, const double* __restrict__ params, const int* __
     // one item per 16-lane half warp (3 of the 44 chain states per lane), two items per warp
     __shared__ double ysm_all[kJsfsWarps * 2][misti::kGroupScratch];
     __shared__ misti::RunTable<misti::HalfWarpLanes> runtab;
-    if (threadIdx.x < 16) runtab.fill_lane(threadIdx.x);
+    runtab.fill(threadIdx.x, blockDim.x);
     __syncthreads();
     const int half = threadIdx.x >> 4, lane = threadIdx.x & 15;
     double* ysm = ysm_all[half];

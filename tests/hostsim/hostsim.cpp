@@ -75,7 +75,7 @@ int hs_jsfs(int numT, int splitT, int sampleDate, const double* times, int n_ban
     }
     misti::SingleLane g;
     static misti::RunTable<misti::SingleLane> runtab;
-    runtab.fill_lane(0);
+    runtab.fill(0, 1);
     misti::LaneCtx<misti::SingleLane> L;
     L.init(g, ysm, &runtab);
     st = misti::jsfs_item<misti::SingleLane>(g, L, md, true, params, rec.data(), nseg, cpost, raw, terms);

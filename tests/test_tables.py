@@ -180,3 +180,29 @@ def test_sixteen_lane_layout():
             assert sorted(got) == sorted(want), (ln, sl)
     codes = {c for ln in rem for sl in ln for (_x, c) in sl} | {c for ln in loc for sl in ln for c in sl}
     assert codes <= set(range(10)) | {12}  # the record's table slots 10, 11 are free for 1/q and lam
+
+
+def test_sixteen_lane_run_table():
+    """the balanced run table of the 16-lane layout holds exactly the projector entries, row by row"""
+    rp, col, ab, val = (_macro("MISTI_NM_%s_INIT" % n) for n in ("ROWPTR", "COL", "AB", "VAL"))
+    pos = _macro("MISTI_L16_POS_INIT")
+    n = _macro("MISTI_R16_LEN")
+    rv = _macro("MISTI_R16_VAL_INIT")
+    rm = [int(x) for x in re.search(r"#define MISTI_R16_META_INIT (.*)", HEADER).group(1).replace("u", "").strip("{} ").split(",")]
+    assert len(rv) == len(rm) == 16 * n
+    got = []
+    for ln in range(16):
+        open_row = None
+        for k in range(n):
+            m, v = rm[16 * k + ln], rv[16 * k + ln]
+            if v == 0.0 and m == 0:
+                assert open_row is None  # padding only after a completed row
+                continue
+            ypos, c, e, last, rpos = m & 255, (m >> 8) & 255, (m >> 16) & 255, (m >> 24) & 1, m >> 25
+            assert e == (16 if c == 0 else 7 + c)
+            assert open_row in (None, rpos)
+            open_row = None if last else rpos
+            got.append((pos.index(rpos), pos.index(ypos), c, v))
+        assert open_row is None
+    want = [(r, col[i], ab[i], val[i]) for r in range(44) for i in range(rp[r], rp[r + 1])]
+    assert sorted(got) == sorted(want)

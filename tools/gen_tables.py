@@ -339,35 +339,68 @@ def main():
     o.append("#define MISTI_QDIAG_INIT { %s }" % ", ".join("{%d,%d,%d,%d}" % t for t in qdiag))
     o.append("// zero-migration runs: non-zero entries of the spectral projector products G0_a G1_b, row-major;")
     o.append("// ab index -> (a, b): 0 (0,0), 1 (1,0), 2 (3,0), 3 (6,0), 4 (0,1), 5 (0,3), 6 (0,6), 7 (1,1)")
-    # order of the entries inside a row: free (it only fixes the order of a sum); chosen so that the 16 lanes of a group,
-    # each walking the list of its own row in step, gather y[col] with few bank conflicts in the 16-lane layout
+    # ---- the run table as the 16-lane groups use it.  Any lane may compute any row (inputs and outputs go through shared
+    # memory), so rows are packed into 16 lists of equal length (first fit decreasing); a list is walked in lock step by
+    # the 16 lanes, entry k of lane l at index 16 k + l.  meta = shared-memory word of the column | slot of c_ab << 8 |
+    # slot of e_ab << 16 (e_0 = 1 sits behind the record, slot 16) | "last entry of its row" << 24 | word of the row << 25.
+    # The order of the rows in a list and of the entries in a row is chosen for few bank conflicts of the y[col] gather.
     by_row = [nm[nm_rowptr[r]:nm_rowptr[r + 1]] for r in range(44)]
+    runlen = -(-len(nm) // 16)
+    while True:
+        bins = [[] for _ in range(16)]
+        ok = True
+        for r in sorted(range(44), key=lambda r: -len(by_row[r])):
+            fits = [bn for bn in bins if sum(len(by_row[x]) for x in bn) + len(by_row[r]) <= runlen]
+            if not fits:
+                ok = False
+                break
+            fits[0].append(r)
+        if ok:
+            break
+        runlen += 1
 
-    def gather_cost(rows_entries):
-        tot = 0
-        for sl in range(3):
-            lists = [rows_entries[l16_row[ln][sl]] if l16_row[ln][sl] < 44 else [] for ln in range(16)]
-            for i in range(max(len(x) for x in lists)):
-                tot += wavefronts([l16_pos[x[i][1]] for x in lists if len(x) > i])
-        return tot
-    cost0 = gather_cost(by_row)
+    def lane_list(bn):
+        return [(e, i == len(by_row[r]) - 1) for r in bn for i, e in enumerate(by_row[r])]
+
+    def gather_cost():
+        lists = [lane_list(bn) for bn in bins]
+        return sum(wavefronts([l16_pos[x[k][0][1]] for x in lists if len(x) > k]) for k in range(runlen))
+    cost0 = gather_cost()
     bestc = cost0
-    for _ in range(40000):
-        r = rnd.randrange(44)
-        if len(by_row[r]) < 2:
-            continue
-        i, j = rnd.sample(range(len(by_row[r])), 2)
-        by_row[r][i], by_row[r][j] = by_row[r][j], by_row[r][i]
-        c = gather_cost(by_row)
-        if c <= bestc:
-            bestc = c
-        else:
+    for _ in range(30000):
+        if rnd.random() < 0.5:
+            r = rnd.randrange(44)
+            if len(by_row[r]) < 2:
+                continue
+            i, j = rnd.sample(range(len(by_row[r])), 2)
             by_row[r][i], by_row[r][j] = by_row[r][j], by_row[r][i]
-    nm = [e for r in range(44) for e in by_row[r]]
-    print("run-table gather wavefronts per group: %d -> %d" % (cost0, bestc))
-    runlen = max(sum(nm_rowptr[r + 1] - nm_rowptr[r] for r in rows if r < 44) for rows in l16_row)
-    o.append("// longest per-lane list of run-table entries in the 16-lane layout")
-    o.append("#define MISTI_L16_RUNLEN %d" % runlen)
+            c = gather_cost()
+            if c <= bestc:
+                bestc = c
+            else:
+                by_row[r][i], by_row[r][j] = by_row[r][j], by_row[r][i]
+        else:
+            bn = bins[rnd.randrange(16)]
+            if len(bn) < 2:
+                continue
+            i, j = rnd.sample(range(len(bn)), 2)
+            bn[i], bn[j] = bn[j], bn[i]
+            c = gather_cost()
+            if c <= bestc:
+                bestc = c
+            else:
+                bn[i], bn[j] = bn[j], bn[i]
+    print("run table: %d entries per lane, gather wavefronts per group %d -> %d (minimum %d)" % (runlen, cost0, bestc, runlen))
+    r16_val, r16_meta = [0.0] * (16 * runlen), [0] * (16 * runlen)
+    for ln, bn in enumerate(bins):
+        for k, (e, last) in enumerate(lane_list(bn)):
+            ab = e[2]
+            r16_val[16 * k + ln] = e[3]
+            r16_meta[16 * k + ln] = l16_pos[e[1]] | (ab << 8) | ((16 if ab == 0 else 7 + ab) << 16) | (int(last) << 24) | (l16_pos[e[0]] << 25)
+    o.append("// run table of the 16-lane layout: entry k of lane l at index 16 k + l (see tools/gen_tables.py)")
+    o.append("#define MISTI_R16_LEN %d" % runlen)
+    o.append("#define MISTI_R16_VAL_INIT { %s }" % ",".join(fmt(v) for v in r16_val))
+    o.append("#define MISTI_R16_META_INIT { %s }" % ",".join("%du" % v for v in r16_meta))
     o.append("#define MISTI_NM_NNZ %d" % len(nm))
     o.append("#define MISTI_NM_ROWPTR_INIT { %s }" % ",".join(str(v) for v in nm_rowptr))
     o.append("#define MISTI_NM_COL_INIT { %s }" % ",".join(str(e[1]) for e in nm))
