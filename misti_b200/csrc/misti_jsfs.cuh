@@ -126,7 +126,7 @@ MISTI_HD inline bool finite_nonneg(double v) { return v >= 0.0 && v <= DBL_MAX; 
 // lc[(pitch*t + g)*stride]; rec has room for min(splitT, numT) records.  Returns MISTI_OK, MISTI_NONFINITE or
 // MISTI_INFINITE_COAL_TIME (no split inside the grid and no migration in the last interval, :475-476).
 MISTI_D inline int build_segments_item(const ModelDesc& md, const double* times, const double* params, const double* lc,
-                                       int pitch, long stride, double* rec, int* nseg_out) {
+                                       int pitch, long stride, double* rec, int* nseg_out, const unsigned* cls = nullptr) {
     const int numT = md.numT;
     const int n2 = md.splitT < numT ? md.splitT : numT;
     const bool inf_last = md.splitT >= numT;
@@ -173,12 +173,14 @@ MISTI_D inline int build_segments_item(const ModelDesc& md, const double* times,
         if (last && !inf_last) break;
         const int t = last ? numT - 1 : it;
         const double la0 = lc[(pitch * t) * stride], la1 = lc[(pitch * t + 1) * stride];
-        const double m0 = band_rate(md, params, t, 0), m1 = band_rate(md, params, t, 1);
+        double mi_t[2], pu_t[2];
+        interval_rates(md, cls, params, t, mi_t, pu_t);
+        const double m0 = mi_t[0], m1 = mi_t[1];
         const double T = last ? 0.0 : times[t];
         if (!(finite_nonneg(la0) && finite_nonneg(la1) && finite_nonneg(m0) && finite_nonneg(m1) && finite_nonneg(T)))
             return MISTI_NONFINITE;
         const bool reset = t == md.sampleDate && t > 0;
-        const bool pulse = md.n_pulses > 0 && pulse_rate(md, params, t, 0) + pulse_rate(md, params, t, 1) > 0;
+        const bool pulse = pu_t[0] + pu_t[1] > 0;
         const bool mig = m0 + m1 != 0.0;
         if (open && (reset || pulse || mig || last)) close_run();
         const unsigned long long flags = (reset ? kSegReset : 0) | (pulse ? kSegPulse : 0) | (t < md.sampleDate ? kSegPre : 0) |

@@ -44,7 +44,7 @@ template <int MINB>
 __global__ void __launch_bounds__(kCorrectThreads, MINB)
 misti_correct_kernel(int B, int P, const double* __restrict__ params, const int* __restrict__ model_ids, int model_default,
                      const ModelDesc* __restrict__ models, const double* __restrict__ times, const double* __restrict__ lh,
-                     const double* __restrict__ gaux, unsigned flags, double mixtureTH, const double* __restrict__ lc_inject, int numT_max, double* lc,
+                     const double* __restrict__ gaux, const unsigned* __restrict__ cls_all, unsigned flags, double mixtureTH, const double* __restrict__ lc_inject, int numT_max, double* lc,
                      long stride, double* __restrict__ cpost, double* pr_out, int* __restrict__ status, int* __restrict__ nfev,
                      double* __restrict__ rec, int seg_cap, int* __restrict__ nseg) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -61,6 +61,7 @@ misti_correct_kernel(int B, int P, const double* __restrict__ params, const int*
     const double* tt = times + md.grid_off;
     const double* ll = lh + 2 * md.grid_off;
     const double* ga = gaux + misti::kGridAux * md.grid_off;
+    const unsigned* cls = cls_all + md.cls_off;
     const double* par = params + (long)b * P;
     double* lcb = lc + b;
     int st = MISTI_OK, nf = 0;
@@ -76,13 +77,13 @@ misti_correct_kernel(int B, int P, const double* __restrict__ params, const int*
         }
     } else {
         double* pr = pr_out ? pr_out + (long)b * (numT_max + 1) * 6 : nullptr;
-        st = misti::correct_lambdas_item(md, tt, ll, par, flags, mixtureTH, lcb, kPitch, stride, pr, &nf, ga, cp, &cp_done);
+        st = misti::correct_lambdas_item(md, tt, ll, par, flags, mixtureTH, lcb, kPitch, stride, pr, &nf, ga, cp, &cp_done, cls);
     }
     int ns = 0;
     if (st == MISTI_OK) {
         if (!cp_done) misti::post_split_coeffs(md, tt, lcb, kPitch, stride, cp);
         // all per-interval scalar work of the JSFS stage: the item's segment records
-        st = misti::build_segments_item(md, tt, par, lcb, kPitch, stride, rec + (long)b * seg_cap * misti::kRecSlots, &ns);
+        st = misti::build_segments_item(md, tt, par, lcb, kPitch, stride, rec + (long)b * seg_cap * misti::kRecSlots, &ns, cls);
     }
     nseg[b] = ns;
     cpost[b] = cp[0];
@@ -481,6 +482,9 @@ struct misti_ctx {
     bool grids_dirty = false;
     // models
     std::vector<ModelDesc> h_models;
+    std::vector<unsigned> h_cls;  // misti::interval_class of every interval of every model, pooled
+    unsigned* d_cls = nullptr;
+    size_t d_cls_cap = 0;
     ModelDesc* d_models = nullptr;
     size_t d_models_cap = 0;
     bool models_dirty = false;
@@ -581,6 +585,15 @@ int sync_tables(misti_ctx* ctx) {
             ctx->d_models_cap = ncap;
         }
         CK(cudaMemcpyAsync(ctx->d_models, ctx->h_models.data(), need * sizeof(ModelDesc), cudaMemcpyHostToDevice, ctx->stream));
+        if (ctx->h_cls.size() > ctx->d_cls_cap) {
+            size_t ncap = ctx->d_cls_cap ? ctx->d_cls_cap : 1024;
+            while (ncap < ctx->h_cls.size()) ncap *= 2;
+            if (ctx->d_cls) CK(cudaFree(ctx->d_cls));
+            ctx->d_cls = nullptr;
+            CK(cudaMalloc((void**)&ctx->d_cls, ncap * sizeof(unsigned)));
+            ctx->d_cls_cap = ncap;
+        }
+        CK(cudaMemcpyAsync(ctx->d_cls, ctx->h_cls.data(), ctx->h_cls.size() * sizeof(unsigned), cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
         ctx->models_dirty = false;
     }
@@ -661,7 +674,7 @@ void misti_ctx_destroy(misti_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    void* ptrs[] = {ctx->d_times, ctx->d_lh, ctx->d_gaux, ctx->d_models, ctx->d_data, ctx->d_lc, ctx->d_cpost, ctx->d_status, ctx->d_nfev, ctx->d_conts, ctx->d_queue[0], ctx->d_queue[1], ctx->d_counts,
+    void* ptrs[] = {ctx->d_times, ctx->d_lh, ctx->d_gaux, ctx->d_cls, ctx->d_models, ctx->d_data, ctx->d_lc, ctx->d_cpost, ctx->d_status, ctx->d_nfev, ctx->d_conts, ctx->d_queue[0], ctx->d_queue[1], ctx->d_counts,
                     ctx->d_rec, ctx->d_nseg, ctx->s_params, ctx->s_llh, ctx->s_jafs, ctx->s_jafs_raw, ctx->s_model_ids, ctx->s_terms, ctx->s_row_ids, ctx->s_lc_io,
                     ctx->s_pr, ctx->d_small};
     for (void* p : ptrs)
@@ -748,6 +761,8 @@ int misti_add_model(misti_ctx* ctx, const misti_model_desc* d, int32_t* model_id
         md.pulse_pop[b] = d->pulse_pop[b]; md.pulse_time[b] = d->pulse_time[b];
         md.pulse_opt[b] = d->pulse_opt[b] < 0 ? -1 : d->pulse_opt[b]; md.pulse_val[b] = d->pulse_val[b];
     }
+    md.cls_off = (int)ctx->h_cls.size();
+    for (int t = 0; t < numT; ++t) ctx->h_cls.push_back(misti::interval_class(md, t));
     ctx->h_models.push_back(md);
     ctx->models_dirty = true;
     *model_id = (int32_t)ctx->h_models.size() - 1;
@@ -758,7 +773,7 @@ int misti_clear_models(misti_ctx* ctx) {
     if (!ctx) return MISTI_E_ARG;
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
-    ctx->grid_numT.clear(); ctx->grid_off.clear(); ctx->h_times.clear(); ctx->h_lh.clear(); ctx->h_gaux.clear(); ctx->h_models.clear();
+    ctx->grid_numT.clear(); ctx->grid_off.clear(); ctx->h_times.clear(); ctx->h_lh.clear(); ctx->h_gaux.clear(); ctx->h_models.clear(); ctx->h_cls.clear();
     ctx->numT_max = 0;
     ctx->grids_dirty = ctx->models_dirty = false;
     return 0;
@@ -807,7 +822,7 @@ static int eval_chunk(misti_ctx* ctx, int B, int P, const double* d_params, cons
     CK(cudaEventRecord(ctx->ev[0], ctx->stream));
 #define MISTI_LAUNCH_CORRECT(MINB)                                                                                       \
     misti_correct_kernel<MINB><<<(B + kCorrectThreads - 1) / kCorrectThreads, kCorrectThreads, 0, ctx->stream>>>(          \
-        B, P, d_params, d_model_ids, model_default, ctx->d_models, ctx->d_times, ctx->d_lh, ctx->d_gaux, flags, mixture_th, \
+        B, P, d_params, d_model_ids, model_default, ctx->d_models, ctx->d_times, ctx->d_lh, ctx->d_gaux, ctx->d_cls, flags, mixture_th, \
         d_lc_inject, \
         numT_max, ctx->d_lc, stride, ctx->d_cpost, d_pr, ctx->d_status, ctx->d_nfev, ctx->d_rec, ctx->cap_seg, ctx->d_nseg)
     switch (ctx->correct_minb) {  // register budget per thread: 4 -> 255, 8 -> 128, 12 -> 80 (tuning knob MISTI_CORRECT_MINB)

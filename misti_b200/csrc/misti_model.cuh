@@ -18,7 +18,7 @@ struct ModelDesc {
     int n_pulses;
     int n_params;
     int grid_off;    // offset of this model's grid inside the pooled arrays (in intervals)
-    int pad_;
+    int cls_off;     // offset of this model's interval classes inside the pooled class array (see interval_class)
     int band_pop[MISTI_MAX_BANDS], band_start[MISTI_MAX_BANDS], band_end[MISTI_MAX_BANDS], band_opt[MISTI_MAX_BANDS];
     int pulse_pop[MISTI_MAX_PULSES], pulse_time[MISTI_MAX_PULSES], pulse_opt[MISTI_MAX_PULSES];
     double band_val[MISTI_MAX_BANDS];
@@ -42,6 +42,42 @@ MISTI_HD inline double pulse_rate(const ModelDesc& md, const double* params, int
     return v;
 }
 
+// Interval class of a model: which band feeds deme 0 / deme 1 and which pulse leaves deme 0 / deme 1 at interval t, as
+// four bytes (index + 1, 0 = none) -- the band / pulse loops above evaluated once per model on the host instead of
+// four times per interval and item on the device.
+MISTI_HD inline unsigned interval_class(const ModelDesc& md, int t) {
+    unsigned w = 0;
+    for (int b = 0; b < md.n_bands; ++b)
+        if (t >= md.band_start[b] && t < md.band_end[b]) {
+            const int sh = md.band_pop[b] == 0 ? 0 : 8;
+            w = (w & ~(255u << sh)) | ((unsigned)(b + 1) << sh);
+        }
+    for (int b = 0; b < md.n_pulses; ++b)
+        if (md.pulse_time[b] == t) {
+            const int sh = md.pulse_pop[b] == 0 ? 16 : 24;
+            w = (w & ~(255u << sh)) | ((unsigned)(b + 1) << sh);
+        }
+    return w;
+}
+
+// mi[t][0..1] and pu[t][0..1] of interval t; cls (nullable) = the model's interval classes
+MISTI_HD inline void interval_rates(const ModelDesc& md, const unsigned* cls, const double* params, int t, double* mi, double* pu) {
+    if (!cls) {
+        mi[0] = band_rate(md, params, t, 0); mi[1] = band_rate(md, params, t, 1);
+        pu[0] = pulse_rate(md, params, t, 0); pu[1] = pulse_rate(md, params, t, 1);
+        return;
+    }
+    const unsigned w = cls[t];
+    mi[0] = mi[1] = pu[0] = pu[1] = 0.0;
+    if (w == 0) return;
+    for (int k = 0; k < 2; ++k) {
+        const unsigned b = (w >> (8 * k)) & 255u;
+        if (b) mi[k] = md.band_opt[b - 1] >= 0 ? params[md.band_opt[b - 1]] : md.band_val[b - 1];
+        const unsigned q = (w >> (16 + 8 * k)) & 255u;
+        if (q) pu[k] = md.pulse_opt[q - 1] >= 0 ? params[md.pulse_opt[q - 1]] : md.pulse_val[q - 1];
+    }
+}
+
 // lc is addressed as lc[(pitch*t+g)*stride] (pitch >= 2 values per interval); times[numT-1]; lh[numT][2].
 // Pr (nullable): [splitT+1][3][2] trajectory of the 3-state chains (MigrationInference.py:309,350).
 // gaux (nullable): [numT][kGridAux] per-interval constants of the grid (grid_aux_row).
@@ -51,7 +87,7 @@ MISTI_HD inline double pulse_rate(const ModelDesc& md, const double* params, int
 MISTI_HD inline int correct_lambdas_item(const ModelDesc& md, const double* times, const double* lh, const double* params,
                                          unsigned flags, double mixtureTH, double* lc, int pitch, long stride, double* Pr,
                                          int* nfev_out, const double* gaux = nullptr, double* cpost = nullptr,
-                                         bool* cpost_done = nullptr) {
+                                         bool* cpost_done = nullptr, const unsigned* cls = nullptr) {
     if (cpost_done) *cpost_done = false;
     const bool correct = flags & MISTI_FLAG_CORRECT, cpfit = flags & MISTI_FLAG_CPFIT;
     int nfev = 0;
@@ -63,8 +99,16 @@ MISTI_HD inline int correct_lambdas_item(const ModelDesc& md, const double* time
     if (Pr) { Pr[0] = 1; Pr[1] = 0; Pr[2] = 0; Pr[3] = 1; Pr[4] = 0; Pr[5] = 0; }
     double nc0 = 0, nc1 = 0;
     const int numT = md.numT, splitT = md.splitT;
+    // SmoothConst (:380-405) as a streaming pass: per genome the current run of equal PSMC rates [sk, t), the rate that
+    // defines it, and the sums of lc T and T over it; a run is averaged and written back when it ends.
+    const bool smooth = (flags & MISTI_FLAG_SMOOTH) != 0;
+    int sk[2] = {0, 0};
+    bool sdone[2] = {!smooth, !smooth};
+    double slam[2] = {lh[0], lh[1]}, snc[2] = {0.0, 0.0}, stime[2] = {0.0, 0.0};
     for (int t = 0; t < splitT; ++t) {
-        const double pu0 = pulse_rate(md, params, t, 0), pu1 = pulse_rate(md, params, t, 1);
+        double mi_t[2], pu_t[2];
+        interval_rates(md, cls, params, t, mi_t, pu_t);
+        const double pu0 = pu_t[0], pu1 = pu_t[1];
         const double pu = pu0 + pu1;
         if (pu > 0) {  // closed-form pulse on the 3-state chains (:315-323)
             const int a = pu0 > 0 ? 0 : 1, b = 1 - a;
@@ -77,18 +121,34 @@ MISTI_HD inline int correct_lambdas_item(const ModelDesc& md, const double* time
                 p[a] = qa; p[b] = qb; p[2] = q2;
             }
         }
-        if (!correct) {
-            lc[(pitch * t) * stride] = lh[2 * t];
-            lc[(pitch * t + 1) * stride] = lh[2 * t + 1];
-        } else {
+        double l[2] = {lh[2 * t], lh[2 * t + 1]};
+        if (correct) {
             st.lh[0] = lh[2 * t]; st.lh[1] = lh[2 * t + 1];
             st.T = times[t];
-            st.mu[0] = band_rate(md, params, t, 0); st.mu[1] = band_rate(md, params, t, 1);
-            double l[2];
+            st.mu[0] = mi_t[0]; st.mu[1] = mi_t[1];
             const bool ok = solve_interval(&st, cpfit, mixtureTH, l, &nfev, gaux ? gaux + kGridAux * t : nullptr);
-            lc[(pitch * t) * stride] = l[0];
-            lc[(pitch * t + 1) * stride] = l[1];
-            if (!ok) { *nfev_out = nfev; return MISTI_CORRECTION_FAILED; }
+            if (!ok) {
+                lc[(pitch * t) * stride] = l[0];
+                lc[(pitch * t + 1) * stride] = l[1];
+                *nfev_out = nfev;
+                return MISTI_CORRECTION_FAILED;
+            }
+        }
+        lc[(pitch * t) * stride] = l[0];
+        lc[(pitch * t + 1) * stride] = l[1];
+        for (int g = 0; g < 2; ++g) {
+            if (sdone[g]) continue;
+            const double lhv = lh[2 * t + g];
+            if (!(fabs(lhv - slam[g]) < 1e-10 && t < numT - 1)) {  // the run [sk, t) ends here
+                if (t > sk[g]) {
+                    const double avg = snc[g] / stime[g];
+                    for (int i = sk[g]; i < t; ++i) lc[(pitch * i + g) * stride] = avg;
+                }
+                if (t >= numT - 1) { sdone[g] = true; continue; }  // the last interval is never smoothed (the reference loops forever here)
+                sk[g] = t; slam[g] = lhv; snc[g] = 0.0; stime[g] = 0.0;
+            }
+            snc[g] += l[g] * times[t];
+            stime[g] += times[t];
         }
         if (Pr) {
             double* q = Pr + 6 * (t + 1);
@@ -97,6 +157,11 @@ MISTI_HD inline int correct_lambdas_item(const ModelDesc& md, const double* time
         nc0 = (st.P0[0][0] + st.P0[0][1]) + st.P0[0][2];  // reference quirk: a probability used as a log (:353-354)
         nc1 = (st.P0[1][0] + st.P0[1][1]) + st.P0[1][2];
     }
+    for (int g = 0; g < 2; ++g)
+        if (!sdone[g] && splitT > sk[g]) {
+            const double avg = snc[g] / stime[g];
+            for (int i = sk[g]; i < splitT; ++i) lc[(pitch * i + g) * stride] = avg;
+        }
     if (cpfit && splitT < numT) {
         // Post-split rates, cpfit mode (:356-374): pnc_t = (exp(-T lh0) + exp((nc1 - nc0) - T lh1)) / (1 + exp(nc1 - nc0)),
         // lam_t = -log(pnc_t) / T, and nc0, nc1 both drop by T lam_t -- so d = nc1 - nc0 never changes and the intervals are
@@ -153,28 +218,6 @@ MISTI_HD inline int correct_lambdas_item(const ModelDesc& md, const double* time
             const double lam = (pr0 + pr1) / (pr0 / lh[2 * t] + pr1 / lh[2 * t + 1]);
             lc[(pitch * t) * stride] = lam;
             lc[(pitch * t + 1) * stride] = lam;
-        }
-    }
-    if (flags & MISTI_FLAG_SMOOTH) {  // SmoothConst for both genomes (:380-405)
-        for (int g = 0; g < 2; ++g) {
-            int k = 0;
-            double lam = lh[g];
-            double time = 0.0, nc = 0.0;
-            while (k < splitT) {
-                int j = k;
-                while (fabs(lh[2 * j + g] - lam) < 1e-10 && j < numT - 1) {
-                    nc += lc[(pitch * j + g) * stride] * times[j];
-                    time += times[j];
-                    ++j;
-                    if (j == splitT) break;
-                }
-                if (j == k) break;  // splitT == numT: the reference loops forever here; we stop
-                const double avg = nc / time;
-                for (int i = k; i < j; ++i) lc[(pitch * i + g) * stride] = avg;
-                lam = lh[2 * j + g];
-                nc = 0.0; time = 0.0;
-                k = j;
-            }
         }
     }
     *nfev_out = nfev;

@@ -29,7 +29,13 @@ int hs_correct_lambdas(int numT, int splitT, int sampleDate, const double* times
         md.pulse_pop[b] = (int)pulses[4 * b]; md.pulse_time[b] = (int)pulses[4 * b + 1];
         md.pulse_val[b] = pulses[4 * b + 2]; md.pulse_opt[b] = (int)pulses[4 * b + 3];
     }
-    return misti::correct_lambdas_item(md, times, lh, params, flags, mixtureTH, lc, 2, 1, Pr, nfev);
+    // the grid constants and interval classes the library precomputes on the host (misti_add_grid / misti_add_model)
+    std::vector<double> gaux((size_t)numT * misti::kGridAux);
+    for (int t = 0; t < numT; ++t) misti::grid_aux_row(lh + 2 * t, t < numT - 1 ? times[t] : 0.0, &gaux[(size_t)t * misti::kGridAux]);
+    std::vector<unsigned> cls(numT);
+    for (int t = 0; t < numT; ++t) cls[t] = misti::interval_class(md, t);
+    return misti::correct_lambdas_item(md, times, lh, params, flags, mixtureTH, lc, 2, 1, Pr, nfev, gaux.data(), nullptr, nullptr,
+                                       cls.data());
 }
 
 static void fill_model(misti::ModelDesc& md, int numT, int splitT, int sampleDate, int n_bands, const double* bands,
@@ -67,7 +73,9 @@ int hs_jsfs(int numT, int splitT, int sampleDate, const double* times, int n_ban
     misti::post_split_coeffs(md, times, lc, 2, 1, cpost);
     std::vector<double> rec((size_t)(numT + 1) * misti::kRecSlots);
     int nseg = 0;
-    int st = misti::build_segments_item(md, times, params, lc, 2, 1, rec.data(), &nseg);
+    std::vector<unsigned> cls(numT);
+    for (int t = 0; t < numT; ++t) cls[t] = misti::interval_class(md, t);
+    int st = misti::build_segments_item(md, times, params, lc, 2, 1, rec.data(), &nseg, cls.data());
     if (st != MISTI_OK) return st;
     if (hs_last_types) {
         for (int i = 0; i < nseg && i < 256; ++i) hs_last_types[i] = misti::seg_type(misti::seg_meta_bits(rec[i * misti::kRecSlots + 15]));
