@@ -105,6 +105,8 @@ misti_jsfs_kernel(int B, int P, const double* __restrict__ params, const int* __
                   int* __restrict__ terms, const int* __restrict__ row_ids, misti::Cont* __restrict__ conts,
                   const int* __restrict__ item_list, const int* __restrict__ item_count, int* __restrict__ next_list,
                   int* __restrict__ next_count, int* __restrict__ work_counter) {
+    // resume pass with an empty queue (the usual case): nothing to set up
+    if (item_list != nullptr && *item_count == 0) return;
     // one item per 16-lane half warp (3 of the 44 chain states per lane), two items per warp
     __shared__ double ysm_all[kJsfsWarps * 2][misti::kGroupScratch];
     __shared__ misti::RunTable<misti::HalfWarpLanes> runtab;

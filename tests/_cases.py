@@ -57,3 +57,48 @@ def relerr(a, b):
 def end_to_end_gated(case):
     """True where the reference is reproducible to 1e-9 end to end (SURVEY.md 7.3 / BASELINE.md 3.7)."""
     return bool(case["stable"]) and case["name"] not in RUNAWAY
+
+
+def random_jsfs_cases(n, seed=2026):
+    """Random models for the JSFS stage alone (trueEPS: the given rates ARE the model rates): short random grids, random
+    rates over two decades, random split (sometimes at the end of the grid = infinite last interval with migration),
+    sampling date, bands (fixed rates, both demes, possibly up to the split) and pulses -- every segment type and event
+    combination of the segment pre-pass.  Returned in the layout of tests/golden/evals.json cases (+ "grid")."""
+    rng = np.random.default_rng(seed)
+    out = []
+    while len(out) < n:
+        numT = int(rng.integers(6, 16))
+        times = (10 ** rng.uniform(-2.5, -0.3, numT - 1)).tolist()
+        lam = (10 ** rng.uniform(-0.7, 1.0, (numT, 2))).tolist()
+        no_split = rng.random() < 0.2
+        st = numT if no_split else int(rng.integers(1, numT))
+        sd = int(rng.integers(0, st + 1)) if rng.random() < 0.4 else 0
+        mi, pu = [], []
+        used = [[False] * numT, [False] * numT]
+        for _ in range(int(rng.integers(0, 4))):
+            pop = int(rng.integers(0, 2))
+            a = int(rng.integers(sd, max(sd + 1, st)))
+            b = int(rng.integers(a + 1, st + 1)) if a + 1 <= st else a + 1
+            if b > numT or any(used[pop][a:b]):
+                continue
+            for i in range(a, b):
+                used[pop][i] = True
+            mi.append([pop + 1, a, b, float(10 ** rng.uniform(-2, 0.7)), 0])
+        if no_split and not (used[0][numT - 1] or used[1][numT - 1]):
+            a = max(sd, numT - 2)
+            if any(used[0][a:numT]):
+                continue
+            for i in range(a, numT):
+                used[0][i] = True
+            mi.append([1, a, numT, float(10 ** rng.uniform(-1, 0.5)), 0])
+        ptimes = set()
+        for _ in range(int(rng.integers(0, 3))):
+            t = int(rng.integers(sd, st)) if st > sd else None
+            if t is None or t in ptimes:
+                continue
+            ptimes.add(t)
+            pu.append([int(rng.integers(1, 3)), t, float(rng.uniform(0.01, 0.6)), 0])
+        out.append({"name": "rnd%d" % len(out), "grid": (times, lam, st, sd), "mi": mi, "pu": pu, "params": [],
+                    "flags": dict(trueEPS=True, cpfit=False, smooth=False, unfolded=bool(rng.integers(0, 2))),
+                    "sfs": [float(1000 + 7 * 300)] + rng.integers(50, 600, 7).astype(float).tolist()})
+    return out

@@ -317,3 +317,35 @@ def test_results_do_not_depend_on_the_warp_partner(engine, golden_datasets, gold
         assert one["terms"][0] == out["terms"][b]
         assert np.array_equal(one["llh"][0], out["llh"][b], equal_nan=True), b
         assert np.array_equal(one["jafs"][0], out["jafs"][b], equal_nan=True), b
+
+
+def test_random_models_in_one_batch(engine):
+    """JSFS stage on 40 random grids / models (tests/_cases.random_jsfs_cases) evaluated as ONE batch with per-item
+    models: neighbours in a warp have different grids, segment lists, events and series lengths."""
+    from _cases import random_jsfs_cases
+    from oracle.misti_oracle import OracleModel
+    import misti_b200
+    cases = random_jsfs_cases(40)
+    for uf in (True, False):
+        sel = [c for c in cases if c["flags"]["unfolded"] == uf]
+        engine.clear_models()
+        mids, refs = [], []
+        for c in sel:
+            times, lam, st, sd = c["grid"]
+            bands, pulses = bands_pulses(c)
+            gid = engine.add_grid(times, lam)
+            mids.append(engine.add_model(gid, st, sd, bands, pulses))
+            om = OracleModel(times, lam, c["sfs"], st, c["mi"], c["pu"], trueEPS=True, unfolded=uf, sampleDate=sd)
+            om.likelihood([])
+            refs.append(om)
+        engine.set_data([c["sfs"] for c in sel], uf)
+        B = len(sel)
+        inj = np.zeros((B, engine.numT_max, 2))
+        for b, om in enumerate(refs):
+            inj[b, :len(om.lc)] = np.array(om.lc)
+        out = engine.evaluate(np.zeros((B, 0)), model_ids=np.array(mids, dtype=np.int32), flags=8 if uf else 0, lc_inject=inj,
+                              row_ids=np.arange(B, dtype=np.int32), want=("jafs", "status"))
+        assert (out["status"] == 0).all()
+        for b, om in enumerate(refs):
+            assert relerr(out["jafs"][b], om.JAFS) < 1e-10, sel[b]["name"]
+            assert relerr(out["llh"][b], om.llh) < TOL, sel[b]["name"]

@@ -168,3 +168,40 @@ def test_segment_lists(hostsim, golden_datasets, golden_cases):
             assert n_mig == 0
             # runs are broken only by the sampling date and by pulses
             assert len(ty) <= 1 + (1 if 0 < sd < st else 0) + len(case["pu"])
+
+
+def _jsfs_random(lib, case, lam):
+    times, _, st, sd = case["grid"]
+    bands, pulses = bands_pulses(case)
+    T, L = _arr(times), _arr(lam)
+    Bn = _arr([[b[0], b[1], b[2], b[3], b[4]] for b in bands] or [[0] * 5])
+    Pu = _arr([[p[0], p[1], p[2], p[3]] for p in pulses] or [[0] * 4])
+    par = _arr([0.0])
+    uf = case["flags"]["unfolded"]
+    row = _arr(case["sfs"])
+    d = row[1:]
+    drow = _arr(list(d) + [0.0]) if uf else _arr([d[0] + d[6], d[1] + d[5], d[2] + d[4], d[3], 0, 0, 0, 0.0])
+    drow[7] = llh_constants([row], uf)[0]
+    raw, jn, llh, terms = np.zeros(7), np.zeros(7), ctypes.c_double(0), ctypes.c_int(0)
+    rc = lib.hs_jsfs(len(lam), st, sd, _p(T), len(bands), _p(Bn), len(pulses), _p(Pu), 0, _p(par), _p(L), int(uf), _p(drow), _p(raw),
+                     _p(jn), ctypes.byref(llh), ctypes.byref(terms))
+    return rc, raw, jn, llh.value
+
+
+def test_random_models_against_oracle(hostsim):
+    """JSFS stage on random grids / rates / splits / sampling dates / bands / pulses vs the CPU oracle"""
+    from _cases import random_jsfs_cases
+    from oracle.misti_oracle import OracleModel
+    seen = set()
+    for case in random_jsfs_cases(40):
+        times, lam, st, sd = case["grid"]
+        om = OracleModel(times, lam, case["sfs"], st, case["mi"], case["pu"], trueEPS=True, unfolded=case["flags"]["unfolded"],
+                         sampleDate=sd)
+        ref = om.likelihood([])
+        rc, raw, jn, llh = _jsfs_random(hostsim, case, om.lc)  # the oracle's rates (its post-split part is always re-fitted)
+        assert rc == 0, case
+        assert relerr(jn, om.JAFS) < 1e-11, (case["name"], relerr(jn, om.JAFS))
+        assert relerr(llh, ref) < 1e-10, case["name"]
+        buf = (ctypes.c_int * 256)()
+        seen |= set(buf[:hostsim.hs_segment_types(buf, 256)])
+    assert {1, 2, 4} <= seen  # swept intervals, closed-form runs and an infinite last interval all occurred
