@@ -47,8 +47,10 @@ extern "C" {
 #define MISTI_CORRECTION_FAILED 2  /* "Lambda correction failed" (MigrationInference.py:575-578)              */
 #define MISTI_NONFINITE 3          /* the reference would have raised or produced NaN                         */
 #define MISTI_INFINITE_COAL_TIME 4 /* last interval before the split without migration (:475-476, ref. exits)  */
-#define MISTI_STIFF 5              /* an interval with rate*length > 131072 (only seen after a run-away correction);
-                                      llh = NaN instead of spending seconds on one item                          */
+#define MISTI_STIFF 5              /* intervals WITH migration and (largest exit rate)*length > 256 are only seen after a
+                                      run-away correction; they take a dense scaling-and-squaring step instead of
+                                      the sweep.  An item that still meets one after two such rounds gets this
+                                      status and llh = NaN                                                        */
 
 #define MISTI_MAX_BANDS 8
 #define MISTI_MAX_PULSES 8
@@ -83,7 +85,7 @@ typedef struct misti_eval_io {
     double* pr_out;          /* [B][numT_max+1][3][2] 3-state trajectories (MigrationInference.Pr)          */
     int32_t* status;         /* [B]                                                                        */
     int32_t* nfev;           /* [B] residual evaluations spent in the correction (least_squares nfev sum)  */
-    int32_t* terms;          /* [B] sparse mat-vecs spent in the JSFS stage                                 */
+    int32_t* terms;          /* [B] sparse mat-vecs spent in the JSFS stage (a closed-form zero-migration run = 1) */
     const int32_t* row_ids;  /* [B] score item b against data row row_ids[b] ONLY; llh is then [B] instead of
                                 [B][R] (one optimiser simplex per (bootstrap row, split time) pair)         */
 } misti_eval_io;
