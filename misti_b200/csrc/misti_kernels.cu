@@ -177,6 +177,7 @@ misti_jsfs_kernel(int B, int P, const double* __restrict__ params, const int* __
 // P1 = E11 P0 and integralP = last column of E (MigrationInference.SolveDifEq, :530-540).
 // ------------------------------------------------------------------------------------------------
 constexpr int kStiffThreads = 128;
+constexpr int kStiffBlocksPerSm = 3;  // 59 KB of shared memory each
 constexpr int kStiffRounds = 2;    // an item may be parked (and resumed) this many times per evaluation
 constexpr int kLd = 50;  // leading dimension of the 48x48 matrices in shared memory (bank spread)
 
@@ -861,7 +862,7 @@ static int eval_chunk(misti_ctx* ctx, int B, int P, const double* d_params, cons
     // stiff rounds: dense scaling-and-squaring step for the parked items, then resume the sweep for them.  The grids
     // are fixed; with an empty queue (the usual case) both kernels return at once.
     for (int r = 0; r < kStiffRounds; ++r) {
-        misti_stiff_kernel<<<ctx->sm_count, kStiffThreads, kStiffSmem, ctx->stream>>>(
+        misti_stiff_kernel<<<ctx->sm_count * kStiffBlocksPerSm, kStiffThreads, kStiffSmem, ctx->stream>>>(
             P, d_params, d_model_ids, model_default, ctx->d_models, ctx->d_times, ctx->d_lc, stride, ctx->d_rec, ctx->cap_seg,
             ctx->d_nseg, ctx->d_conts, ctx->d_queue[r & 1], ctx->d_counts + r, ctx->d_status);
         CK(cudaGetLastError());
