@@ -179,9 +179,10 @@ misti_jsfs_kernel(int B, int P, const double* __restrict__ params, const int* __
 constexpr int kStiffThreads = 128;
 constexpr int kStiffBlocksPerSm = 3;  // 59 KB of shared memory each
 constexpr int kStiffRounds = 2;    // an item may be parked (and resumed) this many times per evaluation
-constexpr int kLd = 50;  // leading dimension of the 48x48 matrices in shared memory (bank spread)
+constexpr int kLd = 52;  // leading dimension of the 48x48 matrices in shared memory: with 52 = 4 mod 16 the 16 lanes of a
+                         // half warp read 16 different bank pairs for both MMA operands (row gid, column tig and vice versa)
 
-constexpr int kStiffSmem = (3 * 48 * 50 + 192 + 192) * (int)sizeof(double);
+constexpr int kStiffSmem = (3 * 48 * kLd + 192 + 192 + 96) * (int)sizeof(double);
 
 __device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
@@ -217,6 +218,9 @@ misti_stiff_kernel(int P, const double* __restrict__ params, const int* __restri
     double* Z = sm + 2 * 48 * kLd;       // [48][kLd]
     double* vec = sm + 3 * 48 * kLd;     // P[48], tmp[48], adiag[48], aug[48], coef[48][4]
     double* Pv = vec; double* tmp = vec + 48; double* adiag = vec + 96; double* aug = vec + 144; double* coef = vec + 192;
+    int* colo = reinterpret_cast<int*>(vec + 384);  // [44][4] offsets of the generator's off-diagonal columns (col * kLd)
+    for (int i = threadIdx.x; i < 44 * 4; i += kStiffThreads) colo[i] = misti::d_ell[i >> 2][i & 3].col * kLd;
+    __syncthreads();
     __shared__ double s_scal[4];
     __shared__ int s_flag[2];
     (void)s_scal;
@@ -331,13 +335,13 @@ misti_stiff_kernel(int P, const double* __restrict__ params, const int* __restri
                 ++k;
                 p *= rr;
                 rr = lam / (k + 1);
-                for (int idx = tid; idx < 45 * 48; idx += kStiffThreads) {
-                    const int r = idx / 48, c = idx % 48;
+                // entry (r, c) = idx / 48, idx % 48 for idx = tid, tid + 128, ...: 128 = 2 * 48 + 32
+                for (int r = tid / 48, c = tid % 48; r < 45; r += c + 32 >= 48 ? 3 : 2, c = c + 32 >= 48 ? c - 16 : c + 32) {
                     double acc;
                     if (r < 44) {
                         acc = adiag[r] * Ya[r * kLd + c];
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) acc += coef[r * 4 + e] * Ya[misti::d_ell[r][e].col * kLd + c];
+                        for (int e = 0; e < 4; ++e) acc += coef[r * 4 + e] * Ya[colo[r * 4 + e] + c];
                         acc += aug[r] * Ya[44 * kLd + c];
                     } else {
                         acc = Ya[44 * kLd + c];
