@@ -188,22 +188,36 @@ __device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, do
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
-// C = A * A for 48x48 (ld = kLd) matrices in shared memory; 4 warps x 9 tiles of 8x8 each
+// C = A * A for 48x48 (ld = kLd) matrices in shared memory.  Each of the 4 warps owns a 24x24 quadrant = 3 x 3 tiles of
+// 8x8 and keeps its 9 accumulator tiles in registers, so a k-step loads 3 + 3 operand fragments for 9 MMAs.
 __device__ void dense_square(const double* __restrict__ A, double* __restrict__ C) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int gid = lane >> 2, tig = lane & 3;
-    for (int t = warp; t < 36; t += kStiffThreads / 32) {
-        const int ti = t / 6, tj = t % 6;
-        double c0 = 0.0, c1 = 0.0;
+    const int r0 = 24 * (warp >> 1), c0 = 24 * (warp & 1);
+    double acc[3][3][2];
 #pragma unroll
-        for (int kk = 0; kk < 12; ++kk) {
-            const double a = A[(8 * ti + gid) * kLd + 4 * kk + tig];
-            const double b = A[(4 * kk + tig) * kLd + 8 * tj + gid];
-            dmma_m8n8k4(c0, c1, a, b);
-        }
-        C[(8 * ti + gid) * kLd + 8 * tj + 2 * tig] = c0;
-        C[(8 * ti + gid) * kLd + 8 * tj + 2 * tig + 1] = c1;
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+#pragma unroll 4
+    for (int kk = 0; kk < 12; ++kk) {
+        double a[3], b[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) a[i] = A[(r0 + 8 * i + gid) * kLd + 4 * kk + tig];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) b[j] = A[(4 * kk + tig) * kLd + c0 + 8 * j + gid];
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
     }
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            C[(r0 + 8 * i + gid) * kLd + c0 + 8 * j + 2 * tig] = acc[i][j][0];
+            C[(r0 + 8 * i + gid) * kLd + c0 + 8 * j + 2 * tig + 1] = acc[i][j][1];
+        }
 }
 
 __global__ void __launch_bounds__(kStiffThreads)
