@@ -643,6 +643,7 @@ struct IntervalState {
     double T;         // interval length
     double mu[2];     // migration rates
     double P0[2][3];  // per genome: P(both lineages in deme 0 / deme 1 / one each), not yet coalesced
+    double nch[2];    // cpfit target of the interval, exp(-lh T) (sum of P0): the same in every residual evaluation
 };
 
 MISTI_HD inline void corr_matrix(const double* l, const double* mu, double T, double* M) {
@@ -672,10 +673,9 @@ struct ResidualProb {
         mat3_expm(M, E);
         for (int k = 0; k < 2; ++k) {
             const double* P = st->P0[k];
-            const double nch = exp(-st->lh[k] * st->T) * ((P[0] + P[1]) + P[2]);
             double p[3];
             mat3_vec(E, P, p);
-            out[k] = ((p[0] + p[1]) + p[2]) - nch;
+            out[k] = ((p[0] + p[1]) + p[2]) - st->nch[k];
         }
         return true;
     }
@@ -770,6 +770,7 @@ MISTI_HD inline bool solve_interval_mig(IntervalState* st, bool cpfit, double* l
     u.lh[0] = lh[0] * T; u.lh[1] = lh[1] * T;
     double x[2] = {u.lh[0], u.lh[1]};
     int nf = 0, status;
+    for (int k = 0; k < 2; ++k) u.nch[k] = exp(-u.lh[k] * u.T) * ((P0[k][0] + P0[k][1]) + P0[k][2]);
     if (cpfit) { ResidualProb fun; fun.st = &u; status = least_squares_trf<2>(fun, x, false, -kInf, &nf); }
     else { ResidualTime fun; fun.st = &u; status = least_squares_trf<2>(fun, x, false, -kInf, &nf); }
     *nfev += nf;
