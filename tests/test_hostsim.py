@@ -205,3 +205,20 @@ def test_random_models_against_oracle(hostsim):
         buf = (ctypes.c_int * 256)()
         seen |= set(buf[:hostsim.hs_segment_types(buf, 256)])
     assert {1, 2, 4} <= seen  # swept intervals, closed-form runs and an infinite last interval all occurred
+
+
+def test_split_at_the_ends_of_the_grid(hostsim, golden_datasets):
+    """split index 0 / 1 (no or one two-population interval), last finite interval, and no split inside the grid"""
+    from oracle.misti_oracle import OracleModel
+    ds = golden_datasets["synthetic"]
+    times, lam = ds["times"], ds["lambdas"]
+    n = len(lam)
+    for st, mi in ((0, []), (1, []), (1, [[1, 0, 1, 0.7, 0]]), (2, [[2, 1, 2, 1.3, 0]]), (n - 1, [[1, 100, n - 1, 0.2, 0]]),
+                   (n, [[1, 120, n, 0.2, 0]])):
+        case = {"grid": (times, lam, st, 0), "mi": mi, "pu": [], "params": [],
+                "flags": dict(trueEPS=True, cpfit=False, smooth=False, unfolded=True), "sfs": ds["sfs"]}
+        om = OracleModel(times, lam, ds["sfs"], st, mi, [], trueEPS=True, unfolded=True)
+        ref = om.likelihood([])
+        rc, raw, jn, llh = _jsfs_random(hostsim, case, om.lc)
+        assert rc == 0, (st, mi)
+        assert relerr(jn, om.JAFS) < 1e-12 and relerr(llh, ref) < 1e-12, (st, mi)
