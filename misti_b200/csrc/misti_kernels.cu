@@ -29,6 +29,7 @@ using misti::ModelDesc;
 
 constexpr int kCorrectThreads = 64;
 constexpr int kCorrectMinBlocks = 8;
+constexpr int kCoopMaxItems = 4096;  // up to here the four-lane variant of K1 still runs at about one warp per scheduler
 constexpr int kJsfsWarps = 4;      // warps per block of the JSFS kernel (8 items per block)
 constexpr int kJsfsMinBlocks = 3;  // occupancy target: caps the kernel at 168 registers per thread (12 warps per SM)
 constexpr int kMaxChunk = 1 << 20;
@@ -38,16 +39,19 @@ static __device__ const double d_l8[8][8] = MISTI_L8_INIT;
 static __device__ const unsigned char d_w8[7][8] = MISTI_W8_INIT;
 
 // ------------------------------------------------------------------------------------------------
-// K1: correction chain, one thread per item
+// K1: correction chain, one thread per item.  COOP = the variant for small batches (an optimiser step): FOUR lanes per
+// item, all running the same chain on the same data, which share out the residual evaluations of a solver round
+// (misti::eval_fj); results are bit-identical to the one-thread variant, the serial chain is shorter.
 // ------------------------------------------------------------------------------------------------
-template <int MINB>
+template <int MINB, bool COOP>
 __global__ void __launch_bounds__(kCorrectThreads, MINB)
 misti_correct_kernel(int B, int P, const double* __restrict__ params, const int* __restrict__ model_ids, int model_default,
                      const ModelDesc* __restrict__ models, const double* __restrict__ times, const double* __restrict__ lh,
                      const double* __restrict__ gaux, const unsigned* __restrict__ cls_all, unsigned flags, double mixtureTH, const double* __restrict__ lc_inject, int numT_max, double* lc,
                      long stride, double* __restrict__ cpost, double* pr_out, int* __restrict__ status, int* __restrict__ nfev,
                      double* __restrict__ rec, int seg_cap, int* __restrict__ nseg) {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = COOP ? gtid >> 2 : gtid;
     // one model for the whole batch (the usual case): its descriptor is staged in shared memory once per block
     __shared__ ModelDesc smd;
     if (!model_ids) {
@@ -77,7 +81,7 @@ misti_correct_kernel(int B, int P, const double* __restrict__ params, const int*
         }
     } else {
         double* pr = pr_out ? pr_out + (long)b * (numT_max + 1) * 6 : nullptr;
-        st = misti::correct_lambdas_item(md, tt, ll, par, flags, mixtureTH, lcb, kPitch, stride, pr, &nf, ga, cp, &cp_done, cls);
+        st = misti::correct_lambdas_item<COOP>(md, tt, ll, par, flags, mixtureTH, lcb, kPitch, stride, pr, &nf, ga, cp, &cp_done, cls);
     }
     int ns = 0;
     if (st == MISTI_OK) {
@@ -537,6 +541,7 @@ struct misti_ctx {
     int64_t launches = 0;
     int jsfs_minb = kJsfsMinBlocks;
     int correct_minb = kCorrectMinBlocks;
+    int correct_coop = -1;  // -1 = by batch size
 };
 
 namespace {
@@ -684,6 +689,7 @@ int misti_ctx_create(int device, void* stream, misti_ctx** out) {
     }
     if (const char* e = getenv("MISTI_JSFS_MINB")) ctx->jsfs_minb = atoi(e);
     if (const char* e = getenv("MISTI_CORRECT_MINB")) ctx->correct_minb = atoi(e);
+    if (const char* e = getenv("MISTI_CORRECT_COOP")) ctx->correct_coop = atoi(e);
     for (int i = 0; i < 3; ++i)
         if (cudaEventCreate(&ctx->ev[i]) != cudaSuccess) { delete ctx; return MISTI_E_CUDA; }
     if (cudaMalloc((void**)&ctx->d_small, (44 * 44 + 2 * 44) * sizeof(double)) != cudaSuccess) { delete ctx; return MISTI_E_CUDA; }
@@ -841,8 +847,12 @@ static int eval_chunk(misti_ctx* ctx, int B, int P, const double* d_params, cons
     const long stride = (long)ctx->cap;
     const int numT_max = ctx->numT_max;
     CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+    // small batches: four lanes per item (see misti_correct_kernel); the knob MISTI_CORRECT_COOP = 0 / 1 forces a variant
+    const bool coop = ctx->correct_coop < 0 ? B <= kCoopMaxItems : ctx->correct_coop != 0;
 #define MISTI_LAUNCH_CORRECT(MINB)                                                                                       \
-    misti_correct_kernel<MINB><<<(B + kCorrectThreads - 1) / kCorrectThreads, kCorrectThreads, 0, ctx->stream>>>(          \
+    if (coop) MISTI_LAUNCH_CORRECT2(MINB, true, 4L * B); else MISTI_LAUNCH_CORRECT2(MINB, false, (long)B)
+#define MISTI_LAUNCH_CORRECT2(MINB, COOP, NTHREADS)                                                                      \
+    misti_correct_kernel<MINB, COOP><<<(unsigned)(((NTHREADS) + kCorrectThreads - 1) / kCorrectThreads), kCorrectThreads, 0, ctx->stream>>>( \
         B, P, d_params, d_model_ids, model_default, ctx->d_models, ctx->d_times, ctx->d_lh, ctx->d_gaux, ctx->d_cls, flags, mixture_th, \
         d_lc_inject, \
         numT_max, ctx->d_lc, stride, ctx->d_cpost, d_pr, ctx->d_status, ctx->d_nfev, ctx->d_rec, ctx->cap_seg, ctx->d_nseg)
@@ -852,6 +862,7 @@ static int eval_chunk(misti_ctx* ctx, int B, int P, const double* d_params, cons
         default: MISTI_LAUNCH_CORRECT(kCorrectMinBlocks); break;
     }
 #undef MISTI_LAUNCH_CORRECT
+#undef MISTI_LAUNCH_CORRECT2
     CK(cudaGetLastError());
     CK(cudaEventRecord(ctx->ev[1], ctx->stream));
     int blocks = (B + 2 * kJsfsWarps - 1) / (2 * kJsfsWarps);

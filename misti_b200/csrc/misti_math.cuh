@@ -429,7 +429,41 @@ MISTI_HD inline bool all_finite(const double* f) {
     return true;
 }
 
-template <int N, class Fun>
+// Residuals f(x) and their 2-point Jacobian.  COOP (device only): the item is run by FOUR lanes in lock step (all of them
+// execute the same code on the same data); here lane 0 of the quad evaluates f(x) and lanes 1..N the shifted points, at
+// the same time, and the results are exchanged by shuffles -- the N + 1 sequential evaluations of a solver round become
+// one.  Every evaluation still runs the out-of-line functor, so the numbers are those of the one-thread path, bit for bit.
+template <int N, bool COOP, class Fun>
+MISTI_HD inline void eval_fj(Fun& fun, const double* x, bool bounded, double lb, double* f, double* J, int* njev_calls) {
+#if defined(__CUDA_ARCH__)
+    if constexpr (COOP) {
+        const unsigned lane = threadIdx.x & 31u, q = lane & 3u, base = lane & ~3u;
+        const unsigned mask = 0xFu << base;
+        double xq[N], fq[N], dx[N];
+        for (int i = 0; i < N; ++i) {
+            double h = kSqrtEps * (x[i] >= 0 ? 1.0 : -1.0) * (fabs(x[i]) > 1.0 ? fabs(x[i]) : 1.0);
+            if (bounded && x[i] + h < lb) h = -h;
+            xq[i] = x[i];
+            const double xs = x[i] + h;
+            dx[i] = xs - x[i];
+            if (q == (unsigned)(i + 1)) xq[i] = xs;
+        }
+        fun(xq, fq);
+        for (int r = 0; r < N; ++r) f[r] = __shfl_sync(mask, fq[r], base);
+        for (int i = 0; i < N; ++i)
+            for (int r = 0; r < N; ++r) {
+                const double f1 = __shfl_sync(mask, fq[r], base + i + 1);
+                J[r * N + i] = (f1 - f[r]) / dx[i];
+            }
+        *njev_calls += N;
+        return;
+    }
+#endif
+    fun(x, f);
+    fd_jacobian<N>(fun, x, f, bounded, lb, J, njev_calls);
+}
+
+template <int N, bool COOP = false, class Fun>
 MISTI_HD inline int least_squares_trf(Fun& fun, double* x, bool bounded, double lb, int* nfev_out) {
     const double ftol = 1e-8, xtol = 1e-10, gtol = 1e-10;
     const int max_nfev = 100 * N;
@@ -440,9 +474,15 @@ MISTI_HD inline int least_squares_trf(Fun& fun, double* x, bool bounded, double 
         make_strictly_feasible<N>(x, lb, 1e-10);
     }
     double f[N], J[N * N], g[N];
-    fun(x, f);
-    if (!all_finite<N>(f)) { *nfev_out = 1; return -1; }      // "Residuals are not finite in the initial point"
-    fd_jacobian<N>(fun, x, f, bounded, lb, J, &fd_calls);
+    [[maybe_unused]] double Jn[N * N];  // COOP: Jacobian at the trial point, evaluated together with its residuals
+    if constexpr (COOP) {
+        eval_fj<N, true>(fun, x, bounded, lb, f, J, &fd_calls);
+        if (!all_finite<N>(f)) { *nfev_out = 1; return -1; }
+    } else {
+        fun(x, f);
+        if (!all_finite<N>(f)) { *nfev_out = 1; return -1; }  // "Residuals are not finite in the initial point"
+        fd_jacobian<N>(fun, x, f, bounded, lb, J, &fd_calls);
+    }
     int nfev = 1;
     double cost = 0;
     for (int i = 0; i < N; ++i) cost += f[i] * f[i];
@@ -589,7 +629,8 @@ MISTI_HD inline int least_squares_trf(Fun& fun, double* x, bool bounded, double 
                 for (int i = 0; i < N; ++i) xn[i] = x[i] + step[i];
                 make_strictly_feasible<N>(xn, lb, 0.0);
             }
-            fun(xn, fn);
+            if constexpr (COOP) eval_fj<N, true>(fun, xn, bounded, lb, fn, Jn, &fd_calls);
+            else fun(xn, fn);
             ++nfev;
             const double step_h_norm = vnorm<N>(step_h);
             if (!all_finite<N>(fn)) {
@@ -622,7 +663,8 @@ MISTI_HD inline int least_squares_trf(Fun& fun, double* x, bool bounded, double 
         if (actual_reduction > 0) {
             for (int i = 0; i < N; ++i) { x[i] = xn[i]; f[i] = fn[i]; }
             cost = cost_new;
-            fd_jacobian<N>(fun, x, f, bounded, lb, J, &fd_calls);
+            if constexpr (COOP) { for (int i = 0; i < N * N; ++i) J[i] = Jn[i]; }
+            else fd_jacobian<N>(fun, x, f, bounded, lb, J, &fd_calls);
             for (int c = 0; c < N; ++c) {
                 double t = 0;
                 for (int r = 0; r < N; ++r) t += J[r * N + c] * f[r];
@@ -750,6 +792,7 @@ MISTI_HD inline void grid_aux_row(const double* lh2, double T, double* out) {
 
 // The interval WITH migration (CorrectLambda.py:276-317): 2-unknown trust-region solve on the 3-state chains.
 // (Inlined: an out-of-line version measured 5 % slower on B200.)
+template <bool COOP = false>
 MISTI_HD inline bool solve_interval_mig(IntervalState* st, bool cpfit, double* lc, int* nfev) {
     const double T = st->T;
     double (*P0)[3] = st->P0;
@@ -771,8 +814,8 @@ MISTI_HD inline bool solve_interval_mig(IntervalState* st, bool cpfit, double* l
     double x[2] = {u.lh[0], u.lh[1]};
     int nf = 0, status;
     for (int k = 0; k < 2; ++k) u.nch[k] = exp(-u.lh[k] * u.T) * ((P0[k][0] + P0[k][1]) + P0[k][2]);
-    if (cpfit) { ResidualProb fun; fun.st = &u; status = least_squares_trf<2>(fun, x, false, -kInf, &nf); }
-    else { ResidualTime fun; fun.st = &u; status = least_squares_trf<2>(fun, x, false, -kInf, &nf); }
+    if (cpfit) { ResidualProb fun; fun.st = &u; status = least_squares_trf<2, COOP>(fun, x, false, -kInf, &nf); }
+    else { ResidualTime fun; fun.st = &u; status = least_squares_trf<2, COOP>(fun, x, false, -kInf, &nf); }
     *nfev += nf;
     if (status < 0) return false;
     // un-stretch exactly as the reference does: mu*T/T, x/T
@@ -792,6 +835,7 @@ MISTI_HD inline bool solve_interval_mig(IntervalState* st, bool cpfit, double* l
 // SolveLambdaSystem (CorrectLambda.py:266-317).  On return lc[2] and st->P0 (advanced through the
 // interval).  Returns false when the reference would report a failed correction or crash.
 // `ga` (nullable): grid_aux_row of this interval.
+template <bool COOP = false>
 MISTI_HD inline bool solve_interval(IntervalState* st, bool cpfit, double mixtureTH, double* lc, int* nfev, const double* ga = nullptr) {
     const double T = st->T;
     double (*P0)[3] = st->P0;
@@ -825,7 +869,7 @@ MISTI_HD inline bool solve_interval(IntervalState* st, bool cpfit, double mixtur
         const double lb = 0.01 * (st->lh[0] < st->lh[1] ? st->lh[0] : st->lh[1]);
         double x[2] = {st->lh[0], st->lh[1]};
         int nf = 0;
-        const int status = least_squares_trf<2>(fun, x, true, lb, &nf);
+        const int status = least_squares_trf<2, COOP>(fun, x, true, lb, &nf);
         *nfev += nf;
         if (status < 0) return false;
         lc[0] = x[0]; lc[1] = x[1];
@@ -833,10 +877,11 @@ MISTI_HD inline bool solve_interval(IntervalState* st, bool cpfit, double mixtur
         for (int k = 0; k < 2; ++k) { P0[k][0] *= e0; P0[k][1] *= e1; }
         return lc[0] > 0 && lc[1] > 0;
     }
-    return solve_interval_mig(st, cpfit, lc, nfev);
+    return solve_interval_mig<COOP>(st, cpfit, lc, nfev);
 }
 
 // FitSinglePop (CorrectLambda.py:88-92) with P0 = [[exp(nc0),0,0],[exp(nc1),0,0]]
+template <bool COOP = false>
 MISTI_HD inline bool fit_single_pop(const double* lh, double T, double nc0, double nc1, double* lam, int* nfev) {
     double p0 = exp(nc0), p1 = exp(nc1);
     const double sp = p0 + p1;
@@ -847,7 +892,7 @@ MISTI_HD inline bool fit_single_pop(const double* lh, double T, double nc0, doub
     double x[1] = {p0 * lh[0] + p1 * lh[1]};
     const double lb = 0.01 * (lh[0] < lh[1] ? lh[0] : lh[1]);
     int nf = 0;
-    const int status = least_squares_trf<1>(fun, x, true, lb, &nf);
+    const int status = least_squares_trf<1, COOP>(fun, x, true, lb, &nf);
     *nfev += nf;
     if (status < 0) return false;
     *lam = x[0];

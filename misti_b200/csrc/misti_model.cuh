@@ -84,6 +84,8 @@ MISTI_HD inline void interval_rates(const ModelDesc& md, const unsigned* cls, co
 // cpost (nullable): in cpfit mode the post-split closed-form coefficients (see post_split_coeffs in misti_jsfs.cuh)
 // fall out of the post-split pass for free (exp(-lam T) is the fitted non-coalescence probability itself);
 // *cpost_done tells the caller whether they were written.
+// COOP (device only): four lanes run the item together, see eval_fj in misti_math.cuh.
+template <bool COOP = false>
 MISTI_HD inline int correct_lambdas_item(const ModelDesc& md, const double* times, const double* lh, const double* params,
                                          unsigned flags, double mixtureTH, double* lc, int pitch, long stride, double* Pr,
                                          int* nfev_out, const double* gaux = nullptr, double* cpost = nullptr,
@@ -126,7 +128,7 @@ MISTI_HD inline int correct_lambdas_item(const ModelDesc& md, const double* time
             st.lh[0] = lh[2 * t]; st.lh[1] = lh[2 * t + 1];
             st.T = times[t];
             st.mu[0] = mi_t[0]; st.mu[1] = mi_t[1];
-            const bool ok = solve_interval(&st, cpfit, mixtureTH, l, &nfev, gaux ? gaux + kGridAux * t : nullptr);
+            const bool ok = solve_interval<COOP>(&st, cpfit, mixtureTH, l, &nfev, gaux ? gaux + kGridAux * t : nullptr);
             if (!ok) {
                 lc[(pitch * t) * stride] = l[0];
                 lc[(pitch * t + 1) * stride] = l[1];
@@ -206,7 +208,7 @@ MISTI_HD inline int correct_lambdas_item(const ModelDesc& md, const double* time
             const double T = times[t];
             if (T == 0) { lc[(pitch * t) * stride] = 1; lc[(pitch * t + 1) * stride] = 1; continue; }
             double lam;
-            if (!fit_single_pop(lh + 2 * t, T, nc0, nc1, &lam, &nfev)) { *nfev_out = nfev; return MISTI_NONFINITE; }
+            if (!fit_single_pop<COOP>(lh + 2 * t, T, nc0, nc1, &lam, &nfev)) { *nfev_out = nfev; return MISTI_NONFINITE; }
             lc[(pitch * t) * stride] = lam;
             lc[(pitch * t + 1) * stride] = lam;
             nc0 += -T * lam;

@@ -349,3 +349,37 @@ def test_random_models_in_one_batch(engine):
         for b, om in enumerate(refs):
             assert relerr(out["jafs"][b], om.JAFS) < 1e-10, sel[b]["name"]
             assert relerr(out["llh"][b], om.llh) < TOL, sel[b]["name"]
+
+
+def test_cooperative_correction_kernel_is_bit_identical(golden_datasets):
+    """small batches run the correction chain with four lanes per item (the residual evaluations of a solver round in
+    parallel); rates, solver evaluation counts, spectra and likelihoods must equal the one-thread-per-item kernel's bit
+    for bit, in both fitting modes."""
+    import os
+    import misti_b200
+    ds = golden_datasets["synthetic"]
+    rng = np.random.default_rng(4)
+    B = 61
+    params = np.column_stack([10 ** rng.uniform(-3, 0.5, B), rng.uniform(0, 2, B), rng.uniform(0, 0.3, B)])
+    res = {}
+    for coop in ("0", "1"):
+        os.environ["MISTI_CORRECT_COOP"] = coop
+        try:
+            eng = misti_b200.Engine(0)
+        finally:
+            del os.environ["MISTI_CORRECT_COOP"]
+        gid = eng.add_grid(ds["times"], ds["lambdas"])
+        mids = [eng.add_model(gid, 40, 0, bands=[(1, 5, 12, 0.8, 0)]),
+                eng.add_model(gid, 40, 0, bands=[(0, 2, 10, 0.3, 0), (1, 5, 12, 0.8, 1)], pulses=[(0, 7, 0.05, 2)]),
+                eng.add_model(gid, 38, 0)]
+        eng.set_data([ds["sfs"]], True)
+        models = np.array([mids[b % 3] for b in range(B)], dtype=np.int32)
+        out = []
+        for flags in (1 | 2 | 4 | 8, 1 | 4 | 8):  # cpfit, default mode
+            out.append(eng.evaluate(params, model_ids=models, flags=flags, want=("jafs", "lc", "status", "nfev")))
+        res[coop] = out
+        eng.close()
+    for a, b in zip(res["0"], res["1"]):
+        assert (a["status"] == 0).sum() > B // 2
+        for k in ("status", "nfev", "lc", "llh", "jafs"):
+            assert np.array_equal(a[k], b[k], equal_nan=True), k
