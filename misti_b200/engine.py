@@ -34,24 +34,24 @@ def _ptr(a):
 
 def llh_constants(rows, unfolded):
     """lnGamma(n+1) - sum lnGamma(k_i+1) per data row, with scipy.special.gammaln exactly as
-    MigrationInference.SetJAFS does (MigrationInference.py:216-227)."""
+    MigrationInference.SetJAFS does (MigrationInference.py:216-227): the same terms subtracted in the same
+    order, vectorised over the rows (1001 bootstrap rows cost 0.2 s one scalar call at a time)."""
     from scipy.special import gammaln
     rows = np.asarray(rows, dtype=np.float64).reshape(-1, 8)
-    out = np.empty(len(rows))
-    for r, row in enumerate(rows):
-        d = [float(v) for v in row[1:]]
-        c = 0
-        c += gammaln(sum(d) + 1)
-        if unfolded:
-            for i in range(7):
-                c -= gammaln(d[i] + 1)
-        else:
-            c -= gammaln(d[0] + d[6] + 1)
-            c -= gammaln(d[1] + d[5] + 1)
-            c -= gammaln(d[2] + d[4] + 1)
-            c -= gammaln(d[3] + 1)
-        out[r] = c
-    return out
+    d = rows[:, 1:]
+    n = np.zeros(len(rows))
+    for i in range(7):  # Python's sum(): left to right, starting from 0
+        n = n + d[:, i]
+    c = 0 + gammaln(n + 1)
+    if unfolded:
+        for i in range(7):
+            c = c - gammaln(d[:, i] + 1)
+    else:
+        c = c - gammaln(d[:, 0] + d[:, 6] + 1)
+        c = c - gammaln(d[:, 1] + d[:, 5] + 1)
+        c = c - gammaln(d[:, 2] + d[:, 4] + 1)
+        c = c - gammaln(d[:, 3] + 1)
+    return np.asarray(c, dtype=np.float64).reshape(-1)
 
 
 class Engine:

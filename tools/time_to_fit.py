@@ -79,14 +79,17 @@ def main():
                                    "reference_local_optimum_llh": ref["llh"]}
 
     sts = list(range(36, 45))
-    t = time.perf_counter()
-    sw = Sweep(inp.times, inp.lambdas, bs, unfolded=False, cpfit=False, smooth=True, engine=eng)
-    for st in sts:
-        sw.add_model(st)
-    llh = sw.evaluate_grid()
-    dt = time.perf_counter() - t
+    first = None
+    for _ in range(2):  # the first pass pays one-time costs (lazy loading of a kernel variant, buffer growth); both are reported
+        t = time.perf_counter()
+        sw = Sweep(inp.times, inp.lambdas, bs, unfolded=False, cpfit=False, smooth=True, engine=eng)
+        for st in sts:
+            sw.add_model(st)
+        llh = sw.evaluate_grid()
+        dt = time.perf_counter() - t
+        first = dt if first is None else first
     best_st = [sts[i] for i in np.argmax(llh, axis=0)]
-    out["config5a_no_migration_grid"] = {"gpu_s": dt, "rows": len(bs), "split_times": sts, "pairs": int(llh.size),
+    out["config5a_no_migration_grid"] = {"gpu_s": dt, "first_call_s": first, "rows": len(bs), "split_times": sts, "pairs": int(llh.size),
                                          "argmax_split_row0": best_st[0],
                                          "argmax_split_histogram": {str(s): int(best_st.count(s)) for s in sts},
                                          "reference_extrapolated_s_1core": 0.28 * llh.size,
