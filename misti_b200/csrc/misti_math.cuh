@@ -49,34 +49,66 @@ MISTI_HD inline void mat3_vec(const double* A, const double* x, double* y) {
     for (int i = 0; i < 3; ++i) y[i] = A[3 * i] * x[0] + A[3 * i + 1] * x[1] + A[3 * i + 2] * x[2];
 }
 
-// Solve Q X = P (3x3, X overwrites P) by Gaussian elimination with partial pivoting.
+// Solve Q X = P (3x3, X overwrites P) by Gaussian elimination with partial pivoting.  The pivot row is picked with
+// compares and the row exchange done with selects on fixed indices (no run-time subscripts), so that after inlining the
+// two matrices live in registers; the arithmetic is that of the textbook loop (first largest pivot wins), bit for bit.
 MISTI_HD inline bool mat3_solve(double* Q, double* P) {
-    for (int k = 0; k < 3; ++k) {
-        int piv = k;
-        double best = fabs(Q[3 * k + k]);
-        for (int i = k + 1; i < 3; ++i)
-            if (fabs(Q[3 * i + k]) > best) { best = fabs(Q[3 * i + k]); piv = i; }
+    double q[3][3], p[3][3];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) { q[i][j] = Q[3 * i + j]; p[i][j] = P[3 * i + j]; }
+    // column 0: pivot among rows 0, 1, 2
+    {
+        int piv = 0;
+        double best = fabs(q[0][0]);
+        if (fabs(q[1][0]) > best) { best = fabs(q[1][0]); piv = 1; }
+        if (fabs(q[2][0]) > best) { best = fabs(q[2][0]); piv = 2; }
         if (best == 0.0) return false;
-        if (piv != k)
-            for (int j = 0; j < 3; ++j) {
-                double t = Q[3 * k + j]; Q[3 * k + j] = Q[3 * piv + j]; Q[3 * piv + j] = t;
-                t = P[3 * k + j]; P[3 * k + j] = P[3 * piv + j]; P[3 * piv + j] = t;
-            }
-        const double inv = 1.0 / Q[3 * k + k];
-        for (int i = k + 1; i < 3; ++i) {
-            const double f = Q[3 * i + k] * inv;
-            for (int j = k; j < 3; ++j) Q[3 * i + j] -= f * Q[3 * k + j];
-            for (int j = 0; j < 3; ++j) P[3 * i + j] -= f * P[3 * k + j];
-        }
-    }
-    for (int k = 2; k >= 0; --k) {
-        const double inv = 1.0 / Q[3 * k + k];
         for (int j = 0; j < 3; ++j) {
-            double v = P[3 * k + j];
-            for (int i = k + 1; i < 3; ++i) v -= Q[3 * k + i] * P[3 * i + j];
-            P[3 * k + j] = v * inv;
+            const double a0 = q[0][j], a1 = q[1][j], a2 = q[2][j];
+            q[0][j] = piv == 1 ? a1 : (piv == 2 ? a2 : a0);
+            q[1][j] = piv == 1 ? a0 : a1;
+            q[2][j] = piv == 2 ? a0 : a2;
+            const double b0 = p[0][j], b1 = p[1][j], b2 = p[2][j];
+            p[0][j] = piv == 1 ? b1 : (piv == 2 ? b2 : b0);
+            p[1][j] = piv == 1 ? b0 : b1;
+            p[2][j] = piv == 2 ? b0 : b2;
+        }
+        const double inv = 1.0 / q[0][0];
+        for (int i = 1; i < 3; ++i) {
+            const double f = q[i][0] * inv;
+            for (int j = 0; j < 3; ++j) q[i][j] -= f * q[0][j];
+            for (int j = 0; j < 3; ++j) p[i][j] -= f * p[0][j];
         }
     }
+    // column 1: pivot among rows 1, 2
+    {
+        const bool sw = fabs(q[2][1]) > fabs(q[1][1]);
+        const double best = sw ? fabs(q[2][1]) : fabs(q[1][1]);
+        if (best == 0.0) return false;
+        for (int j = 0; j < 3; ++j) {
+            const double a1 = q[1][j], a2 = q[2][j];
+            q[1][j] = sw ? a2 : a1;
+            q[2][j] = sw ? a1 : a2;
+            const double b1 = p[1][j], b2 = p[2][j];
+            p[1][j] = sw ? b2 : b1;
+            p[2][j] = sw ? b1 : b2;
+        }
+        const double inv = 1.0 / q[1][1];
+        const double f = q[2][1] * inv;
+        for (int j = 1; j < 3; ++j) q[2][j] -= f * q[1][j];
+        for (int j = 0; j < 3; ++j) p[2][j] -= f * p[1][j];
+    }
+    if (fabs(q[2][2]) == 0.0) return false;
+    for (int k = 2; k >= 0; --k) {
+        const double inv = 1.0 / q[k][k];
+        for (int j = 0; j < 3; ++j) {
+            double v = p[k][j];
+            for (int i = k + 1; i < 3; ++i) v -= q[k][i] * p[i][j];
+            p[k][j] = v * inv;
+        }
+    }
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) { Q[3 * i + j] = q[i][j]; P[3 * i + j] = p[i][j]; }
     return true;
 }
 

@@ -103,10 +103,25 @@ MISTI_HD inline int correct_lambdas_item(const ModelDesc& md, const double* time
     const int numT = md.numT, splitT = md.splitT;
     // SmoothConst (:380-405) as a streaming pass: per genome the current run of equal PSMC rates [sk, t), the rate that
     // defines it, and the sums of lc T and T over it; a run is averaged and written back when it ends.
+    // (one set of scalars per genome and a step function called with a constant genome index: nothing is subscripted at
+    // run time, so the state stays in registers)
     const bool smooth = (flags & MISTI_FLAG_SMOOTH) != 0;
-    int sk[2] = {0, 0};
-    bool sdone[2] = {!smooth, !smooth};
-    double slam[2] = {lh[0], lh[1]}, snc[2] = {0.0, 0.0}, stime[2] = {0.0, 0.0};
+    struct SmoothRun { int k; bool done; double lam, nc, time; };
+    SmoothRun sr0 = {0, !smooth, lh[0], 0.0, 0.0}, sr1 = {0, !smooth, lh[1], 0.0, 0.0};
+    auto smooth_step = [&](SmoothRun& r, int g, int t, double lcv) {
+        if (r.done) return;
+        const double lhv = lh[2 * t + g];
+        if (!(fabs(lhv - r.lam) < 1e-10 && t < numT - 1)) {  // the run [k, t) ends here
+            if (t > r.k) {
+                const double avg = r.nc / r.time;
+                for (int i = r.k; i < t; ++i) lc[(pitch * i + g) * stride] = avg;
+            }
+            if (t >= numT - 1) { r.done = true; return; }  // the last interval is never smoothed (the reference loops forever here)
+            r.k = t; r.lam = lhv; r.nc = 0.0; r.time = 0.0;
+        }
+        r.nc += lcv * times[t];
+        r.time += times[t];
+    };
     for (int t = 0; t < splitT; ++t) {
         double mi_t[2], pu_t[2];
         interval_rates(md, cls, params, t, mi_t, pu_t);
@@ -138,20 +153,8 @@ MISTI_HD inline int correct_lambdas_item(const ModelDesc& md, const double* time
         }
         lc[(pitch * t) * stride] = l[0];
         lc[(pitch * t + 1) * stride] = l[1];
-        for (int g = 0; g < 2; ++g) {
-            if (sdone[g]) continue;
-            const double lhv = lh[2 * t + g];
-            if (!(fabs(lhv - slam[g]) < 1e-10 && t < numT - 1)) {  // the run [sk, t) ends here
-                if (t > sk[g]) {
-                    const double avg = snc[g] / stime[g];
-                    for (int i = sk[g]; i < t; ++i) lc[(pitch * i + g) * stride] = avg;
-                }
-                if (t >= numT - 1) { sdone[g] = true; continue; }  // the last interval is never smoothed (the reference loops forever here)
-                sk[g] = t; slam[g] = lhv; snc[g] = 0.0; stime[g] = 0.0;
-            }
-            snc[g] += l[g] * times[t];
-            stime[g] += times[t];
-        }
+        smooth_step(sr0, 0, t, l[0]);
+        smooth_step(sr1, 1, t, l[1]);
         if (Pr) {
             double* q = Pr + 6 * (t + 1);
             for (int s = 0; s < 3; ++s) { q[2 * s] = st.P0[0][s]; q[2 * s + 1] = st.P0[1][s]; }
@@ -159,11 +162,14 @@ MISTI_HD inline int correct_lambdas_item(const ModelDesc& md, const double* time
         nc0 = (st.P0[0][0] + st.P0[0][1]) + st.P0[0][2];  // reference quirk: a probability used as a log (:353-354)
         nc1 = (st.P0[1][0] + st.P0[1][1]) + st.P0[1][2];
     }
-    for (int g = 0; g < 2; ++g)
-        if (!sdone[g] && splitT > sk[g]) {
-            const double avg = snc[g] / stime[g];
-            for (int i = sk[g]; i < splitT; ++i) lc[(pitch * i + g) * stride] = avg;
-        }
+    if (!sr0.done && splitT > sr0.k) {
+        const double avg = sr0.nc / sr0.time;
+        for (int i = sr0.k; i < splitT; ++i) lc[(pitch * i) * stride] = avg;
+    }
+    if (!sr1.done && splitT > sr1.k) {
+        const double avg = sr1.nc / sr1.time;
+        for (int i = sr1.k; i < splitT; ++i) lc[(pitch * i + 1) * stride] = avg;
+    }
     if (cpfit && splitT < numT) {
         // Post-split rates, cpfit mode (:356-374): pnc_t = (exp(-T lh0) + exp((nc1 - nc0) - T lh1)) / (1 + exp(nc1 - nc0)),
         // lam_t = -log(pnc_t) / T, and nc0, nc1 both drop by T lam_t -- so d = nc1 - nc0 never changes and the intervals are
