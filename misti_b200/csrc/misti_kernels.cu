@@ -1,16 +1,19 @@
 // misti_kernels.cu -- CUDA kernels (sm_100a) and the C ABI of libmisti_b200.so.
 //
 // Two kernels make one batched evaluation:
-//   misti_correct_kernel   one THREAD per item: parameter mapping, negative-parameter test, the
-//                          sequential coalescence-rate correction chain (CorrectLambdas / CorrectLambda /
-//                          Smooth, incl. an iterate-faithful trust-region-reflective least-squares
-//                          solver), and the post-split closed-form coefficients.
-//   misti_jsfs_kernel      one HALF WARP per item (3 chain states per lane, two items per warp): generator assembly from (lc, mi), uniformised
-//                          propagation + branch-length integrals on the 44-state chain, pulses,
-//                          ancient-sample reset, collapse, closed-form one-population tail, the
-//                          7x44 / 7x8 JSFS contraction, normalisation, and -- fused -- the multinomial
-//                          composite log-likelihood against every data row (bootstrap replicates),
-//                          reduced with warp shuffles.
+//   misti_correct_kernel   one THREAD per item (four lanes per item for small batches): parameter mapping,
+//                          negative-parameter test, the sequential coalescence-rate correction chain
+//                          (CorrectLambdas / CorrectLambda / Smooth, incl. an iterate-faithful trust-region-reflective
+//                          least-squares solver), the post-split closed-form coefficients, and the scalar pre-pass of
+//                          the JSFS stage: the item's list of 128-byte segment records (one per interval with
+//                          migration, one per RUN of intervals without).
+//   misti_jsfs_kernel      one HALF WARP per item (3 chain states per lane, two items per warp, persistent grid):
+//                          uniformised propagation + branch-length integrals on the 44-state chain for the segments
+//                          with migration, the closed-form projector pass for the runs without, pulses,
+//                          ancient-sample reset, collapse, closed-form one-population tail, the 7x44 / 7x8 JSFS
+//                          contraction, normalisation, and -- fused -- the multinomial composite log-likelihood
+//                          against every data row (bootstrap replicates).
+//   misti_stiff_kernel     (rarely) the dense scaling-and-squaring step, FP64 MMA, for intervals too stiff to sweep.
 // There is no CPU path: every entry point below launches on the device or fails.
 #include <cuda_runtime.h>
 #include <cmath>
@@ -98,7 +101,7 @@ misti_correct_kernel(int B, int P, const double* __restrict__ params, const int*
 }
 
 // ------------------------------------------------------------------------------------------------
-// K2: expected JSFS + composite log-likelihood, one warp per item
+// K2: expected JSFS + composite log-likelihood, one half warp per item
 // ------------------------------------------------------------------------------------------------
 template <int MINB>
 __global__ void __launch_bounds__(kJsfsWarps * 32, MINB)
