@@ -137,23 +137,20 @@ MISTI_D inline int build_segments_item(const ModelDesc& md, const double* times,
     unsigned long long run_meta = 0;
     int run_n = 0;
     *nseg_out = 0;
-    auto put = [&](const double* slot) {
-        double* o = rec + (long)ns * kRecSlots;
-        for (int i = 0; i < kRecSlots; ++i) o[i] = slot[i];
-        ++ns;
-    };
+    // records are written straight to their place in global memory (no staging array in the thread's stack frame)
     auto close_run = [&]() {
-        double slot[kRecSlots];
-        for (int i = 0; i < 8; ++i) slot[i] = c[i];
+        double* o = rec + (long)ns * kRecSlots;
+        for (int i = 0; i < 8; ++i) o[i] = c[i];
         const double u03 = u0 * u0 * u0, u13 = u1 * u1 * u1;
-        slot[8] = u0; slot[9] = u03; slot[10] = u03 * u03;
-        slot[11] = u1; slot[12] = u13; slot[13] = u13 * u13;
-        slot[14] = u0 * u1;
-        slot[15] = seg_meta_pack(run_meta | ((unsigned long long)run_n << 20));
-        put(slot);
+        o[8] = u0; o[9] = u03; o[10] = u03 * u03;
+        o[11] = u1; o[12] = u13; o[13] = u13 * u13;
+        o[14] = u0 * u1;
+        o[15] = seg_meta_pack(run_meta | ((unsigned long long)run_n << 20));
+        ++ns;
         open = false;
     };
-    auto table = [&](double la0, double la1, double m0, double m1, double* slot, double* q_out) {
+    // coefficient table of a migration interval into slots 0..10 of record `o` (the rest zeroed); returns q
+    auto table = [&](double la0, double la1, double m0, double m1, double* o) -> double {
         double q = 0.0;
         for (int i = 0; i < MISTI_QDIAG_N; ++i) {
             const double d = ((double)MISTI_TAB(qdiag)[i][0] * la0 + (double)MISTI_TAB(qdiag)[i][1] * la1) +
@@ -161,12 +158,13 @@ MISTI_D inline int build_segments_item(const ModelDesc& md, const double* times,
             q = d > q ? d : q;
         }
         const double qinv = 1.0 / q;
-        const double rq[4] = {la0 * qinv, la1 * qinv, m0 * qinv, m1 * qinv};
-        for (int i = 0; i < kRecSlots; ++i) slot[i] = 0.0;
-        for (int k = 0; k < 4; ++k) { slot[k] = rq[k]; slot[4 + k] = 2.0 * rq[k]; }
-        slot[8] = 4.0 * rq[0]; slot[9] = 4.0 * rq[1];
-        slot[10] = qinv;
-        *q_out = q;
+        const double rq0 = la0 * qinv, rq1 = la1 * qinv, rq2 = m0 * qinv, rq3 = m1 * qinv;
+        o[0] = rq0; o[1] = rq1; o[2] = rq2; o[3] = rq3;
+        o[4] = 2.0 * rq0; o[5] = 2.0 * rq1; o[6] = 2.0 * rq2; o[7] = 2.0 * rq3;
+        o[8] = 4.0 * rq0; o[9] = 4.0 * rq1;
+        o[10] = qinv;
+        o[11] = 0.0; o[12] = 0.0; o[13] = 0.0; o[14] = 0.0;
+        return q;
     };
     for (int it = 0; it <= n_fin; ++it) {
         const bool last = it == n_fin;  // the infinite interval (only visited when inf_last)
@@ -187,21 +185,21 @@ MISTI_D inline int build_segments_item(const ModelDesc& md, const double* times,
                                          ((unsigned long long)t << 8) | (1ull << 20);
         if (last) {
             if (!mig) return MISTI_INFINITE_COAL_TIME;
-            double slot[kRecSlots], q;
-            table(la0, la1, m0, m1, slot, &q);
+            double* o = rec + (long)ns * kRecSlots;
+            const double q = table(la0, la1, m0, m1, o);
             if (!(q <= DBL_MAX)) return MISTI_NONFINITE;
-            slot[15] = seg_meta_pack(flags | SEG_INF);
-            put(slot);
+            o[15] = seg_meta_pack(flags | SEG_INF);
+            ++ns;
         } else if (mig) {
-            double slot[kRecSlots], q;
-            table(la0, la1, m0, m1, slot, &q);
+            double* o = rec + (long)ns * kRecSlots;
+            const double q = table(la0, la1, m0, m1, o);
             const double qT = q * T;
             if (!(qT <= DBL_MAX)) return MISTI_NONFINITE;
             if (qT > kUnifMaxStiff) {
                 // rates of 1e5 and more per unit of interval length only come out of a run-away correction; such an
                 // interval is not swept (it would take millions of terms): the item is parked for the dense step
-                for (int i = 0; i < kRecSlots; ++i) slot[i] = 0.0;
-                slot[15] = seg_meta_pack(flags | SEG_STIFF);
+                for (int i = 0; i < 11; ++i) o[i] = 0.0;
+                o[15] = seg_meta_pack(flags | SEG_STIFF);
             } else {
                 const int nsub = qT > kUnifMaxStep ? (int)ceil(qT / kUnifMaxStep) : 1;
                 const double lam = nsub == 1 ? qT : qT / nsub;
@@ -215,10 +213,10 @@ MISTI_D inline int build_segments_item(const ModelDesc& md, const double* times,
                     r = lam * MISTI_RECIP(k + 1);
                 } while (!(r < 1.0 && p < kUnifTol * (1.0 - r)) && k < kUnifMaxTerms);
                 if (k >= kUnifMaxTerms) return MISTI_NONFINITE;
-                slot[11] = lam; slot[13] = p0; slot[14] = t0;
-                slot[15] = seg_meta_pack(flags | SEG_MIG | ((unsigned long long)k << 32) | ((unsigned long long)nsub << 48));
+                o[11] = lam; o[13] = p0; o[14] = t0;
+                o[15] = seg_meta_pack(flags | SEG_MIG | ((unsigned long long)k << 32) | ((unsigned long long)nsub << 48));
             }
-            put(slot);
+            ++ns;
         } else {
             if (!open) {
                 open = true;
