@@ -22,6 +22,8 @@ import math
 import numpy as np
 
 RHO, CHI, PSI, SIGMA = 1.0, 2.0, 0.5, 0.5
+LOOKAHEAD_MAX_POINTS = 4096  # look-ahead (two Nelder-Mead iterations per call) while a call stays this small: up to here
+                             # the device evaluates a batch as fast as a single point (profiles/r01_latency.json)
 NONZDELT, ZDELT = 0.05, 0.00025
 
 
@@ -49,10 +51,48 @@ def initial_simplex(x0):
     return sim
 
 
-def nelder_mead_batch(fun, x0, xatol=1e-4, fatol=1e-4, maxiter=None, maxfev=None, speculative=True, owners=None):
+def _candidates(s):
+    """reflection, expansion, outside and inside contraction points of sorted simplices s [A, N+1, N] (_optimize.py:846-874)"""
+    N = s.shape[2]
+    xbar = s[:, 0].copy()
+    for j in range(1, N):  # np.add.reduce(sim[:-1], 0): sequential row sum
+        xbar = xbar + s[:, j]
+    xbar = xbar / N
+    last = s[:, -1]
+    xr = (1 + RHO) * xbar - RHO * last
+    xe = (1 + RHO * CHI) * xbar - RHO * CHI * last
+    xc = (1 + PSI * RHO) * xbar - PSI * RHO * last
+    xcc = (1 - PSI) * xbar + PSI * last
+    return xr, xe, xc, xcc
+
+
+def _decide(f, fxr, fxe, fxc, fxcc):
+    """scipy's decision tree (_optimize.py:846-896), vectorised over simplices: which candidate replaces the worst vertex
+    (0 expansion, 1 reflection, 2 outside contraction, 3 inside contraction, -1 none = shrink) and scipy's evaluation count"""
+    better_than_best = fxr < f[:, 0]
+    take_e = better_than_best & (fxe < fxr)
+    take_r = (better_than_best & ~(fxe < fxr)) | (~better_than_best & (fxr < f[:, -2]))
+    contract = ~better_than_best & ~(fxr < f[:, -2])
+    outside = contract & (fxr < f[:, -1])
+    inside = contract & ~(fxr < f[:, -1])
+    take_c = outside & (fxc <= fxr)
+    take_cc = inside & (fxcc < f[:, -1])
+    which = np.where(take_e, 0, np.where(take_r, 1, np.where(take_c, 2, np.where(take_cc, 3, -1))))
+    nev = 1 + (better_than_best | contract).astype(np.int64)
+    return which, nev
+
+
+def nelder_mead_batch(fun, x0, xatol=1e-4, fatol=1e-4, maxiter=None, maxfev=None, speculative=True, owners=None, lookahead="auto"):
     """Minimise S independent objectives in lock step.  x0: [S, N].  Returns a dict of arrays:
     x [S, N], fun [S], nit [S], nfev [S] (scipy's count), status [S] (0 converged, 1 maxfev, 2 maxiter),
-    success [S], evaluations (points actually sent to `fun`), launches (calls of `fun`)."""
+    success [S], evaluations (points actually sent to `fun`), launches (calls of `fun`).
+
+    lookahead: with the candidates of the current step also evaluate, speculatively, the candidates of the NEXT step for
+    every way the current one can end (which candidate is accepted x where it lands in the sorted simplex: 3N + 3
+    scenarios of 4 points), so that one call of `fun` advances a simplex by two iterations.  The decisions and scipy's
+    counts are unchanged; it trades (12N + 12) extra points per call for half the calls, which pays while a call's cost
+    does not depend on its size (the device evaluates a few thousand points as fast as one).  "auto" = while the
+    call stays below LOOKAHEAD_MAX_POINTS points."""
     x0 = np.asarray(x0, dtype=np.float64)
     if x0.ndim == 1:
         x0 = x0.reshape(1, -1)
@@ -79,7 +119,14 @@ def nelder_mead_batch(fun, x0, xatol=1e-4, fatol=1e-4, maxiter=None, maxfev=None
     iterations = np.ones(S, dtype=np.int64)
     status = np.full(S, -1, dtype=np.int64)
     active = np.ones(S, dtype=bool)
-    while True:
+    # scenarios of the look-ahead: (accepted candidate, rank of the new vertex in the sorted simplex); see _decide for
+    # the conditions that make other combinations impossible
+    scen = [(0, 0)] + [(1, k) for k in range(N)] + [(2, k) for k in range(N + 1)] + [(3, k) for k in range(N + 1)]
+    n_scen = len(scen)
+    scen_base = np.array([0, 1, 1 + N, 2 + 2 * N], dtype=np.int64)  # first scenario of each accepted candidate
+
+    def retire():
+        """termination tests at the top of scipy's loop; returns the indices still active"""
         budget = (fcalls < maxfev) & (iterations < maxiter)
         with np.errstate(invalid="ignore"):
             conv = (np.max(np.abs(sim[:, 1:] - sim[:, :1]).reshape(S, -1), axis=1) <= xatol) & \
@@ -88,51 +135,22 @@ def nelder_mead_batch(fun, x0, xatol=1e-4, fatol=1e-4, maxiter=None, maxfev=None
         status[done_now & budget & conv] = 0
         status[done_now & ~budget & (fcalls >= maxfev)] = 1
         status[done_now & ~budget & (fcalls < maxfev)] = 2
-        active &= ~done_now
-        idx = np.nonzero(active)[0]
-        if idx.size == 0:
-            break
-        A = idx.size
-        s, f = sim[idx], fsim[idx]
-        xbar = s[:, 0].copy()
-        for j in range(1, N):  # np.add.reduce(sim[:-1], 0): sequential row sum
-            xbar = xbar + s[:, j]
-        xbar = xbar / N
-        last = s[:, -1]
-        xr = (1 + RHO) * xbar - RHO * last
-        xe = (1 + RHO * CHI) * xbar - RHO * CHI * last
-        xc = (1 + PSI * RHO) * xbar - PSI * RHO * last
-        xcc = (1 - PSI) * xbar + PSI * last
-        if speculative:
-            fall = call(np.concatenate([xr, xe, xc, xcc]), np.tile(idx, 4)).reshape(4, A)
-            fxr, fxe, fxc, fxcc = fall
-        else:
-            fxr = call(xr, idx)
-            want_e = fxr < f[:, 0]
-            want_c = ~want_e & ~(fxr < f[:, -2]) & (fxr < f[:, -1])
-            want_cc = ~want_e & ~(fxr < f[:, -2]) & ~(fxr < f[:, -1])
-            second = np.where(want_e[:, None], xe, np.where(want_c[:, None], xc, xcc))
-            need = want_e | want_c | want_cc
-            f2 = np.full(A, np.inf)
-            if need.any():
-                f2[need] = call(second[need], idx[need])
-            fxe, fxc, fxcc = f2, f2, f2
-        # scipy's decision tree (_optimize.py:846-896), vectorised
-        better_than_best = fxr < f[:, 0]
-        take_e = better_than_best & (fxe < fxr)
-        take_r = (better_than_best & ~(fxe < fxr)) | (~better_than_best & (fxr < f[:, -2]))
-        contract = ~better_than_best & ~(fxr < f[:, -2])
-        outside = contract & (fxr < f[:, -1])
-        inside = contract & ~(fxr < f[:, -1])
-        take_c = outside & (fxc <= fxr)
-        take_cc = inside & (fxcc < f[:, -1])
-        shrink = (outside & ~take_c) | (inside & ~take_cc)
-        new_x = np.where(take_e[:, None], xe, np.where(take_r[:, None], xr, np.where(take_c[:, None], xc, xcc)))
-        new_f = np.where(take_e, fxe, np.where(take_r, fxr, np.where(take_c, fxc, fxcc)))
-        replace = take_e | take_r | take_c | take_cc
-        s[replace, -1] = new_x[replace]
-        f[replace, -1] = new_f[replace]
-        fcalls[idx] += 1 + (better_than_best | contract).astype(np.int64)
+        active[done_now] = False
+        return np.nonzero(active)[0]
+
+    def apply(idx, s, f, which, nev, cand, fcand):
+        """replace the worst vertex by the accepted candidate, or shrink (one more call); sort; write back"""
+        nonlocal sim, fsim
+        A = len(idx)
+        rows = np.arange(A)
+        acc = which >= 0
+        w = np.where(acc, which, 0)
+        new_x = cand[w, rows]
+        new_f = fcand[w, rows]
+        s[acc, -1] = new_x[acc]
+        f[acc, -1] = new_f[acc]
+        fcalls[idx] += nev
+        shrink = ~acc
         if shrink.any():
             sh = np.nonzero(shrink)[0]
             s[sh, 1:] = s[sh, :1] + SIGMA * (s[sh, 1:] - s[sh, :1])
@@ -142,6 +160,70 @@ def nelder_mead_batch(fun, x0, xatol=1e-4, fatol=1e-4, maxiter=None, maxfev=None
         s, f = _sort(s, f)
         sim[idx], fsim[idx] = s, f
         iterations[idx] += 1
+
+    while True:
+        idx = retire()
+        if idx.size == 0:
+            break
+        A = idx.size
+        s, f = sim[idx].copy(), fsim[idx].copy()
+        xr, xe, xc, xcc = _candidates(s)
+        cand = np.stack([xe, xr, xc, xcc])  # order of _decide's codes
+        look = speculative and (lookahead is True or (lookahead == "auto" and A * 4 * (1 + n_scen) <= LOOKAHEAD_MAX_POINTS))
+        if not speculative:
+            fxr = call(xr, idx)
+            want_e = fxr < f[:, 0]
+            want_c = ~want_e & ~(fxr < f[:, -2]) & (fxr < f[:, -1])
+            want_cc = ~want_e & ~(fxr < f[:, -2]) & ~(fxr < f[:, -1])
+            second = np.where(want_e[:, None], xe, np.where(want_c[:, None], xc, xcc))
+            need = want_e | want_c | want_cc
+            f2 = np.full(A, np.inf)
+            if need.any():
+                f2[need] = call(second[need], idx[need])
+            fcand = np.stack([f2, fxr, f2, f2])
+            which, nev = _decide(f, fxr, f2, f2, f2)
+            apply(idx, s, f, which, nev, cand, fcand)
+            continue
+        if not look:
+            fcand = call(np.concatenate([xe, xr, xc, xcc]), np.tile(idx, 4)).reshape(4, A)
+            which, nev = _decide(f, fcand[1], fcand[0], fcand[2], fcand[3])
+            apply(idx, s, f, which, nev, cand, fcand)
+            continue
+        # ---- two iterations per call
+        nxt = np.empty((n_scen, 4, A, N))  # candidates of the next step per scenario, in _decide's order
+        nsim = np.empty((n_scen, A, N + 1, N))
+        for q, (o, k) in enumerate(scen):
+            t = np.empty((A, N + 1, N))
+            t[:, :k] = s[:, :k]
+            t[:, k] = cand[o]
+            t[:, k + 1:] = s[:, k:N]
+            nsim[q] = t
+            r2, e2, c2, cc2 = _candidates(t)
+            nxt[q, 0], nxt[q, 1], nxt[q, 2], nxt[q, 3] = e2, r2, c2, cc2
+        X = np.concatenate([cand.reshape(4 * A, N), nxt.reshape(n_scen * 4 * A, N)])
+        fall = call(X, np.tile(idx, 4 * (1 + n_scen)))
+        fcand = fall[:4 * A].reshape(4, A)
+        fnxt = fall[4 * A:].reshape(n_scen, 4, A)
+        which, nev = _decide(f, fcand[1], fcand[0], fcand[2], fcand[3])
+        apply(idx, s, f, which, nev, cand, fcand)
+        # second iteration for the simplices that are still active and whose first step was not a shrink
+        keep = which >= 0
+        retire()
+        sel = np.nonzero(active[idx] & keep)[0]
+        if sel.size == 0:
+            continue
+        idx2 = idx[sel]
+        s2, f2 = sim[idx2].copy(), fsim[idx2].copy()
+        # the scenario that came true: the accepted candidate and the rank it got in the stable sort
+        o = which[sel]
+        fnew = fcand[o, sel]
+        k = (f[sel][:, :N] <= fnew[:, None]).sum(axis=1)  # f still holds the pre-sort values with the new one last
+        q = scen_base[o] + k  # index of (o, k) in scen
+        assert np.array_equal(nsim[q, sel], s2), "look-ahead scenario does not match the simplex"
+        cand2 = nxt[q, :, sel].transpose(1, 0, 2)  # [4, A2, N]
+        fcand2 = fnxt[q, :, sel].T                 # [4, A2]
+        which2, nev2 = _decide(f2, fcand2[1], fcand2[0], fcand2[2], fcand2[3])
+        apply(idx2, s2, f2, which2, nev2, cand2, fcand2)
     return {"x": sim[:, 0].copy(), "fun": fsim.min(axis=1), "nit": iterations, "nfev": fcalls, "status": status,
             "success": status == 0, "sim": sim, "fsim": fsim, "evaluations": evaluations, "launches": launches}
 

@@ -72,3 +72,27 @@ def test_basinhopping_walkers_equal_scipy():
         assert res["fun"][w] == ref.fun
         assert res["nfev"][w] == ref.nfev
         assert res["minimization_failures"][w] == ref.minimization_failures
+
+
+@pytest.mark.parametrize("N", [1, 2, 3])
+def test_lookahead_takes_the_same_decisions_in_half_the_calls(N):
+    """two Nelder-Mead iterations per objective call (speculative candidates of the next step for every possible outcome
+    of the current one): same x, f, nit, nfev as scipy, about half the calls"""
+    rng = np.random.default_rng(N)
+    S = 17
+    x0 = rng.uniform(0.2, 3.0, (S, N))
+    shifts = rng.uniform(0.0, 1.0, S)
+
+    def obj(X, who):
+        X = np.atleast_2d(X)
+        a = X - shifts[np.asarray(who)][:, None]
+        f = (a ** 2).sum(axis=1) + 0.3 * np.cos(3.0 * a).sum(axis=1) + (0.5 * (a[:, :1] * a[:, -1:]).sum(axis=1) if N > 1 else 0.0)
+        return np.where((X < 0).any(axis=1), np.inf, f)
+    res = {la: nelder_mead_batch(obj, x0, xatol=1e-6, fatol=1e-6, maxiter=400, lookahead=la) for la in (False, True)}
+    for k in ("x", "fun", "nit", "nfev", "status"):
+        assert np.array_equal(res[False][k], res[True][k]), k
+    assert res[True]["launches"] < 0.62 * res[False]["launches"]
+    for s in range(S):
+        ref = optimize.minimize(lambda x: float(obj(x, [s])[0]), x0[s], method="Nelder-Mead",
+                                options={"xatol": 1e-6, "fatol": 1e-6, "maxiter": 400})
+        assert np.array_equal(res[True]["x"][s], ref.x) and res[True]["nfev"][s] == ref.nfev and res[True]["nit"][s] == ref.nit
