@@ -35,6 +35,7 @@ for _k in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "NUMEXPR_NUM_THREADS", "OPENBLA
     os.environ.setdefault(_k, "1")  # as MiSTI.py:23-25
 
 METRIC = "expected-JSFS+logL evals/sec"
+_emit = print  # replaced in main() by a writer to the process's original stdout
 SPLIT_T, BAND = 40, [2, 5, 12, 0.8, 1]
 NUM_T = 127
 # dense formulation (Pade-13 + Van Loan, zero squarings) per evaluation
@@ -126,7 +127,7 @@ def run_reference(args):
                        "the reference path; the reference is pure Python and is absent on the GPU box)" % (numpy.__version__, scipy.__version__)},
             "cpu_baseline": {"value": value, "unit": "evals/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    _emit(json.dumps(line))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -328,7 +329,7 @@ def run_gpu(args):
             "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": B * 8, "d2h_bytes_per_step": B * 8 + B * 4,
                     "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks}
-    print(json.dumps(line), flush=True)
+    _emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
@@ -343,10 +344,19 @@ def main():
     ap.add_argument("--skip-cpu", action="store_true", help="omit the cpu_baseline leg (profiling runs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    # Exactly ONE line goes to stdout: while the benchmark runs, file descriptor 1 points to stderr (NCCL prints its
+    # version banner to stdout from C, whatever NCCL_DEBUG_FILE says); the JSON line is written to the real stdout.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    global _emit
+    _emit = lambda text: os.write(real_stdout, (text + "\n").encode())  # noqa: E731
     if args.impl == "reference":
         run_reference(args)
     else:
         run_gpu(args)
+    sys.stdout.flush()
+    os.dup2(real_stdout, 1)
 
 
 if __name__ == "__main__":
