@@ -49,8 +49,8 @@ extern "C" {
 #define MISTI_INFINITE_COAL_TIME 4 /* last interval before the split without migration (:475-476, ref. exits)  */
 #define MISTI_STIFF 5              /* intervals WITH migration and (largest exit rate)*length > 256 are only seen after a
                                       run-away correction; they take a dense scaling-and-squaring step instead of
-                                      the sweep.  An item that still meets one after two such rounds gets this
-                                      status and llh = NaN                                                        */
+                                      the sweep (transparently: the item still ends with status 0).  The code is
+                                      the transient state of such an item between the two kernels                */
 
 #define MISTI_MAX_BANDS 8
 #define MISTI_MAX_PULSES 8

@@ -13,7 +13,9 @@
 //                          ancient-sample reset, collapse, closed-form one-population tail, the 7x44 / 7x8 JSFS
 //                          contraction, normalisation, and -- fused -- the multinomial composite log-likelihood
 //                          against every data row (bootstrap replicates).
-//   misti_stiff_kernel     (rarely) the dense scaling-and-squaring step, FP64 MMA, for intervals too stiff to sweep.
+//   misti_stiff_kernel     (rarely) the dense scaling-and-squaring step, FP64 MMA, for intervals too stiff to sweep,
+//                          followed by the rest of that item's sweep and its results; returns at once when no item
+//                          was parked.  Three launches per evaluation in all.
 // There is no CPU path: every entry point below launches on the device or fails.
 #include <cuda_runtime.h>
 #include <cmath>
@@ -100,6 +102,38 @@ misti_correct_kernel(int B, int P, const double* __restrict__ params, const int*
     nfev[b] = nf;
 }
 
+// Where the results of an item go (the optional pointers may be null)
+struct ItemOut {
+    const double* data;  // [R][8] data rows
+    int R, unfolded;
+    double *llh, *jafs, *jafs_raw;
+    int *status, *terms;
+    const int* row_ids;
+};
+
+// Results of item b from its lane group: status, spectrum, and the fused composite likelihood over all data rows
+// (bootstrap replicates; the lanes stride the rows).  Called after misti::jafs_finish, which left the logs in `ysm`.
+__device__ __forceinline__ void emit_item(const ItemOut& o, const double* ysm, int lane, int b, int st, double raw_c, double jn_c,
+                                          int nt) {
+    if (lane == 0) {
+        o.status[b] = st;
+        if (o.terms) o.terms[b] = nt;
+    }
+    if (lane < 7) {
+        if (o.jafs) o.jafs[(long)b * 7 + lane] = st == MISTI_OK ? jn_c : nan("");
+        if (o.jafs_raw) o.jafs_raw[(long)b * 7 + lane] = st == MISTI_OK ? raw_c : nan("");
+    }
+    const double bad = (st == MISTI_NEGATIVE_PARAM || st == MISTI_CORRECTION_FAILED) ? -misti::kInf : nan("");
+    const double* logj = ysm + misti::kTailLog;
+    if (o.row_ids) {  // one data row per item
+        const int r = o.row_ids[b];
+        if (lane == 0) o.llh[b] = (st == MISTI_OK && r >= 0 && r < o.R) ? misti::score_row(o.data + 8 * (long)r, logj) : bad;
+    } else {
+        for (int r = lane; r < o.R; r += 16)
+            o.llh[(long)b * o.R + r] = st == MISTI_OK ? misti::score_row(o.data + 8 * (long)r, logj) : bad;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // K2: expected JSFS + composite log-likelihood, one half warp per item
 // ------------------------------------------------------------------------------------------------
@@ -107,13 +141,8 @@ template <int MINB>
 __global__ void __launch_bounds__(kJsfsWarps * 32, MINB)
 misti_jsfs_kernel(int B, int P, const double* __restrict__ params, const int* __restrict__ model_ids, int model_default,
                   const ModelDesc* __restrict__ models, const double* __restrict__ rec, int seg_cap, const int* __restrict__ nseg,
-                  long stride, const double* __restrict__ cpost, const double* __restrict__ data, int R, int unfolded,
-                  double* __restrict__ llh, double* __restrict__ jafs, double* __restrict__ jafs_raw, int* __restrict__ status,
-                  int* __restrict__ terms, const int* __restrict__ row_ids, misti::Cont* __restrict__ conts,
-                  const int* __restrict__ item_list, const int* __restrict__ item_count, int* __restrict__ next_list,
-                  int* __restrict__ next_count, int* __restrict__ work_counter) {
-    // resume pass with an empty queue (the usual case): nothing to set up
-    if (item_list != nullptr && *item_count == 0) return;
+                  long stride, const double* __restrict__ cpost, ItemOut out, misti::Cont* __restrict__ conts,
+                  int* __restrict__ park_list, int* __restrict__ park_count, int* __restrict__ work_counter) {
     // one item per 16-lane half warp (3 of the 44 chain states per lane), two items per warp
     __shared__ double ysm_all[kJsfsWarps * 2][misti::kGroupScratch];
     __shared__ misti::RunTable<misti::HalfWarpLanes> runtab;
@@ -124,9 +153,6 @@ misti_jsfs_kernel(int B, int P, const double* __restrict__ params, const int* __
     const misti::HalfWarpLanes g;
     misti::LaneCtx<misti::HalfWarpLanes> L;
     L.init(g, ysm, &runtab);
-    // first pass: all B items; resume pass: the items parked by the previous pass and advanced by misti_stiff_kernel
-    const bool resume = item_list != nullptr;
-    const int n_items = resume ? *item_count : B;
     // The grid is persistent (as many blocks as fit on the device); every warp draws the next PAIR of items from a
     // counter, so the load balances itself although items differ in cost.  The two halves of a warp work on items
     // 2j and 2j + 1 in lock step; the odd one out re-reads the last item.
@@ -134,44 +160,29 @@ misti_jsfs_kernel(int B, int P, const double* __restrict__ params, const int* __
         int i0 = 0;
         if ((threadIdx.x & 31) == 0) i0 = atomicAdd(work_counter, 2);
         i0 = __shfl_sync(0xffffffffu, i0, 0);
-        if (i0 >= n_items) break;
-        const bool has = i0 + (half & 1) < n_items;
-        const int i = has ? i0 + (half & 1) : n_items - 1;
-        const int b = resume ? item_list[i] : i;
+        if (i0 >= B) break;
+        const bool has = i0 + (half & 1) < B;
+        const int b = has ? i0 + (half & 1) : B - 1;
         const ModelDesc& md = models[model_ids ? model_ids[b] : model_default];
-        int st = status[b];
-        if (resume && st == MISTI_STIFF) st = MISTI_OK;  // parked by the previous pass, advanced by misti_stiff_kernel
+        int st = out.status[b];
         double raw_c, jn_c;
         int nt = 0;
         const double cp[3] = {cpost[b], cpost[stride + b], cpost[2 * stride + b]};
         const int js = misti::jsfs_item<misti::HalfWarpLanes>(g, L, md, has && st == MISTI_OK, params + (long)b * P,
                                                               rec + (long)b * seg_cap * misti::kRecSlots, nseg[b], cp, &raw_c, &nt,
-                                                              conts ? conts + b : nullptr, resume);
-        const bool fin = misti::jafs_finish(g, ysm, &raw_c, unfolded != 0, &jn_c);  // all lanes, also of a group without an item
+                                                              conts + b, false);
+        const bool fin = misti::jafs_finish(g, ysm, &raw_c, out.unfolded != 0, &jn_c);  // all lanes, also of a group without an item
         if (!has) continue;
         if (st == MISTI_OK) st = js;
-        if (st == MISTI_STIFF && conts && next_list) {  // parked: queue it for the dense step; results come from a later pass
-            if (lane == 0) next_list[atomicAdd(next_count, 1)] = b;
+        if (st == MISTI_STIFF) {  // parked at a stiff segment: misti_stiff_kernel takes the item from here and emits its results
+            if (lane == 0) {
+                out.status[b] = MISTI_STIFF;
+                park_list[atomicAdd(park_count, 1)] = b;
+            }
+            continue;
         }
         if (st == MISTI_OK && !fin) st = MISTI_NONFINITE;
-        if (lane == 0) {
-            status[b] = st;
-            if (terms) terms[b] = nt;
-        }
-        if (lane < 7) {
-            if (jafs) jafs[(long)b * 7 + lane] = st == MISTI_OK ? jn_c : nan("");
-            if (jafs_raw) jafs_raw[(long)b * 7 + lane] = st == MISTI_OK ? raw_c : nan("");
-        }
-        // fused composite likelihood over all data rows (bootstrap replicates): lanes stride the rows
-        const double bad = (st == MISTI_NEGATIVE_PARAM || st == MISTI_CORRECTION_FAILED) ? -misti::kInf : nan("");
-        const double* logj = ysm + misti::kTailLog;
-        if (row_ids) {  // one data row per item
-            const int r = row_ids[b];
-            if (lane == 0) llh[b] = (st == MISTI_OK && r >= 0 && r < R) ? misti::score_row(data + 8 * (long)r, logj) : bad;
-        } else {
-            for (int r = lane; r < R; r += 16)
-                llh[(long)b * R + r] = st == MISTI_OK ? misti::score_row(data + 8 * (long)r, logj) : bad;
-        }
+        emit_item(out, ysm, lane, b, st, raw_c, jn_c, nt);
     }
 }
 
@@ -182,10 +193,11 @@ misti_jsfs_kernel(int B, int P, const double* __restrict__ params, const int* __
 // products) is summed in shared memory, then squared s times with FP64 tensor-core MMAs (mma.sync m8n8k4.f64,
 // "DMMA").  Every matrix stays non-negative, so the squarings are free of cancellation.  Then
 // P1 = E11 P0 and integralP = last column of E (MigrationInference.SolveDifEq, :530-540).
+// After the stiff segment(s) the first warp of the block resumes the item's sweep (misti::jsfs_item from the continuation
+// record) and emits its results; should the item meet another stiff segment, the block takes the dense step again.
 // ------------------------------------------------------------------------------------------------
 constexpr int kStiffThreads = 128;
 constexpr int kStiffBlocksPerSm = 3;  // 59 KB of shared memory each
-constexpr int kStiffRounds = 2;    // an item may be parked (and resumed) this many times per evaluation
 constexpr int kLd = 52;  // leading dimension of the 48x48 matrices in shared memory: with 52 = 4 mod 16 the 16 lanes of a
                          // half warp read 16 different bank pairs for both MMA operands (row gid, column tig and vice versa)
 
@@ -227,12 +239,14 @@ __device__ void dense_square(const double* __restrict__ A, double* __restrict__ 
         }
 }
 
-__global__ void __launch_bounds__(kStiffThreads)
+__global__ void __launch_bounds__(kStiffThreads, kStiffBlocksPerSm)
 misti_stiff_kernel(int P, const double* __restrict__ params, const int* __restrict__ model_ids, int model_default,
                    const ModelDesc* __restrict__ models, const double* __restrict__ times, const double* __restrict__ lc,
                    long stride, const double* __restrict__ rec, int seg_cap, const int* __restrict__ nseg,
-                   misti::Cont* __restrict__ conts, const int* __restrict__ item_list, const int* __restrict__ item_count,
-                   int* __restrict__ status) {
+                   const double* __restrict__ cpost, ItemOut out, misti::Cont* __restrict__ conts,
+                   const int* __restrict__ item_list, const int* __restrict__ item_count) {
+    const int n_items = *item_count;
+    if (n_items == 0) return;  // the usual case: nothing was parked
     extern __shared__ double sm[];
     double* E = sm;                      // [48][kLd]
     double* Y = sm + 48 * kLd;           // [48][kLd]
@@ -243,10 +257,16 @@ misti_stiff_kernel(int P, const double* __restrict__ params, const int* __restri
     for (int i = threadIdx.x; i < 44 * 4; i += kStiffThreads) colo[i] = misti::d_ell[i >> 2][i & 3].col * kLd;
     __syncthreads();
     __shared__ double s_scal[4];
-    __shared__ int s_flag[2];
-    (void)s_scal;
+    __shared__ int s_flag[3];
+    // the resuming sweep runs in warp 0 (its first half warp owns the item, the second idles)
+    __shared__ double s_ysm[2][misti::kGroupScratch];
+    __shared__ misti::RunTable<misti::HalfWarpLanes> runtab;
+    runtab.fill(threadIdx.x, blockDim.x);
+    __syncthreads();
     const int tid = threadIdx.x;
-    const int n_items = *item_count;
+    const misti::HalfWarpLanes g;
+    misti::LaneCtx<misti::HalfWarpLanes> L;
+    if (tid < 32) L.init(g, s_ysm[tid >> 4], &runtab);
     for (int i = blockIdx.x; i < n_items; i += gridDim.x) {
         const int b = item_list[i];
         const ModelDesc& md = models[model_ids ? model_ids[b] : model_default];
@@ -255,9 +275,11 @@ misti_stiff_kernel(int P, const double* __restrict__ params, const int* __restri
         misti::Cont* ct = conts + b;
         const double* rb = rec + (long)b * seg_cap * misti::kRecSlots;
         const int ns = nseg[b];
+      for (int round = 0; round <= ns; ++round) {  // dense step(s), then resume; again if the sweep parks the item once more
         int seg = ct->seg;
         int nterms = ct->nterms;
         if (tid < 48) Pv[tid] = ct->P[tid];
+        if (tid == 0) s_flag[2] = 0;
         __syncthreads();
         int st = MISTI_OK;
         while (seg < ns) {  // the stiff segment the item was parked at, and any that follow it directly
@@ -402,9 +424,30 @@ misti_stiff_kernel(int P, const double* __restrict__ params, const int* __restri
         if (tid == 0) {
             ct->seg = seg;
             ct->nterms = nterms;
-            if (st != MISTI_OK) status[b] = st;
+        }
+        __syncthreads();  // the continuation record is complete (block-wide visibility of the global stores)
+        if (tid < 32) {
+            const int lane = tid & 15;
+            const bool mine = tid < 16;
+            double raw_c, jn_c;
+            int nt = 0;
+            const double cp[3] = {cpost[b], cpost[stride + b], cpost[2 * stride + b]};
+            int js = misti::jsfs_item<misti::HalfWarpLanes>(g, L, md, mine && st == MISTI_OK, par, rb, ns, cp, &raw_c, &nt, ct, true);
+            const bool fin = misti::jafs_finish(g, s_ysm[tid >> 4], &raw_c, out.unfolded != 0, &jn_c);
+            if (mine) {
+                if (st != MISTI_OK) js = st;
+                if (js == MISTI_STIFF && round < ns) {
+                    if (lane == 0) s_flag[2] = 1;  // parked again at a later stiff segment
+                } else {
+                    if (js == MISTI_OK && !fin) js = MISTI_NONFINITE;
+                    emit_item(out, s_ysm[0], lane, b, js, raw_c, jn_c, nt);
+                }
+            }
         }
         __syncthreads();
+        if (!s_flag[2]) break;
+        __syncthreads();
+      }
     }
 }
 
@@ -869,45 +912,36 @@ static int eval_chunk(misti_ctx* ctx, int B, int P, const double* d_params, cons
     CK(cudaGetLastError());
     CK(cudaEventRecord(ctx->ev[1], ctx->stream));
     int blocks = (B + 2 * kJsfsWarps - 1) / (2 * kJsfsWarps);
-    const int per_sm = (ctx->jsfs_minb >= 2 && ctx->jsfs_minb <= 5 && ctx->jsfs_minb != 4) ? ctx->jsfs_minb
-                       : (ctx->jsfs_minb == 4 ? 4 : kJsfsMinBlocks);
+    const int per_sm = (ctx->jsfs_minb >= 2 && ctx->jsfs_minb <= 5) ? ctx->jsfs_minb : kJsfsMinBlocks;
     const int max_blocks = ctx->sm_count * per_sm;  // persistent grid: exactly the blocks that are resident together
     if (blocks > max_blocks) blocks = max_blocks;
     CK(cudaMemsetAsync(ctx->d_counts, 0, 8 * sizeof(int), ctx->stream));
-#define MISTI_LAUNCH_JSFS(MINB, GRID, LIST, COUNT, NEXT, NEXTCOUNT, WORK)                                                       \
-    misti_jsfs_kernel<MINB><<<GRID, kJsfsWarps * 32, 0, ctx->stream>>>(                                                   \
+    ItemOut out;
+    out.data = ctx->d_data; out.R = ctx->R; out.unfolded = ctx->unfolded;
+    out.llh = d_llh; out.jafs = d_jafs; out.jafs_raw = d_jafs_raw; out.status = ctx->d_status; out.terms = d_terms;
+    out.row_ids = d_row_ids;
+#define MISTI_LAUNCH_JSFS(MINB)                                                                                            \
+    misti_jsfs_kernel<MINB><<<blocks, kJsfsWarps * 32, 0, ctx->stream>>>(                                                  \
         B, P, d_params, d_model_ids, model_default, ctx->d_models, ctx->d_rec, ctx->cap_seg, ctx->d_nseg, stride, ctx->d_cpost, \
-        ctx->d_data, \
-        ctx->R, ctx->unfolded, d_llh, d_jafs, d_jafs_raw, ctx->d_status, d_terms, d_row_ids, ctx->d_conts, LIST, COUNT, NEXT, \
-        NEXTCOUNT, WORK)
-#define MISTI_LAUNCH_JSFS_ANY(GRID, LIST, COUNT, NEXT, NEXTCOUNT, WORK)                                                          \
-    switch (ctx->jsfs_minb) { /* register budget: 2 -> 255, 3 -> 168, 4 -> 128, 5 -> 96 (tuning knob MISTI_JSFS_MINB) */   \
-        case 2: MISTI_LAUNCH_JSFS(2, GRID, LIST, COUNT, NEXT, NEXTCOUNT, WORK); break;                                           \
-        case 3: MISTI_LAUNCH_JSFS(3, GRID, LIST, COUNT, NEXT, NEXTCOUNT, WORK); break;                                           \
-        case 5: MISTI_LAUNCH_JSFS(5, GRID, LIST, COUNT, NEXT, NEXTCOUNT, WORK); break;                                           \
-        default: MISTI_LAUNCH_JSFS(kJsfsMinBlocks, GRID, LIST, COUNT, NEXT, NEXTCOUNT, WORK); break;                             \
+        out, ctx->d_conts, ctx->d_queue[0], ctx->d_counts, ctx->d_counts + 4)
+    switch (ctx->jsfs_minb) {  // register budget: 2 -> 255, 3 -> 168, 4 -> 128, 5 -> 96 (tuning knob MISTI_JSFS_MINB)
+        case 2: MISTI_LAUNCH_JSFS(2); break;
+        case 4: MISTI_LAUNCH_JSFS(4); break;
+        case 5: MISTI_LAUNCH_JSFS(5); break;
+        default: MISTI_LAUNCH_JSFS(kJsfsMinBlocks); break;
     }
-    // pass 0: every item; items that meet a stiff interval are parked in queue 0
-    MISTI_LAUNCH_JSFS_ANY(blocks, (const int*)nullptr, (const int*)nullptr, ctx->d_queue[0], ctx->d_counts, ctx->d_counts + 4);
-    CK(cudaGetLastError());
-    ctx->launches += 1;
-    // stiff rounds: dense scaling-and-squaring step for the parked items, then resume the sweep for them.  The grids
-    // are fixed; with an empty queue (the usual case) both kernels return at once.
-    for (int r = 0; r < kStiffRounds; ++r) {
-        misti_stiff_kernel<<<ctx->sm_count * kStiffBlocksPerSm, kStiffThreads, kStiffSmem, ctx->stream>>>(
-            P, d_params, d_model_ids, model_default, ctx->d_models, ctx->d_times, ctx->d_lc, stride, ctx->d_rec, ctx->cap_seg,
-            ctx->d_nseg, ctx->d_conts, ctx->d_queue[r & 1], ctx->d_counts + r, ctx->d_status);
-        CK(cudaGetLastError());
-        MISTI_LAUNCH_JSFS_ANY(ctx->sm_count * 2, (const int*)ctx->d_queue[r & 1], (const int*)(ctx->d_counts + r),
-                              ctx->d_queue[(r + 1) & 1], ctx->d_counts + r + 1, ctx->d_counts + 5 + r);
-        CK(cudaGetLastError());
-        ctx->launches += 2;
-    }
-#undef MISTI_LAUNCH_JSFS_ANY
 #undef MISTI_LAUNCH_JSFS
+    CK(cudaGetLastError());
+    // items parked at a stiff segment (usually none: the kernel then returns at once): dense scaling-and-squaring step,
+    // rest of the sweep and results, one block per item
+    misti_stiff_kernel<<<ctx->sm_count * kStiffBlocksPerSm, kStiffThreads, kStiffSmem, ctx->stream>>>(
+        P, d_params, d_model_ids, model_default, ctx->d_models, ctx->d_times, ctx->d_lc, stride, ctx->d_rec, ctx->cap_seg,
+        ctx->d_nseg, ctx->d_cpost, out, ctx->d_conts, ctx->d_queue[0], ctx->d_counts);
+    CK(cudaGetLastError());
+    ctx->launches += 2;
     CK(cudaEventRecord(ctx->ev[2], ctx->stream));
     ctx->ev_valid = true;
-    ctx->launches += 1;
+    ctx->launches += 1;  // the correction kernel
     if (d_lc_out) {
         const long n = (long)B * 2 * numT_max;
         misti_gather_lc_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(B, numT_max, d_model_ids, model_default,
