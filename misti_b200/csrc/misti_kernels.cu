@@ -54,8 +54,9 @@ misti_correct_kernel(int B, int P, const double* __restrict__ params, const int*
                      const ModelDesc* __restrict__ models, const double* __restrict__ times, const double* __restrict__ lh,
                      const double* __restrict__ gaux, const unsigned* __restrict__ cls_all, unsigned flags, double mixtureTH, const double* __restrict__ lc_inject, int numT_max, double* lc,
                      long stride, double* __restrict__ cpost, double* pr_out, int* __restrict__ status, int* __restrict__ nfev,
-                     double* __restrict__ rec, int seg_cap, int* __restrict__ nseg) {
+                     double* __restrict__ rec, int seg_cap, int* __restrict__ nseg, int* __restrict__ counters) {
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gtid < 8) counters[gtid] = 0;  // work and park counters of the two kernels that follow in the stream
     const int b = COOP ? gtid >> 2 : gtid;
     // one model for the whole batch (the usual case): its descriptor is staged in shared memory once per block
     __shared__ ModelDesc smd;
@@ -901,7 +902,7 @@ static int eval_chunk(misti_ctx* ctx, int B, int P, const double* d_params, cons
     misti_correct_kernel<MINB, COOP><<<(unsigned)(((NTHREADS) + kCorrectThreads - 1) / kCorrectThreads), kCorrectThreads, 0, ctx->stream>>>( \
         B, P, d_params, d_model_ids, model_default, ctx->d_models, ctx->d_times, ctx->d_lh, ctx->d_gaux, ctx->d_cls, flags, mixture_th, \
         d_lc_inject, \
-        numT_max, ctx->d_lc, stride, ctx->d_cpost, d_pr, ctx->d_status, ctx->d_nfev, ctx->d_rec, ctx->cap_seg, ctx->d_nseg)
+        numT_max, ctx->d_lc, stride, ctx->d_cpost, d_pr, ctx->d_status, ctx->d_nfev, ctx->d_rec, ctx->cap_seg, ctx->d_nseg, ctx->d_counts)
     switch (ctx->correct_minb) {  // register budget per thread: 4 -> 255, 8 -> 128, 12 -> 80 (tuning knob MISTI_CORRECT_MINB)
         case 4: MISTI_LAUNCH_CORRECT(4); break;
         case 12: MISTI_LAUNCH_CORRECT(12); break;
@@ -915,7 +916,6 @@ static int eval_chunk(misti_ctx* ctx, int B, int P, const double* d_params, cons
     const int per_sm = (ctx->jsfs_minb >= 2 && ctx->jsfs_minb <= 5) ? ctx->jsfs_minb : kJsfsMinBlocks;
     const int max_blocks = ctx->sm_count * per_sm;  // persistent grid: exactly the blocks that are resident together
     if (blocks > max_blocks) blocks = max_blocks;
-    CK(cudaMemsetAsync(ctx->d_counts, 0, 8 * sizeof(int), ctx->stream));
     ItemOut out;
     out.data = ctx->d_data; out.R = ctx->R; out.unfolded = ctx->unfolded;
     out.llh = d_llh; out.jafs = d_jafs; out.jafs_raw = d_jafs_raw; out.status = ctx->d_status; out.terms = d_terms;
