@@ -78,18 +78,62 @@ MISTI_HD inline void interval_rates(const ModelDesc& md, const unsigned* cls, co
     }
 }
 
+// Post-split rates in cpfit mode (MigrationInference.py:356-374) and, with them, the post-split closed-form coefficients
+// cpost[3] (see post_split_coeffs in misti_jsfs.cuh).  nc0, nc1 = the reference's running "log probabilities" at the split.
+// pnc_t = (exp(-T lh0) + exp((nc1 - nc0) - T lh1)) / (1 + exp(nc1 - nc0)), lam_t = -log(pnc_t) / T, and nc0, nc1 both drop
+// by T lam_t -- so d = nc1 - nc0 never changes and the intervals are independent of each other:
+// pnc_t = (E0_t + e^d E1_t) / (1 + e^d) with the grid constants E_g = exp(-T lh_g).  The last rate
+// (pr0 + pr1) / (pr0 / lh0 + pr1 / lh1), pr_k = exp(nc_k), is (1 + e^d) / (1 / lh0 + e^d / lh1).
+MISTI_HD inline void post_split_cpfit_item(const ModelDesc& md, const double* times, const double* lh, double nc0, double nc1,
+                                           double* lc, int pitch, long stride, const double* gaux, double* cpost) {
+    const int numT = md.numT, splitT = md.splitT;
+    if (!(splitT < numT)) return;
+    const double ed = exp(nc1 - nc0), wn = 1.0 / (1.0 + ed);
+    double c6 = 0, c3 = 0, c1 = 0, e1 = 1.0;  // e1 = exp(-sum of lam T so far)
+    for (int t = splitT; t < numT - 1; ++t) {
+        const double T = times[t];
+        if (T == 0) { lc[(pitch * t) * stride] = 1; lc[(pitch * t + 1) * stride] = 1; continue; }
+        double ga[kGridAux];
+        if (gaux) { for (int i = 0; i < kGridAux; ++i) ga[i] = gaux[kGridAux * t + i]; }
+        else grid_aux_row(lh + 2 * t, T, ga);
+        const double u = (ga[0] + ed * ga[1]) * wn;   // pnc = exp(-lam T)
+        const double q1 = (ga[2] + ed * ga[3]) * wn;  // 1 - pnc, free of cancellation
+        const double z = -log(u);
+        const double lam = z * ga[4];
+        lc[(pitch * t) * stride] = lam;
+        lc[(pitch * t + 1) * stride] = lam;
+        const double il = z > 0 ? T / z : 0.0;  // 1 / lam
+        const double e3 = e1 * e1 * e1;
+        const double q3 = q1 * (1.0 + u + u * u), q6 = q3 * (1.0 + u * u * u);  // 1 - u^3, 1 - u^6
+        c1 += z > 0 ? e1 * q1 * il : e1 * T;
+        c3 += z > 0 ? e3 * q3 * (il * (1.0 / 3.0)) : e3 * T;
+        c6 += z > 0 ? (e3 * e3) * q6 * (il * (1.0 / 6.0)) : (e3 * e3) * T;
+        e1 *= u;
+    }
+    {
+        const int t = numT - 1;
+        const double lam = (1.0 + ed) / (1.0 / lh[2 * t] + ed / lh[2 * t + 1]);
+        lc[(pitch * t) * stride] = lam;
+        lc[(pitch * t + 1) * stride] = lam;
+        const double il = 1.0 / lam, e3 = e1 * e1 * e1;
+        c1 += e1 * il; c3 += e3 * (il * (1.0 / 3.0)); c6 += (e3 * e3) * (il * (1.0 / 6.0));
+    }
+    if (cpost) { cpost[0] = c6; cpost[1] = c3; cpost[2] = c1; }
+}
+
 // lc is addressed as lc[(pitch*t+g)*stride] (pitch >= 2 values per interval); times[numT-1]; lh[numT][2].
 // Pr (nullable): [splitT+1][3][2] trajectory of the 3-state chains (MigrationInference.py:309,350).
 // gaux (nullable): [numT][kGridAux] per-interval constants of the grid (grid_aux_row).
 // cpost (nullable): in cpfit mode the post-split closed-form coefficients (see post_split_coeffs in misti_jsfs.cuh)
 // fall out of the post-split pass for free (exp(-lam T) is the fitted non-coalescence probability itself);
 // *cpost_done tells the caller whether they were written.
+// nc_out (nullable): in cpfit mode do NOT run the post-split pass here but return nc0, nc1 for post_split_cpfit_item.
 // COOP (device only): four lanes run the item together, see eval_fj in misti_math.cuh.
 template <bool COOP = false>
 MISTI_HD inline int correct_lambdas_item(const ModelDesc& md, const double* times, const double* lh, const double* params,
                                          unsigned flags, double mixtureTH, double* lc, int pitch, long stride, double* Pr,
                                          int* nfev_out, const double* gaux = nullptr, double* cpost = nullptr,
-                                         bool* cpost_done = nullptr, const unsigned* cls = nullptr) {
+                                         bool* cpost_done = nullptr, const unsigned* cls = nullptr, double* nc_out = nullptr) {
     if (cpost_done) *cpost_done = false;
     const bool correct = flags & MISTI_FLAG_CORRECT, cpfit = flags & MISTI_FLAG_CPFIT;
     int nfev = 0;
@@ -171,43 +215,11 @@ MISTI_HD inline int correct_lambdas_item(const ModelDesc& md, const double* time
         for (int i = sr1.k; i < splitT; ++i) lc[(pitch * i + 1) * stride] = avg;
     }
     if (cpfit && splitT < numT) {
-        // Post-split rates, cpfit mode (:356-374): pnc_t = (exp(-T lh0) + exp((nc1 - nc0) - T lh1)) / (1 + exp(nc1 - nc0)),
-        // lam_t = -log(pnc_t) / T, and nc0, nc1 both drop by T lam_t -- so d = nc1 - nc0 never changes and the intervals are
-        // independent of each other: pnc_t = (E0_t + e^d E1_t) / (1 + e^d) with the grid constants E_g = exp(-T lh_g).
-        // The last rate (pr0 + pr1) / (pr0 / lh0 + pr1 / lh1), pr_k = exp(nc_k), is (1 + e^d) / (1 / lh0 + e^d / lh1).
-        const double ed = exp(nc1 - nc0), wn = 1.0 / (1.0 + ed);
-        double c6 = 0, c3 = 0, c1 = 0, e1 = 1.0;  // e1 = exp(-sum of lam T so far)
-        for (int t = splitT; t < numT - 1; ++t) {
-            const double T = times[t];
-            if (T == 0) { lc[(pitch * t) * stride] = 1; lc[(pitch * t + 1) * stride] = 1; continue; }
-            double ga[kGridAux];
-            if (gaux) { for (int i = 0; i < kGridAux; ++i) ga[i] = gaux[kGridAux * t + i]; }
-            else grid_aux_row(lh + 2 * t, T, ga);
-            const double u = (ga[0] + ed * ga[1]) * wn;   // pnc = exp(-lam T)
-            const double q1 = (ga[2] + ed * ga[3]) * wn;  // 1 - pnc, free of cancellation
-            const double z = -log(u);
-            const double lam = z * ga[4];
-            lc[(pitch * t) * stride] = lam;
-            lc[(pitch * t + 1) * stride] = lam;
-            const double il = z > 0 ? T / z : 0.0;  // 1 / lam
-            const double e3 = e1 * e1 * e1;
-            const double q3 = q1 * (1.0 + u + u * u), q6 = q3 * (1.0 + u * u * u);  // 1 - u^3, 1 - u^6
-            c1 += z > 0 ? e1 * q1 * il : e1 * T;
-            c3 += z > 0 ? e3 * q3 * (il * (1.0 / 3.0)) : e3 * T;
-            c6 += z > 0 ? (e3 * e3) * q6 * (il * (1.0 / 6.0)) : (e3 * e3) * T;
-            e1 *= u;
-        }
-        {
-            const int t = numT - 1;
-            const double lam = (1.0 + ed) / (1.0 / lh[2 * t] + ed / lh[2 * t + 1]);
-            lc[(pitch * t) * stride] = lam;
-            lc[(pitch * t + 1) * stride] = lam;
-            const double il = 1.0 / lam, e3 = e1 * e1 * e1;
-            c1 += e1 * il; c3 += e3 * (il * (1.0 / 3.0)); c6 += (e3 * e3) * (il * (1.0 / 6.0));
-        }
-        if (cpost) {
-            cpost[0] = c6; cpost[1] = c3; cpost[2] = c1;
-            if (cpost_done) *cpost_done = true;
+        if (nc_out) {  // the caller runs the post-split pass elsewhere (post_split_cpfit_item)
+            nc_out[0] = nc0; nc_out[1] = nc1;
+        } else {
+            post_split_cpfit_item(md, times, lh, nc0, nc1, lc, pitch, stride, gaux, cpost);
+            if (cpost && cpost_done) *cpost_done = true;
         }
     } else {
         for (int t = splitT; t < numT - 1; ++t) {
