@@ -282,6 +282,7 @@ struct SingleLane {  // test-only host build: one lane owns all 44 rows, every o
     MISTI_HD int lane() const { return 0; }
     MISTI_HD void sync() const {}
     MISTI_HD double sum(double v) const { return v; }
+    MISTI_HD double excl_prod(double) const { return 1.0; }
     MISTI_HD int wmax(int v) const { return v; }
     MISTI_HD int wmin(int v) const { return v; }
     MISTI_HD bool any(bool v) const { return v; }
@@ -325,6 +326,15 @@ struct HalfWarpLanes {  // two items per warp; each lane of a 16-lane half owns 
     __device__ double sum(double v) const {  // within the half
         for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
         return v;
+    }
+    __device__ double excl_prod(double v) const {  // product of v over the lower lanes of the half (1 for lane 0)
+        const int lane = threadIdx.x & 15;
+        for (int o = 1; o < 16; o <<= 1) {
+            const double t = __shfl_up_sync(0xffffffffu, v, o, 16);
+            if (lane >= o) v *= t;
+        }
+        const double e = __shfl_up_sync(0xffffffffu, v, 1, 16);
+        return lane == 0 ? 1.0 : e;
     }
     __device__ int wmax(int v) const {  // over the whole warp (both items); v is uniform within a half
         const int o = __shfl_xor_sync(0xffffffffu, v, 16);
@@ -385,6 +395,54 @@ MISTI_HD inline void post_split_coeffs(const ModelDesc& md, const double* times,
         }
     }
     cpost[0] = c6; cpost[1] = c3; cpost[2] = c1;
+}
+
+// The same coefficients in cpfit mode, straight from ed = exp(nc1 - nc0) of the correction chain (see
+// post_split_cpfit_item in misti_model.cuh: the post-split intervals are independent of each other given ed), by ALL lanes
+// of a group together: lane l takes the `per` consecutive intervals of its slice of the model's table (post_split_table:
+// tab[(k per + j) LANES + l]), accumulates its partial sums relative to the start of the slice, the survival factors
+// exp(-x) at the slice starts come from one exclusive scan over the lanes, and the last lane adds the infinite interval
+// (lh_last = PSMC rates of that interval).  Every lane returns the three sums.  Called by all lanes of the warp (`active`
+// = false for a group without an item: it runs along with neutral values).
+template <class G>
+MISTI_D inline void post_split_cpfit_group(const G& g, bool active, const double* tab, int per, const double* lh_last, double ed,
+                                           double* cpost) {
+    const int lane = g.lane();
+    const int per_own = active ? per : 0;
+    const int per_max = g.wmax(per_own);
+    const double wn = 1.0 / (1.0 + ed);
+    double c6 = 0, c3 = 0, c1 = 0, e1 = 1.0;  // relative to the start of this lane's slice
+    // the loads of step j + 1 are in flight while step j is computed (the table may sit in global memory)
+    const long ks = (long)per * G::LANES;
+    const double* q = tab + lane;
+    double nE0 = 1.0, nE1 = 1.0, nQ0 = 0.0, nQ1 = 0.0, nT = 0.0;
+    if (0 < per_own) { nE0 = q[0]; nE1 = q[ks]; nQ0 = q[2 * ks]; nQ1 = q[3 * ks]; nT = q[4 * ks]; }
+    for (int j = 0; j < per_max; ++j) {
+        const double E0 = nE0, E1 = nE1, Q0 = nQ0, Q1 = nQ1, T = nT;
+        nE0 = 1.0; nE1 = 1.0; nQ0 = 0.0; nQ1 = 0.0; nT = 0.0;
+        if (j + 1 < per_own) {
+            q += G::LANES;
+            nE0 = q[0]; nE1 = q[ks]; nQ0 = q[2 * ks]; nQ1 = q[3 * ks]; nT = q[4 * ks];
+        }
+        const double u = (E0 + ed * E1) * wn;   // exp(-lam T), the fitted non-coalescence probability
+        const double q1 = (Q0 + ed * Q1) * wn;  // 1 - u, free of cancellation
+        const double z = -log(u);
+        const double il = z > 0 ? T / z : 0.0;  // 1 / lam
+        const double e3 = e1 * e1 * e1;
+        const double q3 = q1 * (1.0 + u + u * u), q6 = q3 * (1.0 + u * u * u);  // 1 - u^3, 1 - u^6
+        c1 += z > 0 ? e1 * q1 * il : e1 * T;
+        c3 += z > 0 ? e3 * q3 * (il * (1.0 / 3.0)) : e3 * T;
+        c6 += z > 0 ? (e3 * e3) * q6 * (il * (1.0 / 6.0)) : (e3 * e3) * T;
+        e1 *= u;
+    }
+    const double f1 = g.excl_prod(e1), f3 = f1 * f1 * f1;
+    c1 *= f1; c3 *= f3; c6 *= f3 * f3;
+    if (active && lane == G::LANES - 1) {  // the infinite last interval
+        const double lam = (1.0 + ed) / (1.0 / lh_last[0] + ed / lh_last[1]);
+        const double il = 1.0 / lam, x1 = f1 * e1, x3 = x1 * x1 * x1;
+        c1 += x1 * il; c3 += x3 * (il * (1.0 / 3.0)); c6 += (x3 * x3) * (il * (1.0 / 6.0));
+    }
+    cpost[0] = g.sum(c6); cpost[1] = g.sum(c3); cpost[2] = g.sum(c1);
 }
 
 // The zero-migration run table as the lane groups use it.  Any lane may compute any row (inputs and outputs go through

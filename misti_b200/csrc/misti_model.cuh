@@ -4,6 +4,7 @@
 // Reference: MigrationInference.SetModel / MapParameters (MigrationInference.py:229-298),
 // CorrectLambdas (:305-378), SmoothConst (:387-405).
 #pragma once
+#include <stddef.h>
 #include "misti_math.cuh"
 
 #include "../../include/misti_b200.h"  // flags, status codes and capacity limits are part of the C ABI
@@ -19,6 +20,8 @@ struct ModelDesc {
     int n_params;
     int grid_off;    // offset of this model's grid inside the pooled arrays (in intervals)
     int cls_off;     // offset of this model's interval classes inside the pooled class array (see interval_class)
+    int post_off;    // offset (in doubles) of this model's post-split table inside the pooled table array (post_split_table)
+    int post_per;    // post-split intervals per lane of a 16-lane group in that table
     int band_pop[MISTI_MAX_BANDS], band_start[MISTI_MAX_BANDS], band_end[MISTI_MAX_BANDS], band_opt[MISTI_MAX_BANDS];
     int pulse_pop[MISTI_MAX_PULSES], pulse_time[MISTI_MAX_PULSES], pulse_opt[MISTI_MAX_PULSES];
     double band_val[MISTI_MAX_BANDS];
@@ -84,6 +87,14 @@ MISTI_HD inline void interval_rates(const ModelDesc& md, const unsigned* cls, co
 // by T lam_t -- so d = nc1 - nc0 never changes and the intervals are independent of each other:
 // pnc_t = (E0_t + e^d E1_t) / (1 + e^d) with the grid constants E_g = exp(-T lh_g).  The last rate
 // (pr0 + pr1) / (pr0 / lh0 + pr1 / lh1), pr_k = exp(nc_k), is (1 + e^d) / (1 / lh0 + e^d / lh1).
+// One post-split rate of that pass, from ed = exp(nc1 - nc0) (`ga` = grid_aux_row of interval t, T its length)
+MISTI_HD inline double post_split_cpfit_rate(const ModelDesc& md, int t, double T, const double* ga, const double* lh, double ed) {
+    if (t == md.numT - 1) return (1.0 + ed) / (1.0 / lh[2 * t] + ed / lh[2 * t + 1]);
+    if (T == 0) return 1.0;
+    const double u = (ga[0] + ed * ga[1]) * (1.0 / (1.0 + ed));
+    return -log(u) * ga[4];
+}
+
 MISTI_HD inline void post_split_cpfit_item(const ModelDesc& md, const double* times, const double* lh, double nc0, double nc1,
                                            double* lc, int pitch, long stride, const double* gaux, double* cpost) {
     const int numT = md.numT, splitT = md.splitT;
@@ -121,13 +132,38 @@ MISTI_HD inline void post_split_cpfit_item(const ModelDesc& md, const double* ti
     if (cpost) { cpost[0] = c6; cpost[1] = c3; cpost[2] = c1; }
 }
 
+// The finite post-split intervals of a model as the lane groups of the JSFS kernel read them (post_split_cpfit_group in
+// misti_jsfs.cuh): lane l of `lanes` owns the `per` consecutive intervals splitT + l per + j, j < per, and value k
+// (E0, E1, 1 - E0, 1 - E1 of grid_aux_row, and T) of its j-th interval sits at out[(k per + j) lanes + l] -- one coalesced
+// load per value and step.  Slots past the last finite interval and zero-length intervals (skipped by the reference,
+// MigrationInference.py:358-360) hold the neutral entry E = 1, 1 - E = 0, T = 0.
+constexpr int kPostVals = 5;
+MISTI_HD inline int post_split_per(int numT, int splitT, int lanes) {
+    const int n = splitT < numT ? numT - 1 - splitT : 0;
+    return (n + lanes - 1) / lanes;
+}
+inline void post_split_table(int numT, int splitT, const double* times, const double* gaux, int lanes, double* out) {
+    const int per = post_split_per(numT, splitT, lanes);
+    for (int l = 0; l < lanes; ++l)
+        for (int j = 0; j < per; ++j) {
+            const int t = splitT + l * per + j;
+            const bool have = t < numT - 1 && times[t] != 0;
+            const double v[kPostVals] = {have ? gaux[kGridAux * t] : 1.0, have ? gaux[kGridAux * t + 1] : 1.0,
+                                         have ? gaux[kGridAux * t + 2] : 0.0, have ? gaux[kGridAux * t + 3] : 0.0,
+                                         have ? times[t] : 0.0};
+            for (int k = 0; k < kPostVals; ++k) out[((size_t)k * per + j) * lanes + l] = v[k];
+        }
+}
+
 // lc is addressed as lc[(pitch*t+g)*stride] (pitch >= 2 values per interval); times[numT-1]; lh[numT][2].
 // Pr (nullable): [splitT+1][3][2] trajectory of the 3-state chains (MigrationInference.py:309,350).
 // gaux (nullable): [numT][kGridAux] per-interval constants of the grid (grid_aux_row).
 // cpost (nullable): in cpfit mode the post-split closed-form coefficients (see post_split_coeffs in misti_jsfs.cuh)
 // fall out of the post-split pass for free (exp(-lam T) is the fitted non-coalescence probability itself);
 // *cpost_done tells the caller whether they were written.
-// nc_out (nullable): in cpfit mode do NOT run the post-split pass here but return nc0, nc1 for post_split_cpfit_item.
+// nc_out (nullable): in cpfit mode do NOT run the post-split pass here but return nc0, nc1 (and *cpost_done = true): the
+// caller has the pass done elsewhere (post_split_cpfit_group in the JSFS kernel; the post-split rates themselves are
+// then only computed on request, post_split_cpfit_rate).
 // COOP (device only): four lanes run the item together, see eval_fj in misti_math.cuh.
 template <bool COOP = false>
 MISTI_HD inline int correct_lambdas_item(const ModelDesc& md, const double* times, const double* lh, const double* params,
@@ -215,8 +251,9 @@ MISTI_HD inline int correct_lambdas_item(const ModelDesc& md, const double* time
         for (int i = sr1.k; i < splitT; ++i) lc[(pitch * i + 1) * stride] = avg;
     }
     if (cpfit && splitT < numT) {
-        if (nc_out) {  // the caller runs the post-split pass elsewhere (post_split_cpfit_item)
+        if (nc_out) {  // the caller has the post-split pass run elsewhere
             nc_out[0] = nc0; nc_out[1] = nc1;
+            if (cpost_done) *cpost_done = true;
         } else {
             post_split_cpfit_item(md, times, lh, nc0, nc1, lc, pitch, stride, gaux, cpost);
             if (cpost && cpost_done) *cpost_done = true;

@@ -95,4 +95,44 @@ int hs_jsfs(int numT, int splitT, int sampleDate, const double* times, int n_ban
     return MISTI_OK;
 }
 
+// cpfit post-split coefficients from ed = exp(nc1 - nc0): the sequential pass of the correction chain (seq[3], and the
+// rates lc[numT][2]) against the lane-group pass over the model's table (grp[3]; one lane here, 16 on the device, and
+// `lanes` only shapes the table: the slices are then walked one after the other), and the rate-on-request function
+void hs_post_split(int numT, int splitT, const double* times, const double* lh, double ed, int lanes, double* seq, double* grp,
+                   double* lc, double* lc_req) {
+    misti::ModelDesc md;
+    std::memset(&md, 0, sizeof(md));
+    md.numT = numT; md.splitT = splitT;
+    std::vector<double> gaux((size_t)numT * misti::kGridAux);
+    for (int t = 0; t < numT; ++t) misti::grid_aux_row(lh + 2 * t, t < numT - 1 ? times[t] : 0.0, &gaux[(size_t)t * misti::kGridAux]);
+    misti::post_split_cpfit_item(md, times, lh, 0.0, log(ed), lc, 2, 1, gaux.data(), seq);
+    for (int t = splitT; t < numT; ++t)
+        lc_req[t] = misti::post_split_cpfit_rate(md, t, t < numT - 1 ? times[t] : 0.0, &gaux[(size_t)t * misti::kGridAux], lh, ed);
+    // the table in the device layout, walked slice by slice: partial sums per slice, survival factors by running product
+    const int per = misti::post_split_per(numT, splitT, lanes);
+    std::vector<double> tab((size_t)misti::kPostVals * per * lanes + 1);
+    misti::post_split_table(numT, splitT, times, gaux.data(), lanes, tab.data());
+    misti::SingleLane g;
+    double f1 = 1.0;
+    grp[0] = grp[1] = grp[2] = 0.0;
+    for (int l = 0; l < lanes; ++l) {
+        // slice l as a one-lane table: value k of step j at sl[k per + j]
+        std::vector<double> sl((size_t)misti::kPostVals * per + 1);
+        for (int k = 0; k < misti::kPostVals; ++k)
+            for (int j = 0; j < per; ++j) sl[(size_t)k * per + j] = tab[((size_t)k * per + j) * lanes + l];
+        // a slice alone = a model whose "infinite interval" has rate 1/0: lh_last = inf keeps the last term out
+        double part[3];
+        const double lh_inf[2] = {1e300, 1e300};
+        misti::post_split_cpfit_group(g, true, sl.data(), per, lh_inf, ed, part);
+        double e1 = 1.0;
+        for (int j = 0; j < per; ++j) e1 *= (sl[j] + ed * sl[(size_t)per + j]) * (1.0 / (1.0 + ed));
+        const double f3 = f1 * f1 * f1;
+        grp[0] += f3 * f3 * part[0]; grp[1] += f3 * part[1]; grp[2] += f1 * part[2];
+        f1 *= e1;
+    }
+    const double lam = (1.0 + ed) / (1.0 / lh[2 * (numT - 1)] + ed / lh[2 * (numT - 1) + 1]);
+    const double f3 = f1 * f1 * f1;
+    grp[0] += f3 * f3 / (6.0 * lam); grp[1] += f3 / (3.0 * lam); grp[2] += f1 / lam;
+}
+
 }  // extern "C"

@@ -383,3 +383,45 @@ def test_cooperative_correction_kernel_is_bit_identical(golden_datasets):
         assert (a["status"] == 0).sum() > B // 2
         for k in ("status", "nfev", "lc", "llh", "jafs"):
             assert np.array_equal(a[k], b[k], equal_nan=True), k
+
+
+@pytest.mark.gpu
+def test_post_split_pass_in_the_jsfs_kernel(golden_datasets):
+    """cpfit mode: by default the post-split pass runs in the lane groups of the JSFS kernel (coefficients) and on request
+    only (rates); spectra, likelihoods and rates must agree with the sequential pass of the correction kernel
+    (MISTI_DEFER_POST=0) to rounding, over several split times (different slice lengths), with and without a sampling
+    date at the split."""
+    import os
+    import misti_b200
+    ds = golden_datasets["synthetic"]
+    rng = np.random.default_rng(11)
+    B = 203
+    params = np.column_stack([10 ** rng.uniform(-3, 0.7, B)])
+    res = {}
+    for defer in ("0", "1"):
+        os.environ["MISTI_DEFER_POST"] = defer
+        try:
+            eng = misti_b200.Engine(0)
+        finally:
+            del os.environ["MISTI_DEFER_POST"]
+        gid = eng.add_grid(ds["times"], ds["lambdas"])
+        numT = len(ds["lambdas"])
+        mids = [eng.add_model(gid, st, 0, bands=[(1, 5, min(12, st), 0.8, 0)]) for st in (13, 40, 41, 94, numT - 2, numT - 1)]
+        mids.append(eng.add_model(gid, numT, 0, bands=[(1, 5, numT, 0.8, 0)]))  # no split inside the grid
+        eng.set_data([ds["sfs"], ds["bs_rows"][1]], True)
+        models = np.array([mids[b % len(mids)] for b in range(B)], dtype=np.int32)
+        res[defer] = [eng.evaluate(params, model_ids=models, flags=1 | 2 | 4 | 8, want=("jafs", "lc", "status")),
+                      eng.evaluate(params, model_ids=models, flags=1 | 2 | 4 | 8, want=("status",)),
+                      # one model for the whole batch: its table is staged in shared memory
+                      eng.evaluate(params, model=mids[1], flags=1 | 2 | 4 | 8, want=("jafs", "lc", "status"))]
+        eng.close()
+    for k in (0, 2):
+        a, b = res["0"][k], res["1"][k]
+        assert np.array_equal(a["status"], b["status"])
+        ok = a["status"] == 0
+        assert ok.sum() > B // 2
+        assert relerr(b["jafs"][ok], a["jafs"][ok]) < 1e-13
+        assert relerr(b["llh"][ok], a["llh"][ok]) < 1e-12
+        assert relerr(b["lc"][ok], a["lc"][ok]) < 1e-13
+    # asking for the rates does not change the likelihoods
+    assert np.array_equal(res["1"][0]["llh"], res["1"][1]["llh"], equal_nan=True)

@@ -222,3 +222,25 @@ def test_split_at_the_ends_of_the_grid(hostsim, golden_datasets):
         rc, raw, jn, llh = _jsfs_random(hostsim, case, om.lc)
         assert rc == 0, (st, mi)
         assert relerr(jn, om.JAFS) < 1e-12 and relerr(llh, ref) < 1e-12, (st, mi)
+
+
+def test_post_split_pass_by_lane_groups(hostsim, golden_datasets):
+    """cpfit mode: the post-split coefficients summed slice by slice over the 16-lane table of a model (the JSFS kernel's
+    pass) equal the sequential pass of the correction chain (MigrationInference.py:356-374), and the rate computed on
+    request equals the rate that pass writes."""
+    ds = golden_datasets["synthetic"]
+    T0, L = _arr(ds["times"]), _arr(ds["lambdas"])
+    numT = len(L)
+    rng = np.random.default_rng(5)
+    for trial in range(40):
+        T = T0.copy()
+        splitT = int(rng.integers(1, numT))
+        if trial % 4 == 0 and splitT < numT - 1:
+            T[int(rng.integers(splitT, numT - 1))] = 0.0  # a zero-length interval is skipped (:358-360)
+        ed = float(np.exp(rng.uniform(-3, 3)))
+        for lanes in (1, 16):
+            seq, grp, lc, req = np.zeros(3), np.zeros(3), np.zeros((numT, 2)), np.zeros(numT)
+            hostsim.hs_post_split(numT, splitT, _p(T), _p(L), ctypes.c_double(ed), lanes, _p(seq), _p(grp), _p(lc), _p(req))
+            # (the sequential pass gets ed as exp(log(ed)): one rounding apart)
+            assert relerr(grp, seq) < 1e-13, (splitT, lanes, grp, seq)
+            assert relerr(req[splitT:], lc[splitT:, 0]) < 1e-13
