@@ -47,6 +47,7 @@ extern "C" {
 #define MISTI_CORRECTION_FAILED 2  /* "Lambda correction failed" (MigrationInference.py:575-578)              */
 #define MISTI_NONFINITE 3          /* the reference would have raised or produced NaN                         */
 #define MISTI_INFINITE_COAL_TIME 4 /* last interval before the split without migration (:475-476, ref. exits)  */
+#define MISTI_SKIPPED 6            /* item with model id -1: slot left empty by the on-device optimiser           */
 #define MISTI_STIFF 5              /* intervals WITH migration and (largest exit rate)*length > 256 are only seen after a
                                       run-away correction; they take a dense scaling-and-squaring step instead of
                                       the sweep (transparently: the item still ends with status 0).  The code is
@@ -124,6 +125,18 @@ int misti_set_data(misti_ctx* ctx, int32_t R, const double* sfs, const double* l
  * Replaces: one MigrationInference.JAFSLikelihood call per item per data row. */
 int misti_eval_batch(misti_ctx* ctx, int32_t B, int32_t P, const double* params, const int32_t* model_ids,
                      int32_t model_default, uint32_t flags, double mixture_th, double* llh, const misti_eval_io* io);
+
+/* Fit S independent (model, data row) pairs by Nelder-Mead ON THE DEVICE: every simplex takes the decisions of
+ * scipy.optimize.minimize(method='Nelder-Mead') as MigrationInference.Solve calls it (MigrationInference.py:718-729;
+ * scipy 1.18.1 _optimize.py:_minimize_neldermead), the objective is -llh of the pair's model against its data row, and
+ * a fit is a stream of launches (propose, evaluate, apply) without a host round trip per step.  Host pointers.
+ * x0[S][N] start vectors (N >= every model's n_params, N >= 1), model_ids[S], row_ids[S] (NULL = row 0);
+ * maxiter / maxfev < 0 = none.  Out: x[S][N] best vertex, fun[S] = -llh there, nit[S], nfev[S] (scipy's counts),
+ * status[S] (0 converged, 1 maxfev, 2 maxiter), info[2] = rounds of launches, points evaluated (nullable).
+ * Replaces: one MigrationInference.Solve (one MiSTI.py process in the reference's bootstrap loops) per pair. */
+int misti_nelder_mead(misti_ctx* ctx, int32_t S, int32_t N, const double* x0, const int32_t* model_ids, const int32_t* row_ids,
+                      uint32_t flags, double mixture_th, double xatol, double fatol, int64_t maxiter, int64_t maxfev,
+                      double* x, double* fun, int64_t* nit, int64_t* nfev, int32_t* status, int64_t* info);
 
 /* Score B given spectra (7 non-negative weights each, normalised on the device) against every data
  * row: llh[b*R + r].  Host pointers.  Replaces the likelihood tail used on its own, e.g.

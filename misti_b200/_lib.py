@@ -12,7 +12,7 @@ LIB_PATH = os.environ.get("MISTI_B200_LIB") or os.path.join(HERE, "libmisti_b200
 MAX_BANDS, MAX_PULSES, MAX_PARAMS = 8, 8, 16
 
 FLAG_CORRECT, FLAG_CPFIT, FLAG_SMOOTH, FLAG_UNFOLDED, FLAG_DEVICE_PTRS = 1, 2, 4, 8, 256
-OK, NEGATIVE_PARAM, CORRECTION_FAILED, NONFINITE, INFINITE_COAL_TIME, STIFF = 0, 1, 2, 3, 4, 5
+OK, NEGATIVE_PARAM, CORRECTION_FAILED, NONFINITE, INFINITE_COAL_TIME, STIFF, SKIPPED = 0, 1, 2, 3, 4, 5, 6
 E_ARG, E_CUDA, E_NODEV = -1, -2, -3
 
 c_double_p = ctypes.POINTER(ctypes.c_double)
@@ -54,6 +54,10 @@ SIGNATURES = {
     "misti_eval_batch": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p,
                                         ctypes.c_int32, ctypes.c_uint32, ctypes.c_double, ctypes.c_void_p,
                                         ctypes.POINTER(EvalIO)]),
+    "misti_nelder_mead": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, c_double_p, c_int32_p, c_int32_p,
+                                         ctypes.c_uint32, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_int64,
+                                         ctypes.c_int64, c_double_p, c_double_p, ctypes.POINTER(ctypes.c_int64),
+                                         ctypes.POINTER(ctypes.c_int64), c_int32_p, ctypes.POINTER(ctypes.c_int64)]),
     "misti_score_spectra": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, c_double_p, c_double_p]),
     "misti_last_kernel_ms": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_float)]),
     "misti_launch_count": (ctypes.c_int64, [ctypes.c_void_p]),

@@ -18,6 +18,7 @@
 //                          was parked.  Three launches per evaluation in all.
 // There is no CPU path: every entry point below launches on the device or fails.
 #include <cuda_runtime.h>
+#include <climits>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -27,6 +28,7 @@
 #include <vector>
 
 #include "misti_jsfs.cuh"
+#include "misti_optim.cuh"
 
 namespace {
 
@@ -69,6 +71,12 @@ misti_correct_kernel(int B, int P, const double* __restrict__ params, const int*
         __syncthreads();
     }
     if (b >= B) return;
+    if (model_ids && model_ids[b] < 0) {  // an empty slot of the on-device optimiser (all lanes of the item leave together)
+        nseg[b] = 0;
+        status[b] = MISTI_SKIPPED;
+        nfev[b] = 0;
+        return;
+    }
     const ModelDesc& md = model_ids ? models[model_ids[b]] : smd;
     const double* tt = times + md.grid_off;
     const double* ll = lh + 2 * md.grid_off;
@@ -181,7 +189,8 @@ misti_jsfs_kernel(int B, int P, const double* __restrict__ params, const int* __
         if (i0 >= B) break;
         const bool has = i0 + (half & 1) < B;
         const int b = has ? i0 + (half & 1) : B - 1;
-        const ModelDesc& md = models[model_ids ? model_ids[b] : model_default];
+        const int mid = model_ids ? model_ids[b] : model_default;
+        const ModelDesc& md = models[mid < 0 ? 0 : mid];  // an empty slot (status MISTI_SKIPPED) runs along inactive
         int st = out.status[b];
         double raw_c, jn_c;
         int nt = 0;
@@ -573,6 +582,44 @@ __global__ void misti_state_to_jaf_kernel(int which, int* out) {
     }
 }
 
+// ---- Nelder-Mead on the device (misti_optim.cuh): one thread per simplex ---------------------------
+struct NmState {
+    double *sim, *fsim;          // [S][(N+1) N], [S][N+1]
+    long long *iters, *fcalls;   // [S]
+    int *status, *phase;         // [S]
+    const int *model, *row;      // [S] the pair each simplex fits
+};
+
+// the points of this round -> the evaluation batch (slot j of simplex s is item s * slots + j; unused slots get model -1)
+__global__ void misti_nm_propose_kernel(int S, misti::NmConfig cfg, NmState st, double* __restrict__ params,
+                                        int* __restrict__ item_model, int* __restrict__ item_row, int* __restrict__ n_submitted) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    const int N = cfg.N;
+    double pts[(MISTI_MAX_PARAMS + 1) * MISTI_MAX_PARAMS];
+    const int n = misti::nm_propose(cfg, st.sim + (long)s * (N + 1) * N, st.fsim + (long)s * (N + 1), st.iters + s, st.fcalls + s,
+                                    st.status + s, st.phase + s, pts);
+    for (int j = 0; j < cfg.slots; ++j) {
+        const long b = (long)s * cfg.slots + j;
+        item_model[b] = j < n ? st.model[s] : -1;
+        item_row[b] = st.row[s];
+        if (j < n)
+            for (int k = 0; k < N; ++k) params[b * N + k] = pts[j * N + k];
+    }
+    if (n > 0) atomicAdd(n_submitted, n);
+}
+
+__global__ void misti_nm_apply_kernel(int S, misti::NmConfig cfg, NmState st, const double* __restrict__ params,
+                                      const double* __restrict__ llh) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S || st.phase[s] == misti::NM_DONE) return;
+    const int N = cfg.N;
+    double fv[MISTI_MAX_PARAMS + 1];
+    for (int j = 0; j < cfg.slots && j <= MISTI_MAX_PARAMS; ++j) fv[j] = -llh[(long)s * cfg.slots + j];  // the objective is -llh
+    misti::nm_apply(cfg, st.sim + (long)s * (N + 1) * N, st.fsim + (long)s * (N + 1), st.iters + s, st.fcalls + s, st.phase + s,
+                    params + (long)s * cfg.slots * N, fv);
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
@@ -624,6 +671,10 @@ struct misti_ctx {
     int *s_model_ids = nullptr, *s_terms = nullptr, *s_row_ids = nullptr;
     double *s_lc_io = nullptr, *s_pr = nullptr;
     size_t s_lc_io_cap = 0, s_pr_cap = 0;
+    unsigned char* d_nm = nullptr;  // state and batch buffers of misti_nelder_mead (one block, carved up per call)
+    size_t d_nm_cap = 0;
+    int* h_nm_counts = nullptr;     // pinned: points submitted per round (ring of kNmRing entries)
+    cudaEvent_t nm_ev[4] = {nullptr, nullptr, nullptr, nullptr};
     double* d_small = nullptr;  // 44*44 + 2*44 doubles for the table export kernels
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
     bool ev_valid = false;
@@ -804,11 +855,14 @@ void misti_ctx_destroy(misti_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     void* ptrs[] = {ctx->d_times, ctx->d_lh, ctx->d_gaux, ctx->d_cls, ctx->d_post, ctx->d_models, ctx->d_data, ctx->d_lc, ctx->d_cpost, ctx->d_status, ctx->d_nfev, ctx->d_conts, ctx->d_queue[0], ctx->d_queue[1], ctx->d_counts,
                     ctx->d_rec, ctx->d_nseg, ctx->s_params, ctx->s_llh, ctx->s_jafs, ctx->s_jafs_raw, ctx->s_model_ids, ctx->s_terms, ctx->s_row_ids, ctx->s_lc_io,
-                    ctx->s_pr, ctx->d_small};
+                    ctx->s_pr, ctx->d_small, ctx->d_nm};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     for (int i = 0; i < 3; ++i)
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    for (int i = 0; i < 4; ++i)
+        if (ctx->nm_ev[i]) cudaEventDestroy(ctx->nm_ev[i]);
+    if (ctx->h_nm_counts) cudaFreeHost(ctx->h_nm_counts);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -1123,6 +1177,99 @@ int misti_eval_batch(misti_ctx* ctx, int32_t B, int32_t P, const double* params,
         if (io->terms) CK(cudaMemcpyAsync(io->terms + off, ctx->s_terms, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
     }
+    return 0;
+}
+
+int misti_nelder_mead(misti_ctx* ctx, int32_t S, int32_t N, const double* x0, const int32_t* model_ids, const int32_t* row_ids,
+                      uint32_t flags, double mixture_th, double xatol, double fatol, int64_t maxiter, int64_t maxfev,
+                      double* x, double* fun, int64_t* nit, int64_t* nfev, int32_t* status, int64_t* info) {
+    if (!ctx) return MISTI_E_ARG;
+    if (S < 0 || N < 1 || N > MISTI_MAX_PARAMS || !x0 || !model_ids || !x || !fun || !nit || !nfev || !status)
+        return fail(ctx, MISTI_E_ARG, "misti_nelder_mead: bad arguments");
+    if (info) info[0] = info[1] = 0;
+    if (S == 0) return 0;
+    if (ctx->R < 1) return fail(ctx, MISTI_E_ARG, "misti_nelder_mead: no data rows (misti_set_data)");
+    const int n_models = (int)ctx->h_models.size();
+    for (int s = 0; s < S; ++s) {
+        if (model_ids[s] < 0 || model_ids[s] >= n_models) return fail(ctx, MISTI_E_ARG, "misti_nelder_mead: unknown model id");
+        if (ctx->h_models[model_ids[s]].n_params > N) return fail(ctx, MISTI_E_ARG, "misti_nelder_mead: incorrect number of parameters");
+        if (row_ids && (row_ids[s] < 0 || row_ids[s] >= ctx->R)) return fail(ctx, MISTI_E_ARG, "misti_nelder_mead: unknown data row");
+    }
+    CK(cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = sync_tables(ctx))) return rc;
+    misti::NmConfig cfg;
+    cfg.N = N;
+    cfg.slots = N + 1 > 4 ? N + 1 : 4;
+    cfg.xatol = xatol; cfg.fatol = fatol;
+    cfg.maxiter = maxiter < 0 ? LLONG_MAX : maxiter;
+    cfg.maxfev = maxfev < 0 ? LLONG_MAX : maxfev;
+    const long B = (long)S * cfg.slots;
+    if (B > kMaxChunk) return fail(ctx, MISTI_E_ARG, "misti_nelder_mead: too many simplices for one call");
+    // one block of device memory, carved up (8-byte items first)
+    constexpr int kNmRing = 64;
+    const size_t n_sim = (size_t)S * (N + 1) * N, n_fsim = (size_t)S * (N + 1);
+    size_t off = 0;
+    auto carve = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
+    const size_t o_sim = carve(n_sim * 8), o_fsim = carve(n_fsim * 8), o_it = carve((size_t)S * 8), o_fc = carve((size_t)S * 8),
+                 o_par = carve((size_t)B * N * 8), o_llh = carve((size_t)B * 8), o_st = carve((size_t)S * 4), o_ph = carve((size_t)S * 4),
+                 o_mod = carve((size_t)S * 4), o_row = carve((size_t)S * 4), o_bm = carve((size_t)B * 4), o_br = carve((size_t)B * 4),
+                 o_cnt = carve(kNmRing * 4);
+    if ((rc = ensure(ctx, &ctx->d_nm, &ctx->d_nm_cap, off))) return rc;
+    if (!ctx->h_nm_counts) CK(cudaMallocHost((void**)&ctx->h_nm_counts, kNmRing * sizeof(int)));
+    for (int i = 0; i < 4; ++i)
+        if (!ctx->nm_ev[i]) CK(cudaEventCreateWithFlags(&ctx->nm_ev[i], cudaEventDisableTiming));
+    unsigned char* base = ctx->d_nm;
+    NmState st;
+    st.sim = (double*)(base + o_sim); st.fsim = (double*)(base + o_fsim);
+    st.iters = (long long*)(base + o_it); st.fcalls = (long long*)(base + o_fc);
+    st.status = (int*)(base + o_st); st.phase = (int*)(base + o_ph);
+    int* d_mod = (int*)(base + o_mod); int* d_row = (int*)(base + o_row);
+    st.model = d_mod; st.row = d_row;
+    double* d_par = (double*)(base + o_par); double* d_llh = (double*)(base + o_llh);
+    int* d_bm = (int*)(base + o_bm); int* d_br = (int*)(base + o_br); int* d_cnt = (int*)(base + o_cnt);
+    cudaStream_t sm = ctx->stream;
+    // initial state: vertex 0 = x0, everything else zero (phase NM_INIT = 0, status -1 set below)
+    CK(cudaMemsetAsync(base, 0, off, sm));
+    CK(cudaMemcpy2DAsync(st.sim, (size_t)(N + 1) * N * 8, x0, (size_t)N * 8, (size_t)N * 8, S, cudaMemcpyHostToDevice, sm));
+    CK(cudaMemsetAsync(st.status, 0xff, (size_t)S * 4, sm));
+    CK(cudaMemcpyAsync(d_mod, model_ids, (size_t)S * 4, cudaMemcpyHostToDevice, sm));
+    if (row_ids) CK(cudaMemcpyAsync(d_row, row_ids, (size_t)S * 4, cudaMemcpyHostToDevice, sm));
+    const unsigned eflags = (flags | MISTI_FLAG_DEVICE_PTRS);
+    const int tb = 64, gb = (S + tb - 1) / tb;
+    int64_t rounds = 0, points = 0;
+    // The host runs at most two rounds ahead of the device: before round r is queued, the count of round r - 2 is in;
+    // a round in which no simplex submitted a point ends the fit (the rounds queued behind it are empty and cost microseconds).
+    for (long r = 0;; ++r) {
+        if (r >= 2) {
+            CK(cudaEventSynchronize(ctx->nm_ev[(r - 2) & 3]));
+            const int n = ctx->h_nm_counts[(r - 2) % kNmRing];
+            if (n == 0) break;
+            points += n;
+            ++rounds;
+        }
+        int* cnt = d_cnt + (r % kNmRing);
+        CK(cudaMemsetAsync(cnt, 0, sizeof(int), sm));
+        misti_nm_propose_kernel<<<gb, tb, 0, sm>>>(S, cfg, st, d_par, d_bm, d_br, cnt);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(ctx->h_nm_counts + (r % kNmRing), cnt, sizeof(int), cudaMemcpyDeviceToHost, sm));
+        CK(cudaEventRecord(ctx->nm_ev[r & 3], sm));
+        if ((rc = eval_chunk(ctx, (int)B, N, d_par, d_bm, -1, eflags, mixture_th, nullptr, d_llh, nullptr, nullptr, nullptr, nullptr,
+                             nullptr, nullptr, nullptr, d_br)))
+            return rc;
+        misti_nm_apply_kernel<<<gb, tb, 0, sm>>>(S, cfg, st, d_par, d_llh);
+        CK(cudaGetLastError());
+        ctx->launches += 2;
+    }
+    // results: best vertex and value (the simplices are sorted), counts
+    CK(cudaMemcpy2DAsync(x, (size_t)N * 8, st.sim, (size_t)(N + 1) * N * 8, (size_t)N * 8, S, cudaMemcpyDeviceToHost, sm));
+    CK(cudaMemcpy2DAsync(fun, 8, st.fsim, (size_t)(N + 1) * 8, 8, S, cudaMemcpyDeviceToHost, sm));
+    static_assert(sizeof(long long) == sizeof(int64_t), "64-bit counters");
+    CK(cudaMemcpyAsync(nit, st.iters, (size_t)S * 8, cudaMemcpyDeviceToHost, sm));
+    CK(cudaMemcpyAsync(nfev, st.fcalls, (size_t)S * 8, cudaMemcpyDeviceToHost, sm));
+    CK(cudaMemcpyAsync(status, st.status, (size_t)S * 4, cudaMemcpyDeviceToHost, sm));
+    CK(cudaStreamSynchronize(sm));
+    if (info) { info[0] = rounds; info[1] = points; }
     return 0;
 }
 

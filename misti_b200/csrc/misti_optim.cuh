@@ -1,0 +1,183 @@
+// misti_optim.cuh -- Nelder-Mead on the device: the decision logic of one simplex, one step at a time.
+//
+// The reference fits by scipy.optimize.minimize(method='Nelder-Mead') around the objective, one evaluation per call
+// (MigrationInference.Solve, MigrationInference.py:718-733).  misti_b200/optim.py advances many simplices in lock step
+// from the host, one batched evaluation per step; here the same step is taken ON the device so that a fit is a stream
+// of kernel launches (propose -> evaluate -> apply) without a host round trip per step.  Every simplex takes exactly
+// the decisions of scipy 1.18.1 (_optimize.py:_minimize_neldermead: rho = 1, chi = 2, psi = 0.5, sigma = 0.5, initial
+// simplex x0 (1.05) or 0.00025, strict / non-strict comparisons, stable re-ordering, termination
+// max|x_i - x_0| <= xatol and max|f_i - f_0| <= fatol, maxiter / maxfev) with the arithmetic of numpy (no fused
+// multiply-adds: every product and sum is rounded on its own), so the iterates, the iteration count and scipy's
+// evaluation count are those of the host drivers, bit for bit, given the same objective values.
+//
+// Like the host driver with speculative=True, a step evaluates the four candidates (expansion, reflection, outside and
+// inside contraction) together; a shrink takes one more round for its N points.  scipy enforces maxfev INSIDE an
+// iteration (its objective wrapper raises once the budget is spent, _optimize.py:549-559, and the iteration is abandoned
+// where it stands): the second evaluation of a step, or the rest of a shrink, is then dropped -- reproduced here.
+// Host and device compile this header (tests/hostsim drives it on the CPU against scipy itself).
+#pragma once
+#include "misti_math.cuh"
+
+namespace misti {
+
+struct NmConfig {
+    int N;             // parameters per simplex
+    int slots;         // points a simplex may submit per round: max(4, N + 1)
+    double xatol, fatol;
+    long long maxiter, maxfev;  // LLONG_MAX = none
+};
+
+enum { NM_INIT = 0, NM_STEP = 1, NM_SHRINK = 2, NM_DONE = 3 };
+
+// rounded-once arithmetic (numpy evaluates a * b - c * d as two products and a difference)
+#if defined(__CUDA_ARCH__)
+MISTI_HD inline double nm_mul(double a, double b) { return __dmul_rn(a, b); }
+MISTI_HD inline double nm_add(double a, double b) { return __dadd_rn(a, b); }
+MISTI_HD inline double nm_sub(double a, double b) { return __dsub_rn(a, b); }
+MISTI_HD inline double nm_div(double a, double b) { return __ddiv_rn(a, b); }
+#else
+MISTI_HD inline double nm_mul(double a, double b) { volatile double r = a * b; return r; }
+MISTI_HD inline double nm_add(double a, double b) { volatile double r = a + b; return r; }
+MISTI_HD inline double nm_sub(double a, double b) { volatile double r = a - b; return r; }
+MISTI_HD inline double nm_div(double a, double b) { volatile double r = a / b; return r; }
+#endif
+
+// stable sort of the N + 1 vertices by objective value (numpy argsort(kind="stable")): insertion sort
+MISTI_HD inline void nm_sort(int N, double* sim, double* fsim) {
+    for (int i = 1; i <= N; ++i) {
+        const double fi = fsim[i];
+        double row[MISTI_MAX_PARAMS];
+        for (int k = 0; k < N; ++k) row[k] = sim[i * N + k];
+        int j = i - 1;
+        while (j >= 0 && fsim[j] > fi) {
+            fsim[j + 1] = fsim[j];
+            for (int k = 0; k < N; ++k) sim[(j + 1) * N + k] = sim[j * N + k];
+            --j;
+        }
+        fsim[j + 1] = fi;
+        for (int k = 0; k < N; ++k) sim[(j + 1) * N + k] = row[k];
+    }
+}
+
+// Termination tests at the top of scipy's loop (_optimize.py:833-836 and the while condition); returns true when the
+// simplex stops and sets *status (0 converged, 1 maxfev, 2 maxiter).  numpy's max propagates NaN (inf - inf), and a NaN
+// compares false: not converged.
+MISTI_HD inline bool nm_retire(const NmConfig& c, const double* sim, const double* fsim, long long iters, long long fcalls, int* status) {
+    const int N = c.N;
+    const bool budget = fcalls < c.maxfev && iters < c.maxiter;
+    double dx = 0.0, df = 0.0;
+    bool nan_x = false, nan_f = false;
+    for (int j = 1; j <= N; ++j) {
+        for (int k = 0; k < N; ++k) {
+            const double d = fabs(sim[j * N + k] - sim[k]);
+            if (d != d) nan_x = true;
+            dx = d > dx ? d : dx;
+        }
+        const double d = fabs(fsim[0] - fsim[j]);
+        if (d != d) nan_f = true;
+        df = d > df ? d : df;
+    }
+    const bool conv = !nan_x && !nan_f && dx <= c.xatol && df <= c.fatol;
+    if (budget && !conv) return false;
+    *status = (budget && conv) ? 0 : (fcalls >= c.maxfev ? 1 : 2);
+    return true;
+}
+
+// The points a simplex wants evaluated in this round, written to pts[slots][N]; returns how many (0 = none: done).
+// sim[(N+1)][N], fsim[N+1] are sorted except in phase NM_INIT (sim[0] = x0) and NM_SHRINK (vertices 1..N just moved).
+MISTI_HD inline int nm_propose(const NmConfig& c, double* sim, const double* fsim, const long long* iters, const long long* fcalls,
+                               int* status, int* phase, double* pts) {
+    const int N = c.N;
+    if (*phase == NM_DONE) return 0;
+    if (*phase == NM_INIT) {  // scipy's default simplex (_optimize.py:775-801)
+        for (int j = 1; j <= N; ++j)
+            for (int k = 0; k < N; ++k) {
+                double y = sim[k];
+                if (k == j - 1) y = y != 0 ? nm_mul(1 + 0.05, y) : 0.00025;
+                sim[j * N + k] = y;
+            }
+        for (int i = 0; i < (N + 1) * N; ++i) pts[i] = sim[i];
+        return c.maxfev < N + 1 ? (int)c.maxfev : N + 1;
+    }
+    if (*phase == NM_SHRINK) {  // the vertices the budget still covers (nm_apply moved no more than that, plus one)
+        const long long left = c.maxfev - *fcalls;
+        const int n = left < N ? (int)left : N;
+        for (int j = 1; j <= n; ++j)
+            for (int k = 0; k < N; ++k) pts[(j - 1) * N + k] = sim[j * N + k];
+        return n;
+    }
+    if (nm_retire(c, sim, fsim, *iters, *fcalls, status)) {
+        *phase = NM_DONE;
+        return 0;
+    }
+    // candidates (_optimize.py:846-874), in the order of the decision codes: expansion, reflection, outside, inside
+    for (int k = 0; k < N; ++k) {
+        double xbar = sim[k];
+        for (int j = 1; j < N; ++j) xbar = nm_add(xbar, sim[j * N + k]);  // np.add.reduce(sim[:-1], 0): row by row
+        xbar = nm_div(xbar, (double)N);
+        const double last = sim[N * N + k];
+        pts[0 * N + k] = nm_sub(nm_mul(3.0, xbar), nm_mul(2.0, last));   // (1 + rho chi) xbar - rho chi last
+        pts[1 * N + k] = nm_sub(nm_mul(2.0, xbar), nm_mul(1.0, last));   // (1 + rho) xbar - rho last
+        pts[2 * N + k] = nm_sub(nm_mul(1.5, xbar), nm_mul(0.5, last));   // (1 + psi rho) xbar - psi rho last
+        pts[3 * N + k] = nm_add(nm_mul(0.5, xbar), nm_mul(0.5, last));   // (1 - psi) xbar + psi last
+    }
+    return 4;
+}
+
+// The round's objective values fv[] (in the order of the submitted points; NaN counts as +inf) applied to the simplex.
+MISTI_HD inline void nm_apply(const NmConfig& c, double* sim, double* fsim, long long* iters, long long* fcalls, int* phase,
+                              const double* pts, const double* fv_in) {
+    const int N = c.N;
+    double fv[MISTI_MAX_PARAMS + 1];
+    const long long left = c.maxfev - *fcalls;  // evaluations the budget still covers
+    const int n = *phase == NM_INIT ? (left < N + 1 ? (int)left : N + 1) : (*phase == NM_SHRINK ? (left < N ? (int)left : N) : 4);
+    for (int i = 0; i < n; ++i) fv[i] = fv_in[i] != fv_in[i] ? kInf : fv_in[i];
+    if (*phase == NM_INIT) {
+        for (int j = 0; j <= N; ++j) fsim[j] = j < n ? fv[j] : kInf;  // vertices past the budget keep scipy's initial +inf
+        *fcalls = n;
+        *iters = 1;
+        nm_sort(N, sim, fsim);
+        *phase = NM_STEP;
+        return;
+    }
+    if (*phase == NM_SHRINK) {
+        for (int j = 1; j <= n; ++j) fsim[j] = fv[j - 1];
+        *fcalls += n;
+        nm_sort(N, sim, fsim);
+        if (n == N) *iters += 1;  // an iteration cut short by the budget is not counted (:929-931)
+        *phase = NM_STEP;
+        return;
+    }
+    // scipy's decision tree (_optimize.py:846-896)
+    const double fxe = fv[0], fxr = fv[1], fxc = fv[2], fxcc = fv[3];
+    const bool better = fxr < fsim[0];
+    const bool second = fxr < fsim[N - 1];
+    const bool take_e = better && fxe < fxr;
+    const bool take_r = (better && !(fxe < fxr)) || (!better && second);
+    const bool contract = !better && !second;
+    const bool outside = contract && fxr < fsim[N], inside = contract && !(fxr < fsim[N]);
+    const bool take_c = outside && fxc <= fxr, take_cc = inside && fxcc < fsim[N];
+    const int which = take_e ? 0 : (take_r ? 1 : (take_c ? 2 : (take_cc ? 3 : -1)));
+    const bool two = better || contract;  // scipy evaluates a second point
+    if (two && left < 2) {  // ... but the budget ends after the reflection: the iteration is abandoned, nothing changes
+        *fcalls += 1;
+        return;
+    }
+    *fcalls += two ? 2 : 1;
+    if (which >= 0) {
+        for (int k = 0; k < N; ++k) sim[N * N + k] = pts[which * N + k];
+        fsim[N] = fv[which];
+        nm_sort(N, sim, fsim);
+        *iters += 1;
+        return;
+    }
+    // shrink towards the best vertex: sim[0] + sigma (sim[j] - sim[0]); scipy moves and evaluates the vertices one at a
+    // time, so with `rest` evaluations left vertices 1..rest + 1 move (the last of them is not evaluated any more)
+    const long long rest = c.maxfev - *fcalls;
+    const int nmove = rest < N ? (int)rest + 1 : N;
+    for (int j = 1; j <= nmove; ++j)
+        for (int k = 0; k < N; ++k) sim[j * N + k] = nm_add(sim[k], nm_mul(0.5, nm_sub(sim[j * N + k], sim[k])));
+    if (rest >= 1) *phase = NM_SHRINK;  // else: nothing left to evaluate; the next round's budget test ends the fit
+}
+
+}  // namespace misti

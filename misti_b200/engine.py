@@ -211,6 +211,41 @@ class Engine:
                                                ctypes.c_void_p(model_ids_ptr) if model_ids_ptr else None, int(model), flags,
                                                float(mixtureTH), ctypes.c_void_p(llh_ptr), ctypes.byref(io)))
 
+    def nelder_mead(self, x0, model_ids, row_ids=None, flags=_lib.FLAG_CORRECT, mixtureTH=0.0, xatol=1e-4, fatol=1e-4,
+                    maxiter=None, maxfev=None):
+        """Nelder-Mead fits of S (model, data row) pairs on the device (misti_nelder_mead): the objective is -llh, every
+        simplex takes scipy's decisions, and no step returns to the host.  x0: [S, N].  maxiter / maxfev as in
+        scipy.optimize.minimize (both None: N * 200 each).  Returns the dict of misti_b200.optim.nelder_mead_batch
+        (x, fun, nit, nfev, status, success, evaluations, launches = rounds of device launches)."""
+        x0 = _as_f64(x0)
+        if x0.ndim == 1:
+            x0 = x0.reshape(1, -1)
+        S, N = x0.shape
+        mids = np.ascontiguousarray(model_ids, dtype=np.int32).reshape(-1)
+        rows = None if row_ids is None else np.ascontiguousarray(row_ids, dtype=np.int32).reshape(-1)
+        if mids.shape[0] != S or (rows is not None and rows.shape[0] != S):
+            raise ValueError("model_ids / row_ids must have one entry per start vector")
+        if maxiter is None and maxfev is None:  # scipy's defaults (_optimize.py:751-768)
+            maxiter, maxfev = N * 200, N * 200
+        elif maxiter is None:
+            maxiter = N * 200 if maxfev == np.inf else np.inf
+        elif maxfev is None:
+            maxfev = N * 200 if maxiter == np.inf else np.inf
+        lim = [(-1 if v == np.inf else int(v)) for v in (maxiter, maxfev)]
+        flags = int(flags) & ~_lib.FLAG_DEVICE_PTRS
+        flags = (flags | _lib.FLAG_UNFOLDED) if self.unfolded else (flags & ~_lib.FLAG_UNFOLDED)
+        x, fun = np.empty((S, N)), np.empty(S)
+        nit, nfev, info = np.zeros(S, dtype=np.int64), np.zeros(S, dtype=np.int64), np.zeros(2, dtype=np.int64)
+        status = np.zeros(S, dtype=np.int32)
+        i64p = ctypes.POINTER(ctypes.c_int64)
+        self._check(self._lib.misti_nelder_mead(
+            self._h, S, N, x0.ctypes.data_as(_lib.c_double_p), mids.ctypes.data_as(_lib.c_int32_p),
+            rows.ctypes.data_as(_lib.c_int32_p) if rows is not None else None, flags, float(mixtureTH), float(xatol), float(fatol),
+            lim[0], lim[1], x.ctypes.data_as(_lib.c_double_p), fun.ctypes.data_as(_lib.c_double_p), nit.ctypes.data_as(i64p),
+            nfev.ctypes.data_as(i64p), status.ctypes.data_as(_lib.c_int32_p), info.ctypes.data_as(i64p)))
+        return {"x": x, "fun": fun, "nit": nit, "nfev": nfev, "status": status.astype(np.int64), "success": status == 0,
+                "evaluations": int(info[1]), "launches": int(info[0])}
+
     def score_spectra(self, spectra):
         """llh [B, R] of given spectra (7 weights each, normalised on the device) against every data row."""
         sp = _as_f64(spectra).reshape(-1, 7)

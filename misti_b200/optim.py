@@ -113,8 +113,15 @@ def nelder_mead_batch(fun, x0, xatol=1e-4, fatol=1e-4, maxiter=None, maxfev=None
         launches += 1
         return _clean(fun(np.ascontiguousarray(X), owners[who]))
 
-    fsim = call(sim.reshape(-1, N), np.repeat(np.arange(S), N + 1)).reshape(S, N + 1)
-    fcalls = np.full(S, N + 1, dtype=np.int64)
+    if maxfev < N + 1:  # scipy stops evaluating the initial simplex when the budget is spent; the rest stays at +inf
+        n0 = int(maxfev)
+        fsim = np.full((S, N + 1), np.inf)
+        if n0 > 0:
+            fsim[:, :n0] = call(sim[:, :n0].reshape(-1, N), np.repeat(np.arange(S), n0)).reshape(S, n0)
+        fcalls = np.full(S, n0, dtype=np.int64)
+    else:
+        fsim = call(sim.reshape(-1, N), np.repeat(np.arange(S), N + 1)).reshape(S, N + 1)
+        fcalls = np.full(S, N + 1, dtype=np.int64)
     sim, fsim = _sort(sim, fsim)
     iterations = np.ones(S, dtype=np.int64)
     status = np.full(S, -1, dtype=np.int64)
@@ -161,8 +168,67 @@ def nelder_mead_batch(fun, x0, xatol=1e-4, fatol=1e-4, maxiter=None, maxfev=None
         sim[idx], fsim[idx] = s, f
         iterations[idx] += 1
 
+    class _BudgetSpent(Exception):
+        pass
+
+    def finish_serially(i):
+        """scipy enforces maxfev INSIDE an iteration (its objective wrapper raises once the budget is spent,
+        _optimize.py:549-559, and the iteration is abandoned where it stands).  A simplex that could run out of budget
+        within the coming step is therefore taken through scipy's own loop (_optimize.py:867-934), one evaluation at a
+        time, to its end."""
+        def f(x):
+            if fcalls[i] >= maxfev:
+                raise _BudgetSpent
+            fcalls[i] += 1
+            return call(x.reshape(1, N), np.array([i]))[0]
+        s, fs = sim[i].copy(), fsim[i].copy()
+        while fcalls[i] < maxfev and iterations[i] < maxiter:
+            try:
+                with np.errstate(invalid="ignore"):
+                    if np.max(np.abs(s[1:] - s[0])) <= xatol and np.max(np.abs(fs[0] - fs[1:])) <= fatol:
+                        break
+                xr, xe, xc, xcc = (v[0] for v in _candidates(s[None]))
+                fxr = f(xr)
+                doshrink = False
+                if fxr < fs[0]:
+                    fxe = f(xe)
+                    if fxe < fxr:
+                        s[-1], fs[-1] = xe, fxe
+                    else:
+                        s[-1], fs[-1] = xr, fxr
+                elif fxr < fs[-2]:
+                    s[-1], fs[-1] = xr, fxr
+                elif fxr < fs[-1]:
+                    fxc = f(xc)
+                    if fxc <= fxr:
+                        s[-1], fs[-1] = xc, fxc
+                    else:
+                        doshrink = True
+                else:
+                    fxcc = f(xcc)
+                    if fxcc < fs[-1]:
+                        s[-1], fs[-1] = xcc, fxcc
+                    else:
+                        doshrink = True
+                if doshrink:
+                    for j in range(1, N + 1):
+                        s[j] = s[0] + SIGMA * (s[j] - s[0])
+                        fs[j] = f(s[j])
+                iterations[i] += 1
+            except _BudgetSpent:
+                pass
+            ind = np.argsort(fs, kind="stable")
+            s, fs = s[ind], fs[ind]
+        sim[i], fsim[i] = s, fs
+        status[i] = 1 if fcalls[i] >= maxfev else (2 if iterations[i] >= maxiter else 0)
+        active[i] = False
+
     while True:
         idx = retire()
+        if maxfev != np.inf and idx.size:
+            for i in idx[fcalls[idx] + 2 * (2 + N) > maxfev]:  # a call may take two iterations (look-ahead)
+                finish_serially(int(i))
+            idx = np.nonzero(active)[0]
         if idx.size == 0:
             break
         A = idx.size
@@ -229,10 +295,12 @@ def nelder_mead_batch(fun, x0, xatol=1e-4, fatol=1e-4, maxiter=None, maxfev=None
 
 
 def basinhopping_batch(fun, x0, niter=100, T=1.0, stepsize=0.5, interval=50, target_accept_rate=0.5, stepwise_factor=0.9,
-                       seeds=None, xatol=1e-4, fatol=1e-4, maxiter=None, maxfev=None, speculative=True):
+                       seeds=None, xatol=1e-4, fatol=1e-4, maxiter=None, maxfev=None, speculative=True, local_solver=None):
     """W basin-hopping walkers in lock step (scipy/optimize/_basinhopping.py), local search = nelder_mead_batch.
     x0: [W, N]; seeds: one seed (or numpy Generator) per walker.  Returns dict: x [W, N], fun [W], nfev [W],
-    nit, accepted [W], minimization_failures [W], evaluations, launches."""
+    nit, accepted [W], minimization_failures [W], evaluations, launches.
+    local_solver(xs[W, N]) -> the dict of nelder_mead_batch: replaces the host-driven local search (e.g. by the on-device
+    Nelder-Mead, Engine.nelder_mead); `fun` is then not called."""
     x0 = np.asarray(x0, dtype=np.float64)
     if x0.ndim == 1:
         x0 = x0.reshape(1, -1)
@@ -244,7 +312,10 @@ def basinhopping_batch(fun, x0, niter=100, T=1.0, stepsize=0.5, interval=50, tar
 
     def local(xs):
         nonlocal evaluations, launches
-        r = nelder_mead_batch(fun, xs, xatol=xatol, fatol=fatol, maxiter=maxiter, maxfev=maxfev, speculative=speculative)
+        if local_solver is not None:
+            r = local_solver(xs)
+        else:
+            r = nelder_mead_batch(fun, xs, xatol=xatol, fatol=fatol, maxiter=maxiter, maxfev=maxfev, speculative=speculative)
         evaluations += r["evaluations"]
         launches += r["launches"]
         return r

@@ -77,10 +77,16 @@ class Sweep:
         return out["llh"]
 
     # -- fits ------------------------------------------------------------------------------------------
-    def solve(self, pairs=None, tol=1e-4, globalOpt=False, niter=100, seed=0, speculative=True):
+    # up to this many points per round the Nelder-Mead steps are taken on the device (Engine.nelder_mead: no host round
+    # trip per step); beyond, the host driver wins because it packs only the simplices that are still running
+    DEVICE_NM_MAX_POINTS = 16384
+
+    def solve(self, pairs=None, tol=1e-4, globalOpt=False, niter=100, seed=0, speculative=True, on_device="auto"):
         """Fit every (model, row) pair (default: all).  Nelder-Mead with xatol = fatol = tol, maxiter = 1000 as
         MigrationInference.Solve; globalOpt = basin-hopping with T = 0.5 as the reference calls it (scipy-default
-        inner tolerances), seeded per pair.  Returns a dict of arrays indexed by pair."""
+        inner tolerances), seeded per pair.  Returns a dict of arrays indexed by pair.
+        on_device: take the Nelder-Mead steps on the device (True / False / "auto" = by the size of a round); the
+        decisions, iterates and counts are the same either way."""
         M, R = len(self.models), self.rows.shape[0]
         if pairs is None:
             pairs = [(m, r) for r in range(R) for m in range(M)]
@@ -106,10 +112,22 @@ class Sweep:
             def fun(X, who, sel=sel):
                 llh, _ = self.evaluate(pairs[sel[who], 0], X, pairs[sel[who], 1])
                 return -llh
+            dev = on_device is True or (on_device == "auto" and speculative and sel.size * max(4, P + 1) <= self.DEVICE_NM_MAX_POINTS)
+            mids = np.array([self.models[m]["id"] for m in pairs[sel, 0]], dtype=np.int32)
+
+            def device_nm(xs, mids=mids, rows=pairs[sel, 1], **kw):
+                r = self.engine.nelder_mead(xs, mids, rows, flags=self.flags, mixtureTH=self.mixtureTH, **kw)
+                MigrationInference.COUNT_LLH += r["evaluations"]
+                MigrationInference.CORRECTION_CALLED += r["evaluations"]
+                return r
             if globalOpt:
-                r = basinhopping_batch(fun, x0, niter=niter, T=0.5, seeds=[seed + int(k) for k in sel], speculative=speculative)
+                r = basinhopping_batch(fun, x0, niter=niter, T=0.5, seeds=[seed + int(k) for k in sel], speculative=speculative,
+                                       local_solver=device_nm if dev else None)
             else:
-                r = nelder_mead_batch(fun, x0, xatol=tol, fatol=tol, maxiter=1000, speculative=speculative)
+                if dev:
+                    r = device_nm(x0, xatol=tol, fatol=tol, maxiter=1000)
+                else:
+                    r = nelder_mead_batch(fun, x0, xatol=tol, fatol=tol, maxiter=1000, speculative=speculative)
                 res["nit"][sel] = r["nit"]
             res["x"][sel, :P] = r["x"]
             res["llh"][sel] = -r["fun"]

@@ -2,10 +2,12 @@
 // misti_b200/csrc/misti_math.cuh and misti_model.cuh, so the scalar correction chain (K1's body)
 // can be unit-tested against the oracle in a container without a GPU.  It is NOT part of the
 // product: libmisti_b200.so has no CPU path and nothing under misti_b200/ loads this library.
+#include <climits>
 #include <cstring>
 #include <vector>
 #include "../../misti_b200/csrc/misti_model.cuh"
 #include "../../misti_b200/csrc/misti_jsfs.cuh"
+#include "../../misti_b200/csrc/misti_optim.cuh"
 
 extern "C" {
 
@@ -133,6 +135,25 @@ void hs_post_split(int numT, int splitT, const double* times, const double* lh, 
     const double lam = (1.0 + ed) / (1.0 / lh[2 * (numT - 1)] + ed / lh[2 * (numT - 1) + 1]);
     const double f3 = f1 * f1 * f1;
     grp[0] += f3 * f3 / (6.0 * lam); grp[1] += f3 / (3.0 * lam); grp[2] += f1 / lam;
+}
+
+// one simplex of the on-device Nelder-Mead (misti_optim.cuh), driven from the test: propose -> the test evaluates the
+// objective -> apply.  maxiter / maxfev < 0 = none.
+static misti::NmConfig hs_nm_cfg(int N, double xatol, double fatol, long long maxiter, long long maxfev) {
+    misti::NmConfig c;
+    c.N = N; c.slots = N + 1 > 4 ? N + 1 : 4; c.xatol = xatol; c.fatol = fatol;
+    c.maxiter = maxiter < 0 ? LLONG_MAX : maxiter; c.maxfev = maxfev < 0 ? LLONG_MAX : maxfev;
+    return c;
+}
+
+int hs_nm_propose(int N, double xatol, double fatol, long long maxiter, long long maxfev, double* sim, double* fsim,
+                  long long* iters, long long* fcalls, int* status, int* phase, double* pts) {
+    return misti::nm_propose(hs_nm_cfg(N, xatol, fatol, maxiter, maxfev), sim, fsim, iters, fcalls, status, phase, pts);
+}
+
+void hs_nm_apply(int N, double xatol, double fatol, long long maxiter, long long maxfev, double* sim, double* fsim,
+                 long long* iters, long long* fcalls, int* phase, const double* pts, const double* fv) {
+    misti::nm_apply(hs_nm_cfg(N, xatol, fatol, maxiter, maxfev), sim, fsim, iters, fcalls, phase, pts, fv);
 }
 
 }  // extern "C"

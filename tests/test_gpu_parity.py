@@ -425,3 +425,37 @@ def test_post_split_pass_in_the_jsfs_kernel(golden_datasets):
         assert relerr(b["lc"][ok], a["lc"][ok]) < 1e-13
     # asking for the rates does not change the likelihoods
     assert np.array_equal(res["1"][0]["llh"], res["1"][1]["llh"], equal_nan=True)
+
+
+@pytest.mark.gpu
+def test_nelder_mead_on_the_device(engine, golden_datasets):
+    """misti_nelder_mead (propose / evaluate / apply on the device, no host round trip per step) against the host-driven
+    lock-step driver around the same objective: identical iterates, likelihoods, iteration and evaluation counts for
+    every (model, row) pair, with one, two and three parameters, tight budgets, and as the local search of basin-hopping."""
+    from misti_b200.sweep import Sweep
+    ds = golden_datasets["synthetic"]
+    rows = [ds["sfs"]] + ds["bs_rows"][1:5]
+    sw = Sweep(ds["times"], ds["lambdas"], rows, unfolded=True, cpfit=True, smooth=True, engine=engine)
+    m1 = sw.add_model(40, [[2, 5, 12, 0.8, 1]])
+    m1b = sw.add_model(38, [[1, 4, 38, 3.0, 1]])
+    m3 = sw.add_model(40, [[1, 2, 10, 0.3, 1], [2, 5, 12, 0.8, 1]], [[1, 7, 0.05, 1]])
+    m2 = sw.add_model(41, [[1, 2, 10, 0.3, 1], [2, 5, 12, 0.8, 1]])
+    dev = sw.solve(tol=1e-4, on_device=True)
+    host = sw.solve(tol=1e-4, on_device=False)
+    assert dev["launches"] > 0 and len(dev["llh"]) == 4 * len(rows)
+    for k in ("x", "llh", "nfev", "nit", "success"):
+        assert np.array_equal(dev[k], host[k], equal_nan=True), k
+    assert dev["success"].all()
+    # budgets: scipy's maxfev cuts an iteration short; the device follows (the CPU test holds it against scipy itself)
+    x0 = np.array([[0.8], [0.3], [2.5]])
+    mids = np.array([sw.models[m1]["id"]] * 3, dtype=np.int32)
+    r = engine.nelder_mead(x0, mids, np.zeros(3, dtype=np.int32), flags=sw.flags, maxiter=7)
+    assert (r["nit"] == 7).all() and (r["status"] == 2).all()
+    r = engine.nelder_mead(x0, mids, np.zeros(3, dtype=np.int32), flags=sw.flags, maxfev=9)
+    assert (r["nfev"] == 9).all() and (r["status"] == 1).all()
+    # basin-hopping: the same walkers with the local search on the device and on the host
+    pairs = [(m3, 0), (m3, 1), (m1, 2)]
+    a = sw.solve(pairs=pairs, globalOpt=True, niter=3, seed=5, on_device=True)
+    b = sw.solve(pairs=pairs, globalOpt=True, niter=3, seed=5, on_device=False)
+    for k in ("x", "llh", "nfev"):
+        assert np.array_equal(a[k], b[k], equal_nan=True), k

@@ -96,3 +96,100 @@ def test_lookahead_takes_the_same_decisions_in_half_the_calls(N):
         ref = optimize.minimize(lambda x: float(obj(x, [s])[0]), x0[s], method="Nelder-Mead",
                                 options={"xatol": 1e-6, "fatol": 1e-6, "maxiter": 400})
         assert np.array_equal(res[True]["x"][s], ref.x) and res[True]["nfev"][s] == ref.nfev and res[True]["nit"][s] == ref.nit
+
+
+def _device_logic_nelder_mead(lib, fun, x0, xatol=1e-4, fatol=1e-4, maxiter=-1, maxfev=-1):
+    """One simplex through the step logic of the ON-DEVICE Nelder-Mead (misti_b200/csrc/misti_optim.cuh, compiled for the
+    host by tests/hostsim): propose -> evaluate here -> apply, until nothing is proposed."""
+    import ctypes
+    dp, lp, ip = ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_longlong), ctypes.POINTER(ctypes.c_int)
+    N = len(x0)
+    sim, fsim = np.zeros((N + 1, N)), np.zeros(N + 1)
+    sim[0] = x0
+    iters, fcalls = ctypes.c_longlong(0), ctypes.c_longlong(0)
+    status, phase = ctypes.c_int(-1), ctypes.c_int(0)
+    pts = np.zeros((max(4, N + 1), N))
+    cfg = (N, ctypes.c_double(xatol), ctypes.c_double(fatol), ctypes.c_longlong(maxiter), ctypes.c_longlong(maxfev))
+    lib.hs_nm_propose.restype = ctypes.c_int
+    rounds = 0
+    while True:
+        n = lib.hs_nm_propose(*cfg, sim.ctypes.data_as(dp), fsim.ctypes.data_as(dp), ctypes.byref(iters), ctypes.byref(fcalls),
+                              ctypes.byref(status), ctypes.byref(phase), pts.ctypes.data_as(dp))
+        if n == 0:
+            break
+        fv = np.full(len(pts), np.nan)
+        fv[:n] = [fun(pts[j].copy()) for j in range(n)]
+        lib.hs_nm_apply(*cfg, sim.ctypes.data_as(dp), fsim.ctypes.data_as(dp), ctypes.byref(iters), ctypes.byref(fcalls),
+                        ctypes.byref(phase), pts.ctypes.data_as(dp), fv.ctypes.data_as(dp))
+        rounds += 1
+        assert rounds < 100000
+    return dict(x=sim[0].copy(), fun=fsim[0], nit=iters.value, nfev=fcalls.value, status=status.value)
+
+
+@pytest.mark.parametrize("N", [1, 2, 3, 5])
+def test_device_step_logic_equals_scipy(hostsim, N):
+    """the decisions, iterates and counts of the on-device Nelder-Mead are scipy's, also through +inf / NaN objective
+    values, shrinks, and the iteration / evaluation budgets"""
+    rng = np.random.default_rng(10 + N)
+
+    def make(shift, kind):
+        def f(x):
+            x = np.asarray(x, dtype=np.float64)
+            if kind == 0:  # smooth valley with an infeasible region
+                if (x < 0).any():
+                    return np.inf
+                a = x[0] - shift
+                b = x[1 % len(x)]
+                return float(100.0 * (b - a * a) ** 2 + (1 - a) ** 2 + 0.1 * (x ** 2).sum())
+            if kind == 1:  # bumpy: many contractions and shrinks
+                return float(np.cos(14.5 * (x[0] - shift) - 0.3) + ((x[0] - shift) + 0.2) * (x[0] - shift) + 0.1 * (x ** 2).sum()
+                             + np.abs(np.sin(37.0 * x).sum()))
+            return float("nan") if x[0] > 2.5 else float(((x - shift) ** 2).sum())  # NaN counts as +inf
+        return f
+    shrinks = 0
+    for trial in range(24):
+        x0 = rng.uniform(0.0, 3.0, N)
+        if trial % 5 == 0:
+            x0[-1] = 0.0  # zero coordinate -> 0.00025 step
+        fun = make(rng.uniform(0, 1), trial % 3)
+        budget = {} if trial % 4 else {"maxiter": 15 + trial}
+        if trial % 6 == 1:
+            budget = {"maxfev": 20 + trial}
+        opts = {"xatol": 1e-4, "fatol": 1e-4}
+        opts.update(budget)
+        with np.errstate(invalid="ignore"):
+            clean = (lambda x: np.inf if np.isnan(fun(x)) else fun(x))
+            ref = optimize.minimize(clean, x0, method="Nelder-Mead", options=opts)
+        # scipy's defaults for the missing budget (_optimize.py:751-768), as Engine.nelder_mead applies them
+        mi, mf = budget.get("maxiter"), budget.get("maxfev")
+        if mi is None and mf is None:
+            mi, mf = N * 200, N * 200
+        elif mi is None:
+            mi = -1
+        elif mf is None:
+            mf = -1
+        got = _device_logic_nelder_mead(hostsim, fun, x0, maxiter=mi, maxfev=mf)
+        assert np.array_equal(got["x"], ref.x), (N, trial)
+        assert got["fun"] == ref.fun and got["nit"] == ref.nit and got["nfev"] == ref.nfev, (N, trial, got, ref.nit, ref.nfev)
+        assert got["status"] == ref.status, (N, trial)
+        shrinks += got["nfev"] > 2 * got["nit"] + N + 1
+    assert N == 1 or shrinks > 0
+
+
+def test_host_driver_follows_scipy_through_the_evaluation_budget():
+    """maxfev is enforced inside an iteration by scipy (the iteration is abandoned where it stands); the lock-step
+    driver hands a simplex that is about to run out to scipy's own serial loop, so x, counts and status stay scipy's
+    for every budget, with and without look-ahead"""
+    def f1(x):
+        x = np.asarray(x)
+        return float(np.cos(14.5 * x[0] - 0.3) + (x[0] + 0.2) * x[0] + 0.1 * (x ** 2).sum() + abs(np.sin(37 * x).sum()))
+    rng = np.random.default_rng(3)
+    for N in (1, 2, 3):
+        for mf in list(range(1, 26)) + [N * 200]:
+            for look, spec in ((False, True), ("auto", True), (False, False)):
+                x0 = rng.uniform(0, 3, (3, N))
+                r = nelder_mead_batch(lambda X, who: np.array([f1(x) for x in X]), x0, maxfev=mf, lookahead=look, speculative=spec)
+                for s in range(3):
+                    ref = optimize.minimize(f1, x0[s], method="Nelder-Mead", options={"maxfev": mf, "xatol": 1e-4, "fatol": 1e-4})
+                    assert np.array_equal(r["x"][s], ref.x), (N, mf, look, spec)
+                    assert (r["nfev"][s], r["nit"][s], r["status"][s]) == (ref.nfev, ref.nit, ref.status), (N, mf, look, spec)
