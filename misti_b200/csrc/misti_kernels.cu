@@ -596,15 +596,13 @@ __global__ void misti_nm_propose_kernel(int S, misti::NmConfig cfg, NmState st, 
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= S) return;
     const int N = cfg.N;
-    double pts[(MISTI_MAX_PARAMS + 1) * MISTI_MAX_PARAMS];
+    const long b0 = (long)s * cfg.slots;
     const int n = misti::nm_propose(cfg, st.sim + (long)s * (N + 1) * N, st.fsim + (long)s * (N + 1), st.iters + s, st.fcalls + s,
-                                    st.status + s, st.phase + s, pts);
+                                    st.status + s, st.phase + s, params + b0 * N);
+    const int model = st.model[s], row = st.row[s];
     for (int j = 0; j < cfg.slots; ++j) {
-        const long b = (long)s * cfg.slots + j;
-        item_model[b] = j < n ? st.model[s] : -1;
-        item_row[b] = st.row[s];
-        if (j < n)
-            for (int k = 0; k < N; ++k) params[b * N + k] = pts[j * N + k];
+        item_model[b0 + j] = j < n ? model : -1;
+        item_row[b0 + j] = row;
     }
     if (n > 0) atomicAdd(n_submitted, n);
 }
@@ -614,10 +612,9 @@ __global__ void misti_nm_apply_kernel(int S, misti::NmConfig cfg, NmState st, co
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= S || st.phase[s] == misti::NM_DONE) return;
     const int N = cfg.N;
-    double fv[MISTI_MAX_PARAMS + 1];
-    for (int j = 0; j < cfg.slots && j <= MISTI_MAX_PARAMS; ++j) fv[j] = -llh[(long)s * cfg.slots + j];  // the objective is -llh
-    misti::nm_apply(cfg, st.sim + (long)s * (N + 1) * N, st.fsim + (long)s * (N + 1), st.iters + s, st.fcalls + s, st.phase + s,
-                    params + (long)s * cfg.slots * N, fv);
+    const long b0 = (long)s * cfg.slots;
+    misti::nm_apply(cfg, st.sim + (long)s * (N + 1) * N, st.fsim + (long)s * (N + 1), st.iters + s, st.fcalls + s, st.status + s,
+                    st.phase + s, params + b0 * N, llh + b0, true);  // the objective is -llh
 }
 
 }  // namespace
@@ -682,6 +679,7 @@ struct misti_ctx {
     int jsfs_minb = kJsfsMinBlocks;
     int correct_minb = kCorrectMinBlocks;
     int correct_coop = -1;  // -1 = by batch size
+    int nm_lookahead = -1;  // on-device Nelder-Mead: two iterations per round; -1 = by size (tuning knob MISTI_NM_LOOKAHEAD)
     int defer_post = -1;    // cpfit mode: post-split pass in the JSFS kernel; -1 = by batch size (tuning knob MISTI_DEFER_POST)
 };
 
@@ -842,6 +840,7 @@ int misti_ctx_create(int device, void* stream, misti_ctx** out) {
     if (const char* e = getenv("MISTI_CORRECT_MINB")) ctx->correct_minb = atoi(e);
     if (const char* e = getenv("MISTI_CORRECT_COOP")) ctx->correct_coop = atoi(e);
     if (const char* e = getenv("MISTI_DEFER_POST")) ctx->defer_post = atoi(e);
+    if (const char* e = getenv("MISTI_NM_LOOKAHEAD")) ctx->nm_lookahead = atoi(e);
     for (int i = 0; i < 3; ++i)
         if (cudaEventCreate(&ctx->ev[i]) != cudaSuccess) { delete ctx; return MISTI_E_CUDA; }
     if (cudaMalloc((void**)&ctx->d_small, (44 * 44 + 2 * 44) * sizeof(double)) != cudaSuccess) { delete ctx; return MISTI_E_CUDA; }
@@ -1200,7 +1199,10 @@ int misti_nelder_mead(misti_ctx* ctx, int32_t S, int32_t N, const double* x0, co
     if ((rc = sync_tables(ctx))) return rc;
     misti::NmConfig cfg;
     cfg.N = N;
-    cfg.slots = N + 1 > 4 ? N + 1 : 4;
+    // two iterations per round (look-ahead) while a round stays in the flat part of the latency curve of one evaluation
+    const bool look_fits = N <= misti::kNmLookaheadMaxN && (long)S * misti::nm_slots(N, true) <= kCoopMaxItems;
+    cfg.lookahead = ctx->nm_lookahead < 0 ? look_fits : (ctx->nm_lookahead != 0 && N <= misti::kNmLookaheadMaxN);
+    cfg.slots = misti::nm_slots(N, cfg.lookahead != 0);
     cfg.xatol = xatol; cfg.fatol = fatol;
     cfg.maxiter = maxiter < 0 ? LLONG_MAX : maxiter;
     cfg.maxfev = maxfev < 0 ? LLONG_MAX : maxfev;

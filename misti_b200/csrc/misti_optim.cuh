@@ -22,7 +22,8 @@ namespace misti {
 
 struct NmConfig {
     int N;             // parameters per simplex
-    int slots;         // points a simplex may submit per round: max(4, N + 1)
+    int slots;         // points a simplex may submit per round: nm_slots(N, lookahead)
+    int lookahead;     // two iterations per round (N <= kNmLookaheadMaxN)
     double xatol, fatol;
     long long maxiter, maxfev;  // LLONG_MAX = none
 };
@@ -83,6 +84,30 @@ MISTI_HD inline bool nm_retire(const NmConfig& c, const double* sim, const doubl
     return true;
 }
 
+// reflection-type candidates of a sorted simplex (_optimize.py:846-874), in the order of the decision codes: expansion,
+// reflection, outside and inside contraction -> pts[4][N]
+MISTI_HD inline void nm_candidates(int N, const double* sim, double* pts) {
+    for (int k = 0; k < N; ++k) {
+        double xbar = sim[k];
+        for (int j = 1; j < N; ++j) xbar = nm_add(xbar, sim[j * N + k]);  // np.add.reduce(sim[:-1], 0): row by row
+        xbar = nm_div(xbar, (double)N);
+        const double last = sim[N * N + k];
+        pts[0 * N + k] = nm_sub(nm_mul(3.0, xbar), nm_mul(2.0, last));   // (1 + rho chi) xbar - rho chi last
+        pts[1 * N + k] = nm_sub(nm_mul(2.0, xbar), nm_mul(1.0, last));   // (1 + rho) xbar - rho last
+        pts[2 * N + k] = nm_sub(nm_mul(1.5, xbar), nm_mul(0.5, last));   // (1 + psi rho) xbar - psi rho last
+        pts[3 * N + k] = nm_add(nm_mul(0.5, xbar), nm_mul(0.5, last));   // (1 - psi) xbar + psi last
+    }
+}
+
+// Look-ahead (as in misti_b200/optim.py): with the candidates of the current step a simplex also submits the candidates
+// of the NEXT step for every way the current one can end -- accepted candidate o, landing at rank k of the sorted
+// simplex: expansion (rank 0), reflection (ranks 0..N-1), either contraction (ranks 0..N): 3N + 3 scenarios of 4 points
+// -- so that one round of launches advances it by two iterations.  Decisions and counts are unchanged.
+constexpr int kNmLookaheadMaxN = 4;  // 4 (3N + 4) points per simplex and round: 28 ... 64
+MISTI_HD inline int nm_scenarios(int N) { return 3 * N + 3; }
+MISTI_HD inline int nm_scenario(int N, int o, int k) { return (o == 0 ? 0 : (o == 1 ? 1 : (o == 2 ? 1 + N : 2 + 2 * N))) + k; }
+MISTI_HD inline int nm_slots(int N, bool lookahead) { return lookahead ? 4 * (1 + nm_scenarios(N)) : (N + 1 > 4 ? N + 1 : 4); }
+
 // The points a simplex wants evaluated in this round, written to pts[slots][N]; returns how many (0 = none: done).
 // sim[(N+1)][N], fsim[N+1] are sorted except in phase NM_INIT (sim[0] = x0) and NM_SHRINK (vertices 1..N just moved).
 MISTI_HD inline int nm_propose(const NmConfig& c, double* sim, const double* fsim, const long long* iters, const long long* fcalls,
@@ -110,46 +135,36 @@ MISTI_HD inline int nm_propose(const NmConfig& c, double* sim, const double* fsi
         *phase = NM_DONE;
         return 0;
     }
-    // candidates (_optimize.py:846-874), in the order of the decision codes: expansion, reflection, outside, inside
-    for (int k = 0; k < N; ++k) {
-        double xbar = sim[k];
-        for (int j = 1; j < N; ++j) xbar = nm_add(xbar, sim[j * N + k]);  // np.add.reduce(sim[:-1], 0): row by row
-        xbar = nm_div(xbar, (double)N);
-        const double last = sim[N * N + k];
-        pts[0 * N + k] = nm_sub(nm_mul(3.0, xbar), nm_mul(2.0, last));   // (1 + rho chi) xbar - rho chi last
-        pts[1 * N + k] = nm_sub(nm_mul(2.0, xbar), nm_mul(1.0, last));   // (1 + rho) xbar - rho last
-        pts[2 * N + k] = nm_sub(nm_mul(1.5, xbar), nm_mul(0.5, last));   // (1 + psi rho) xbar - psi rho last
-        pts[3 * N + k] = nm_add(nm_mul(0.5, xbar), nm_mul(0.5, last));   // (1 - psi) xbar + psi last
+    nm_candidates(N, sim, pts);
+    if (!c.lookahead) return 4;
+    double t[(kNmLookaheadMaxN + 1) * kNmLookaheadMaxN];
+    for (int o = 0; o < 4; ++o) {
+        const int kmax = o == 0 ? 0 : (o == 1 ? N - 1 : N);
+        for (int k = 0; k <= kmax; ++k) {  // the simplex after candidate o has replaced the worst vertex and sorted to rank k
+            for (int j = 0; j <= N; ++j) {
+                const double* src = j < k ? sim + j * N : (j == k ? pts + o * N : sim + (j - 1) * N);
+                for (int i = 0; i < N; ++i) t[j * N + i] = src[i];
+            }
+            nm_candidates(N, t, pts + (long)(4 + 4 * nm_scenario(N, o, k)) * N);
+        }
     }
-    return 4;
+    return 4 * (1 + nm_scenarios(N));
 }
 
-// The round's objective values fv[] (in the order of the submitted points; NaN counts as +inf) applied to the simplex.
-MISTI_HD inline void nm_apply(const NmConfig& c, double* sim, double* fsim, long long* iters, long long* fcalls, int* phase,
-                              const double* pts, const double* fv_in) {
+MISTI_HD inline double nm_clean(double v, bool negate) {  // NaN counts as +inf; the device hands over llh = -objective
+    v = negate ? -v : v;
+    return v != v ? kInf : v;
+}
+
+// One reflection-type step (scipy's decision tree, _optimize.py:846-896) with the objective values fv[4] of pts[4][N].
+// Returns the accepted candidate (0..3; *rank = where it landed in the sorted simplex), -1 after a shrink move (phase
+// NM_SHRINK unless the budget is spent), -2 when the budget cut the iteration short.
+MISTI_HD inline int nm_step(const NmConfig& c, double* sim, double* fsim, long long* iters, long long* fcalls, int* phase,
+                            const double* pts, const double* fv_in, bool negate, int* rank) {
     const int N = c.N;
-    double fv[MISTI_MAX_PARAMS + 1];
     const long long left = c.maxfev - *fcalls;  // evaluations the budget still covers
-    const int n = *phase == NM_INIT ? (left < N + 1 ? (int)left : N + 1) : (*phase == NM_SHRINK ? (left < N ? (int)left : N) : 4);
-    for (int i = 0; i < n; ++i) fv[i] = fv_in[i] != fv_in[i] ? kInf : fv_in[i];
-    if (*phase == NM_INIT) {
-        for (int j = 0; j <= N; ++j) fsim[j] = j < n ? fv[j] : kInf;  // vertices past the budget keep scipy's initial +inf
-        *fcalls = n;
-        *iters = 1;
-        nm_sort(N, sim, fsim);
-        *phase = NM_STEP;
-        return;
-    }
-    if (*phase == NM_SHRINK) {
-        for (int j = 1; j <= n; ++j) fsim[j] = fv[j - 1];
-        *fcalls += n;
-        nm_sort(N, sim, fsim);
-        if (n == N) *iters += 1;  // an iteration cut short by the budget is not counted (:929-931)
-        *phase = NM_STEP;
-        return;
-    }
-    // scipy's decision tree (_optimize.py:846-896)
-    const double fxe = fv[0], fxr = fv[1], fxc = fv[2], fxcc = fv[3];
+    const double fxe = nm_clean(fv_in[0], negate), fxr = nm_clean(fv_in[1], negate), fxc = nm_clean(fv_in[2], negate),
+                 fxcc = nm_clean(fv_in[3], negate);
     const bool better = fxr < fsim[0];
     const bool second = fxr < fsim[N - 1];
     const bool take_e = better && fxe < fxr;
@@ -161,15 +176,19 @@ MISTI_HD inline void nm_apply(const NmConfig& c, double* sim, double* fsim, long
     const bool two = better || contract;  // scipy evaluates a second point
     if (two && left < 2) {  // ... but the budget ends after the reflection: the iteration is abandoned, nothing changes
         *fcalls += 1;
-        return;
+        return -2;
     }
     *fcalls += two ? 2 : 1;
     if (which >= 0) {
-        for (int k = 0; k < N; ++k) sim[N * N + k] = pts[which * N + k];
-        fsim[N] = fv[which];
+        const double fnew = which == 0 ? fxe : (which == 1 ? fxr : (which == 2 ? fxc : fxcc));
+        int k = 0;
+        for (int j = 0; j < N; ++j) k += fsim[j] <= fnew;  // the stable sort puts the new vertex behind its equals
+        *rank = k;
+        for (int i = 0; i < N; ++i) sim[N * N + i] = pts[which * N + i];
+        fsim[N] = fnew;
         nm_sort(N, sim, fsim);
         *iters += 1;
-        return;
+        return which;
     }
     // shrink towards the best vertex: sim[0] + sigma (sim[j] - sim[0]); scipy moves and evaluates the vertices one at a
     // time, so with `rest` evaluations left vertices 1..rest + 1 move (the last of them is not evaluated any more)
@@ -178,6 +197,43 @@ MISTI_HD inline void nm_apply(const NmConfig& c, double* sim, double* fsim, long
     for (int j = 1; j <= nmove; ++j)
         for (int k = 0; k < N; ++k) sim[j * N + k] = nm_add(sim[k], nm_mul(0.5, nm_sub(sim[j * N + k], sim[k])));
     if (rest >= 1) *phase = NM_SHRINK;  // else: nothing left to evaluate; the next round's budget test ends the fit
+    return -1;
+}
+
+// The round's values fv_in[] (in the order of the submitted points; objective values, or llh = -objective with `negate`)
+// applied to the simplex.
+MISTI_HD inline void nm_apply(const NmConfig& c, double* sim, double* fsim, long long* iters, long long* fcalls, int* status,
+                              int* phase, const double* pts, const double* fv_in, bool negate) {
+    const int N = c.N;
+    const long long left = c.maxfev - *fcalls;
+    if (*phase == NM_INIT) {
+        const int n = left < N + 1 ? (int)left : N + 1;
+        for (int j = 0; j <= N; ++j) fsim[j] = j < n ? nm_clean(fv_in[j], negate) : kInf;  // past the budget: scipy's initial +inf
+        *fcalls = n;
+        *iters = 1;
+        nm_sort(N, sim, fsim);
+        *phase = NM_STEP;
+        return;
+    }
+    if (*phase == NM_SHRINK) {
+        const int n = left < N ? (int)left : N;
+        for (int j = 1; j <= n; ++j) fsim[j] = nm_clean(fv_in[j - 1], negate);
+        *fcalls += n;
+        nm_sort(N, sim, fsim);
+        if (n == N) *iters += 1;  // an iteration cut short by the budget is not counted (:929-931)
+        *phase = NM_STEP;
+        return;
+    }
+    int rank = 0;
+    const int o = nm_step(c, sim, fsim, iters, fcalls, phase, pts, fv_in, negate, &rank);
+    if (!c.lookahead || o < 0) return;
+    // second iteration: the termination tests in between, then the scenario that came true
+    if (nm_retire(c, sim, fsim, *iters, *fcalls, status)) {
+        *phase = NM_DONE;
+        return;
+    }
+    const int q = nm_scenario(N, o, rank);
+    nm_step(c, sim, fsim, iters, fcalls, phase, pts + (long)(4 + 4 * q) * N, fv_in + 4 + 4 * q, negate, &rank);
 }
 
 }  // namespace misti

@@ -139,21 +139,23 @@ void hs_post_split(int numT, int splitT, const double* times, const double* lh, 
 
 // one simplex of the on-device Nelder-Mead (misti_optim.cuh), driven from the test: propose -> the test evaluates the
 // objective -> apply.  maxiter / maxfev < 0 = none.
-static misti::NmConfig hs_nm_cfg(int N, double xatol, double fatol, long long maxiter, long long maxfev) {
+static misti::NmConfig hs_nm_cfg(int N, double xatol, double fatol, long long maxiter, long long maxfev, int lookahead) {
     misti::NmConfig c;
-    c.N = N; c.slots = N + 1 > 4 ? N + 1 : 4; c.xatol = xatol; c.fatol = fatol;
+    c.N = N; c.lookahead = lookahead; c.slots = misti::nm_slots(N, lookahead != 0); c.xatol = xatol; c.fatol = fatol;
     c.maxiter = maxiter < 0 ? LLONG_MAX : maxiter; c.maxfev = maxfev < 0 ? LLONG_MAX : maxfev;
     return c;
 }
 
-int hs_nm_propose(int N, double xatol, double fatol, long long maxiter, long long maxfev, double* sim, double* fsim,
+int hs_nm_slots(int N, int lookahead) { return misti::nm_slots(N, lookahead != 0); }
+
+int hs_nm_propose(int N, double xatol, double fatol, long long maxiter, long long maxfev, int lookahead, double* sim, double* fsim,
                   long long* iters, long long* fcalls, int* status, int* phase, double* pts) {
-    return misti::nm_propose(hs_nm_cfg(N, xatol, fatol, maxiter, maxfev), sim, fsim, iters, fcalls, status, phase, pts);
+    return misti::nm_propose(hs_nm_cfg(N, xatol, fatol, maxiter, maxfev, lookahead), sim, fsim, iters, fcalls, status, phase, pts);
 }
 
-void hs_nm_apply(int N, double xatol, double fatol, long long maxiter, long long maxfev, double* sim, double* fsim,
-                 long long* iters, long long* fcalls, int* phase, const double* pts, const double* fv) {
-    misti::nm_apply(hs_nm_cfg(N, xatol, fatol, maxiter, maxfev), sim, fsim, iters, fcalls, phase, pts, fv);
+void hs_nm_apply(int N, double xatol, double fatol, long long maxiter, long long maxfev, int lookahead, double* sim, double* fsim,
+                 long long* iters, long long* fcalls, int* status, int* phase, const double* pts, const double* fv) {
+    misti::nm_apply(hs_nm_cfg(N, xatol, fatol, maxiter, maxfev, lookahead), sim, fsim, iters, fcalls, status, phase, pts, fv, false);
 }
 
 }  // extern "C"

@@ -453,6 +453,23 @@ def test_nelder_mead_on_the_device(engine, golden_datasets):
     assert (r["nit"] == 7).all() and (r["status"] == 2).all()
     r = engine.nelder_mead(x0, mids, np.zeros(3, dtype=np.int32), flags=sw.flags, maxfev=9)
     assert (r["nfev"] == 9).all() and (r["status"] == 1).all()
+    # one iteration per round (these small batches take two by default: look-ahead)
+    import os
+    import misti_b200
+    os.environ["MISTI_NM_LOOKAHEAD"] = "0"
+    try:
+        eng1 = misti_b200.Engine(0)
+    finally:
+        del os.environ["MISTI_NM_LOOKAHEAD"]
+    sw1 = Sweep(ds["times"], ds["lambdas"], rows, unfolded=True, cpfit=True, smooth=True, engine=eng1)
+    for args in ((40, [[2, 5, 12, 0.8, 1]]), (38, [[1, 4, 38, 3.0, 1]]), (40, [[1, 2, 10, 0.3, 1], [2, 5, 12, 0.8, 1]], [[1, 7, 0.05, 1]]),
+                 (41, [[1, 2, 10, 0.3, 1], [2, 5, 12, 0.8, 1]])):
+        sw1.add_model(*args)
+    one = sw1.solve(tol=1e-4, on_device=True)
+    eng1.close()
+    for k in ("x", "llh", "nfev", "nit", "success"):
+        assert np.array_equal(one[k], host[k], equal_nan=True), k
+    assert one["launches"] > 1.5 * dev["launches"]
     # basin-hopping: the same walkers with the local search on the device and on the host
     pairs = [(m3, 0), (m3, 1), (m1, 2)]
     a = sw.solve(pairs=pairs, globalOpt=True, niter=3, seed=5, on_device=True)

@@ -98,7 +98,7 @@ def test_lookahead_takes_the_same_decisions_in_half_the_calls(N):
         assert np.array_equal(res[True]["x"][s], ref.x) and res[True]["nfev"][s] == ref.nfev and res[True]["nit"][s] == ref.nit
 
 
-def _device_logic_nelder_mead(lib, fun, x0, xatol=1e-4, fatol=1e-4, maxiter=-1, maxfev=-1):
+def _device_logic_nelder_mead(lib, fun, x0, xatol=1e-4, fatol=1e-4, maxiter=-1, maxfev=-1, lookahead=0):
     """One simplex through the step logic of the ON-DEVICE Nelder-Mead (misti_b200/csrc/misti_optim.cuh, compiled for the
     host by tests/hostsim): propose -> evaluate here -> apply, until nothing is proposed."""
     import ctypes
@@ -108,8 +108,8 @@ def _device_logic_nelder_mead(lib, fun, x0, xatol=1e-4, fatol=1e-4, maxiter=-1, 
     sim[0] = x0
     iters, fcalls = ctypes.c_longlong(0), ctypes.c_longlong(0)
     status, phase = ctypes.c_int(-1), ctypes.c_int(0)
-    pts = np.zeros((max(4, N + 1), N))
-    cfg = (N, ctypes.c_double(xatol), ctypes.c_double(fatol), ctypes.c_longlong(maxiter), ctypes.c_longlong(maxfev))
+    pts = np.zeros((lib.hs_nm_slots(N, lookahead), N))
+    cfg = (N, ctypes.c_double(xatol), ctypes.c_double(fatol), ctypes.c_longlong(maxiter), ctypes.c_longlong(maxfev), lookahead)
     lib.hs_nm_propose.restype = ctypes.c_int
     rounds = 0
     while True:
@@ -120,14 +120,14 @@ def _device_logic_nelder_mead(lib, fun, x0, xatol=1e-4, fatol=1e-4, maxiter=-1, 
         fv = np.full(len(pts), np.nan)
         fv[:n] = [fun(pts[j].copy()) for j in range(n)]
         lib.hs_nm_apply(*cfg, sim.ctypes.data_as(dp), fsim.ctypes.data_as(dp), ctypes.byref(iters), ctypes.byref(fcalls),
-                        ctypes.byref(phase), pts.ctypes.data_as(dp), fv.ctypes.data_as(dp))
+                        ctypes.byref(status), ctypes.byref(phase), pts.ctypes.data_as(dp), fv.ctypes.data_as(dp))
         rounds += 1
         assert rounds < 100000
-    return dict(x=sim[0].copy(), fun=fsim[0], nit=iters.value, nfev=fcalls.value, status=status.value)
+    return dict(x=sim[0].copy(), fun=fsim[0], nit=iters.value, nfev=fcalls.value, status=status.value, rounds=rounds)
 
 
-@pytest.mark.parametrize("N", [1, 2, 3, 5])
-def test_device_step_logic_equals_scipy(hostsim, N):
+@pytest.mark.parametrize("N,lookahead", [(1, 0), (2, 0), (3, 0), (5, 0), (1, 1), (2, 1), (3, 1), (4, 1)])
+def test_device_step_logic_equals_scipy(hostsim, N, lookahead):
     """the decisions, iterates and counts of the on-device Nelder-Mead are scipy's, also through +inf / NaN objective
     values, shrinks, and the iteration / evaluation budgets"""
     rng = np.random.default_rng(10 + N)
@@ -168,8 +168,9 @@ def test_device_step_logic_equals_scipy(hostsim, N):
             mi = -1
         elif mf is None:
             mf = -1
-        got = _device_logic_nelder_mead(hostsim, fun, x0, maxiter=mi, maxfev=mf)
+        got = _device_logic_nelder_mead(hostsim, fun, x0, maxiter=mi, maxfev=mf, lookahead=lookahead)
         assert np.array_equal(got["x"], ref.x), (N, trial)
+        assert got["rounds"] <= (ref.nit if not lookahead else ref.nit // 2 + 1) + (got["nfev"] - ref.nit) + 2
         assert got["fun"] == ref.fun and got["nit"] == ref.nit and got["nfev"] == ref.nfev, (N, trial, got, ref.nit, ref.nfev)
         assert got["status"] == ref.status, (N, trial)
         shrinks += got["nfev"] > 2 * got["nit"] + N + 1
