@@ -204,6 +204,12 @@ def test_fit_matches_reference(golden_datasets, golden_fits):
     exp = fit["expect"]
     assert relerr(sol[0], exp["x"]) < 1e-6
     assert relerr(sol[1], exp["llh"]) < TOL
+    # SolveBatch: the same fit for every data row at once, taken through scipy's decisions on the device
+    M.SetJAFSBatch([list(d["sfs"])] + [list(r) for r in d["bs_rows"][1:4]])
+    x, llh, info = M.SolveBatch(fit["tol"])
+    assert x.shape == (4, len(exp["x"])) and np.array_equal(x[0], np.asarray(sol[0]))
+    assert llh[0] == sol[1] and info["nfev"][0] == len(exp["calls"]) and info["success"].all()
+    assert len(set(np.round(llh, 3))) == 4
 
 
 def test_sweep_lockstep_fits(engine, golden_datasets, golden_fits):
