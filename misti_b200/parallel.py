@@ -62,3 +62,37 @@ def evaluate_sharded(evaluate, params, model_ids=None, group=None, device=None):
     local = np.asarray(evaluate(params[idx], mids), dtype=np.float64)
     local = local.reshape(len(idx), -1)
     return gather_rows(local, B, group=group, device=device)
+
+
+def solve_sharded(solve, pairs, group=None, device=None):
+    """Fit a global list of independent (model, data row) pairs cooperatively: rank r fits the pairs
+    shard_indices(len(pairs), r, world) with `solve(pairs_shard) -> dict` (e.g. Sweep.solve: arrays x [n, P], llh [n],
+    nfev [n], nit [n], success [n] in the order of the shard) and every rank returns the dict for ALL pairs, in pair order.
+    The only collective is the all-gather of these few numbers per fit (basin-hopping walkers and bootstrap x split-time
+    fits shard the same way)."""
+    import torch.distributed as dist
+    pairs = np.asarray(pairs, dtype=np.int64).reshape(-1, 2)
+    K = pairs.shape[0]
+    if dist.is_available() and dist.is_initialized():
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+    else:
+        world, rank = 1, 0
+    idx = shard_indices(K, rank, world)
+    res = solve(pairs[idx]) if len(idx) else None
+    # the width of x is the same on every rank only if every rank knows the widest model: take it from the results
+    P_local = 0 if res is None else int(np.asarray(res["x"]).reshape(len(idx), -1).shape[1])
+    if world > 1:
+        import torch
+        t = torch.tensor([P_local], dtype=torch.int64, device=torch.device(device) if device is not None else torch.device("cpu"))
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+        P = int(t.item())
+    else:
+        P = P_local
+    cols = np.full((len(idx), P + 4), np.nan)
+    if res is not None:
+        cols[:, :P_local] = np.asarray(res["x"], dtype=np.float64).reshape(len(idx), -1)
+        for j, k in enumerate(("llh", "nfev", "nit", "success")):
+            cols[:, P + j] = np.asarray(res[k], dtype=np.float64)
+    full = gather_rows(cols, K, group=group, device=device)
+    return {"model": pairs[:, 0], "row": pairs[:, 1], "x": full[:, :P], "llh": full[:, P], "nfev": full[:, P + 1].astype(np.int64),
+            "nit": full[:, P + 2].astype(np.int64), "success": full[:, P + 3] != 0}

@@ -137,6 +137,16 @@ class Sweep:
             res["launches"] += r["launches"]
         return res
 
+    def solve_distributed(self, pairs=None, group=None, device=None, **kw):
+        """solve() with the (model, row) pairs dealt over the ranks of the torch.distributed job (one process per GPU, every
+        rank holding the same Sweep): each rank fits its share, one all-gather brings x, llh and the counts of every pair
+        to every rank (misti_b200.parallel.solve_sharded).  Without a process group it is solve()."""
+        from .parallel import solve_sharded
+        M, R = len(self.models), self.rows.shape[0]
+        if pairs is None:
+            pairs = [(m, r) for r in range(R) for m in range(M)]
+        return solve_sharded(lambda shard: self.solve(pairs=shard, **kw), pairs, group=group, device=device)
+
     def result_line(self, res, k, scaleTime=1.0, bs_id=None):
         """The reference's result line (MiSTI.py:240) for pair k of a solve() result."""
         m = self.models[int(res["model"][k])]

@@ -9,13 +9,24 @@ import numpy as np
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from misti_b200.parallel import evaluate_sharded, gather_rows, shard_indices, shard_sizes
+from misti_b200.parallel import evaluate_sharded, gather_rows, shard_indices, shard_sizes, solve_sharded
 
 
 def _fake_llh(params, mids):
     # a deterministic function of (params, model id) with R = 3 "data rows"
     base = (params ** 2).sum(axis=1) + (0 if mids is None else 100.0 * np.asarray(mids))
     return np.stack([base, base + 0.5, -base], axis=1)
+
+
+def _fake_solve(pairs):
+    # a deterministic "fit" per (model, row) pair; model 2 has two parameters, the others one (x padded with NaN)
+    pairs = np.asarray(pairs)
+    n = len(pairs)
+    x = np.full((n, 2), np.nan)
+    x[:, 0] = pairs[:, 0] + 0.1 * pairs[:, 1]
+    x[pairs[:, 0] == 2, 1] = 7.0
+    return {"x": x, "llh": -(pairs[:, 0] * 10.0 + pairs[:, 1]), "nfev": 30 + pairs[:, 1], "nit": 15 + pairs[:, 0],
+            "success": pairs[:, 1] != 3}
 
 
 def _worker(rank, world, port, B, out):
@@ -35,6 +46,12 @@ def _worker(rank, world, port, B, out):
     # rows of unequal shard sizes (B odd) and a scalar column
     col = gather_rows(np.arange(rank, B, world, dtype=float).reshape(-1, 1), B)
     ok = ok and np.array_equal(col[:, 0], np.arange(B, dtype=float))
+    # fits: every rank solves its share of the (model, row) pairs and ends up with all results in pair order
+    pairs = [(m, r) for r in range(5) for m in range(3)]
+    res = solve_sharded(_fake_solve, pairs)
+    ref = _fake_solve(np.array(pairs))
+    ok = ok and all(np.array_equal(res[k], ref[k], equal_nan=True) for k in ("x", "llh", "nfev", "nit", "success"))
+    ok = ok and np.array_equal(res["model"], np.array(pairs)[:, 0])
     out[rank] = bool(ok)
     dist.destroy_process_group()
 
@@ -64,3 +81,6 @@ def test_world_size_two_gloo():
 def test_single_process_passthrough():
     params = np.random.default_rng(1).uniform(0, 1, (5, 2))
     assert np.array_equal(evaluate_sharded(_fake_llh, params), _fake_llh(params, None))
+    pairs = [(m, r) for r in range(4) for m in range(3)]
+    res, ref = solve_sharded(_fake_solve, pairs), _fake_solve(np.array(pairs))
+    assert all(np.array_equal(res[k], ref[k], equal_nan=True) for k in ("x", "llh", "nfev", "nit", "success"))
