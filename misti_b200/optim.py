@@ -341,7 +341,8 @@ def basinhopping_batch(fun, x0, niter=100, T=1.0, stepsize=0.5, interval=50, tar
         failures += (~r["success"]).astype(np.int64)
         fn, xn, okn = r["fun"], r["x"], r["success"]
         for w in range(W):  # Metropolis.accept_reject, with Python's min(0, nan) == 0 semantics
-            prod = -(fn[w] - energy[w]) * beta
+            with np.errstate(invalid="ignore"):  # inf - inf = nan: min(0, nan) is 0 in Python, as in scipy
+                prod = -(fn[w] - energy[w]) * beta
             wgt = math.exp(min(0, prod))
             accept = wgt >= rngs[w].uniform() and (okn[w] or not ok[w])
             if accept:
