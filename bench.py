@@ -12,6 +12,8 @@ One "step" = one pass of the hot path over one batch of B synthetic parameter ve
              buffers, H2D of the parameters and D2H of llh + status inside the timed region
   roofline   the dominant kernel against the measured FP64 peak (dense-equivalent algorithmic FLOPs of
              SURVEY.md 8d AND the FLOPs actually executed, counted from the kernel's own term counter)
+  time_to_fit   one Nelder-Mead fit of the bench model stepped on the device (misti_nelder_mead) next to the same fit by
+             the CPU oracle on one core (the second half of the BASELINE metric; rank 0, N = 1 only)
   cpu_baseline  the CPU oracle (oracle/misti_oracle.py, numpy/scipy port of the reference path) timed on
              the host cores on a bounded sample of the same parameter vectors (rank 0, N = 1 only)
 
@@ -321,6 +323,26 @@ def run_gpu(args):
         cpu = {"value": rate, "unit": "evals/s", "cores": cores, "kind": "port",
                "sample": "%d of the batch's parameter vectors through oracle/misti_oracle.py (numpy/scipy port of the reference "
                          "path), %d worker processes, %.1f s" % (n, cores, dt)}
+    # second half of the BASELINE metric: time to fit.  One Nelder-Mead fit of the bench model (MiSTI.py ... -mi 2 5 12 0.8 1
+    # --cpfit, tol 1e-4) stepped on the device, next to the same fit by the CPU oracle (scipy Nelder-Mead, one core).
+    ttf = None
+    if world == 1 and not args.skip_cpu:
+        import numpy as np
+        x0, one, zero = np.array([[BAND[3]]]), np.array([mid], dtype=np.int32), np.zeros(1, dtype=np.int32)
+        eng.nelder_mead(x0, one, zero, flags=flags, xatol=1e-4, fatol=1e-4, maxiter=1000)
+        t0 = time.perf_counter()
+        fit = eng.nelder_mead(x0, one, zero, flags=flags, xatol=1e-4, fatol=1e-4, maxiter=1000)
+        gpu_s = time.perf_counter() - t0
+        from oracle.misti_oracle import OracleModel
+        om = OracleModel(ds["times"], ds["lambdas"], ds["sfs"], SPLIT_T, [BAND], [], cpfit=True, smooth=True, unfolded=True)
+        t0 = time.perf_counter()
+        ref = om.solve(1e-4)
+        cpu_s = time.perf_counter() - t0
+        ref_x, ref_llh = ref[0], ref[1]
+        ttf = {"config": "config2: one Nelder-Mead fit of the optimised band (tol 1e-4, start 0.8)", "gpu_s": gpu_s,
+               "gpu_x": fit["x"][0].tolist(), "gpu_llh": float(-fit["fun"][0]), "gpu_nfev": int(fit["nfev"][0]),
+               "gpu_rounds_of_launches": int(fit["launches"]), "cpu_s": cpu_s, "cpu_kind": "port", "cpu_cores": 1,
+               "cpu_x": [float(v) for v in ref_x], "cpu_llh": float(ref_llh)}
     line = {"metric": METRIC, "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
@@ -328,7 +350,7 @@ def run_gpu(args):
                        "parallelism": "independent items sharded across ranks; all_gather of llh only"},
             "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": B * 8, "d2h_bytes_per_step": B * 8 + B * 4,
                     "ms_per_step": e2e_ms / args.steps},
-            "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks}
+            "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "time_to_fit": ttf, "clocks": clocks}
     _emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
