@@ -32,6 +32,7 @@ class Sweep:
         self.mixtureTH = float(mixtureTH)
         self.models = []     # per model: dict(id, splitT (as given), mi, pu, init, n_params, host)
         self._base_grid = None
+        self._mid_arr = None
 
     def add_model(self, splitT, mi=(), pu=()):
         """Same arguments as the MiSTI.py command line: split time (may be fractional), -mi 5-tuples, -pu 4-tuples."""
@@ -47,6 +48,12 @@ class Sweep:
                                 n_params=len(init), host=host))
         return len(self.models) - 1
 
+    def _model_ids(self):
+        """engine model id of every model of the sweep, as an array (looked up per item of every batch)"""
+        if self._mid_arr is None or len(self._mid_arr) != len(self.models):
+            self._mid_arr = np.array([m["id"] for m in self.models], dtype=np.int32)
+        return self._mid_arr
+
     # -- evaluation of arbitrary (model, params, row) triples ----------------------------------------
     def evaluate(self, model_idx, params, row_idx):
         model_idx = np.asarray(model_idx, dtype=np.int64).reshape(-1)
@@ -55,7 +62,7 @@ class Sweep:
         X = np.zeros((K, P))
         params = np.asarray(params, dtype=np.float64).reshape(K, -1) if K else np.zeros((0, P))
         X[:, :params.shape[1]] = params
-        mids = np.array([self.models[i]["id"] for i in model_idx], dtype=np.int32)
+        mids = self._model_ids()[model_idx]
         out = self.engine.evaluate(X, model_ids=mids, flags=self.flags, mixtureTH=self.mixtureTH, want=("status",),
                                    row_ids=np.asarray(row_idx, dtype=np.int32))
         MigrationInference.COUNT_LLH += K
@@ -113,7 +120,7 @@ class Sweep:
                 llh, _ = self.evaluate(pairs[sel[who], 0], X, pairs[sel[who], 1])
                 return -llh
             dev = on_device is True or (on_device == "auto" and speculative and sel.size * max(4, P + 1) <= self.DEVICE_NM_MAX_POINTS)
-            mids = np.array([self.models[m]["id"] for m in pairs[sel, 0]], dtype=np.int32)
+            mids = self._model_ids()[pairs[sel, 0]]
 
             def device_nm(xs, mids=mids, rows=pairs[sel, 1], **kw):
                 r = self.engine.nelder_mead(xs, mids, rows, flags=self.flags, mixtureTH=self.mixtureTH, **kw)
