@@ -482,3 +482,37 @@ def test_nelder_mead_on_the_device(engine, golden_datasets):
     b = sw.solve(pairs=pairs, globalOpt=True, niter=3, seed=5, on_device=False)
     for k in ("x", "llh", "nfev"):
         assert np.array_equal(a[k], b[k], equal_nan=True), k
+
+
+@pytest.mark.gpu
+def test_command_line_reproduces_the_reference_run(capsys, tmp_path):
+    """python -m misti_b200.cli with MiSTI.py's arguments (MiSTI.py:43-140) on the synthetic files of BASELINE config 2:
+    the result line (MiSTI.py:240) carries the reference's fitted rate and likelihood (golden fit), the .mi file is
+    written with -bs 0; the sweep form prints one such line per (row, split time)."""
+    import os
+    import re
+    from misti_b200 import cli
+    data = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "data", "synthetic")
+    import json
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fits.json")) as f:
+        gold = [g for g in json.load(f)["fits"] if g["name"] == "fit_c2_cpfit"][0]["expect"]
+    out_mi = str(tmp_path / "run.mi")
+    common = ["--funits", os.path.join(data, "setunits.txt"), "-wd", data]
+    # bs.sfs: row 0 = the data (column sums of m.sfs, utils/generateJSFS_bs.py:39-48); -bs 0 selects it and writes the .mi file
+    rc = cli.main(["m1.psmc", "m2.psmc", "bs.sfs", "40", "-uf", "-mi", "2", "5", "12", "0.8", "1", "--cpfit", "-bs", "0", "-o", out_mi] + common)
+    text = capsys.readouterr().out
+    assert rc == 0
+    m = re.search(r"bs_id = 0 \tsplitT = 40\.0 \ttime = (\S+) \tmigration rates optim = \[(\S+)\] \tllh = (\S+)", text)
+    assert m, text[-2000:]
+    assert abs(float(m.group(2)) - gold["x"][0]) < 1e-6 * gold["x"][0]
+    assert relerr(float(m.group(3)), gold["llh"]) < TOL
+    assert "Total number of likelihood function calls is" in text
+    assert os.path.exists(os.path.join(data, out_mi)) or os.path.exists(out_mi)
+    # sweep form: three split times x two bootstrap rows in one process
+    rc = cli.main(["m1.psmc", "m2.psmc", "bs.sfs", "40", "-uf", "-mi", "1", "4", "st", "3", "1", "--cpfit", "--st-grid", "39", "41",
+                   "--bs-rows", "0", "1"] + common)
+    text = capsys.readouterr().out
+    assert rc == 0
+    lines = [ln for ln in text.splitlines() if ln.startswith("bs_id = ")]
+    assert len(lines) == 6 and all("llh = -" in ln for ln in lines)
+    assert sorted({ln.split("\t")[1].strip() for ln in lines}) == ["splitT = 39", "splitT = 40", "splitT = 41"]
