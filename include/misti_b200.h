@@ -101,6 +101,10 @@ void misti_ctx_destroy(misti_ctx* ctx);
 const char* misti_last_error(const misti_ctx* ctx);
 int misti_ctx_set_stream(misti_ctx* ctx, void* stream);
 int misti_ctx_synchronize(misti_ctx* ctx);
+/* Optional: size the context's scratch buffers for batches of up to B items with P parameters and rows_per_item
+ * likelihoods each (1 with misti_eval_io.row_ids, else the number of data rows), for the grids and models registered so
+ * far, so that a run whose batches grow does not re-allocate on the way. */
+int misti_ctx_reserve(misti_ctx* ctx, int32_t B, int32_t P, int32_t rows_per_item);
 
 /* Register a merged PSMC time grid: times[numT-1] interval lengths and lh[numT][2] apparent
  * coalescence rates of the two genomes (InputData.times / .lambdas from migrationIO.ReadPSMC,

@@ -47,6 +47,7 @@ SIGNATURES = {
     "misti_last_error": (ctypes.c_char_p, [ctypes.c_void_p]),
     "misti_ctx_set_stream": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "misti_ctx_synchronize": (ctypes.c_int, [ctypes.c_void_p]),
+    "misti_ctx_reserve": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32]),
     "misti_add_grid": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, c_double_p, c_double_p, c_int32_p]),
     "misti_add_model": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ModelDesc), c_int32_p]),
     "misti_clear_models": (ctypes.c_int, [ctypes.c_void_p]),

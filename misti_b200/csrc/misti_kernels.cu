@@ -808,6 +808,26 @@ int ensure_batch(misti_ctx* ctx, size_t B) {
     return 0;
 }
 
+// device staging buffers of the host-pointer calls, for chunks of up to n items
+int ensure_staging(misti_ctx* ctx, size_t n, size_t R, size_t Pe) {
+    const int numT_max = ctx->numT_max;
+    if (n <= ctx->st_cap && R <= ctx->st_capR && Pe <= ctx->st_capP && numT_max <= ctx->st_numT) return 0;
+    int rc;
+    size_t ncap = ctx->st_cap ? ctx->st_cap : 1024;
+    while (ncap < n) ncap *= 2;
+    const size_t nR = R > ctx->st_capR ? R : ctx->st_capR;
+    const size_t nP = Pe > ctx->st_capP ? Pe : ctx->st_capP;
+    if ((rc = realloc_exact(ctx, &ctx->s_params, ncap * nP))) return rc;
+    if ((rc = realloc_exact(ctx, &ctx->s_llh, ncap * nR))) return rc;
+    if ((rc = realloc_exact(ctx, &ctx->s_jafs, ncap * 7))) return rc;
+    if ((rc = realloc_exact(ctx, &ctx->s_jafs_raw, ncap * 7))) return rc;
+    if ((rc = realloc_exact(ctx, &ctx->s_model_ids, ncap))) return rc;
+    if ((rc = realloc_exact(ctx, &ctx->s_terms, ncap))) return rc;
+    if ((rc = realloc_exact(ctx, &ctx->s_row_ids, ncap))) return rc;
+    ctx->st_cap = ncap; ctx->st_capR = nR; ctx->st_capP = nP; ctx->st_numT = numT_max;
+    return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -888,6 +908,18 @@ int misti_ctx_synchronize(misti_ctx* ctx) {
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
     return 0;
+}
+
+int misti_ctx_reserve(misti_ctx* ctx, int32_t B, int32_t P, int32_t rows_per_item) {
+    if (!ctx) return MISTI_E_ARG;
+    if (B < 0 || P < 0 || P > MISTI_MAX_PARAMS || rows_per_item < 1)
+        return fail(ctx, MISTI_E_ARG, "misti_ctx_reserve: bad arguments");
+    if (B == 0 || ctx->h_models.empty()) return 0;
+    CK(cudaSetDevice(ctx->device));
+    const size_t n = B < kMaxChunk ? (size_t)B : (size_t)kMaxChunk;
+    int rc;
+    if ((rc = ensure_batch(ctx, n))) return rc;
+    return ensure_staging(ctx, n, (size_t)rows_per_item, (size_t)(P > 0 ? P : 1));
 }
 
 int misti_add_grid(misti_ctx* ctx, int32_t numT, const double* times, const double* lh, int32_t* grid_id) {
@@ -1128,20 +1160,7 @@ int misti_eval_batch(misti_ctx* ctx, int32_t B, int32_t P, const double* params,
             if (model_ids[b] < 0 || model_ids[b] >= n_models) return fail(ctx, MISTI_E_ARG, "misti_eval_batch: unknown model id");
     for (long off = 0; off < B; off += kMaxChunk) {
         const int n = (int)((B - off) < kMaxChunk ? (B - off) : kMaxChunk);
-        if ((size_t)n > ctx->st_cap || (size_t)R > ctx->st_capR || (size_t)Pe > ctx->st_capP || numT_max > ctx->st_numT) {
-            size_t ncap = ctx->st_cap ? ctx->st_cap : 1024;
-            while (ncap < (size_t)n) ncap *= 2;
-            const size_t nR = (size_t)R > ctx->st_capR ? (size_t)R : ctx->st_capR;
-            const size_t nP = (size_t)Pe > ctx->st_capP ? (size_t)Pe : ctx->st_capP;
-            if ((rc = realloc_exact(ctx, &ctx->s_params, ncap * nP))) return rc;
-            if ((rc = realloc_exact(ctx, &ctx->s_llh, ncap * nR))) return rc;
-            if ((rc = realloc_exact(ctx, &ctx->s_jafs, ncap * 7))) return rc;
-            if ((rc = realloc_exact(ctx, &ctx->s_jafs_raw, ncap * 7))) return rc;
-            if ((rc = realloc_exact(ctx, &ctx->s_model_ids, ncap))) return rc;
-            if ((rc = realloc_exact(ctx, &ctx->s_terms, ncap))) return rc;
-            if ((rc = realloc_exact(ctx, &ctx->s_row_ids, ncap))) return rc;
-            ctx->st_cap = ncap; ctx->st_capR = nR; ctx->st_capP = nP; ctx->st_numT = numT_max;
-        }
+        if ((rc = ensure_staging(ctx, (size_t)n, (size_t)Rl, (size_t)Pe))) return rc;  // Rl likelihoods per item
         const bool need_lc_io = io->lc_inject || io->lc_out;
         if (need_lc_io && (rc = ensure(ctx, &ctx->s_lc_io, &ctx->s_lc_io_cap, (size_t)n * 2 * numT_max))) return rc;
         if (io->pr_out && (rc = ensure(ctx, &ctx->s_pr, &ctx->s_pr_cap, (size_t)n * (numT_max + 1) * 6))) return rc;

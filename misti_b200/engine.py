@@ -96,6 +96,11 @@ class Engine:
     def synchronize(self):
         self._check(self._lib.misti_ctx_synchronize(self._h))
 
+    def reserve(self, B, P=1, rows_per_item=1):
+        """Size the scratch buffers for batches of up to B items (optional; avoids re-allocation while batches grow).
+        rows_per_item: likelihoods per item -- 1 for calls with row_ids, else the number of data rows."""
+        self._check(self._lib.misti_ctx_reserve(self._h, int(B), int(P), int(rows_per_item)))
+
     # -- registration ---------------------------------------------------------------------------
     def add_grid(self, times, lambdas):
         lh = _as_f64(lambdas).reshape(-1, 2)

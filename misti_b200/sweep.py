@@ -114,6 +114,7 @@ class Sweep:
             res["launches"] += 1
         for P in sorted(set(nparams[nparams > 0].tolist())):
             sel = np.nonzero(nparams == P)[0]
+            self.engine.reserve(sel.size * max(4, P + 1), Pmax)  # a step submits four candidates (or a shrink) per simplex
             x0 = np.array([self.models[m]["init"] for m in pairs[sel, 0]], dtype=np.float64)
 
             def fun(X, who, sel=sel):
