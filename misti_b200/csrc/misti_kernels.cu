@@ -41,7 +41,7 @@ constexpr int kJsfsWarps = 4;      // warps per block of the JSFS kernel (8 item
 constexpr int kJsfsMinBlocks = 3;  // occupancy target: caps the kernel at 168 registers per thread (12 warps per SM)
 constexpr int kDeferPostMaxItems = 16384;  // up to here the post-split pass of cpfit mode runs in the JSFS kernel
 constexpr int kPostSmemDoubles = 1024;  // shared-memory budget of the JSFS kernel for a model's post-split table (8 KB)
-constexpr int kMaxChunk = 1 << 20;
+constexpr int kMaxChunk = 1 << 18;  // items per launch: the machine is full from 65 536 on; scratch is ~6 KB per item (records, rates)
 constexpr int kPitch = 2;  // per interval and item the rate buffer holds la0, la1
 
 static __device__ const double d_l8[8][8] = MISTI_L8_INIT;
@@ -679,6 +679,7 @@ struct misti_ctx {
     int jsfs_minb = kJsfsMinBlocks;
     int correct_minb = kCorrectMinBlocks;
     int correct_coop = -1;  // -1 = by batch size
+    int max_chunk = kMaxChunk;  // items per launch (test knob MISTI_MAX_CHUNK: chunk boundaries with small batches)
     int nm_lookahead = -1;  // on-device Nelder-Mead: two iterations per round; -1 = by size (tuning knob MISTI_NM_LOOKAHEAD)
     int defer_post = -1;    // cpfit mode: post-split pass in the JSFS kernel; -1 = by batch size (tuning knob MISTI_DEFER_POST)
 };
@@ -861,6 +862,10 @@ int misti_ctx_create(int device, void* stream, misti_ctx** out) {
     if (const char* e = getenv("MISTI_CORRECT_COOP")) ctx->correct_coop = atoi(e);
     if (const char* e = getenv("MISTI_DEFER_POST")) ctx->defer_post = atoi(e);
     if (const char* e = getenv("MISTI_NM_LOOKAHEAD")) ctx->nm_lookahead = atoi(e);
+    if (const char* e = getenv("MISTI_MAX_CHUNK")) {
+        const int v = atoi(e);
+        if (v >= 1 && v <= kMaxChunk) ctx->max_chunk = v;
+    }
     for (int i = 0; i < 3; ++i)
         if (cudaEventCreate(&ctx->ev[i]) != cudaSuccess) { delete ctx; return MISTI_E_CUDA; }
     if (cudaMalloc((void**)&ctx->d_small, (44 * 44 + 2 * 44) * sizeof(double)) != cudaSuccess) { delete ctx; return MISTI_E_CUDA; }
@@ -916,7 +921,7 @@ int misti_ctx_reserve(misti_ctx* ctx, int32_t B, int32_t P, int32_t rows_per_ite
         return fail(ctx, MISTI_E_ARG, "misti_ctx_reserve: bad arguments");
     if (B == 0 || ctx->h_models.empty()) return 0;
     CK(cudaSetDevice(ctx->device));
-    const size_t n = B < kMaxChunk ? (size_t)B : (size_t)kMaxChunk;
+    const size_t n = B < ctx->max_chunk ? (size_t)B : (size_t)ctx->max_chunk;
     int rc;
     if ((rc = ensure_batch(ctx, n))) return rc;
     return ensure_staging(ctx, n, (size_t)rows_per_item, (size_t)(P > 0 ? P : 1));
@@ -1140,8 +1145,8 @@ int misti_eval_batch(misti_ctx* ctx, int32_t B, int32_t P, const double* params,
 
     if (flags & MISTI_FLAG_DEVICE_PTRS) {
         // asynchronous, everything already resident; chunks only bound the scratch size
-        for (long off = 0; off < B; off += kMaxChunk) {
-            const int n = (int)((B - off) < kMaxChunk ? (B - off) : kMaxChunk);
+        for (long off = 0; off < B; off += ctx->max_chunk) {
+            const int n = (int)((B - off) < ctx->max_chunk ? (B - off) : ctx->max_chunk);
             rc = eval_chunk(ctx, n, P, params ? params + off * P : nullptr, model_ids ? model_ids + off : nullptr, model_default,
                             flags, mixture_th, io->lc_inject ? io->lc_inject + off * 2 * numT_max : nullptr, llh + off * Rl,
                             io->jafs ? io->jafs + off * 7 : nullptr, io->jafs_raw ? io->jafs_raw + off * 7 : nullptr,
@@ -1158,8 +1163,8 @@ int misti_eval_batch(misti_ctx* ctx, int32_t B, int32_t P, const double* params,
     if (model_ids)
         for (int b = 0; b < B; ++b)
             if (model_ids[b] < 0 || model_ids[b] >= n_models) return fail(ctx, MISTI_E_ARG, "misti_eval_batch: unknown model id");
-    for (long off = 0; off < B; off += kMaxChunk) {
-        const int n = (int)((B - off) < kMaxChunk ? (B - off) : kMaxChunk);
+    for (long off = 0; off < B; off += ctx->max_chunk) {
+        const int n = (int)((B - off) < ctx->max_chunk ? (B - off) : ctx->max_chunk);
         if ((rc = ensure_staging(ctx, (size_t)n, (size_t)Rl, (size_t)Pe))) return rc;  // Rl likelihoods per item
         const bool need_lc_io = io->lc_inject || io->lc_out;
         if (need_lc_io && (rc = ensure(ctx, &ctx->s_lc_io, &ctx->s_lc_io_cap, (size_t)n * 2 * numT_max))) return rc;
@@ -1226,7 +1231,7 @@ int misti_nelder_mead(misti_ctx* ctx, int32_t S, int32_t N, const double* x0, co
     cfg.maxiter = maxiter < 0 ? LLONG_MAX : maxiter;
     cfg.maxfev = maxfev < 0 ? LLONG_MAX : maxfev;
     const long B = (long)S * cfg.slots;
-    if (B > kMaxChunk) return fail(ctx, MISTI_E_ARG, "misti_nelder_mead: too many simplices for one call");
+    if (B > ctx->max_chunk) return fail(ctx, MISTI_E_ARG, "misti_nelder_mead: too many simplices for one call");
     // one block of device memory, carved up (8-byte items first)
     constexpr int kNmRing = 64;
     const size_t n_sim = (size_t)S * (N + 1) * N, n_fsim = (size_t)S * (N + 1);

@@ -516,3 +516,44 @@ def test_command_line_reproduces_the_reference_run(capsys, tmp_path):
     lines = [ln for ln in text.splitlines() if ln.startswith("bs_id = ")]
     assert len(lines) == 6 and all("llh = -" in ln for ln in lines)
     assert sorted({ln.split("\t")[1].strip() for ln in lines}) == ["splitT = 39", "splitT = 40", "splitT = 41"]
+
+
+@pytest.mark.gpu
+def test_batches_larger_than_one_launch_are_chunked(golden_datasets):
+    """a batch beyond the per-launch limit is evaluated in chunks (here the limit is lowered to 700 items): every output,
+    with per-item models and per-item data rows, equals the single-launch result bit for bit; an on-device fit that would
+    not fit in one launch is refused"""
+    import os
+    import misti_b200
+    ds = golden_datasets["synthetic"]
+    rng = np.random.default_rng(21)
+    B = 2500
+    params = np.column_stack([10 ** rng.uniform(-3, 0.6, B), rng.uniform(0, 2, B), rng.uniform(0, 0.3, B)])
+    res = []
+    for limit in (None, "700"):
+        if limit:
+            os.environ["MISTI_MAX_CHUNK"] = limit
+        try:
+            eng = misti_b200.Engine(0)
+        finally:
+            os.environ.pop("MISTI_MAX_CHUNK", None)
+        gid = eng.add_grid(ds["times"], ds["lambdas"])
+        mids = [eng.add_model(gid, 40, 0, bands=[(1, 5, 12, 0.8, 0)]),
+                eng.add_model(gid, 40, 0, bands=[(0, 2, 10, 0.3, 0), (1, 5, 12, 0.8, 1)], pulses=[(0, 7, 0.05, 2)]),
+                eng.add_model(gid, 38, 0)]
+        rows = [ds["sfs"]] + ds["bs_rows"][1:4]
+        eng.set_data(rows, True)
+        models = np.array([mids[b % 3] for b in range(B)], dtype=np.int32)
+        a = eng.evaluate(params, model_ids=models, flags=1 | 2 | 4 | 8, want=("jafs", "lc", "status", "nfev", "terms"))
+        b = eng.evaluate(params, model_ids=models, flags=1 | 2 | 4 | 8, want=("status",), row_ids=np.arange(B, dtype=np.int32) % 4)
+        c = eng.evaluate(params[:, :1], model=mids[0], flags=1 | 2 | 4 | 8, want=("jafs", "status"))
+        if limit:
+            with pytest.raises(misti_b200.MistiLibraryError):
+                eng.nelder_mead(params[:300, :1], np.full(300, mids[0], dtype=np.int32), flags=1 | 2 | 4 | 8)
+        res.append((a, b, c))
+        eng.close()
+    for x, y in zip(res[0], res[1]):
+        for k in x:
+            assert np.array_equal(x[k], y[k], equal_nan=True), k
+    assert res[0][0]["llh"].shape == (B, 4) and res[0][1]["llh"].shape == (B, 1)
+    assert np.array_equal(res[0][1]["llh"][:, 0], res[0][0]["llh"][np.arange(B), np.arange(B) % 4], equal_nan=True)
