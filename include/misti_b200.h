@@ -47,7 +47,8 @@ extern "C" {
 #define MISTI_CORRECTION_FAILED 2  /* "Lambda correction failed" (MigrationInference.py:575-578)              */
 #define MISTI_NONFINITE 3          /* the reference would have raised or produced NaN                         */
 #define MISTI_INFINITE_COAL_TIME 4 /* last interval before the split without migration (:475-476, ref. exits)  */
-#define MISTI_SKIPPED 6            /* item with model id -1: slot left empty by the on-device optimiser           */
+#define MISTI_SKIPPED 6            /* item whose model id is not a registered model (-1: slot left empty by the on-device
+                                      optimiser; device-pointer calls are not validated on the host): llh = NaN      */
 #define MISTI_STIFF 5              /* intervals WITH migration and (largest exit rate)*length > 256 are only seen after a
                                       run-away correction; they take a dense scaling-and-squaring step instead of
                                       the sweep (transparently: the item still ends with status 0).  The code is

@@ -58,7 +58,8 @@ misti_correct_kernel(int B, int P, const double* __restrict__ params, const int*
                      const ModelDesc* __restrict__ models, const double* __restrict__ times, const double* __restrict__ lh,
                      const double* __restrict__ gaux, const unsigned* __restrict__ cls_all, unsigned flags, double mixtureTH, const double* __restrict__ lc_inject, int numT_max, double* lc,
                      long stride, double* __restrict__ cpost, double* pr_out, int* __restrict__ status, int* __restrict__ nfev,
-                     double* __restrict__ rec, int seg_cap, int* __restrict__ nseg, int* __restrict__ counters, int defer_post) {
+                     double* __restrict__ rec, int seg_cap, int* __restrict__ nseg, int* __restrict__ counters, int defer_post,
+                     int n_models) {
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
     if (gtid < 8) counters[gtid] = 0;  // work and park counters of the two kernels that follow in the stream
     const int b = COOP ? gtid >> 2 : gtid;
@@ -71,7 +72,8 @@ misti_correct_kernel(int B, int P, const double* __restrict__ params, const int*
         __syncthreads();
     }
     if (b >= B) return;
-    if (model_ids && model_ids[b] < 0) {  // an empty slot of the on-device optimiser (all lanes of the item leave together)
+    if (model_ids && (unsigned)model_ids[b] >= (unsigned)n_models) {  // id -1: an empty slot of the on-device optimiser; any
+        // other id outside the registered models (device-pointer calls are not validated on the host) is skipped as well
         nseg[b] = 0;
         status[b] = MISTI_SKIPPED;
         nfev[b] = 0;
@@ -189,9 +191,9 @@ misti_jsfs_kernel(int B, int P, const double* __restrict__ params, const int* __
         if (i0 >= B) break;
         const bool has = i0 + (half & 1) < B;
         const int b = has ? i0 + (half & 1) : B - 1;
-        const int mid = model_ids ? model_ids[b] : model_default;
-        const ModelDesc& md = models[mid < 0 ? 0 : mid];  // an empty slot (status MISTI_SKIPPED) runs along inactive
         int st = out.status[b];
+        // an item the correction kernel skipped (model id outside the registered models) runs along inactive
+        const ModelDesc& md = models[st == MISTI_SKIPPED ? 0 : (model_ids ? model_ids[b] : model_default)];
         double raw_c, jn_c;
         int nt = 0;
         double cp[3] = {cpost[b], cpost[stride + b], cpost[2 * stride + b]};
@@ -507,12 +509,14 @@ __global__ void misti_gather_lc_kernel(int B, int numT_max, const int* __restric
                                        const ModelDesc* __restrict__ models, const double* __restrict__ lc, long stride,
                                        double* __restrict__ out, int defer_post, const double* __restrict__ cpost,
                                        const double* __restrict__ times, const double* __restrict__ lh,
-                                       const double* __restrict__ gaux) {
+                                       const double* __restrict__ gaux, int n_models) {
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     const long n = (long)B * 2 * numT_max;
     if (i >= n) return;
     const int b = (int)(i / (2 * numT_max)), j = (int)(i % (2 * numT_max));
-    const ModelDesc& md = models[model_ids ? model_ids[b] : model_default];
+    const int mid = model_ids ? model_ids[b] : model_default;
+    if ((unsigned)mid >= (unsigned)n_models) { out[i] = 0.0; return; }  // a skipped item
+    const ModelDesc& md = models[mid];
     const int t = j >> 1;
     double v = 0.0;
     if (t < md.numT) {
@@ -1058,7 +1062,7 @@ static int eval_chunk(misti_ctx* ctx, int B, int P, const double* d_params, cons
         B, P, d_params, d_model_ids, model_default, ctx->d_models, ctx->d_times, ctx->d_lh, ctx->d_gaux, ctx->d_cls, flags, mixture_th, \
         d_lc_inject, \
         numT_max, ctx->d_lc, stride, ctx->d_cpost, d_pr, ctx->d_status, ctx->d_nfev, ctx->d_rec, ctx->cap_seg, ctx->d_nseg, ctx->d_counts, \
-        defer_post)
+        defer_post, (int)ctx->h_models.size())
     switch (ctx->correct_minb) {  // register budget per thread: 4 -> 255, 8 -> 128, 12 -> 80 (tuning knob MISTI_CORRECT_MINB)
         case 4: MISTI_LAUNCH_CORRECT(4); break;
         case 12: MISTI_LAUNCH_CORRECT(12); break;
@@ -1106,7 +1110,7 @@ static int eval_chunk(misti_ctx* ctx, int B, int P, const double* d_params, cons
         misti_gather_lc_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(B, numT_max, d_model_ids, model_default,
                                                                                      ctx->d_models, ctx->d_lc, stride, d_lc_out,
                                                                                      defer_post, ctx->d_cpost, ctx->d_times, ctx->d_lh,
-                                                                                     ctx->d_gaux);
+                                                                                     ctx->d_gaux, (int)ctx->h_models.size());
         CK(cudaGetLastError());
         ctx->launches += 1;
     }

@@ -557,3 +557,35 @@ def test_batches_larger_than_one_launch_are_chunked(golden_datasets):
             assert np.array_equal(x[k], y[k], equal_nan=True), k
     assert res[0][0]["llh"].shape == (B, 4) and res[0][1]["llh"].shape == (B, 1)
     assert np.array_equal(res[0][1]["llh"][:, 0], res[0][0]["llh"][np.arange(B), np.arange(B) % 4], equal_nan=True)
+
+
+@pytest.mark.gpu
+def test_device_pointer_call_skips_unregistered_models(engine, golden_datasets):
+    """device-resident buffers (torch tensors): the asynchronous entry evaluates in place; an item whose model id is not
+    a registered model cannot be validated on the host and is skipped on the device (status MISTI_SKIPPED, llh NaN)
+    without touching its neighbours"""
+    import torch
+    import misti_b200
+    ds = golden_datasets["synthetic"]
+    engine.clear_models()
+    gid = engine.add_grid(ds["times"], ds["lambdas"])
+    mid = engine.add_model(gid, 40, 0, bands=[(1, 5, 12, 0.8, 0)])
+    engine.set_data([ds["sfs"]], True)
+    flags = 1 | 2 | 4 | 8
+    B = 70
+    p_h = np.random.default_rng(8).uniform(0, 3, (B, 1))
+    ids_h = np.full(B, mid, dtype=np.int32)
+    ids_h[[3, 33, 69]] = [-1, 12345, mid + 1]
+    ref = engine.evaluate(p_h, model=mid, flags=flags, want=("status",))
+    dev = torch.device("cuda", engine.device)
+    p_d, ids_d = torch.from_numpy(p_h).to(dev), torch.from_numpy(ids_h).to(dev)
+    llh_d = torch.zeros((B, 1), dtype=torch.float64, device=dev)
+    st_d = torch.zeros((B,), dtype=torch.int32, device=dev)
+    torch.cuda.synchronize(dev)
+    engine.evaluate_device(B, 1, p_d.data_ptr(), llh_d.data_ptr(), model_ids_ptr=ids_d.data_ptr(), flags=flags, status_ptr=st_d.data_ptr())
+    engine.synchronize()
+    llh, st = llh_d.cpu().numpy()[:, 0], st_d.cpu().numpy()
+    bad = np.zeros(B, dtype=bool)
+    bad[[3, 33, 69]] = True
+    assert (st[bad] == misti_b200._lib.SKIPPED).all() and np.isnan(llh[bad]).all()
+    assert np.array_equal(llh[~bad], ref["llh"][~bad, 0]) and np.array_equal(st[~bad], ref["status"][~bad])
