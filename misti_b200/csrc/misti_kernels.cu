@@ -122,8 +122,9 @@ misti_correct_kernel(int B, int P, const double* __restrict__ params, const int*
 
 // Where the results of an item go (the optional pointers may be null)
 struct ItemOut {
-    const double* data;  // [R][8] data rows
-    int R, unfolded;
+    const double* data;    // [R][8] data rows (7 counts, folded by the host if needed, + the likelihood constant)
+    const double* data_t;  // the same transposed, [8][Rs]: lanes that stride the rows read consecutive words
+    int R, Rs, unfolded;
     double *llh, *jafs, *jafs_raw;
     int *status, *terms;
     const int* row_ids;
@@ -146,9 +147,36 @@ __device__ __forceinline__ void emit_item(const ItemOut& o, const double* ysm, i
     if (o.row_ids) {  // one data row per item
         const int r = o.row_ids[b];
         if (lane == 0) o.llh[b] = (st == MISTI_OK && r >= 0 && r < o.R) ? misti::score_row(o.data + 8 * (long)r, logj) : bad;
+    } else if (st != MISTI_OK) {
+        for (int r = lane; r < o.R; r += 16) o.llh[(long)b * o.R + r] = bad;
     } else {
-        for (int r = lane; r < o.R; r += 16)
-            o.llh[(long)b * o.R + r] = st == MISTI_OK ? misti::score_row(o.data + 8 * (long)r, logj) : bad;
+        // every data row (bootstrap replicates): llh[r] = const_r + sum_i d_ri log p_i in the reference's order (score_row).
+        // The stage is a stream of 8 bytes written per (item, row) pair; four rows per lane are in flight so that the
+        // dependent multiply-adds of one row do not wait for the loads of the next.
+        double lj[7];
+#pragma unroll
+        for (int c = 0; c < 7; ++c) lj[c] = logj[c];
+        const double* dt = o.data_t;
+        const long Rs = o.Rs;
+        double* dst = o.llh + (long)b * o.R;
+        int r = lane;
+        for (; r + 48 < o.R; r += 64) {
+            double v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = dt[7 * Rs + r + 16 * u];
+#pragma unroll
+            for (int c = 0; c < 7; ++c)
+#pragma unroll
+                for (int u = 0; u < 4; ++u) v[u] += dt[c * Rs + r + 16 * u] * lj[c];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) dst[r + 16 * u] = v[u];
+        }
+        for (; r < o.R; r += 16) {
+            double v = dt[7 * Rs + r];
+#pragma unroll
+            for (int c = 0; c < 7; ++c) v += dt[c * Rs + r] * lj[c];
+            dst[r] = v;
+        }
     }
 }
 
@@ -1010,7 +1038,7 @@ int misti_set_data(misti_ctx* ctx, int32_t R, const double* sfs, const double* l
     if (!ctx) return MISTI_E_ARG;
     if (R < 1 || !sfs) return fail(ctx, MISTI_E_ARG, "misti_set_data: need at least one data row");
     CK(cudaSetDevice(ctx->device));
-    std::vector<double> rows((size_t)R * 8);
+    std::vector<double> rows((size_t)R * 16);  // [R][8] followed by the transposed copy [8][R]
     for (int r = 0; r < R; ++r) {
         const double* d = sfs + 8 * (size_t)r + 1;
         double* o = rows.data() + 8 * (size_t)r;
@@ -1028,6 +1056,7 @@ int misti_set_data(misti_ctx* ctx, int32_t R, const double* sfs, const double* l
             c -= lgamma(o[0] + 1.0) + lgamma(o[1] + 1.0) + lgamma(o[2] + 1.0) + lgamma(o[3] + 1.0);
         }
         o[7] = llh_const ? llh_const[r] : c;
+        for (int i = 0; i < 8; ++i) rows[8 * (size_t)R + (size_t)i * R + r] = o[i];
     }
     int rc;
     if ((rc = ensure(ctx, &ctx->d_data, &ctx->d_data_cap, rows.size()))) return rc;
@@ -1077,7 +1106,7 @@ static int eval_chunk(misti_ctx* ctx, int B, int P, const double* d_params, cons
     const int max_blocks = ctx->sm_count * per_sm;  // persistent grid: exactly the blocks that are resident together
     if (blocks > max_blocks) blocks = max_blocks;
     ItemOut out;
-    out.data = ctx->d_data; out.R = ctx->R; out.unfolded = ctx->unfolded;
+    out.data = ctx->d_data; out.data_t = ctx->d_data + 8 * (size_t)ctx->R; out.R = ctx->R; out.Rs = ctx->R; out.unfolded = ctx->unfolded;
     out.llh = d_llh; out.jafs = d_jafs; out.jafs_raw = d_jafs_raw; out.status = ctx->d_status; out.terms = d_terms;
     out.row_ids = d_row_ids;
 #define MISTI_LAUNCH_JSFS(MINB)                                                                                            \
