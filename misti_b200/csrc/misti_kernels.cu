@@ -704,6 +704,8 @@ struct misti_ctx {
     size_t d_nm_cap = 0;
     int* h_nm_counts = nullptr;     // pinned: points submitted per round (ring of kNmRing entries)
     cudaEvent_t nm_ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    double* d_score = nullptr;      // scratch of misti_score_spectra
+    size_t d_score_cap = 0;
     double* d_small = nullptr;  // 44*44 + 2*44 doubles for the table export kernels
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
     bool ev_valid = false;
@@ -911,7 +913,7 @@ void misti_ctx_destroy(misti_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     void* ptrs[] = {ctx->d_times, ctx->d_lh, ctx->d_gaux, ctx->d_cls, ctx->d_post, ctx->d_models, ctx->d_data, ctx->d_lc, ctx->d_cpost, ctx->d_status, ctx->d_nfev, ctx->d_conts, ctx->d_queue[0], ctx->d_queue[1], ctx->d_counts,
                     ctx->d_rec, ctx->d_nseg, ctx->s_params, ctx->s_llh, ctx->s_jafs, ctx->s_jafs_raw, ctx->s_model_ids, ctx->s_terms, ctx->s_row_ids, ctx->s_lc_io,
-                    ctx->s_pr, ctx->d_small, ctx->d_nm};
+                    ctx->s_pr, ctx->d_small, ctx->d_nm, ctx->d_score};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     for (int i = 0; i < 3; ++i)
@@ -1338,21 +1340,17 @@ int misti_score_spectra(misti_ctx* ctx, int32_t B, const double* spectra, double
     if (ctx->R < 1) return fail(ctx, MISTI_E_ARG, "misti_score_spectra: no data rows (misti_set_data)");
     if (B == 0) return 0;
     CK(cudaSetDevice(ctx->device));
-    double *d_sp = nullptr, *d_out = nullptr;
-    CK(cudaMalloc((void**)&d_sp, (size_t)B * 7 * sizeof(double)));
-    cudaError_t e = cudaMalloc((void**)&d_out, (size_t)B * ctx->R * sizeof(double));
-    if (e != cudaSuccess) { cudaFree(d_sp); return fail(ctx, MISTI_E_CUDA, cudaGetErrorString(e)); }
-    e = cudaMemcpyAsync(d_sp, spectra, (size_t)B * 7 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
-    if (e == cudaSuccess) {
-        misti_score_kernel<<<(B + 3) / 4, 128, 0, ctx->stream>>>(B, d_sp, ctx->d_data, ctx->R, ctx->unfolded, d_out);
-        e = cudaGetLastError();
-        ctx->launches += 1;
-    }
-    if (e == cudaSuccess) e = cudaMemcpyAsync(llh, d_out, (size_t)B * ctx->R * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    cudaFree(d_sp);
-    cudaFree(d_out);
-    if (e != cudaSuccess) return fail(ctx, MISTI_E_CUDA, std::string("misti_score_spectra: ") + cudaGetErrorString(e));
+    // context-owned scratch (one block: the spectra, then the likelihoods), grown on demand
+    const size_t n_sp = (size_t)B * 7, n_out = (size_t)B * ctx->R;
+    int rc;
+    if ((rc = ensure(ctx, &ctx->d_score, &ctx->d_score_cap, n_sp + n_out))) return rc;
+    double *d_sp = ctx->d_score, *d_out = ctx->d_score + n_sp;
+    CK(cudaMemcpyAsync(d_sp, spectra, n_sp * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    misti_score_kernel<<<(B + 3) / 4, 128, 0, ctx->stream>>>(B, d_sp, ctx->d_data, ctx->R, ctx->unfolded, d_out);
+    CK(cudaGetLastError());
+    ctx->launches += 1;
+    CK(cudaMemcpyAsync(llh, d_out, n_out * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
     return 0;
 }
 
