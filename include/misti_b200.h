@@ -148,6 +148,15 @@ int misti_nelder_mead(misti_ctx* ctx, int32_t S, int32_t N, const double* x0, co
  * MigrationInference.MaximumLLHFunction (MigrationInference.py:696-711) with the data spectrum. */
 int misti_score_spectra(misti_ctx* ctx, int32_t B, const double* spectra, double* llh);
 
+/* The forward map true rates -> PSMC-apparent rates, MigrationInference.CoalescentRates (MigrationInference.py:542-564;
+ * CorrectLambda.CoalRates, CorrectLambda.py:112-122), used by TestModel.py:120 and to write model-consistent PSMC input:
+ * the registered grid's rates are taken as the TRUE rates of model `model_id`.  mu0, mu1: the reference propagates every
+ * interval with the migration rates its CorrectLambda helper was left with by the preceding likelihood call (those of
+ * interval split_t - 1); the caller passes them.  Out (host pointers): lh_out[numT][2] and, nullable,
+ * pr_out[(min(split_t, numT) + 1)][3][2], the trajectory of the two 3-state chains (.Pr). */
+int misti_coalescent_rates(misti_ctx* ctx, int32_t model_id, int32_t P, const double* params, double mu0, double mu1,
+                           double* lh_out, double* pr_out);
+
 /* Device time in milliseconds of the two kernels of the last misti_eval_batch on this context
  * (CUDA events on the context's stream): out[0] = correction kernel, out[1] = JSFS+likelihood kernel.
  * Synchronises with the stream. */

@@ -59,6 +59,8 @@ SIGNATURES = {
                                          ctypes.c_uint32, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_int64,
                                          ctypes.c_int64, c_double_p, c_double_p, ctypes.POINTER(ctypes.c_int64),
                                          ctypes.POINTER(ctypes.c_int64), c_int32_p, ctypes.POINTER(ctypes.c_int64)]),
+    "misti_coalescent_rates": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, c_double_p, ctypes.c_double,
+                                              ctypes.c_double, c_double_p, c_double_p]),
     "misti_score_spectra": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, c_double_p, c_double_p]),
     "misti_last_kernel_ms": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_float)]),
     "misti_launch_count": (ctypes.c_int64, [ctypes.c_void_p]),

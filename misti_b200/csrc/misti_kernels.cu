@@ -614,6 +614,17 @@ __global__ void misti_state_to_jaf_kernel(int which, int* out) {
     }
 }
 
+// forward map true rates -> PSMC-apparent rates (CoalescentRates): one chain, one thread
+__global__ void misti_coal_rates_kernel(const ModelDesc* __restrict__ models, int model, const double* __restrict__ times,
+                                        const double* __restrict__ lh, const unsigned* __restrict__ cls_all,
+                                        const double* __restrict__ params, double mu0, double mu1, double* __restrict__ lh_out,
+                                        double* __restrict__ pr_out) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    const ModelDesc& md = models[model];
+    const double mu[2] = {mu0, mu1};
+    misti::coalescent_rates_item(md, times + md.grid_off, lh + 2 * (long)md.grid_off, params, mu, cls_all + md.cls_off, lh_out, pr_out);
+}
+
 // ---- Nelder-Mead on the device (misti_optim.cuh): one thread per simplex ---------------------------
 struct NmState {
     double *sim, *fsim;          // [S][(N+1) N], [S][N+1]
@@ -1365,6 +1376,32 @@ int misti_last_kernel_ms(misti_ctx* ctx, float* out2) {
 }
 
 int64_t misti_launch_count(const misti_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int misti_coalescent_rates(misti_ctx* ctx, int32_t model_id, int32_t P, const double* params, double mu0, double mu1,
+                           double* lh_out, double* pr_out) {
+    if (!ctx) return MISTI_E_ARG;
+    if (model_id < 0 || model_id >= (int)ctx->h_models.size() || P < 0 || P > MISTI_MAX_PARAMS || (P > 0 && !params) || !lh_out)
+        return fail(ctx, MISTI_E_ARG, "misti_coalescent_rates: bad arguments");
+    const ModelDesc& md = ctx->h_models[model_id];
+    if (md.n_params > P) return fail(ctx, MISTI_E_ARG, "misti_coalescent_rates: incorrect number of parameters");
+    CK(cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = sync_tables(ctx))) return rc;
+    const int n2 = md.splitT < md.numT ? md.splitT : md.numT;
+    const size_t n_lh = 2 * (size_t)md.numT, n_pr = 6 * (size_t)(n2 + 1);
+    if ((rc = ensure(ctx, &ctx->d_score, &ctx->d_score_cap, MISTI_MAX_PARAMS + n_lh + n_pr))) return rc;
+    double *d_par = ctx->d_score, *d_lh = d_par + MISTI_MAX_PARAMS, *d_pr = d_lh + n_lh;
+    if (P > 0) CK(cudaMemcpyAsync(d_par, params, (size_t)P * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemsetAsync(d_pr, 0, n_pr * sizeof(double), ctx->stream));
+    misti_coal_rates_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_models, model_id, ctx->d_times, ctx->d_lh, ctx->d_cls, d_par, mu0, mu1,
+                                                       d_lh, d_pr);
+    CK(cudaGetLastError());
+    ctx->launches += 1;
+    CK(cudaMemcpyAsync(lh_out, d_lh, n_lh * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (pr_out) CK(cudaMemcpyAsync(pr_out, d_pr, n_pr * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
 
 int misti_generator(misti_ctx* ctx, int32_t which, double l1, double l2, double m1, double m2, double* out) {
     if (!ctx || !out || (which != 0 && which != 1)) return MISTI_E_ARG;

@@ -281,4 +281,49 @@ MISTI_HD inline int correct_lambdas_item(const ModelDesc& md, const double* time
     return MISTI_OK;
 }
 
+// The forward map MigrationInference.CoalescentRates (MigrationInference.py:542-564 -> CorrectLambda.CoalRates,
+// CorrectLambda.py:112-122): `lc` = the true model rates [numT][2]; out: lh_out[numT][2] = the rates PSMC would see
+// (only the intervals before the split change) and Pr[(splitT + 1)][3][2], the trajectory of the two 3-state chains.
+// mu[2]: the reference never sets the migration rates of its CorrectLambda helper in this method, so EVERY interval is
+// propagated with the rates its last CorrectLambdas call left there (those of interval splitT - 1) -- the caller passes them.
+MISTI_HD inline void coalescent_rates_item(const ModelDesc& md, const double* times, const double* lc, const double* params,
+                                           const double* mu, const unsigned* cls, double* lh_out, double* Pr) {
+    const int numT = md.numT, splitT = md.splitT;
+    for (int i = 0; i < 2 * numT; ++i) lh_out[i] = lc[i];
+    double P0[2][3] = {{1.0, 0.0, 0.0}, {0.0, 1.0, 0.0}};
+    for (int t = 0; t < splitT; ++t) {
+        double mi_t[2], pu_t[2];
+        interval_rates(md, cls, params, t, mi_t, pu_t);
+        const double pu0 = pu_t[0], pu1 = pu_t[1], pu = pu0 + pu1;
+        if (pu > 0) {  // closed-form pulse on the 3-state chains (:549-556)
+            const int a = pu0 > 0 ? 0 : 1, b = 1 - a;
+            for (int k = 0; k < 2; ++k) {
+                double* p = P0[k];
+                const double om = 1 - pu;
+                const double qa = p[a] * (om * om);
+                const double qb = (p[a] * (pu * pu) + p[b]) + p[2] * pu;
+                const double q2 = ((p[a] * 2) * om) * pu + p[2] * om;
+                p[a] = qa; p[b] = qb; p[2] = q2;
+            }
+        }
+        if (t == 0 && Pr)
+            for (int s = 0; s < 3; ++s) { Pr[2 * s] = P0[0][s]; Pr[2 * s + 1] = P0[1][s]; }
+        const double T = times[t];
+        double M[9], E[9];
+        corr_matrix(lc + 2 * t, mu, T, M);
+        mat3_expm(M, E);
+        for (int k = 0; k < 2; ++k) {
+            double p[3];
+            mat3_vec(E, P0[k], p);
+            const double before = (P0[k][0] + P0[k][1]) + P0[k][2], after = (p[0] + p[1]) + p[2];
+            lh_out[2 * t + k] = -log(after / before) / T;
+            P0[k][0] = p[0]; P0[k][1] = p[1]; P0[k][2] = p[2];
+        }
+        if (Pr) {
+            double* q = Pr + 6 * (t + 1);
+            for (int s = 0; s < 3; ++s) { q[2 * s] = P0[0][s]; q[2 * s + 1] = P0[1][s]; }
+        }
+    }
+}
+
 }  // namespace misti

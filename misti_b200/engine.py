@@ -251,6 +251,18 @@ class Engine:
         return {"x": x, "fun": fun, "nit": nit, "nfev": nfev, "status": status.astype(np.int64), "success": status == 0,
                 "evaluations": int(info[1]), "launches": int(info[0])}
 
+    def coalescent_rates(self, model, params, mu):
+        """Forward map of model `model` (misti_coalescent_rates): its grid's rates taken as the true rates -> the rates PSMC
+        would see, lh [numT, 2], and the chain trajectory Pr [splitT + 1, 3, 2].  mu = (mu0, mu1), see the header."""
+        m = self.models[int(model)]
+        numT, n2 = m["numT"], min(m["splitT"], m["numT"])
+        p = _as_f64(params).reshape(-1)
+        lh, pr = np.zeros((numT, 2)), np.zeros((n2 + 1, 3, 2))
+        self._check(self._lib.misti_coalescent_rates(self._h, int(model), int(p.shape[0]), p.ctypes.data_as(_lib.c_double_p) if p.size else None,
+                                                     float(mu[0]), float(mu[1]), lh.ctypes.data_as(_lib.c_double_p),
+                                                     pr.ctypes.data_as(_lib.c_double_p)))
+        return lh, pr
+
     def score_spectra(self, spectra):
         """llh [B, R] of given spectra (7 weights each, normalised on the device) against every data row."""
         sp = _as_f64(spectra).reshape(-1, 7)

@@ -257,12 +257,37 @@ class MigrationInference:
         """MigrationInference.CorrectLambdas (MigrationInference.py:305-378) + Smooth, on the device.
         Fills self.lc / self.Pr; returns False where the reference does."""
         MigrationInference.CORRECTION_CALLED += 1
+        self._note_cl_mu()
         out = self._evaluate([self._current_params()], want=("lc", "pr", "status"))
         st = int(out["status"][0])
         self._store_chain(out)
         if st == _lib.CORRECTION_FAILED:
             MigrationInference.CORRECTION_FAILED += 1
         return st not in (_lib.CORRECTION_FAILED, _lib.NEGATIVE_PARAM)
+
+    def _note_cl_mu(self):
+        """CorrectLambdas leaves the migration rates of the last interval it visits in the CorrectLambda helper
+        (cl.SetMu, MigrationInference.py:324); CoalescentRates later uses exactly those for every interval."""
+        if self.splitT > 0:
+            t = min(self.splitT, self.numT) - 1
+            self._cl_mu = [float(self.mi[t][0]), float(self.mi[t][1])]
+
+    def CoalescentRates(self):
+        """MigrationInference.CoalescentRates (MigrationInference.py:542-564): the forward map, on the device -- the
+        object's rates self.lh are taken as the TRUE model rates (copied to self.lc) and replaced, before the split, by the
+        rates PSMC would see; self.Pr gets the trajectory of the 3-state chains.  Like the reference the method uses, for
+        EVERY interval, the migration rates the preceding CorrectLambdas / JAFSLikelihood call left in the helper (those of
+        the last interval before the split), and fails with AttributeError when there was no such call (TestModel.py:96,120
+        calls JAFSLikelihood first)."""
+        if getattr(self, "_cl_mu", None) is None:
+            raise AttributeError("'CorrectLambda' object has no attribute 'mu'")
+        eng = self._sync_engine()
+        lh, pr = eng.coalescent_rates(self._model_id, self._current_params(), self._cl_mu)
+        self.lc = [[float(v[0]), float(v[1])] for v in self.lh]
+        for t in range(min(self.splitT, self.numT)):
+            self.lh[t][0], self.lh[t][1] = float(lh[t, 0]), float(lh[t, 1])
+        self.Pr = [[[float(pr[t, s, 0]), float(pr[t, s, 1])] for s in range(3)] for t in range(pr.shape[0])]
+        self._registered = False  # the grid registered in the engine still holds the true rates
 
     def JAFSpectrum(self):
         """MigrationInference.JAFSpectrum (MigrationInference.py:467-506) for the CURRENT self.lc
@@ -287,6 +312,7 @@ class MigrationInference:
                 return -np.inf
         self.MapParameters(mu)
         MigrationInference.CORRECTION_CALLED += 1
+        self._note_cl_mu()
         out = self._evaluate([list(mu)], want=("jafs", "lc", "pr", "status"))
         st = int(out["status"][0])
         self._store_chain(out)

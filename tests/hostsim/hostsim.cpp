@@ -40,6 +40,10 @@ int hs_correct_lambdas(int numT, int splitT, int sampleDate, const double* times
                                        cls.data());
 }
 
+// CoalescentRates (forward map): lc[numT][2] true rates -> lh_out[numT][2], Pr[(splitT + 1)][3][2]
+void hs_coal_rates(int numT, int splitT, const double* times, const double* lc, int n_bands, const double* bands, int n_pulses,
+                   const double* pulses, int n_params, const double* params, double mu0, double mu1, double* lh_out, double* Pr);
+
 static void fill_model(misti::ModelDesc& md, int numT, int splitT, int sampleDate, int n_bands, const double* bands,
                        int n_pulses, const double* pulses, int n_params) {
     std::memset(&md, 0, sizeof(md));
@@ -53,6 +57,16 @@ static void fill_model(misti::ModelDesc& md, int numT, int splitT, int sampleDat
         md.pulse_pop[b] = (int)pulses[4 * b]; md.pulse_time[b] = (int)pulses[4 * b + 1];
         md.pulse_val[b] = pulses[4 * b + 2]; md.pulse_opt[b] = (int)pulses[4 * b + 3];
     }
+}
+
+void hs_coal_rates(int numT, int splitT, const double* times, const double* lc, int n_bands, const double* bands, int n_pulses,
+                   const double* pulses, int n_params, const double* params, double mu0, double mu1, double* lh_out, double* Pr) {
+    misti::ModelDesc md;
+    fill_model(md, numT, splitT, 0, n_bands, bands, n_pulses, pulses, n_params);
+    std::vector<unsigned> cls(numT);
+    for (int t = 0; t < numT; ++t) cls[t] = misti::interval_class(md, t);
+    const double mu[2] = {mu0, mu1};
+    misti::coalescent_rates_item(md, times, lc, params, mu, cls.data(), lh_out, Pr);
 }
 
 static int hs_types_buf[256];

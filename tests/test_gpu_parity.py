@@ -589,3 +589,28 @@ def test_device_pointer_call_skips_unregistered_models(engine, golden_datasets):
     bad[[3, 33, 69]] = True
     assert (st[bad] == misti_b200._lib.SKIPPED).all() and np.isnan(llh[bad]).all()
     assert np.array_equal(llh[~bad], ref["llh"][~bad, 0]) and np.array_equal(st[~bad], ref["status"][~bad])
+
+
+@pytest.mark.gpu
+def test_forward_map_of_the_drop_in_class():
+    """MigrationInference.CoalescentRates on the device against outputs of the unmodified reference
+    (tests/golden/coal.json): apparent rates, chain trajectory, lc = the true rates, AttributeError without a preceding
+    likelihood call (the reference's helper has no migration rates then), and the object keeps working afterwards"""
+    import json
+    import os
+    from misti_b200 import MigrationInference
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "coal.json")) as f:
+        cases = json.load(f)["cases"]
+    for c in cases:
+        M = MigrationInference(list(c["times"]), [list(v) for v in c["lambdas"]], [1] * 8, c["splitT"], [list(m) for m in c["mi"]],
+                               [list(p) for p in c["pu"]], unfolded=True, trueEPS=True)
+        with pytest.raises(AttributeError):
+            M.CoalescentRates()
+        llh0 = M.JAFSLikelihood([])
+        M.CoalescentRates()
+        assert relerr(M.lh, c["expect"]["lh"]) < 1e-11, c["name"]
+        assert relerr(np.array(M.Pr) + 1.0, np.array(c["expect"]["Pr"]) + 1.0) < 1e-13, c["name"]
+        assert relerr(M.lc, c["lambdas"]) == 0.0
+        # the object now holds the apparent rates: correcting them (cpfit) recovers a model close to the truth
+        llh1 = M.JAFSLikelihood([])
+        assert np.isfinite(llh0) and np.isfinite(llh1)

@@ -244,3 +244,35 @@ def test_post_split_pass_by_lane_groups(hostsim, golden_datasets):
             # (the sequential pass gets ed as exp(log(ed)): one rounding apart)
             assert relerr(grp, seq) < 1e-13, (splitT, lanes, grp, seq)
             assert relerr(req[splitT:], lc[splitT:, 0]) < 1e-13
+
+
+def _coal_cases():
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "coal.json")) as f:
+        return json.load(f)["cases"]
+
+
+def _mu_last(case):
+    """migration rates of the last interval before the split (what the reference's helper is left with, MigrationInference.py:324)"""
+    t = case["splitT"] - 1
+    mu = [0.0, 0.0]
+    for pop, a, b, val, _ in case["mi"]:
+        if a <= t < b:
+            mu[int(pop) - 1] = float(val)
+    return mu
+
+
+def test_forward_map_matches_reference(hostsim):
+    """the device's CoalescentRates (coalescent_rates_item, host build) against outputs of the unmodified reference"""
+    for case in _coal_cases():
+        T, L = _arr(case["times"]), _arr(case["lambdas"])
+        numT, st = len(L), case["splitT"]
+        Bn = _arr([[m[0] - 1, m[1], m[2], m[3], -1] for m in case["mi"]] or [[0] * 5])
+        Pu = _arr([[p[0] - 1, p[1], p[2], -1] for p in case["pu"]] or [[0] * 4])
+        mu = _mu_last(case)
+        lh, Pr, par = np.zeros((numT, 2)), np.zeros((st + 1, 3, 2)), _arr([0.0])
+        hostsim.hs_coal_rates(numT, st, _p(T), _p(L), len(case["mi"]), _p(Bn), len(case["pu"]), _p(Pu), 0, _p(par),
+                              ctypes.c_double(mu[0]), ctypes.c_double(mu[1]), _p(lh), _p(Pr))
+        assert relerr(lh, case["expect"]["lh"]) < 1e-11, case["name"]
+        assert relerr(Pr + 1.0, np.array(case["expect"]["Pr"]) + 1.0) < 1e-13, case["name"]
