@@ -53,12 +53,13 @@ class Units:
 class InputData:
     """What MiSTI.py hands to MigrationInference (migrationIO.InputData, migrationIO.py:46-63)."""
 
-    def __init__(self, times, lambdas, scaleTime, theta, divTime=-1, scaleEPS=1.0, rho=None, sampleDateDiscr=0, Tpsmc=None):
+    def __init__(self, times, lambdas, scaleTime, theta, divTime=-1, scaleEPS=1.0, rho=None, sampleDateDiscr=0, Tpsmc=None,
+                 mi=None, pu=None):
         self.times, self.lambdas = times, lambdas
         self.divergenceTime = divTime
         self.scaleTime, self.theta, self.scaleEPS, self.rho = scaleTime, theta, scaleEPS, rho
         self.sampleDateDiscr, self.Tpsmc = sampleDateDiscr, Tpsmc
-        self.mi, self.pu = None, None
+        self.mi, self.pu = mi, pu
 
 
 class JAFS:
@@ -233,3 +234,89 @@ ReadPSMCFile, ReadPSMC, ReadJAFS, OutputMigration = read_psmc_file, read_psmc, r
 
 def BootstrapJAFS(Jafs, normalize=False, rng=None):
     return bootstrap_jafs(Jafs.jafs, rng if rng is not None else random.Random(), normalize)
+
+
+def read_ms(argument_string):
+    """An ms command line -> the model it describes, as TestModel.py consumes it (migrationIO.ReadMS, migrationIO.py:659-766):
+    InputData with times (interval lengths in units of 2 N0 generations), lambdas (1 / population size per deme),
+    divergenceTime = index of the split interval, mi = [-mi pop start end rate 0] and pu = [-pu pop time rate 0].
+
+    Understood, with the reference's conventions (it warns that it makes many assumptions about the command line):
+    `-n i x`, `-en t i x`, `-eN t x` (sizes), `-em t i j r` (from time t on, migration rate r for deme i -- the target j is
+    not looked at -- until the next -em of the same deme or the split; MiSTI's rate is 2 r), `-es t i p` (pulse: a
+    fraction 1 - p of deme i's lineages moves), `-ej t i j` with i <= 2 (the split: deme i joins, and afterwards carries
+    the other deme's sizes).  Everything else is skipped token by token.  A size of exactly 0 means "not set here"."""
+    args = argument_string.split(" ")
+    sizes = [{0.0: 1.0}, {0.0: 1.0}]   # per deme: time -> size
+    bands = [{}, {}]                   # per deme: time -> rate
+    pulses = {}                        # time -> (rate, deme)
+    split_time, joining = 0, None
+    i = 0
+    while i < len(args):
+        a = args[i]
+        if a in ("-n", "-en"):
+            off = 0 if a == "-n" else 1
+            t = 0.0 if a == "-n" else float(args[i + 1])
+            deme, x = int(args[i + 1 + off]), float(args[i + 2 + off])
+            if deme not in (1, 2):
+                print("Population id should be 1 or 2.")
+                print(*args[i:i + 3 + off])
+                sys.exit(0)
+            sizes[deme - 1][t] = x
+            i += 3 + off
+        elif a == "-eN":
+            t, x = float(args[i + 1]), float(args[i + 2])
+            sizes[0][t] = x
+            sizes[1][t] = x
+            i += 3
+        elif a == "-em":
+            t, deme, r = float(args[i + 1]), int(args[i + 2]), float(args[i + 4])
+            bands[deme - 1][t] = r
+            i += 5
+        elif a == "-es":
+            t, deme, p = float(args[i + 1]), int(args[i + 2]), float(args[i + 3])
+            pulses[t] = (1 - p, deme)
+            i += 4
+        elif a == "-ej":
+            if int(args[i + 2]) <= 2:
+                split_time, joining = float(args[i + 1]), int(args[i + 2]) - 1
+            i += 4
+        else:
+            i += 1
+    if joining is None:
+        print("Populations should be merged. (-ej [time] 2 1)")
+        sys.exit(0)
+    events = set([split_time]) | set(pulses)
+    for k in (0, 1):
+        events |= set(sizes[k]) | set(bands[k])
+    grid = sorted(events)
+    index = {t: n for n, t in enumerate(grid)}
+    split_index = index[split_time]
+    # sizes held constant between their change points; after the split the joining deme carries the other one's
+    table = [[0, 0] for _ in grid]
+    for k in (0, 1):
+        for t, x in sizes[k].items():
+            table[index[t]][k] = x
+        current = 0
+        for row in table:
+            if row[k] == 0:
+                row[k] = current
+            else:
+                current = row[k]
+    for row in table[split_index:]:
+        row[joining] = row[1 - joining]
+    mi = []
+    for k in (0, 1):
+        for t, r in bands[k].items():
+            mi.append([k + 1, index[t], split_index, 2 * r, 0])
+    mi.sort(key=lambda el: (el[0], el[1]))
+    for cur, nxt in zip(mi[:-1], mi[1:]):
+        if cur[0] == nxt[0]:
+            cur[2] = nxt[1]
+    pu = [[deme, index[t], rate, 0] for t, (rate, deme) in pulses.items()]
+    times = [2 * (b - a) for a, b in zip(grid[:-1], grid[1:])]
+    lambdas = [[1.0 / row[0], 1.0 / row[1]] for row in table]
+    return InputData(times, lambdas, 1.0, 1.0, divTime=split_index, mi=mi, pu=pu)
+
+
+ReadMS = read_ms

@@ -614,3 +614,39 @@ def test_forward_map_of_the_drop_in_class():
         # the object now holds the apparent rates: correcting them (cpfit) recovers a model close to the truth
         llh1 = M.JAFSLikelihood([])
         assert np.isfinite(llh0) and np.isfinite(llh1)
+
+
+@pytest.mark.gpu
+def test_testmodel_command_line(capsys, tmp_path):
+    """python -m misti_b200.testmodel: TestModel.py's flow (ms command line -> expected SFS -> likelihood -> forward map ->
+    .mi file) on the device.  Known answers: the expected SFS the reference prints for README.md:102 and for the example
+    of migrationIO.ReadMS with its likelihood against an all-ones SFS."""
+    import os
+    import re
+    from misti_b200 import testmodel
+    data = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "data", "synthetic")
+    units = ["--funits", os.path.join(data, "setunits.txt")]
+
+    def expected_sfs(text):
+        m = re.search(r"Expected SFS \[([^\]]+)\]", text)
+        assert m, text
+        return [float(v) for v in m.group(1).split(",")]
+    ms1 = "4 100 -t 15000 -r 1920 30000000 -l -I 2 2 2 -n 1 10 -n 2 4.5 -eN 0.025 0.2 -ej 0.045 2 1 -eN 0.175 3 -eN 0.625 1.8 -eN 3 3.2 -eN 8 5.5"
+    assert testmodel.main([ms1, "-uf"] + units) == 0
+    assert relerr(expected_sfs(capsys.readouterr().out), [0.22998834064908938, 0.08294220884438291, 0.22829443325938523,
+                                                         0.13101603530972647, 0.12169802476759099, 0.08321539267623594,
+                                                         0.12284556449358902]) < TOL
+    ms2 = ("-n 2 3.0 -em 0.0 1 2 2.0 -em 0.05 2 1 3.0 -en 0.01 1 0.5 -en 0.02 2 0.05 -en 0.0375 1 0.5 -en 0.0375 2 0.5 "
+           "-ej 1.25 2 1 -eM 1.25 0.0 -eN 1.25 1.0 -eN 2.0 5.0")
+    out_mi = str(tmp_path / "model.mi")
+    assert testmodel.main([ms2, os.path.join(data, "m.sfs"), "-uf", "-bs", "40", "-o", out_mi] + units) == 0
+    text = capsys.readouterr().out
+    assert relerr(expected_sfs(text), [0.32751790404974335, 0.08735496365016926, 0.1683384572669584, 0.09243206819249608,
+                                       0.054717229426100106, 0.1189672260946906, 0.1506721513198424]) < TOL
+    llh = float(re.search(r"data llh under the model is (\S+)", text).group(1))
+    mx = float(re.search(r"maximum of the llh function is (\S+)", text).group(1))
+    assert np.isfinite(llh) and llh < mx
+    lo, hi = (float(v) for v in re.search(r"10% confidence interval (\S+) (\S+)", text).groups())
+    assert lo <= hi < 0
+    lines = open(out_mi).read().splitlines()
+    assert lines[0] == "#MiSTI2 ver 0.4" and lines[2] == "ST\t5" and sum(ln.startswith("RS\t") for ln in lines) == 7

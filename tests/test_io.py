@@ -4,6 +4,7 @@ import os
 import random
 
 import numpy as np
+import pytest
 
 from misti_b200 import io as mio
 
@@ -72,3 +73,21 @@ def test_mi_writer(tmp_path):
     rs = [ln.split("\t") for ln in lines if ln.startswith("RS")]
     assert len(rs) == 3 and rs[0][1:8] == ["0", "1.0", "0.5", "1.0", "1.0", "0.0", "0.5"] and len(rs[0]) == 14 and len(rs[1]) == 8
     assert np.isclose(float(rs[2][1]), 0.3)
+
+
+def test_read_ms_against_reference():
+    """ms command line -> model (migrationIO.ReadMS, migrationIO.py:659-766), against outputs of the unmodified reference
+    (tests/golden/ms.json, gen_ms_golden.py): README example, the function's own example, pulses, several bands per deme,
+    deme 1 joining deme 2."""
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ms.json")) as f:
+        cases = json.load(f)["cases"]
+    assert len(cases) >= 5
+    for c in cases:
+        d = mio.read_ms(c["ms"])
+        assert d.times == c["times"] and d.lambdas == c["lambdas"], c["ms"]
+        assert d.divergenceTime == c["splitT"]
+        assert [list(m) for m in d.mi] == c["mi"] and [list(p) for p in d.pu] == c["pu"], c["ms"]
+    with pytest.raises(SystemExit):
+        mio.read_ms("-n 1 2.0 -em 0.0 2 1 0.5")  # no -ej: the reference prints a notice and exits
