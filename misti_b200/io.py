@@ -205,6 +205,30 @@ def generate_bootstrap(rows, n, seed=0):
     return [column_sums(rows)] + [bootstrap_jafs(rows, rng) for _ in range(n)]
 
 
+def write_jafs(rows, pop1=None, pop2=None, file=None):
+    """A joint SFS file (migrationIO.PrintJAFSFile, migrationIO.py:526-555): header, optional population names, the column
+    line, then one row per spectrum -- 8 numbers, or 7 with the total prepended; a single flat spectrum is one row.
+    `file`: an open text file (default: stdout, as the reference prints).  read_jafs reads it back."""
+    out = sys.stdout if file is None else file
+    print("#MiSTI_JSFS version 1.0", file=out)
+    for tag, name in (("#pop1", pop1), ("#pop2", pop2)):
+        if name:
+            print(tag, str(name).strip("\n\r"), sep="\t", file=out)
+    print("\t".join(["total", "0100", "1100", "0001", "0101", "1101", "0011", "0111"]), file=out)
+    if not isinstance(rows, list):
+        sys.stderr.write("Unexpected SFS value: should be a list of a list of lists\n")
+        sys.exit(0)
+    if not isinstance(rows[0], list):
+        rows = [rows]
+    for sfs in rows:
+        if len(sfs) == 7:
+            sfs = [sum(sfs)] + list(sfs)
+        elif len(sfs) != 8:
+            print("Unexpected SFS entry.")
+            sys.exit(0)
+        print("\t".join(str(v) for v in sfs), file=out)
+
+
 def output_migration(fout, mu, Migration, scaleTime=1, scaleEPS=1):
     """The `.mi` result file, format "#MiSTI2 ver 0.4" (migrationIO.OutputMigration, migrationIO.py:346-375)."""
     llh = Migration.llh if len(mu) == 0 else Migration.JAFSLikelihood(mu)
@@ -319,4 +343,4 @@ def read_ms(argument_string):
     return InputData(times, lambdas, 1.0, 1.0, divTime=split_index, mi=mi, pu=pu)
 
 
-ReadMS = read_ms
+ReadMS, PrintJAFSFile = read_ms, write_jafs

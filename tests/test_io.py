@@ -91,3 +91,21 @@ def test_read_ms_against_reference():
         assert [list(m) for m in d.mi] == c["mi"] and [list(p) for p in d.pu] == c["pu"], c["ms"]
     with pytest.raises(SystemExit):
         mio.read_ms("-n 1 2.0 -em 0.0 2 1 0.5")  # no -ej: the reference prints a notice and exits
+
+
+def test_write_jafs_round_trip(tmp_path):
+    """PrintJAFSFile's format (migrationIO.py:526-555) as written by write_jafs reads back unchanged; the bootstrap file of
+    utils/generateJSFS_bs.py (row 0 = the data total, then the replicates) is generate_bootstrap + write_jafs."""
+    rows = [[1000.0, 3.0, 1.0, 4.0, 1.0, 5.0, 9.0, 2.0], [2000.0, 6.0, 5.0, 3.0, 5.0, 8.0, 9.0, 7.0], [1500.0, 9.0, 3.0, 2.0, 3.0, 8.0, 4.0, 6.0]]
+    bs = mio.generate_bootstrap(rows, 5, seed=3)
+    fn = tmp_path / "bs.sfs"
+    with open(fn, "w") as f:
+        mio.write_jafs(bs, "A", "B\n", file=f)
+    back = mio.read_jafs(str(fn))
+    assert back.jafs == bs and back.pop1 == "A" and back.pop2 == "B"
+    assert back.jafs[0] == mio.column_sums(rows)
+    text = open(fn).read().splitlines()
+    assert text[0] == "#MiSTI_JSFS version 1.0" and text[3].split("\t") == ["total", "0100", "1100", "0001", "0101", "1101", "0011", "0111"]
+    with open(fn, "w") as f:
+        mio.write_jafs([3.0, 1.0, 4.0, 1.0, 5.0, 9.0, 2.0], file=f)  # a single spectrum without its total
+    assert mio.read_jafs(str(fn)).jafs == [[25.0, 3.0, 1.0, 4.0, 1.0, 5.0, 9.0, 2.0]]
