@@ -137,7 +137,8 @@ int misti_eval_batch(misti_ctx* ctx, int32_t B, int32_t P, const double* params,
  * a fit is a stream of launches (propose, evaluate, apply) without a host round trip per step.  Host pointers.
  * x0[S][N] start vectors (N >= every model's n_params, N >= 1), model_ids[S], row_ids[S] (NULL = row 0);
  * maxiter / maxfev < 0 = none.  Out: x[S][N] best vertex, fun[S] = -llh there, nit[S], nfev[S] (scipy's counts),
- * status[S] (0 converged, 1 maxfev, 2 maxiter), info[2] = rounds of launches, points evaluated (nullable).
+ * status[S] (0 converged, 1 maxfev, 2 maxiter), info[3] = rounds of launches, points evaluated, 1 if the rounds were
+ * replayed as a CUDA graph (nullable).
  * Replaces: one MigrationInference.Solve (one MiSTI.py process in the reference's bootstrap loops) per pair. */
 int misti_nelder_mead(misti_ctx* ctx, int32_t S, int32_t N, const double* x0, const int32_t* model_ids, const int32_t* row_ids,
                       uint32_t flags, double mixture_th, double xatol, double fatol, int64_t maxiter, int64_t maxfev,

@@ -634,10 +634,16 @@ struct NmState {
 };
 
 // the points of this round -> the evaluation batch (slot j of simplex s is item s * slots + j; unused slots get model -1)
+// (the number of points a round submits is added up in slot `round % kNmRing` of a ring; the round counter lives on the
+// device and is advanced by the apply kernel, so that a round is the same sequence of launches with the same arguments
+// every time -- a CUDA graph)
+constexpr int kNmRing = 64;
 __global__ void misti_nm_propose_kernel(int S, misti::NmConfig cfg, NmState st, double* __restrict__ params,
-                                        int* __restrict__ item_model, int* __restrict__ item_row, int* __restrict__ n_submitted) {
+                                        int* __restrict__ item_model, int* __restrict__ item_row, int* __restrict__ ring,
+                                        const int* __restrict__ round) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= S) return;
+    int* n_submitted = ring + (*round % kNmRing);
     const int N = cfg.N;
     const long b0 = (long)s * cfg.slots;
     const int n = misti::nm_propose(cfg, st.sim + (long)s * (N + 1) * N, st.fsim + (long)s * (N + 1), st.iters + s, st.fcalls + s,
@@ -651,8 +657,13 @@ __global__ void misti_nm_propose_kernel(int S, misti::NmConfig cfg, NmState st, 
 }
 
 __global__ void misti_nm_apply_kernel(int S, misti::NmConfig cfg, NmState st, const double* __restrict__ params,
-                                      const double* __restrict__ llh) {
+                                      const double* __restrict__ llh, int* __restrict__ ring, int* __restrict__ round) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s == 0) {  // next round: advance the counter, clear its slot of the ring
+        const int r = *round + 1;
+        *round = r;
+        ring[r % kNmRing] = 0;
+    }
     if (s >= S || st.phase[s] == misti::NM_DONE) return;
     const int N = cfg.N;
     const long b0 = (long)s * cfg.slots;
@@ -714,6 +725,10 @@ struct misti_ctx {
     unsigned char* d_nm = nullptr;  // state and batch buffers of misti_nelder_mead (one block, carved up per call)
     size_t d_nm_cap = 0;
     int* h_nm_counts = nullptr;     // pinned: points submitted per round (ring of kNmRing entries)
+    cudaGraphExec_t nm_graph = nullptr;   // one round of misti_nelder_mead as a CUDA graph, kept while its arguments stay valid
+    std::vector<unsigned long long> nm_graph_key;
+    unsigned long long generation = 0;    // bumped whenever a device buffer moves or a launch argument of the kernels changes
+    int nm_use_graph = 1;                 // tuning knob MISTI_NM_GRAPH
     cudaEvent_t nm_ev[4] = {nullptr, nullptr, nullptr, nullptr};
     double* d_score = nullptr;      // scratch of misti_score_spectra
     size_t d_score_cap = 0;
@@ -752,6 +767,7 @@ int ensure(misti_ctx* ctx, T** p, size_t* cap, size_t need) {
     *p = nullptr;
     CK(cudaMalloc((void**)p, ncap * sizeof(T)));
     *cap = ncap;
+    ++ctx->generation;
     return 0;
 }
 
@@ -760,10 +776,12 @@ int realloc_exact(misti_ctx* ctx, T** p, size_t n) {
     if (*p) CK(cudaFree(*p));
     *p = nullptr;
     if (n) CK(cudaMalloc((void**)p, n * sizeof(T)));
+    ++ctx->generation;
     return 0;
 }
 
 int sync_tables(misti_ctx* ctx) {
+    if (ctx->grids_dirty || ctx->models_dirty) ++ctx->generation;
     if (ctx->grids_dirty) {
         size_t need = ctx->h_times.size();
         if (need > ctx->d_grid_cap) {
@@ -907,6 +925,7 @@ int misti_ctx_create(int device, void* stream, misti_ctx** out) {
     if (const char* e = getenv("MISTI_CORRECT_COOP")) ctx->correct_coop = atoi(e);
     if (const char* e = getenv("MISTI_DEFER_POST")) ctx->defer_post = atoi(e);
     if (const char* e = getenv("MISTI_NM_LOOKAHEAD")) ctx->nm_lookahead = atoi(e);
+    if (const char* e = getenv("MISTI_NM_GRAPH")) ctx->nm_use_graph = atoi(e);
     if (const char* e = getenv("MISTI_MAX_CHUNK")) {
         const int v = atoi(e);
         if (v >= 1 && v <= kMaxChunk) ctx->max_chunk = v;
@@ -932,6 +951,7 @@ void misti_ctx_destroy(misti_ctx* ctx) {
     for (int i = 0; i < 4; ++i)
         if (ctx->nm_ev[i]) cudaEventDestroy(ctx->nm_ev[i]);
     if (ctx->h_nm_counts) cudaFreeHost(ctx->h_nm_counts);
+    if (ctx->nm_graph) cudaGraphExecDestroy(ctx->nm_graph);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -950,6 +970,7 @@ int misti_ctx_set_stream(misti_ctx* ctx, void* stream) {
         ctx->own_stream = true;
     }
     ctx->ev_valid = false;
+    ++ctx->generation;
     return 0;
 }
 
@@ -1044,6 +1065,7 @@ int misti_clear_models(misti_ctx* ctx) {
     ctx->grid_numT.clear(); ctx->grid_off.clear(); ctx->h_times.clear(); ctx->h_lh.clear(); ctx->h_gaux.clear(); ctx->h_models.clear(); ctx->h_cls.clear(); ctx->h_post.clear();
     ctx->numT_max = 0;
     ctx->grids_dirty = ctx->models_dirty = false;
+    ++ctx->generation;
     return 0;
 }
 
@@ -1077,6 +1099,7 @@ int misti_set_data(misti_ctx* ctx, int32_t R, const double* sfs, const double* l
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->R = R;
     ctx->unfolded = unfolded ? 1 : 0;
+    ++ctx->generation;
     return 0;
 }
 
@@ -1255,7 +1278,7 @@ int misti_nelder_mead(misti_ctx* ctx, int32_t S, int32_t N, const double* x0, co
     if (!ctx) return MISTI_E_ARG;
     if (S < 0 || N < 1 || N > MISTI_MAX_PARAMS || !x0 || !model_ids || !x || !fun || !nit || !nfev || !status)
         return fail(ctx, MISTI_E_ARG, "misti_nelder_mead: bad arguments");
-    if (info) info[0] = info[1] = 0;
+    if (info) info[0] = info[1] = info[2] = 0;
     if (S == 0) return 0;
     if (ctx->R < 1) return fail(ctx, MISTI_E_ARG, "misti_nelder_mead: no data rows (misti_set_data)");
     const int n_models = (int)ctx->h_models.size();
@@ -1279,14 +1302,13 @@ int misti_nelder_mead(misti_ctx* ctx, int32_t S, int32_t N, const double* x0, co
     const long B = (long)S * cfg.slots;
     if (B > ctx->max_chunk) return fail(ctx, MISTI_E_ARG, "misti_nelder_mead: too many simplices for one call");
     // one block of device memory, carved up (8-byte items first)
-    constexpr int kNmRing = 64;
     const size_t n_sim = (size_t)S * (N + 1) * N, n_fsim = (size_t)S * (N + 1);
     size_t off = 0;
     auto carve = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
     const size_t o_sim = carve(n_sim * 8), o_fsim = carve(n_fsim * 8), o_it = carve((size_t)S * 8), o_fc = carve((size_t)S * 8),
                  o_par = carve((size_t)B * N * 8), o_llh = carve((size_t)B * 8), o_st = carve((size_t)S * 4), o_ph = carve((size_t)S * 4),
                  o_mod = carve((size_t)S * 4), o_row = carve((size_t)S * 4), o_bm = carve((size_t)B * 4), o_br = carve((size_t)B * 4),
-                 o_cnt = carve(kNmRing * 4);
+                 o_cnt = carve((kNmRing + 1) * 4);  // the ring and, behind it, the round counter
     if ((rc = ensure(ctx, &ctx->d_nm, &ctx->d_nm_cap, off))) return rc;
     if (!ctx->h_nm_counts) CK(cudaMallocHost((void**)&ctx->h_nm_counts, kNmRing * sizeof(int)));
     for (int i = 0; i < 4; ++i)
@@ -1309,6 +1331,52 @@ int misti_nelder_mead(misti_ctx* ctx, int32_t S, int32_t N, const double* x0, co
     if (row_ids) CK(cudaMemcpyAsync(d_row, row_ids, (size_t)S * 4, cudaMemcpyHostToDevice, sm));
     const unsigned eflags = (flags | MISTI_FLAG_DEVICE_PTRS);
     const int tb = 64, gb = (S + tb - 1) / tb;
+    int* d_round = d_cnt + kNmRing;
+    if ((rc = ensure_batch(ctx, (size_t)B))) return rc;  // no allocation inside a round (a round may be captured)
+    // one round: propose, count back to the host, evaluate (three kernels), apply
+    auto round_body = [&]() -> int {
+        misti_nm_propose_kernel<<<gb, tb, 0, sm>>>(S, cfg, st, d_par, d_bm, d_br, d_cnt, d_round);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(ctx->h_nm_counts, d_cnt, kNmRing * sizeof(int), cudaMemcpyDeviceToHost, sm));
+        int rc2 = eval_chunk(ctx, (int)B, N, d_par, d_bm, -1, eflags, mixture_th, nullptr, d_llh, nullptr, nullptr, nullptr, nullptr,
+                             nullptr, nullptr, nullptr, d_br);
+        if (rc2) return rc2;
+        misti_nm_apply_kernel<<<gb, tb, 0, sm>>>(S, cfg, st, d_par, d_llh, d_cnt, d_round);
+        CK(cudaGetLastError());
+        return 0;
+    };
+    // The round is the same sequence of launches with the same arguments every time: it is captured once as a CUDA graph
+    // and replayed (one launch call per round instead of a dozen stream operations); the graph is kept for the next fit
+    // as long as nothing it refers to has moved.
+    cudaGraphExec_t exec = nullptr;
+    if (ctx->nm_use_graph) {
+        unsigned long long mt_bits, xa_bits, fa_bits;
+        std::memcpy(&mt_bits, &mixture_th, 8); std::memcpy(&xa_bits, &xatol, 8); std::memcpy(&fa_bits, &fatol, 8);
+        const std::vector<unsigned long long> key = {ctx->generation, (unsigned long long)S, (unsigned long long)N,
+                                                     (unsigned long long)cfg.slots, (unsigned long long)cfg.lookahead, xa_bits, fa_bits,
+                                                     (unsigned long long)cfg.maxiter, (unsigned long long)cfg.maxfev,
+                                                     (unsigned long long)flags, mt_bits, (unsigned long long)(size_t)sm};
+        if (ctx->nm_graph && key == ctx->nm_graph_key) {
+            exec = ctx->nm_graph;
+        } else {
+            if (ctx->nm_graph) { cudaGraphExecDestroy(ctx->nm_graph); ctx->nm_graph = nullptr; }
+            const int64_t launches_before = ctx->launches;
+            if (cudaStreamBeginCapture(sm, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+                const int rcb = round_body();
+                cudaGraph_t graph = nullptr;
+                const cudaError_t e = cudaStreamEndCapture(sm, &graph);
+                if (rcb == 0 && e == cudaSuccess && graph && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess) {
+                    ctx->nm_graph = exec;
+                    ctx->nm_graph_key = key;
+                } else {
+                    exec = nullptr;
+                    cudaGetLastError();  // clear the capture error: the rounds are launched directly instead
+                }
+                if (graph) cudaGraphDestroy(graph);
+            }
+            ctx->launches = launches_before;  // nothing ran during the capture
+        }
+    }
     int64_t rounds = 0, points = 0;
     // The host runs at most two rounds ahead of the device: before round r is queued, the count of round r - 2 is in;
     // a round in which no simplex submitted a point ends the fit (the rounds queued behind it are empty and cost microseconds).
@@ -1320,19 +1388,16 @@ int misti_nelder_mead(misti_ctx* ctx, int32_t S, int32_t N, const double* x0, co
             points += n;
             ++rounds;
         }
-        int* cnt = d_cnt + (r % kNmRing);
-        CK(cudaMemsetAsync(cnt, 0, sizeof(int), sm));
-        misti_nm_propose_kernel<<<gb, tb, 0, sm>>>(S, cfg, st, d_par, d_bm, d_br, cnt);
-        CK(cudaGetLastError());
-        CK(cudaMemcpyAsync(ctx->h_nm_counts + (r % kNmRing), cnt, sizeof(int), cudaMemcpyDeviceToHost, sm));
+        if (exec) {
+            CK(cudaGraphLaunch(exec, sm));
+            ctx->launches += 5;
+        } else {
+            if ((rc = round_body())) return rc;
+            ctx->launches += 2;
+        }
         CK(cudaEventRecord(ctx->nm_ev[r & 3], sm));
-        if ((rc = eval_chunk(ctx, (int)B, N, d_par, d_bm, -1, eflags, mixture_th, nullptr, d_llh, nullptr, nullptr, nullptr, nullptr,
-                             nullptr, nullptr, nullptr, d_br)))
-            return rc;
-        misti_nm_apply_kernel<<<gb, tb, 0, sm>>>(S, cfg, st, d_par, d_llh);
-        CK(cudaGetLastError());
-        ctx->launches += 2;
     }
+    ctx->ev_valid = false;  // the timing events of the evaluation were recorded inside the rounds
     // results: best vertex and value (the simplices are sorted), counts
     CK(cudaMemcpy2DAsync(x, (size_t)N * 8, st.sim, (size_t)(N + 1) * N * 8, (size_t)N * 8, S, cudaMemcpyDeviceToHost, sm));
     CK(cudaMemcpy2DAsync(fun, 8, st.fsim, (size_t)(N + 1) * 8, 8, S, cudaMemcpyDeviceToHost, sm));
@@ -1341,7 +1406,7 @@ int misti_nelder_mead(misti_ctx* ctx, int32_t S, int32_t N, const double* x0, co
     CK(cudaMemcpyAsync(nfev, st.fcalls, (size_t)S * 8, cudaMemcpyDeviceToHost, sm));
     CK(cudaMemcpyAsync(status, st.status, (size_t)S * 4, cudaMemcpyDeviceToHost, sm));
     CK(cudaStreamSynchronize(sm));
-    if (info) { info[0] = rounds; info[1] = points; }
+    if (info) { info[0] = rounds; info[1] = points; info[2] = exec ? 1 : 0; }
     return 0;
 }
 

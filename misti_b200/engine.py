@@ -240,7 +240,7 @@ class Engine:
         flags = int(flags) & ~_lib.FLAG_DEVICE_PTRS
         flags = (flags | _lib.FLAG_UNFOLDED) if self.unfolded else (flags & ~_lib.FLAG_UNFOLDED)
         x, fun = np.empty((S, N)), np.empty(S)
-        nit, nfev, info = np.zeros(S, dtype=np.int64), np.zeros(S, dtype=np.int64), np.zeros(2, dtype=np.int64)
+        nit, nfev, info = np.zeros(S, dtype=np.int64), np.zeros(S, dtype=np.int64), np.zeros(3, dtype=np.int64)
         status = np.zeros(S, dtype=np.int32)
         i64p = ctypes.POINTER(ctypes.c_int64)
         self._check(self._lib.misti_nelder_mead(
@@ -249,7 +249,7 @@ class Engine:
             lim[0], lim[1], x.ctypes.data_as(_lib.c_double_p), fun.ctypes.data_as(_lib.c_double_p), nit.ctypes.data_as(i64p),
             nfev.ctypes.data_as(i64p), status.ctypes.data_as(_lib.c_int32_p), info.ctypes.data_as(i64p)))
         return {"x": x, "fun": fun, "nit": nit, "nfev": nfev, "status": status.astype(np.int64), "success": status == 0,
-                "evaluations": int(info[1]), "launches": int(info[0])}
+                "evaluations": int(info[1]), "launches": int(info[0]), "graph": bool(info[2])}
 
     def coalescent_rates(self, model, params, mu):
         """Forward map of model `model` (misti_coalescent_rates): its grid's rates taken as the true rates -> the rates PSMC

@@ -457,6 +457,7 @@ def test_nelder_mead_on_the_device(engine, golden_datasets):
     mids = np.array([sw.models[m1]["id"]] * 3, dtype=np.int32)
     r = engine.nelder_mead(x0, mids, np.zeros(3, dtype=np.int32), flags=sw.flags, maxiter=7)
     assert (r["nit"] == 7).all() and (r["status"] == 2).all()
+    assert r["graph"]  # a round of launches is captured once and replayed as a CUDA graph
     r = engine.nelder_mead(x0, mids, np.zeros(3, dtype=np.int32), flags=sw.flags, maxfev=9)
     assert (r["nfev"] == 9).all() and (r["status"] == 1).all()
     # one iteration per round (these small batches take two by default: look-ahead)
