@@ -38,6 +38,8 @@ def build_parser():
     p.add_argument("--trueEPS", action="store_true")
     p.add_argument("--cpfit", action="store_true")
     p.add_argument("--bsMode", "-bs", type=int, default=-1)
+    p.add_argument("--psmcMode", "-pm", type=int, default=0, help="1: re-estimate both trajectories on the average collapsed grid "
+                   "with the split time (st, then in years) inserted (migrationIO.ReadPSMC1)")
     p.add_argument("--debug", action="store_true")
     # additions
     p.add_argument("--st-grid", nargs=2, type=int, metavar=("FIRST", "LAST"), help="sweep the integer split times FIRST..LAST")
@@ -67,7 +69,15 @@ def main(argv=None):
     print("pop2\t", f2)
     print("jafs\t", fj)
     jafs = mio.read_jafs(fj, silent_mode=False)
-    inp = mio.read_psmc(f1, f2, a.sdate, a.rd, units)
+    if a.psmcMode == 0:
+        inp = mio.read_psmc(f1, f2, a.sdate, a.rd, units)
+    else:  # MiSTI.py:190-195: st is a time in years and becomes the index of that time in the re-estimated grid
+        if a.st_grid:
+            print("--st-grid sweeps split indices of one grid; with -pm 1 the grid depends on the split time.")
+            sys.exit(0)
+        inp = mio.read_psmc1(f1, f2, a.rd, divergenceTime=a.st, units=units)
+        if inp.divergenceTime != -1:
+            a.st = inp.divergenceTime
     kw = dict(smooth=not a.nosmooth, unfolded=a.uf, trueEPS=a.trueEPS, cpfit=a.cpfit, sampleDate=inp.sampleDateDiscr, mixtureTH=a.mth)
     t1 = time.time()
     if a.st_grid or a.bs_rows:

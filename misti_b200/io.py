@@ -8,6 +8,7 @@ class statics), readers return fresh objects (the reference's JAFS() default lis
 calls, migrationIO.py:39), bootstrap resampling takes an explicit seed (the reference uses the unseeded
 global `random`).  Reference-named aliases (ReadPSMC, ReadJAFS, BootstrapJAFS, OutputMigration) are kept.
 """
+import math
 import random
 import sys
 
@@ -136,6 +137,93 @@ def read_psmc(fn1, fn2, sampleDate=0.0, RD=-1, units=None):
     times = [b - a for a, b in zip(Tk[:-1], Tk[1:])]
     return InputData(times, lambdas, scaleTime, theta, scaleEPS=1, rho=d1[4] * theta / d1[3], sampleDateDiscr=sampleDateDiscr,
                      Tpsmc=Tpsmc)
+
+
+def psmc_pattern(fn):
+    """Free-parameter pattern of a PSMC run as the list of its segment lengths, e.g. `MM pattern:4+25*2+4+6,` ->
+    [4, 2 x 25, 4, 6] (psmc.PSMC.ReadPSMCFile, psmc.py:51-61)."""
+    segs = []
+    with open(fn) as f:
+        for ln in f:
+            w = ln.split()
+            if len(w) > 1 and w[0] == "MM" and w[1].startswith("pattern"):
+                for part in w[1][:-1].split(":")[1].split("+"):
+                    v = [int(x) for x in part.split("*")]
+                    segs += [v[0]] if len(v) == 1 else [v[1]] * v[0]
+    return segs
+
+
+def _pieces(t, eps, t1, t2):
+    """The pieces [tl, tu) x size of the piecewise-constant trajectory (t, eps) inside [t1, t2); t2 may be inf."""
+    inf = float("inf")
+    k = 0
+    while k < len(t) and t[k] <= t1:
+        k += 1
+    k -= 1
+    while k < len(t) and t[k] < t2:
+        nxt = t[k + 1] if k + 1 < len(t) else inf
+        yield max(t1, t[k]), min(t2, nxt), eps[k]
+        k += 1
+
+
+def psmc_mean_size(t, eps, t1, t2):
+    """Size of a constant population with the same coalescence hazard over [t1, t2): the time-weighted harmonic mean
+    (psmc.PSMC.AverageCoalescentRate, psmc.py:97-119; same order of operations)."""
+    if t1 > t2:
+        sys.exit(1)
+    hazard, span = 0.0, 0.0
+    for tl, tu, e in _pieces(t, eps, t1, t2):
+        hazard += tu / e - tl / e
+        span += tu - tl
+    return span / hazard
+
+
+def psmc_tail_size(t, eps, t1):
+    """Size of a constant population with the same expected coalescence time beyond t1 (psmc.PSMC.FitCoalescentTime with
+    t2 = inf, psmc.py:121-146, incl. its bounded least-squares solve of `size = expected time - t1`)."""
+    from scipy.optimize import least_squares
+    inf = float("inf")
+    et, lognc = 0.0, 0.0
+    for tl, tu, e in _pieces(t, eps, t1, inf):
+        ru, rl = tu / e, tl / e
+        vu = 0.0 if ru == inf else (ru + 1.0) * math.exp(rl - ru)
+        et += math.exp(lognc) * ((rl + 1.0) - vu) * e
+        lognc -= ru - rl
+    et = et / (1.0 - math.exp(lognc))
+    return least_squares(lambda size: (et - t1) - size, 1.0, bounds=(0.0, inf), ftol=4e-16, xtol=4e-16, gtol=4e-16).x[0]
+
+
+def read_psmc1(fn1, fn2, RD=-1, divergenceTime=-1, units=None):
+    """The reference's second input mode (MiSTI.py -pm 1; migrationIO.ReadPSMC1, migrationIO.py:297-344): both trajectories
+    are rescaled to the common theta, the grid is the average of their collapsed (one point per pattern segment) grids with
+    the split time -- given in YEARS -- inserted, and each trajectory is re-estimated on it (mean size per interval, fitted
+    size beyond the last point).  Returns the intervals, the size pairs, and the index of the split time in the grid
+    (-1 when none was given).  Like the reference, this mode ignores heterozygosity loss and the sampling date."""
+    u = units if units is not None else Units()
+    if u.hetloss1 != 0.0 or u.hetloss2 != 0.0:
+        print("Hetloss id not implemented in this version.")
+    theta = 4.0 * u.binsize * u.mutRate * u.N0
+    scaleTime = 2 * u.genTime * u.N0
+    traj, collapsed = [], []
+    for fn in (fn1, fn2):
+        t, eps, _, th, _ = read_psmc_file(fn, RD)
+        t = [v * th / theta for v in t]
+        eps = [v * th / theta for v in eps]
+        traj.append((t, eps))
+        starts, k = [], 0
+        for n in psmc_pattern(fn):
+            starts.append(t[k])
+            k += n
+        collapsed.append(starts)
+    if len(collapsed[0]) != len(collapsed[1]):
+        sys.exit(1)
+    split = None if divergenceTime == -1 else divergenceTime / scaleTime
+    Tk = sorted(set(([] if split is None else [split]) + [(a + b) / 2.0 for a, b in zip(collapsed[0], collapsed[1])]))
+    sizes = []
+    for t, eps in traj:
+        sizes.append([psmc_mean_size(t, eps, a, b) for a, b in zip(Tk[:-1], Tk[1:])] + [psmc_tail_size(t, eps, Tk[-1])])
+    return InputData([b - a for a, b in zip(Tk[:-1], Tk[1:])], [[a, b] for a, b in zip(sizes[0], sizes[1])], scaleTime, theta,
+                     divTime=-1 if split is None else Tk.index(split))
 
 
 def read_jafs(fn, silent_mode=True):

@@ -520,6 +520,35 @@ def test_command_line_reproduces_the_reference_run(capsys, tmp_path):
 
 
 @pytest.mark.gpu
+def test_command_line_second_psmc_mode(capsys, tmp_path):
+    """MiSTI.py -pm 1 (migrationIO.ReadPSMC1): the split time is given in years, the grid is re-estimated around it; the
+    command line prints the split index and the likelihood the reference gets from the same files (tests/golden/psmc1.json)."""
+    import json
+    import os
+    import re
+    from misti_b200 import cli
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    data = os.path.join(root, "data", "synthetic")
+    with open(os.path.join(root, "tests", "golden", "psmc1.json")) as f:
+        cases = [c for c in json.load(f)["cases"] if "llh_cpfit" in c]
+    assert len(cases) >= 2
+    for c in cases:
+        for n in ("m1.psmc", "m2.psmc"):
+            with open(os.path.join(data, n)) as f:
+                body = f.read()
+            (tmp_path / n).write_text("MM\tpattern:%s, n:63, n_free_lambdas:%d\n" % (c["pattern"], len(c["pattern"].split("+"))) + body)
+        args = [str(tmp_path / "m1.psmc"), str(tmp_path / "m2.psmc"), os.path.join(data, "m.sfs"), str(c["st_years"]), "-pm", "1",
+                "--cpfit", "--funits", os.path.join(data, "setunits.txt")] + (["-uf"] if c["unfolded"] else [])
+        rc = cli.main(args)
+        text = capsys.readouterr().out
+        assert rc == 0
+        m = re.search(r"bs_id = -1 \tsplitT = (\S+) \ttime = (\S+) \tmigration rates  \tllh = (\S+)", text)
+        assert m, text[-2000:]
+        assert int(m.group(1)) == c["divTime"]
+        assert relerr(float(m.group(3)), c["llh_cpfit"]) < TOL, c["name"]
+
+
+@pytest.mark.gpu
 def test_batches_larger_than_one_launch_are_chunked(golden_datasets):
     """a batch beyond the per-launch limit is evaluated in chunks (here the limit is lowered to 700 items): every output,
     with per-item models and per-item data rows, equals the single-launch result bit for bit; an on-device fit that would

@@ -109,3 +109,30 @@ def test_write_jafs_round_trip(tmp_path):
     with open(fn, "w") as f:
         mio.write_jafs([3.0, 1.0, 4.0, 1.0, 5.0, 9.0, 2.0], file=f)  # a single spectrum without its total
     assert mio.read_jafs(str(fn)).jafs == [[25.0, 3.0, 1.0, 4.0, 1.0, 5.0, 9.0, 2.0]]
+
+
+def _with_pattern(tmp_path, pattern):
+    names = []
+    for n in ("m1.psmc", "m2.psmc"):
+        with open(os.path.join(DATA, n)) as f:
+            body = f.read()
+        dst = tmp_path / n
+        dst.write_text("MM\tpattern:%s, n:63, n_free_lambdas:%d\n" % (pattern, len(pattern.split("+"))) + body)
+        names.append(str(dst))
+    return names
+
+
+def test_read_psmc1_equals_the_reference(tmp_path):
+    """MiSTI.py -pm 1 (migrationIO.ReadPSMC1 over psmc.PSMC): grid, re-estimated sizes and split index as the reference
+    produced them from the same files (tests/golden/psmc1.json, generator gen_psmc1_golden.py) -- bit for bit."""
+    import json
+    with open(os.path.join(ROOT, "tests", "golden", "psmc1.json")) as f:
+        cases = json.load(f)["cases"]
+    units = mio.Units.from_file(os.path.join(DATA, "setunits.txt"))
+    for c in cases:
+        f1, f2 = _with_pattern(tmp_path, c["pattern"])
+        assert sum(mio.psmc_pattern(f1)) == 64
+        inp = mio.read_psmc1(f1, f2, c["RD"], divergenceTime=c["st_years"], units=units)
+        assert inp.times == c["times"] and inp.lambdas == c["lambdas"], c["name"]
+        assert inp.divergenceTime == c["divTime"] and inp.scaleTime == c["scaleTime"] and inp.theta == c["theta"]
+        assert inp.sampleDateDiscr == 0 and inp.rho is None and inp.Tpsmc is None
