@@ -227,9 +227,9 @@ def read_psmc1(fn1, fn2, RD=-1, divergenceTime=-1, units=None):
 
 
 def read_jafs(fn, silent_mode=True):
-    """Joint SFS file, format version >= 1 (migrationIO.ReadJAFS, migrationIO.py:557-614): header lines starting
-    with '#', an optional column line starting with 'total', then rows of 8 TAB-separated numbers
-    [total sites, 0100, 1100, 0001, 0101, 1101, 0011, 0111]."""
+    """Joint SFS file (migrationIO.ReadJAFS, migrationIO.py:557-608): header lines starting with '#', an optional
+    column line starting with 'total', then rows of 8 TAB-separated numbers
+    [total sites, 0100, 1100, 0001, 0101, 1101, 0011, 0111].  Files of a format version < 1 go to the old reader."""
     out = JAFS()
     with open(fn) as f:
         lines = [ln.rstrip("\n") for ln in f]
@@ -237,7 +237,9 @@ def read_jafs(fn, silent_mode=True):
         sys.stderr.write("Corrupted JSFS file header.\n")
         sys.exit(0)
     if float(lines[0].split(" ")[2]) < 1:
-        sys.stderr.write("The file version is not supported anymore.\n")
+        return _read_jafs_v0(lines, silent_mode)
+    if not lines[0].startswith("#MiSTI_JSFS"):  # the two older names only exist with format versions < 1
+        sys.stderr.write("Corrupted JSFS file header.\n")
         sys.exit(0)
     for ln in lines[1:]:
         if ln.startswith("#"):
@@ -257,6 +259,39 @@ def read_jafs(fn, silent_mode=True):
             sys.stderr.write("Unexpected line. Expected an entry for JSFS with eight TAB-separated columns.\n")
             sys.exit(0)
         out.jafs.append([float(v) for v in cols])
+    return out
+
+
+def _read_jafs_v0(lines, silent_mode):
+    """Format versions < 1 (migrationIO.ReadJAFS_old, migrationIO.py:610-656): header fields separated by a blank, then
+    exactly eight lines `label<TAB>integer count` -- one spectrum, no chunk rows."""
+    out, counts = JAFS(), []
+    for ln in (x.rstrip() for x in lines):
+        if ln.startswith("#") and not counts:
+            w = ln.split(" ")
+            if ln[1:10] == "MiSTI_JAF" or ln[1:14] == "Migration_JAF":
+                if len(w) < 3:
+                    sys.stderr.write("Corrupted JAF file header.\n")
+                    sys.exit(0)
+                if not silent_mode:
+                    print("JAFS format version:", w[2])
+            elif ln[1:5] in ("pop1", "pop2"):
+                if len(w) != 2:
+                    sys.stderr.write("Corrupted JAF file header.\n")
+                    sys.exit(0)
+                setattr(out, ln[1:5], w[1])
+                if not silent_mode:
+                    print(ln[1:5] + "\t", w[1])
+            continue
+        w = ln.split("\t")
+        if len(w) != 2:
+            sys.stderr.write("Unexpected line. Expected an entry for JAFS with two TAB-separated columns.\n")
+            sys.exit(0)
+        counts.append(int(w[1]))
+    if len(counts) != 8:
+        print("Unexpected number of lines in the JAFS file.")
+        sys.exit(0)
+    out.jafs.append(counts)
     return out
 
 

@@ -136,3 +136,22 @@ def test_read_psmc1_equals_the_reference(tmp_path):
         assert inp.times == c["times"] and inp.lambdas == c["lambdas"], c["name"]
         assert inp.divergenceTime == c["divTime"] and inp.scaleTime == c["scaleTime"] and inp.theta == c["theta"]
         assert inp.sampleDateDiscr == 0 and inp.rho is None and inp.Tpsmc is None
+
+
+def test_read_jafs_format_version_0(tmp_path, capsys):
+    """files of a format version < 1 (one spectrum as eight `label<TAB>count` lines, header fields separated by a blank) go
+    through the old reader (migrationIO.ReadJAFS_old, migrationIO.py:610-656); the expectation below -- rows, population
+    names and what is printed -- is what the reference's ReadJAFS returned for this very file in the build container."""
+    counts = [2500000000, 910, 320, 905, 411, 380, 333, 290]
+    labels = ["total", "0100", "1100", "0001", "0101", "1101", "0011", "0111"]
+    fn = tmp_path / "old.jafs"
+    fn.write_text("#MiSTI_JAF version 0.3\n#pop1 YRI\n#pop2 CEU\n" + "".join("%s\t%d\n" % lv for lv in zip(labels, counts)))
+    j = mio.read_jafs(str(fn), silent_mode=False)
+    assert j.jafs == [counts] and all(isinstance(v, int) for v in j.jafs[0]) and (j.pop1, j.pop2) == ("YRI", "CEU")
+    assert capsys.readouterr().out == "JAFS format version: 0.3\npop1\t YRI\npop2\t CEU\n"
+    fn.write_text("#MiSTI_JAF version 0.3\n" + "".join("%s\t%d\n" % lv for lv in zip(labels[:7], counts[:7])))
+    with pytest.raises(SystemExit):
+        mio.read_jafs(str(fn))
+    fn.write_text("#MiSTI_JAF version 1.0\n")  # the older names only exist with versions < 1
+    with pytest.raises(SystemExit):
+        mio.read_jafs(str(fn))
