@@ -2,8 +2,8 @@
 the `.mi` result file.  Host-side text handling only (runs once per process); nothing here is accelerated.
 
 Functional restatement of migrationIO.Units / ReadPSMCFile / ReadPSMC (migrationIO.py:100-176, 183-295),
-ReadJAFS (:557-656), BootstrapJAFS (:506-524), utils/generateJSFS_bs.py:39-48 and OutputMigration
-(:346-375), without the reference's process-global state: units are a value object (the reference mutates
+ReadPSMC1 (:297-344, with the parts of psmc.py it uses), ReadJAFS (:557-656), BootstrapJAFS (:506-524),
+utils/generateJSFS_bs.py:39-48, OutputMigration (:346-375) and ReadMigration (:377-505, minus plotting), without the reference's process-global state: units are a value object (the reference mutates
 class statics), readers return fresh objects (the reference's JAFS() default list accumulates rows across
 calls, migrationIO.py:39), bootstrap resampling takes an explicit seed (the reference uses the unseeded
 global `random`).  Reference-named aliases (ReadPSMC, ReadJAFS, BootstrapJAFS, OutputMigration) are kept.
@@ -375,8 +375,77 @@ def output_migration(fout, mu, Migration, scaleTime=1, scaleEPS=1):
             f.write(text)
 
 
+class MigData:
+    """What read_migration returns (migrationIO.MigData, migrationIO.py:65-98) plus the columns the reference parses and
+    then only plots: migration rates per interval (mu1, mu2) and the lineage-state probabilities (pr11, pr22, pr12)."""
+
+    def __init__(self):
+        self.llh = self.splitT = self.migStart = self.migEnd = self.thrh = self.mi = self.sampleDate = self.jaf = None
+        self.times, self.lambda1, self.lambda2, self.lambdah1, self.lambdah2 = [], [], [], [], []
+        self.mu1, self.mu2 = [], []
+        self.pr11, self.pr22, self.pr12 = [[], []], [[], []], [[], []]
+
+
+def read_migration(fmigr, scaleTime=1, scaleEPS=1):
+    """A `.mi` result file back into numbers (migrationIO.ReadMigration, migrationIO.py:377-505, without its plotting
+    branch): times in units of scaleTime, corrected / PSMC-apparent RATES lambda = 1 / size / scaleEPS.  Files of the
+    current family ("#MiSTI2 ver >= 0.3") carry their own SCT / SCE lines, which replace the arguments from the line on
+    where they stand; the older family has neither, nor the PSMC columns, but a single band (MS / ME / MU)."""
+    d = MigData()
+    with open(fmigr) as f:
+        head = next(f).rstrip().split(" ")
+        version = float(head[2])
+        print("Format version: ", version)
+        if version < 0.3:
+            sys.stderr.write("File version is not supported anymore.\n")
+            sys.exit(0)
+        current = head[0] == "#MiSTI2"
+        for ln in f:
+            w = ln.split("\t")
+            key = w[0]
+            if key == "LK":
+                d.llh = float(w[1])
+            elif key == "ST":
+                d.splitT = int(w[1])
+            elif key == "SD":
+                d.sampleDate = int(w[1])
+            elif key == "TR":
+                d.thrh = [float(w[1]), float(w[2])]
+            elif key == "SFS":
+                d.jaf = [float(v) for v in w[1:]]
+            elif key == "SCT" and current:
+                scaleTime = float(w[1])
+            elif key == "SCE" and current:
+                scaleEPS = float(w[1])
+            elif key == "MS" and not current:
+                d.migStart = int(w[1])
+            elif key == "ME" and not current:
+                d.migEnd = int(w[1])
+            elif key == "MU" and not current:
+                d.mi = [float(w[1]), float(w[2])]
+            elif key == "RS":
+                d.times.append(float(w[1]) * scaleTime)
+                d.lambda1.append(1.0 / float(w[2]) / scaleEPS)
+                d.lambda2.append(1.0 / float(w[3]) / scaleEPS)
+                if not current:
+                    continue
+                c = 4
+                if version >= 0.4:
+                    d.lambdah1.append(1.0 / float(w[4]) / scaleEPS)
+                    d.lambdah2.append(1.0 / float(w[5]) / scaleEPS)
+                    c = 6
+                d.mu1.append(float(w[c]))
+                d.mu2.append(float(w[c + 1]))
+                pr = [float(v) for v in w[c + 2:c + 8]] if len(w) > c + 2 else [0] * 6
+                for k, dst in enumerate((d.pr11, d.pr22, d.pr12)):
+                    dst[0].append(pr[2 * k])
+                    dst[1].append(pr[2 * k + 1])
+    return d
+
+
 # reference-named aliases
-ReadPSMCFile, ReadPSMC, ReadJAFS, OutputMigration = read_psmc_file, read_psmc, read_jafs, output_migration
+ReadPSMCFile, ReadPSMC, ReadPSMC1, ReadJAFS, OutputMigration, ReadMigration = (read_psmc_file, read_psmc, read_psmc1, read_jafs,
+                                                                                output_migration, read_migration)
 
 
 def BootstrapJAFS(Jafs, normalize=False, rng=None):

@@ -191,6 +191,43 @@ def test_drop_in_class(golden_datasets, golden_cases):
         assert M.numT == exp["numT"] and M.splitT == exp["splitT_int"]
 
 
+def test_mi_file_round_trip_against_the_reference(golden_datasets, tmp_path, capsys):
+    """output side: the drop-in class evaluates the models of tests/golden/mi.json on the device, output_migration writes the
+    `.mi` file (migrationIO.OutputMigration), read_migration reads it back -- and every number equals what the reference
+    parsed from ITS file for the same model (corrected rates, Pr columns' presence, spectrum, likelihood) to 1e-9."""
+    import json
+    import os
+    from misti_b200 import MigrationInference, io as mio
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "mi.json")) as f:
+        cases = {c["name"]: c for c in json.load(f)["cases"]}
+    runs = [("config2_cpfit", "synthetic", 40, [["2", "5", "12", "0.8", "1"]], [0.8], dict(cpfit=True)),
+            ("config4_ancient", "synthetic_ancient", 45, [], [], dict())]
+    for name, dsn, st, mi, mu, kw in runs:
+        ds, c = golden_datasets[dsn], cases[name]
+        M = MigrationInference(list(ds["times"]), [list(v) for v in ds["lambdas"]], list(ds["sfs"]), st, mi, [],
+                               thrh=[ds["theta"], ds["rho"]], enableOutput=False, smooth=True, unfolded=True,
+                               sampleDate=ds.get("sampleDate", 0), **kw)
+        M.JAFSLikelihood(mu)
+        fn = str(tmp_path / (name + ".mi"))
+        mio.output_migration(fn, mu, M, ds["scaleTime"], 1)
+        d = mio.read_migration(fn)
+        capsys.readouterr()
+        assert d.splitT == c["splitT"] and d.sampleDate == c["sampleDate"] and d.thrh == c["thrh"]
+        assert d.times == c["times"] and d.lambdah1 == c["lambdah1"] and d.lambdah2 == c["lambdah2"]
+        assert relerr(d.llh, c["llh"]) < TOL and relerr(d.jaf, c["jaf"]) < TOL
+        assert relerr(d.lambda1, c["lambda1"]) < 1e-8 and relerr(d.lambda2, c["lambda2"]) < 1e-8
+        with open(fn) as f:
+            ours = f.read().splitlines()
+        theirs = c["text"].splitlines()
+        assert len(ours) == len(theirs) and [len(a.split("\t")) for a in ours] == [len(b.split("\t")) for b in theirs]
+        for a, b in zip(ours, theirs):  # same keys, and every number of the file within 1e-8 (Pr columns absolute)
+            wa, wb = a.split("\t"), b.split("\t")
+            assert wa[0] == wb[0]
+            if wa[0] in ("RS", "SFS", "DSF", "LK", "TR", "SCT", "SCE"):
+                va, vb = np.array(wa[1:], dtype=float), np.array(wb[1:], dtype=float)
+                assert np.all(np.abs(va - vb) <= 1e-8 * np.maximum(1.0, np.abs(vb))), (name, a, b)
+
+
 def test_fit_matches_reference(golden_datasets, golden_fits):
     """Solve(): scipy Nelder-Mead around the device objective reproduces the reference's simplex sequence."""
     from misti_b200 import MigrationInference

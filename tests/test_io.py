@@ -155,3 +155,24 @@ def test_read_jafs_format_version_0(tmp_path, capsys):
     fn.write_text("#MiSTI_JAF version 1.0\n")  # the older names only exist with versions < 1
     with pytest.raises(SystemExit):
         mio.read_jafs(str(fn))
+
+
+def test_read_migration_equals_the_reference(tmp_path, capsys):
+    """`.mi` files written by the reference (tests/golden/mi.json, generator gen_mi_golden.py) parse to exactly what the
+    reference's ReadMigration made of them: scaled times, corrected and PSMC-apparent rates, likelihood, split, spectrum."""
+    import json
+    with open(os.path.join(ROOT, "tests", "golden", "mi.json")) as f:
+        cases = json.load(f)["cases"]
+    for c in cases:
+        fn = tmp_path / (c["name"] + ".mi")
+        fn.write_text(c["text"])
+        d = mio.read_migration(str(fn))
+        assert capsys.readouterr().out == "Format version:  0.4\n"
+        for k in ("llh", "splitT", "sampleDate", "thrh", "jaf", "times", "lambda1", "lambda2", "lambdah1", "lambdah2"):
+            assert getattr(d, k) == c[k], (c["name"], k)
+        n = len(c["times"])
+        assert len(d.mu1) == len(d.mu2) == n and all(len(p[0]) == len(p[1]) == n for p in (d.pr11, d.pr22, d.pr12))
+        assert d.migStart is None and d.mi is None
+        if c["name"] == "config2_cpfit":  # the band -mi 2 5 12 0.8: rates into population 2 on intervals 5..11
+            assert [k for k, v in enumerate(d.mu2) if v != 0] == list(range(5, 12)) and not any(d.mu1)
+            assert abs(d.pr11[0][0] - 1.0) < 1e-12 and d.pr11[0][c["splitT"]] == 0  # no Pr columns from the split on
