@@ -1,0 +1,166 @@
+#!/usr/bin/env python3
+"""Wider parity sweeps than the test suite affords (run under gpurun; prints JSON):
+
+A  JSFS stage alone on N random grids / models per seed (tests/_cases.random_jsfs_cases: every segment type and event
+   combination), rates injected, against the CPU oracle;
+B  end to end in --cpfit mode on the synthetic PSMC pairs (plain and ancient-sample): random split time, one or two bands
+   with optimised rates at random places before the split, sometimes a pulse, random parameter vectors -- the correction
+   chain with its trust-region solves, the segment pre-pass, the sweep and the likelihood against the CPU oracle.
+
+The oracle (test infrastructure) runs on the host cores in worker processes."""
+import json
+import multiprocessing as mp
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+for _k in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS"):
+    os.environ.setdefault(_k, "1")
+
+
+def relerr(a, b):
+    a, b = np.asarray(a, dtype=float), np.asarray(b, dtype=float)
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300)))
+
+
+def oracle_jsfs(c):
+    from oracle.misti_oracle import ModelError, OracleModel
+    times, lam, st, sd = c["grid"]
+    try:
+        om = OracleModel(times, lam, c["sfs"], st, c["mi"], c["pu"], trueEPS=True, unfolded=c["flags"]["unfolded"], sampleDate=sd)
+    except ModelError:  # the generator can draw a layout the reference rejects (an empty band at the end of the grid)
+        return None
+    llh = om.likelihood([])
+    return float(llh), [float(v) for v in om.JAFS], [[float(a), float(b)] for a, b in om.lc]
+
+
+def oracle_e2e(job):
+    from oracle.misti_oracle import OracleModel
+    ds, st, mi, pu, par = job
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):
+        om = OracleModel(ds["times"], ds["lambdas"], ds["sfs"], st, mi, pu, cpfit=True, smooth=True, unfolded=True,
+                         sampleDate=ds.get("sampleDate", 0))
+        llh = om.likelihood(list(par))
+    return float(llh), ([float(v) for v in om.JAFS] if np.isfinite(llh) else None)
+
+
+def main():
+    import misti_b200
+    from _cases import bands_pulses, random_jsfs_cases
+    out = {}
+    eng = misti_b200.Engine(0)
+    pool = mp.get_context("spawn").Pool(os.cpu_count() or 1)
+
+    # ---- A ------------------------------------------------------------------------------------------
+    worst, n_cases, bad = 0.0, 0, []
+    for seed in range(1, 11):
+        cases = random_jsfs_cases(60, seed=seed)
+        refs = pool.map(oracle_jsfs, cases)
+        cases, refs = [c for c, r in zip(cases, refs) if r is not None], [r for r in refs if r is not None]
+        for uf in (True, False):
+            sel = [(c, r) for c, r in zip(cases, refs) if c["flags"]["unfolded"] == uf]
+            eng.clear_models()
+            mids = []
+            for c, _ in sel:
+                times, lam, st, sd = c["grid"]
+                bands, pulses = bands_pulses(c)
+                mids.append(eng.add_model(eng.add_grid(times, lam), st, sd, bands, pulses))
+            eng.set_data([c["sfs"] for c, _ in sel], uf)
+            B = len(sel)
+            inj = np.zeros((B, eng.numT_max, 2))
+            for b, (_, r) in enumerate(sel):
+                inj[b, :len(r[2])] = np.array(r[2])
+            res = eng.evaluate(np.zeros((B, 0)), model_ids=np.array(mids, dtype=np.int32), flags=8 if uf else 0, lc_inject=inj,
+                               row_ids=np.arange(B, dtype=np.int32), want=("jafs", "status"))
+            for b, (c, r) in enumerate(sel):
+                n_cases += 1
+                n = 7 if uf else 4
+                if res["status"][b] != 0 or not np.isfinite(r[0]):
+                    bad.append({"seed": seed, "name": c["name"], "status": int(res["status"][b]), "oracle_llh": r[0]})
+                    continue
+                e = max(relerr(res["llh"][b, 0], r[0]), relerr(res["jafs"][b][:n], r[1][:n]))
+                if e > 1e-9:
+                    bad.append({"seed": seed, "name": c["name"], "relerr": e})
+                worst = max(worst, e)
+    out["A_jsfs_stage"] = {"cases": n_cases, "worst_relerr": worst, "outside_1e-9_or_failed": bad}
+    print("A", n_cases, worst, len(bad), file=sys.stderr, flush=True)
+
+    # ---- B ------------------------------------------------------------------------------------------
+    with open(os.path.join(ROOT, "tests", "golden", "datasets.json")) as f:
+        dss = json.load(f)["datasets"]
+    rng = np.random.default_rng(77)
+    flags = misti_b200.FLAG_CORRECT | misti_b200.FLAG_CPFIT | misti_b200.FLAG_SMOOTH | misti_b200.FLAG_UNFOLDED
+    errs, mism, runaway, n_ok, n_tot = [], [], 0, 0, 0
+    for dsn in ("synthetic", "synthetic_ancient"):
+        ds = dss[dsn]
+        sd = int(ds.get("sampleDate", 0))
+        jobs, layouts = [], []
+        for _ in range(40):  # 40 layouts x 6 parameter vectors per data set
+            st = int(rng.integers(max(sd + 8, 25), 61))
+            mi, pu, used = [], [], [[False] * st, [False] * st]
+            for _b in range(int(rng.integers(1, 3))):
+                pop = int(rng.integers(0, 2))
+                a = int(rng.integers(sd, st - 3))
+                b = int(rng.integers(a + 1, min(st, a + 12) + 1))
+                if any(used[pop][a:b]):
+                    continue
+                for i in range(a, b):
+                    used[pop][i] = True
+                mi.append([pop + 1, a, b, 0.5, 1])
+            if not mi:
+                continue
+            if rng.random() < 0.3:
+                pu.append([int(rng.integers(1, 3)), int(rng.integers(sd, st)), 0.05, 1])
+            P = len(mi) + len(pu)
+            for _p in range(6):
+                par = rng.uniform(0.0, 2.0, P)
+                if pu:
+                    par[-1] = rng.uniform(0.0, 0.5)
+                jobs.append((ds, st, mi, pu, [float(v) for v in par]))
+            layouts.append((st, mi, pu, P))
+        refs = pool.map(oracle_e2e, jobs, chunksize=4)
+        eng.clear_models()
+        gid = eng.add_grid(ds["times"], ds["lambdas"])
+        eng.set_data([ds["sfs"]], True)
+        k = 0
+        for st, mi, pu, P in layouts:
+            bands, pulses = bands_pulses({"mi": mi, "pu": pu})
+            mid = eng.add_model(gid, st, sd, bands, pulses)
+            par = np.array([jobs[k + j][4] for j in range(6)])
+            res = eng.evaluate(par, model=mid, flags=flags, want=("jafs", "status", "lc"))
+            for j in range(6):
+                llh_ref, jafs_ref = refs[k + j]
+                n_tot += 1
+                stt = int(res["status"][j])
+                if not np.isfinite(llh_ref) or stt != 0:
+                    if np.isfinite(llh_ref) != (stt == 0):
+                        mism.append({"dataset": dsn, "st": st, "mi": mi, "pu": pu, "par": jobs[k + j][4], "status": stt, "oracle_llh": llh_ref})
+                    continue
+                e = max(relerr(res["llh"][j, 0], llh_ref), relerr(res["jafs"][j], jafs_ref))
+                big = float(np.nanmax(res["lc"][j])) > 1e3  # a run-away correction of the reference's own solver (rates ~1e5...1e8)
+                if big:
+                    runaway += 1
+                else:
+                    n_ok += 1
+                errs.append({"e": e, "runaway": big, "dataset": dsn, "st": st, "mi": mi, "pu": pu, "par": jobs[k + j][4]})
+            k += 6
+    reg = [x["e"] for x in errs if not x["runaway"]]
+    run = [x["e"] for x in errs if x["runaway"]]
+    out["B_end_to_end_cpfit"] = {"items": n_tot, "compared_regular": n_ok, "compared_runaway": runaway,
+                                 "worst_relerr_regular": max(reg) if reg else None, "worst_relerr_runaway": max(run) if run else None,
+                                 "regular_outside_1e-9": [x for x in errs if not x["runaway"] and x["e"] > 1e-9],
+                                 "ok_failed_mismatches": mism}
+    print("B", n_tot, n_ok, runaway, max(reg) if reg else None, max(run) if run else None, len(mism), file=sys.stderr, flush=True)
+    pool.close()
+    eng.close()
+    print(json.dumps(out, indent=1))
+
+
+if __name__ == "__main__":
+    main()
