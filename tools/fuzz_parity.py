@@ -7,6 +7,9 @@ B  end to end in --cpfit mode on the synthetic PSMC pairs (plain and ancient-sam
    with optimised rates at random places before the split, sometimes a pulse, random parameter vectors -- the correction
    chain with its trust-region solves, the segment pre-pass, the sweep and the likelihood against the CPU oracle.
 
+C  no migration: every split time of the grid (incl. the split at the end of the grid and at the sampling date), default and
+   --cpfit mode, folded and unfolded spectrum, both PSMC pairs.
+
 The oracle (test infrastructure) runs on the host cores in worker processes."""
 import json
 import multiprocessing as mp
@@ -47,6 +50,18 @@ def oracle_e2e(job):
         om = OracleModel(ds["times"], ds["lambdas"], ds["sfs"], st, mi, pu, cpfit=True, smooth=True, unfolded=True,
                          sampleDate=ds.get("sampleDate", 0))
         llh = om.likelihood(list(par))
+    return float(llh), ([float(v) for v in om.JAFS] if np.isfinite(llh) else None)
+
+
+def oracle_nomig(job):
+    from oracle.misti_oracle import OracleModel
+    import contextlib
+    import io
+    ds, st, uf, cpfit = job
+    with contextlib.redirect_stdout(io.StringIO()):
+        om = OracleModel(ds["times"], ds["lambdas"], ds["sfs"], st, [], [], cpfit=cpfit, smooth=True, unfolded=uf,
+                         sampleDate=ds.get("sampleDate", 0))
+        llh = om.likelihood([])
     return float(llh), ([float(v) for v in om.JAFS] if np.isfinite(llh) else None)
 
 
@@ -157,6 +172,37 @@ def main():
                                  "regular_outside_1e-9": [x for x in errs if not x["runaway"] and x["e"] > 1e-9],
                                  "ok_failed_mismatches": mism}
     print("B", n_tot, n_ok, runaway, max(reg) if reg else None, max(run) if run else None, len(mism), file=sys.stderr, flush=True)
+    # ---- C: no migration, every split time of the grid, default and cpfit mode, folded and unfolded -----------------------
+    worst_c, n_c, bad_c = 0.0, 0, []
+    for dsn in ("synthetic", "synthetic_ancient"):
+        ds = dss[dsn]
+        sd = int(ds.get("sampleDate", 0))
+        numT = len(ds["lambdas"])
+        sts = list(range(max(sd, 1), numT))  # a split at numT without migration never coalesces (the reference fails there)
+        for uf in (True, False):
+            for cpfit in (False, True):
+                refs = pool.map(oracle_nomig, [(ds, st, uf, cpfit) for st in sts], chunksize=4)
+                eng.clear_models()
+                gid = eng.add_grid(ds["times"], ds["lambdas"])
+                eng.set_data([ds["sfs"]], uf)
+                mids = np.array([eng.add_model(gid, st, sd) for st in sts], dtype=np.int32)
+                fl = misti_b200.FLAG_CORRECT | misti_b200.FLAG_SMOOTH | (misti_b200.FLAG_CPFIT if cpfit else 0) | (misti_b200.FLAG_UNFOLDED if uf else 0)
+                res = eng.evaluate(np.zeros((len(sts), 0)), model_ids=mids, flags=fl, want=("jafs", "status"))
+                n = 7 if uf else 4
+                for k, st in enumerate(sts):
+                    n_c += 1
+                    llh_ref, jafs_ref = refs[k]
+                    stt = int(res["status"][k])
+                    if not np.isfinite(llh_ref) or stt != 0:
+                        if np.isfinite(llh_ref) != (stt == 0):
+                            bad_c.append({"dataset": dsn, "st": st, "unfolded": uf, "cpfit": cpfit, "status": stt, "oracle_llh": llh_ref})
+                        continue
+                    e = max(relerr(res["llh"][k, 0], llh_ref), relerr(res["jafs"][k][:n], jafs_ref[:n]))
+                    worst_c = max(worst_c, e)
+                    if e > 1e-9:
+                        bad_c.append({"dataset": dsn, "st": st, "unfolded": uf, "cpfit": cpfit, "relerr": e})
+    out["C_no_migration_all_splits"] = {"items": n_c, "worst_relerr": worst_c, "outside_1e-9_or_mismatch": bad_c}
+    print("C", n_c, worst_c, len(bad_c), file=sys.stderr, flush=True)
     pool.close()
     eng.close()
     print(json.dumps(out, indent=1))
