@@ -101,6 +101,43 @@ def test_batch_against_oracle(engine, golden_datasets):
             assert relerr(out["llh"][b, 0], ref) < TOL, (b, params[b])
 
 
+def test_tiny_migration_rates_are_continuous(engine, golden_datasets):
+    """Where the REFERENCE loses accuracy: for a tiny positive rate m the 44-state generator is nearly singular (7 states
+    become stationary as m -> 0), and MigrationInference.SolveDifEq (:530-540) integrates with inv(M), so its expected
+    JSFS carries an error of about 1e-16 / m -- 7e-5 relative in the likelihood at m = 8e-12 and 14 % at m = 1e-14 for the
+    layout below (measured with the oracle, which makes the same scipy calls; tools/fuzz_parity.py part D found the regime:
+    Nelder-Mead walks into it whenever a rate is fitted to zero).  The device path has no inverse (uniformisation), so it
+    must be Lipschitz in m down to zero: |llh(m) - llh(0)| <= 2 |s| m with the slope s taken at m = 1e-5, where device and
+    oracle still agree to 1e-9 -- and it agrees with the oracle at m = 0 and from m = 1e-5 up."""
+    from oracle.misti_oracle import OracleModel
+    ds = golden_datasets["synthetic"]
+    mi, pu = [[2, 15, 23, 1.418, 1], [1, 8, 13, 1.358, 1]], [[1, 35, 0.05, 1]]
+    case = {"dataset": "synthetic", "splitT": 51, "mi": mi, "pu": pu, "flags": dict(trueEPS=False, cpfit=True, smooth=True, unfolded=True)}
+    mid, _ = _register(engine, golden_datasets, case)
+    x0, x2 = 1.7209222496044632, 0.4466402770983831
+
+    def oracle(m):
+        om = OracleModel(ds["times"], ds["lambdas"], ds["sfs"], 51, mi, pu, cpfit=True, smooth=True, unfolded=True)
+        return om.likelihood([x0, m, x2])
+
+    ms = [0.0, 1e-14, 1e-12, 7.84e-12, 9.9e-11, 1.01e-10, 1e-9, 1e-8, 1e-7, 1e-6, 1e-5, 1e-4, 1e-3]
+    out = engine.evaluate(np.array([[x0, m, x2] for m in ms]), model=mid, flags=flags_of(case), want=("jafs", "status"))
+    assert (out["status"] == 0).all()
+    llh = out["llh"][:, 0]
+    ref0 = oracle(0.0)
+    assert relerr(llh[0], ref0) < TOL
+    for m, v in zip(ms[-3:], llh[-3:]):
+        assert relerr(v, oracle(m)) < TOL, m
+    s = (llh[ms.index(1e-5)] - llh[0]) / 1e-5
+    assert 0.1 < abs(s) / abs(ref0) < 10.0  # the likelihood does depend on this rate: d llh / dm ~ 0.19 |llh|
+    for m, v in zip(ms[1:-3], llh[1:-3]):
+        assert abs(v - llh[0]) <= 1e-10 * abs(ref0) + 2.0 * abs(s) * m, (m, v, llh[0])
+    for m in (1e-9, 1e-8, 1e-7, 1e-6):  # and linear from where the slope term is above rounding
+        assert abs((llh[ms.index(m)] - llh[0]) / m - s) < 0.05 * abs(s) + 1e-11 * abs(ref0) / m, m
+    # the reference's own deviation from that curve, for the record: four orders of magnitude above the tolerance
+    assert abs(oracle(7.84e-12) - ref0) > 1e-6 * abs(ref0)
+
+
 def test_bootstrap_rows_and_split_grid(engine, golden_datasets):
     """config 5 shape: several split times (one model each) x bootstrap rows in ONE call; each (item, row)
     llh must equal the single-row evaluation, and row/items must be independent of batch composition."""
