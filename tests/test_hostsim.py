@@ -276,3 +276,37 @@ def test_forward_map_matches_reference(hostsim):
                               ctypes.c_double(mu[0]), ctypes.c_double(mu[1]), _p(lh), _p(Pr))
         assert relerr(lh, case["expect"]["lh"]) < 1e-11, case["name"]
         assert relerr(Pr + 1.0, np.array(case["expect"]["Pr"]) + 1.0) < 1e-13, case["name"]
+
+
+def test_tiny_migration_rates_host_build(hostsim, golden_datasets):
+    """CPU counterpart of tests/test_gpu_parity.py::test_tiny_migration_rates_are_continuous: for a tiny positive rate the
+    reference's SolveDifEq (inv(M) of a nearly singular generator, MigrationInference.py:530-540) is off by about 1e-16 / m,
+    which the oracle -- same scipy calls -- reproduces; the device numerics (uniformisation, no inverse) stay Lipschitz in m
+    down to zero and agree with the oracle at m = 0 and where the oracle is accurate (m >= 1e-5)."""
+    from oracle.misti_oracle import OracleModel
+    ds = golden_datasets["synthetic"]
+    mi, pu = [[2, 15, 23, 1.418, 1], [1, 8, 13, 1.358, 1]], [[1, 35, 0.05, 1]]
+    x0, x2 = 1.7209222496044632, 0.4466402770983831
+
+    def host(m):
+        case = {"dataset": "synthetic", "splitT": 51, "mi": mi, "pu": pu, "params": [x0, m, x2],
+                "flags": dict(trueEPS=False, cpfit=True, smooth=True, unfolded=True)}
+        rc, lc, _, _ = _chain(hostsim, golden_datasets, case)
+        assert rc == 0
+        rc, _, _, llh, _ = _jsfs(hostsim, golden_datasets, case, lc)
+        assert rc == 0
+        return llh
+
+    def oracle(m):
+        om = OracleModel(ds["times"], ds["lambdas"], ds["sfs"], 51, mi, pu, cpfit=True, smooth=True, unfolded=True)
+        return om.likelihood([x0, m, x2])
+
+    ref0, h0 = oracle(0.0), host(0.0)
+    assert relerr(h0, ref0) < 1e-9
+    for m in (1e-5, 1e-3):
+        assert relerr(host(m), oracle(m)) < 1e-9, m
+    s = (host(1e-5) - h0) / 1e-5
+    for m in (1e-14, 7.84e-12, 1e-9, 1e-7):
+        assert abs(host(m) - h0) <= 1e-10 * abs(ref0) + 2.0 * abs(s) * m, m
+    # the reference's algorithm at the same points: 14 % off at 1e-14, 7e-5 at 7.84e-12
+    assert abs(oracle(1e-14) - ref0) > 1e-2 * abs(ref0) and abs(oracle(7.84e-12) - ref0) > 1e-6 * abs(ref0)
