@@ -101,6 +101,30 @@ def test_batch_against_oracle(engine, golden_datasets):
             assert relerr(out["llh"][b, 0], ref) < TOL, (b, params[b])
 
 
+def test_mixture_threshold(engine, golden_datasets):
+    """MiSTI.py -mth (CorrectLambda.SolveLambdaSystem, CorrectLambda.py:267-272): once the lineage distributions of the two
+    genomes are closer than the threshold the interval is rejected and the evaluation fails (-inf).  Same accept / reject
+    pattern over a range of migration rates as the oracle, same likelihoods where accepted."""
+    from oracle.misti_oracle import OracleModel
+    ds = golden_datasets["synthetic"]
+    mi = [[2, 5, 12, 0.8, 1]]
+    case = {"dataset": "synthetic", "splitT": 40, "mi": mi, "pu": [], "flags": dict(trueEPS=False, cpfit=True, smooth=True, unfolded=True)}
+    mid, _ = _register(engine, golden_datasets, case)
+    ms = np.linspace(0.0, 4.0, 21).reshape(-1, 1)
+    seen = set()
+    for th in (0.9, 1.2, 1.35):
+        out = engine.evaluate(ms, model=mid, flags=flags_of(case), mixtureTH=th, want=("jafs", "status"))
+        for b in range(len(ms)):
+            om = OracleModel(ds["times"], ds["lambdas"], ds["sfs"], 40, mi, [], cpfit=True, smooth=True, unfolded=True, mixtureTH=th)
+            ref = om.likelihood([float(ms[b, 0])])
+            seen.add(bool(np.isfinite(ref)))
+            if not np.isfinite(ref):
+                assert out["status"][b] != 0 and out["llh"][b, 0] == -np.inf, (th, ms[b, 0])
+            else:
+                assert out["status"][b] == 0 and relerr(out["llh"][b, 0], ref) < TOL, (th, ms[b, 0])
+    assert seen == {True, False}  # the thresholds above cut the range of rates in two
+
+
 def test_tiny_migration_rates_are_continuous(engine, golden_datasets):
     """Where the REFERENCE loses accuracy: for a tiny positive rate m the 44-state generator is nearly singular (7 states
     become stationary as m -> 0), and MigrationInference.SolveDifEq (:530-540) integrates with inv(M), so its expected
