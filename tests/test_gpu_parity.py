@@ -101,6 +101,28 @@ def test_batch_against_oracle(engine, golden_datasets):
             assert relerr(out["llh"][b, 0], ref) < TOL, (b, params[b])
 
 
+def test_nosmooth_against_oracle(engine, golden_datasets):
+    """MiSTI.py --nosmooth (MigrationInference smooth=False: the corrected rates are used as they come, no SmoothConst pass,
+    MigrationInference.py:380-405): with and without migration, cpfit and default mode, folded and unfolded, both PSMC pairs."""
+    from oracle.misti_oracle import OracleModel
+    for dsn, st in (("synthetic", 40), ("synthetic_ancient", 45)):
+        ds = golden_datasets[dsn]
+        sd = int(ds["sampleDate"])
+        for uf in (True, False):
+            for cpfit, mi, par in ((True, [[2, sd + 2, sd + 9, 0.8, 1]], [0.0, 0.4, 1.1, 2.3]), (True, [], [None]), (False, [], [None])):
+                case = {"dataset": dsn, "splitT": st, "mi": mi, "pu": [], "flags": dict(trueEPS=False, cpfit=cpfit, smooth=False, unfolded=uf)}
+                mid, _ = _register(engine, golden_datasets, case)
+                P = 1 if mi else 0
+                params = np.array([[p] for p in par]) if mi else np.zeros((1, 0))
+                out = engine.evaluate(params, model=mid, flags=flags_of(case), want=("jafs", "status"))
+                n = 7 if uf else 4
+                for b, p in enumerate(par):
+                    om = OracleModel(ds["times"], ds["lambdas"], ds["sfs"], st, mi, [], cpfit=cpfit, smooth=False, unfolded=uf, sampleDate=sd)
+                    ref = om.likelihood([p] if P else [])
+                    assert np.isfinite(ref) and out["status"][b] == 0, (dsn, uf, cpfit, p)
+                    assert relerr(out["llh"][b, 0], ref) < TOL and relerr(out["jafs"][b][:n], om.JAFS[:n]) < TOL, (dsn, uf, cpfit, p)
+
+
 def test_mixture_threshold(engine, golden_datasets):
     """MiSTI.py -mth (CorrectLambda.SolveLambdaSystem, CorrectLambda.py:267-272): once the lineage distributions of the two
     genomes are closer than the threshold the interval is rejected and the evaluation fails (-inf).  Same accept / reject
