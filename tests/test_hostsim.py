@@ -310,3 +310,37 @@ def test_tiny_migration_rates_host_build(hostsim, golden_datasets):
         assert abs(host(m) - h0) <= 1e-10 * abs(ref0) + 2.0 * abs(s) * m, m
     # the reference's algorithm at the same points: 14 % off at 1e-14, 7e-5 at 7.84e-12
     assert abs(oracle(1e-14) - ref0) > 1e-2 * abs(ref0) and abs(oracle(7.84e-12) - ref0) > 1e-6 * abs(ref0)
+
+
+def test_random_layouts_end_to_end_host_build(hostsim, golden_datasets):
+    """--cpfit mode end to end on random layouts (split time, one or two optimised bands, sometimes a pulse; plain and
+    ancient-sample PSMC pair) with random parameters: correction chain + segment pre-pass + sweep + likelihood of the device
+    numerics (host build) against the oracle; an item fails in both or in neither.  (The GPU-sized version of this sweep is
+    tools/fuzz_parity.py part B.)"""
+    from oracle.misti_oracle import OracleModel
+    rng = np.random.default_rng(77)
+    compared = 0
+    for dsn in ("synthetic", "synthetic_ancient"):
+        ds = golden_datasets[dsn]
+        sd = int(ds["sampleDate"])
+        for _ in range(8):
+            st = int(rng.integers(max(sd + 8, 25), 61))
+            a = int(rng.integers(sd, st - 3))
+            b = int(rng.integers(a + 1, min(st, a + 12) + 1))
+            mi = [[int(rng.integers(1, 3)), a, b, 0.5, 1]]
+            pu = [[int(rng.integers(1, 3)), int(rng.integers(sd, st)), 0.05, 1]] if rng.random() < 0.3 else []
+            par = [float(rng.uniform(0.0, 2.0))] + ([float(rng.uniform(0.0, 0.5))] if pu else [])
+            case = {"dataset": dsn, "splitT": st, "mi": mi, "pu": pu, "params": par,
+                    "flags": dict(trueEPS=False, cpfit=True, smooth=True, unfolded=True)}
+            om = OracleModel(ds["times"], ds["lambdas"], ds["sfs"], st, mi, pu, cpfit=True, smooth=True, unfolded=True, sampleDate=sd)
+            ref = om.likelihood(par)
+            rc, lc, _, _ = _chain(hostsim, golden_datasets, case)
+            if not np.isfinite(ref):
+                assert rc != 0, (dsn, st, mi, pu, par)
+                continue
+            assert rc == 0, (dsn, st, mi, pu, par)
+            rc, raw, jn, llh, terms = _jsfs(hostsim, golden_datasets, case, lc)
+            assert rc == 0
+            assert relerr(jn, om.JAFS) < 1e-9 and relerr(llh, ref) < 1e-9, (dsn, st, mi, pu, par)
+            compared += 1
+    assert compared >= 10
