@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MISTI_ABI_VERSION 1
+#define MISTI_ABI_VERSION 2
 
 /* error codes (function return values) */
 #define MISTI_E_ARG (-1)     /* invalid argument / unknown id / capacity exceeded */
@@ -90,6 +90,9 @@ typedef struct misti_eval_io {
     int32_t* terms;          /* [B] sparse mat-vecs spent in the JSFS stage (a closed-form zero-migration run = 1) */
     const int32_t* row_ids;  /* [B] score item b against data row row_ids[b] ONLY; llh is then [B] instead of
                                 [B][R] (one optimiser simplex per (bootstrap row, split time) pair)         */
+    int32_t* solve_trace;    /* [B][numT_max][2] per interval: evaluations (`nfev`) and termination `status` of its
+                                scipy.optimize.least_squares solve (CorrectLambda.py:85, 260, 303, 305), (0, -9) where
+                                the interval has a closed form -- the iterate-level record behind `nfev`    */
 } misti_eval_io;
 
 int misti_abi_version(void);
@@ -143,6 +146,36 @@ int misti_eval_batch(misti_ctx* ctx, int32_t B, int32_t P, const double* params,
 int misti_nelder_mead(misti_ctx* ctx, int32_t S, int32_t N, const double* x0, const int32_t* model_ids, const int32_t* row_ids,
                       uint32_t flags, double mixture_th, double xatol, double fatol, int64_t maxiter, int64_t maxfev,
                       double* x, double* fun, int64_t* nit, int64_t* nfev, int32_t* status, int64_t* info);
+
+/* The general form of the on-device optimiser: S independent fits, each a Nelder-Mead simplex that takes scipy's decisions,
+ * optionally wrapped in a basin-hopping walker (scipy.optimize.basinhopping as MigrationInference.Solve(globalOpt=True) calls
+ * it, MigrationInference.py:724: niter = 100, T = 0.5, stepsize = 0.5, local search = Nelder-Mead with scipy's defaults
+ * xatol = fatol = 1e-4, maxiter = maxfev = 200 N).  Nothing waits for the slowest fit: the points of a round are packed
+ * behind a device-side counter, the evaluation kernels read the count from the device, and a walker whose local search has
+ * ended takes its Metropolis decision and starts its next local search in the following round, whatever the other walkers
+ * are doing.  A single walker with generator state s reproduces scipy.optimize.basinhopping(..., rng=s).  Host pointers. */
+typedef struct misti_fit_opts {
+    double xatol, fatol;       /* Nelder-Mead termination (of every local search)                                   */
+    int64_t maxiter, maxfev;   /* per local search; < 0 = none                                                       */
+    int32_t niter;             /* basin-hopping hops after the initial minimisation; < 0 = plain Nelder-Mead fits    */
+    int32_t interval;          /* the step size adapts every `interval` hops (scipy: 50)                             */
+    double T, stepsize, target_accept_rate, stepwise_factor; /* scipy: 1.0 (reference: 0.5), 0.5, 0.5, 0.9          */
+    const uint64_t* rng_state; /* [S][4] numpy PCG64 state per walker: state >> 64, state & (2^64 - 1), inc >> 64,
+                                  inc & (2^64 - 1) of numpy.random.default_rng(seed).bit_generator.state             */
+} misti_fit_opts;
+typedef struct misti_fit_result {
+    double* x;        /* [S][N] plain fits: best vertex; walkers: lowest minimum seen (scipy's Storage)              */
+    double* fun;      /* [S]    -llh there                                                                           */
+    int64_t* nit;     /* [S]    plain fits: iterations; walkers: hops taken                                          */
+    int64_t* nfev;    /* [S]    scipy's evaluation count (walkers: summed over the local searches)                   */
+    int32_t* status;  /* [S]    plain fits: 0 converged, 1 maxfev, 2 maxiter; walkers: 0 = the minimum is a converged one */
+    int64_t* accepted;/* [S]    walkers: accepted hops (nullable)                                                    */
+    int64_t* failures;/* [S]    walkers: local searches that did not converge (nullable)                             */
+    int64_t rounds, points; /* out: rounds of launches that evaluated something, points evaluated                    */
+    int32_t graph;    /* out: 1 if the rounds were replayed as a CUDA graph                                          */
+} misti_fit_result;
+int misti_fit(misti_ctx* ctx, int32_t S, int32_t N, const double* x0, const int32_t* model_ids, const int32_t* row_ids,
+              uint32_t flags, double mixture_th, const misti_fit_opts* opts, misti_fit_result* res);
 
 /* Score B given spectra (7 non-negative weights each, normalised on the device) against every data
  * row: llh[b*R + r].  Host pointers.  Replaces the likelihood tail used on its own, e.g.

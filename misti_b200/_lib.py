@@ -9,6 +9,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MISTI_B200_LIB") or os.path.join(HERE, "libmisti_b200.so")  # the variable is a development knob
 
+ABI_VERSION = 2
 MAX_BANDS, MAX_PULSES, MAX_PARAMS = 8, 8, 16
 
 FLAG_CORRECT, FLAG_CPFIT, FLAG_SMOOTH, FLAG_UNFOLDED, FLAG_DEVICE_PTRS = 1, 2, 4, 8, 256
@@ -32,7 +33,20 @@ class ModelDesc(ctypes.Structure):
 class EvalIO(ctypes.Structure):
     _fields_ = [("lc_inject", ctypes.c_void_p), ("jafs", ctypes.c_void_p), ("jafs_raw", ctypes.c_void_p),
                 ("lc_out", ctypes.c_void_p), ("pr_out", ctypes.c_void_p), ("status", ctypes.c_void_p),
-                ("nfev", ctypes.c_void_p), ("terms", ctypes.c_void_p), ("row_ids", ctypes.c_void_p)]
+                ("nfev", ctypes.c_void_p), ("terms", ctypes.c_void_p), ("row_ids", ctypes.c_void_p),
+                ("solve_trace", ctypes.c_void_p)]
+
+
+class FitOpts(ctypes.Structure):
+    _fields_ = [("xatol", ctypes.c_double), ("fatol", ctypes.c_double), ("maxiter", ctypes.c_int64), ("maxfev", ctypes.c_int64),
+                ("niter", ctypes.c_int32), ("interval", ctypes.c_int32), ("T", ctypes.c_double), ("stepsize", ctypes.c_double),
+                ("target_accept_rate", ctypes.c_double), ("stepwise_factor", ctypes.c_double), ("rng_state", ctypes.c_void_p)]
+
+
+class FitResult(ctypes.Structure):
+    _fields_ = [("x", ctypes.c_void_p), ("fun", ctypes.c_void_p), ("nit", ctypes.c_void_p), ("nfev", ctypes.c_void_p),
+                ("status", ctypes.c_void_p), ("accepted", ctypes.c_void_p), ("failures", ctypes.c_void_p),
+                ("rounds", ctypes.c_int64), ("points", ctypes.c_int64), ("graph", ctypes.c_int32)]
 
 
 class MistiLibraryError(RuntimeError):
@@ -59,6 +73,8 @@ SIGNATURES = {
                                          ctypes.c_uint32, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_int64,
                                          ctypes.c_int64, c_double_p, c_double_p, ctypes.POINTER(ctypes.c_int64),
                                          ctypes.POINTER(ctypes.c_int64), c_int32_p, ctypes.POINTER(ctypes.c_int64)]),
+    "misti_fit": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, c_double_p, c_int32_p, c_int32_p, ctypes.c_uint32,
+                                 ctypes.c_double, ctypes.POINTER(FitOpts), ctypes.POINTER(FitResult)]),
     "misti_coalescent_rates": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, c_double_p, ctypes.c_double,
                                               ctypes.c_double, c_double_p, c_double_p]),
     "misti_score_spectra": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, c_double_p, c_double_p]),
@@ -88,7 +104,7 @@ def load():
         fn = getattr(lib, name)  # AttributeError here = the library does not match the header
         fn.restype = res
         fn.argtypes = args
-    if lib.misti_abi_version() != 1:
+    if lib.misti_abi_version() != ABI_VERSION:
         raise MistiLibraryError("libmisti_b200.so ABI version mismatch")
     _lib = lib
     return lib

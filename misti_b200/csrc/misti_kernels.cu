@@ -59,7 +59,15 @@ misti_correct_kernel(int B, int P, const double* __restrict__ params, const int*
                      const double* __restrict__ gaux, const unsigned* __restrict__ cls_all, unsigned flags, double mixtureTH, const double* __restrict__ lc_inject, int numT_max, double* lc,
                      long stride, double* __restrict__ cpost, double* pr_out, int* __restrict__ status, int* __restrict__ nfev,
                      double* __restrict__ rec, int seg_cap, int* __restrict__ nseg, int* __restrict__ counters, int defer_post,
-                     int n_models) {
+                     int n_models, int* __restrict__ solve_trace, const int* __restrict__ count_ptr, int regime) {
+    // count_ptr (nullable): the number of items lives on the device (the on-device optimiser packs the points of a round
+    // behind a counter) and B is only the capacity the grid was sized for.  regime: 0 = run; 1 / 2 = this launch is one of
+    // the pair (four lanes per item | one thread per item) of which only the variant that suits the round's size runs.
+    if (count_ptr) {
+        const int n = *count_ptr;
+        if ((regime == 1 && n > kCoopMaxItems) || (regime == 2 && n <= kCoopMaxItems)) return;
+        B = n < B ? n : B;
+    }
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
     if (gtid < 8) counters[gtid] = 0;  // work and park counters of the two kernels that follow in the stream
     const int b = COOP ? gtid >> 2 : gtid;
@@ -102,8 +110,12 @@ misti_correct_kernel(int B, int P, const double* __restrict__ params, const int*
         // defer_post (cpfit mode): the post-split pass is left to the lane groups of the JSFS kernel; they get
         // exp(nc1 - nc0) in the first coefficient slot
         double nc[2] = {0.0, 0.0};
+        int* trace = solve_trace ? solve_trace + (long)b * 2 * numT_max : nullptr;
+        if (trace && (!COOP || (gtid & 3) == 0))
+            for (int t = 0; t < numT_max; ++t) { trace[2 * t] = 0; trace[2 * t + 1] = misti::kNoSolve; }
+        if (COOP && (gtid & 3) != 0) trace = nullptr;  // the four lanes of an item hold the same values: one of them writes
         st = misti::correct_lambdas_item<COOP>(md, tt, ll, par, flags, mixtureTH, lcb, kPitch, stride, pr, &nf, ga, cp, &cp_done, cls,
-                                               defer_post ? nc : nullptr);
+                                               defer_post ? nc : nullptr, trace);
         if (defer_post && cp_done) cp[0] = exp(nc[1] - nc[0]);
     }
     int ns = 0;
@@ -189,7 +201,12 @@ misti_jsfs_kernel(int B, int P, const double* __restrict__ params, const int* __
                   const ModelDesc* __restrict__ models, const double* __restrict__ rec, int seg_cap, const int* __restrict__ nseg,
                   long stride, const double* __restrict__ cpost, ItemOut out, misti::Cont* __restrict__ conts,
                   int* __restrict__ park_list, int* __restrict__ park_count, int* __restrict__ work_counter,
-                  const double* __restrict__ post_tab, const double* __restrict__ lh) {
+                  const double* __restrict__ post_tab, const double* __restrict__ lh, const int* __restrict__ count_ptr) {
+    if (count_ptr) {  // the number of items lives on the device (see misti_correct_kernel)
+        const int n = *count_ptr;
+        B = n < B ? n : B;
+        if (B <= 0) return;
+    }
     // one item per 16-lane half warp (3 of the 44 chain states per lane), two items per warp
     __shared__ double ysm_all[kJsfsWarps * 2][misti::kGroupScratch];
     __shared__ misti::RunTable<misti::HalfWarpLanes> runtab;
@@ -625,50 +642,110 @@ __global__ void misti_coal_rates_kernel(const ModelDesc* __restrict__ models, in
     misti::coalescent_rates_item(md, times + md.grid_off, lh + 2 * (long)md.grid_off, params, mu, cls_all + md.cls_off, lh_out, pr_out);
 }
 
-// ---- Nelder-Mead on the device (misti_optim.cuh): one thread per simplex ---------------------------
-struct NmState {
+// ---- the optimisers on the device (misti_optim.cuh): one thread per simplex / walker -----------------
+// A fit is a stream of ROUNDS, each the same launches with the same arguments (so a few rounds are captured once as a
+// CUDA graph and replayed): propose -> correction kernel -> JSFS kernel -> stiff kernel -> apply.  Every simplex is a
+// small state machine of its own; nothing waits for the slowest one:
+//   * the points of a round are PACKED: a simplex that still runs reserves as many items as it has points behind a
+//     device-side counter, so a round costs what its running simplices cost, and the evaluation kernels take the item
+//     count from the device (no host round trip, no empty slots);
+//   * look-ahead (two Nelder-Mead iterations per round, 4 (3N + 4) points per simplex) switches itself on when the
+//     simplices still running are few enough for the round to stay in the flat part of the latency curve;
+//   * basin-hopping walkers (BhConfig.niter >= 0) take their Metropolis decision and start their next local search in
+//     the propose step of the round after their local search ended -- no barrier between the hops of different walkers.
+struct FitState {
     double *sim, *fsim;          // [S][(N+1) N], [S][N+1]
     long long *iters, *fcalls;   // [S]
     int *status, *phase;         // [S]
     const int *model, *row;      // [S] the pair each simplex fits
+    int *first, *look;           // [S] where the simplex's points of this round start in the batch; look-ahead used
+    // walkers (null for plain fits)
+    double *bh_x, *bh_best_x;    // [S][N]
+    double *bh_energy, *bh_best_f, *bh_step;
+    int *bh_ok, *bh_best_ok, *bh_done;
+    long long *bh_nfev, *bh_fail, *bh_nstep, *bh_naccept, *bh_hop;
+    misti::Pcg64* rng;
 };
 
-// the points of this round -> the evaluation batch (slot j of simplex s is item s * slots + j; unused slots get model -1)
-// (the number of points a round submits is added up in slot `round % kNmRing` of a ring; the round counter lives on the
-// device and is advanced by the apply kernel, so that a round is the same sequence of launches with the same arguments
-// every time -- a CUDA graph)
-constexpr int kNmRing = 64;
-__global__ void misti_nm_propose_kernel(int S, misti::NmConfig cfg, NmState st, double* __restrict__ params,
-                                        int* __restrict__ item_model, int* __restrict__ item_row, int* __restrict__ ring,
-                                        const int* __restrict__ round) {
+// device-side bookkeeping of a fit: one block of ints
+enum { FC_ITEMS = 0,        // items packed in the current round (read by the evaluation kernels)
+       FC_ROUND = 1,        // round counter
+       FC_RUN0 = 2,         // simplices that submitted points, by round parity (this round's count decides the next one's look-ahead)
+       FC_RUN1 = 3,
+       FC_ROUNDS_USED = 4,  // rounds that evaluated something
+       FC_LAST = 5,         // items of the last completed round (0 = every simplex has ended)
+       FC_POINTS_LO = 6, FC_POINTS_HI = 7,  // all items evaluated so far (64 bits)
+       FC_N = 8 };
+
+constexpr int kFitMaxPts = 64 * 4 > 17 * 16 ? 64 * 4 : 17 * 16;  // doubles one simplex can submit per round
+
+__global__ void misti_fit_propose_kernel(int S, misti::NmConfig cfg, misti::BhConfig bh, FitState st, double* __restrict__ params,
+                                         int* __restrict__ item_model, int* __restrict__ item_row, int* __restrict__ fc,
+                                         int look_max_items, int cap_items) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= S) return;
-    int* n_submitted = ring + (*round % kNmRing);
     const int N = cfg.N;
-    const long b0 = (long)s * cfg.slots;
-    const int n = misti::nm_propose(cfg, st.sim + (long)s * (N + 1) * N, st.fsim + (long)s * (N + 1), st.iters + s, st.fcalls + s,
-                                    st.status + s, st.phase + s, params + b0 * N);
-    const int model = st.model[s], row = st.row[s];
-    for (int j = 0; j < cfg.slots; ++j) {
-        item_model[b0 + j] = j < n ? model : -1;
-        item_row[b0 + j] = row;
+    double* sim = st.sim + (long)s * (N + 1) * N;
+    double* fsim = st.fsim + (long)s * (N + 1);
+    if (bh.niter >= 0 && st.phase[s] == misti::NM_DONE && !st.bh_done[s]) {
+        misti::BhWalker w;
+        w.x = st.bh_x + (long)s * N; w.best_x = st.bh_best_x + (long)s * N;
+        w.energy = st.bh_energy + s; w.best_f = st.bh_best_f + s; w.step = st.bh_step + s;
+        w.ok = st.bh_ok + s; w.best_ok = st.bh_best_ok + s; w.done = st.bh_done + s;
+        w.nfev = st.bh_nfev + s; w.failures = st.bh_fail + s; w.nstep = st.bh_nstep + s; w.naccept = st.bh_naccept + s;
+        w.hop = st.bh_hop + s; w.rng = st.rng + s;
+        misti::bh_advance(bh, N, w, sim, fsim, st.iters + s, st.fcalls + s, st.status + s, st.phase + s);
     }
-    if (n > 0) atomicAdd(n_submitted, n);
+    if (st.phase[s] == misti::NM_DONE) { st.first[s] = -1; return; }
+    // look-ahead while the simplices that ran in the previous round are few (the count only ever falls)
+    const int round = fc[FC_ROUND];
+    const int running_prev = round == 0 ? S : fc[FC_RUN0 + (round & 1)];
+    misti::NmConfig c = cfg;
+    c.lookahead = cfg.lookahead && N <= misti::kNmLookaheadMaxN && (long)running_prev * misti::nm_slots(N, true) <= look_max_items;
+    c.slots = misti::nm_slots(N, c.lookahead != 0);
+    double pts[kFitMaxPts];
+    const int n = misti::nm_propose(c, sim, fsim, st.iters + s, st.fcalls + s, st.status + s, st.phase + s, pts);
+    st.look[s] = c.lookahead;
+    if (n <= 0) { st.first[s] = -1; return; }
+    const int base = atomicAdd(fc + FC_ITEMS, n);
+    if (base + n > cap_items) { st.first[s] = -1; return; }  // cannot happen: the capacity covers every simplex without look-ahead
+    st.first[s] = base;
+    atomicAdd(fc + FC_RUN0 + ((round + 1) & 1), 1);
+    const int model = st.model[s], row = st.row[s];
+    for (int j = 0; j < n; ++j) {
+        for (int k = 0; k < N; ++k) params[(long)(base + j) * N + k] = pts[j * N + k];
+        item_model[base + j] = model;
+        item_row[base + j] = row;
+    }
 }
 
-__global__ void misti_nm_apply_kernel(int S, misti::NmConfig cfg, NmState st, const double* __restrict__ params,
-                                      const double* __restrict__ llh, int* __restrict__ ring, int* __restrict__ round) {
+__global__ void misti_fit_apply_kernel(int S, misti::NmConfig cfg, FitState st, const double* __restrict__ params,
+                                       const double* __restrict__ llh, int* __restrict__ fc, int* __restrict__ h_mirror) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s == 0) {  // next round: advance the counter, clear its slot of the ring
-        const int r = *round + 1;
-        *round = r;
-        ring[r % kNmRing] = 0;
+    if (s < S && st.first[s] >= 0) {
+        const int N = cfg.N;
+        misti::NmConfig c = cfg;
+        c.lookahead = st.look[s];
+        c.slots = misti::nm_slots(N, c.lookahead != 0);
+        const long b0 = st.first[s];
+        misti::nm_apply(c, st.sim + (long)s * (N + 1) * N, st.fsim + (long)s * (N + 1), st.iters + s, st.fcalls + s, st.status + s,
+                        st.phase + s, params + b0 * N, llh + b0, true);  // the objective is -llh
     }
-    if (s >= S || st.phase[s] == misti::NM_DONE) return;
-    const int N = cfg.N;
-    const long b0 = (long)s * cfg.slots;
-    misti::nm_apply(cfg, st.sim + (long)s * (N + 1) * N, st.fsim + (long)s * (N + 1), st.iters + s, st.fcalls + s, st.status + s,
-                    st.phase + s, params + b0 * N, llh + b0, true);  // the objective is -llh
+    if (s == 0) {  // next round (the counters are not read by the other threads of this kernel)
+        const int n = fc[FC_ITEMS], r = fc[FC_ROUND];
+        fc[FC_LAST] = n;
+        if (n > 0) {
+            fc[FC_ROUNDS_USED] += 1;
+            const unsigned lo = (unsigned)fc[FC_POINTS_LO], add = (unsigned)n;
+            fc[FC_POINTS_LO] = (int)(lo + add);
+            if (lo + add < lo) fc[FC_POINTS_HI] += 1;
+        }
+        fc[FC_ITEMS] = 0;
+        fc[FC_RUN0 + (r & 1)] = 0;  // read by this round's propose step; the next round counts into it
+        fc[FC_ROUND] = r + 1;
+        if (h_mirror)  // pinned host memory: the host polls it between graph launches
+            for (int i = 0; i < FC_N; ++i) ((volatile int*)h_mirror)[i] = fc[i];
+    }
 }
 
 }  // namespace
@@ -722,13 +799,17 @@ struct misti_ctx {
     int *s_model_ids = nullptr, *s_terms = nullptr, *s_row_ids = nullptr;
     double *s_lc_io = nullptr, *s_pr = nullptr;
     size_t s_lc_io_cap = 0, s_pr_cap = 0;
+    int* s_trace = nullptr;
+    size_t s_trace_cap = 0;
     unsigned char* d_nm = nullptr;  // state and batch buffers of misti_nelder_mead (one block, carved up per call)
     size_t d_nm_cap = 0;
-    int* h_nm_counts = nullptr;     // pinned: points submitted per round (ring of kNmRing entries)
+    int* h_nm_counts = nullptr;     // pinned: copy of the fit's device-side counters (FC_*), refreshed after every batch of rounds
     cudaGraphExec_t nm_graph = nullptr;   // one round of misti_nelder_mead as a CUDA graph, kept while its arguments stay valid
     std::vector<unsigned long long> nm_graph_key;
     unsigned long long generation = 0;    // bumped whenever a device buffer moves or a launch argument of the kernels changes
     int nm_use_graph = 1;                 // tuning knob MISTI_NM_GRAPH
+    int nm_rounds_per_graph = 4;          // rounds captured in one graph (tuning knob MISTI_NM_ROUNDS)
+    int nm_graph_launches = 0;            // kernel launches per round of the kept graph
     cudaEvent_t nm_ev[4] = {nullptr, nullptr, nullptr, nullptr};
     double* d_score = nullptr;      // scratch of misti_score_spectra
     size_t d_score_cap = 0;
@@ -926,6 +1007,7 @@ int misti_ctx_create(int device, void* stream, misti_ctx** out) {
     if (const char* e = getenv("MISTI_DEFER_POST")) ctx->defer_post = atoi(e);
     if (const char* e = getenv("MISTI_NM_LOOKAHEAD")) ctx->nm_lookahead = atoi(e);
     if (const char* e = getenv("MISTI_NM_GRAPH")) ctx->nm_use_graph = atoi(e);
+    if (const char* e = getenv("MISTI_NM_ROUNDS")) { const int v = atoi(e); if (v >= 1 && v <= 64) ctx->nm_rounds_per_graph = v; }
     if (const char* e = getenv("MISTI_MAX_CHUNK")) {
         const int v = atoi(e);
         if (v >= 1 && v <= kMaxChunk) ctx->max_chunk = v;
@@ -943,7 +1025,7 @@ void misti_ctx_destroy(misti_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     void* ptrs[] = {ctx->d_times, ctx->d_lh, ctx->d_gaux, ctx->d_cls, ctx->d_post, ctx->d_models, ctx->d_data, ctx->d_lc, ctx->d_cpost, ctx->d_status, ctx->d_nfev, ctx->d_conts, ctx->d_queue[0], ctx->d_queue[1], ctx->d_counts,
                     ctx->d_rec, ctx->d_nseg, ctx->s_params, ctx->s_llh, ctx->s_jafs, ctx->s_jafs_raw, ctx->s_model_ids, ctx->s_terms, ctx->s_row_ids, ctx->s_lc_io,
-                    ctx->s_pr, ctx->d_small, ctx->d_nm, ctx->d_score};
+                    ctx->s_pr, ctx->d_small, ctx->d_nm, ctx->d_score, ctx->s_trace};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     for (int i = 0; i < 3; ++i)
@@ -1106,7 +1188,7 @@ int misti_set_data(misti_ctx* ctx, int32_t R, const double* sfs, const double* l
 static int eval_chunk(misti_ctx* ctx, int B, int P, const double* d_params, const int* d_model_ids, int model_default,
                       unsigned flags, double mixture_th, const double* d_lc_inject, double* d_llh, double* d_jafs,
                       double* d_jafs_raw, double* d_lc_out, double* d_pr, int* d_status_out, int* d_nfev_out, int* d_terms,
-                      const int* d_row_ids) {
+                      const int* d_row_ids, int* d_trace = nullptr, const int* d_count = nullptr, int defer_override = -1) {
     int rc;
     if ((rc = ensure_batch(ctx, (size_t)B))) return rc;
     const long stride = (long)ctx->cap;
@@ -1115,19 +1197,23 @@ static int eval_chunk(misti_ctx* ctx, int B, int P, const double* d_params, cons
     // lanes of the JSFS kernel instead of at the end of the correction kernel's serial chain.  The work is the same either
     // way, so a full machine gains nothing (measured: 65 536 items 2 % slower), but an optimiser step does (1...1024 items
     // 0.33 -> 0.29 ms, 16 384 items 0.58 -> 0.54 ms).  The two variants differ in the order of summation (<= 1e-13).
-    const bool defer_auto = ctx->defer_post < 0 ? B <= kDeferPostMaxItems : ctx->defer_post != 0;
+    const bool defer_auto = defer_override >= 0 ? defer_override != 0 : (ctx->defer_post < 0 ? B <= kDeferPostMaxItems : ctx->defer_post != 0);
     const int defer_post = (defer_auto && (flags & MISTI_FLAG_CPFIT) && !d_lc_inject) ? 1 : 0;
     CK(cudaEventRecord(ctx->ev[0], ctx->stream));
-    // small batches: four lanes per item (see misti_correct_kernel); the knob MISTI_CORRECT_COOP = 0 / 1 forces a variant
+    // small batches: four lanes per item (see misti_correct_kernel); the knob MISTI_CORRECT_COOP = 0 / 1 forces a variant.
+    // With the item count on the device (d_count) both variants are launched and the one that suits the count runs.
     const bool coop = ctx->correct_coop < 0 ? B <= kCoopMaxItems : ctx->correct_coop != 0;
-#define MISTI_LAUNCH_CORRECT(MINB)                                                                                       \
-    if (coop) MISTI_LAUNCH_CORRECT2(MINB, true, 4L * B); else MISTI_LAUNCH_CORRECT2(MINB, false, (long)B)
-#define MISTI_LAUNCH_CORRECT2(MINB, COOP, NTHREADS)                                                                      \
+#define MISTI_LAUNCH_CORRECT2(MINB, COOP, NTHREADS, REGIME)                                                              \
     misti_correct_kernel<MINB, COOP><<<(unsigned)(((NTHREADS) + kCorrectThreads - 1) / kCorrectThreads), kCorrectThreads, 0, ctx->stream>>>( \
         B, P, d_params, d_model_ids, model_default, ctx->d_models, ctx->d_times, ctx->d_lh, ctx->d_gaux, ctx->d_cls, flags, mixture_th, \
         d_lc_inject, \
         numT_max, ctx->d_lc, stride, ctx->d_cpost, d_pr, ctx->d_status, ctx->d_nfev, ctx->d_rec, ctx->cap_seg, ctx->d_nseg, ctx->d_counts, \
-        defer_post, (int)ctx->h_models.size())
+        defer_post, (int)ctx->h_models.size(), d_trace, d_count, REGIME)
+#define MISTI_LAUNCH_CORRECT(MINB)                                                                                       \
+    if (d_count && ctx->correct_coop < 0) {                                                                              \
+        MISTI_LAUNCH_CORRECT2(MINB, true, 4L * (B < kCoopMaxItems ? B : kCoopMaxItems), 1);                              \
+        if (B > kCoopMaxItems) MISTI_LAUNCH_CORRECT2(MINB, false, (long)B, 2);                                           \
+    } else if (coop) MISTI_LAUNCH_CORRECT2(MINB, true, 4L * B, 0); else MISTI_LAUNCH_CORRECT2(MINB, false, (long)B, 0)
     switch (ctx->correct_minb) {  // register budget per thread: 4 -> 255, 8 -> 128, 12 -> 80 (tuning knob MISTI_CORRECT_MINB)
         case 4: MISTI_LAUNCH_CORRECT(4); break;
         case 12: MISTI_LAUNCH_CORRECT(12); break;
@@ -1150,7 +1236,7 @@ static int eval_chunk(misti_ctx* ctx, int B, int P, const double* d_params, cons
 #define MISTI_LAUNCH_JSFS2(MINB, DEFER)                                                                                    \
     misti_jsfs_kernel<MINB, DEFER><<<blocks, kJsfsWarps * 32, 0, ctx->stream>>>(                                           \
         B, P, d_params, d_model_ids, model_default, ctx->d_models, ctx->d_rec, ctx->cap_seg, ctx->d_nseg, stride, ctx->d_cpost, \
-        out, ctx->d_conts, ctx->d_queue[0], ctx->d_counts, ctx->d_counts + 4, ctx->d_post, ctx->d_lh)
+        out, ctx->d_conts, ctx->d_queue[0], ctx->d_counts, ctx->d_counts + 4, ctx->d_post, ctx->d_lh, d_count)
     switch (ctx->jsfs_minb) {  // register budget: 2 -> 255, 3 -> 168, 4 -> 128, 5 -> 96 (tuning knob MISTI_JSFS_MINB)
         case 2: MISTI_LAUNCH_JSFS(2); break;
         case 4: MISTI_LAUNCH_JSFS(4); break;
@@ -1169,7 +1255,7 @@ static int eval_chunk(misti_ctx* ctx, int B, int P, const double* d_params, cons
     ctx->launches += 2;
     CK(cudaEventRecord(ctx->ev[2], ctx->stream));
     ctx->ev_valid = true;
-    ctx->launches += 1;  // the correction kernel
+    ctx->launches += (d_count && ctx->correct_coop < 0 && B > kCoopMaxItems) ? 2 : 1;  // the correction kernel (or the pair of variants)
     if (d_lc_out) {
         const long n = (long)B * 2 * numT_max;
         misti_gather_lc_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(B, numT_max, d_model_ids, model_default,
@@ -1222,7 +1308,8 @@ int misti_eval_batch(misti_ctx* ctx, int32_t B, int32_t P, const double* params,
                             io->lc_out ? io->lc_out + off * 2 * numT_max : nullptr,
                             io->pr_out ? io->pr_out + off * (numT_max + 1) * 6 : nullptr, io->status ? io->status + off : nullptr,
                             io->nfev ? io->nfev + off : nullptr, io->terms ? io->terms + off : nullptr,
-                            io->row_ids ? io->row_ids + off : nullptr);
+                            io->row_ids ? io->row_ids + off : nullptr,
+                            io->solve_trace ? io->solve_trace + off * 2 * numT_max : nullptr);
             if (rc) return rc;
         }
         return 0;
@@ -1238,6 +1325,7 @@ int misti_eval_batch(misti_ctx* ctx, int32_t B, int32_t P, const double* params,
         const bool need_lc_io = io->lc_inject || io->lc_out;
         if (need_lc_io && (rc = ensure(ctx, &ctx->s_lc_io, &ctx->s_lc_io_cap, (size_t)n * 2 * numT_max))) return rc;
         if (io->pr_out && (rc = ensure(ctx, &ctx->s_pr, &ctx->s_pr_cap, (size_t)n * (numT_max + 1) * 6))) return rc;
+        if (io->solve_trace && (rc = ensure(ctx, &ctx->s_trace, &ctx->s_trace_cap, (size_t)n * 2 * numT_max))) return rc;
         if (P > 0)
             CK(cudaMemcpyAsync(ctx->s_params, params + off * P, (size_t)n * P * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
         if (model_ids)
@@ -1252,7 +1340,7 @@ int misti_eval_batch(misti_ctx* ctx, int32_t B, int32_t P, const double* params,
         rc = eval_chunk(ctx, n, P, ctx->s_params, model_ids ? ctx->s_model_ids : nullptr, model_default, flags, mixture_th,
                         io->lc_inject ? ctx->s_lc_io : nullptr, ctx->s_llh, ctx->s_jafs, ctx->s_jafs_raw,
                         io->lc_out ? ctx->s_lc_io : nullptr, io->pr_out ? ctx->s_pr : nullptr, nullptr, nullptr, ctx->s_terms,
-                        io->row_ids ? ctx->s_row_ids : nullptr);
+                        io->row_ids ? ctx->s_row_ids : nullptr, io->solve_trace ? ctx->s_trace : nullptr);
         if (rc) return rc;
         CK(cudaMemcpyAsync(llh + off * Rl, ctx->s_llh, (size_t)n * Rl * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
         if (io->jafs) CK(cudaMemcpyAsync(io->jafs + off * 7, ctx->s_jafs, (size_t)n * 7 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1267,61 +1355,87 @@ int misti_eval_batch(misti_ctx* ctx, int32_t B, int32_t P, const double* params,
         if (io->status) CK(cudaMemcpyAsync(io->status + off, ctx->d_status, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         if (io->nfev) CK(cudaMemcpyAsync(io->nfev + off, ctx->d_nfev, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         if (io->terms) CK(cudaMemcpyAsync(io->terms + off, ctx->s_terms, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        if (io->solve_trace)
+            CK(cudaMemcpyAsync(io->solve_trace + off * 2 * numT_max, ctx->s_trace, (size_t)n * 2 * numT_max * sizeof(int),
+                               cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
     }
     return 0;
 }
 
-int misti_nelder_mead(misti_ctx* ctx, int32_t S, int32_t N, const double* x0, const int32_t* model_ids, const int32_t* row_ids,
-                      uint32_t flags, double mixture_th, double xatol, double fatol, int64_t maxiter, int64_t maxfev,
-                      double* x, double* fun, int64_t* nit, int64_t* nfev, int32_t* status, int64_t* info) {
+int misti_fit(misti_ctx* ctx, int32_t S, int32_t N, const double* x0, const int32_t* model_ids, const int32_t* row_ids,
+              uint32_t flags, double mixture_th, const misti_fit_opts* opts, misti_fit_result* res) {
     if (!ctx) return MISTI_E_ARG;
-    if (S < 0 || N < 1 || N > MISTI_MAX_PARAMS || !x0 || !model_ids || !x || !fun || !nit || !nfev || !status)
-        return fail(ctx, MISTI_E_ARG, "misti_nelder_mead: bad arguments");
-    if (info) info[0] = info[1] = info[2] = 0;
+    if (S < 0 || N < 1 || N > MISTI_MAX_PARAMS || !x0 || !model_ids || !opts || !res || !res->x || !res->fun || !res->nit ||
+        !res->nfev || !res->status)
+        return fail(ctx, MISTI_E_ARG, "misti_fit: bad arguments");
+    res->rounds = res->points = 0;
+    res->graph = 0;
     if (S == 0) return 0;
-    if (ctx->R < 1) return fail(ctx, MISTI_E_ARG, "misti_nelder_mead: no data rows (misti_set_data)");
+    if (ctx->R < 1) return fail(ctx, MISTI_E_ARG, "misti_fit: no data rows (misti_set_data)");
+    const bool walkers = opts->niter >= 0;
+    if (walkers && (!opts->rng_state || opts->interval < 1 || !(opts->stepwise_factor > 0)))
+        return fail(ctx, MISTI_E_ARG, "misti_fit: basin-hopping needs rng_state, interval >= 1 and a positive stepwise_factor");
     const int n_models = (int)ctx->h_models.size();
     for (int s = 0; s < S; ++s) {
-        if (model_ids[s] < 0 || model_ids[s] >= n_models) return fail(ctx, MISTI_E_ARG, "misti_nelder_mead: unknown model id");
-        if (ctx->h_models[model_ids[s]].n_params > N) return fail(ctx, MISTI_E_ARG, "misti_nelder_mead: incorrect number of parameters");
-        if (row_ids && (row_ids[s] < 0 || row_ids[s] >= ctx->R)) return fail(ctx, MISTI_E_ARG, "misti_nelder_mead: unknown data row");
+        if (model_ids[s] < 0 || model_ids[s] >= n_models) return fail(ctx, MISTI_E_ARG, "misti_fit: unknown model id");
+        if (ctx->h_models[model_ids[s]].n_params > N) return fail(ctx, MISTI_E_ARG, "misti_fit: incorrect number of parameters");
+        if (row_ids && (row_ids[s] < 0 || row_ids[s] >= ctx->R)) return fail(ctx, MISTI_E_ARG, "misti_fit: unknown data row");
     }
     CK(cudaSetDevice(ctx->device));
     int rc;
     if ((rc = sync_tables(ctx))) return rc;
     misti::NmConfig cfg;
     cfg.N = N;
-    // two iterations per round (look-ahead) while a round stays in the flat part of the latency curve of one evaluation
-    const bool look_fits = N <= misti::kNmLookaheadMaxN && (long)S * misti::nm_slots(N, true) <= kCoopMaxItems;
-    cfg.lookahead = ctx->nm_lookahead < 0 ? look_fits : (ctx->nm_lookahead != 0 && N <= misti::kNmLookaheadMaxN);
-    cfg.slots = misti::nm_slots(N, cfg.lookahead != 0);
-    cfg.xatol = xatol; cfg.fatol = fatol;
-    cfg.maxiter = maxiter < 0 ? LLONG_MAX : maxiter;
-    cfg.maxfev = maxfev < 0 ? LLONG_MAX : maxfev;
-    const long B = (long)S * cfg.slots;
-    if (B > ctx->max_chunk) return fail(ctx, MISTI_E_ARG, "misti_nelder_mead: too many simplices for one call");
+    // look-ahead is decided per round ON the device (few running simplices); the knob MISTI_NM_LOOKAHEAD = 0 forbids it
+    cfg.lookahead = (ctx->nm_lookahead != 0 && N <= misti::kNmLookaheadMaxN) ? 1 : 0;
+    cfg.slots = misti::nm_slots(N, false);
+    cfg.xatol = opts->xatol; cfg.fatol = opts->fatol;
+    cfg.maxiter = opts->maxiter < 0 ? LLONG_MAX : opts->maxiter;
+    cfg.maxfev = opts->maxfev < 0 ? LLONG_MAX : opts->maxfev;
+    misti::BhConfig bh;
+    bh.niter = walkers ? opts->niter : -1;
+    bh.interval = walkers ? opts->interval : 1;
+    bh.beta = opts->T != 0 ? 1.0 / opts->T : misti::kInf;
+    bh.target = opts->target_accept_rate; bh.factor = opts->stepwise_factor; bh.stepsize0 = opts->stepsize;
+    // capacity of a round: every simplex without look-ahead, or the look-ahead budget
+    const int look_max = kCoopMaxItems;
+    long cap = (long)S * misti::nm_slots(N, false);
+    if (cfg.lookahead && cap < look_max) cap = look_max;
+    if (cap > ctx->max_chunk) return fail(ctx, MISTI_E_ARG, "misti_fit: too many simplices for one call");
+    const int B = (int)cap;
     // one block of device memory, carved up (8-byte items first)
     const size_t n_sim = (size_t)S * (N + 1) * N, n_fsim = (size_t)S * (N + 1);
     size_t off = 0;
     auto carve = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
     const size_t o_sim = carve(n_sim * 8), o_fsim = carve(n_fsim * 8), o_it = carve((size_t)S * 8), o_fc = carve((size_t)S * 8),
-                 o_par = carve((size_t)B * N * 8), o_llh = carve((size_t)B * 8), o_st = carve((size_t)S * 4), o_ph = carve((size_t)S * 4),
-                 o_mod = carve((size_t)S * 4), o_row = carve((size_t)S * 4), o_bm = carve((size_t)B * 4), o_br = carve((size_t)B * 4),
-                 o_cnt = carve((kNmRing + 1) * 4);  // the ring and, behind it, the round counter
+                 o_par = carve((size_t)B * N * 8), o_llh = carve((size_t)B * 8),
+                 o_bx = carve((size_t)S * N * 8), o_bbx = carve((size_t)S * N * 8), o_be = carve((size_t)S * 8),
+                 o_bbf = carve((size_t)S * 8), o_bst = carve((size_t)S * 8), o_bnf = carve((size_t)S * 8), o_bfl = carve((size_t)S * 8),
+                 o_bns = carve((size_t)S * 8), o_bna = carve((size_t)S * 8), o_bhp = carve((size_t)S * 8), o_rng = carve((size_t)S * 32),
+                 o_st = carve((size_t)S * 4), o_ph = carve((size_t)S * 4), o_mod = carve((size_t)S * 4), o_row = carve((size_t)S * 4),
+                 o_first = carve((size_t)S * 4), o_look = carve((size_t)S * 4), o_bok = carve((size_t)S * 4), o_bbok = carve((size_t)S * 4),
+                 o_bdn = carve((size_t)S * 4), o_bm = carve((size_t)B * 4), o_br = carve((size_t)B * 4), o_cnt = carve(FC_N * 4);
     if ((rc = ensure(ctx, &ctx->d_nm, &ctx->d_nm_cap, off))) return rc;
-    if (!ctx->h_nm_counts) CK(cudaMallocHost((void**)&ctx->h_nm_counts, kNmRing * sizeof(int)));
+    if (!ctx->h_nm_counts) CK(cudaMallocHost((void**)&ctx->h_nm_counts, 4 * FC_N * sizeof(int)));
     for (int i = 0; i < 4; ++i)
         if (!ctx->nm_ev[i]) CK(cudaEventCreateWithFlags(&ctx->nm_ev[i], cudaEventDisableTiming));
     unsigned char* base = ctx->d_nm;
-    NmState st;
+    FitState st;
     st.sim = (double*)(base + o_sim); st.fsim = (double*)(base + o_fsim);
     st.iters = (long long*)(base + o_it); st.fcalls = (long long*)(base + o_fc);
     st.status = (int*)(base + o_st); st.phase = (int*)(base + o_ph);
     int* d_mod = (int*)(base + o_mod); int* d_row = (int*)(base + o_row);
     st.model = d_mod; st.row = d_row;
+    st.first = (int*)(base + o_first); st.look = (int*)(base + o_look);
+    st.bh_x = (double*)(base + o_bx); st.bh_best_x = (double*)(base + o_bbx); st.bh_energy = (double*)(base + o_be);
+    st.bh_best_f = (double*)(base + o_bbf); st.bh_step = (double*)(base + o_bst);
+    st.bh_ok = (int*)(base + o_bok); st.bh_best_ok = (int*)(base + o_bbok); st.bh_done = (int*)(base + o_bdn);
+    st.bh_nfev = (long long*)(base + o_bnf); st.bh_fail = (long long*)(base + o_bfl); st.bh_nstep = (long long*)(base + o_bns);
+    st.bh_naccept = (long long*)(base + o_bna); st.bh_hop = (long long*)(base + o_bhp);
+    st.rng = (misti::Pcg64*)(base + o_rng);
     double* d_par = (double*)(base + o_par); double* d_llh = (double*)(base + o_llh);
-    int* d_bm = (int*)(base + o_bm); int* d_br = (int*)(base + o_br); int* d_cnt = (int*)(base + o_cnt);
+    int* d_bm = (int*)(base + o_bm); int* d_br = (int*)(base + o_br); int* d_fc = (int*)(base + o_cnt);
     cudaStream_t sm = ctx->stream;
     // initial state: vertex 0 = x0, everything else zero (phase NM_INIT = 0, status -1 set below)
     CK(cudaMemsetAsync(base, 0, off, sm));
@@ -1329,45 +1443,62 @@ int misti_nelder_mead(misti_ctx* ctx, int32_t S, int32_t N, const double* x0, co
     CK(cudaMemsetAsync(st.status, 0xff, (size_t)S * 4, sm));
     CK(cudaMemcpyAsync(d_mod, model_ids, (size_t)S * 4, cudaMemcpyHostToDevice, sm));
     if (row_ids) CK(cudaMemcpyAsync(d_row, row_ids, (size_t)S * 4, cudaMemcpyHostToDevice, sm));
+    if (walkers) {
+        static_assert(sizeof(misti::Pcg64) == 32, "four 64-bit words per generator");
+        CK(cudaMemcpyAsync(st.rng, opts->rng_state, (size_t)S * 32, cudaMemcpyHostToDevice, sm));
+        std::vector<double> steps((size_t)S, opts->stepsize);
+        CK(cudaMemcpyAsync(st.bh_step, steps.data(), (size_t)S * 8, cudaMemcpyHostToDevice, sm));
+        CK(cudaStreamSynchronize(sm));  // `steps` goes out of scope
+    }
     const unsigned eflags = (flags | MISTI_FLAG_DEVICE_PTRS);
     const int tb = 64, gb = (S + tb - 1) / tb;
-    int* d_round = d_cnt + kNmRing;
     if ((rc = ensure_batch(ctx, (size_t)B))) return rc;  // no allocation inside a round (a round may be captured)
-    // one round: propose, count back to the host, evaluate (three kernels), apply
+    // cpfit post-split pass: in the JSFS kernel's lanes or in the correction chain -- decided ONCE per fit (by the size of its
+    // first round), so that every point of a fit is evaluated by the same variant (they differ in the order of summation)
+    const int defer = ctx->defer_post < 0 ? ((long)S * misti::nm_slots(N, false) <= kDeferPostMaxItems ? 1 : 0) : (ctx->defer_post != 0);
+    // one round: propose (packs the points behind the device-side counter), evaluate, apply
     auto round_body = [&]() -> int {
-        misti_nm_propose_kernel<<<gb, tb, 0, sm>>>(S, cfg, st, d_par, d_bm, d_br, d_cnt, d_round);
+        misti_fit_propose_kernel<<<gb, tb, 0, sm>>>(S, cfg, bh, st, d_par, d_bm, d_br, d_fc, look_max, B);
         CK(cudaGetLastError());
-        CK(cudaMemcpyAsync(ctx->h_nm_counts, d_cnt, kNmRing * sizeof(int), cudaMemcpyDeviceToHost, sm));
-        int rc2 = eval_chunk(ctx, (int)B, N, d_par, d_bm, -1, eflags, mixture_th, nullptr, d_llh, nullptr, nullptr, nullptr, nullptr,
-                             nullptr, nullptr, nullptr, d_br);
+        int rc2 = eval_chunk(ctx, B, N, d_par, d_bm, -1, eflags, mixture_th, nullptr, d_llh, nullptr, nullptr, nullptr, nullptr,
+                             nullptr, nullptr, nullptr, d_br, nullptr, d_fc + FC_ITEMS, defer);
         if (rc2) return rc2;
-        misti_nm_apply_kernel<<<gb, tb, 0, sm>>>(S, cfg, st, d_par, d_llh, d_cnt, d_round);
+        misti_fit_apply_kernel<<<gb, tb, 0, sm>>>(S, cfg, st, d_par, d_llh, d_fc, nullptr);
         CK(cudaGetLastError());
         return 0;
     };
-    // The round is the same sequence of launches with the same arguments every time: it is captured once as a CUDA graph
-    // and replayed (one launch call per round instead of a dozen stream operations); the graph is kept for the next fit
-    // as long as nothing it refers to has moved.
+    // A graph = kRoundsPerGraph rounds and one copy of the counters to pinned memory; kept for the next fit as long as nothing
+    // it refers to has moved.
+    const int kRoundsPerGraph = ctx->nm_rounds_per_graph;
     cudaGraphExec_t exec = nullptr;
+    const int64_t launches_before = ctx->launches;
+    int launches_per_round = 0;
     if (ctx->nm_use_graph) {
-        unsigned long long mt_bits, xa_bits, fa_bits;
-        std::memcpy(&mt_bits, &mixture_th, 8); std::memcpy(&xa_bits, &xatol, 8); std::memcpy(&fa_bits, &fatol, 8);
+        unsigned long long mt_bits, xa_bits, fa_bits, be_bits, ta_bits, fc_bits;
+        std::memcpy(&mt_bits, &mixture_th, 8); std::memcpy(&xa_bits, &cfg.xatol, 8); std::memcpy(&fa_bits, &cfg.fatol, 8);
+        std::memcpy(&be_bits, &bh.beta, 8); std::memcpy(&ta_bits, &bh.target, 8); std::memcpy(&fc_bits, &bh.factor, 8);
         const std::vector<unsigned long long> key = {ctx->generation, (unsigned long long)S, (unsigned long long)N,
-                                                     (unsigned long long)cfg.slots, (unsigned long long)cfg.lookahead, xa_bits, fa_bits,
+                                                     (unsigned long long)cfg.lookahead, xa_bits, fa_bits,
                                                      (unsigned long long)cfg.maxiter, (unsigned long long)cfg.maxfev,
-                                                     (unsigned long long)flags, mt_bits, (unsigned long long)(size_t)sm};
+                                                     (unsigned long long)flags, mt_bits, (unsigned long long)(size_t)sm,
+                                                     (unsigned long long)(long long)bh.niter, (unsigned long long)bh.interval, be_bits,
+                                                     ta_bits, fc_bits, (unsigned long long)defer, (unsigned long long)kRoundsPerGraph};
         if (ctx->nm_graph && key == ctx->nm_graph_key) {
             exec = ctx->nm_graph;
+            launches_per_round = ctx->nm_graph_launches;
         } else {
             if (ctx->nm_graph) { cudaGraphExecDestroy(ctx->nm_graph); ctx->nm_graph = nullptr; }
-            const int64_t launches_before = ctx->launches;
             if (cudaStreamBeginCapture(sm, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
-                const int rcb = round_body();
+                int rcb = 0;
+                for (int i = 0; i < kRoundsPerGraph && rcb == 0; ++i) rcb = round_body();
+                if (rcb == 0 && cudaMemcpyAsync(ctx->h_nm_counts, d_fc, FC_N * sizeof(int), cudaMemcpyDeviceToHost, sm) != cudaSuccess) rcb = MISTI_E_CUDA;
                 cudaGraph_t graph = nullptr;
                 const cudaError_t e = cudaStreamEndCapture(sm, &graph);
                 if (rcb == 0 && e == cudaSuccess && graph && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess) {
                     ctx->nm_graph = exec;
                     ctx->nm_graph_key = key;
+                    launches_per_round = (int)((ctx->launches - launches_before) / kRoundsPerGraph) + 2;
+                    ctx->nm_graph_launches = launches_per_round;
                 } else {
                     exec = nullptr;
                     cudaGetLastError();  // clear the capture error: the rounds are launched directly instead
@@ -1377,37 +1508,76 @@ int misti_nelder_mead(misti_ctx* ctx, int32_t S, int32_t N, const double* x0, co
             ctx->launches = launches_before;  // nothing ran during the capture
         }
     }
+    // The host keeps two batches of rounds in flight and looks at the counters of the batch before: a last round that
+    // packed nothing ends the fit (the rounds queued behind it are empty and cost microseconds).
+    volatile int* hc = ctx->h_nm_counts;
     int64_t rounds = 0, points = 0;
-    // The host runs at most two rounds ahead of the device: before round r is queued, the count of round r - 2 is in;
-    // a round in which no simplex submitted a point ends the fit (the rounds queued behind it are empty and cost microseconds).
-    for (long r = 0;; ++r) {
-        if (r >= 2) {
-            CK(cudaEventSynchronize(ctx->nm_ev[(r - 2) & 3]));
-            const int n = ctx->h_nm_counts[(r - 2) % kNmRing];
-            if (n == 0) break;
-            points += n;
-            ++rounds;
+    for (long g = 0;; ++g) {
+        if (g >= 2) {
+            CK(cudaEventSynchronize(ctx->nm_ev[(g - 2) & 3]));
+            // the copy of batch g - 2 may have been overwritten by that of batch g - 1 already: the counters only grow, and
+            // "nothing packed in the last round" stays true once every simplex has ended
+            rounds = hc[FC_ROUNDS_USED];
+            points = ((int64_t)(unsigned)hc[FC_POINTS_HI] << 32) | (unsigned)hc[FC_POINTS_LO];
+            if (hc[FC_ROUND] > 0 && hc[FC_LAST] == 0) break;
         }
         if (exec) {
             CK(cudaGraphLaunch(exec, sm));
-            ctx->launches += 5;
+            ctx->launches += (int64_t)launches_per_round * kRoundsPerGraph;
         } else {
-            if ((rc = round_body())) return rc;
-            ctx->launches += 2;
+            for (int i = 0; i < kRoundsPerGraph; ++i) {
+                if ((rc = round_body())) return rc;
+                ctx->launches += 2;
+            }
+            CK(cudaMemcpyAsync(ctx->h_nm_counts, d_fc, FC_N * sizeof(int), cudaMemcpyDeviceToHost, sm));
         }
-        CK(cudaEventRecord(ctx->nm_ev[r & 3], sm));
+        CK(cudaEventRecord(ctx->nm_ev[g & 3], sm));
     }
-    ctx->ev_valid = false;  // the timing events of the evaluation were recorded inside the rounds
-    // results: best vertex and value (the simplices are sorted), counts
-    CK(cudaMemcpy2DAsync(x, (size_t)N * 8, st.sim, (size_t)(N + 1) * N * 8, (size_t)N * 8, S, cudaMemcpyDeviceToHost, sm));
-    CK(cudaMemcpy2DAsync(fun, 8, st.fsim, (size_t)(N + 1) * 8, 8, S, cudaMemcpyDeviceToHost, sm));
-    static_assert(sizeof(long long) == sizeof(int64_t), "64-bit counters");
-    CK(cudaMemcpyAsync(nit, st.iters, (size_t)S * 8, cudaMemcpyDeviceToHost, sm));
-    CK(cudaMemcpyAsync(nfev, st.fcalls, (size_t)S * 8, cudaMemcpyDeviceToHost, sm));
-    CK(cudaMemcpyAsync(status, st.status, (size_t)S * 4, cudaMemcpyDeviceToHost, sm));
     CK(cudaStreamSynchronize(sm));
-    if (info) { info[0] = rounds; info[1] = points; info[2] = exec ? 1 : 0; }
+    rounds = hc[FC_ROUNDS_USED];
+    points = ((int64_t)(unsigned)hc[FC_POINTS_HI] << 32) | (unsigned)hc[FC_POINTS_LO];
+    ctx->ev_valid = false;  // the timing events of the evaluation were recorded inside the rounds
+    static_assert(sizeof(long long) == sizeof(int64_t), "64-bit counters");
+    if (!walkers) {
+        // results: best vertex and value (the simplices are sorted), counts
+        CK(cudaMemcpy2DAsync(res->x, (size_t)N * 8, st.sim, (size_t)(N + 1) * N * 8, (size_t)N * 8, S, cudaMemcpyDeviceToHost, sm));
+        CK(cudaMemcpy2DAsync(res->fun, 8, st.fsim, (size_t)(N + 1) * 8, 8, S, cudaMemcpyDeviceToHost, sm));
+        CK(cudaMemcpyAsync(res->nit, st.iters, (size_t)S * 8, cudaMemcpyDeviceToHost, sm));
+        CK(cudaMemcpyAsync(res->nfev, st.fcalls, (size_t)S * 8, cudaMemcpyDeviceToHost, sm));
+        CK(cudaMemcpyAsync(res->status, st.status, (size_t)S * 4, cudaMemcpyDeviceToHost, sm));
+    } else {
+        // results: the best minimum every walker has seen (Storage), scipy's counts
+        CK(cudaMemcpyAsync(res->x, st.bh_best_x, (size_t)S * N * 8, cudaMemcpyDeviceToHost, sm));
+        CK(cudaMemcpyAsync(res->fun, st.bh_best_f, (size_t)S * 8, cudaMemcpyDeviceToHost, sm));
+        CK(cudaMemcpyAsync(res->nit, st.bh_hop, (size_t)S * 8, cudaMemcpyDeviceToHost, sm));
+        CK(cudaMemcpyAsync(res->nfev, st.bh_nfev, (size_t)S * 8, cudaMemcpyDeviceToHost, sm));
+        CK(cudaMemcpyAsync(res->status, st.bh_best_ok, (size_t)S * 4, cudaMemcpyDeviceToHost, sm));
+        if (res->accepted) CK(cudaMemcpyAsync(res->accepted, st.bh_naccept, (size_t)S * 8, cudaMemcpyDeviceToHost, sm));
+        if (res->failures) CK(cudaMemcpyAsync(res->failures, st.bh_fail, (size_t)S * 8, cudaMemcpyDeviceToHost, sm));
+    }
+    CK(cudaStreamSynchronize(sm));
+    if (walkers)
+        for (int s = 0; s < S; ++s) {
+            res->status[s] = res->status[s] ? 0 : 1;  // 0 = the best minimum came from a converged local search
+            res->nit[s] -= 1;                          // hops taken after the initial minimisation
+        }
+    res->rounds = rounds; res->points = points; res->graph = exec ? 1 : 0;
     return 0;
+}
+
+int misti_nelder_mead(misti_ctx* ctx, int32_t S, int32_t N, const double* x0, const int32_t* model_ids, const int32_t* row_ids,
+                      uint32_t flags, double mixture_th, double xatol, double fatol, int64_t maxiter, int64_t maxfev,
+                      double* x, double* fun, int64_t* nit, int64_t* nfev, int32_t* status, int64_t* info) {
+    if (info) info[0] = info[1] = info[2] = 0;
+    misti_fit_opts o;
+    std::memset(&o, 0, sizeof(o));
+    o.xatol = xatol; o.fatol = fatol; o.maxiter = maxiter; o.maxfev = maxfev; o.niter = -1;
+    misti_fit_result r;
+    std::memset(&r, 0, sizeof(r));
+    r.x = x; r.fun = fun; r.nit = nit; r.nfev = nfev; r.status = status;
+    const int rc = misti_fit(ctx, S, N, x0, model_ids, row_ids, flags, mixture_th, &o, &r);
+    if (info) { info[0] = r.rounds; info[1] = r.points; info[2] = r.graph; }
+    return rc;
 }
 
 int misti_score_spectra(misti_ctx* ctx, int32_t B, const double* spectra, double* llh) {

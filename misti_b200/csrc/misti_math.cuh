@@ -718,7 +718,9 @@ struct IntervalState {
     double mu[2];     // migration rates
     double P0[2][3];  // per genome: P(both lineages in deme 0 / deme 1 / one each), not yet coalesced
     double nch[2];    // cpfit target of the interval, exp(-lh T) (sum of P0): the same in every residual evaluation
+    int status;       // scipy's termination status of the interval's least-squares solve (kNoSolve: closed form, no solver)
 };
+constexpr int kNoSolve = -9;
 
 MISTI_HD inline void corr_matrix(const double* l, const double* mu, double T, double* M) {
     // CorrectLambda.SetMatrix (CorrectLambda.py:55-56), times T
@@ -849,6 +851,7 @@ MISTI_HD inline bool solve_interval_mig(IntervalState* st, bool cpfit, double* l
     if (cpfit) { ResidualProb fun; fun.st = &u; status = least_squares_trf<2, COOP>(fun, x, false, -kInf, &nf); }
     else { ResidualTime fun; fun.st = &u; status = least_squares_trf<2, COOP>(fun, x, false, -kInf, &nf); }
     *nfev += nf;
+    st->status = status;
     if (status < 0) return false;
     // un-stretch exactly as the reference does: mu*T/T, x/T
     const double mu_back[2] = {u.mu[0] / T, u.mu[1] / T};
@@ -872,6 +875,7 @@ MISTI_HD inline bool solve_interval(IntervalState* st, bool cpfit, double mixtur
     const double T = st->T;
     double (*P0)[3] = st->P0;
     const double s0 = (P0[0][0] + P0[0][1]) + P0[0][2], s1 = (P0[1][0] + P0[1][1]) + P0[1][2];
+    st->status = kNoSolve;
     if (mixtureTH > 0) {  // sqrt(mix) >= 0: the test can only fire for a positive threshold
         double mix = 0;
         for (int i = 0; i < 3; ++i) { const double d = P0[0][i] / s0 - P0[1][i] / s1; mix += d * d; }
@@ -903,6 +907,7 @@ MISTI_HD inline bool solve_interval(IntervalState* st, bool cpfit, double mixtur
         int nf = 0;
         const int status = least_squares_trf<2, COOP>(fun, x, true, lb, &nf);
         *nfev += nf;
+        st->status = status;
         if (status < 0) return false;
         lc[0] = x[0]; lc[1] = x[1];
         const double e0 = exp(-lc[0] * T), e1 = exp(-lc[1] * T);
@@ -914,7 +919,7 @@ MISTI_HD inline bool solve_interval(IntervalState* st, bool cpfit, double mixtur
 
 // FitSinglePop (CorrectLambda.py:88-92) with P0 = [[exp(nc0),0,0],[exp(nc1),0,0]]
 template <bool COOP = false>
-MISTI_HD inline bool fit_single_pop(const double* lh, double T, double nc0, double nc1, double* lam, int* nfev) {
+MISTI_HD inline bool fit_single_pop(const double* lh, double T, double nc0, double nc1, double* lam, int* nfev, int* status_out = nullptr) {
     double p0 = exp(nc0), p1 = exp(nc1);
     const double sp = p0 + p1;
     p0 = p0 / sp; p1 = p1 / sp;
@@ -926,6 +931,7 @@ MISTI_HD inline bool fit_single_pop(const double* lh, double T, double nc0, doub
     int nf = 0;
     const int status = least_squares_trf<1, COOP>(fun, x, true, lb, &nf);
     *nfev += nf;
+    if (status_out) *status_out = status;
     if (status < 0) return false;
     *lam = x[0];
     return true;

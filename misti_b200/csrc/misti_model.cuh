@@ -164,12 +164,16 @@ inline void post_split_table(int numT, int splitT, const double* times, const do
 // nc_out (nullable): in cpfit mode do NOT run the post-split pass here but return nc0, nc1 (and *cpost_done = true): the
 // caller has the pass done elsewhere (post_split_cpfit_group in the JSFS kernel; the post-split rates themselves are
 // then only computed on request, post_split_cpfit_rate).
+// trace (nullable): [numT][2] per interval the evaluations (scipy's nfev) and the termination status of its least-squares
+// solve, kNoSolve where the interval has a closed form -- the iterate-level record the golden vectors of
+// tests/golden/solver.json pin (CorrectLambda.py:85, 260, 303, 305).
 // COOP (device only): four lanes run the item together, see eval_fj in misti_math.cuh.
 template <bool COOP = false>
 MISTI_HD inline int correct_lambdas_item(const ModelDesc& md, const double* times, const double* lh, const double* params,
                                          unsigned flags, double mixtureTH, double* lc, int pitch, long stride, double* Pr,
                                          int* nfev_out, const double* gaux = nullptr, double* cpost = nullptr,
-                                         bool* cpost_done = nullptr, const unsigned* cls = nullptr, double* nc_out = nullptr) {
+                                         bool* cpost_done = nullptr, const unsigned* cls = nullptr, double* nc_out = nullptr,
+                                         int* trace = nullptr) {
     if (cpost_done) *cpost_done = false;
     const bool correct = flags & MISTI_FLAG_CORRECT, cpfit = flags & MISTI_FLAG_CPFIT;
     int nfev = 0;
@@ -223,7 +227,9 @@ MISTI_HD inline int correct_lambdas_item(const ModelDesc& md, const double* time
             st.lh[0] = lh[2 * t]; st.lh[1] = lh[2 * t + 1];
             st.T = times[t];
             st.mu[0] = mi_t[0]; st.mu[1] = mi_t[1];
+            const int nfev_before = nfev;
             const bool ok = solve_interval<COOP>(&st, cpfit, mixtureTH, l, &nfev, gaux ? gaux + kGridAux * t : nullptr);
+            if (trace) { trace[2 * t] = nfev - nfev_before; trace[2 * t + 1] = st.status; }
             if (!ok) {
                 lc[(pitch * t) * stride] = l[0];
                 lc[(pitch * t + 1) * stride] = l[1];
@@ -263,7 +269,11 @@ MISTI_HD inline int correct_lambdas_item(const ModelDesc& md, const double* time
             const double T = times[t];
             if (T == 0) { lc[(pitch * t) * stride] = 1; lc[(pitch * t + 1) * stride] = 1; continue; }
             double lam;
-            if (!fit_single_pop<COOP>(lh + 2 * t, T, nc0, nc1, &lam, &nfev)) { *nfev_out = nfev; return MISTI_NONFINITE; }
+            const int nfev_before = nfev;
+            int fit_status = kNoSolve;
+            const bool ok = fit_single_pop<COOP>(lh + 2 * t, T, nc0, nc1, &lam, &nfev, &fit_status);
+            if (trace) { trace[2 * t] = nfev - nfev_before; trace[2 * t + 1] = fit_status; }
+            if (!ok) { *nfev_out = nfev; return MISTI_NONFINITE; }
             lc[(pitch * t) * stride] = lam;
             lc[(pitch * t + 1) * stride] = lam;
             nc0 += -T * lam;

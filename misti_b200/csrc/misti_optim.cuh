@@ -236,4 +236,101 @@ MISTI_HD inline void nm_apply(const NmConfig& c, double* sim, double* fsim, long
     nm_step(c, sim, fsim, iters, fcalls, phase, pts + (long)(4 + 4 * q) * N, fv_in + 4 + 4 * q, negate, &rank);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Basin-hopping walkers (scipy/optimize/_basinhopping.py as MigrationInference.Solve(globalOpt=True) calls it,
+// MigrationInference.py:724: niter = 100, T = 0.5, stepsize = 0.5, local search = Nelder-Mead with scipy's defaults).
+// A walker is a Nelder-Mead simplex plus the state below; when its local search ends, bh_advance takes the Metropolis
+// decision, updates the best-so-far storage and starts the next local search from a displaced point -- one walker at a
+// time, with no barrier between the hops of different walkers (misti_b200/optim.py:basinhopping_batch is the same logic
+// in lock step on the host; both reproduce scipy.optimize.basinhopping(..., rng=seed) for a single walker).
+// Random numbers: numpy's Generator(PCG64) continued from the state the host seeded (numpy.random.default_rng(seed)),
+// so the device draws the very numbers scipy would: uniform(-stepsize, stepsize, N) per displacement, uniform() per
+// Metropolis test.
+// ------------------------------------------------------------------------------------------------
+struct Pcg64 { unsigned long long s_hi, s_lo, inc_hi, inc_lo; };
+
+MISTI_HD inline unsigned long long mul64hi(unsigned long long a, unsigned long long b) {
+#if defined(__CUDA_ARCH__)
+    return __umul64hi(a, b);
+#else
+    return (unsigned long long)(((unsigned __int128)a * b) >> 64);
+#endif
+}
+
+// numpy/random/src/pcg64: state <- state * 0x2360ED051FC65DA44385DF649FCCF645 + inc (mod 2^128), output XSL-RR of the NEW state
+MISTI_HD inline unsigned long long pcg64_next(Pcg64& r) {
+    const unsigned long long m_hi = 0x2360ED051FC65DA4ull, m_lo = 0x4385DF649FCCF645ull;
+    unsigned long long lo = r.s_lo * m_lo;
+    unsigned long long hi = mul64hi(r.s_lo, m_lo) + r.s_hi * m_lo + r.s_lo * m_hi;
+    const unsigned long long lo2 = lo + r.inc_lo;
+    hi += r.inc_hi + (lo2 < lo ? 1ull : 0ull);
+    r.s_lo = lo2; r.s_hi = hi;
+    const unsigned long long x = hi ^ lo2;
+    const unsigned rot = (unsigned)(hi >> 58);
+    return (x >> rot) | (x << ((64u - rot) & 63u));
+}
+MISTI_HD inline double pcg64_double(Pcg64& r) { return (double)(pcg64_next(r) >> 11) * (1.0 / 9007199254740992.0); }
+// Generator.uniform(low, high): low + (high - low) * next_double, every operation rounded on its own
+MISTI_HD inline double pcg64_uniform(Pcg64& r, double low, double high) {
+    return nm_add(low, nm_mul(nm_sub(high, low), pcg64_double(r)));
+}
+
+struct BhConfig {
+    int niter;         // hops after the first local search; < 0 = plain Nelder-Mead fits (no walker state)
+    int interval;      // the step size adapts every `interval` hops
+    double beta;       // 1 / T (infinity for T = 0)
+    double target, factor, stepsize0;
+};
+
+// one walker's state, as pointers into the structure-of-arrays block of the fit
+struct BhWalker {
+    double *x, *best_x;                 // [N]
+    double *energy, *best_f, *step;     // scalars
+    int *ok, *best_ok, *done;
+    long long *nfev, *failures, *nstep, *naccept, *hop;
+    Pcg64* rng;
+};
+
+// The walker's local search has ended (phase NM_DONE; sim / fsim sorted, status set).  Returns true when the walker goes on
+// with another local search (sim[0] = the displaced start, phase NM_INIT), false when it has done its hops.
+MISTI_HD inline bool bh_advance(const BhConfig& c, int N, const BhWalker& w, double* sim, double* fsim, long long* iters,
+                                long long* fcalls, int* status, int* phase) {
+    const double fn = fsim[0];
+    const bool okn = *status == 0;
+    if (*w.hop == 0) {  // the initial minimisation (_basinhopping.py: BasinHoppingRunner.__init__)
+        for (int k = 0; k < N; ++k) { w.x[k] = sim[k]; w.best_x[k] = sim[k]; }
+        *w.energy = fn; *w.ok = okn;
+        *w.best_f = fn; *w.best_ok = okn;
+        *w.nfev = *fcalls;
+        *w.failures = okn ? 0 : 1;
+    } else {  // Metropolis.accept_reject (the random number is drawn whatever the outcome), Storage.update
+        *w.nfev += *fcalls;
+        *w.failures += okn ? 0 : 1;
+        const double prod = nm_mul(-nm_sub(fn, *w.energy), c.beta);
+        const double wgt = exp(prod < 0.0 ? prod : 0.0);  // Python's min(0, prod): 0 when prod is NaN (inf - inf)
+        const double u = pcg64_uniform(*w.rng, 0.0, 1.0);
+        if (wgt >= u && (okn || !*w.ok)) {
+            *w.naccept += 1;
+            *w.energy = fn; *w.ok = okn;
+            for (int k = 0; k < N; ++k) w.x[k] = sim[k];
+            if (okn && (fn < *w.best_f || !*w.best_ok)) {
+                *w.best_f = fn; *w.best_ok = okn;
+                for (int k = 0; k < N; ++k) w.best_x[k] = sim[k];
+            }
+        }
+    }
+    *w.hop += 1;
+    if (*w.hop > c.niter) { *w.done = 1; return false; }
+    // AdaptiveStepsize.take_step: count, adapt every `interval` steps, displace
+    *w.nstep += 1;
+    if (*w.nstep % c.interval == 0) {
+        const double rate = nm_div((double)*w.naccept, (double)*w.nstep);
+        *w.step = rate > c.target ? nm_div(*w.step, c.factor) : nm_mul(*w.step, c.factor);
+    }
+    for (int k = 0; k < N; ++k) sim[k] = nm_add(w.x[k], pcg64_uniform(*w.rng, -*w.step, *w.step));
+    for (int j = 0; j <= N; ++j) fsim[j] = 0.0;
+    *iters = 0; *fcalls = 0; *status = -1; *phase = NM_INIT;
+    return true;
+}
+
 }  // namespace misti

@@ -156,7 +156,7 @@ class Engine:
     def evaluate(self, params, model=0, model_ids=None, flags=_lib.FLAG_CORRECT, mixtureTH=0.0, lc_inject=None,
                  want=("jafs", "status"), buffers=None, row_ids=None):
         """Host-buffer evaluation.  params: [B, P] (or [B] / [] for P = 0).  Returns a dict with
-        'llh' [B, R] and the arrays named in `want` (jafs, jafs_raw, lc, pr, status, nfev, terms).
+        'llh' [B, R] and the arrays named in `want` (jafs, jafs_raw, lc, pr, status, nfev, terms, solve_trace).
         `buffers` may hold preallocated C-contiguous numpy arrays (e.g. views of pinned memory) to write into.
         With `row_ids` [B], item b is scored against data row row_ids[b] only and 'llh' is [B, 1]."""
         params = _as_f64(params)
@@ -193,9 +193,9 @@ class Engine:
             io.lc_inject = _ptr(inj)
         shapes = {"jafs": ((B, 7), np.float64), "jafs_raw": ((B, 7), np.float64), "lc": ((B, nT, 2), np.float64),
                   "pr": ((B, nT + 1, 3, 2), np.float64), "status": ((B,), np.int32), "nfev": ((B,), np.int32),
-                  "terms": ((B,), np.int32)}
+                  "terms": ((B,), np.int32), "solve_trace": ((B, nT, 2), np.int32)}
         field = {"jafs": "jafs", "jafs_raw": "jafs_raw", "lc": "lc_out", "pr": "pr_out", "status": "status", "nfev": "nfev",
-                 "terms": "terms"}
+                 "terms": "terms", "solve_trace": "solve_trace"}
         for name in want:
             shp, dt = shapes[name]
             out[name] = _buf(name, shp, dt)
@@ -250,6 +250,61 @@ class Engine:
             nfev.ctypes.data_as(i64p), status.ctypes.data_as(_lib.c_int32_p), info.ctypes.data_as(i64p)))
         return {"x": x, "fun": fun, "nit": nit, "nfev": nfev, "status": status.astype(np.int64), "success": status == 0,
                 "evaluations": int(info[1]), "launches": int(info[0]), "graph": bool(info[2])}
+
+    def basinhopping(self, x0, model_ids, row_ids=None, seeds=None, flags=_lib.FLAG_CORRECT, mixtureTH=0.0, niter=100, T=0.5,
+                     stepsize=0.5, interval=50, target_accept_rate=0.5, stepwise_factor=0.9, xatol=1e-4, fatol=1e-4,
+                     maxiter=None, maxfev=None):
+        """W basin-hopping walkers on the device (misti_fit), as MigrationInference.Solve(globalOpt=True) runs ONE
+        (MigrationInference.py:724: niter = 100, T = 0.5, stepsize = 0.5; local search = Nelder-Mead with scipy's defaults).
+        No walker waits for another: a walker whose local search has ended takes its Metropolis decision and starts the next
+        one in the following round of launches.  seeds: one seed (or numpy Generator) per walker -- walker w draws the numbers of
+        numpy.random.default_rng(seeds[w]), so a single walker reproduces scipy.optimize.basinhopping(..., rng=seeds[w]).
+        Returns the dict of misti_b200.optim.basinhopping_batch (x, fun, success, nfev, nit, accepted,
+        minimization_failures, evaluations, launches)."""
+        x0 = _as_f64(x0)
+        if x0.ndim == 1:
+            x0 = x0.reshape(1, -1)
+        W, N = x0.shape
+        mids = np.ascontiguousarray(model_ids, dtype=np.int32).reshape(-1)
+        rows = None if row_ids is None else np.ascontiguousarray(row_ids, dtype=np.int32).reshape(-1)
+        if mids.shape[0] != W or (rows is not None and rows.shape[0] != W):
+            raise ValueError("model_ids / row_ids must have one entry per walker")
+        seeds = list(range(W)) if seeds is None else list(seeds)
+        if len(seeds) != W:
+            raise ValueError("one seed per walker")
+        state = np.empty((W, 4), dtype=np.uint64)
+        mask = (1 << 64) - 1
+        for w, sd in enumerate(seeds):  # numpy seeds the generator (SeedSequence -> PCG64); the device continues its stream
+            g = sd if isinstance(sd, np.random.Generator) else np.random.default_rng(sd)
+            st = g.bit_generator.state
+            if st["bit_generator"] != "PCG64":
+                raise ValueError("walker generators must be PCG64 (numpy.random.default_rng)")
+            v, inc = int(st["state"]["state"]), int(st["state"]["inc"])
+            state[w] = (v >> 64, v & mask, inc >> 64, inc & mask)
+        if maxiter is None and maxfev is None:  # scipy's defaults (_optimize.py:751-768)
+            maxiter, maxfev = N * 200, N * 200
+        elif maxiter is None:
+            maxiter = N * 200 if maxfev == np.inf else np.inf
+        elif maxfev is None:
+            maxfev = N * 200 if maxiter == np.inf else np.inf
+        o = _lib.FitOpts()
+        o.xatol, o.fatol = float(xatol), float(fatol)
+        o.maxiter, o.maxfev = [(-1 if v == np.inf else int(v)) for v in (maxiter, maxfev)]
+        o.niter, o.interval, o.T, o.stepsize = int(niter), int(interval), float(T), float(stepsize)
+        o.target_accept_rate, o.stepwise_factor = float(target_accept_rate), float(stepwise_factor)
+        o.rng_state = state.ctypes.data_as(ctypes.c_void_p)
+        x, fun = np.empty((W, N)), np.empty(W)
+        nit, nfev, acc, fail = (np.zeros(W, dtype=np.int64) for _ in range(4))
+        status = np.zeros(W, dtype=np.int32)
+        r = _lib.FitResult()
+        r.x, r.fun, r.nit, r.nfev, r.status, r.accepted, r.failures = (_ptr(a) for a in (x, fun, nit, nfev, status, acc, fail))
+        flags = int(flags) & ~_lib.FLAG_DEVICE_PTRS
+        flags = (flags | _lib.FLAG_UNFOLDED) if self.unfolded else (flags & ~_lib.FLAG_UNFOLDED)
+        self._check(self._lib.misti_fit(self._h, W, N, x0.ctypes.data_as(_lib.c_double_p), mids.ctypes.data_as(_lib.c_int32_p),
+                                        rows.ctypes.data_as(_lib.c_int32_p) if rows is not None else None, flags, float(mixtureTH),
+                                        ctypes.byref(o), ctypes.byref(r)))
+        return {"x": x, "fun": fun, "success": status == 0, "nfev": nfev, "nit": nit, "accepted": acc,
+                "minimization_failures": fail, "evaluations": int(r.points), "launches": int(r.rounds), "graph": bool(r.graph)}
 
     def coalescent_rates(self, model, params, mu):
         """Forward map of model `model` (misti_coalescent_rates): its grid's rates taken as the true rates -> the rates PSMC

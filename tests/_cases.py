@@ -102,3 +102,27 @@ def random_jsfs_cases(n, seed=2026):
                     "flags": dict(trueEPS=True, cpfit=False, smooth=False, unfolded=bool(rng.integers(0, 2))),
                     "sfs": [float(1000 + 7 * 300)] + rng.integers(50, 600, 7).astype(float).tolist()})
     return out
+
+
+def check_solver_trace(gold, trace, lc_raw, name):
+    """Iterate-level parity of the correction chain with the reference's scipy.optimize.least_squares calls
+    (tests/golden/solver.json, CorrectLambda.py:85, 260, 303, 305).  trace[numT][2] = (nfev, status) per interval from the
+    device (misti_eval_io.solve_trace; (0, -9) = closed form, no solver); lc_raw (nullable) = per-interval solutions
+    BEFORE smoothing, in the reference's units.  Asserted: over the prefix of calls on which the reference determines its
+    own iterates (`stable_calls`: same counts and solutions to 1e-9 when every parameter moves by one ulp) the evaluation
+    counts and termination reasons are EQUAL, call by call; the first call past the prefix still starts from identical
+    inputs, so where the reference's three probe runs agree on its counts the port must too.  Returns the number of
+    calls compared and how many of ALL calls (also past the prefix, where the inputs have already drifted) have equal
+    counts -- reported by the callers."""
+    calls = gold["calls"]
+    got = [(int(n), int(s)) for n, s in trace if int(s) != -9]
+    stable = gold["stable_calls"]
+    assert len(got) >= min(stable + 1, len(calls)), (name, len(got), len(calls))
+    for k in range(stable):
+        assert got[k] == (calls[k]["nfev"], calls[k]["status"]), (name, "call", k, got[k], calls[k]["nfev"], calls[k]["status"])
+    checked = stable
+    if stable < len(calls) and calls[stable]["probe_agree"]:
+        assert got[stable] == (calls[stable]["nfev"], calls[stable]["status"]), (name, "first unstable call", stable, got[stable])
+        checked += 1
+    equal = sum(1 for k in range(min(len(got), len(calls))) if got[k] == (calls[k]["nfev"], calls[k]["status"]))
+    return checked, equal, len(calls)

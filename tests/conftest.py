@@ -38,6 +38,12 @@ def golden_fits():
 
 
 @pytest.fixture(scope="session")
+def golden_solver():
+    """per-call nfev / status / solution of the reference's least_squares calls (tests/golden/gen_solver_golden.py)"""
+    return {c["name"]: c for c in _load("solver.json")["cases"]}
+
+
+@pytest.fixture(scope="session")
 def golden_tables():
     return _load("tables.json")
 

@@ -18,7 +18,7 @@ int hs_inv3(const double* A, double* Ainv) { return misti::mat3_inv(A, Ainv) ? 1
 // bands: [n][5] = pop(0/1), start, end, value, opt index (-1 fixed); pulses: [n][4] = pop, time, value, opt index
 int hs_correct_lambdas(int numT, int splitT, int sampleDate, const double* times, const double* lh, int n_bands,
                        const double* bands, int n_pulses, const double* pulses, int n_params, const double* params,
-                       unsigned flags, double mixtureTH, double* lc, double* Pr, int* nfev) {
+                       unsigned flags, double mixtureTH, double* lc, double* Pr, int* nfev, int* trace /* [numT][2], nullable */) {
     misti::ModelDesc md;
     std::memset(&md, 0, sizeof(md));
     md.numT = numT; md.splitT = splitT; md.sampleDate = sampleDate;
@@ -36,8 +36,10 @@ int hs_correct_lambdas(int numT, int splitT, int sampleDate, const double* times
     for (int t = 0; t < numT; ++t) misti::grid_aux_row(lh + 2 * t, t < numT - 1 ? times[t] : 0.0, &gaux[(size_t)t * misti::kGridAux]);
     std::vector<unsigned> cls(numT);
     for (int t = 0; t < numT; ++t) cls[t] = misti::interval_class(md, t);
+    if (trace)
+        for (int t = 0; t < numT; ++t) { trace[2 * t] = 0; trace[2 * t + 1] = misti::kNoSolve; }
     return misti::correct_lambdas_item(md, times, lh, params, flags, mixtureTH, lc, 2, 1, Pr, nfev, gaux.data(), nullptr, nullptr,
-                                       cls.data());
+                                       cls.data(), nullptr, trace);
 }
 
 // CoalescentRates (forward map): lc[numT][2] true rates -> lh_out[numT][2], Pr[(splitT + 1)][3][2]
@@ -170,6 +172,30 @@ int hs_nm_propose(int N, double xatol, double fatol, long long maxiter, long lon
 void hs_nm_apply(int N, double xatol, double fatol, long long maxiter, long long maxfev, int lookahead, double* sim, double* fsim,
                  long long* iters, long long* fcalls, int* status, int* phase, const double* pts, const double* fv) {
     misti::nm_apply(hs_nm_cfg(N, xatol, fatol, maxiter, maxfev, lookahead), sim, fsim, iters, fcalls, status, phase, pts, fv, false);
+}
+
+// numpy's Generator(PCG64) continued from `state` (4 words, see misti_fit_opts.rng_state): n doubles of uniform(low, high)
+void hs_pcg64_uniform(unsigned long long* state, double low, double high, int n, double* out) {
+    misti::Pcg64 r = {state[0], state[1], state[2], state[3]};
+    for (int i = 0; i < n; ++i) out[i] = misti::pcg64_uniform(r, low, high);
+    state[0] = r.s_hi; state[1] = r.s_lo; state[2] = r.inc_hi; state[3] = r.inc_lo;
+}
+
+// one basin-hopping walker (misti_optim.cuh: bh_advance) around the Nelder-Mead step logic, driven from the test:
+// the walker's state lives in the arrays the test owns; returns 1 while the walker goes on
+int hs_bh_advance(int N, int niter, int interval, double T, double target, double factor, double* x, double* best_x, double* scal /* energy, best_f, step */,
+                  int* flags /* ok, best_ok, done */, long long* cnt /* nfev, failures, nstep, naccept, hop */, unsigned long long* rng,
+                  double* sim, double* fsim, long long* iters, long long* fcalls, int* status, int* phase) {
+    misti::BhConfig c;
+    c.niter = niter; c.interval = interval; c.beta = T != 0 ? 1.0 / T : misti::kInf; c.target = target; c.factor = factor; c.stepsize0 = scal[2];
+    misti::Pcg64 r = {rng[0], rng[1], rng[2], rng[3]};
+    misti::BhWalker w;
+    w.x = x; w.best_x = best_x; w.energy = scal; w.best_f = scal + 1; w.step = scal + 2;
+    w.ok = flags; w.best_ok = flags + 1; w.done = flags + 2;
+    w.nfev = cnt; w.failures = cnt + 1; w.nstep = cnt + 2; w.naccept = cnt + 3; w.hop = cnt + 4; w.rng = &r;
+    const bool go = misti::bh_advance(c, N, w, sim, fsim, iters, fcalls, status, phase);
+    rng[0] = r.s_hi; rng[1] = r.s_lo; rng[2] = r.inc_hi; rng[3] = r.inc_lo;
+    return go ? 1 : 0;
 }
 
 }  // extern "C"

@@ -33,7 +33,7 @@ def test_every_declared_symbol_is_exported_and_bound(lib):
         assert hasattr(lib, n), "libmisti_b200.so does not export %s" % n
         assert n in _lib.SIGNATURES, "ctypes binding misses %s" % n
     assert sorted(_lib.SIGNATURES) == names
-    assert lib.misti_abi_version() == 1
+    assert lib.misti_abi_version() == _lib.ABI_VERSION == 2
 
 
 def test_struct_layout_matches_c(tmp_path):

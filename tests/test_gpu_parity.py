@@ -61,18 +61,60 @@ def test_golden_jsfs_stage_with_injected_rates(engine, golden_datasets, golden_c
         assert out["terms"][0] > 0
 
 
-def test_unstable_cases_reported(engine, golden_datasets, golden_cases, capsys):
-    """default-mode correction with migration: not gated; the discrepancy is printed next to the
-    reference's own noise floor (1e-4 .. 1e-2 in llh)."""
+def test_solver_iterates_match_the_reference_call_by_call(engine, golden_datasets, golden_cases, golden_solver):
+    """Iterate-level parity of the correction chain ON THE DEVICE (misti_eval_io.solve_trace): every
+    scipy.optimize.least_squares call of the reference (CorrectLambda.py:85, 260, 303, 305; recorded per call by
+    tests/golden/gen_solver_golden.py) against the device's solve of the same interval -- evaluation count `nfev` and
+    termination status, call by call, bounded (n = 1, 2) and unbounded trust-region solves, default and cpfit residuals.
+    Wherever the reference determines its own iterates (the counts and solutions survive a one-ulp move of its parameters
+    and of its 3x3 expm results) the device's counts are the reference's, exactly; default mode WITH migration is
+    ulp-chaotic in the reference itself from the first interval with migration on, there the comparison
+    covers the chain up to that interval and the share of equal counts behind it is reported."""
+    from _cases import check_solver_trace
+    by_name = {c["name"]: c for c in golden_cases}
+    total_equal = total_calls = 0
+    for coop in (False,):
+        for name, gold in golden_solver.items():
+            case = by_name[name]
+            mid, numT = _register(engine, golden_datasets, case)
+            P = len(case["params"])
+            out = engine.evaluate(np.array([case["params"]]).reshape(1, P), model=mid, flags=flags_of(case),
+                                  want=("lc", "status", "nfev", "solve_trace"))
+            trace = out["solve_trace"][0, :numT]
+            checked, equal, n = check_solver_trace(gold, trace, None, name)
+            print("solver trace", name, "calls", n, "self-determined prefix", gold["stable_calls"], "checked", checked, "equal counts", equal)
+            total_equal += equal
+            total_calls += n
+            if gold["stable_calls"] == n:
+                assert equal == n, (name, equal, n)
+                assert out["nfev"][0] == sum(c["nfev"] for c in gold["calls"]), name
+                assert out["nfev"][0] == int(trace[:, 0].sum()), name
+    assert total_equal >= 0.97 * total_calls, (total_equal, total_calls)
+
+
+def test_default_mode_with_migration_stays_inside_the_references_own_band(engine, golden_datasets, golden_cases, golden_solver):
+    """Default-mode correction with migration: the reference does not determine its own result -- moving its parameters or
+    the entries of its 3x3 expm results by ONE ULP moves its log-likelihood by 1e-4 ... 1e-2 relative (recorded per case in
+    tests/golden/solver.json, `llh_one_ulp_probe`).  No implementation can be held to 1e-9 there; what can be held is
+    that the device's likelihood lies inside the band the reference's own one-ulp runs span (widened by half its width on
+    either side), and that with the reference's rates injected the same cases pass at 1e-9
+    (test_golden_jsfs_stage_with_injected_rates)."""
+    checked = 0
     for case in golden_cases:
-        if case["stable"] or not case["expect"]["ok"]:
+        if case["stable"] or not case["expect"]["ok"] or case["name"] not in golden_solver:
             continue
+        gold = golden_solver[case["name"]]
+        band = [v for v in [gold["llh"]] + gold["llh_one_ulp_probe"] if np.isfinite(v)]
+        lo, hi = min(band), max(band)
+        assert hi - lo > 1e-6 * abs(gold["llh"]), case["name"]  # the case IS unstable in the reference
         mid, _ = _register(engine, golden_datasets, case)
         out = engine.evaluate(np.array([case["params"]]), model=mid, flags=flags_of(case), want=("status",))
-        if out["status"][0] == 0:
-            err = relerr(out["llh"][0, 0], case["expect"]["llh"])
-            print("unstable", case["name"], "llh rel err", err)
-            assert err < 5e-2
+        assert out["status"][0] == 0, case["name"]
+        v = out["llh"][0, 0]
+        print("unstable", case["name"], "device llh", v, "reference", gold["llh"], "reference's one-ulp band", lo, hi)
+        assert lo - 0.5 * (hi - lo) <= v <= hi + 0.5 * (hi - lo), (case["name"], v, lo, hi)
+        checked += 1
+    assert checked >= 3
 
 
 def test_batch_against_oracle(engine, golden_datasets):

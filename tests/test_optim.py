@@ -194,3 +194,79 @@ def test_host_driver_follows_scipy_through_the_evaluation_budget():
                     ref = optimize.minimize(f1, x0[s], method="Nelder-Mead", options={"maxfev": mf, "xatol": 1e-4, "fatol": 1e-4})
                     assert np.array_equal(r["x"][s], ref.x), (N, mf, look, spec)
                     assert (r["nfev"][s], r["nit"][s], r["status"][s]) == (ref.nfev, ref.nit, ref.status), (N, mf, look, spec)
+
+
+def _pcg_state(seed):
+    st = np.random.default_rng(seed).bit_generator.state["state"]
+    mask = (1 << 64) - 1
+    return np.array([st["state"] >> 64, st["state"] & mask, st["inc"] >> 64, st["inc"] & mask], dtype=np.uint64)
+
+
+def test_device_generator_continues_numpys_stream(hostsim):
+    """the walkers' random numbers (misti_optim.cuh: Pcg64) are numpy's Generator(PCG64) stream, draw for draw:
+    uniform(-s, s, N) displacements and uniform() Metropolis numbers in any interleaving"""
+    import ctypes
+    up, dp = ctypes.POINTER(ctypes.c_ulonglong), ctypes.POINTER(ctypes.c_double)
+    for seed in (0, 1, 2024, 123456789):
+        ref = np.random.default_rng(seed)
+        state = _pcg_state(seed)
+        for low, high, n in ((-0.5, 0.5, 3), (0.0, 1.0, 1), (-0.45, 0.45, 5), (0.0, 1.0, 1), (-1.7, 1.7, 64)):
+            out = np.zeros(n)
+            hostsim.hs_pcg64_uniform(state.ctypes.data_as(up), ctypes.c_double(low), ctypes.c_double(high), n, out.ctypes.data_as(dp))
+            want = ref.uniform(low, high, n) if n > 1 else np.array([ref.uniform(low, high)])
+            assert np.array_equal(out, want), (seed, low, high)
+
+
+def _device_logic_basinhopping(lib, fun, x0, seed, niter, T=0.5, stepsize=0.5, interval=50, target=0.5, factor=0.9):
+    """one walker through the device's walker logic (bh_advance around the Nelder-Mead step logic), objective on the host"""
+    import ctypes
+    dp, lp, ip, up = (ctypes.POINTER(t) for t in (ctypes.c_double, ctypes.c_longlong, ctypes.c_int, ctypes.c_ulonglong))
+    N = len(x0)
+    sim, fsim = np.zeros((N + 1, N)), np.zeros(N + 1)
+    sim[0] = x0
+    iters, fcalls = ctypes.c_longlong(0), ctypes.c_longlong(0)
+    status, phase = ctypes.c_int(-1), ctypes.c_int(0)
+    pts = np.zeros((lib.hs_nm_slots(N, 0), N))
+    cfg = (N, ctypes.c_double(1e-4), ctypes.c_double(1e-4), ctypes.c_longlong(200 * N), ctypes.c_longlong(200 * N), 0)
+    x, best_x, scal = np.zeros(N), np.zeros(N), np.array([0.0, 0.0, stepsize])
+    flags, cnt, rng = np.zeros(3, dtype=np.int32), np.zeros(5, dtype=np.int64), _pcg_state(seed)
+    lib.hs_nm_propose.restype = ctypes.c_int
+    while True:
+        n = lib.hs_nm_propose(*cfg, sim.ctypes.data_as(dp), fsim.ctypes.data_as(dp), ctypes.byref(iters), ctypes.byref(fcalls),
+                              ctypes.byref(status), ctypes.byref(phase), pts.ctypes.data_as(dp))
+        if n == 0:  # the local search has ended: the walker decides and, unless it has done its hops, starts the next one
+            go = lib.hs_bh_advance(N, niter, interval, ctypes.c_double(T), ctypes.c_double(target), ctypes.c_double(factor),
+                                   x.ctypes.data_as(dp), best_x.ctypes.data_as(dp), scal.ctypes.data_as(dp), flags.ctypes.data_as(ip),
+                                   cnt.ctypes.data_as(lp), rng.ctypes.data_as(up), sim.ctypes.data_as(dp), fsim.ctypes.data_as(dp),
+                                   ctypes.byref(iters), ctypes.byref(fcalls), ctypes.byref(status), ctypes.byref(phase))
+            if not go:
+                break
+            continue
+        fv = np.full(len(pts), np.nan)
+        fv[:n] = [fun(pts[j].copy()) for j in range(n)]
+        lib.hs_nm_apply(*cfg, sim.ctypes.data_as(dp), fsim.ctypes.data_as(dp), ctypes.byref(iters), ctypes.byref(fcalls),
+                        ctypes.byref(status), ctypes.byref(phase), pts.ctypes.data_as(dp), fv.ctypes.data_as(dp))
+    return dict(x=best_x.copy(), fun=scal[1], nfev=int(cnt[0]), failures=int(cnt[1]), accepted=int(cnt[3]), step=scal[2])
+
+
+@pytest.mark.parametrize("N", [1, 2, 3])
+def test_device_walker_logic_equals_scipy_basinhopping(hostsim, N):
+    """a single walker of the on-device basin-hopping reproduces scipy.optimize.basinhopping(..., rng=seed) as
+    MigrationInference.Solve(globalOpt=True) calls it (MigrationInference.py:724): same minimum, same evaluation count,
+    same number of failed local searches -- through adaptive step sizes (interval 7) and infinite objective values"""
+    from scipy import optimize
+    rng = np.random.default_rng(40 + N)
+    for trial in range(3):
+        shift = rng.uniform(-1, 1, N)
+
+        def f(x, shift=shift):
+            if x[0] < -1.2:  # a region where the model does not evaluate (negative rate): +inf, as the reference returns
+                return np.inf
+            return float(bumpy(np.asarray(x).reshape(1, -1), shift)[0])
+        x0 = rng.uniform(-1, 1, N)
+        seed = 1000 * N + trial
+        got = _device_logic_basinhopping(hostsim, f, x0, seed, niter=12, T=0.5, stepsize=0.5, interval=7)
+        ref = optimize.basinhopping(f, x0, niter=12, T=0.5, stepsize=0.5, interval=7, rng=seed,
+                                    minimizer_kwargs={"method": "Nelder-Mead"})
+        assert np.array_equal(got["x"], ref.x) and got["fun"] == ref.fun, (N, trial)
+        assert got["nfev"] == ref.nfev and got["failures"] == ref.minimization_failures, (N, trial)
