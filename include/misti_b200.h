@@ -93,6 +93,11 @@ typedef struct misti_eval_io {
     int32_t* solve_trace;    /* [B][numT_max][2] per interval: evaluations (`nfev`) and termination `status` of its
                                 scipy.optimize.least_squares solve (CorrectLambda.py:85, 260, 303, 305), (0, -9) where
                                 the interval has a closed form -- the iterate-level record behind `nfev`    */
+    double* row_best_llh;    /* [R] max over the B items of llh[b][r], reduced ON THE DEVICE, and                   */
+    int32_t* row_best_item;  /* [R] the item that attains it (the first one): what the reference's bootstrap notebook
+                                computes from one result line per (row, split time) (test.bs/bs_conf_int.ipynb).  With
+                                these set `llh` may be NULL: the B x R likelihoods then never leave the device.  Host
+                                pointers, no row_ids                                                          */
 } misti_eval_io;
 
 int misti_abi_version(void);

@@ -34,7 +34,7 @@ class EvalIO(ctypes.Structure):
     _fields_ = [("lc_inject", ctypes.c_void_p), ("jafs", ctypes.c_void_p), ("jafs_raw", ctypes.c_void_p),
                 ("lc_out", ctypes.c_void_p), ("pr_out", ctypes.c_void_p), ("status", ctypes.c_void_p),
                 ("nfev", ctypes.c_void_p), ("terms", ctypes.c_void_p), ("row_ids", ctypes.c_void_p),
-                ("solve_trace", ctypes.c_void_p)]
+                ("solve_trace", ctypes.c_void_p), ("row_best_llh", ctypes.c_void_p), ("row_best_item", ctypes.c_void_p)]
 
 
 class FitOpts(ctypes.Structure):

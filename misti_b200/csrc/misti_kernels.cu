@@ -548,6 +548,41 @@ misti_score_kernel(int B, const double* __restrict__ spectra, const double* __re
     for (int r = lane; r < R; r += 32) llh[(long)b * R + r] = ok ? misti::score_row(data + 8 * (long)r, logj) : nan("");
 }
 
+// Reduction over the ITEMS of a batch, per data row: best[r] = max_b llh[b][r] and the item that attains it (the first one,
+// as numpy.argmax) -- what the reference's bootstrap notebook computes from 9 009 result lines (test.bs/bs_conf_int.ipynb:
+// per replicate the split time of the highest likelihood), done where the likelihoods are, so that a sweep returns 2 R
+// numbers instead of B R.  Two steps: chunks of `per` items per thread (rows across the threads: coalesced), then the
+// chunks in order, merged into the running best of the call (item_offset = first item of this launch in the call).
+__global__ void __launch_bounds__(128)
+misti_rowmax_partial_kernel(int B, int R, const double* __restrict__ llh, int per, double* __restrict__ pbest, int* __restrict__ pitem) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x, c = blockIdx.y;
+    if (r >= R) return;
+    const int b0 = c * per, b1 = b0 + per < B ? b0 + per : B;
+    double best = llh[(long)b0 * R + r];
+    int item = b0;
+    for (int b = b0 + 1; b < b1; ++b) {
+        const double v = llh[(long)b * R + r];
+        if (v > best) { best = v; item = b; }
+    }
+    pbest[(long)c * R + r] = best;
+    pitem[(long)c * R + r] = item;
+}
+
+__global__ void __launch_bounds__(128)
+misti_rowmax_final_kernel(int nchunks, int R, const double* __restrict__ pbest, const int* __restrict__ pitem, int item_offset, int first,
+                          double* __restrict__ best, int* __restrict__ item) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    double bv = first ? pbest[r] : best[r];
+    int bi = first ? pitem[r] + item_offset : item[r];
+    for (int c = first ? 1 : 0; c < nchunks; ++c) {
+        const double v = pbest[(long)c * R + r];
+        if (v > bv) { bv = v; bi = pitem[(long)c * R + r] + item_offset; }
+    }
+    best[r] = bv;
+    item[r] = bi;
+}
+
 // lc[(2t+g)*stride + b]  ->  out[b][numT_max][2].  With defer_post (cpfit mode) the correction kernel left the post-split
 // rates out (nothing on the path needs them): they are computed here from exp(nc1 - nc0), one interval per thread.
 __global__ void misti_gather_lc_kernel(int B, int numT_max, const int* __restrict__ model_ids, int model_default,
@@ -801,6 +836,8 @@ struct misti_ctx {
     size_t s_lc_io_cap = 0, s_pr_cap = 0;
     int* s_trace = nullptr;
     size_t s_trace_cap = 0;
+    double* d_rowmax = nullptr;  // scratch of the per-row reduction over items: partial bests, then best[R]; items behind as ints
+    size_t d_rowmax_cap = 0;
     unsigned char* d_nm = nullptr;  // state and batch buffers of misti_nelder_mead (one block, carved up per call)
     size_t d_nm_cap = 0;
     int* h_nm_counts = nullptr;     // pinned: copy of the fit's device-side counters (FC_*), refreshed after every batch of rounds
@@ -1025,7 +1062,7 @@ void misti_ctx_destroy(misti_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     void* ptrs[] = {ctx->d_times, ctx->d_lh, ctx->d_gaux, ctx->d_cls, ctx->d_post, ctx->d_models, ctx->d_data, ctx->d_lc, ctx->d_cpost, ctx->d_status, ctx->d_nfev, ctx->d_conts, ctx->d_queue[0], ctx->d_queue[1], ctx->d_counts,
                     ctx->d_rec, ctx->d_nseg, ctx->s_params, ctx->s_llh, ctx->s_jafs, ctx->s_jafs_raw, ctx->s_model_ids, ctx->s_terms, ctx->s_row_ids, ctx->s_lc_io,
-                    ctx->s_pr, ctx->d_small, ctx->d_nm, ctx->d_score, ctx->s_trace};
+                    ctx->s_pr, ctx->d_small, ctx->d_nm, ctx->d_score, ctx->s_trace, ctx->d_rowmax};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     for (int i = 0; i < 3; ++i)
@@ -1270,10 +1307,37 @@ static int eval_chunk(misti_ctx* ctx, int B, int P, const double* d_params, cons
     return 0;
 }
 
+// per-row reduction over the n items of one launch (likelihoods d_llh[n][R] on the device) into the running best of the call;
+// layout of ctx->d_rowmax: partial bests [nchunks][R], best [R], then (as ints) partial items [nchunks][R], item [R]
+constexpr int kRowmaxPer = 64;
+static int rowmax_chunk(misti_ctx* ctx, int n, int R, const double* d_llh, long item_offset, bool first, double** d_best, int** d_item) {
+    const int nchunks_max = (ctx->max_chunk + kRowmaxPer - 1) / kRowmaxPer;
+    const size_t doubles = (size_t)(nchunks_max + 1) * R, ints = (size_t)(nchunks_max + 1) * R;
+    int rc;
+    if (first && (rc = ensure(ctx, &ctx->d_rowmax, &ctx->d_rowmax_cap, doubles + (ints + 1) / 2))) return rc;
+    double* pbest = ctx->d_rowmax;
+    double* best = pbest + (size_t)nchunks_max * R;
+    int* pitem = reinterpret_cast<int*>(ctx->d_rowmax + doubles);
+    int* item = pitem + (size_t)nchunks_max * R;
+    const int nchunks = (n + kRowmaxPer - 1) / kRowmaxPer;
+    const dim3 grid((unsigned)((R + 127) / 128), (unsigned)nchunks);
+    misti_rowmax_partial_kernel<<<grid, 128, 0, ctx->stream>>>(n, R, d_llh, kRowmaxPer, pbest, pitem);
+    CK(cudaGetLastError());
+    misti_rowmax_final_kernel<<<(unsigned)((R + 127) / 128), 128, 0, ctx->stream>>>(nchunks, R, pbest, pitem, (int)item_offset, first ? 1 : 0, best, item);
+    CK(cudaGetLastError());
+    ctx->launches += 2;
+    *d_best = best;
+    *d_item = item;
+    return 0;
+}
+
 int misti_eval_batch(misti_ctx* ctx, int32_t B, int32_t P, const double* params, const int32_t* model_ids, int32_t model_default,
                      uint32_t flags, double mixture_th, double* llh, const misti_eval_io* io) {
     if (!ctx) return MISTI_E_ARG;
-    if (B < 0 || P < 0 || P > MISTI_MAX_PARAMS || !llh) return fail(ctx, MISTI_E_ARG, "misti_eval_batch: bad arguments");
+    const bool want_rowmax = io && (io->row_best_llh || io->row_best_item);
+    if (B < 0 || P < 0 || P > MISTI_MAX_PARAMS || (!llh && !want_rowmax)) return fail(ctx, MISTI_E_ARG, "misti_eval_batch: bad arguments");
+    if (want_rowmax && (io->row_ids || (flags & MISTI_FLAG_DEVICE_PTRS)))
+        return fail(ctx, MISTI_E_ARG, "misti_eval_batch: row_best_* needs host pointers and no row_ids");
     if (B == 0) return 0;
     if (P > 0 && !params) return fail(ctx, MISTI_E_ARG, "misti_eval_batch: params is null");
     if (ctx->h_models.empty()) return fail(ctx, MISTI_E_ARG, "misti_eval_batch: no model registered");
@@ -1342,7 +1406,16 @@ int misti_eval_batch(misti_ctx* ctx, int32_t B, int32_t P, const double* params,
                         io->lc_out ? ctx->s_lc_io : nullptr, io->pr_out ? ctx->s_pr : nullptr, nullptr, nullptr, ctx->s_terms,
                         io->row_ids ? ctx->s_row_ids : nullptr, io->solve_trace ? ctx->s_trace : nullptr);
         if (rc) return rc;
-        CK(cudaMemcpyAsync(llh + off * Rl, ctx->s_llh, (size_t)n * Rl * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        if (llh) CK(cudaMemcpyAsync(llh + off * Rl, ctx->s_llh, (size_t)n * Rl * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        if (want_rowmax) {
+            double* d_best = nullptr;
+            int* d_item = nullptr;
+            if ((rc = rowmax_chunk(ctx, n, R, ctx->s_llh, off, off == 0, &d_best, &d_item))) return rc;
+            if (off + n >= B) {  // the last launch of the call: the running best is final
+                if (io->row_best_llh) CK(cudaMemcpyAsync(io->row_best_llh, d_best, (size_t)R * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+                if (io->row_best_item) CK(cudaMemcpyAsync(io->row_best_item, d_item, (size_t)R * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+            }
+        }
         if (io->jafs) CK(cudaMemcpyAsync(io->jafs + off * 7, ctx->s_jafs, (size_t)n * 7 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
         if (io->jafs_raw)
             CK(cudaMemcpyAsync(io->jafs_raw + off * 7, ctx->s_jafs_raw, (size_t)n * 7 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));

@@ -154,11 +154,13 @@ class Engine:
 
     # -- evaluation -----------------------------------------------------------------------------
     def evaluate(self, params, model=0, model_ids=None, flags=_lib.FLAG_CORRECT, mixtureTH=0.0, lc_inject=None,
-                 want=("jafs", "status"), buffers=None, row_ids=None):
+                 want=("jafs", "status"), buffers=None, row_ids=None, row_best=False):
         """Host-buffer evaluation.  params: [B, P] (or [B] / [] for P = 0).  Returns a dict with
         'llh' [B, R] and the arrays named in `want` (jafs, jafs_raw, lc, pr, status, nfev, terms, solve_trace).
         `buffers` may hold preallocated C-contiguous numpy arrays (e.g. views of pinned memory) to write into.
-        With `row_ids` [B], item b is scored against data row row_ids[b] only and 'llh' is [B, 1]."""
+        With `row_ids` [B], item b is scored against data row row_ids[b] only and 'llh' is [B, 1].
+        row_best: reduce over the items ON THE DEVICE -- 'row_best_llh' [R] = max_b llh[b, r] and 'row_best_item' [R] = the item
+        that attains it; with row_best="only" the [B, R] likelihoods never leave the device ('llh' is then absent)."""
         params = _as_f64(params)
         if params.ndim == 1:
             params = params.reshape(-1, 1) if params.size else params.reshape(1, 0)
@@ -186,7 +188,10 @@ class Engine:
             if rows.shape[0] != B or (B and (rows.min() < 0 or rows.max() >= self.R)):
                 raise ValueError("row_ids must hold one valid data row index per item")
             io.row_ids = _ptr(rows)
-        out = {"llh": _buf("llh", (B, 1 if rows is not None else self.R), np.float64)}
+        out = {} if row_best == "only" else {"llh": _buf("llh", (B, 1 if rows is not None else self.R), np.float64)}
+        if row_best:
+            out["row_best_llh"], out["row_best_item"] = np.zeros(self.R), np.zeros(self.R, dtype=np.int32)
+            io.row_best_llh, io.row_best_item = _ptr(out["row_best_llh"]), _ptr(out["row_best_item"])
         nT = self.numT_max
         if lc_inject is not None:
             inj = _as_f64(lc_inject).reshape(B, nT, 2)
@@ -201,7 +206,7 @@ class Engine:
             out[name] = _buf(name, shp, dt)
             setattr(io, field[name], _ptr(out[name]))
         self._check(self._lib.misti_eval_batch(self._h, B, P, _ptr(params) if P else None, _ptr(mids), int(model), flags,
-                                               float(mixtureTH), _ptr(out["llh"]), ctypes.byref(io)))
+                                               float(mixtureTH), _ptr(out.get("llh")), ctypes.byref(io)))
         return out
 
     def evaluate_device(self, B, P, params_ptr, llh_ptr, model=0, model_ids_ptr=None, flags=_lib.FLAG_CORRECT, mixtureTH=0.0,

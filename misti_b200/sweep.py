@@ -83,10 +83,26 @@ class Sweep:
         MigrationInference.COUNT_LLH += M
         return out["llh"]
 
+    def argmax_split(self, params_per_model=None):
+        """Per data row (bootstrap replicate) the model -- split time -- of the highest likelihood at fixed parameters, and
+        that likelihood: the reduction of the reference's bootstrap notebook (test.bs/bs_conf_int.ipynb: per replicate the
+        arg-max over `st` of the result lines), taken on the device, so that M x R likelihoods come back as 2 R numbers.
+        Returns dict(model [R] index into self.models, splitT [R], llh [R])."""
+        M = len(self.models)
+        P = max([m["n_params"] for m in self.models] + [0])
+        X = np.zeros((M, P))
+        for i, m in enumerate(self.models):
+            v = m["init"] if params_per_model is None else params_per_model[i]
+            X[i, :len(v)] = v
+        out = self.engine.evaluate(X, model_ids=self._model_ids(), flags=self.flags, mixtureTH=self.mixtureTH, want=(), row_best="only")
+        MigrationInference.COUNT_LLH += M
+        idx = out["row_best_item"].astype(np.int64)
+        return {"model": idx, "splitT": np.array([self.models[i]["splitT"] for i in idx]), "llh": out["row_best_llh"]}
+
     # -- fits ------------------------------------------------------------------------------------------
-    # up to this many points per round the Nelder-Mead steps are taken on the device (Engine.nelder_mead: no host round
-    # trip per step); beyond, the host driver wins because it packs only the simplices that are still running
-    DEVICE_NM_MAX_POINTS = 16384
+    # up to this many points per round the fits are stepped on the device (Engine.nelder_mead / Engine.basinhopping: no host
+    # round trip per step, only the simplices still running are packed into a round); beyond, the host driver takes over
+    DEVICE_NM_MAX_POINTS = 1 << 18
 
     def solve(self, pairs=None, tol=1e-4, globalOpt=False, niter=100, seed=0, speculative=True, on_device="auto"):
         """Fit every (model, row) pair (default: all).  Nelder-Mead with xatol = fatol = tol, maxiter = 1000 as
@@ -128,9 +144,13 @@ class Sweep:
                 MigrationInference.COUNT_LLH += r["evaluations"]
                 MigrationInference.CORRECTION_CALLED += r["evaluations"]
                 return r
-            if globalOpt:
-                r = basinhopping_batch(fun, x0, niter=niter, T=0.5, seeds=[seed + int(k) for k in sel], speculative=speculative,
-                                       local_solver=device_nm if dev else None)
+            if globalOpt and dev:  # walkers on the device: no barrier between the hops of different walkers
+                r = self.engine.basinhopping(x0, mids, pairs[sel, 1], seeds=[seed + int(k) for k in sel], flags=self.flags,
+                                             mixtureTH=self.mixtureTH, niter=niter, T=0.5)
+                MigrationInference.COUNT_LLH += r["evaluations"]
+                MigrationInference.CORRECTION_CALLED += r["evaluations"]
+            elif globalOpt:
+                r = basinhopping_batch(fun, x0, niter=niter, T=0.5, seeds=[seed + int(k) for k in sel], speculative=speculative)
             else:
                 if dev:
                     r = device_nm(x0, xatol=tol, fatol=tol, maxiter=1000)

@@ -127,11 +127,26 @@ def main():
                 stable = min(stable, k)
         out.append({"name": name, "calls": calls, "stable_calls": stable, "llh": llh, "llh_one_ulp_probe": llh_probe})
         print(name, len(calls), "calls, stable", stable, "nfev total", sum(c["nfev"] for c in calls), llh, llh_probe, flush=True)
+    # An ill-conditioned --cpfit chain found by the fuzz sweep (tools/fuzz_parity.py part D, profiles/r01_fuzz_parity.json):
+    # the corrected rates run away to ~200 before the split and the reference's result is BISTABLE -- one trust-region solve
+    # stops one evaluation earlier or later depending on the last bit of its 3x3 expm results, and the likelihood lands on
+    # one of two values 1.5e-8 apart.  Recorded: the reference's likelihood as is and under eight one-ulp expm probes.
+    branch_case = {"name": "fuzz_st52_two_bands", "dataset": "synthetic", "splitT": 52, "mi": [[1, 3, 10, 0.607, 1], [2, 42, 49, 0.802, 1]],
+                   "pu": [], "flags": {"smooth": True, "unfolded": True, "trueEPS": False, "cpfit": True}}
+    branch_points = [[3.705137947124301, 8.757866362592685], [3.7058955164970597, 8.758171298915583],
+                     [3.7067050415996903, 8.758509405044837], [3.707060261654498, 8.758613320009076],
+                     [3.706956953503096, 8.758538988322861], [3.706831580522753, 8.758501444193307]]
+    branches = []
+    for x in branch_points:
+        calls, llh = run(ds, branch_case, x)
+        probes = [run(ds, branch_case, x, expm_seed=k)[1] for k in range(1, 9)]
+        branches.append({"x": x, "llh": llh, "llh_expm_one_ulp_probes": probes, "nfev": sum(c["nfev"] for c in calls)})
+        print("branch", x, llh, sorted(set(round(v, 6) for v in probes)), flush=True)
     import scipy
     meta = {"numpy": np.__version__, "scipy": scipy.__version__, "generated_by": "tests/golden/gen_solver_golden.py",
             "reference": "Genomics-HSE/MiSTI (unmodified, via ref_shim; scipy.optimize.least_squares wrapped, not changed)"}
     with open(os.path.join(HERE, "solver.json"), "w") as f:
-        json.dump({"meta": meta, "cases": out}, f)
+        json.dump({"meta": meta, "cases": out, "bistable": {"case": branch_case, "points": branches}}, f)
 
 
 if __name__ == "__main__":
