@@ -1,25 +1,29 @@
 #!/usr/bin/env python3
-"""bench.py -- batched expected-JSFS + composite-logL evaluations per second (BASELINE.json metric).
+"""bench.py -- batched expected-JSFS + composite-logL evaluations per second, and time to fit (BASELINE.json metric).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl ours|reference]
 
-One "step" = one pass of the hot path over one batch of B synthetic parameter vectors per GPU
-(BASELINE config 2: split index 40, unfolded SFS, one optimised migration band `-mi 2 5 12 0.8 1`,
-`--cpfit`, m ~ U(0,5), numpy default_rng(1234 + rank)).  Prints ONE JSON line.
+One "step" = one pass of the hot path over one batch of B synthetic parameter vectors per GPU (BASELINE config 2: split
+index 40, unfolded SFS, one optimised migration band `-mi 2 5 12 0.8 1`, `--cpfit`, m ~ U(0,5), numpy
+default_rng(1234 + rank)).  Prints ONE JSON line.
 
-  value      evaluations/s, whole job, inputs resident in HBM, CUDA-event timed per step
-  e2e        the same metric through the public host-buffer API (Engine.evaluate): pinned host
-             buffers, H2D of the parameters and D2H of llh + status inside the timed region
-  roofline   the dominant kernel against the measured FP64 peak (dense-equivalent algorithmic FLOPs of
-             SURVEY.md 8d AND the FLOPs actually executed, counted from the kernel's own term counter)
-  time_to_fit   one Nelder-Mead fit of the bench model stepped on the device (misti_nelder_mead) next to the same fit by
-             the CPU oracle on one core (the second half of the BASELINE metric; rank 0, N = 1 only)
-  cpu_baseline  the CPU oracle (oracle/misti_oracle.py, numpy/scipy port of the reference path) timed on
-             the host cores on a bounded sample of the same parameter vectors (rank 0, N = 1 only)
+  value        evaluations/s, whole job, inputs resident in HBM, CUDA-event timed per step.  At N > 1 every timed step
+               ends with the path's one collective, the all-gather of the likelihood vectors to every rank
+               (misti_b200.parallel.gather_rows_device, device-resident) -- `value_no_collective` is the same without it
+  e2e          the same metric through the public host-buffer API: pinned host buffers, H2D of the parameters, the kernels,
+               (N > 1: the all-gather,) D2H of llh + expected JSFS + status inside the timed region
+  roofline     the dominant kernel (misti_correct_kernel) against the measured FP64 peak of this pool's B200: FLOPs it
+               executed (SASS counts of the committed ncu capture) / its CUDA-event time; the second kernel and the
+               dense-equivalent figure of SURVEY.md 8d are listed beside it under their own keys
+  batch_sweep  evaluations/s at B = 2, 64, 4096, 65536
+  time_to_fit  the second half of the metric, device-timed, fits sharded over the N ranks (strong scaling):
+               config 2 (one Nelder-Mead fit), config 5b (9 009 fits = 1 001 bootstrap rows x 9 split times), config 3
+               (basin-hopping walkers, 1 024 per GPU)
+  cpu_baseline the reference's own CPU implementation (oracle/_ref, the unmodified Genomics-HSE/MiSTI staged by
+               oracle/make_ref.py; kind "reference") -- or, where that is absent, the oracle port (kind "port") -- on
+               the host cores, bounded sample of the same parameter vectors (rank 0, N = 1 only)
 
---impl reference times the CPU implementation of the same path on the host cores (the reference is
-pure Python and cannot travel to the GPU box; the oracle port is the same algorithm on the same scipy
-calls), with one worker process per core.
+--impl reference times that CPU implementation alone, one worker process per host core (BLAS threads 1 as MiSTI.py:23-25).
 """
 import argparse
 import json
@@ -42,18 +46,18 @@ SPLIT_T, BAND = 40, [2, 5, 12, 0.8, 1]
 NUM_T = 127
 # dense formulation (Pade-13 + Van Loan, zero squarings) per evaluation
 F_DENSE = SPLIT_T * (12 + 8.0 / 3) * 45 ** 3 + (NUM_T - SPLIT_T) * (12 + 8.0 / 3) * 9 ** 3
-# executed FLOPs per sparse mat-vec term of the uniformisation kernel (misti_jsfs.cuh inner loop):
-# 44 rows x (1 diagonal + 4 off-diagonal slots) FMAs + 2 FMAs (P1, integral) + 1 per row
-F_TERM = 44 * (2 * 5 + 2 * 2 + 1)
 FP64_PEAK_FILE = os.path.join(ROOT, "profiles", "r01_fp64_peak.json")
-EXEC_FLOPS_FILE = os.path.join(ROOT, "profiles", "r01_executed_flops.json")
-DRAM_TRAFFIC = None  # bytes per launch pair from the committed ncu --set full capture (set below when profiles/ has it)
-if os.path.exists(EXEC_FLOPS_FILE):
-    try:
-        with open(EXEC_FLOPS_FILE) as _f:
-            DRAM_TRAFFIC = json.load(_f).get("dram_bytes_per_launch_pair")
-    except (OSError, ValueError):
-        DRAM_TRAFFIC = None
+
+
+def _first_existing(*names):
+    for n in names:
+        p = os.path.join(ROOT, "profiles", n)
+        if os.path.exists(p):
+            return p
+    return None
+
+
+EXEC_FLOPS_FILE = _first_existing("r02_executed_flops.json", "r01_executed_flops.json")
 
 
 def load_dataset():
@@ -71,24 +75,54 @@ def workload_name(B):
             "B=%d vectors/GPU, m~U(0,5)" % B)
 
 
+def bench_config(B):
+    """the same dict in both arms (the driver compares them)"""
+    return {"workload": workload_name(B), "l2": "256 MiB buffer rewritten between timed iterations",
+            "parallelism": "independent items sharded across ranks; all_gather of llh inside every timed step at N > 1"}
+
+
 # ------------------------------------------------------------------------------------------------
-# CPU arm (oracle port): one worker process per core
+# CPU arm: the unmodified reference (oracle/_ref) when staged, else the oracle port; one worker process per core
 # ------------------------------------------------------------------------------------------------
 _worker_model = None
+
+
+def cpu_kind():
+    from oracle import ref_loader
+    return "reference" if ref_loader.available() else "port"
+
+
+def _cpu_model(mi=(BAND,), pu=(), st=SPLIT_T):
+    from oracle import ref_loader
+    ds = load_dataset()
+    if ref_loader.available():
+        M = ref_loader.make_model(ds["times"], ds["lambdas"], ds["sfs"], st, mi, pu, cpfit=True, smooth=True, unfolded=True)
+        return lambda x: float(ref_loader.quiet(M.JAFSLikelihood, list(x))), M
+    from oracle.misti_oracle import OracleModel
+    M = OracleModel(ds["times"], ds["lambdas"], ds["sfs"], st, [list(m) for m in mi], [list(p) for p in pu], cpfit=True, smooth=True,
+                    unfolded=True)
+    return lambda x: float(M.likelihood(list(x))), M
 
 
 def _worker_eval(m):
     global _worker_model
     if _worker_model is None:
-        from oracle.misti_oracle import OracleModel
-        ds = load_dataset()
-        _worker_model = OracleModel(ds["times"], ds["lambdas"], ds["sfs"], SPLIT_T, [BAND], [], cpfit=True, smooth=True,
-                                    unfolded=True)
-    return float(_worker_model.likelihood([m]))
+        _worker_model = _cpu_model()[0]
+    return _worker_model([m])
+
+
+def cpu_path_text():
+    import numpy
+    import scipy
+    if cpu_kind() == "reference":
+        return ("oracle/_ref/misti_reference.zip: Genomics-HSE/MiSTI unmodified (MigrationInference.JAFSLikelihood), numpy %s / "
+                "scipy %s" % (numpy.__version__, scipy.__version__))
+    return "oracle/misti_oracle.py (numpy %s / scipy %s port of the reference path; oracle/_ref is not staged)" % (
+        numpy.__version__, scipy.__version__)
 
 
 def cpu_rate(n_evals, cores, rank=0):
-    """evals/s of the CPU oracle on `cores` worker processes over n_evals parameter vectors."""
+    """evals/s of the CPU implementation on `cores` worker processes over n_evals parameter vectors."""
     import multiprocessing as mp
     ms = [float(v) for v in make_params(n_evals, rank)[:, 0]]
     ctx = mp.get_context("spawn")
@@ -105,7 +139,8 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    per_step = 16 * cores
+    kind = cpu_kind()
+    per_step = (2 if kind == "reference" else 16) * cores  # a step stays well under a second per core
     import multiprocessing as mp
     ms_all = [float(v) for v in make_params(per_step * (args.steps + args.warmup), 0)[:, 0]]
     ctx = mp.get_context("spawn")
@@ -121,13 +156,10 @@ def run_reference(args):
     total = sum(times)
     value = per_step * args.steps / total
     sample = "%d evaluations per step (same parameter distribution), %d worker processes, BLAS threads 1" % (per_step, cores)
-    import numpy, scipy
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "evals/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(args.batch), "cpu_path": "oracle/misti_oracle.py (numpy %s / scipy %s port of "
-                       "the reference path; the reference is pure Python and is absent on the GPU box)" % (numpy.__version__, scipy.__version__)},
-            "cpu_baseline": {"value": value, "unit": "evals/s", "cores": cores, "kind": "port", "sample": sample},
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": bench_config(args.batch), "cpu_path": cpu_path_text(),
+            "cpu_baseline": {"value": value, "unit": "evals/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     _emit(json.dumps(line))
 
@@ -145,7 +177,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.QUERY,
-                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE, text=True)
+                                          "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
@@ -154,15 +186,15 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([time.monotonic()] + [c.strip() for c in line.split(",")])
 
-    def stop(self, t0, t1):
-        """median SM clock over the samples taken inside [t0, t1] (the timed regions)"""
+    def stop(self, windows):
+        """median SM clock over the samples taken inside the timed windows [(t0, t1), ...]"""
         if self.proc is not None:
             self.proc.terminate()
             try:
                 self.proc.wait(timeout=5)
             except Exception:
                 pass
-        rows = [r[1:] for r in self.rows if t0 <= r[0] <= t1 + 0.05]
+        rows = [r[1:] for r in self.rows if any(t0 <= r[0] <= t1 + 0.02 for t0, t1 in windows)]
         sm = [float(r[1]) for r in rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
         mx = [float(r[2]) for r in rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
         reasons = set()
@@ -176,11 +208,124 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def time_to_fit(args, eng, dev, world, rank, barrier, stream):
+    """Device-timed fits, sharded over the ranks (strong scaling for config 5b, 1 024 walkers per GPU for config 3)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import misti_b200
+    from misti_b200 import io as mio
+    from misti_b200.parallel import gather_rows, shard_indices
+    from misti_b200.sweep import Sweep
+    data_dir = os.path.join(ROOT, "data", "synthetic")
+    units = mio.Units.from_file(os.path.join(data_dir, "setunits.txt"))
+    inp = mio.read_psmc(os.path.join(data_dir, "m1.psmc"), os.path.join(data_dir, "m2.psmc"), 0, -1, units)
+    data = mio.column_sums(mio.read_jafs(os.path.join(data_dir, "m.sfs")).jafs)
+    bs = mio.read_jafs(os.path.join(data_dir, "bs.sfs")).jafs
+    out = {}
+
+    def timed(fn, reps=2):
+        """fn() run `reps` times (the first pays graph capture and buffer growth); device time of the last, max over ranks"""
+        res, ms = None, 0.0
+        for _ in range(reps):
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0 = time.perf_counter()
+            e0.record(stream)
+            res = fn()
+            e1.record(stream)
+            torch.cuda.synchronize(dev)
+            ms = e0.elapsed_time(e1)
+            wall = time.perf_counter() - t0
+        t = torch.tensor([ms, 1e3 * wall], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return res, float(t[0].item()) * 1e-3, float(t[1].item()) * 1e-3
+
+    # ---- config 5b: 1 001 rows x split times 36..44, `-uf -mi 1 4 st 3 1 --cpfit`: 9 009 Nelder-Mead fits, dealt over the ranks
+    sts = list(range(36, 45))
+    sw = Sweep(inp.times, inp.lambdas, bs, unfolded=True, cpfit=True, smooth=True, engine=eng)
+    for st in sts:
+        sw.add_model(st, [[1, 4, st, 3, 1]])
+    pairs = np.array([(m, r) for r in range(len(bs)) for m in range(len(sts))], dtype=np.int64)
+    mine = pairs[shard_indices(len(pairs), rank, world)]
+
+    def fits_5b():
+        r = sw.solve(pairs=mine, tol=1e-4)
+        cols = torch.from_numpy(np.column_stack([r["x"][:, 0], r["llh"], r["nfev"].astype(np.float64)])).to(dev)
+        full = gather_rows(cols, len(pairs))  # x, llh, nfev of every fit on every rank: the collective of the fit path
+        return r, full
+    (r5, full5), s5, w5 = timed(fits_5b)
+    full5 = full5.cpu().numpy()
+    out["config5b"] = {"what": "9 009 Nelder-Mead fits (1 001 bootstrap rows x split times 36..44, -uf -mi 1 4 st 3 1 --cpfit, tol 1e-4), "
+                               "fits dealt over the ranks, x / llh / nfev all-gathered",
+                       "scaling": "strong", "fits": int(len(pairs)), "device_s": s5, "wall_s": w5, "fits_per_s": len(pairs) / s5,
+                       "rounds_of_launches_rank0": int(r5["launches"]), "device_evaluations_rank0": int(r5["evaluations"]),
+                       "scipy_nfev_total": int(full5[:, 2].sum()), "checksum_llh": float(full5[:, 1].sum()),
+                       "converged_rank0": int(r5["success"].sum()), "limiter": "rounds x latency of one item's serial correction chain "
+                       "(36 trust-region intervals per item; the first rounds start in the run-away regime m = 3)"}
+
+    # ---- config 3: two bands + pulse, basin-hopping walkers (1 024 per GPU), niter hops, T = 0.5, stepsize = 0.5, seed 2024
+    sw3 = Sweep(inp.times, inp.lambdas, [data], unfolded=True, cpfit=True, engine=eng)
+    m3 = sw3.add_model(40, [[1, 2, 10, 0.3, 1], [2, 5, 12, 0.8, 1]], [[1, 7, 0.05, 1]])
+    W = args.walkers
+    rng = np.random.default_rng(2024 + rank)
+    x0 = np.column_stack([rng.uniform(0, 5, W), rng.uniform(0, 5, W), rng.uniform(0, 0.5, W)])
+    mids = np.full(W, sw3.models[m3]["id"], dtype=np.int32)
+    seeds = [2024 + rank * W + w for w in range(W)]
+
+    def walkers_3():
+        r = eng.basinhopping(x0, mids, np.zeros(W, dtype=np.int32), seeds=seeds, flags=sw3.flags, niter=args.fit_niter, T=0.5, stepsize=0.5)
+        best = int(np.argmin(r["fun"]))
+        row = torch.tensor([[r["fun"][best]] + r["x"][best].tolist() + [float(r["nfev"].sum()), float(r["evaluations"])]],
+                           dtype=torch.float64, device=dev)
+        return r, gather_rows(row, world)  # every rank learns every rank's best walker
+    (r3, best3), s3, w3 = timed(walkers_3, reps=1 if args.fit_niter >= 50 else 2)
+    best3 = best3.cpu().numpy()
+    k = int(np.argmin(best3[:, 0]))
+    out["config3"] = {"what": "basin-hopping (-mi 1 2 10 0.3 1 -mi 2 5 12 0.8 1 -pu 1 7 0.05 1 --cpfit), T = 0.5, stepsize = 0.5, seeds 2024.., "
+                              "%d walkers per GPU x %d hops, walkers advance independently on the device" % (W, args.fit_niter),
+                      "scaling": "weak", "walkers_total": W * world, "niter": args.fit_niter, "device_s": s3, "wall_s": w3,
+                      "scipy_nfev_total": int(best3[:, 4].sum()), "device_evaluations_total": int(best3[:, 5].sum()),
+                      "scipy_evals_per_s": float(best3[:, 4].sum()) / s3, "rounds_of_launches_rank0": int(r3["launches"]),
+                      "best_llh": float(-best3[k, 0]), "best_x": [float(v) for v in best3[k, 1:4]],
+                      "limiter": "rounds x latency of one evaluation (a walker's hops and iterations are sequential)"}
+    if rank != 0:
+        return None
+
+    # ---- config 2: ONE Nelder-Mead fit (latency of a serial fit), next to the CPU implementation on one core
+    sw2 = Sweep(inp.times, inp.lambdas, [data], unfolded=True, cpfit=True, engine=eng)
+    sw2.add_model(SPLIT_T, [BAND])
+    r2, s2, w2 = None, None, None
+    for _ in range(3):
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        r2 = sw2.solve(tol=1e-4)
+        w2 = time.perf_counter() - t0
+    out["config2"] = {"what": "one Nelder-Mead fit of the optimised band (tol 1e-4, start 0.8)", "wall_s": w2, "x": r2["x"][0][:1].tolist(),
+                      "llh": float(r2["llh"][0]), "nfev": int(r2["nfev"][0]), "rounds_of_launches": int(r2["launches"])}
+    if world == 1 and not args.skip_cpu:
+        from scipy import optimize
+        f, _ = _cpu_model()
+        t0 = time.perf_counter()
+        ref = optimize.minimize(lambda x: -f(x), [BAND[3]], method="Nelder-Mead", options={"xatol": 1e-4, "fatol": 1e-4, "maxiter": 1000})
+        cpu_s = time.perf_counter() - t0
+        out["config2"].update({"cpu_s": cpu_s, "cpu_kind": cpu_kind(), "cpu_cores": 1, "cpu_x": [float(v) for v in ref.x],
+                               "cpu_llh": float(-ref.fun), "cpu_nfev": int(ref.nfev)})
+        per_eval = cpu_s / max(1, ref.nfev)
+        out["config5b"]["cpu_extrapolated_s_1core"] = per_eval * out["config5b"]["scipy_nfev_total"]
+        out["config3"]["cpu_extrapolated_s_1core"] = per_eval * out["config3"]["scipy_nfev_total"]
+        out["cpu_note"] = ("cpu_extrapolated_s_1core = the CPU implementation's measured seconds per evaluation in the config-2 fit "
+                           "x scipy's evaluation count of the fits (its models cost the CPU at least as much per evaluation)")
+    return out
+
+
 def run_gpu(args):
     import numpy as np
     import torch
     import torch.distributed as dist
     import misti_b200
+    from misti_b200.parallel import ShardedEvaluator, gather_rows_device
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -191,7 +336,7 @@ def run_gpu(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    stream = torch.cuda.Stream(dev)  # a real (non-NULL) stream shared by torch events and the engine's launches
+    stream = torch.cuda.Stream(dev)  # a real (non-NULL) stream shared by torch events, NCCL and the engine's launches
     torch.cuda.set_stream(stream)
     eng = misti_b200.Engine(local, stream=stream.cuda_stream)
 
@@ -216,62 +361,80 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def step_device():
-        eng.evaluate_device(B, 1, params_d.data_ptr(), llh_d.data_ptr(), model=mid, flags=flags, jafs_ptr=jafs_d.data_ptr(),
+    def step_device(n=B, collective=True):
+        eng.evaluate_device(n, 1, params_d.data_ptr(), llh_d.data_ptr(), model=mid, flags=flags, jafs_ptr=jafs_d.data_ptr(),
                             status_ptr=status_d.data_ptr(), terms_ptr=terms_d.data_ptr())
+        if world > 1 and collective:
+            return gather_rows_device(llh_d[:n], world * n)  # the path's one collective: llh of every item on every rank
+        return llh_d
 
-    # ---- device-resident throughput -----------------------------------------------------------
+    def timed_steps(fn, steps):
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        k1_ms, k2_ms = [], []
+        barrier()
+        t0 = time.monotonic()
+        for s in range(steps):
+            flush.zero_()  # L2 flush between timed iterations (outside the per-step events)
+            ev[s][0].record(stream)
+            fn()
+            ev[s][1].record(stream)
+            a, b = eng.last_kernel_ms()  # synchronises with this step
+            k1_ms.append(a)
+            k2_ms.append(b)
+        barrier()
+        return sum(e0.elapsed_time(e1) for e0, e1 in ev), k1_ms, k2_ms, (t0, time.monotonic())
+
+    # ---- device-resident throughput (with the collective at N > 1) -----------------------------
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    windows = []
     for _ in range(args.warmup):
         flush.zero_()
         step_device()
     barrier()
     launches0 = eng.launch_count()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    k1_ms, k2_ms = [], []
-    barrier()
-    t_load0 = time.monotonic()
-    for s in range(args.steps):
-        flush.zero_()  # L2 flush between timed iterations (outside the per-step events)
-        ev[s][0].record(stream)
-        step_device()
-        ev[s][1].record(stream)
-        a, b = eng.last_kernel_ms()  # synchronises with this step
-        k1_ms.append(a)
-        k2_ms.append(b)
-    barrier()
+    total_ms, k1_ms, k2_ms, win = timed_steps(step_device, args.steps)
+    windows.append(win)
     launches = eng.launch_count() - launches0
-    total_ms = sum(e0.elapsed_time(e1) for e0, e1 in ev)
+    nocoll_ms = total_ms
+    if world > 1:
+        nocoll_ms, _, _, win = timed_steps(lambda: step_device(collective=False), args.steps)
+        windows.append(win)
 
     # ---- end to end through the public host-buffer API -----------------------------------------
-    llh_h = torch.empty((B, 1), dtype=torch.float64).pin_memory()
-    status_h = torch.empty((B,), dtype=torch.int32).pin_memory()
-    bufs = {"llh": llh_h.numpy(), "status": status_h.numpy()}
-    p_np = params_h.numpy()
+    shard = ShardedEvaluator(eng, dev, B, 1, want_jafs=True)
     for _ in range(max(1, args.warmup)):
-        eng.evaluate(p_np, model=mid, flags=flags, want=("status",), buffers=bufs)
-    barrier()
-    ee = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    for s in range(args.steps):
-        flush.zero_()
-        ee[s][0].record(stream)
-        eng.evaluate(p_np, model=mid, flags=flags, want=("status",), buffers=bufs)
-        ee[s][1].record(stream)
-    barrier()
-    e2e_ms = sum(e0.elapsed_time(e1) for e0, e1 in ee)
-    clocks = sampler.stop(t_load0, time.monotonic()) if rank == 0 else None
+        shard.evaluate(params_h, mid, flags)
+    e2e_ms, _, _, win = timed_steps(lambda: shard.evaluate(params_h, mid, flags), args.steps)
+    windows.append(win)
+    assert torch.equal(shard.llh_all_h[rank::world] if world > 1 else shard.llh_all_h, llh_d.cpu())  # same numbers both ways
 
     ok_frac = float((status_d == 0).float().mean().item())
     terms_mean = float(terms_d.double().mean().item())
-    t = torch.tensor([total_ms, e2e_ms], dtype=torch.float64, device=dev)
+
+    # ---- throughput vs batch size (B = 2, 64, 4096, 65536) -----------------
+    sweep = []
+    for n in (2, 64, 4096, 65536):
+        if n > B:
+            continue
+        for _ in range(3):
+            step_device(n)
+        ms, a, b, win = timed_steps(lambda n=n: step_device(n), 10)
+        windows.append(win)
+        sweep.append({"B_per_gpu": n, "ms_per_step": ms / 10, "evals_per_s": world * n * 10 / (ms * 1e-3),
+                      "kernel_ms": {"misti_correct_kernel": sum(a) / len(a), "misti_jsfs_kernel": sum(b) / len(b)}})
+
+    # ---- time to fit ---------------------------------------------------------------------------
+    t_fit0 = time.monotonic()
+    ttf = None if args.skip_fits else time_to_fit(args, eng, dev, world, rank, barrier, stream)
+    windows.append((t_fit0, time.monotonic()))
+    clocks = sampler.stop(windows) if rank == 0 else None
+
+    t = torch.tensor([total_ms, e2e_ms, nocoll_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        # the only data-path collective of the workload: gather the small likelihood vectors to every rank
-        gathered = torch.empty((world * B, 1), dtype=torch.float64, device=dev)
-        dist.all_gather_into_tensor(gathered, llh_d)
-    total_ms, e2e_ms = float(t[0].item()), float(t[1].item())
+    total_ms, e2e_ms, nocoll_ms = (float(v) for v in t.tolist())
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -280,80 +443,76 @@ def run_gpu(args):
     value = world * B * args.steps / (total_ms * 1e-3)
     e2e_value = world * B * args.steps / (e2e_ms * 1e-3)
     k1, k2 = sum(k1_ms) / len(k1_ms), sum(k2_ms) / len(k2_ms)
-    dom = "misti_jsfs_kernel" if k2 >= k1 else "misti_correct_kernel"
     with open(FP64_PEAK_FILE) as f:
         peaks = json.load(f)
     peak = peaks["dfma_tflops"]  # the executed kernels are DFMA code
-    # One evaluation = one item through BOTH kernels (correction chain, then JSFS + likelihood); the algorithmic figure of
-    # SURVEY 8d belongs to the evaluation, so it is set against the device time of the pair.
-    pair_ms = k1 + k2
-    dense_tflops = F_DENSE * B / (pair_ms * 1e-3) / 1e12
-    k2_flops = F_TERM * terms_mean  # counted by the kernel: mat-vec terms (a zero-migration run counts as one)
-    k1_flops, k1_src = None, None
-    if os.path.exists(EXEC_FLOPS_FILE):
+    ex = {}
+    if EXEC_FLOPS_FILE:
         with open(EXEC_FLOPS_FILE) as f:
             ex = json.load(f)
-        k1_flops = ex["misti_correct_kernel"]["flops_per_item"]
-        k1_src = "profiles/r01_executed_flops.json (ncu SASS instruction counts of this workload: thread-level 2*DFMA + DMUL + DADD)"
-    exec_flops = k2_flops + (k1_flops or 0.0)
-    exec_tflops = exec_flops * B / (pair_ms * 1e-3) / 1e12
-    roofline = {"bound": "fp64", "kernel": "misti_correct_kernel + misti_jsfs_kernel (one evaluation = both; longer one: %s)" % dom,
-                "achieved": dense_tflops, "peak": peak, "unit": "TFLOP/s", "frac": dense_tflops / peak, "traffic": DRAM_TRAFFIC,
-                "note": "achieved = dense-equivalent algorithmic FLOPs of SURVEY 8d (%.1f MFLOP/eval: Pade-13 + Van Loan on 45x45 / "
-                        "9x9) / device time of the kernel pair; the path instead runs closed forms for zero-migration runs and the "
-                        "post-split tail and a sparse uniformisation for the intervals with migration, so frac >> 1 is expected; "
-                        "'executed' is what the FP64 pipe really did; traffic = dram bytes read + written per launch pair "
-                        "(ncu --set full, profiles/)" % (F_DENSE / 1e6),
-                "executed": {"tflops": exec_tflops, "frac": exec_tflops / peak, "flops_per_eval": exec_flops,
-                             "misti_jsfs_kernel": {"flops_per_eval": k2_flops, "terms_per_eval": terms_mean,
-                                                   "tflops": k2_flops * B / (k2 * 1e-3) / 1e12,
-                                                   "frac": k2_flops * B / (k2 * 1e-3) / 1e12 / peak},
-                             "misti_correct_kernel": None if k1_flops is None else {
-                                 "flops_per_eval": k1_flops, "tflops": k1_flops * B / (k1 * 1e-3) / 1e12,
-                                 "frac": k1_flops * B / (k1 * 1e-3) / 1e12 / peak, "source": k1_src}},
-                "kernel_ms": {"misti_correct_kernel": k1, "misti_jsfs_kernel": k2},
+    k1_flops = ex.get("misti_correct_kernel", {}).get("flops_per_item")
+    k2_flops = ex.get("misti_jsfs_kernel", {}).get("flops_per_item")
+    src = os.path.relpath(EXEC_FLOPS_FILE, ROOT) if EXEC_FLOPS_FILE else None
+
+    def kernel_entry(name, ms, flops, bound):
+        tf = None if flops is None else flops * B / (ms * 1e-3) / 1e12
+        return {"kernel": name, "ms": ms, "flops_per_eval_executed": flops, "tflops": tf, "frac_of_fp64_peak": None if tf is None else tf / peak,
+                "bound": bound}
+    dom_is_k1 = k1 >= k2
+    kernels = {"misti_correct_kernel": kernel_entry("misti_correct_kernel", k1, k1_flops, "latency of one thread's serial FP64 chain "
+                                                    "(one wave, 3.5 warps per scheduler; ncu: issue slots 38 %, stalls long scoreboard / fixed latency)"),
+               "misti_jsfs_kernel": kernel_entry("misti_jsfs_kernel (+ misti_stiff_kernel, nothing parked)", k2, k2_flops,
+                                                 "shared-memory / shuffle pipe (ncu: 81 % of peak), FP64 pipe 32 %")}
+    dom = kernels["misti_correct_kernel" if dom_is_k1 else "misti_jsfs_kernel"]
+    tr = ex.get("dram_bytes", {}).get("misti_correct_kernel" if dom_is_k1 else "misti_jsfs_kernel")
+    traffic = None if not tr else tr["read"] + tr["write"]  # dram__bytes_read.sum + dram__bytes_write.sum of that kernel, one launch
+    alg_bytes = B * (8 + 8 + 56 + 4)  # per item: parameter in, llh + spectrum + status out
+    roofline = {"bound": "fp64", "kernel": dom["kernel"], "achieved": dom["tflops"], "peak": peak, "unit": "TFLOP/s",
+                "frac": dom["frac_of_fp64_peak"], "traffic": traffic,
+                "note": "dominant kernel: FP64 operations it EXECUTED (thread-level 2*DFMA + DMUL + DADD from the SASS page of the "
+                        "committed ncu capture, %s) x items / its CUDA-event time, against the measured DFMA peak; the kernel is not "
+                        "at a throughput roof: see `kernels[...].bound` (what ncu shows)" % src,
+                "kernels": kernels,
+                "pair": {"ms": k1 + k2, "tflops": None if None in (k1_flops, k2_flops) else (k1_flops + k2_flops) * B / ((k1 + k2) * 1e-3) / 1e12,
+                         "frac_of_fp64_peak": None if None in (k1_flops, k2_flops) else (k1_flops + k2_flops) * B / ((k1 + k2) * 1e-3) / 1e12 / peak},
+                "dense_equivalent": {"flops_per_eval": F_DENSE, "tflops": F_DENSE * B / ((k1 + k2) * 1e-3) / 1e12,
+                                     "frac_of_fp64_peak": F_DENSE * B / ((k1 + k2) * 1e-3) / 1e12 / peak,
+                                     "note": "SURVEY 8d's dense formulation (Pade-13 + Van Loan on 45x45 / 9x9) over the kernel pair: not a "
+                                             "utilisation -- the path runs closed forms and a sparse uniformisation, ~440x fewer FLOPs"},
+                "hbm": {"algorithmic_bytes_per_step": alg_bytes, "achieved_gbs": alg_bytes / ((k1 + k2) * 1e-3) / 1e9,
+                        "peak_gbs": _measured_hbm(), "note": "HBM is not a bound of this path"},
+                "terms_per_eval": terms_mean,
                 "peak_source": "profiles/r01_fp64_peak.json (tools/fp64_peak.cu on this pool's B200: DFMA %.1f, DMMA %.1f, cuBLAS DGEMM "
                                "%.1f TFLOP/s; MEASURED_PEAKS.json has no FP64 entry)" % (peaks["dfma_tflops"], peaks["dmma_tflops"],
                                                                                           peaks["cublas_dgemm_tflops"])}
     cpu = None
     if world == 1 and not args.skip_cpu:
         cores = os.cpu_count() or 1
-        n = 128 * cores
+        kind = cpu_kind()
+        n = (6 if kind == "reference" else 128) * cores
         rate, dt = cpu_rate(n, cores)
-        cpu = {"value": rate, "unit": "evals/s", "cores": cores, "kind": "port",
-               "sample": "%d of the batch's parameter vectors through oracle/misti_oracle.py (numpy/scipy port of the reference "
-                         "path), %d worker processes, %.1f s" % (n, cores, dt)}
-    # second half of the BASELINE metric: time to fit.  One Nelder-Mead fit of the bench model (MiSTI.py ... -mi 2 5 12 0.8 1
-    # --cpfit, tol 1e-4) stepped on the device, next to the same fit by the CPU oracle (scipy Nelder-Mead, one core).
-    ttf = None
-    if world == 1 and not args.skip_cpu:
-        import numpy as np
-        x0, one, zero = np.array([[BAND[3]]]), np.array([mid], dtype=np.int32), np.zeros(1, dtype=np.int32)
-        eng.nelder_mead(x0, one, zero, flags=flags, xatol=1e-4, fatol=1e-4, maxiter=1000)
-        t0 = time.perf_counter()
-        fit = eng.nelder_mead(x0, one, zero, flags=flags, xatol=1e-4, fatol=1e-4, maxiter=1000)
-        gpu_s = time.perf_counter() - t0
-        from oracle.misti_oracle import OracleModel
-        om = OracleModel(ds["times"], ds["lambdas"], ds["sfs"], SPLIT_T, [BAND], [], cpfit=True, smooth=True, unfolded=True)
-        t0 = time.perf_counter()
-        ref = om.solve(1e-4)
-        cpu_s = time.perf_counter() - t0
-        ref_x, ref_llh = ref[0], ref[1]
-        ttf = {"config": "config2: one Nelder-Mead fit of the optimised band (tol 1e-4, start 0.8)", "gpu_s": gpu_s,
-               "gpu_x": fit["x"][0].tolist(), "gpu_llh": float(-fit["fun"][0]), "gpu_nfev": int(fit["nfev"][0]),
-               "gpu_rounds_of_launches": int(fit["launches"]), "cpu_s": cpu_s, "cpu_kind": "port", "cpu_cores": 1,
-               "cpu_x": [float(v) for v in ref_x], "cpu_llh": float(ref_llh)}
+        cpu = {"value": rate, "unit": "evals/s", "cores": cores, "kind": kind,
+               "sample": "%d of the batch's parameter vectors through %s, %d worker processes, %.1f s" % (n, cpu_path_text(), cores, dt)}
+    d2h = world * B * 8 + B * 56 + B * 4
     line = {"metric": METRIC, "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic",
-            "config": {"workload": workload_name(B), "l2": "256 MiB buffer rewritten between timed iterations", "ok_fraction": ok_frac,
-                       "parallelism": "independent items sharded across ranks; all_gather of llh only"},
-            "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": B * 8, "d2h_bytes_per_step": B * 8 + B * 4,
-                    "ms_per_step": e2e_ms / args.steps},
-            "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "time_to_fit": ttf, "clocks": clocks}
+            "data": "synthetic", "config": bench_config(B), "ok_fraction": ok_frac,
+            "value_no_collective": world * B * args.steps / (nocoll_ms * 1e-3),
+            "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": B * 8, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms / args.steps,
+                    "returns": "llh of every item of the job (all-gathered at N > 1), expected JSFS [7] and status of this rank's items"},
+            "gpu_launches": launches, "roofline": roofline, "batch_sweep": sweep, "cpu_baseline": cpu, "time_to_fit": ttf, "clocks": clocks}
     _emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def _measured_hbm():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f).get("hbm_gbs")
+    except (OSError, ValueError):
+        return 6650.0  # B200_PROFILING.md fallback
 
 
 def main():
@@ -363,7 +522,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=65536, help="parameter vectors per GPU per step")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--skip-cpu", action="store_true", help="omit the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--skip-cpu", action="store_true", help="omit the CPU legs (profiling runs)")
+    ap.add_argument("--skip-fits", action="store_true", help="omit the time-to-fit legs (profiling runs)")
+    ap.add_argument("--walkers", type=int, default=1024, help="basin-hopping walkers per GPU (config 3)")
+    ap.add_argument("--fit-niter", type=int, default=100, help="basin-hopping hops per walker (config 3; the reference: 100)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     # Exactly ONE line goes to stdout: while the benchmark runs, file descriptor 1 points to stderr (NCCL prints its

@@ -52,25 +52,30 @@ static __device__ const unsigned char d_w8[7][8] = MISTI_W8_INIT;
 // item, all running the same chain on the same data, which share out the residual evaluations of a solver round
 // (misti::eval_fj); results are bit-identical to the one-thread variant, the serial chain is shorter.
 // ------------------------------------------------------------------------------------------------
-template <int MINB, bool COOP>
+// FIT = the variant the on-device optimiser launches: item count and item list on the device, interruptible chains
+template <int MINB, bool COOP, bool FIT>
 __global__ void __launch_bounds__(kCorrectThreads, MINB)
 misti_correct_kernel(int B, int P, const double* __restrict__ params, const int* __restrict__ model_ids, int model_default,
                      const ModelDesc* __restrict__ models, const double* __restrict__ times, const double* __restrict__ lh,
                      const double* __restrict__ gaux, const unsigned* __restrict__ cls_all, unsigned flags, double mixtureTH, const double* __restrict__ lc_inject, int numT_max, double* lc,
                      long stride, double* __restrict__ cpost, double* pr_out, int* __restrict__ status, int* __restrict__ nfev,
                      double* __restrict__ rec, int seg_cap, int* __restrict__ nseg, int* __restrict__ counters, int defer_post,
-                     int n_models, int* __restrict__ solve_trace, const int* __restrict__ count_ptr, int regime) {
+                     int n_models, int* __restrict__ solve_trace, const int* __restrict__ count_ptr, int regime,
+                     const int* __restrict__ item_list, misti::ChainCkpt* __restrict__ ckpt, int* __restrict__ slice_ctl, int yield_below) {
     // count_ptr (nullable): the number of items lives on the device (the on-device optimiser packs the points of a round
     // behind a counter) and B is only the capacity the grid was sized for.  regime: 0 = run; 1 / 2 = this launch is one of
     // the pair (four lanes per item | one thread per item) of which only the variant that suits the round's size runs.
-    if (count_ptr) {
+    if (FIT && count_ptr) {
         const int n = *count_ptr;
         if ((regime == 1 && n > kCoopMaxItems) || (regime == 2 && n <= kCoopMaxItems)) return;
         B = n < B ? n : B;
     }
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
     if (gtid < 8) counters[gtid] = 0;  // work and park counters of the two kernels that follow in the stream
-    const int b = COOP ? gtid >> 2 : gtid;
+    // item_list (nullable): the launch covers the items item_list[0 .. B) -- the on-device optimiser keeps an item's scratch
+    // (rates, records, checkpoint) at a fixed index while the list of items that run in a round is packed
+    const int slot = COOP ? gtid >> 2 : gtid;
+    const int b = (FIT && item_list && slot < B) ? item_list[slot] : slot;
     // one model for the whole batch (the usual case): its descriptor is staged in shared memory once per block
     __shared__ ModelDesc smd;
     if (!model_ids) {
@@ -79,7 +84,7 @@ misti_correct_kernel(int B, int P, const double* __restrict__ params, const int*
         for (int i = threadIdx.x; i < (int)(sizeof(ModelDesc) / sizeof(int)); i += blockDim.x) dst[i] = src[i];
         __syncthreads();
     }
-    if (b >= B) return;
+    if (slot >= B) return;
     if (model_ids && (unsigned)model_ids[b] >= (unsigned)n_models) {  // id -1: an empty slot of the on-device optimiser; any
         // other id outside the registered models (device-pointer calls are not validated on the host) is skipped as well
         nseg[b] = 0;
@@ -114,8 +119,20 @@ misti_correct_kernel(int B, int P, const double* __restrict__ params, const int*
         if (trace && (!COOP || (gtid & 3) == 0))
             for (int t = 0; t < numT_max; ++t) { trace[2 * t] = 0; trace[2 * t + 1] = misti::kNoSolve; }
         if (COOP && (gtid & 3) != 0) trace = nullptr;  // the four lanes of an item hold the same values: one of them writes
+        // inside the on-device optimiser the chain may yield at an interval boundary when its time slice is used up (ChainCkpt)
+        misti::ChainResume rs;
+        rs.ck = ckpt ? ckpt + b : nullptr;
+        // slice_ctl: [0] the time slice in microseconds (adapted by the optimiser between rounds), [1] / [2] how many items of
+        // this round ran to the end / were interrupted
+        rs.budget_ns = (ckpt && b < yield_below) ? 1000LL * slice_ctl[0] : 0;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(rs.t_start));
         st = misti::correct_lambdas_item<COOP>(md, tt, ll, par, flags, mixtureTH, lcb, kPitch, stride, pr, &nf, ga, cp, &cp_done, cls,
-                                               defer_post ? nc : nullptr, trace);
+                                               defer_post ? nc : nullptr, trace, ckpt ? &rs : nullptr);
+        if (st == MISTI_PENDING) {  // interrupted: the checkpoint is written; the item runs on in the next round
+            if (!COOP || (gtid & 3) == 0) { status[b] = MISTI_PENDING; atomicAdd(slice_ctl + 2, 1); }
+            return;
+        }
+        if (ckpt && (!COOP || (gtid & 3) == 0)) { ckpt[b].active = 0; atomicAdd(slice_ctl + 1, 1); }
         if (defer_post && cp_done) cp[0] = exp(nc[1] - nc[0]);
     }
     int ns = 0;
@@ -201,7 +218,8 @@ misti_jsfs_kernel(int B, int P, const double* __restrict__ params, const int* __
                   const ModelDesc* __restrict__ models, const double* __restrict__ rec, int seg_cap, const int* __restrict__ nseg,
                   long stride, const double* __restrict__ cpost, ItemOut out, misti::Cont* __restrict__ conts,
                   int* __restrict__ park_list, int* __restrict__ park_count, int* __restrict__ work_counter,
-                  const double* __restrict__ post_tab, const double* __restrict__ lh, const int* __restrict__ count_ptr) {
+                  const double* __restrict__ post_tab, const double* __restrict__ lh, const int* __restrict__ count_ptr,
+                  const int* __restrict__ item_list) {
     if (count_ptr) {  // the number of items lives on the device (see misti_correct_kernel)
         const int n = *count_ptr;
         B = n < B ? n : B;
@@ -235,7 +253,8 @@ misti_jsfs_kernel(int B, int P, const double* __restrict__ params, const int* __
         i0 = __shfl_sync(0xffffffffu, i0, 0);
         if (i0 >= B) break;
         const bool has = i0 + (half & 1) < B;
-        const int b = has ? i0 + (half & 1) : B - 1;
+        const int slot = has ? i0 + (half & 1) : B - 1;
+        const int b = item_list ? item_list[slot] : slot;  // see misti_correct_kernel
         int st = out.status[b];
         // an item the correction kernel skipped (model id outside the registered models) runs along inactive
         const ModelDesc& md = models[st == MISTI_SKIPPED ? 0 : (model_ids ? model_ids[b] : model_default)];
@@ -693,7 +712,8 @@ struct FitState {
     long long *iters, *fcalls;   // [S]
     int *status, *phase;         // [S]
     const int *model, *row;      // [S] the pair each simplex fits
-    int *first, *look;           // [S] where the simplex's points of this round start in the batch; look-ahead used
+    int *first, *cnt, *look;     // [S] the simplex's points of the current step: first item, how many; look-ahead used
+    int *waiting;                // [S] some of them were interrupted in the correction kernel and run on (ChainCkpt)
     // walkers (null for plain fits)
     double *bh_x, *bh_best_x;    // [S][N]
     double *bh_energy, *bh_best_f, *bh_step;
@@ -709,17 +729,37 @@ enum { FC_ITEMS = 0,        // items packed in the current round (read by the ev
        FC_RUN1 = 3,
        FC_ROUNDS_USED = 4,  // rounds that evaluated something
        FC_LAST = 5,         // items of the last completed round (0 = every simplex has ended)
-       FC_POINTS_LO = 6, FC_POINTS_HI = 7,  // all items evaluated so far (64 bits)
-       FC_N = 8 };
+       FC_POINTS_LO = 6, FC_POINTS_HI = 7,  // all items evaluated so far (64 bits; an interrupted item counts once per slice)
+       FC_LOOKBASE = 8,     // items handed out in the look-ahead region in the current round
+       FC_SLICE_US = 9,     // time slice of the correction chains (ChainCkpt), adapted between rounds
+       FC_SLICE_DONE = 10, FC_SLICE_PEND = 11,  // chains of the current round that ran to the end / were interrupted
+       FC_SLICE_MIN = 12,
+       FC_N = 16 };
 
 constexpr int kFitMaxPts = 64 * 4 > 17 * 16 ? 64 * 4 : 17 * 16;  // doubles one simplex can submit per round
 
 __global__ void misti_fit_propose_kernel(int S, misti::NmConfig cfg, misti::BhConfig bh, FitState st, double* __restrict__ params,
-                                         int* __restrict__ item_model, int* __restrict__ item_row, int* __restrict__ fc,
-                                         int look_max_items, int cap_items) {
+                                         int* __restrict__ item_model, int* __restrict__ item_row, int* __restrict__ item_list,
+                                         const int* __restrict__ item_status, int* __restrict__ fc, int look_max_items, int cap_list) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= S) return;
     const int N = cfg.N;
+    const int round = fc[FC_ROUND];
+    const int slots_plain = misti::nm_slots(N, false);
+    if (st.waiting[s]) {
+        // some points of the simplex's current step were interrupted in the correction kernel (ChainCkpt): they run on, the
+        // simplex waits -- only ITS step takes longer, the other simplices go on at their own pace
+        int n = 0;
+        for (int j = 0; j < st.cnt[s]; ++j) n += item_status[st.first[s] + j] == MISTI_PENDING;
+        const int at = atomicAdd(fc + FC_ITEMS, n);
+        if (at + n <= cap_list) {
+            int k = 0;
+            for (int j = 0; j < st.cnt[s]; ++j)
+                if (item_status[st.first[s] + j] == MISTI_PENDING) item_list[at + k++] = st.first[s] + j;
+        }
+        atomicAdd(fc + FC_RUN0 + ((round + 1) & 1), 1);
+        return;
+    }
     double* sim = st.sim + (long)s * (N + 1) * N;
     double* fsim = st.fsim + (long)s * (N + 1);
     if (bh.niter >= 0 && st.phase[s] == misti::NM_DONE && !st.bh_done[s]) {
@@ -731,9 +771,8 @@ __global__ void misti_fit_propose_kernel(int S, misti::NmConfig cfg, misti::BhCo
         w.hop = st.bh_hop + s; w.rng = st.rng + s;
         misti::bh_advance(bh, N, w, sim, fsim, st.iters + s, st.fcalls + s, st.status + s, st.phase + s);
     }
-    if (st.phase[s] == misti::NM_DONE) { st.first[s] = -1; return; }
+    if (st.phase[s] == misti::NM_DONE) { st.first[s] = -1; st.cnt[s] = 0; return; }
     // look-ahead while the simplices that ran in the previous round are few (the count only ever falls)
-    const int round = fc[FC_ROUND];
     const int running_prev = round == 0 ? S : fc[FC_RUN0 + (round & 1)];
     misti::NmConfig c = cfg;
     c.lookahead = cfg.lookahead && N <= misti::kNmLookaheadMaxN && (long)running_prev * misti::nm_slots(N, true) <= look_max_items;
@@ -741,30 +780,40 @@ __global__ void misti_fit_propose_kernel(int S, misti::NmConfig cfg, misti::BhCo
     double pts[kFitMaxPts];
     const int n = misti::nm_propose(c, sim, fsim, st.iters + s, st.fcalls + s, st.status + s, st.phase + s, pts);
     st.look[s] = c.lookahead;
-    if (n <= 0) { st.first[s] = -1; return; }
-    const int base = atomicAdd(fc + FC_ITEMS, n);
-    if (base + n > cap_items) { st.first[s] = -1; return; }  // cannot happen: the capacity covers every simplex without look-ahead
+    if (n <= 0) { st.first[s] = -1; st.cnt[s] = 0; return; }
+    // where the points live: a simplex's own slots (fixed: an interrupted item keeps its scratch across rounds), or -- the
+    // 4 (3N + 4) points of a look-ahead step -- a range of the shared look-ahead region behind them
+    const int base = c.lookahead ? S * slots_plain + atomicAdd(fc + FC_LOOKBASE, n) : s * slots_plain;
+    const int at = atomicAdd(fc + FC_ITEMS, n);
+    if (at + n > cap_list || (c.lookahead && base + n > S * slots_plain + look_max_items)) { st.first[s] = -1; st.cnt[s] = 0; return; }  // cannot happen
     st.first[s] = base;
+    st.cnt[s] = n;
     atomicAdd(fc + FC_RUN0 + ((round + 1) & 1), 1);
     const int model = st.model[s], row = st.row[s];
     for (int j = 0; j < n; ++j) {
         for (int k = 0; k < N; ++k) params[(long)(base + j) * N + k] = pts[j * N + k];
         item_model[base + j] = model;
         item_row[base + j] = row;
+        item_list[at + j] = base + j;
     }
 }
 
 __global__ void misti_fit_apply_kernel(int S, misti::NmConfig cfg, FitState st, const double* __restrict__ params,
-                                       const double* __restrict__ llh, int* __restrict__ fc, int* __restrict__ h_mirror) {
+                                       const double* __restrict__ llh, const int* __restrict__ item_status, int* __restrict__ fc) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s < S && st.first[s] >= 0) {
-        const int N = cfg.N;
-        misti::NmConfig c = cfg;
-        c.lookahead = st.look[s];
-        c.slots = misti::nm_slots(N, c.lookahead != 0);
-        const long b0 = st.first[s];
-        misti::nm_apply(c, st.sim + (long)s * (N + 1) * N, st.fsim + (long)s * (N + 1), st.iters + s, st.fcalls + s, st.status + s,
-                        st.phase + s, params + b0 * N, llh + b0, true);  // the objective is -llh
+        bool pending = false;
+        for (int j = 0; j < st.cnt[s]; ++j) pending |= item_status[st.first[s] + j] == MISTI_PENDING;
+        st.waiting[s] = pending ? 1 : 0;
+        if (!pending) {
+            const int N = cfg.N;
+            misti::NmConfig c = cfg;
+            c.lookahead = st.look[s];
+            c.slots = misti::nm_slots(N, c.lookahead != 0);
+            const long b0 = st.first[s];
+            misti::nm_apply(c, st.sim + (long)s * (N + 1) * N, st.fsim + (long)s * (N + 1), st.iters + s, st.fcalls + s, st.status + s,
+                            st.phase + s, params + b0 * N, llh + b0, true);  // the objective is -llh
+        }
     }
     if (s == 0) {  // next round (the counters are not read by the other threads of this kernel)
         const int n = fc[FC_ITEMS], r = fc[FC_ROUND];
@@ -775,11 +824,21 @@ __global__ void misti_fit_apply_kernel(int S, misti::NmConfig cfg, FitState st, 
             fc[FC_POINTS_LO] = (int)(lo + add);
             if (lo + add < lo) fc[FC_POINTS_HI] += 1;
         }
+        // The time slice follows the work: when most chains of a round could not finish, the typical item is longer than the
+        // slice and cutting it only adds rounds -- double it; when nothing was cut, let it fall back slowly towards its
+        // minimum, so that an outlier (a run-away correction among ordinary ones) is cut again.
+        const int done = fc[FC_SLICE_DONE], pend = fc[FC_SLICE_PEND];
+        if (2 * pend > done + pend) fc[FC_SLICE_US] = fc[FC_SLICE_US] < (1 << 24) ? 2 * fc[FC_SLICE_US] : fc[FC_SLICE_US];
+        else if (pend == 0 && fc[FC_SLICE_US] > fc[FC_SLICE_MIN]) {
+            const int v = fc[FC_SLICE_US] - fc[FC_SLICE_US] / 8;
+            fc[FC_SLICE_US] = v > fc[FC_SLICE_MIN] ? v : fc[FC_SLICE_MIN];
+        }
+        fc[FC_SLICE_DONE] = 0;
+        fc[FC_SLICE_PEND] = 0;
         fc[FC_ITEMS] = 0;
+        fc[FC_LOOKBASE] = 0;
         fc[FC_RUN0 + (r & 1)] = 0;  // read by this round's propose step; the next round counts into it
         fc[FC_ROUND] = r + 1;
-        if (h_mirror)  // pinned host memory: the host polls it between graph launches
-            for (int i = 0; i < FC_N; ++i) ((volatile int*)h_mirror)[i] = fc[i];
     }
 }
 
@@ -846,6 +905,7 @@ struct misti_ctx {
     unsigned long long generation = 0;    // bumped whenever a device buffer moves or a launch argument of the kernels changes
     int nm_use_graph = 1;                 // tuning knob MISTI_NM_GRAPH
     int nm_rounds_per_graph = 4;          // rounds captured in one graph (tuning knob MISTI_NM_ROUNDS)
+    int fit_slice_us = 350;               // time slice of a correction chain inside the on-device optimiser (MISTI_FIT_SLICE_US)
     int nm_graph_launches = 0;            // kernel launches per round of the kept graph
     cudaEvent_t nm_ev[4] = {nullptr, nullptr, nullptr, nullptr};
     double* d_score = nullptr;      // scratch of misti_score_spectra
@@ -1044,6 +1104,7 @@ int misti_ctx_create(int device, void* stream, misti_ctx** out) {
     if (const char* e = getenv("MISTI_DEFER_POST")) ctx->defer_post = atoi(e);
     if (const char* e = getenv("MISTI_NM_LOOKAHEAD")) ctx->nm_lookahead = atoi(e);
     if (const char* e = getenv("MISTI_NM_GRAPH")) ctx->nm_use_graph = atoi(e);
+    if (const char* e = getenv("MISTI_FIT_SLICE_US")) { const int v = atoi(e); if (v >= 0) ctx->fit_slice_us = v; }
     if (const char* e = getenv("MISTI_NM_ROUNDS")) { const int v = atoi(e); if (v >= 1 && v <= 64) ctx->nm_rounds_per_graph = v; }
     if (const char* e = getenv("MISTI_MAX_CHUNK")) {
         const int v = atoi(e);
@@ -1225,7 +1286,8 @@ int misti_set_data(misti_ctx* ctx, int32_t R, const double* sfs, const double* l
 static int eval_chunk(misti_ctx* ctx, int B, int P, const double* d_params, const int* d_model_ids, int model_default,
                       unsigned flags, double mixture_th, const double* d_lc_inject, double* d_llh, double* d_jafs,
                       double* d_jafs_raw, double* d_lc_out, double* d_pr, int* d_status_out, int* d_nfev_out, int* d_terms,
-                      const int* d_row_ids, int* d_trace = nullptr, const int* d_count = nullptr, int defer_override = -1) {
+                      const int* d_row_ids, int* d_trace = nullptr, const int* d_count = nullptr, int defer_override = -1,
+                      const int* d_item_list = nullptr, misti::ChainCkpt* d_ckpt = nullptr, int* d_slice_ctl = nullptr, int yield_below = 0) {
     int rc;
     if ((rc = ensure_batch(ctx, (size_t)B))) return rc;
     const long stride = (long)ctx->cap;
@@ -1240,17 +1302,20 @@ static int eval_chunk(misti_ctx* ctx, int B, int P, const double* d_params, cons
     // small batches: four lanes per item (see misti_correct_kernel); the knob MISTI_CORRECT_COOP = 0 / 1 forces a variant.
     // With the item count on the device (d_count) both variants are launched and the one that suits the count runs.
     const bool coop = ctx->correct_coop < 0 ? B <= kCoopMaxItems : ctx->correct_coop != 0;
-#define MISTI_LAUNCH_CORRECT2(MINB, COOP, NTHREADS, REGIME)                                                              \
-    misti_correct_kernel<MINB, COOP><<<(unsigned)(((NTHREADS) + kCorrectThreads - 1) / kCorrectThreads), kCorrectThreads, 0, ctx->stream>>>( \
+#define MISTI_LAUNCH_CORRECT2(MINB, COOP, NTHREADS, REGIME) MISTI_LAUNCH_CORRECT3(MINB, COOP, false, NTHREADS, REGIME)
+#define MISTI_LAUNCH_CORRECT3(MINB, COOP, FIT, NTHREADS, REGIME)                                                         \
+    misti_correct_kernel<MINB, COOP, FIT><<<(unsigned)(((NTHREADS) + kCorrectThreads - 1) / kCorrectThreads), kCorrectThreads, 0, ctx->stream>>>( \
         B, P, d_params, d_model_ids, model_default, ctx->d_models, ctx->d_times, ctx->d_lh, ctx->d_gaux, ctx->d_cls, flags, mixture_th, \
         d_lc_inject, \
         numT_max, ctx->d_lc, stride, ctx->d_cpost, d_pr, ctx->d_status, ctx->d_nfev, ctx->d_rec, ctx->cap_seg, ctx->d_nseg, ctx->d_counts, \
-        defer_post, (int)ctx->h_models.size(), d_trace, d_count, REGIME)
+        defer_post, (int)ctx->h_models.size(), d_trace, d_count, REGIME, d_item_list, d_ckpt, d_slice_ctl, yield_below)
 #define MISTI_LAUNCH_CORRECT(MINB)                                                                                       \
-    if (d_count && ctx->correct_coop < 0) {                                                                              \
-        MISTI_LAUNCH_CORRECT2(MINB, true, 4L * (B < kCoopMaxItems ? B : kCoopMaxItems), 1);                              \
-        if (B > kCoopMaxItems) MISTI_LAUNCH_CORRECT2(MINB, false, (long)B, 2);                                           \
-    } else if (coop) MISTI_LAUNCH_CORRECT2(MINB, true, 4L * B, 0); else MISTI_LAUNCH_CORRECT2(MINB, false, (long)B, 0)
+    if (coop) MISTI_LAUNCH_CORRECT2(MINB, true, 4L * B, 0); else MISTI_LAUNCH_CORRECT2(MINB, false, (long)B, 0)
+    if (d_count) {  // the on-device optimiser: the pair of variants, of which the one that suits the round's item count runs
+        if (ctx->correct_coop != 0) MISTI_LAUNCH_CORRECT3(kCorrectMinBlocks, true, true, 4L * (B < kCoopMaxItems ? B : kCoopMaxItems), ctx->correct_coop < 0 ? 1 : 0);
+        if (ctx->correct_coop == 0 || (ctx->correct_coop < 0 && B > kCoopMaxItems))
+            MISTI_LAUNCH_CORRECT3(kCorrectMinBlocks, false, true, (long)B, ctx->correct_coop < 0 ? 2 : 0);
+    } else
     switch (ctx->correct_minb) {  // register budget per thread: 4 -> 255, 8 -> 128, 12 -> 80 (tuning knob MISTI_CORRECT_MINB)
         case 4: MISTI_LAUNCH_CORRECT(4); break;
         case 12: MISTI_LAUNCH_CORRECT(12); break;
@@ -1258,6 +1323,7 @@ static int eval_chunk(misti_ctx* ctx, int B, int P, const double* d_params, cons
     }
 #undef MISTI_LAUNCH_CORRECT
 #undef MISTI_LAUNCH_CORRECT2
+#undef MISTI_LAUNCH_CORRECT3
     CK(cudaGetLastError());
     CK(cudaEventRecord(ctx->ev[1], ctx->stream));
     int blocks = (B + 2 * kJsfsWarps - 1) / (2 * kJsfsWarps);
@@ -1273,7 +1339,7 @@ static int eval_chunk(misti_ctx* ctx, int B, int P, const double* d_params, cons
 #define MISTI_LAUNCH_JSFS2(MINB, DEFER)                                                                                    \
     misti_jsfs_kernel<MINB, DEFER><<<blocks, kJsfsWarps * 32, 0, ctx->stream>>>(                                           \
         B, P, d_params, d_model_ids, model_default, ctx->d_models, ctx->d_rec, ctx->cap_seg, ctx->d_nseg, stride, ctx->d_cpost, \
-        out, ctx->d_conts, ctx->d_queue[0], ctx->d_counts, ctx->d_counts + 4, ctx->d_post, ctx->d_lh, d_count)
+        out, ctx->d_conts, ctx->d_queue[0], ctx->d_counts, ctx->d_counts + 4, ctx->d_post, ctx->d_lh, d_count, d_item_list)
     switch (ctx->jsfs_minb) {  // register budget: 2 -> 255, 3 -> 168, 4 -> 128, 5 -> 96 (tuning knob MISTI_JSFS_MINB)
         case 2: MISTI_LAUNCH_JSFS(2); break;
         case 4: MISTI_LAUNCH_JSFS(4); break;
@@ -1471,12 +1537,15 @@ int misti_fit(misti_ctx* ctx, int32_t S, int32_t N, const double* x0, const int3
     bh.interval = walkers ? opts->interval : 1;
     bh.beta = opts->T != 0 ? 1.0 / opts->T : misti::kInf;
     bh.target = opts->target_accept_rate; bh.factor = opts->stepwise_factor; bh.stepsize0 = opts->stepsize;
-    // capacity of a round: every simplex without look-ahead, or the look-ahead budget
+    // items: every simplex has its own nm_slots(N) slots (fixed, so that an interrupted item keeps its scratch across
+    // rounds); behind them the region the look-ahead steps of the few simplices of a late round share
     const int look_max = kCoopMaxItems;
-    long cap = (long)S * misti::nm_slots(N, false);
-    if (cfg.lookahead && cap < look_max) cap = look_max;
+    const int stable_items = S * misti::nm_slots(N, false);
+    const long cap = (long)stable_items + (cfg.lookahead ? look_max : 0);
     if (cap > ctx->max_chunk) return fail(ctx, MISTI_E_ARG, "misti_fit: too many simplices for one call");
     const int B = (int)cap;
+    // time slice of the correction chain inside a round (tuning knob MISTI_FIT_SLICE_US; 0 = chains are never interrupted)
+    const long long budget_ns = (long long)ctx->fit_slice_us * 1000;
     // one block of device memory, carved up (8-byte items first)
     const size_t n_sim = (size_t)S * (N + 1) * N, n_fsim = (size_t)S * (N + 1);
     size_t off = 0;
@@ -1488,7 +1557,9 @@ int misti_fit(misti_ctx* ctx, int32_t S, int32_t N, const double* x0, const int3
                  o_bns = carve((size_t)S * 8), o_bna = carve((size_t)S * 8), o_bhp = carve((size_t)S * 8), o_rng = carve((size_t)S * 32),
                  o_st = carve((size_t)S * 4), o_ph = carve((size_t)S * 4), o_mod = carve((size_t)S * 4), o_row = carve((size_t)S * 4),
                  o_first = carve((size_t)S * 4), o_look = carve((size_t)S * 4), o_bok = carve((size_t)S * 4), o_bbok = carve((size_t)S * 4),
-                 o_bdn = carve((size_t)S * 4), o_bm = carve((size_t)B * 4), o_br = carve((size_t)B * 4), o_cnt = carve(FC_N * 4);
+                 o_bdn = carve((size_t)S * 4), o_bm = carve((size_t)B * 4), o_br = carve((size_t)B * 4), o_cnt = carve(FC_N * 4),
+                 o_ncnt = carve((size_t)S * 4), o_wait = carve((size_t)S * 4), o_list = carve((size_t)B * 4),
+                 o_ck = carve((size_t)B * sizeof(misti::ChainCkpt));
     if ((rc = ensure(ctx, &ctx->d_nm, &ctx->d_nm_cap, off))) return rc;
     if (!ctx->h_nm_counts) CK(cudaMallocHost((void**)&ctx->h_nm_counts, 4 * FC_N * sizeof(int)));
     for (int i = 0; i < 4; ++i)
@@ -1501,6 +1572,9 @@ int misti_fit(misti_ctx* ctx, int32_t S, int32_t N, const double* x0, const int3
     int* d_mod = (int*)(base + o_mod); int* d_row = (int*)(base + o_row);
     st.model = d_mod; st.row = d_row;
     st.first = (int*)(base + o_first); st.look = (int*)(base + o_look);
+    st.cnt = (int*)(base + o_ncnt); st.waiting = (int*)(base + o_wait);
+    int* d_list = (int*)(base + o_list);
+    misti::ChainCkpt* d_ck = budget_ns > 0 ? (misti::ChainCkpt*)(base + o_ck) : nullptr;
     st.bh_x = (double*)(base + o_bx); st.bh_best_x = (double*)(base + o_bbx); st.bh_energy = (double*)(base + o_be);
     st.bh_best_f = (double*)(base + o_bbf); st.bh_step = (double*)(base + o_bst);
     st.bh_ok = (int*)(base + o_bok); st.bh_best_ok = (int*)(base + o_bbok); st.bh_done = (int*)(base + o_bdn);
@@ -1523,6 +1597,11 @@ int misti_fit(misti_ctx* ctx, int32_t S, int32_t N, const double* x0, const int3
         CK(cudaMemcpyAsync(st.bh_step, steps.data(), (size_t)S * 8, cudaMemcpyHostToDevice, sm));
         CK(cudaStreamSynchronize(sm));  // `steps` goes out of scope
     }
+    if (budget_ns > 0) {
+        const int slice[4] = {ctx->fit_slice_us, 0, 0, ctx->fit_slice_us};
+        CK(cudaMemcpyAsync(d_fc + FC_SLICE_US, slice, sizeof(slice), cudaMemcpyHostToDevice, sm));
+        CK(cudaStreamSynchronize(sm));
+    }
     const unsigned eflags = (flags | MISTI_FLAG_DEVICE_PTRS);
     const int tb = 64, gb = (S + tb - 1) / tb;
     if ((rc = ensure_batch(ctx, (size_t)B))) return rc;  // no allocation inside a round (a round may be captured)
@@ -1531,12 +1610,12 @@ int misti_fit(misti_ctx* ctx, int32_t S, int32_t N, const double* x0, const int3
     const int defer = ctx->defer_post < 0 ? ((long)S * misti::nm_slots(N, false) <= kDeferPostMaxItems ? 1 : 0) : (ctx->defer_post != 0);
     // one round: propose (packs the points behind the device-side counter), evaluate, apply
     auto round_body = [&]() -> int {
-        misti_fit_propose_kernel<<<gb, tb, 0, sm>>>(S, cfg, bh, st, d_par, d_bm, d_br, d_fc, look_max, B);
+        misti_fit_propose_kernel<<<gb, tb, 0, sm>>>(S, cfg, bh, st, d_par, d_bm, d_br, d_list, ctx->d_status, d_fc, look_max, B);
         CK(cudaGetLastError());
         int rc2 = eval_chunk(ctx, B, N, d_par, d_bm, -1, eflags, mixture_th, nullptr, d_llh, nullptr, nullptr, nullptr, nullptr,
-                             nullptr, nullptr, nullptr, d_br, nullptr, d_fc + FC_ITEMS, defer);
+                             nullptr, nullptr, nullptr, d_br, nullptr, d_fc + FC_ITEMS, defer, d_list, d_ck, d_fc + FC_SLICE_US, stable_items);
         if (rc2) return rc2;
-        misti_fit_apply_kernel<<<gb, tb, 0, sm>>>(S, cfg, st, d_par, d_llh, d_fc, nullptr);
+        misti_fit_apply_kernel<<<gb, tb, 0, sm>>>(S, cfg, st, d_par, d_llh, ctx->d_status, d_fc);
         CK(cudaGetLastError());
         return 0;
     };
@@ -1555,7 +1634,7 @@ int misti_fit(misti_ctx* ctx, int32_t S, int32_t N, const double* x0, const int3
                                                      (unsigned long long)cfg.maxiter, (unsigned long long)cfg.maxfev,
                                                      (unsigned long long)flags, mt_bits, (unsigned long long)(size_t)sm,
                                                      (unsigned long long)(long long)bh.niter, (unsigned long long)bh.interval, be_bits,
-                                                     ta_bits, fc_bits, (unsigned long long)defer, (unsigned long long)kRoundsPerGraph};
+                                                     ta_bits, fc_bits, (unsigned long long)defer, (unsigned long long)kRoundsPerGraph, (unsigned long long)budget_ns};
         if (ctx->nm_graph && key == ctx->nm_graph_key) {
             exec = ctx->nm_graph;
             launches_per_round = ctx->nm_graph_launches;
@@ -1581,10 +1660,35 @@ int misti_fit(misti_ctx* ctx, int32_t S, int32_t N, const double* x0, const int3
             ctx->launches = launches_before;  // nothing ran during the capture
         }
     }
-    // The host keeps two batches of rounds in flight and looks at the counters of the batch before: a last round that
-    // packed nothing ends the fit (the rounds queued behind it are empty and cost microseconds).
     volatile int* hc = ctx->h_nm_counts;
     int64_t rounds = 0, points = 0;
+    if (const char* trace_path = getenv("MISTI_FIT_TRACE")) {
+        // diagnostics: one round at a time, synchronised, with the device times of its kernels written to a file
+        // (round, items, correction kernel ms, JSFS + stiff kernels ms, wall ms of the round)
+        FILE* tf = fopen(trace_path, "a");
+        for (long r = 0; r < 10000000; ++r) {
+            cudaEvent_t e0, e1;
+            cudaEventCreate(&e0); cudaEventCreate(&e1);
+            CK(cudaEventRecord(e0, sm));
+            if ((rc = round_body())) return rc;
+            CK(cudaEventRecord(e1, sm));
+            int items = 0;
+            CK(cudaMemcpyAsync(ctx->h_nm_counts, d_fc, FC_N * sizeof(int), cudaMemcpyDeviceToHost, sm));
+            CK(cudaStreamSynchronize(sm));
+            items = hc[FC_LAST];
+            float k1 = 0, k2 = 0, all = 0;
+            cudaEventElapsedTime(&k1, ctx->ev[0], ctx->ev[1]);
+            cudaEventElapsedTime(&k2, ctx->ev[1], ctx->ev[2]);
+            cudaEventElapsedTime(&all, e0, e1);
+            cudaEventDestroy(e0); cudaEventDestroy(e1);
+            if (tf) fprintf(tf, "%ld %d %.4f %.4f %.4f\n", r, items, k1, k2, all);
+            if (items == 0) break;
+        }
+        if (tf) fclose(tf);
+        exec = nullptr;
+    } else
+    // The host keeps two batches of rounds in flight and looks at the counters of the batch before: a last round that
+    // packed nothing ends the fit (the rounds queued behind it are empty and cost microseconds).
     for (long g = 0;; ++g) {
         if (g >= 2) {
             CK(cudaEventSynchronize(ctx->nm_ev[(g - 2) & 3]));

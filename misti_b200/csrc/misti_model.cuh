@@ -155,6 +155,39 @@ inline void post_split_table(int numT, int splitT, const double* times, const do
         }
 }
 
+// Checkpoint of an interrupted correction chain (one per item, global memory).  The chain is strictly sequential and, where
+// the reference's own solver runs away (rates ~1e7: trust-region solves that spend their whole budget of 200 evaluations on
+// matrices that need 20 squarings), one item can take ten times as long as its neighbours; inside the on-device optimiser
+// such an item would hold up every simplex of the round.  There the chain may YIELD at an interval boundary once it has run
+// for its time slice: everything the next interval needs is the state below (the rates written so far stay where they are),
+// and the next round resumes it -- same instructions on the same data, so the result does not depend on where, or whether,
+// a chain was cut.
+struct ChainCkpt {
+    int active;        // 1 = interrupted: resume at interval t_next
+    int t_next, nfev;
+    int sr_k[2], sr_done[2];
+    double P0[6], sr_lam[2], sr_nc[2], sr_time[2];
+};
+struct ChainResume {
+    ChainCkpt* ck;
+    long long t_start, budget_ns;  // device clock at the start of this slice; <= 0: never yield
+};
+#define MISTI_PENDING 7  // internal (never leaves the optimiser): the item's chain was interrupted and resumes next round
+
+MISTI_HD inline bool chain_should_yield(const ChainResume* rs, bool coop) {
+#if defined(__CUDA_ARCH__)
+    if (!rs || rs->budget_ns <= 0) return false;
+    long long now;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
+    bool y = now - rs->t_start > rs->budget_ns;
+    if (coop) y = __shfl_sync(0xFu << (threadIdx.x & 28u), (int)y, threadIdx.x & 28u) != 0;  // the four lanes of an item agree
+    return y;
+#else
+    (void)rs; (void)coop;
+    return false;
+#endif
+}
+
 // lc is addressed as lc[(pitch*t+g)*stride] (pitch >= 2 values per interval); times[numT-1]; lh[numT][2].
 // Pr (nullable): [splitT+1][3][2] trajectory of the 3-state chains (MigrationInference.py:309,350).
 // gaux (nullable): [numT][kGridAux] per-interval constants of the grid (grid_aux_row).
@@ -173,7 +206,7 @@ MISTI_HD inline int correct_lambdas_item(const ModelDesc& md, const double* time
                                          unsigned flags, double mixtureTH, double* lc, int pitch, long stride, double* Pr,
                                          int* nfev_out, const double* gaux = nullptr, double* cpost = nullptr,
                                          bool* cpost_done = nullptr, const unsigned* cls = nullptr, double* nc_out = nullptr,
-                                         int* trace = nullptr) {
+                                         int* trace = nullptr, const ChainResume* rs = nullptr) {
     if (cpost_done) *cpost_done = false;
     const bool correct = flags & MISTI_FLAG_CORRECT, cpfit = flags & MISTI_FLAG_CPFIT;
     int nfev = 0;
@@ -192,6 +225,17 @@ MISTI_HD inline int correct_lambdas_item(const ModelDesc& md, const double* time
     const bool smooth = (flags & MISTI_FLAG_SMOOTH) != 0;
     struct SmoothRun { int k; bool done; double lam, nc, time; };
     SmoothRun sr0 = {0, !smooth, lh[0], 0.0, 0.0}, sr1 = {0, !smooth, lh[1], 0.0, 0.0};
+    int t_first = 0;
+    if (rs && rs->ck->active) {  // resume an interrupted chain (see ChainCkpt)
+        const ChainCkpt& k = *rs->ck;
+        t_first = k.t_next;
+        nfev = k.nfev;
+        for (int i = 0; i < 3; ++i) { st.P0[0][i] = k.P0[i]; st.P0[1][i] = k.P0[3 + i]; }
+        sr0.k = k.sr_k[0]; sr0.done = k.sr_done[0] != 0; sr0.lam = k.sr_lam[0]; sr0.nc = k.sr_nc[0]; sr0.time = k.sr_time[0];
+        sr1.k = k.sr_k[1]; sr1.done = k.sr_done[1] != 0; sr1.lam = k.sr_lam[1]; sr1.nc = k.sr_nc[1]; sr1.time = k.sr_time[1];
+        nc0 = (st.P0[0][0] + st.P0[0][1]) + st.P0[0][2];
+        nc1 = (st.P0[1][0] + st.P0[1][1]) + st.P0[1][2];
+    }
     auto smooth_step = [&](SmoothRun& r, int g, int t, double lcv) {
         if (r.done) return;
         const double lhv = lh[2 * t + g];
@@ -206,7 +250,23 @@ MISTI_HD inline int correct_lambdas_item(const ModelDesc& md, const double* time
         r.nc += lcv * times[t];
         r.time += times[t];
     };
-    for (int t = 0; t < splitT; ++t) {
+    for (int t = t_first; t < splitT; ++t) {
+        if (t > t_first && chain_should_yield(rs, COOP)) {  // time slice used up: park the chain at this interval boundary
+            ChainCkpt& k = *rs->ck;
+            bool writer = true;
+#if defined(__CUDA_ARCH__)
+            if (COOP) writer = (threadIdx.x & 3u) == 0;
+#endif
+            if (writer) {
+                k.t_next = t; k.nfev = nfev;
+                for (int i = 0; i < 3; ++i) { k.P0[i] = st.P0[0][i]; k.P0[3 + i] = st.P0[1][i]; }
+                k.sr_k[0] = sr0.k; k.sr_done[0] = sr0.done; k.sr_lam[0] = sr0.lam; k.sr_nc[0] = sr0.nc; k.sr_time[0] = sr0.time;
+                k.sr_k[1] = sr1.k; k.sr_done[1] = sr1.done; k.sr_lam[1] = sr1.lam; k.sr_nc[1] = sr1.nc; k.sr_time[1] = sr1.time;
+                k.active = 1;
+            }
+            *nfev_out = nfev;
+            return MISTI_PENDING;
+        }
         double mi_t[2], pu_t[2];
         interval_rates(md, cls, params, t, mi_t, pu_t);
         const double pu0 = pu_t[0], pu1 = pu_t[1];

@@ -18,33 +18,91 @@ def shard_sizes(n_items, world):
     return [(n_items - r + world - 1) // world for r in range(world)]
 
 
-def gather_rows(local_rows, n_items, group=None, device=None):
-    """All-gather per-item rows computed on each rank's shard back into item order on every rank.
-
-    local_rows: array [n_local, K] for the items shard_indices(n_items, rank, world), in that order.
-    Returns a numpy array [n_items, K].  Backend-agnostic: NCCL (tensors staged on `device`) or Gloo (CPU).
-    """
+def gather_rows_device(local, n_items, group=None):
+    """The collective of the path, device-resident: `local` is a torch tensor [n_local, K] ON THE DEVICE holding the rows of
+    the items shard_indices(n_items, rank, world); returns a device tensor [n_items, K] in item order on every rank (one
+    NCCL all-gather over NVLink and one strided device copy; nothing is staged through the host)."""
     import torch
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()):
-        return np.asarray(local_rows)
+        return local
     world, rank = dist.get_world_size(group), dist.get_rank(group)
-    local_rows = np.ascontiguousarray(local_rows, dtype=np.float64)
-    local_rows = local_rows.reshape(local_rows.shape[0], -1)
-    K = local_rows.shape[1]
     sizes = shard_sizes(n_items, world)
-    assert local_rows.shape[0] == sizes[rank], "shard size mismatch"
+    assert local.shape[0] == sizes[rank], "shard size mismatch"
+    K = local.shape[1]
     pad = max(sizes)
-    dev = torch.device(device) if device is not None else torch.device("cpu")
-    send = torch.zeros((pad, K), dtype=torch.float64, device=dev)
-    send[:sizes[rank]] = torch.from_numpy(local_rows).to(dev)
-    recv = torch.empty((world * pad, K), dtype=torch.float64, device=dev)
-    dist.all_gather_into_tensor(recv, send, group=group)
-    recv = recv.cpu().numpy().reshape(world, pad, K)
-    out = np.empty((n_items, K))
+    if sizes[rank] == pad:
+        send = local.contiguous()
+    else:
+        send = torch.zeros((pad, K), dtype=local.dtype, device=local.device)
+        send[:sizes[rank]] = local
+    recv = torch.empty((world, pad, K), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(recv.view(world * pad, K), send, group=group)
+    if n_items == world * pad:  # every shard full: item i = recv[i % world, i // world]
+        return recv.permute(1, 0, 2).reshape(n_items, K)
+    out = torch.empty((n_items, K), dtype=local.dtype, device=local.device)
     for r in range(world):
         out[r::world] = recv[r, :sizes[r]]
     return out
+
+
+def gather_rows(local_rows, n_items, group=None, device=None):
+    """All-gather per-item rows computed on each rank's shard back into item order on every rank.
+
+    local_rows: array [n_local, K] for the items shard_indices(n_items, rank, world), in that order -- a numpy array
+    (returned as numpy [n_items, K]; with NCCL it crosses to `device` for the collective) or a torch tensor on the device
+    (returned as a device tensor, see gather_rows_device).  Backend-agnostic: NCCL or Gloo (CPU)."""
+    import torch
+    import torch.distributed as dist
+    if isinstance(local_rows, torch.Tensor):
+        return gather_rows_device(local_rows.reshape(local_rows.shape[0], -1), n_items, group=group)
+    if not (dist.is_available() and dist.is_initialized()):
+        return np.asarray(local_rows)
+    local_rows = np.ascontiguousarray(local_rows, dtype=np.float64)
+    local_rows = local_rows.reshape(local_rows.shape[0], -1)
+    dev = torch.device(device) if device is not None else torch.device("cpu")
+    return gather_rows_device(torch.from_numpy(local_rows).to(dev), n_items, group=group).cpu().numpy()
+
+
+class ShardedEvaluator:
+    """The batched objective over the ranks of a job, device-resident: every rank evaluates its shard of a global batch on
+    its own GPU (Engine.evaluate_device on its torch stream) and ONE all-gather brings the likelihood rows to every rank
+     -- the call an optimiser that lives on every rank makes per step.  Buffers are allocated once."""
+
+    def __init__(self, engine, device, n_local, P, group=None, want_jafs=False):
+        import torch
+        import torch.distributed as dist
+        self.engine, self.group, self.device = engine, group, torch.device(device)
+        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        self.n_local, self.P, self.R = int(n_local), int(P), engine.R
+        self.params_d = torch.empty((n_local, max(P, 1)), dtype=torch.float64, device=self.device)
+        self.llh_d = torch.empty((n_local, self.R), dtype=torch.float64, device=self.device)
+        self.status_d = torch.empty((n_local,), dtype=torch.int32, device=self.device)
+        self.jafs_d = torch.empty((n_local, 7), dtype=torch.float64, device=self.device) if want_jafs else None
+        self.llh_all_h = torch.empty((self.world * n_local, self.R), dtype=torch.float64).pin_memory()
+        self.status_h = torch.empty((n_local,), dtype=torch.int32).pin_memory()
+        self.jafs_h = torch.empty((n_local, 7), dtype=torch.float64).pin_memory() if want_jafs else None
+
+    def evaluate_device(self, params_d, model, flags):
+        """shard on the device -> global likelihood rows on the device [world * n_local, R], item order"""
+        self.engine.evaluate_device(self.n_local, self.P, params_d.data_ptr() if self.P else None, self.llh_d.data_ptr(), model=model,
+                                    flags=flags, status_ptr=self.status_d.data_ptr(),
+                                    jafs_ptr=self.jafs_d.data_ptr() if self.jafs_d is not None else None)
+        return gather_rows_device(self.llh_d, self.world * self.n_local, group=self.group)
+
+    def evaluate(self, params_h, model, flags):
+        """host shard (pinned tensor [n_local, P]) -> global likelihood rows on the host (pinned), + this shard's status and
+        spectra.  H2D of the parameters, the two kernels, the all-gather and the D2H of the results are queued on the
+        current torch stream; returns after they have completed."""
+        import torch
+        self.params_d.copy_(params_h, non_blocking=True)
+        llh_all = self.evaluate_device(self.params_d, model, flags)
+        self.llh_all_h.copy_(llh_all, non_blocking=True)
+        self.status_h.copy_(self.status_d, non_blocking=True)
+        if self.jafs_h is not None:
+            self.jafs_h.copy_(self.jafs_d, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return self.llh_all_h, self.status_h, self.jafs_h
 
 
 def evaluate_sharded(evaluate, params, model_ids=None, group=None, device=None):

@@ -109,7 +109,12 @@ def test_full_bootstrap_sweep_1001_rows_times_9_split_times(engine):
         # another order of summation)
         assert relerr(alone["llh"][j], res["llh"][k]) < 1e-12, k
     from scipy import optimize
-    for k in sample[:2]:
+    # two fits with an interior optimum against scipy around the oracle (where the rate is fitted to zero the simplex walks
+    # down to m ~ 1e-8, where the REFERENCE's own likelihood is inaccurate -- inv(M) of a nearly singular generator, error ~
+    # 1e-16 / m, test_tiny_migration_rates_are_continuous -- and its last decisions are not determined to the last bit)
+    interior = [k for k in range(len(res["llh"])) if res["x"][k][0] > 0.05][:2]
+    assert len(interior) == 2
+    for k in interior:
         m, r = int(res["model"][k]), int(res["row"][k])
         om = OracleModel(inp.times, inp.lambdas, list(bs[r]), sts[m], [[1, 4, sts[m], 3, 1]], [], cpfit=True, smooth=True, unfolded=True)
         ref = optimize.minimize(lambda x: -om.likelihood(list(x)), [3.0], method="Nelder-Mead",
