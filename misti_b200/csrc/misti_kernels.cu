@@ -52,8 +52,10 @@ static __device__ const unsigned char d_w8[7][8] = MISTI_W8_INIT;
 // item, all running the same chain on the same data, which share out the residual evaluations of a solver round
 // (misti::eval_fj); results are bit-identical to the one-thread variant, the serial chain is shorter.
 // ------------------------------------------------------------------------------------------------
-// FIT = the variant the on-device optimiser launches: item count and item list on the device, interruptible chains
-template <int MINB, bool COOP, bool FIT>
+// MODE 1 = the variant the on-device optimiser launches (item count and item list on the device, interruptible chains);
+// MODE 2 = the diagnostic variant that records the per-interval solver trace (misti_eval_io.solve_trace); 0 = neither: the
+// plain batched evaluation carries none of that code
+template <int MINB, bool COOP, int MODE>
 __global__ void __launch_bounds__(kCorrectThreads, MINB)
 misti_correct_kernel(int B, int P, const double* __restrict__ params, const int* __restrict__ model_ids, int model_default,
                      const ModelDesc* __restrict__ models, const double* __restrict__ times, const double* __restrict__ lh,
@@ -65,6 +67,7 @@ misti_correct_kernel(int B, int P, const double* __restrict__ params, const int*
     // count_ptr (nullable): the number of items lives on the device (the on-device optimiser packs the points of a round
     // behind a counter) and B is only the capacity the grid was sized for.  regime: 0 = run; 1 / 2 = this launch is one of
     // the pair (four lanes per item | one thread per item) of which only the variant that suits the round's size runs.
+    constexpr bool FIT = MODE == 1;
     if (FIT && count_ptr) {
         const int n = *count_ptr;
         if ((regime == 1 && n > kCoopMaxItems) || (regime == 2 && n <= kCoopMaxItems)) return;
@@ -115,24 +118,35 @@ misti_correct_kernel(int B, int P, const double* __restrict__ params, const int*
         // defer_post (cpfit mode): the post-split pass is left to the lane groups of the JSFS kernel; they get
         // exp(nc1 - nc0) in the first coefficient slot
         double nc[2] = {0.0, 0.0};
-        int* trace = solve_trace ? solve_trace + (long)b * 2 * numT_max : nullptr;
-        if (trace && (!COOP || (gtid & 3) == 0))
-            for (int t = 0; t < numT_max; ++t) { trace[2 * t] = 0; trace[2 * t + 1] = misti::kNoSolve; }
-        if (COOP && (gtid & 3) != 0) trace = nullptr;  // the four lanes of an item hold the same values: one of them writes
-        // inside the on-device optimiser the chain may yield at an interval boundary when its time slice is used up (ChainCkpt)
-        misti::ChainResume rs;
-        rs.ck = ckpt ? ckpt + b : nullptr;
-        // slice_ctl: [0] the time slice in microseconds (adapted by the optimiser between rounds), [1] / [2] how many items of
-        // this round ran to the end / were interrupted
-        rs.budget_ns = (ckpt && b < yield_below) ? 1000LL * slice_ctl[0] : 0;
-        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(rs.t_start));
-        st = misti::correct_lambdas_item<COOP>(md, tt, ll, par, flags, mixtureTH, lcb, kPitch, stride, pr, &nf, ga, cp, &cp_done, cls,
-                                               defer_post ? nc : nullptr, trace, ckpt ? &rs : nullptr);
-        if (st == MISTI_PENDING) {  // interrupted: the checkpoint is written; the item runs on in the next round
-            if (!COOP || (gtid & 3) == 0) { status[b] = MISTI_PENDING; atomicAdd(slice_ctl + 2, 1); }
-            return;
+        int* trace = nullptr;
+        if (MODE == 2) {
+            trace = solve_trace ? solve_trace + (long)b * 2 * numT_max : nullptr;
+            if (trace && (!COOP || (gtid & 3) == 0))
+                for (int t = 0; t < numT_max; ++t) { trace[2 * t] = 0; trace[2 * t + 1] = misti::kNoSolve; }
+            if (COOP && (gtid & 3) != 0) trace = nullptr;  // the four lanes of an item hold the same values: one of them writes
         }
-        if (ckpt && (!COOP || (gtid & 3) == 0)) { ckpt[b].active = 0; atomicAdd(slice_ctl + 1, 1); }
+        if (FIT && ckpt) {
+            // inside the on-device optimiser the chain may yield at an interval boundary when its time slice is used up
+            // (ChainCkpt).  slice_ctl: [0] the time slice in microseconds (adapted by the optimiser between rounds),
+            // [1] / [2] how many chains of this round ran to the end / were interrupted
+            misti::ChainResume rs;
+            rs.ck = ckpt + b;
+            rs.budget_ns = b < yield_below ? 1000LL * slice_ctl[0] : 0;
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(rs.t_start));
+            st = misti::correct_lambdas_item<COOP, true, false>(md, tt, ll, par, flags, mixtureTH, lcb, kPitch, stride, pr, &nf, ga, cp,
+                                                                &cp_done, cls, defer_post ? nc : nullptr, nullptr, &rs);
+            if (st == MISTI_PENDING) {  // interrupted: the checkpoint is written; the item runs on in the next round
+                if (!COOP || (gtid & 3) == 0) { status[b] = MISTI_PENDING; atomicAdd(slice_ctl + 2, 1); }
+                return;
+            }
+            if (!COOP || (gtid & 3) == 0) { ckpt[b].active = 0; atomicAdd(slice_ctl + 1, 1); }
+        } else if (MODE == 2) {
+            st = misti::correct_lambdas_item<COOP, false, true>(md, tt, ll, par, flags, mixtureTH, lcb, kPitch, stride, pr, &nf, ga, cp,
+                                                                &cp_done, cls, defer_post ? nc : nullptr, trace, nullptr);
+        } else {
+            st = misti::correct_lambdas_item<COOP, false, false>(md, tt, ll, par, flags, mixtureTH, lcb, kPitch, stride, pr, &nf, ga, cp,
+                                                                 &cp_done, cls, defer_post ? nc : nullptr, nullptr, nullptr);
+        }
         if (defer_post && cp_done) cp[0] = exp(nc[1] - nc[0]);
     }
     int ns = 0;
@@ -212,7 +226,7 @@ __device__ __forceinline__ void emit_item(const ItemOut& o, const double* ysm, i
 // ------------------------------------------------------------------------------------------------
 // K2: expected JSFS + composite log-likelihood, one half warp per item
 // ------------------------------------------------------------------------------------------------
-template <int MINB, bool DEFER>
+template <int MINB, bool DEFER, bool FIT>
 __global__ void __launch_bounds__(kJsfsWarps * 32, MINB)
 misti_jsfs_kernel(int B, int P, const double* __restrict__ params, const int* __restrict__ model_ids, int model_default,
                   const ModelDesc* __restrict__ models, const double* __restrict__ rec, int seg_cap, const int* __restrict__ nseg,
@@ -220,7 +234,7 @@ misti_jsfs_kernel(int B, int P, const double* __restrict__ params, const int* __
                   int* __restrict__ park_list, int* __restrict__ park_count, int* __restrict__ work_counter,
                   const double* __restrict__ post_tab, const double* __restrict__ lh, const int* __restrict__ count_ptr,
                   const int* __restrict__ item_list) {
-    if (count_ptr) {  // the number of items lives on the device (see misti_correct_kernel)
+    if (FIT && count_ptr) {  // the number of items lives on the device (see misti_correct_kernel)
         const int n = *count_ptr;
         B = n < B ? n : B;
         if (B <= 0) return;
@@ -254,7 +268,7 @@ misti_jsfs_kernel(int B, int P, const double* __restrict__ params, const int* __
         if (i0 >= B) break;
         const bool has = i0 + (half & 1) < B;
         const int slot = has ? i0 + (half & 1) : B - 1;
-        const int b = item_list ? item_list[slot] : slot;  // see misti_correct_kernel
+        const int b = (FIT && item_list) ? item_list[slot] : slot;  // see misti_correct_kernel
         int st = out.status[b];
         // an item the correction kernel skipped (model id outside the registered models) runs along inactive
         const ModelDesc& md = models[st == MISTI_SKIPPED ? 0 : (model_ids ? model_ids[b] : model_default)];
@@ -762,23 +776,28 @@ __global__ void misti_fit_propose_kernel(int S, misti::NmConfig cfg, misti::BhCo
     }
     double* sim = st.sim + (long)s * (N + 1) * N;
     double* fsim = st.fsim + (long)s * (N + 1);
-    if (bh.niter >= 0 && st.phase[s] == misti::NM_DONE && !st.bh_done[s]) {
-        misti::BhWalker w;
-        w.x = st.bh_x + (long)s * N; w.best_x = st.bh_best_x + (long)s * N;
-        w.energy = st.bh_energy + s; w.best_f = st.bh_best_f + s; w.step = st.bh_step + s;
-        w.ok = st.bh_ok + s; w.best_ok = st.bh_best_ok + s; w.done = st.bh_done + s;
-        w.nfev = st.bh_nfev + s; w.failures = st.bh_fail + s; w.nstep = st.bh_nstep + s; w.naccept = st.bh_naccept + s;
-        w.hop = st.bh_hop + s; w.rng = st.rng + s;
-        misti::bh_advance(bh, N, w, sim, fsim, st.iters + s, st.fcalls + s, st.status + s, st.phase + s);
-    }
-    if (st.phase[s] == misti::NM_DONE) { st.first[s] = -1; st.cnt[s] = 0; return; }
     // look-ahead while the simplices that ran in the previous round are few (the count only ever falls)
     const int running_prev = round == 0 ? S : fc[FC_RUN0 + (round & 1)];
     misti::NmConfig c = cfg;
     c.lookahead = cfg.lookahead && N <= misti::kNmLookaheadMaxN && (long)running_prev * misti::nm_slots(N, true) <= look_max_items;
     c.slots = misti::nm_slots(N, c.lookahead != 0);
     double pts[kFitMaxPts];
-    const int n = misti::nm_propose(c, sim, fsim, st.iters + s, st.fcalls + s, st.status + s, st.phase + s, pts);
+    int n = 0;
+    for (int pass = 0; pass < 2 && n == 0; ++pass) {
+        // a walker whose local search has ended takes its Metropolis decision and starts the next one at once: a simplex
+        // that is not finished submits points in EVERY round (the host ends the fit at the first round without points)
+        if (bh.niter >= 0 && st.phase[s] == misti::NM_DONE && !st.bh_done[s]) {
+            misti::BhWalker w;
+            w.x = st.bh_x + (long)s * N; w.best_x = st.bh_best_x + (long)s * N;
+            w.energy = st.bh_energy + s; w.best_f = st.bh_best_f + s; w.step = st.bh_step + s;
+            w.ok = st.bh_ok + s; w.best_ok = st.bh_best_ok + s; w.done = st.bh_done + s;
+            w.nfev = st.bh_nfev + s; w.failures = st.bh_fail + s; w.nstep = st.bh_nstep + s; w.naccept = st.bh_naccept + s;
+            w.hop = st.bh_hop + s; w.rng = st.rng + s;
+            misti::bh_advance(bh, N, w, sim, fsim, st.iters + s, st.fcalls + s, st.status + s, st.phase + s);
+        }
+        if (st.phase[s] == misti::NM_DONE) break;
+        n = misti::nm_propose(c, sim, fsim, st.iters + s, st.fcalls + s, st.status + s, st.phase + s, pts);  // 0: the search has just ended
+    }
     st.look[s] = c.lookahead;
     if (n <= 0) { st.first[s] = -1; st.cnt[s] = 0; return; }
     // where the points live: a simplex's own slots (fixed: an interrupted item keeps its scratch across rounds), or -- the
@@ -905,7 +924,8 @@ struct misti_ctx {
     unsigned long long generation = 0;    // bumped whenever a device buffer moves or a launch argument of the kernels changes
     int nm_use_graph = 1;                 // tuning knob MISTI_NM_GRAPH
     int nm_rounds_per_graph = 4;          // rounds captured in one graph (tuning knob MISTI_NM_ROUNDS)
-    int fit_slice_us = 350;               // time slice of a correction chain inside the on-device optimiser (MISTI_FIT_SLICE_US)
+    int fit_slice_us = 200;               // time slice of a correction chain inside the on-device optimiser (MISTI_FIT_SLICE_US)
+    bool fit_slice_forced = false;        // the knob was set: slices also in large sweeps
     int nm_graph_launches = 0;            // kernel launches per round of the kept graph
     cudaEvent_t nm_ev[4] = {nullptr, nullptr, nullptr, nullptr};
     double* d_score = nullptr;      // scratch of misti_score_spectra
@@ -1104,7 +1124,7 @@ int misti_ctx_create(int device, void* stream, misti_ctx** out) {
     if (const char* e = getenv("MISTI_DEFER_POST")) ctx->defer_post = atoi(e);
     if (const char* e = getenv("MISTI_NM_LOOKAHEAD")) ctx->nm_lookahead = atoi(e);
     if (const char* e = getenv("MISTI_NM_GRAPH")) ctx->nm_use_graph = atoi(e);
-    if (const char* e = getenv("MISTI_FIT_SLICE_US")) { const int v = atoi(e); if (v >= 0) ctx->fit_slice_us = v; }
+    if (const char* e = getenv("MISTI_FIT_SLICE_US")) { const int v = atoi(e); if (v >= 0) { ctx->fit_slice_us = v; ctx->fit_slice_forced = true; } }
     if (const char* e = getenv("MISTI_NM_ROUNDS")) { const int v = atoi(e); if (v >= 1 && v <= 64) ctx->nm_rounds_per_graph = v; }
     if (const char* e = getenv("MISTI_MAX_CHUNK")) {
         const int v = atoi(e);
@@ -1302,7 +1322,7 @@ static int eval_chunk(misti_ctx* ctx, int B, int P, const double* d_params, cons
     // small batches: four lanes per item (see misti_correct_kernel); the knob MISTI_CORRECT_COOP = 0 / 1 forces a variant.
     // With the item count on the device (d_count) both variants are launched and the one that suits the count runs.
     const bool coop = ctx->correct_coop < 0 ? B <= kCoopMaxItems : ctx->correct_coop != 0;
-#define MISTI_LAUNCH_CORRECT2(MINB, COOP, NTHREADS, REGIME) MISTI_LAUNCH_CORRECT3(MINB, COOP, false, NTHREADS, REGIME)
+#define MISTI_LAUNCH_CORRECT2(MINB, COOP, NTHREADS, REGIME) MISTI_LAUNCH_CORRECT3(MINB, COOP, 0, NTHREADS, REGIME)
 #define MISTI_LAUNCH_CORRECT3(MINB, COOP, FIT, NTHREADS, REGIME)                                                         \
     misti_correct_kernel<MINB, COOP, FIT><<<(unsigned)(((NTHREADS) + kCorrectThreads - 1) / kCorrectThreads), kCorrectThreads, 0, ctx->stream>>>( \
         B, P, d_params, d_model_ids, model_default, ctx->d_models, ctx->d_times, ctx->d_lh, ctx->d_gaux, ctx->d_cls, flags, mixture_th, \
@@ -1312,9 +1332,11 @@ static int eval_chunk(misti_ctx* ctx, int B, int P, const double* d_params, cons
 #define MISTI_LAUNCH_CORRECT(MINB)                                                                                       \
     if (coop) MISTI_LAUNCH_CORRECT2(MINB, true, 4L * B, 0); else MISTI_LAUNCH_CORRECT2(MINB, false, (long)B, 0)
     if (d_count) {  // the on-device optimiser: the pair of variants, of which the one that suits the round's item count runs
-        if (ctx->correct_coop != 0) MISTI_LAUNCH_CORRECT3(kCorrectMinBlocks, true, true, 4L * (B < kCoopMaxItems ? B : kCoopMaxItems), ctx->correct_coop < 0 ? 1 : 0);
+        if (ctx->correct_coop != 0) MISTI_LAUNCH_CORRECT3(kCorrectMinBlocks, true, 1, 4L * (B < kCoopMaxItems ? B : kCoopMaxItems), ctx->correct_coop < 0 ? 1 : 0);
         if (ctx->correct_coop == 0 || (ctx->correct_coop < 0 && B > kCoopMaxItems))
-            MISTI_LAUNCH_CORRECT3(kCorrectMinBlocks, false, true, (long)B, ctx->correct_coop < 0 ? 2 : 0);
+            MISTI_LAUNCH_CORRECT3(kCorrectMinBlocks, false, 1, (long)B, ctx->correct_coop < 0 ? 2 : 0);
+    } else if (d_trace) {  // diagnostics: the per-interval solver trace
+        if (coop) MISTI_LAUNCH_CORRECT3(kCorrectMinBlocks, true, 2, 4L * B, 0); else MISTI_LAUNCH_CORRECT3(kCorrectMinBlocks, false, 2, (long)B, 0);
     } else
     switch (ctx->correct_minb) {  // register budget per thread: 4 -> 255, 8 -> 128, 12 -> 80 (tuning knob MISTI_CORRECT_MINB)
         case 4: MISTI_LAUNCH_CORRECT(4); break;
@@ -1336,8 +1358,9 @@ static int eval_chunk(misti_ctx* ctx, int B, int P, const double* d_params, cons
     out.row_ids = d_row_ids;
 #define MISTI_LAUNCH_JSFS(MINB)                                                                                            \
     if (defer_post) MISTI_LAUNCH_JSFS2(MINB, true); else MISTI_LAUNCH_JSFS2(MINB, false)
-#define MISTI_LAUNCH_JSFS2(MINB, DEFER)                                                                                    \
-    misti_jsfs_kernel<MINB, DEFER><<<blocks, kJsfsWarps * 32, 0, ctx->stream>>>(                                           \
+#define MISTI_LAUNCH_JSFS2(MINB, DEFER) if (d_count) MISTI_LAUNCH_JSFS3(kJsfsMinBlocks, DEFER, true); else MISTI_LAUNCH_JSFS3(MINB, DEFER, false)
+#define MISTI_LAUNCH_JSFS3(MINB, DEFER, FIT)                                                                               \
+    misti_jsfs_kernel<MINB, DEFER, FIT><<<blocks, kJsfsWarps * 32, 0, ctx->stream>>>(                                           \
         B, P, d_params, d_model_ids, model_default, ctx->d_models, ctx->d_rec, ctx->cap_seg, ctx->d_nseg, stride, ctx->d_cpost, \
         out, ctx->d_conts, ctx->d_queue[0], ctx->d_counts, ctx->d_counts + 4, ctx->d_post, ctx->d_lh, d_count, d_item_list)
     switch (ctx->jsfs_minb) {  // register budget: 2 -> 255, 3 -> 168, 4 -> 128, 5 -> 96 (tuning knob MISTI_JSFS_MINB)
@@ -1348,6 +1371,7 @@ static int eval_chunk(misti_ctx* ctx, int B, int P, const double* d_params, cons
     }
 #undef MISTI_LAUNCH_JSFS
 #undef MISTI_LAUNCH_JSFS2
+#undef MISTI_LAUNCH_JSFS3
     CK(cudaGetLastError());
     // items parked at a stiff segment (usually none: the kernel then returns at once): dense scaling-and-squaring step,
     // rest of the sweep and results, one block per item
@@ -1544,8 +1568,13 @@ int misti_fit(misti_ctx* ctx, int32_t S, int32_t N, const double* x0, const int3
     const long cap = (long)stable_items + (cfg.lookahead ? look_max : 0);
     if (cap > ctx->max_chunk) return fail(ctx, MISTI_E_ARG, "misti_fit: too many simplices for one call");
     const int B = (int)cap;
-    // time slice of the correction chain inside a round (tuning knob MISTI_FIT_SLICE_US; 0 = chains are never interrupted)
-    const long long budget_ns = (long long)ctx->fit_slice_us * 1000;
+    // Time slice of the correction chains inside a round (tuning knob MISTI_FIT_SLICE_US; 0 = chains are never interrupted).
+    // Walkers and small sweeps run in the latency regime, where one run-away chain (ten times the ordinary one) would hold up
+    // every simplex of its round: measured on 1 024 walkers x 20 hops, 9.6 s without, 5.6 s with a slice of 150 ... 350 us.
+    // A large sweep of like fits (config 5b: 36 036 chains per round, all equally long) gains nothing and pays for the extra
+    // rounds and the checkpoint code (0.146 -> 0.175 s): there the chains run through.
+    const bool slicing = ctx->fit_slice_us > 0 && (walkers || stable_items <= kCoopMaxItems || ctx->fit_slice_forced);
+    const long long budget_ns = slicing ? (long long)ctx->fit_slice_us * 1000 : 0;
     // one block of device memory, carved up (8-byte items first)
     const size_t n_sim = (size_t)S * (N + 1) * N, n_fsim = (size_t)S * (N + 1);
     size_t off = 0;
@@ -1681,7 +1710,7 @@ int misti_fit(misti_ctx* ctx, int32_t S, int32_t N, const double* x0, const int3
             cudaEventElapsedTime(&k2, ctx->ev[1], ctx->ev[2]);
             cudaEventElapsedTime(&all, e0, e1);
             cudaEventDestroy(e0); cudaEventDestroy(e1);
-            if (tf) fprintf(tf, "%ld %d %.4f %.4f %.4f\n", r, items, k1, k2, all);
+            if (tf) fprintf(tf, "%ld %d %.4f %.4f %.4f %d\n", r, items, k1, k2, all, hc[FC_SLICE_US]);
             if (items == 0) break;
         }
         if (tf) fclose(tf);

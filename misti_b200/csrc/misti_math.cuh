@@ -718,9 +718,8 @@ struct IntervalState {
     double mu[2];     // migration rates
     double P0[2][3];  // per genome: P(both lineages in deme 0 / deme 1 / one each), not yet coalesced
     double nch[2];    // cpfit target of the interval, exp(-lh T) (sum of P0): the same in every residual evaluation
-    int status;       // scipy's termination status of the interval's least-squares solve (kNoSolve: closed form, no solver)
 };
-constexpr int kNoSolve = -9;
+constexpr int kNoSolve = -9;  // "termination status" of an interval that has a closed form (no least-squares solve)
 
 MISTI_HD inline void corr_matrix(const double* l, const double* mu, double T, double* M) {
     // CorrectLambda.SetMatrix (CorrectLambda.py:55-56), times T
@@ -827,7 +826,7 @@ MISTI_HD inline void grid_aux_row(const double* lh2, double T, double* out) {
 // The interval WITH migration (CorrectLambda.py:276-317): 2-unknown trust-region solve on the 3-state chains.
 // (Inlined: an out-of-line version measured 5 % slower on B200.)
 template <bool COOP = false>
-MISTI_HD inline bool solve_interval_mig(IntervalState* st, bool cpfit, double* lc, int* nfev) {
+MISTI_HD inline bool solve_interval_mig(IntervalState* st, bool cpfit, double* lc, int* nfev, int* status_out = nullptr) {
     const double T = st->T;
     double (*P0)[3] = st->P0;
     double lh[2] = {st->lh[0], st->lh[1]};
@@ -851,7 +850,7 @@ MISTI_HD inline bool solve_interval_mig(IntervalState* st, bool cpfit, double* l
     if (cpfit) { ResidualProb fun; fun.st = &u; status = least_squares_trf<2, COOP>(fun, x, false, -kInf, &nf); }
     else { ResidualTime fun; fun.st = &u; status = least_squares_trf<2, COOP>(fun, x, false, -kInf, &nf); }
     *nfev += nf;
-    st->status = status;
+    if (status_out) *status_out = status;
     if (status < 0) return false;
     // un-stretch exactly as the reference does: mu*T/T, x/T
     const double mu_back[2] = {u.mu[0] / T, u.mu[1] / T};
@@ -871,11 +870,12 @@ MISTI_HD inline bool solve_interval_mig(IntervalState* st, bool cpfit, double* l
 // interval).  Returns false when the reference would report a failed correction or crash.
 // `ga` (nullable): grid_aux_row of this interval.
 template <bool COOP = false>
-MISTI_HD inline bool solve_interval(IntervalState* st, bool cpfit, double mixtureTH, double* lc, int* nfev, const double* ga = nullptr) {
+MISTI_HD inline bool solve_interval(IntervalState* st, bool cpfit, double mixtureTH, double* lc, int* nfev, const double* ga = nullptr,
+                                    int* status_out = nullptr) {  // status_out (nullable): scipy's termination status of the solve, kNoSolve if none
     const double T = st->T;
     double (*P0)[3] = st->P0;
     const double s0 = (P0[0][0] + P0[0][1]) + P0[0][2], s1 = (P0[1][0] + P0[1][1]) + P0[1][2];
-    st->status = kNoSolve;
+    if (status_out) *status_out = kNoSolve;
     if (mixtureTH > 0) {  // sqrt(mix) >= 0: the test can only fire for a positive threshold
         double mix = 0;
         for (int i = 0; i < 3; ++i) { const double d = P0[0][i] / s0 - P0[1][i] / s1; mix += d * d; }
@@ -907,14 +907,14 @@ MISTI_HD inline bool solve_interval(IntervalState* st, bool cpfit, double mixtur
         int nf = 0;
         const int status = least_squares_trf<2, COOP>(fun, x, true, lb, &nf);
         *nfev += nf;
-        st->status = status;
+        if (status_out) *status_out = status;
         if (status < 0) return false;
         lc[0] = x[0]; lc[1] = x[1];
         const double e0 = exp(-lc[0] * T), e1 = exp(-lc[1] * T);
         for (int k = 0; k < 2; ++k) { P0[k][0] *= e0; P0[k][1] *= e1; }
         return lc[0] > 0 && lc[1] > 0;
     }
-    return solve_interval_mig<COOP>(st, cpfit, lc, nfev);
+    return solve_interval_mig<COOP>(st, cpfit, lc, nfev, status_out);
 }
 
 // FitSinglePop (CorrectLambda.py:88-92) with P0 = [[exp(nc0),0,0],[exp(nc1),0,0]]

@@ -201,7 +201,7 @@ MISTI_HD inline bool chain_should_yield(const ChainResume* rs, bool coop) {
 // solve, kNoSolve where the interval has a closed form -- the iterate-level record the golden vectors of
 // tests/golden/solver.json pin (CorrectLambda.py:85, 260, 303, 305).
 // COOP (device only): four lanes run the item together, see eval_fj in misti_math.cuh.
-template <bool COOP = false>
+template <bool COOP = false, bool RESUME = false, bool TRACE = false>
 MISTI_HD inline int correct_lambdas_item(const ModelDesc& md, const double* times, const double* lh, const double* params,
                                          unsigned flags, double mixtureTH, double* lc, int pitch, long stride, double* Pr,
                                          int* nfev_out, const double* gaux = nullptr, double* cpost = nullptr,
@@ -225,8 +225,11 @@ MISTI_HD inline int correct_lambdas_item(const ModelDesc& md, const double* time
     const bool smooth = (flags & MISTI_FLAG_SMOOTH) != 0;
     struct SmoothRun { int k; bool done; double lam, nc, time; };
     SmoothRun sr0 = {0, !smooth, lh[0], 0.0, 0.0}, sr1 = {0, !smooth, lh[1], 0.0, 0.0};
+    // (RESUME / TRACE are compile-time switches: the plain batched evaluation carries neither the checkpoint code nor the trace)
+    if (!TRACE) trace = nullptr;
+    if (!RESUME) rs = nullptr;
     int t_first = 0;
-    if (rs && rs->ck->active) {  // resume an interrupted chain (see ChainCkpt)
+    if (RESUME && rs && rs->ck->active) {  // resume an interrupted chain (see ChainCkpt)
         const ChainCkpt& k = *rs->ck;
         t_first = k.t_next;
         nfev = k.nfev;
@@ -251,7 +254,7 @@ MISTI_HD inline int correct_lambdas_item(const ModelDesc& md, const double* time
         r.time += times[t];
     };
     for (int t = t_first; t < splitT; ++t) {
-        if (t > t_first && chain_should_yield(rs, COOP)) {  // time slice used up: park the chain at this interval boundary
+        if (RESUME && t > t_first && chain_should_yield(rs, COOP)) {  // time slice used up: park the chain at this interval boundary
             ChainCkpt& k = *rs->ck;
             bool writer = true;
 #if defined(__CUDA_ARCH__)
@@ -288,8 +291,10 @@ MISTI_HD inline int correct_lambdas_item(const ModelDesc& md, const double* time
             st.T = times[t];
             st.mu[0] = mi_t[0]; st.mu[1] = mi_t[1];
             const int nfev_before = nfev;
-            const bool ok = solve_interval<COOP>(&st, cpfit, mixtureTH, l, &nfev, gaux ? gaux + kGridAux * t : nullptr);
-            if (trace) { trace[2 * t] = nfev - nfev_before; trace[2 * t + 1] = st.status; }
+            int solve_status = kNoSolve;
+            const bool ok = solve_interval<COOP>(&st, cpfit, mixtureTH, l, &nfev, gaux ? gaux + kGridAux * t : nullptr,
+                                                 trace ? &solve_status : nullptr);
+            if (trace) { trace[2 * t] = nfev - nfev_before; trace[2 * t + 1] = solve_status; }
             if (!ok) {
                 lc[(pitch * t) * stride] = l[0];
                 lc[(pitch * t + 1) * stride] = l[1];

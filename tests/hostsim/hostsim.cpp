@@ -38,8 +38,8 @@ int hs_correct_lambdas(int numT, int splitT, int sampleDate, const double* times
     for (int t = 0; t < numT; ++t) cls[t] = misti::interval_class(md, t);
     if (trace)
         for (int t = 0; t < numT; ++t) { trace[2 * t] = 0; trace[2 * t + 1] = misti::kNoSolve; }
-    return misti::correct_lambdas_item(md, times, lh, params, flags, mixtureTH, lc, 2, 1, Pr, nfev, gaux.data(), nullptr, nullptr,
-                                       cls.data(), nullptr, trace);
+    return misti::correct_lambdas_item<false, false, true>(md, times, lh, params, flags, mixtureTH, lc, 2, 1, Pr, nfev, gaux.data(), nullptr,
+                                                           nullptr, cls.data(), nullptr, trace);
 }
 
 // CoalescentRates (forward map): lc[numT][2] true rates -> lh_out[numT][2], Pr[(splitT + 1)][3][2]

@@ -222,3 +222,31 @@ def test_bistable_chain_lands_on_one_of_the_references_branches(engine, golden_d
         print("bistable point", p["x"], "device", out["llh"][k, 0], "reference", p["llh"], "nearest reference branch at", dist,
               "nfev device / reference", out["nfev"][k], p["nfev"])
         assert dist < TOL, (p["x"], out["llh"][k, 0], values)
+
+
+def test_walkers_finish_their_hops_and_do_not_depend_on_the_time_slice(golden_datasets):
+    """300 walkers x 8 hops on the device: every walker takes all its hops (the host must not take a round in which the
+    last running walkers are between two local searches for the end of the fit), and the results do not depend on where
+    -- or whether -- the correction chains of a round were interrupted (ChainCkpt): time slices of 50 us, 350 us and none."""
+    import misti_b200
+    ds = golden_datasets["synthetic"]
+    W, niter = 300, 8
+    rng = np.random.default_rng(77)
+    x0 = np.column_stack([rng.uniform(0, 5, W), rng.uniform(0, 5, W), rng.uniform(0, 0.5, W)])
+    res = {}
+    for us in ("0", "50", "350"):
+        os.environ["MISTI_FIT_SLICE_US"] = us
+        try:
+            eng = misti_b200.Engine(0)
+        finally:
+            del os.environ["MISTI_FIT_SLICE_US"]
+        gid = eng.add_grid(ds["times"], ds["lambdas"])
+        mid = eng.add_model(gid, 40, 0, bands=[(0, 2, 10, 0.3, 0), (1, 5, 12, 0.8, 1)], pulses=[(0, 7, 0.05, 2)])
+        eng.set_data([ds["sfs"]], True)
+        res[us] = eng.basinhopping(x0, np.full(W, mid, dtype=np.int32), seeds=[500 + w for w in range(W)], flags=CPFIT_UF, niter=niter)
+        eng.close()
+        assert (res[us]["nit"] == niter).all(), us
+    assert res["50"]["launches"] > res["0"]["launches"]  # chains WERE interrupted
+    for us in ("50", "350"):
+        for k in ("x", "fun", "nfev", "accepted", "minimization_failures"):
+            assert np.array_equal(res[us][k], res["0"][k], equal_nan=True), (us, k)
