@@ -51,7 +51,15 @@ def build_parser():
 
 
 def _subst(mi, st):
-    return [[str(st) if str(v) == "st" else v for v in el] for el in mi]
+    """-mi / -pu descriptors with the token `st` (the split time of the model, as in test.bs/din_sar.bs.sh: `-mi 1 4 ${st} 3 1`)
+    replaced.  The token stands for an interval INDEX (SetModel takes int() of it): a whole split time is written as an
+    integer ("40", not "40.0" -- argparse delivers -st as a float), a fractional one has no index to stand for."""
+    if not any(str(v) == "st" for el in mi for v in el):
+        return [list(el) for el in mi]
+    if float(st) != int(float(st)):
+        print("The `st` token in -mi / -pu needs a whole split time (got %s)." % st)
+        sys.exit(0)
+    return [[str(int(float(st))) if str(v) == "st" else v for v in el] for el in mi]
 
 
 def main(argv=None):

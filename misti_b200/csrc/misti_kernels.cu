@@ -171,12 +171,13 @@ struct ItemOut {
     double *llh, *jafs, *jafs_raw;
     int *status, *terms;
     const int* row_ids;
+    double* logs;          // [B][8] (nullable) the 7 logs of every item, for misti_score_rows_kernel (many data rows)
 };
 
 // Results of item b from its lane group: status, spectrum, and the fused composite likelihood over all data rows
 // (bootstrap replicates; the lanes stride the rows).  Called after misti::jafs_finish, which left the logs in `ysm`.
 __device__ __forceinline__ void emit_item(const ItemOut& o, const double* ysm, int lane, int b, int st, double raw_c, double jn_c,
-                                          int nt) {
+                                          int nt, bool with_rows = true) {
     if (lane == 0) {
         o.status[b] = st;
         if (o.terms) o.terms[b] = nt;
@@ -184,6 +185,10 @@ __device__ __forceinline__ void emit_item(const ItemOut& o, const double* ysm, i
     if (lane < 7) {
         if (o.jafs) o.jafs[(long)b * 7 + lane] = st == MISTI_OK ? jn_c : nan("");
         if (o.jafs_raw) o.jafs_raw[(long)b * 7 + lane] = st == MISTI_OK ? raw_c : nan("");
+    }
+    if (!with_rows) {  // many data rows: misti_score_rows_kernel writes them from the item's logs
+        if (lane < 8) o.logs[(long)b * 8 + lane] = lane < 7 ? ysm[misti::kTailLog + lane] : 0.0;
+        return;
     }
     const double bad = (st == MISTI_NEGATIVE_PARAM || st == MISTI_CORRECTION_FAILED) ? -misti::kInf : nan("");
     const double* logj = ysm + misti::kTailLog;
@@ -219,6 +224,51 @@ __device__ __forceinline__ void emit_item(const ItemOut& o, const double* ysm, i
 #pragma unroll
             for (int c = 0; c < 7; ++c) v += dt[c * Rs + r] * lj[c];
             dst[r] = v;
+        }
+    }
+}
+
+// MANY data rows (bootstrap replicates): the likelihoods llh[b][r] = const_r + sum_c d_rc log p_bc are a [B, 8] x [8, R]
+// product whose cost is its OUTPUT (8 bytes per (item, row) pair), so the stage is a kernel of its own, shaped for the
+// stores: the JSFS kernel leaves the 7 logs of an item in a 64-byte record, and here a warp keeps the data of 128 rows in
+// registers (4 rows per lane, 8 doubles each), walks over its slice of the items -- 7 broadcast loads per item for 128
+// pairs, against 8 loads per PAIR when every item streams the rows through L1 -- and writes 256 contiguous bytes per store
+// instruction with a streaming hint.  Summation order = the reference's (score_row).
+constexpr int kWarpRowsMin = 64;       // from this many data rows on
+constexpr int kScoreItemsPerWarp = 64;
+__global__ void __launch_bounds__(128)
+misti_score_rows_kernel(int B, int R, const double* __restrict__ data_t, long Rs, const double* __restrict__ logs,
+                        const int* __restrict__ status, double* __restrict__ llh) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int r0 = blockIdx.x * 128 + lane;
+    const int i0 = (blockIdx.y * 4 + warp) * kScoreItemsPerWarp;
+    if (i0 >= B) return;
+    double d[4][8];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) d[u][c] = r0 + 32 * u < R ? data_t[c * Rs + r0 + 32 * u] : 0.0;
+    const int i1 = i0 + kScoreItemsPerWarp < B ? i0 + kScoreItemsPerWarp : B;
+    for (int b = i0; b < i1; ++b) {
+        const int st = status[b];
+        double* dst = llh + (long)b * R;
+        if (st != MISTI_OK) {
+            if (st == MISTI_SKIPPED) continue;
+            const double bad = (st == MISTI_NEGATIVE_PARAM || st == MISTI_CORRECTION_FAILED) ? -misti::kInf : nan("");
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (r0 + 32 * u < R) __stcs(dst + r0 + 32 * u, bad);
+            continue;
+        }
+        double lj[7];
+#pragma unroll
+        for (int c = 0; c < 7; ++c) lj[c] = logs[(long)b * 8 + c];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            double v = d[u][7];
+#pragma unroll
+            for (int c = 0; c < 7; ++c) v += d[u][c] * lj[c];
+            if (r0 + 32 * u < R) __stcs(dst + r0 + 32 * u, v);
         }
     }
 }
@@ -285,17 +335,19 @@ misti_jsfs_kernel(int B, int P, const double* __restrict__ params, const int* __
                                                               rec + (long)b * seg_cap * misti::kRecSlots, nseg[b], cp, &raw_c, &nt,
                                                               conts + b, false);
         const bool fin = misti::jafs_finish(g, ysm, &raw_c, out.unfolded != 0, &jn_c);  // all lanes, also of a group without an item
-        if (!has) continue;
-        if (st == MISTI_OK) st = js;
-        if (st == MISTI_STIFF) {  // parked at a stiff segment: misti_stiff_kernel takes the item from here and emits its results
-            if (lane == 0) {
-                out.status[b] = MISTI_STIFF;
-                park_list[atomicAdd(park_count, 1)] = b;
+        const bool warp_rows = out.logs != nullptr;  // many data rows: scored by misti_score_rows_kernel from the item's logs
+        if (has) {
+            if (st == MISTI_OK) st = js;
+            if (st == MISTI_STIFF) {  // parked at a stiff segment: misti_stiff_kernel takes the item from here and emits its results
+                if (lane == 0) {
+                    out.status[b] = MISTI_STIFF;
+                    park_list[atomicAdd(park_count, 1)] = b;
+                }
+            } else {
+                if (st == MISTI_OK && !fin) st = MISTI_NONFINITE;
+                emit_item(out, ysm, lane, b, st, raw_c, jn_c, nt, !warp_rows);
             }
-            continue;
         }
-        if (st == MISTI_OK && !fin) st = MISTI_NONFINITE;
-        emit_item(out, ysm, lane, b, st, raw_c, jn_c, nt);
     }
 }
 
@@ -557,7 +609,7 @@ misti_stiff_kernel(int P, const double* __restrict__ params, const int* __restri
                     if (lane == 0) s_flag[2] = 1;  // parked again at a later stiff segment
                 } else {
                     if (js == MISTI_OK && !fin) js = MISTI_NONFINITE;
-                    emit_item(out, s_ysm[0], lane, b, js, raw_c, jn_c, nt);
+                    emit_item(out, s_ysm[0], lane, b, js, raw_c, jn_c, nt, out.logs == nullptr);
                 }
             }
         }
@@ -579,6 +631,35 @@ misti_score_kernel(int B, const double* __restrict__ spectra, const double* __re
     for (int c = 0; c < 7; ++c) raw[c] = spectra[(long)b * 7 + c];
     const bool ok = misti::jafs_normalise_logs(raw, unfolded != 0, jn, logj);
     for (int r = lane; r < R; r += 32) llh[(long)b * R + r] = ok ? misti::score_row(data + 8 * (long)r, logj) : nan("");
+}
+
+// The post-split pass of cpfit mode as a kernel of its own (large batches): one half warp per item runs
+// misti::post_split_cpfit_group -- 86 logs per item that would otherwise sit at the end of the correction kernel's serial
+// chain (14 % of it), spread over all lanes of the machine.  In: cpost[b] = exp(nc1 - nc0) from the correction kernel; out:
+// the three coefficients in cpost[0..2][b], and exp(nc1 - nc0) kept in cpost[3][b] for the rates-on-request path.  The same
+// function, table and lane count as the variant inside the JSFS kernel (small batches): bit-identical coefficients.
+__global__ void __launch_bounds__(128)
+misti_post_split_kernel(int B, const int* __restrict__ model_ids, int model_default, const ModelDesc* __restrict__ models,
+                        const int* __restrict__ status, long stride, double* __restrict__ cpost, const double* __restrict__ post_tab,
+                        const double* __restrict__ lh, const int* __restrict__ count_ptr, const int* __restrict__ item_list) {
+    if (count_ptr) {
+        const int n = *count_ptr;
+        B = n < B ? n : B;
+    }
+    const int slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+    const bool has = slot < B;
+    const int b = has ? (item_list ? item_list[slot] : slot) : 0;
+    const misti::HalfWarpLanes g;
+    const int st = has ? status[b] : MISTI_SKIPPED;
+    const ModelDesc& md = models[(st == MISTI_SKIPPED || !has) ? 0 : (model_ids ? model_ids[b] : model_default)];
+    const bool act = has && st == MISTI_OK && md.splitT < md.numT;
+    const double ed_in = has ? cpost[b] : 1.0;  // read by every lane before lane 0 overwrites the slot
+    const double ed = act ? ed_in : 1.0;
+    double cp[3];
+    misti::post_split_cpfit_group(g, act, post_tab + md.post_off, md.post_per, lh + 2 * (long)(md.grid_off + md.numT - 1), ed, cp);
+    g.sync();
+    if (act && g.lane() < 3) cpost[g.lane() * stride + b] = cp[g.lane()];
+    if (has && g.lane() == 3) cpost[3 * stride + b] = ed_in;
 }
 
 // Reduction over the ITEMS of a batch, per data row: best[r] = max_b llh[b][r] and the item that attains it (the first one,
@@ -914,6 +995,8 @@ struct misti_ctx {
     size_t s_lc_io_cap = 0, s_pr_cap = 0;
     int* s_trace = nullptr;
     size_t s_trace_cap = 0;
+    double* d_logs = nullptr;    // [cap][8] per-item logs for misti_score_rows_kernel
+    size_t d_logs_cap = 0;
     double* d_rowmax = nullptr;  // scratch of the per-row reduction over items: partial bests, then best[R]; items behind as ints
     size_t d_rowmax_cap = 0;
     unsigned char* d_nm = nullptr;  // state and batch buffers of misti_nelder_mead (one block, carved up per call)
@@ -924,6 +1007,7 @@ struct misti_ctx {
     unsigned long long generation = 0;    // bumped whenever a device buffer moves or a launch argument of the kernels changes
     int nm_use_graph = 1;                 // tuning knob MISTI_NM_GRAPH
     int nm_rounds_per_graph = 4;          // rounds captured in one graph (tuning knob MISTI_NM_ROUNDS)
+    int score_kernel = 1;                 // many data rows: likelihood stage as a kernel of its own (knob MISTI_SCORE_KERNEL)
     int fit_slice_us = 200;               // time slice of a correction chain inside the on-device optimiser (MISTI_FIT_SLICE_US)
     bool fit_slice_forced = false;        // the knob was set: slices also in large sweeps
     int nm_graph_launches = 0;            // kernel launches per round of the kept graph
@@ -1058,7 +1142,7 @@ int ensure_batch(misti_ctx* ctx, size_t B) {
     if ((rc = realloc_exact(ctx, &ctx->d_rec, ncap * (size_t)seg_need * misti::kRecSlots))) return rc;
     if ((rc = realloc_exact(ctx, &ctx->d_nseg, ncap))) return rc;
     ctx->cap_seg = seg_need;
-    if ((rc = realloc_exact(ctx, &ctx->d_cpost, ncap * 3))) return rc;
+    if ((rc = realloc_exact(ctx, &ctx->d_cpost, ncap * 4))) return rc;  // three coefficients + exp(nc1 - nc0) (misti_post_split_kernel)
     if ((rc = realloc_exact(ctx, &ctx->d_status, ncap))) return rc;
     if ((rc = realloc_exact(ctx, &ctx->d_nfev, ncap))) return rc;
     if ((rc = realloc_exact(ctx, &ctx->d_conts, ncap))) return rc;
@@ -1124,6 +1208,7 @@ int misti_ctx_create(int device, void* stream, misti_ctx** out) {
     if (const char* e = getenv("MISTI_DEFER_POST")) ctx->defer_post = atoi(e);
     if (const char* e = getenv("MISTI_NM_LOOKAHEAD")) ctx->nm_lookahead = atoi(e);
     if (const char* e = getenv("MISTI_NM_GRAPH")) ctx->nm_use_graph = atoi(e);
+    if (const char* e = getenv("MISTI_SCORE_KERNEL")) ctx->score_kernel = atoi(e);
     if (const char* e = getenv("MISTI_FIT_SLICE_US")) { const int v = atoi(e); if (v >= 0) { ctx->fit_slice_us = v; ctx->fit_slice_forced = true; } }
     if (const char* e = getenv("MISTI_NM_ROUNDS")) { const int v = atoi(e); if (v >= 1 && v <= 64) ctx->nm_rounds_per_graph = v; }
     if (const char* e = getenv("MISTI_MAX_CHUNK")) {
@@ -1143,7 +1228,7 @@ void misti_ctx_destroy(misti_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     void* ptrs[] = {ctx->d_times, ctx->d_lh, ctx->d_gaux, ctx->d_cls, ctx->d_post, ctx->d_models, ctx->d_data, ctx->d_lc, ctx->d_cpost, ctx->d_status, ctx->d_nfev, ctx->d_conts, ctx->d_queue[0], ctx->d_queue[1], ctx->d_counts,
                     ctx->d_rec, ctx->d_nseg, ctx->s_params, ctx->s_llh, ctx->s_jafs, ctx->s_jafs_raw, ctx->s_model_ids, ctx->s_terms, ctx->s_row_ids, ctx->s_lc_io,
-                    ctx->s_pr, ctx->d_small, ctx->d_nm, ctx->d_score, ctx->s_trace, ctx->d_rowmax};
+                    ctx->s_pr, ctx->d_small, ctx->d_nm, ctx->d_score, ctx->s_trace, ctx->d_rowmax, ctx->d_logs};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     for (int i = 0; i < 3; ++i)
@@ -1316,8 +1401,17 @@ static int eval_chunk(misti_ctx* ctx, int B, int P, const double* d_params, cons
     // lanes of the JSFS kernel instead of at the end of the correction kernel's serial chain.  The work is the same either
     // way, so a full machine gains nothing (measured: 65 536 items 2 % slower), but an optimiser step does (1...1024 items
     // 0.33 -> 0.29 ms, 16 384 items 0.58 -> 0.54 ms).  The two variants differ in the order of summation (<= 1e-13).
-    const bool defer_auto = defer_override >= 0 ? defer_override != 0 : (ctx->defer_post < 0 ? B <= kDeferPostMaxItems : ctx->defer_post != 0);
-    const int defer_post = (defer_auto && (flags & MISTI_FLAG_CPFIT) && !d_lc_inject) ? 1 : 0;
+    // Large batches: the pass is a kernel of its own between the two (misti_post_split_kernel; same numbers as the variant inside
+    // the JSFS kernel, bit for bit).  defer_mode: 0 = in the correction chain (knob MISTI_DEFER_POST = 0), 1 = in the JSFS
+    // kernel's lanes, 2 = kernel of its own.
+    int defer_mode = 0;
+    if ((flags & MISTI_FLAG_CPFIT) && !d_lc_inject) {
+        const int knob = defer_override >= 0 ? defer_override : ctx->defer_post;
+        defer_mode = knob < 0 ? (B <= kDeferPostMaxItems ? 1 : 2) : knob;
+        if (defer_mode < 0 || defer_mode > 2) defer_mode = 0;
+    }
+    const int defer_post = defer_mode != 0 ? 1 : 0;   // what the correction kernel and the rates-on-request path see
+    const int defer_lanes = defer_mode == 1 ? 1 : 0;  // the JSFS / stiff kernels run the pass themselves
     CK(cudaEventRecord(ctx->ev[0], ctx->stream));
     // small batches: four lanes per item (see misti_correct_kernel); the knob MISTI_CORRECT_COOP = 0 / 1 forces a variant.
     // With the item count on the device (d_count) both variants are launched and the one that suits the count runs.
@@ -1347,6 +1441,12 @@ static int eval_chunk(misti_ctx* ctx, int B, int P, const double* d_params, cons
 #undef MISTI_LAUNCH_CORRECT2
 #undef MISTI_LAUNCH_CORRECT3
     CK(cudaGetLastError());
+    if (defer_mode == 2) {
+        misti_post_split_kernel<<<(unsigned)((16L * B + 127) / 128), 128, 0, ctx->stream>>>(
+            B, d_model_ids, model_default, ctx->d_models, ctx->d_status, stride, ctx->d_cpost, ctx->d_post, ctx->d_lh, d_count, d_item_list);
+        CK(cudaGetLastError());
+        ctx->launches += 1;
+    }
     CK(cudaEventRecord(ctx->ev[1], ctx->stream));
     int blocks = (B + 2 * kJsfsWarps - 1) / (2 * kJsfsWarps);
     const int per_sm = (ctx->jsfs_minb >= 2 && ctx->jsfs_minb <= 5) ? ctx->jsfs_minb : kJsfsMinBlocks;
@@ -1356,8 +1456,13 @@ static int eval_chunk(misti_ctx* ctx, int B, int P, const double* d_params, cons
     out.data = ctx->d_data; out.data_t = ctx->d_data + 8 * (size_t)ctx->R; out.R = ctx->R; out.Rs = ctx->R; out.unfolded = ctx->unfolded;
     out.llh = d_llh; out.jafs = d_jafs; out.jafs_raw = d_jafs_raw; out.status = ctx->d_status; out.terms = d_terms;
     out.row_ids = d_row_ids;
+    out.logs = nullptr;
+    if (!d_row_ids && ctx->R >= kWarpRowsMin && ctx->score_kernel) {
+        if ((rc = ensure(ctx, &ctx->d_logs, &ctx->d_logs_cap, (size_t)ctx->cap * 8))) return rc;
+        out.logs = ctx->d_logs;
+    }
 #define MISTI_LAUNCH_JSFS(MINB)                                                                                            \
-    if (defer_post) MISTI_LAUNCH_JSFS2(MINB, true); else MISTI_LAUNCH_JSFS2(MINB, false)
+    if (defer_lanes) MISTI_LAUNCH_JSFS2(MINB, true); else MISTI_LAUNCH_JSFS2(MINB, false)
 #define MISTI_LAUNCH_JSFS2(MINB, DEFER) if (d_count) MISTI_LAUNCH_JSFS3(kJsfsMinBlocks, DEFER, true); else MISTI_LAUNCH_JSFS3(MINB, DEFER, false)
 #define MISTI_LAUNCH_JSFS3(MINB, DEFER, FIT)                                                                               \
     misti_jsfs_kernel<MINB, DEFER, FIT><<<blocks, kJsfsWarps * 32, 0, ctx->stream>>>(                                           \
@@ -1377,9 +1482,15 @@ static int eval_chunk(misti_ctx* ctx, int B, int P, const double* d_params, cons
     // rest of the sweep and results, one block per item
     misti_stiff_kernel<<<ctx->sm_count * kStiffBlocksPerSm, kStiffThreads, kStiffSmem, ctx->stream>>>(
         P, d_params, d_model_ids, model_default, ctx->d_models, ctx->d_times, ctx->d_lc, stride, ctx->d_rec, ctx->cap_seg,
-        ctx->d_nseg, ctx->d_cpost, out, ctx->d_conts, ctx->d_queue[0], ctx->d_counts, defer_post, ctx->d_post, ctx->d_lh);
+        ctx->d_nseg, ctx->d_cpost, out, ctx->d_conts, ctx->d_queue[0], ctx->d_counts, defer_lanes, ctx->d_post, ctx->d_lh);
     CK(cudaGetLastError());
     ctx->launches += 2;
+    if (out.logs) {  // many data rows: the likelihood stage as a kernel of its own, after every item has its logs
+        const dim3 grid((unsigned)((ctx->R + 127) / 128), (unsigned)((B + 4 * kScoreItemsPerWarp - 1) / (4 * kScoreItemsPerWarp)));
+        misti_score_rows_kernel<<<grid, 128, 0, ctx->stream>>>(B, ctx->R, out.data_t, (long)out.Rs, out.logs, ctx->d_status, d_llh);
+        CK(cudaGetLastError());
+        ctx->launches += 1;
+    }
     CK(cudaEventRecord(ctx->ev[2], ctx->stream));
     ctx->ev_valid = true;
     ctx->launches += (d_count && ctx->correct_coop < 0 && B > kCoopMaxItems) ? 2 : 1;  // the correction kernel (or the pair of variants)
@@ -1387,7 +1498,7 @@ static int eval_chunk(misti_ctx* ctx, int B, int P, const double* d_params, cons
         const long n = (long)B * 2 * numT_max;
         misti_gather_lc_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(B, numT_max, d_model_ids, model_default,
                                                                                      ctx->d_models, ctx->d_lc, stride, d_lc_out,
-                                                                                     defer_post, ctx->d_cpost, ctx->d_times, ctx->d_lh,
+                                                                                     defer_post, ctx->d_cpost + (defer_mode == 2 ? 3 * stride : 0), ctx->d_times, ctx->d_lh,
                                                                                      ctx->d_gaux, (int)ctx->h_models.size());
         CK(cudaGetLastError());
         ctx->launches += 1;
@@ -1636,7 +1747,7 @@ int misti_fit(misti_ctx* ctx, int32_t S, int32_t N, const double* x0, const int3
     if ((rc = ensure_batch(ctx, (size_t)B))) return rc;  // no allocation inside a round (a round may be captured)
     // cpfit post-split pass: in the JSFS kernel's lanes or in the correction chain -- decided ONCE per fit (by the size of its
     // first round), so that every point of a fit is evaluated by the same variant (they differ in the order of summation)
-    const int defer = ctx->defer_post < 0 ? ((long)S * misti::nm_slots(N, false) <= kDeferPostMaxItems ? 1 : 0) : (ctx->defer_post != 0);
+    const int defer = ctx->defer_post < 0 ? ((long)S * misti::nm_slots(N, false) <= kDeferPostMaxItems ? 1 : 2) : ctx->defer_post;
     // one round: propose (packs the points behind the device-side counter), evaluate, apply
     auto round_body = [&]() -> int {
         misti_fit_propose_kernel<<<gb, tb, 0, sm>>>(S, cfg, bh, st, d_par, d_bm, d_br, d_list, ctx->d_status, d_fc, look_max, B);

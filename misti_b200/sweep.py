@@ -183,6 +183,8 @@ class Sweep:
         fs = "fixed = [" + ", ".join(str(v) for v in fixed) + "]" if fixed else ""
         os_ = "optim = [" + ", ".join(str(v) for v in x) + "]" if x else ""
         mig = fs + "\t" + os_ if fs and os_ else fs + os_
-        t = sum(self.times[0:ceil(float(m["splitT"]))]) * scaleTime
+        # MiSTI.py:240 sums the caller's list AFTER the constructor has cut the split interval in two (fractional split
+        # times): of that interval only the fraction counts -- the model's own (cut) grid, not the sweep's
+        t = sum(m["host"].times[0:ceil(float(m["splitT"]))]) * scaleTime
         row = int(res["row"][k]) if bs_id is None else bs_id
         return "bs_id = %s \tsplitT = %s \ttime = %s \tmigration rates %s \tllh = %s" % (row, m["splitT"], t, mig, res["llh"][k])

@@ -566,7 +566,7 @@ def test_post_split_pass_in_the_jsfs_kernel(golden_datasets):
     B = 203
     params = np.column_stack([10 ** rng.uniform(-3, 0.7, B)])
     res = {}
-    for defer in ("0", "1"):
+    for defer in ("0", "1", "2"):
         os.environ["MISTI_DEFER_POST"] = defer
         try:
             eng = misti_b200.Engine(0)
@@ -593,6 +593,11 @@ def test_post_split_pass_in_the_jsfs_kernel(golden_datasets):
         assert relerr(b["lc"][ok], a["lc"][ok]) < 1e-13
     # asking for the rates does not change the likelihoods
     assert np.array_equal(res["1"][0]["llh"], res["1"][1]["llh"], equal_nan=True)
+    # the pass as a kernel of its own (large batches; knob value 2) is the pass in the JSFS kernel's lanes, bit for bit
+    for k in range(3):
+        for key in ("llh", "jafs", "lc", "status"):
+            if key in res["1"][k]:
+                assert np.array_equal(res["2"][k][key], res["1"][k][key], equal_nan=True), (k, key)
 
 
 @pytest.mark.gpu
@@ -679,6 +684,21 @@ def test_command_line_reproduces_the_reference_run(capsys, tmp_path):
     lines = [ln for ln in text.splitlines() if ln.startswith("bs_id = ")]
     assert len(lines) == 6 and all("llh = -" in ln for ln in lines)
     assert sorted({ln.split("\t")[1].strip() for ln in lines}) == ["splitT = 39", "splitT = 40", "splitT = 41"]
+    # bootstrap rows at ONE split time, with the `st` token and no --st-grid (the split time arrives as a float from argparse)
+    rc = cli.main(["m1.psmc", "m2.psmc", "bs.sfs", "40", "-uf", "-mi", "1", "4", "st", "3", "1", "--cpfit", "--bs-rows", "0", "2"] + common)
+    text = capsys.readouterr().out
+    assert rc == 0
+    rows3 = [ln for ln in text.splitlines() if ln.startswith("bs_id = ")]
+    assert len(rows3) == 3 and [ln.split("\t")[0].strip() for ln in rows3] == ["bs_id = 0", "bs_id = 1", "bs_id = 2"]
+    assert rows3[0].split("llh = ")[1] == [ln for ln in lines if ln.startswith("bs_id = 0 ") and "splitT = 40" in ln][0].split("llh = ")[1]
+    # a fractional split time in sweep mode: `time =` counts only the fraction of the cut interval, as MiSTI.py:240 does
+    rc = cli.main(["m1.psmc", "m2.psmc", "bs.sfs", "40.5", "-uf", "--cpfit", "--bs-rows", "0", "0"] + common)
+    text = capsys.readouterr().out
+    frac = [ln for ln in text.splitlines() if ln.startswith("bs_id = ")][0]
+    rc = cli.main(["m1.psmc", "m2.psmc", "bs.sfs", "40.5", "-uf", "--cpfit", "-bs", "0"] + common)
+    single = [ln for ln in capsys.readouterr().out.splitlines() if ln.startswith("bs_id = ")][0]
+    assert float(frac.split("time = ")[1].split()[0]) == float(single.split("time = ")[1].split()[0])
+    assert relerr(float(frac.split("llh = ")[1]), float(single.split("llh = ")[1])) < 1e-12
 
 
 @pytest.mark.gpu

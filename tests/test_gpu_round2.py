@@ -103,11 +103,8 @@ def test_full_bootstrap_sweep_1001_rows_times_9_split_times(engine):
     sample = [0, 4, 9 * 500 + 2, 9 * 1000 + 8, 9 * 77 + 5]
     alone = sw.solve(pairs=[(int(res["model"][k]), int(res["row"][k])) for k in sample], tol=1e-4)
     for j, k in enumerate(sample):
-        for key in ("x", "nfev", "nit"):
+        for key in ("x", "llh", "nfev", "nit"):
             assert np.array_equal(np.asarray(alone[key][j]), np.asarray(res[key][k])), (key, k)
-        # (a small call runs the cpfit post-split sums in the lanes of the JSFS kernel, a large one in the correction chain:
-        # another order of summation)
-        assert relerr(alone["llh"][j], res["llh"][k]) < 1e-12, k
     from scipy import optimize
     # two fits with an interior optimum against scipy around the oracle (where the rate is fitted to zero the simplex walks
     # down to m ~ 1e-8, where the REFERENCE's own likelihood is inaccurate -- inv(M) of a nearly singular generator, error ~

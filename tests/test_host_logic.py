@@ -78,3 +78,17 @@ def test_negative_parameter_short_circuits_without_a_device(capsys):
     assert M.JAFSLikelihood([-0.1]) == -np.inf  # MigrationInference.py:569-572: returns before any evaluation
     assert MigrationInference.COUNT_LLH == before + 1
     assert "Hit negative value of migration rate" in capsys.readouterr().out
+
+
+def test_st_token_of_the_sweep_command_line(capsys):
+    """`-mi 1 4 st 3 1` (test.bs/din_sar.bs.sh:29-38): the token stands for the split INDEX.  argparse delivers -st as a float;
+    the substitution must write "40", which SetModel's int() accepts, and refuse a fractional split time."""
+    import pytest
+    from misti_b200.cli import _subst
+    assert _subst([["1", "4", "st", "3", "1"]], 40.0) == [["1", "4", "40", "3", "1"]]
+    assert _subst([["1", "4", "st", "3", "1"]], 37) == [["1", "4", "37", "3", "1"]]
+    assert int(_subst([["1", "4", "st", "3", "1"]], 40.0)[0][2]) == 40
+    assert _subst([["2", "5", "12", "0.8", "1"]], 40.5) == [["2", "5", "12", "0.8", "1"]]  # no token: nothing to substitute
+    with pytest.raises(SystemExit):
+        _subst([["1", "4", "st", "3", "1"]], 40.5)
+    assert "whole split time" in capsys.readouterr().out
