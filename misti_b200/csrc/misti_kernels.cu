@@ -924,14 +924,18 @@ __global__ void misti_fit_apply_kernel(int S, misti::NmConfig cfg, FitState st, 
             fc[FC_POINTS_LO] = (int)(lo + add);
             if (lo + add < lo) fc[FC_POINTS_HI] += 1;
         }
-        // The time slice follows the work: when most chains of a round could not finish, the typical item is longer than the
-        // slice and cutting it only adds rounds -- double it; when nothing was cut, let it fall back slowly towards its
-        // minimum, so that an outlier (a run-away correction among ordinary ones) is cut again.
+        // The time slice follows the work.  A chain that is cut advances by one slice per ROUND, and a round lasts at least as
+        // long as its ordinary chains take: slicing trades the latency of the cut chains (and of their simplices) for that of
+        // all the others.  With f = the share of this round's chains that were cut: most of them (f > 1/2) -- the typical chain
+        // is longer than the slice, cutting only adds rounds: double it; otherwise minimum x (1 + 8 f): short while the
+        // run-away chains are a few among thousands of ordinary ones, long when the fit is down to a few simplices and the
+        // cut ones ARE the critical path.
         const int done = fc[FC_SLICE_DONE], pend = fc[FC_SLICE_PEND];
-        if (2 * pend > done + pend) fc[FC_SLICE_US] = fc[FC_SLICE_US] < (1 << 24) ? 2 * fc[FC_SLICE_US] : fc[FC_SLICE_US];
-        else if (pend == 0 && fc[FC_SLICE_US] > fc[FC_SLICE_MIN]) {
-            const int v = fc[FC_SLICE_US] - fc[FC_SLICE_US] / 8;
-            fc[FC_SLICE_US] = v > fc[FC_SLICE_MIN] ? v : fc[FC_SLICE_MIN];
+        if (done + pend > 0) {
+            long long v;
+            if (2 * pend > done + pend) v = 2LL * fc[FC_SLICE_US];
+            else v = fc[FC_SLICE_MIN] + 8LL * fc[FC_SLICE_MIN] * pend / (done + pend);
+            fc[FC_SLICE_US] = v < (1 << 24) ? (int)v : (1 << 24);
         }
         fc[FC_SLICE_DONE] = 0;
         fc[FC_SLICE_PEND] = 0;

@@ -71,13 +71,17 @@ def main():
 
     def on_device(xs):  # the local searches as streams of device launches (Engine.nelder_mead); same decisions as the host driver
         return eng.nelder_mead(xs, mids, np.zeros(walkers, dtype=np.int32), flags=sw.flags)
-    host_driver = os.environ.get("MISTI_TTF_HOST_DRIVER") == "1"
-    r = basinhopping_batch(fun, x0, niter=niter, T=0.5, seeds=[2024 + w for w in range(walkers)],
-                           local_solver=None if host_driver else on_device)
+    mode = os.environ.get("MISTI_TTF_MODE", "device_walkers")  # device_walkers | lockstep_hops | host_driver
+    seeds = [2024 + w for w in range(walkers)]
+    if mode == "device_walkers":  # round 2: walkers advance independently on the device (misti_fit)
+        r = eng.basinhopping(x0, mids, np.zeros(walkers, dtype=np.int32), seeds=seeds, flags=sw.flags, niter=niter, T=0.5, stepsize=0.5)
+    else:  # round 1: hops in lock step on the host, local searches on the device or host-driven
+        r = basinhopping_batch(fun, x0, niter=niter, T=0.5, seeds=seeds, local_solver=None if mode == "host_driver" else on_device)
+    host_driver = mode
     dt = time.perf_counter() - t
     best = int(np.argmin(r["fun"]))
     ref = fits["fit_c3_cpfit"]["expect"]
-    out["config3_basinhopping"] = {"gpu_s": dt, "local_search": "host-driven lock step" if host_driver else "on the device", "walkers": walkers, "niter": niter, "best_x": r["x"][best].tolist(),
+    out["config3_basinhopping"] = {"gpu_s": dt, "mode": host_driver, "walkers": walkers, "niter": niter, "best_x": r["x"][best].tolist(),
                                    "best_llh": float(-r["fun"][best]), "scipy_nfev_total": int(r["nfev"].sum()),
                                    "device_evaluations": r["evaluations"], "launches": r["launches"],
                                    "reference_single_nelder_mead_s_1core": ref["seconds"], "reference_single_nfev": len(ref["calls"]),
