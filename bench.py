@@ -10,8 +10,10 @@ default_rng(1234 + rank)).  Prints ONE JSON line.
   value        evaluations/s, whole job, inputs resident in HBM, CUDA-event timed per step.  At N > 1 every timed step
                ends with the path's one collective, the all-gather of the likelihood vectors to every rank
                (misti_b200.parallel.gather_rows_device, device-resident) -- `value_no_collective` is the same without it
-  e2e          the same metric through the public host-buffer API: pinned host buffers, H2D of the parameters, the kernels,
-               (N > 1: the all-gather,) D2H of llh + expected JSFS + status inside the timed region
+  e2e          the same metric through the public host-buffer API (misti_b200.parallel.ShardedEvaluator): pinned host buffers,
+               parameters host -> device, the kernels, (N > 1: the all-gather,) llh + expected JSFS + status device -> host
+               inside the timed region.  The pinned buffers are device-accessible, so the kernels read / write them across
+               PCIe themselves while they compute (--no-zero-copy: staged cudaMemcpyAsync instead, 8 % slower)
   roofline     the dominant kernel (misti_correct_kernel) against the measured FP64 peak of this pool's B200: FLOPs it
                executed (SASS counts of the committed ncu capture) / its CUDA-event time; the second kernel and the
                dense-equivalent figure of SURVEY.md 8d are listed beside it under their own keys
@@ -403,7 +405,7 @@ def run_gpu(args):
         windows.append(win)
 
     # ---- end to end through the public host-buffer API -----------------------------------------
-    shard = ShardedEvaluator(eng, dev, B, 1, want_jafs=True)
+    shard = ShardedEvaluator(eng, dev, B, 1, want_jafs=True, zero_copy=not args.no_zero_copy)
     for _ in range(max(1, args.warmup)):
         shard.evaluate(params_h, mid, flags)
     e2e_ms, _, _, win = timed_steps(lambda: shard.evaluate(params_h, mid, flags), args.steps)
@@ -529,6 +531,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--skip-cpu", action="store_true", help="omit the CPU legs (profiling runs)")
     ap.add_argument("--skip-fits", action="store_true", help="omit the time-to-fit legs (profiling runs)")
+    ap.add_argument("--no-zero-copy", action="store_true", help="e2e at N = 1 through staged copies instead of pinned buffers the kernels access directly")
     ap.add_argument("--walkers", type=int, default=1024, help="basin-hopping walkers per GPU (config 3)")
     ap.add_argument("--fit-niter", type=int, default=100, help="basin-hopping hops per walker (config 3; the reference: 100)")
     args = ap.parse_args()

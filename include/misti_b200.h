@@ -38,8 +38,11 @@ extern "C" {
 #define MISTI_FLAG_CPFIT 2u    /* cpfit=True: fit non-coalescence probabilities                     */
 #define MISTI_FLAG_SMOOTH 4u   /* smooth=True: SmoothConst over runs of equal PSMC rates            */
 #define MISTI_FLAG_UNFOLDED 8u /* unfolded=True: 7-bin likelihood, else 4 folded bins               */
-#define MISTI_FLAG_DEVICE_PTRS 256u /* params/model_ids/lc_inject/llh/jafs/status are DEVICE pointers; the call is
-                                       asynchronous on the context's stream (no host synchronisation)  */
+#define MISTI_FLAG_DEVICE_PTRS 256u /* params/model_ids/lc_inject/llh/jafs/status are DEVICE-ACCESSIBLE pointers; the call is
+                                       asynchronous on the context's stream (no host synchronisation).  Pinned host
+                                       memory qualifies (unified addressing): the kernels then read the parameters and
+                                       write likelihoods, spectra and status across PCIe while they compute, and no
+                                       copy trails the evaluation (misti_b200.parallel.ShardedEvaluator)              */
 
 /* per-item status codes */
 #define MISTI_OK 0

@@ -69,10 +69,10 @@ class ShardedEvaluator:
     its own GPU (Engine.evaluate_device on its torch stream) and ONE all-gather brings the likelihood rows to every rank
      -- the call an optimiser that lives on every rank makes per step.  Buffers are allocated once."""
 
-    def __init__(self, engine, device, n_local, P, group=None, want_jafs=False):
+    def __init__(self, engine, device, n_local, P, group=None, want_jafs=False, zero_copy=True):
         import torch
         import torch.distributed as dist
-        self.engine, self.group, self.device = engine, group, torch.device(device)
+        self.engine, self.group, self.device, self.zero_copy = engine, group, torch.device(device), zero_copy
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
         self.n_local, self.P, self.R = int(n_local), int(P), engine.R
         self.params_d = torch.empty((n_local, max(P, 1)), dtype=torch.float64, device=self.device)
@@ -93,8 +93,27 @@ class ShardedEvaluator:
     def evaluate(self, params_h, model, flags):
         """host shard (pinned tensor [n_local, P]) -> global likelihood rows on the host (pinned), + this shard's status and
         spectra.  H2D of the parameters, the two kernels, the all-gather and the D2H of the results are queued on the
-        current torch stream; returns after they have completed."""
+        current torch stream; returns after they have completed.
+        One rank (no collective): the kernels work on the pinned host buffers DIRECTLY -- pinned memory is device-accessible
+        (unified addressing), so the correction kernel reads its parameters and the JSFS kernel writes likelihoods, spectra
+        and status across PCIe while it computes, and no separate copy trails the step."""
         import torch
+        if self.world == 1 and self.zero_copy and params_h.is_pinned():
+            self.engine.evaluate_device(self.n_local, self.P, params_h.data_ptr() if self.P else None, self.llh_all_h.data_ptr(),
+                                        model=model, flags=flags, status_ptr=self.status_h.data_ptr(),
+                                        jafs_ptr=self.jafs_h.data_ptr() if self.jafs_h is not None else None)
+            torch.cuda.current_stream(self.device).synchronize()
+            return self.llh_all_h, self.status_h, self.jafs_h
+        if self.zero_copy and params_h.is_pinned():
+            # several ranks: parameters, spectra and status cross PCIe from / to the pinned buffers inside the kernels as
+            # above; the likelihood rows go through the all-gather on the device and are copied out
+            self.engine.evaluate_device(self.n_local, self.P, params_h.data_ptr() if self.P else None, self.llh_d.data_ptr(), model=model,
+                                        flags=flags, status_ptr=self.status_h.data_ptr(),
+                                        jafs_ptr=self.jafs_h.data_ptr() if self.jafs_h is not None else None)
+            llh_all = gather_rows_device(self.llh_d, self.world * self.n_local, group=self.group)
+            self.llh_all_h.copy_(llh_all, non_blocking=True)
+            torch.cuda.current_stream(self.device).synchronize()
+            return self.llh_all_h, self.status_h, self.jafs_h
         self.params_d.copy_(params_h, non_blocking=True)
         llh_all = self.evaluate_device(self.params_d, model, flags)
         self.llh_all_h.copy_(llh_all, non_blocking=True)
