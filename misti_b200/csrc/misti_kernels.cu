@@ -1430,7 +1430,9 @@ static int eval_chunk(misti_ctx* ctx, int B, int P, const double* d_params, cons
 #define MISTI_LAUNCH_CORRECT(MINB)                                                                                       \
     if (coop) MISTI_LAUNCH_CORRECT2(MINB, true, 4L * B, 0); else MISTI_LAUNCH_CORRECT2(MINB, false, (long)B, 0)
     if (d_count) {  // the on-device optimiser: the pair of variants, of which the one that suits the round's item count runs
-        if (ctx->correct_coop != 0) MISTI_LAUNCH_CORRECT3(kCorrectMinBlocks, true, 1, 4L * (B < kCoopMaxItems ? B : kCoopMaxItems), ctx->correct_coop < 0 ? 1 : 0);
+        if (ctx->correct_coop != 0)  // (the knob MISTI_CORRECT_COOP = 1 forces the four-lane variant for every round: whole capacity)
+            MISTI_LAUNCH_CORRECT3(kCorrectMinBlocks, true, 1, 4L * ((ctx->correct_coop < 0 && B > kCoopMaxItems) ? kCoopMaxItems : B),
+                                  ctx->correct_coop < 0 ? 1 : 0);
         if (ctx->correct_coop == 0 || (ctx->correct_coop < 0 && B > kCoopMaxItems))
             MISTI_LAUNCH_CORRECT3(kCorrectMinBlocks, false, 1, (long)B, ctx->correct_coop < 0 ? 2 : 0);
     } else if (d_trace) {  // diagnostics: the per-interval solver trace
