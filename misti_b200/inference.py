@@ -376,13 +376,16 @@ class MigrationInference:
             return [res.x, -res.fun]
         return [[], self.JAFSLikelihood([])]
 
-    def SolveBatch(self, tol=1e-4, x0=None):
+    def SolveBatch(self, tol=1e-4, x0=None, globalOpt=False, niter=100, seeds=None):
         """Addition: Solve() for EVERY data row set with SetJAFSBatch at once -- one Nelder-Mead fit per
         row (e.g. per bootstrap replicate), all taken through scipy's decisions on the device (Engine.nelder_mead: no
         host round trip per step, nothing printed per evaluation).  x0: start vector(s) [P] or [R, P]; default = the
         model's initial values as in Solve.  Returns (x [R, P], llh [R], info) with info = the optimiser's dict
         (nit, nfev, status, success as scipy counts them).  Row r of the result equals what Solve(tol) returns for a
-        model whose data are row r."""
+        model whose data are row r.
+        globalOpt: Solve(globalOpt=True) per row instead -- one basin-hopping walker per row on the device
+        (Engine.basinhopping: T = 0.5, scipy's defaults otherwise, `niter` hops; the reference passes no seed, here walker r
+        draws the numbers of numpy.random.default_rng(seeds[r]), default seeds 0, 1, ...)."""
         eng = self._sync_engine()
         P = self.optMisSize + self.optPusSize
         R = len(self._data_rows)
@@ -392,6 +395,13 @@ class MigrationInference:
             return np.zeros((R, 0)), out["llh"][0].copy(), {"nfev": np.ones(R, dtype=np.int64)}
         init = [val[3] for val in self.optMis] + [val[2] for val in self.optPus] if x0 is None else x0
         X0 = np.broadcast_to(np.asarray(init, dtype=np.float64).reshape(-1, P), (R, P)).copy()
+        if globalOpt:
+            r = eng.basinhopping(X0, np.full(R, self._model_id, dtype=np.int32), np.arange(R, dtype=np.int32),
+                                 seeds=list(range(R)) if seeds is None else list(seeds), flags=self._flags(), mixtureTH=self.mixtureTH,
+                                 niter=niter, T=0.5)
+            MigrationInference.COUNT_LLH += r["evaluations"]
+            MigrationInference.CORRECTION_CALLED += r["evaluations"]
+            return r["x"], -r["fun"], r
         r = eng.nelder_mead(X0, np.full(R, self._model_id, dtype=np.int32), np.arange(R, dtype=np.int32), flags=self._flags(),
                             mixtureTH=self.mixtureTH, xatol=tol, fatol=tol, maxiter=1000)
         MigrationInference.COUNT_LLH += r["evaluations"]

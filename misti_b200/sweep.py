@@ -102,7 +102,7 @@ class Sweep:
     # -- fits ------------------------------------------------------------------------------------------
     # up to this many points per round the fits are stepped on the device (Engine.nelder_mead / Engine.basinhopping: no host
     # round trip per step, only the simplices still running are packed into a round); beyond, the host driver takes over
-    DEVICE_NM_MAX_POINTS = 1 << 18
+    DEVICE_NM_MAX_POINTS = (1 << 18) - 4096  # misti_fit: every simplex's own slots + the shared look-ahead region fit one launch
 
     def solve(self, pairs=None, tol=1e-4, globalOpt=False, niter=100, seed=0, speculative=True, on_device="auto"):
         """Fit every (model, row) pair (default: all).  Nelder-Mead with xatol = fatol = tol, maxiter = 1000 as

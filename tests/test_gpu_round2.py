@@ -183,6 +183,13 @@ def test_basinhopping_on_the_device_equals_scipy_around_the_oracle(engine, golde
     alone = engine.basinhopping(X0[:1], [mid], seeds=seeds[:1], flags=CPFIT_UF, niter=niter, T=0.5, stepsize=0.5)
     for k in ("x", "fun", "nfev", "accepted"):
         assert np.array_equal(alone[k][0], got[k][0]), k
+    # the drop-in class: SolveBatch(globalOpt=True) = Solve(globalOpt=True) for every data row, one walker per row
+    from misti_b200 import MigrationInference
+    M = MigrationInference(list(ds["times"]), [list(v) for v in ds["lambdas"]], list(ds["sfs"]), 40, [list(map(str, m)) for m in mi], [],
+                           smooth=True, unfolded=True, cpfit=True, sampleDate=0)
+    M.SetJAFSBatch([list(ds["sfs"])])
+    xb, llhb, info = M.SolveBatch(globalOpt=True, niter=niter, seeds=[seeds[0]])
+    assert np.array_equal(xb[0], got["x"][0]) and llhb[0] == -got["fun"][0] and info["nfev"][0] == refs[0].nfev
     # the host-driven lock-step walkers (misti_b200.optim.basinhopping_batch) take the same path
     from misti_b200.optim import basinhopping_batch
 
