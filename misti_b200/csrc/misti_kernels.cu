@@ -1011,6 +1011,7 @@ struct misti_ctx {
     unsigned long long generation = 0;    // bumped whenever a device buffer moves or a launch argument of the kernels changes
     int nm_use_graph = 1;                 // tuning knob MISTI_NM_GRAPH
     int nm_rounds_per_graph = 4;          // rounds captured in one graph (tuning knob MISTI_NM_ROUNDS)
+    int nm_look_max = kCoopMaxItems;      // look-ahead while a round of look-ahead steps stays below this many items (MISTI_NM_LOOK_MAX)
     int score_kernel = 1;                 // many data rows: likelihood stage as a kernel of its own (knob MISTI_SCORE_KERNEL)
     int fit_slice_us = 200;               // time slice of a correction chain inside the on-device optimiser (MISTI_FIT_SLICE_US)
     bool fit_slice_forced = false;        // the knob was set: slices also in large sweeps
@@ -1213,6 +1214,7 @@ int misti_ctx_create(int device, void* stream, misti_ctx** out) {
     if (const char* e = getenv("MISTI_NM_LOOKAHEAD")) ctx->nm_lookahead = atoi(e);
     if (const char* e = getenv("MISTI_NM_GRAPH")) ctx->nm_use_graph = atoi(e);
     if (const char* e = getenv("MISTI_SCORE_KERNEL")) ctx->score_kernel = atoi(e);
+    if (const char* e = getenv("MISTI_NM_LOOK_MAX")) { const int v = atoi(e); if (v >= 64 && v <= kMaxChunk / 2) ctx->nm_look_max = v; }
     if (const char* e = getenv("MISTI_FIT_SLICE_US")) { const int v = atoi(e); if (v >= 0) { ctx->fit_slice_us = v; ctx->fit_slice_forced = true; } }
     if (const char* e = getenv("MISTI_NM_ROUNDS")) { const int v = atoi(e); if (v >= 1 && v <= 64) ctx->nm_rounds_per_graph = v; }
     if (const char* e = getenv("MISTI_MAX_CHUNK")) {
@@ -1680,7 +1682,7 @@ int misti_fit(misti_ctx* ctx, int32_t S, int32_t N, const double* x0, const int3
     bh.target = opts->target_accept_rate; bh.factor = opts->stepwise_factor; bh.stepsize0 = opts->stepsize;
     // items: every simplex has its own nm_slots(N) slots (fixed, so that an interrupted item keeps its scratch across
     // rounds); behind them the region the look-ahead steps of the few simplices of a late round share
-    const int look_max = kCoopMaxItems;
+    const int look_max = ctx->nm_look_max;
     const int stable_items = S * misti::nm_slots(N, false);
     const long cap = (long)stable_items + (cfg.lookahead ? look_max : 0);
     if (cap > ctx->max_chunk) return fail(ctx, MISTI_E_ARG, "misti_fit: too many simplices for one call");
@@ -1780,7 +1782,7 @@ int misti_fit(misti_ctx* ctx, int32_t S, int32_t N, const double* x0, const int3
                                                      (unsigned long long)cfg.maxiter, (unsigned long long)cfg.maxfev,
                                                      (unsigned long long)flags, mt_bits, (unsigned long long)(size_t)sm,
                                                      (unsigned long long)(long long)bh.niter, (unsigned long long)bh.interval, be_bits,
-                                                     ta_bits, fc_bits, (unsigned long long)defer, (unsigned long long)kRoundsPerGraph, (unsigned long long)budget_ns};
+                                                     ta_bits, fc_bits, (unsigned long long)defer, (unsigned long long)kRoundsPerGraph, (unsigned long long)budget_ns, (unsigned long long)look_max};
         if (ctx->nm_graph && key == ctx->nm_graph_key) {
             exec = ctx->nm_graph;
             launches_per_round = ctx->nm_graph_launches;
