@@ -356,8 +356,12 @@ misti_jsfs_kernel(int B, int P, const double* __restrict__ params, const int* __
 // M~ = [[M, P0], [0, 0]] (45x45, padded to 48) by scaling and squaring of the UNIFORMISED matrix: for
 // T' = T / 2^s with q T' <= 1/2 the series E = sum_k Pois(k; q T') A~^k (A~ = I + M~/q >= 0, sparse x dense
 // products) is summed in shared memory, then squared s times with FP64 tensor-core MMAs (mma.sync m8n8k4.f64,
-// "DMMA").  Every matrix stays non-negative, so the squarings are free of cancellation.  Then
-// P1 = E11 P0 and integralP = last column of E (MigrationInference.SolveDifEq, :530-540).
+// "DMMA").  What is carried is F = E - I, never E: with rates of 1e7 next to rates of 1 the slow states have
+// A~_cc = 1 - r/q with r/q ~ 1e-7, and storing "one minus tiny" costs the tiny part q/r ulps -- 5e-9 in the spectrum,
+// measured against 50-digit values (tests/golden/stiff_exact.json), where the reference's own float64 result is good to
+// 1e-15.  So the series runs on G = M~/q itself, D_k = A~^k - I = D_(k-1) + G D_(k-1) + G (D_0 = 0), F = sum_k Pois(k) D_k,
+// and a squaring is F <- 2 F + F F.  Then P1 = P0 + F11 P0 and integralP = last column of F
+// (MigrationInference.SolveDifEq, :530-540).
 // After the stiff segment(s) the first warp of the block resumes the item's sweep (misti::jsfs_item from the continuation
 // record) and emits its results; should the item meet another stiff segment, the block takes the dense step again.
 // ------------------------------------------------------------------------------------------------
@@ -372,8 +376,9 @@ __device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, do
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
-// C = A * A for 48x48 (ld = kLd) matrices in shared memory.  Each of the 4 warps owns a 24x24 quadrant = 3 x 3 tiles of
-// 8x8 and keeps its 9 accumulator tiles in registers, so a k-step loads 3 + 3 operand fragments for 9 MMAs.
+// C = 2 A + A * A for 48x48 (ld = kLd) matrices in shared memory: one squaring step of F = E - I, (I + F)^2 = I + (2 F + F F).
+// Each of the 4 warps owns a 24x24 quadrant = 3 x 3 tiles of 8x8 and keeps its 9 accumulator tiles in registers, so a
+// k-step loads 3 + 3 operand fragments for 9 MMAs.
 __device__ void dense_square(const double* __restrict__ A, double* __restrict__ C) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int gid = lane >> 2, tig = lane & 3;
@@ -382,7 +387,10 @@ __device__ void dense_square(const double* __restrict__ A, double* __restrict__ 
 #pragma unroll
     for (int i = 0; i < 3; ++i)
 #pragma unroll
-        for (int j = 0; j < 3; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+        for (int j = 0; j < 3; ++j) {
+            acc[i][j][0] = 2.0 * A[(r0 + 8 * i + gid) * kLd + c0 + 8 * j + 2 * tig];
+            acc[i][j][1] = 2.0 * A[(r0 + 8 * i + gid) * kLd + c0 + 8 * j + 2 * tig + 1];
+        }
 #pragma unroll 4
     for (int kk = 0; kk < 12; ++kk) {
         double a[3], b[3];
@@ -512,7 +520,7 @@ misti_stiff_kernel(int P, const double* __restrict__ params, const int* __restri
                 double d = 0.0;
                 if (tid < 44)
                     for (int k = 0; k < 4; ++k) d += (double)misti::d_diag[tid][k] * rate[k];
-                adiag[tid] = tid < 44 ? (q - d) * qinv : (tid == 44 ? 1.0 : 0.0);
+                adiag[tid] = tid < 44 ? -d * qinv : 0.0;  // diagonal of G = M~ / q (NOT of A~ = I + G: see above)
                 aug[tid] = tid < 44 ? Pv[tid] * qinv : 0.0;
                 for (int e = 0; e < 4; ++e) {
                     double c = 0.0;
@@ -528,13 +536,12 @@ misti_stiff_kernel(int P, const double* __restrict__ params, const int* __restri
             int sq = 0;
             double lam = qT;
             while (lam > 0.5) { lam *= 0.5; ++sq; }
-            // E = sum_k Pois(k; lam) A~^k,  Y_k = A~ Y_(k-1), Y_0 = I
+            // F = sum_k Pois(k; lam) D_k,  D_k = A~^k - I = D_(k-1) + G D_(k-1) + G, D_0 = 0 (rows 44..47 of D stay zero)
             const double p0 = exp(-lam);
             for (int idx = tid; idx < 48 * kLd; idx += kStiffThreads) {
-                const int r = idx / kLd, c = idx % kLd;
-                const double v = (r == c && r < 45) ? 1.0 : 0.0;
-                Y[idx] = v;
-                E[idx] = p0 * v;
+                Y[idx] = 0.0;
+                Z[idx] = 0.0;
+                E[idx] = 0.0;
             }
             __syncthreads();
             double p = p0, rr = lam;
@@ -545,18 +552,17 @@ misti_stiff_kernel(int P, const double* __restrict__ params, const int* __restri
                 p *= rr;
                 rr = lam / (k + 1);
                 // entry (r, c) = idx / 48, idx % 48 for idx = tid, tid + 128, ...: 128 = 2 * 48 + 32
-                for (int r = tid / 48, c = tid % 48; r < 45; r += c + 32 >= 48 ? 3 : 2, c = c + 32 >= 48 ? c - 16 : c + 32) {
-                    double acc;
-                    if (r < 44) {
-                        acc = adiag[r] * Ya[r * kLd + c];
+                for (int r = tid / 48, c = tid % 48; r < 44; r += c + 32 >= 48 ? 3 : 2, c = c + 32 >= 48 ? c - 16 : c + 32) {
+                    double acc = adiag[r] * Ya[r * kLd + c];
+                    double gen = r == c ? adiag[r] : (c == 44 ? aug[r] : 0.0);  // G[r][c]
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) acc += coef[r * 4 + e] * Ya[colo[r * 4 + e] + c];
-                        acc += aug[r] * Ya[44 * kLd + c];
-                    } else {
-                        acc = Ya[44 * kLd + c];
+                    for (int e = 0; e < 4; ++e) {
+                        acc += coef[r * 4 + e] * Ya[colo[r * 4 + e] + c];
+                        if (colo[r * 4 + e] == c * kLd) gen += coef[r * 4 + e];
                     }
-                    Yb[r * kLd + c] = acc;
-                    E[r * kLd + c] += p * acc;
+                    const double d = Ya[r * kLd + c] + (acc + gen);
+                    Yb[r * kLd + c] = d;
+                    E[r * kLd + c] += p * d;
                 }
                 __syncthreads();
                 double* t = Ya; Ya = Yb; Yb = t;
@@ -564,18 +570,18 @@ misti_stiff_kernel(int P, const double* __restrict__ params, const int* __restri
                 if (k > 200) { st = MISTI_NONFINITE; break; }
             }
             nterms += k;
-            // squarings (DMMA): E <- E E, sq times
+            // squarings (DMMA): F <- 2 F + F F, sq times
             double* Ea = E; double* Eb = Ya;  // Ya is free now (Yb too)
             for (int j = 0; j < sq; ++j) {
                 dense_square(Ea, Eb);
                 __syncthreads();
                 double* t = Ea; Ea = Eb; Eb = t;
             }
-            // P1 = E11 P0, integral = E[:, 44]
+            // P1 = P0 + F11 P0, integral = F[:, 44]
             if (tid < 44) {
                 double acc = 0.0;
                 for (int c = 0; c < 44; ++c) acc += Ea[tid * kLd + c] * Pv[c];
-                tmp[tid] = acc;
+                tmp[tid] = Pv[tid] + acc;
                 const double I = Ea[tid * kLd + 44];
                 if (it < md.sampleDate) ct->Ia[tid] += I;
                 else ct->Ib[tid] += I;
