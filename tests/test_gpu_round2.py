@@ -254,3 +254,26 @@ def test_walkers_finish_their_hops_and_do_not_depend_on_the_time_slice(golden_da
     for us in ("50", "350"):
         for k in ("x", "fun", "nfev", "accepted", "minimization_failures"):
             assert np.array_equal(res[us][k], res["0"][k], equal_nan=True), (us, k)
+
+
+def test_tiny_migration_rates_against_50_digit_values(engine, golden_datasets):
+    """The device against 50-digit values of the JSFS stage at m = 1e-14 ... 1e-4 (tests/golden/tiny_rate_exact.json): within
+    1e-12 of the exact value throughout, while the reference's own float64 result is off by ~5e-17 / m (5e-3 at m = 1e-14) --
+    where a fit walks to m -> 0 the two optimisers see different objectives for a reason on the reference's side."""
+    with open(os.path.join(ROOT, "tests", "golden", "tiny_rate_exact.json")) as f:
+        gold = json.load(f)
+    ds = golden_datasets["synthetic"]
+    engine.clear_models()
+    gid = engine.add_grid(ds["times"], ds["lambdas"])
+    mid = engine.add_model(gid, 40, 0, bands=[(1, 5, 12, 0.8, 0)])
+    engine.set_data([ds["sfs"]], True)
+    pts = gold["points"]
+    inj = np.zeros((len(pts), engine.numT_max, 2))
+    for k, pt in enumerate(pts):
+        inj[k, :len(pt["lc"])] = np.array(pt["lc"])
+    out = engine.evaluate(np.array([[pt["m"]] for pt in pts]), model=mid, flags=CPFIT_UF, lc_inject=inj, want=("jafs", "status"))
+    for k, pt in enumerate(pts):
+        assert out["status"][k] == 0
+        exact = [float(v) for v in pt["jafs_exact"]]
+        print("m", pt["m"], "device vs exact", relerr(out["jafs"][k], exact), "reference vs exact", pt["reference_jafs_relerr_vs_exact"])
+        assert relerr(out["jafs"][k], exact) < 1e-12 and relerr(out["llh"][k, 0], pt["llh_exact"]) < 1e-11, pt["m"]

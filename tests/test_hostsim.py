@@ -369,3 +369,24 @@ def test_solver_iterates_match_the_reference_call_by_call(hostsim, golden_datase
             assert equal == n, (name, equal, n)
             assert nfev == sum(c["nfev"] for c in gold["calls"]), name
     assert total_equal >= 0.97 * total_calls, (total_equal, total_calls)
+
+
+def test_tiny_migration_rates_against_50_digit_values(hostsim, golden_datasets):
+    """Where a fitted rate walks to zero (m = 1e-14 ... 1e-4) the REFERENCE loses ~5e-17 / m: SolveDifEq integrates with
+    inv(M)(P1 - P0) of a generator that is singular at m = 0 (MigrationInference.py:530-540).  tests/golden/tiny_rate_exact.json
+    holds, per rate, the reference's result and the 50-digit value of the same stage for the reference's own rates (mpmath,
+    tests/golden/gen_tiny_rate_exact.py): the reference is off by 5e-3 at m = 1e-14 and 1.6e-9 at m = 1e-8; the
+    uniformised sweep has no inverse and must stay at 1e-12 from the exact value throughout."""
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "tiny_rate_exact.json")) as f:
+        gold = json.load(f)
+    for pt in gold["points"]:
+        case = dict(gold["case"], params=[pt["m"]])
+        rc, raw, jn, llh, terms = _jsfs(hostsim, golden_datasets, case, pt["lc"])
+        assert rc == 0
+        exact = [float(v) for v in pt["jafs_exact"]]
+        assert relerr(jn, exact) < 1e-12, (pt["m"], relerr(jn, exact))
+        assert relerr(llh, pt["llh_exact"]) < 1e-11, pt["m"]
+        if pt["m"] <= 1e-10:  # ... where the reference itself is outside 1e-9 of the exact value
+            assert pt["reference_jafs_relerr_vs_exact"] > 1e-9 and relerr(jn, pt["reference_jafs"]) > 1e-9
