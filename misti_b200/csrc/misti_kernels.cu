@@ -1688,10 +1688,14 @@ int misti_fit(misti_ctx* ctx, int32_t S, int32_t N, const double* x0, const int3
     bh.target = opts->target_accept_rate; bh.factor = opts->stepwise_factor; bh.stepsize0 = opts->stepsize;
     // items: every simplex has its own nm_slots(N) slots (fixed, so that an interrupted item keeps its scratch across
     // rounds); behind them the region the look-ahead steps of the few simplices of a late round share
-    const int look_max = ctx->nm_look_max;
+    int look_max = ctx->nm_look_max;
     const int stable_items = S * misti::nm_slots(N, false);
+    if (stable_items > ctx->max_chunk) return fail(ctx, MISTI_E_ARG, "misti_fit: too many simplices for one call");
+    if (cfg.lookahead && (long)stable_items + look_max > ctx->max_chunk) {  // a launch holds at most max_chunk items: the shared
+        look_max = ctx->max_chunk - stable_items;                           // look-ahead region takes what the simplices' own slots leave
+        if (look_max < misti::nm_slots(N, true)) { look_max = 0; cfg.lookahead = 0; }
+    }
     const long cap = (long)stable_items + (cfg.lookahead ? look_max : 0);
-    if (cap > ctx->max_chunk) return fail(ctx, MISTI_E_ARG, "misti_fit: too many simplices for one call");
     const int B = (int)cap;
     // Time slice of the correction chains inside a round (tuning knob MISTI_FIT_SLICE_US; 0 = chains are never interrupted).
     // Walkers and small sweeps run in the latency regime, where one run-away chain (ten times the ordinary one) would hold up

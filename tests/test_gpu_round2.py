@@ -277,3 +277,14 @@ def test_tiny_migration_rates_against_50_digit_values(engine, golden_datasets):
         exact = [float(v) for v in pt["jafs_exact"]]
         print("m", pt["m"], "device vs exact", relerr(out["jafs"][k], exact), "reference vs exact", pt["reference_jafs_relerr_vs_exact"])
         assert relerr(out["jafs"][k], exact) < 1e-12 and relerr(out["llh"][k, 0], pt["llh_exact"]) < 1e-11, pt["m"]
+
+
+def test_small_launches_and_short_time_slices_change_nothing():
+    """tools/sanitize_case.py: every kernel of the library on a small case, once with launches of at most 3 000 items and
+    time slices of 30 us (several chunks per call, the per-row reduction merged across chunks, chains interrupted many
+    times, the look-ahead region squeezed) and once with the defaults -- all 44 result arrays bit for bit the same."""
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "sanitize_case.py")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "differing: []" in r.stdout
