@@ -288,3 +288,34 @@ def test_small_launches_and_short_time_slices_change_nothing():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "sanitize_case.py")], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "differing: []" in r.stdout
+
+
+def test_sharded_evaluator_zero_copy_equals_staged_copies(golden_datasets):
+    """misti_b200.parallel.ShardedEvaluator (the host-buffer call bench.py times end to end): with pinned buffers the kernels
+    read the parameters and write likelihoods, spectra and status across PCIe themselves (MISTI_FLAG_DEVICE_PTRS with
+    device-accessible host memory); the results are those of the staged-copy path and of Engine.evaluate, bit for bit."""
+    import torch
+    import misti_b200
+    from misti_b200.parallel import ShardedEvaluator
+    ds = golden_datasets["synthetic"]
+    dev = torch.device("cuda", 0)
+    stream = torch.cuda.Stream(dev)
+    with torch.cuda.stream(stream):
+        eng = misti_b200.Engine(0, stream=stream.cuda_stream)
+        gid = eng.add_grid(ds["times"], ds["lambdas"])
+        mid = eng.add_model(gid, 40, 0, bands=[(1, 5, 12, 0.8, 0)])
+        eng.set_data([ds["sfs"], ds["bs_rows"][1]], True)
+        B = 3001
+        p = torch.from_numpy(np.random.default_rng(5).uniform(-0.1, 5.0, (B, 1))).pin_memory()
+        ref = eng.evaluate(p.numpy(), model=mid, flags=CPFIT_UF, want=("jafs", "status"))
+        outs = []
+        for zc in (True, False):
+            sh = ShardedEvaluator(eng, dev, B, 1, want_jafs=True, zero_copy=zc)
+            llh, status, jafs = sh.evaluate(p, mid, CPFIT_UF)
+            outs.append((llh.numpy().copy(), status.numpy().copy(), jafs.numpy().copy()))
+        eng.close()
+    for llh, status, jafs in outs:
+        assert np.array_equal(llh, ref["llh"], equal_nan=True) and np.array_equal(status, ref["status"])
+        ok = status == 0
+        assert ok.sum() > B // 2 and (~ok).sum() > 0
+        assert np.array_equal(jafs[ok], ref["jafs"][ok])
