@@ -16,6 +16,22 @@ from .inference import MigrationInference
 from .optim import basinhopping_batch, nelder_mead_batch
 
 
+def split_time_interval(best_split_per_row, level=0.975):
+    """The reduction of the reference's bootstrap notebook (test.bs/bs_conf_int.ipynb: conf_int_bs): row 0 is the data, rows
+    1.. are bootstrap replicates, each with the split time of its highest likelihood; returns dict(interval = Student-t interval
+    of the replicates' mean at `level` (the notebook's scipy.stats.t.interval(0.975, n - 1, loc = mean, scale = sem)),
+    from_data = row 0's split time, histogram = {split time: replicates})."""
+    from collections import Counter
+    from scipy import stats
+    best = [float(v) for v in best_split_per_row]
+    a = np.array(best[1:], dtype=np.float64)
+    if a.size < 2:
+        raise ValueError("need the data row and at least two bootstrap replicates")
+    sem = stats.sem(a)
+    lo, hi = stats.t.interval(level, len(a) - 1, loc=np.mean(a), scale=sem) if sem > 0 else (float(np.mean(a)), float(np.mean(a)))
+    return {"interval": (float(lo), float(hi)), "from_data": best[0], "histogram": dict(Counter(best[1:]))}
+
+
 class Sweep:
     def __init__(self, times, lambdas, rows, unfolded=False, cpfit=False, smooth=True, trueEPS=False, sampleDate=0,
                  mixtureTH=0.0, engine=None, device=0):
@@ -98,6 +114,20 @@ class Sweep:
         MigrationInference.COUNT_LLH += M
         idx = out["row_best_item"].astype(np.int64)
         return {"model": idx, "splitT": np.array([self.models[i]["splitT"] for i in idx]), "llh": out["row_best_llh"]}
+
+    def split_time_confidence(self, res=None, level=0.975):
+        """Confidence interval of the split time over the bootstrap rows, as the reference's notebook computes it from one
+        result line per (row, split time): per row the split time of the highest likelihood -- at fixed parameters reduced on
+        the device (argmax_split), or taken from a solve() result `res` (fitted likelihoods) -- then split_time_interval."""
+        R = self.rows.shape[0]
+        if res is None:
+            best = self.argmax_split()["splitT"]
+        else:
+            best = np.empty(R)
+            for r in range(R):
+                k = np.nonzero(np.asarray(res["row"]) == r)[0]
+                best[r] = self.models[int(np.asarray(res["model"])[k[np.argmax(np.asarray(res["llh"])[k])]])]["splitT"]
+        return split_time_interval(best, level)
 
     # -- fits ------------------------------------------------------------------------------------------
     # up to this many points per round the fits are stepped on the device (Engine.nelder_mead / Engine.basinhopping: no host

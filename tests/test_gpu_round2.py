@@ -91,6 +91,9 @@ def test_full_bootstrap_sweep_1001_rows_times_9_split_times(engine):
     best = sw.argmax_split()
     assert np.array_equal(best["model"], np.argmax(llh, axis=0)) and np.array_equal(best["llh"], llh.max(axis=0))
     assert set(best["splitT"].tolist()) <= set(sts)
+    ci = sw.split_time_confidence()  # the notebook's confidence interval over the 1 000 replicates, from the device's reduction
+    assert ci["from_data"] == best["splitT"][0] and sum(ci["histogram"].values()) == 1000
+    assert ci["interval"][0] <= np.mean(best["splitT"][1:]) <= ci["interval"][1]
     # (b) one migration band up to the split, optimised: 9 009 fits
     sw = Sweep(inp.times, inp.lambdas, bs, unfolded=True, cpfit=True, smooth=True, engine=engine)
     for st in sts:
@@ -105,6 +108,9 @@ def test_full_bootstrap_sweep_1001_rows_times_9_split_times(engine):
     for j, k in enumerate(sample):
         for key in ("x", "llh", "nfev", "nit"):
             assert np.array_equal(np.asarray(alone[key][j]), np.asarray(res[key][k])), (key, k)
+    ci = sw.split_time_confidence(res)  # ... and from the fitted likelihoods of the 9 009 fits
+    fitted_best = np.array([sts[int(np.argmax(res["llh"][9 * r:9 * r + 9]))] for r in range(1001)])
+    assert ci["from_data"] == fitted_best[0] and ci["histogram"] == {float(k): int(v) for k, v in zip(*np.unique(fitted_best[1:], return_counts=True))}
     from scipy import optimize
     # two fits with an interior optimum against scipy around the oracle (where the rate is fitted to zero the simplex walks
     # down to m ~ 1e-8, where the REFERENCE's own likelihood is inaccurate -- inv(M) of a nearly singular generator, error ~

@@ -92,3 +92,20 @@ def test_st_token_of_the_sweep_command_line(capsys):
     with pytest.raises(SystemExit):
         _subst([["1", "4", "st", "3", "1"]], 40.5)
     assert "whole split time" in capsys.readouterr().out
+
+
+def test_split_time_interval_is_the_notebooks_reduction():
+    """misti_b200.sweep.split_time_interval against the formulas of test.bs/bs_conf_int.ipynb (conf_int_bs): per replicate the
+    split time of the highest likelihood, Student-t interval of their mean, histogram; row 0 (the data) kept apart."""
+    from collections import Counter
+    import scipy.stats as st
+    from misti_b200.sweep import split_time_interval
+    rng = np.random.default_rng(8)
+    sts = np.arange(36, 45)
+    llh = -1e4 - (sts[None, :] - 40 - rng.normal(0, 1.2, (101, 1))) ** 2 + rng.normal(0, 0.1, (101, 9))
+    best = sts[np.argmax(llh, axis=1)]
+    got = split_time_interval(best)
+    a = [float(v) for v in best[1:]]  # the notebook: bs_mas[1:], "zero is without bootstrap"
+    want = st.t.interval(0.975, len(a) - 1, loc=np.mean(a), scale=st.sem(a))
+    assert got["interval"] == (float(want[0]), float(want[1])) and got["from_data"] == float(best[0])
+    assert got["histogram"] == dict(Counter(a))
