@@ -1848,6 +1848,8 @@ int misti_fit(misti_ctx* ctx, int32_t S, int32_t N, const double* x0, const int3
     // The host keeps two batches of rounds in flight and looks at the counters of the batch before: a last round that
     // packed nothing ends the fit (the rounds queued behind it are empty and cost microseconds).
     for (long g = 0;; ++g) {
+        if (g * kRoundsPerGraph > (1L << 26))  // a fit without budgets that never converges (scipy would loop for ever as well)
+            return fail(ctx, MISTI_E_ARG, "misti_fit: no end after 2^26 rounds (give maxiter / maxfev)");
         if (g >= 2) {
             CK(cudaEventSynchronize(ctx->nm_ev[(g - 2) & 3]));
             // the copy of batch g - 2 may have been overwritten by that of batch g - 1 already: the counters only grow, and
