@@ -12,7 +12,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmisti_b200.so")
 SOURCES = [os.path.join(CSRC, "misti_kernels.cu")]
-HEADERS = [os.path.join(CSRC, n) for n in ("misti_math.cuh", "misti_model.cuh", "misti_jsfs.cuh", "misti_optim.cuh", "misti_tables.h")] + [
+HEADERS = [os.path.join(CSRC, n) for n in ("misti_math.cuh", "misti_model.cuh", "misti_jsfs.cuh", "misti_optim.cuh", "misti_tables.h", "misti_pair.cuh", "misti_pair_code.h")] + [
     os.path.join(ROOT, "include", "misti_b200.h")]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC",
               "-shared"]

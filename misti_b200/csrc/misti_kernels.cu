@@ -28,6 +28,7 @@
 #include <vector>
 
 #include "misti_jsfs.cuh"
+#include "misti_pair.cuh"
 #include "misti_optim.cuh"
 
 namespace {
@@ -55,9 +56,8 @@ static __device__ const unsigned char d_w8[7][8] = MISTI_W8_INIT;
 // MODE 1 = the variant the on-device optimiser launches (item count and item list on the device, interruptible chains);
 // MODE 2 = the diagnostic variant that records the per-interval solver trace (misti_eval_io.solve_trace); 0 = neither: the
 // plain batched evaluation carries none of that code
-template <int MINB, bool COOP, int MODE>
-__global__ void __launch_bounds__(kCorrectThreads, MINB)
-misti_correct_kernel(int B, int P, const double* __restrict__ params, const int* __restrict__ model_ids, int model_default,
+template <bool COOP, int MODE>
+__device__ __forceinline__ void correct_body(int B, int P, const double* __restrict__ params, const int* __restrict__ model_ids, int model_default,
                      const ModelDesc* __restrict__ models, const double* __restrict__ times, const double* __restrict__ lh,
                      const double* __restrict__ gaux, const unsigned* __restrict__ cls_all, unsigned flags, double mixtureTH, const double* __restrict__ lc_inject, int numT_max, double* lc,
                      long stride, double* __restrict__ cpost, double* pr_out, int* __restrict__ status, int* __restrict__ nfev,
@@ -161,6 +161,31 @@ misti_correct_kernel(int B, int P, const double* __restrict__ params, const int*
     cpost[2 * stride + b] = cp[2];
     status[b] = st;
     nfev[b] = nf;
+}
+
+template <int MINB, bool COOP, int MODE>
+__global__ void __launch_bounds__(kCorrectThreads, MINB)
+misti_correct_kernel(int B, int P, const double* __restrict__ params, const int* __restrict__ model_ids, int model_default,
+                     const ModelDesc* __restrict__ models, const double* __restrict__ times, const double* __restrict__ lh,
+                     const double* __restrict__ gaux, const unsigned* __restrict__ cls_all, unsigned flags, double mixtureTH, const double* __restrict__ lc_inject, int numT_max, double* lc,
+                     long stride, double* __restrict__ cpost, double* pr_out, int* __restrict__ status, int* __restrict__ nfev,
+                     double* __restrict__ rec, int seg_cap, int* __restrict__ nseg, int* __restrict__ counters, int defer_post,
+                     int n_models, int* __restrict__ solve_trace, const int* __restrict__ count_ptr, int regime,
+                     const int* __restrict__ item_list, misti::ChainCkpt* __restrict__ ckpt, int* __restrict__ slice_ctl, int yield_below) {
+    correct_body<COOP, MODE>(B, P, params, model_ids, model_default, models, times, lh, gaux, cls_all, flags, mixtureTH, lc_inject, numT_max, lc, stride, cpost, pr_out, status, nfev, rec, seg_cap, nseg, counters, defer_post, n_models, solve_trace, count_ptr, regime, item_list, ckpt, slice_ctl, yield_below);
+}
+
+// The plain one-thread-per-item variant with 144 registers per thread: one warp per block, 14 blocks per SM -- still ONE wave for
+// 65 536 items (14 x 148 = 2 072 warps) with 16 registers more than the 128 of the 8 x 64 layout (tuning knob MISTI_CORRECT_MINB = 14)
+__global__ void __maxnreg__(144)
+misti_correct_kernel_r144(int B, int P, const double* __restrict__ params, const int* __restrict__ model_ids, int model_default,
+                     const ModelDesc* __restrict__ models, const double* __restrict__ times, const double* __restrict__ lh,
+                     const double* __restrict__ gaux, const unsigned* __restrict__ cls_all, unsigned flags, double mixtureTH, const double* __restrict__ lc_inject, int numT_max, double* lc,
+                     long stride, double* __restrict__ cpost, double* pr_out, int* __restrict__ status, int* __restrict__ nfev,
+                     double* __restrict__ rec, int seg_cap, int* __restrict__ nseg, int* __restrict__ counters, int defer_post,
+                     int n_models, int* __restrict__ solve_trace, const int* __restrict__ count_ptr, int regime,
+                     const int* __restrict__ item_list, misti::ChainCkpt* __restrict__ ckpt, int* __restrict__ slice_ctl, int yield_below) {
+    correct_body<false, 0>(B, P, params, model_ids, model_default, models, times, lh, gaux, cls_all, flags, mixtureTH, lc_inject, numT_max, lc, stride, cpost, pr_out, status, nfev, rec, seg_cap, nseg, counters, defer_post, n_models, solve_trace, count_ptr, regime, item_list, ckpt, slice_ctl, yield_below);
 }
 
 // Where the results of an item go (the optional pointers may be null)
@@ -347,6 +372,143 @@ misti_jsfs_kernel(int B, int P, const double* __restrict__ params, const int* __
                 if (st == MISTI_OK && !fin) st = MISTI_NONFINITE;
                 emit_item(out, ysm, lane, b, st, raw_c, jn_c, nt, !warp_rows);
             }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2 for large batches: expected JSFS + composite log-likelihood, one PAIR of lanes per item (16 items per warp), the
+// chain's state, integrals and generator in registers (misti_pair.cuh).  Persistent grid; warps draw 16 items at a time.
+// Items with a stiff segment or an infinite last interval are put on the redo list for the 16-lane kernel.
+// ------------------------------------------------------------------------------------------------
+constexpr int kPairWarps = 4;
+constexpr int kPairMinBlocks = 2;  // 255 registers per thread, 8 warps per SM
+__global__ void __launch_bounds__(kPairWarps * 32, kPairMinBlocks)
+misti_jsfs_pair_kernel(int B, int P, const double* __restrict__ params, const int* __restrict__ model_ids, int model_default,
+                       const ModelDesc* __restrict__ models, const double* __restrict__ rec, int seg_cap, const int* __restrict__ nseg,
+                       long stride, const double* __restrict__ cpost, ItemOut out, int* __restrict__ redo_list,
+                       int* __restrict__ redo_count, int* __restrict__ work_counter) {
+    __shared__ double ysm_all[kPairWarps * 16][48];
+    const int lane = threadIdx.x & 31, role = lane & 1;
+    double* ysm = ysm_all[threadIdx.x >> 1];
+    while (true) {
+        int i0 = 0;
+        if (lane == 0) i0 = atomicAdd(work_counter, 16);
+        i0 = __shfl_sync(0xffffffffu, i0, 0);
+        if (i0 >= B) break;
+        const int slot = i0 + (lane >> 1);
+        const bool has = slot < B;
+        const int b = has ? slot : B - 1;
+        int st = out.status[b];
+        // an item the correction kernel skipped (model id outside the registered models) runs along inactive
+        const ModelDesc& md = models[st == MISTI_SKIPPED ? 0 : (model_ids ? model_ids[b] : model_default)];
+        const double cp[3] = {cpost[b], cpost[stride + b], cpost[2 * stride + b]};
+        // The 16 items of a warp run in lock step, segment by segment, which only pays when they share a model (the same
+        // segment list); and this kernel has no dense step for stiff segments or the infinite last interval.  So a warp whose
+        // items differ in model hands all of them, and any warp the items that hold such a segment, to the 16-lane kernel
+        // (redo list) before any work is done on them.
+        const double* recb = rec + (long)b * seg_cap * misti::kRecSlots;
+        const int ns = nseg[b];
+        bool redo = false;
+        if (model_ids) {
+            const int mid = model_ids[b], mid0 = __shfl_sync(0xffffffffu, mid, 0);
+            redo = __any_sync(0xffffffffu, has && mid != mid0);
+        }
+        if (has && st == MISTI_OK && !redo) {
+            for (int sg = role; sg < ns; sg += 2) {
+                const int type = misti::seg_type(misti::seg_meta_bits(recb[(long)sg * misti::kRecSlots + 15]));
+                redo |= type == misti::SEG_STIFF || type == misti::SEG_INF;
+            }
+        }
+        redo = __shfl_xor_sync(0xffffffffu, (int)redo, 1) != 0 || redo;
+        misti::PairResult res;
+        misti::jsfs_pair_item(md, has && st == MISTI_OK && !redo, params + (long)b * P, recb, ns, cp, ysm, &res);
+        res.redo = res.redo || (redo && st == MISTI_OK);
+        // normalise and take the logs (MigrationInference.py:583-613): the seven (unfolded) or four (folded) logs are split
+        // between the two lanes and exchanged
+        const bool unfolded = out.unfolded != 0;
+        double tot = 0.0;
+#pragma unroll
+        for (int c = 0; c < 7; ++c) tot += res.raw[c];
+        double jn[7];
+#pragma unroll
+        for (int c = 0; c < 7; ++c) jn[c] = res.raw[c] / tot;
+        double a[4];
+        if (unfolded) {
+            a[0] = role ? jn[4] : jn[0]; a[1] = role ? jn[5] : jn[1]; a[2] = role ? jn[6] : jn[2]; a[3] = role ? 1.0 : jn[3];
+        } else {
+            a[0] = role ? jn[2] + jn[4] : jn[0] + jn[6]; a[1] = role ? jn[3] : jn[1] + jn[5]; a[2] = 1.0; a[3] = 1.0;
+        }
+        double lm[4], lo[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) lm[u] = log(a[u]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) lo[u] = __shfl_xor_sync(0xffffffffu, lm[u], 1);
+        double lj[7];
+        if (unfolded) {
+            lj[0] = role ? lo[0] : lm[0]; lj[1] = role ? lo[1] : lm[1]; lj[2] = role ? lo[2] : lm[2]; lj[3] = role ? lo[3] : lm[3];
+            lj[4] = role ? lm[0] : lo[0]; lj[5] = role ? lm[1] : lo[1]; lj[6] = role ? lm[2] : lo[2];
+        } else {
+            lj[0] = role ? lo[0] : lm[0]; lj[1] = role ? lo[1] : lm[1]; lj[2] = role ? lm[0] : lo[0]; lj[3] = role ? lm[1] : lo[1];
+            lj[4] = 0.0; lj[5] = 0.0; lj[6] = 0.0;
+        }
+        bool fin = true;
+#pragma unroll
+        for (int c = 0; c < 7; ++c) fin = fin && (fabs(lj[c]) <= DBL_MAX);
+        // results (the counterpart of emit_item).  The 16 items of a warp are consecutive, so everything is staged through
+        // the warp's shared memory and stored in contiguous runs (the outputs may be pinned host memory: 8-byte stores
+        // scattered at a 56-byte stride cost a PCIe transaction each).  Items on the redo list are written too -- the
+        // 16-lane kernel overwrites them later in the stream -- except their status, which it reads.
+        const bool live = has && !res.redo;
+        if (has && res.redo && role == 0) redo_list[atomicAdd(redo_count, 1)] = b;
+        if (st == MISTI_OK && !fin) st = MISTI_NONFINITE;
+        const int nv = B - i0 < 16 ? B - i0 : 16;
+        {
+            const int src = (lane & 15) * 2;
+            const int st_i = __shfl_sync(0xffffffffu, st, src), nt_i = __shfl_sync(0xffffffffu, res.nterms, src);
+            const bool live_i = __shfl_sync(0xffffffffu, (int)live, src) != 0;
+            if (lane < 16 && live_i) {
+                out.status[i0 + lane] = st_i;
+                if (out.terms) out.terms[i0 + lane] = nt_i;
+            }
+        }
+        double* wsm = ysm_all[(threadIdx.x >> 5) * 16];  // the warp's 768 doubles
+        const int it16 = lane >> 1;
+        auto flush = [&](double* dst, int per) {
+            __syncwarp();
+            for (int t = lane; t < nv * per; t += 32) dst[(long)i0 * per + t] = wsm[t];
+            __syncwarp();
+        };
+        const bool ok = st == MISTI_OK;
+        // lane 0 of a pair holds categories 0..3, lane 1 categories 4..6
+        if (out.jafs) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (4 * role + u < 7) wsm[it16 * 7 + 4 * role + u] = ok ? (role ? jn[(4 + u) % 7] : jn[u]) : nan("");
+            flush(out.jafs, 7);
+        }
+        if (out.jafs_raw) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (4 * role + u < 7) wsm[it16 * 7 + 4 * role + u] = ok ? (role ? res.raw[(4 + u) % 7] : res.raw[u]) : nan("");
+            flush(out.jafs_raw, 7);
+        }
+        if (out.logs) {  // many data rows: misti_score_rows_kernel writes them from the item's logs
+#pragma unroll
+            for (int u = 0; u < 4; ++u) wsm[it16 * 8 + 4 * role + u] = role ? (u < 3 ? lj[(4 + u) % 7] : 0.0) : lj[u];
+            flush(out.logs, 8);
+            continue;
+        }
+        const double bad = (st == MISTI_NEGATIVE_PARAM || st == MISTI_CORRECTION_FAILED) ? -misti::kInf : nan("");
+        if (out.row_ids) {  // one data row per item
+            const int r = out.row_ids[b];
+            if (role == 0) wsm[it16] = (ok && r >= 0 && r < out.R) ? misti::score_row(out.data + 8 * (long)r, lj) : bad;
+            flush(out.llh, 1);
+        } else if (out.R <= 32) {
+            for (int r = role; r < out.R; r += 2) wsm[it16 * out.R + r] = ok ? misti::score_row(out.data + 8 * (long)r, lj) : bad;
+            flush(out.llh, out.R);
+        } else if (live) {
+            for (int r = role; r < out.R; r += 2) out.llh[(long)b * out.R + r] = ok ? misti::score_row(out.data + 8 * (long)r, lj) : bad;
         }
     }
 }
@@ -1018,6 +1180,7 @@ struct misti_ctx {
     int nm_use_graph = 1;                 // tuning knob MISTI_NM_GRAPH
     int nm_rounds_per_graph = 4;          // rounds captured in one graph (tuning knob MISTI_NM_ROUNDS)
     int nm_look_max = kCoopMaxItems;      // look-ahead while a round of look-ahead steps stays below this many items (MISTI_NM_LOOK_MAX)
+    int jsfs_pair = -1;                   // JSFS kernel with a pair of lanes per item (-1 = large batches; knob MISTI_JSFS_PAIR = 0 / 1)
     int score_kernel = 1;                 // many data rows: likelihood stage as a kernel of its own (knob MISTI_SCORE_KERNEL)
     int fit_slice_us = 200;               // time slice of a correction chain inside the on-device optimiser (MISTI_FIT_SLICE_US)
     bool fit_slice_forced = false;        // the knob was set: slices also in large sweeps
@@ -1220,6 +1383,7 @@ int misti_ctx_create(int device, void* stream, misti_ctx** out) {
     if (const char* e = getenv("MISTI_NM_LOOKAHEAD")) ctx->nm_lookahead = atoi(e);
     if (const char* e = getenv("MISTI_NM_GRAPH")) ctx->nm_use_graph = atoi(e);
     if (const char* e = getenv("MISTI_SCORE_KERNEL")) ctx->score_kernel = atoi(e);
+    if (const char* e = getenv("MISTI_JSFS_PAIR")) ctx->jsfs_pair = atoi(e);
     if (const char* e = getenv("MISTI_NM_LOOK_MAX")) { const int v = atoi(e); if (v >= 64 && v <= kMaxChunk / 2) ctx->nm_look_max = v; }
     if (const char* e = getenv("MISTI_FIT_SLICE_US")) { const int v = atoi(e); if (v >= 0) { ctx->fit_slice_us = v; ctx->fit_slice_forced = true; } }
     if (const char* e = getenv("MISTI_NM_ROUNDS")) { const int v = atoi(e); if (v >= 1 && v <= 64) ctx->nm_rounds_per_graph = v; }
@@ -1449,6 +1613,15 @@ static int eval_chunk(misti_ctx* ctx, int B, int P, const double* d_params, cons
     switch (ctx->correct_minb) {  // register budget per thread: 4 -> 255, 8 -> 128, 12 -> 80 (tuning knob MISTI_CORRECT_MINB)
         case 4: MISTI_LAUNCH_CORRECT(4); break;
         case 12: MISTI_LAUNCH_CORRECT(12); break;
+        case 14:  // one warp per block, 14 blocks per SM: 144 registers per thread and still one wave for 65 536 items
+            if (coop) { MISTI_LAUNCH_CORRECT2(kCorrectMinBlocks, true, 4L * B, 0); }
+            else
+                misti_correct_kernel_r144<<<(unsigned)((B + 31) / 32), 32, 0, ctx->stream>>>(
+                    B, P, d_params, d_model_ids, model_default, ctx->d_models, ctx->d_times, ctx->d_lh, ctx->d_gaux, ctx->d_cls, flags, mixture_th,
+                    d_lc_inject, numT_max, ctx->d_lc, stride, ctx->d_cpost, d_pr, ctx->d_status, ctx->d_nfev, ctx->d_rec, ctx->cap_seg,
+                    ctx->d_nseg, ctx->d_counts, defer_post, (int)ctx->h_models.size(), d_trace, d_count, 0, d_item_list, d_ckpt, d_slice_ctl,
+                    yield_below);
+            break;
         default: MISTI_LAUNCH_CORRECT(kCorrectMinBlocks); break;
     }
 #undef MISTI_LAUNCH_CORRECT
@@ -1475,6 +1648,21 @@ static int eval_chunk(misti_ctx* ctx, int B, int P, const double* d_params, cons
         if ((rc = ensure(ctx, &ctx->d_logs, &ctx->d_logs_cap, (size_t)ctx->cap * 8))) return rc;
         out.logs = ctx->d_logs;
     }
+    // Large plain batches: the pair-of-lanes kernel takes every item it can (all but those with a stiff segment or an
+    // infinite last interval), the 16-lane kernel then runs over the redo list (usually empty: it returns at once).
+    const bool pair_kernel = !d_count && !defer_lanes && (ctx->jsfs_pair < 0 ? B > kDeferPostMaxItems : ctx->jsfs_pair != 0);
+    if (pair_kernel) {
+        int pblocks = (B + 16 * kPairWarps - 1) / (16 * kPairWarps);
+        if (pblocks > ctx->sm_count * kPairMinBlocks) pblocks = ctx->sm_count * kPairMinBlocks;
+        misti_jsfs_pair_kernel<<<pblocks, kPairWarps * 32, 0, ctx->stream>>>(
+            B, P, d_params, d_model_ids, model_default, ctx->d_models, ctx->d_rec, ctx->cap_seg, ctx->d_nseg, stride, ctx->d_cpost, out,
+            ctx->d_queue[1], ctx->d_counts + 6, ctx->d_counts + 5);
+        CK(cudaGetLastError());
+        ctx->launches += 1;
+        misti_jsfs_kernel<kJsfsMinBlocks, false, true><<<blocks, kJsfsWarps * 32, 0, ctx->stream>>>(
+            B, P, d_params, d_model_ids, model_default, ctx->d_models, ctx->d_rec, ctx->cap_seg, ctx->d_nseg, stride, ctx->d_cpost,
+            out, ctx->d_conts, ctx->d_queue[0], ctx->d_counts, ctx->d_counts + 4, ctx->d_post, ctx->d_lh, ctx->d_counts + 6, ctx->d_queue[1]);
+    } else
 #define MISTI_LAUNCH_JSFS(MINB)                                                                                            \
     if (defer_lanes) MISTI_LAUNCH_JSFS2(MINB, true); else MISTI_LAUNCH_JSFS2(MINB, false)
 #define MISTI_LAUNCH_JSFS2(MINB, DEFER) if (d_count) MISTI_LAUNCH_JSFS3(kJsfsMinBlocks, DEFER, true); else MISTI_LAUNCH_JSFS3(MINB, DEFER, false)
