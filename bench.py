@@ -59,7 +59,7 @@ def _first_existing(*names):
     return None
 
 
-EXEC_FLOPS_FILE = _first_existing("r02_executed_flops.json", "r01_executed_flops.json")
+EXEC_FLOPS_FILE = _first_existing("r03_executed_flops.json", "r02_executed_flops.json", "r01_executed_flops.json")
 
 
 def load_dataset():
@@ -455,7 +455,9 @@ def run_gpu(args):
     k1_flops = ex.get("misti_correct_kernel", {}).get("flops_per_item")
     if k1_flops is not None:  # the cpfit post-split pass of a large batch runs as a kernel of its own, inside the same pair of events
         k1_flops += ex.get("misti_post_split_kernel", {}).get("flops_per_item", 0.0)
-    k2_flops = ex.get("misti_jsfs_kernel", {}).get("flops_per_item")
+    pair_kernel = B > 16384 and os.environ.get("MISTI_JSFS_PAIR", "1") != "0"  # large batches: two lanes per item (csrc/misti_pair.cuh)
+    k2_name = "misti_jsfs_pair_kernel" if pair_kernel and "misti_jsfs_pair_kernel" in ex else "misti_jsfs_kernel"
+    k2_flops = ex.get(k2_name, {}).get("flops_per_item")
     src = os.path.relpath(EXEC_FLOPS_FILE, ROOT) if EXEC_FLOPS_FILE else None
 
     def kernel_entry(name, ms, flops, bound):
@@ -468,10 +470,14 @@ def run_gpu(args):
                                                     "issue slots 35 %, FP64 pipe 27 %, stalls: fixed latency 27 %, long scoreboard 27 % (thread-"
                                                     "local stack), no instruction 20 % (86 KB of hot code)); the post-split kernel is FP64-bound "
                                                     "(issue slots 77 %, FP64 pipe 49 %)"),
-               "misti_jsfs_kernel": kernel_entry("misti_jsfs_kernel (+ misti_stiff_kernel, nothing parked)", k2, k2_flops,
-                                                 "shared-memory / shuffle pipe (ncu: 81 % of peak), FP64 pipe 32 %")}
+               "misti_jsfs_kernel": kernel_entry(
+                   k2_name + (" (+ misti_jsfs_kernel over an empty redo list, misti_stiff_kernel with nothing parked)" if k2_name != "misti_jsfs_kernel"
+                              else " (+ misti_stiff_kernel, nothing parked)"), k2, k2_flops,
+                   "FP64 issue with two warps per scheduler (ncu r03: FP64 pipe 48 %, issue slots 44 %, 255 registers, state / integrals / "
+                   "generator in registers, 34 shuffles per mat-vec, shared memory unused in the sweep)" if k2_name != "misti_jsfs_kernel"
+                   else "shared-memory / shuffle pipe (ncu: 81 % of peak), FP64 pipe 32 %")}
     dom = kernels["misti_correct_kernel" if dom_is_k1 else "misti_jsfs_kernel"]
-    tr = ex.get("dram_bytes", {}).get("misti_correct_kernel" if dom_is_k1 else "misti_jsfs_kernel")
+    tr = ex.get("dram_bytes", {}).get("misti_correct_kernel" if dom_is_k1 else k2_name)
     traffic = None if not tr else tr["read"] + tr["write"]  # dram__bytes_read.sum + dram__bytes_write.sum of that kernel, one launch
     alg_bytes = B * (8 + 8 + 56 + 4)  # per item: parameter in, llh + spectrum + status out
     roofline = {"bound": "fp64", "kernel": dom["kernel"], "achieved": dom["tflops"], "peak": peak, "unit": "TFLOP/s",

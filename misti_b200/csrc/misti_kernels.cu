@@ -56,8 +56,9 @@ static __device__ const unsigned char d_w8[7][8] = MISTI_W8_INIT;
 // MODE 1 = the variant the on-device optimiser launches (item count and item list on the device, interruptible chains);
 // MODE 2 = the diagnostic variant that records the per-interval solver trace (misti_eval_io.solve_trace); 0 = neither: the
 // plain batched evaluation carries none of that code
-template <bool COOP, int MODE>
-__device__ __forceinline__ void correct_body(int B, int P, const double* __restrict__ params, const int* __restrict__ model_ids, int model_default,
+template <int MINB, bool COOP, int MODE>
+__global__ void __launch_bounds__(kCorrectThreads, MINB)
+misti_correct_kernel(int B, int P, const double* __restrict__ params, const int* __restrict__ model_ids, int model_default,
                      const ModelDesc* __restrict__ models, const double* __restrict__ times, const double* __restrict__ lh,
                      const double* __restrict__ gaux, const unsigned* __restrict__ cls_all, unsigned flags, double mixtureTH, const double* __restrict__ lc_inject, int numT_max, double* lc,
                      long stride, double* __restrict__ cpost, double* pr_out, int* __restrict__ status, int* __restrict__ nfev,
@@ -161,31 +162,6 @@ __device__ __forceinline__ void correct_body(int B, int P, const double* __restr
     cpost[2 * stride + b] = cp[2];
     status[b] = st;
     nfev[b] = nf;
-}
-
-template <int MINB, bool COOP, int MODE>
-__global__ void __launch_bounds__(kCorrectThreads, MINB)
-misti_correct_kernel(int B, int P, const double* __restrict__ params, const int* __restrict__ model_ids, int model_default,
-                     const ModelDesc* __restrict__ models, const double* __restrict__ times, const double* __restrict__ lh,
-                     const double* __restrict__ gaux, const unsigned* __restrict__ cls_all, unsigned flags, double mixtureTH, const double* __restrict__ lc_inject, int numT_max, double* lc,
-                     long stride, double* __restrict__ cpost, double* pr_out, int* __restrict__ status, int* __restrict__ nfev,
-                     double* __restrict__ rec, int seg_cap, int* __restrict__ nseg, int* __restrict__ counters, int defer_post,
-                     int n_models, int* __restrict__ solve_trace, const int* __restrict__ count_ptr, int regime,
-                     const int* __restrict__ item_list, misti::ChainCkpt* __restrict__ ckpt, int* __restrict__ slice_ctl, int yield_below) {
-    correct_body<COOP, MODE>(B, P, params, model_ids, model_default, models, times, lh, gaux, cls_all, flags, mixtureTH, lc_inject, numT_max, lc, stride, cpost, pr_out, status, nfev, rec, seg_cap, nseg, counters, defer_post, n_models, solve_trace, count_ptr, regime, item_list, ckpt, slice_ctl, yield_below);
-}
-
-// The plain one-thread-per-item variant with 144 registers per thread: one warp per block, 14 blocks per SM -- still ONE wave for
-// 65 536 items (14 x 148 = 2 072 warps) with 16 registers more than the 128 of the 8 x 64 layout (tuning knob MISTI_CORRECT_MINB = 14)
-__global__ void __maxnreg__(144)
-misti_correct_kernel_r144(int B, int P, const double* __restrict__ params, const int* __restrict__ model_ids, int model_default,
-                     const ModelDesc* __restrict__ models, const double* __restrict__ times, const double* __restrict__ lh,
-                     const double* __restrict__ gaux, const unsigned* __restrict__ cls_all, unsigned flags, double mixtureTH, const double* __restrict__ lc_inject, int numT_max, double* lc,
-                     long stride, double* __restrict__ cpost, double* pr_out, int* __restrict__ status, int* __restrict__ nfev,
-                     double* __restrict__ rec, int seg_cap, int* __restrict__ nseg, int* __restrict__ counters, int defer_post,
-                     int n_models, int* __restrict__ solve_trace, const int* __restrict__ count_ptr, int regime,
-                     const int* __restrict__ item_list, misti::ChainCkpt* __restrict__ ckpt, int* __restrict__ slice_ctl, int yield_below) {
-    correct_body<false, 0>(B, P, params, model_ids, model_default, models, times, lh, gaux, cls_all, flags, mixtureTH, lc_inject, numT_max, lc, stride, cpost, pr_out, status, nfev, rec, seg_cap, nseg, counters, defer_post, n_models, solve_trace, count_ptr, regime, item_list, ckpt, slice_ctl, yield_below);
 }
 
 // Where the results of an item go (the optional pointers may be null)
@@ -1613,15 +1589,6 @@ static int eval_chunk(misti_ctx* ctx, int B, int P, const double* d_params, cons
     switch (ctx->correct_minb) {  // register budget per thread: 4 -> 255, 8 -> 128, 12 -> 80 (tuning knob MISTI_CORRECT_MINB)
         case 4: MISTI_LAUNCH_CORRECT(4); break;
         case 12: MISTI_LAUNCH_CORRECT(12); break;
-        case 14:  // one warp per block, 14 blocks per SM: 144 registers per thread and still one wave for 65 536 items
-            if (coop) { MISTI_LAUNCH_CORRECT2(kCorrectMinBlocks, true, 4L * B, 0); }
-            else
-                misti_correct_kernel_r144<<<(unsigned)((B + 31) / 32), 32, 0, ctx->stream>>>(
-                    B, P, d_params, d_model_ids, model_default, ctx->d_models, ctx->d_times, ctx->d_lh, ctx->d_gaux, ctx->d_cls, flags, mixture_th,
-                    d_lc_inject, numT_max, ctx->d_lc, stride, ctx->d_cpost, d_pr, ctx->d_status, ctx->d_nfev, ctx->d_rec, ctx->cap_seg,
-                    ctx->d_nseg, ctx->d_counts, defer_post, (int)ctx->h_models.size(), d_trace, d_count, 0, d_item_list, d_ckpt, d_slice_ctl,
-                    yield_below);
-            break;
         default: MISTI_LAUNCH_CORRECT(kCorrectMinBlocks); break;
     }
 #undef MISTI_LAUNCH_CORRECT
