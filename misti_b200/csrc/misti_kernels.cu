@@ -379,27 +379,34 @@ misti_jsfs_pair_kernel(int B, int P, const double* __restrict__ params, const in
         // an item the correction kernel skipped (model id outside the registered models) runs along inactive
         const ModelDesc& md = models[st == MISTI_SKIPPED ? 0 : (model_ids ? model_ids[b] : model_default)];
         const double cp[3] = {cpost[b], cpost[stride + b], cpost[2 * stride + b]};
-        // The 16 items of a warp run in lock step, segment by segment, which only pays when they share a model (the same
-        // segment list); and this kernel has no dense step for stiff segments or the infinite last interval.  So a warp whose
-        // items differ in model hands all of them, and any warp the items that hold such a segment, to the 16-lane kernel
+        // The 16 items of a warp run in lock step, segment by segment, which only pays when their segment lists agree in
+        // length and in type (sweep / closed-form run) position by position -- the same model, or models that differ in split
+        // time or rates only; and this kernel has no dense step for stiff segments or the infinite last interval.  So a warp
+        // whose items disagree hands all of them, and any warp the items that hold such a segment, to the 16-lane kernel
         // (redo list) before any work is done on them.
         const double* recb = rec + (long)b * seg_cap * misti::kRecSlots;
-        const int ns = nseg[b];
+        const bool act0 = has && st == MISTI_OK;
+        const int ns = act0 ? nseg[b] : 0;
         bool redo = false;
-        if (model_ids) {
-            const int mid = model_ids[b], mid0 = __shfl_sync(0xffffffffu, mid, 0);
-            redo = __any_sync(0xffffffffu, has && mid != mid0);
-        }
-        if (has && st == MISTI_OK && !redo) {
-            for (int sg = role; sg < ns; sg += 2) {
-                const int type = misti::seg_type(misti::seg_meta_bits(recb[(long)sg * misti::kRecSlots + 15]));
-                redo |= type == misti::SEG_STIFF || type == misti::SEG_INF;
-            }
+        unsigned sig = 0;  // which segments are sweeps (positions folded modulo 32; the same model always agrees with itself)
+#pragma unroll 4  // independent loads of lines the correction kernel wrote: in flight together
+        for (int sg = role; sg < ns; sg += 2) {
+            const int type = misti::seg_type(misti::seg_meta_bits(recb[(long)sg * misti::kRecSlots + 15]));
+            redo |= type == misti::SEG_STIFF || type == misti::SEG_INF;
+            if (type == misti::SEG_MIG) sig ^= 1u << (sg & 31);
         }
         redo = __shfl_xor_sync(0xffffffffu, (int)redo, 1) != 0 || redo;
+        sig ^= __shfl_xor_sync(0xffffffffu, sig, 1);
+        {
+            const unsigned actm = __ballot_sync(0xffffffffu, act0 && !redo);
+            const int ref = actm ? __ffs(actm) - 1 : 0;  // the first pair with work sets the pattern
+            const unsigned sig0 = __shfl_sync(0xffffffffu, sig, ref);
+            const int ns0 = __shfl_sync(0xffffffffu, ns, ref);
+            if (__any_sync(0xffffffffu, act0 && !redo && (sig != sig0 || ns != ns0))) redo = true;
+        }
         misti::PairResult res;
-        misti::jsfs_pair_item(md, has && st == MISTI_OK && !redo, params + (long)b * P, recb, ns, cp, ysm, &res);
-        res.redo = res.redo || (redo && st == MISTI_OK);
+        misti::jsfs_pair_item(md, act0 && !redo, params + (long)b * P, recb, ns, cp, ysm, &res);
+        res.redo = res.redo || (redo && act0);
         // normalise and take the logs (MigrationInference.py:583-613): the seven (unfolded) or four (folded) logs are split
         // between the two lanes and exchanged
         const bool unfolded = out.unfolded != 0;

@@ -107,10 +107,12 @@ __device__ __forceinline__ void jsfs_pair_item(const ModelDesc& md, bool active,
     };
 
     const int n_loop = __reduce_max_sync(FULL, nown);
+    double meta_next = nown > 0 ? rec[15] : 0.0;  // the meta word of the next record is fetched a segment ahead
     for (int sg = 0; sg < n_loop; ++sg) {
         const bool have = sg < nown;
         const double* r = rec + (long)sg * kRecSlots;
-        const unsigned long long meta = have ? seg_meta_bits(r[15]) : 0ull;
+        const unsigned long long meta = have ? seg_meta_bits(meta_next) : 0ull;
+        meta_next = sg + 1 < nown ? r[kRecSlots + 15] : 0.0;
         int type = seg_type(meta);
         const int it = seg_it(meta);
         if (type == SEG_STIFF || type == SEG_INF) {  // not for this kernel: the whole item goes to the 16-lane one

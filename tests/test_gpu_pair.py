@@ -116,6 +116,9 @@ def test_large_batches_take_the_pair_kernel_and_agree_with_the_16_lane_kernel(go
             outs[R] = eng.evaluate(p, model_ids=mids, flags=15, want=("jafs", "status", "terms"))
         eng.set_data([ds["sfs"]], True)
         outs["one_model"] = eng.evaluate(p[:, :1].copy(), model=ms[0], flags=15, want=("jafs", "status", "terms"))
+        # a split-time grid interleaved item by item: segment lists of the same type pattern, lock step across models
+        grid = np.array([eng.add_model(gid, st, 0, bands=[(1, 5, 12, 0.8, 0)]) for st in range(36, 45)], dtype=np.int32)
+        outs["split_grid"] = eng.evaluate(p, model_ids=grid[np.arange(n) % 9], flags=15, want=("jafs", "status", "terms"))
         res.append(outs)
         eng.close()
     for key in res[0]:

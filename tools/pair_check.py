@@ -54,6 +54,9 @@ def run():
     mids = np.array([m1, m2, m3, m4, m5, m6, m7], dtype=np.int32)[np.arange(40000) % 7]
     case("mixed", 40000, mids=mids)
     case("mixed_default", 20000, mids=mids[:20000], flags=13)
+    # a split-time grid, interleaved item by item: the segment lists agree in type, so the warps stay in the pair kernel
+    grid = np.array([eng.add_model(gid, st, 0, bands=[(1, 5, 12, 0.8, 0)]) for st in range(36, 45)], dtype=np.int32)
+    case("split_grid", 45000, mids=grid[np.arange(45000) % 9])
     eng.close()
     return res, ms
 
