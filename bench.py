@@ -18,6 +18,7 @@ default_rng(1234 + rank)).  Prints ONE JSON line.
                executed (SASS counts of the committed ncu capture) / its CUDA-event time; the second kernel and the
                dense-equivalent figure of SURVEY.md 8d are listed beside it under their own keys
   batch_sweep  evaluations/s at B = 2, 64, 4096, 65536
+  config_sweep kernel time of one batch for the layouts of BASELINE configs 1, 3, 4 and config 2 in the reference's default mode
   time_to_fit  the second half of the metric, device-timed, fits sharded over the N ranks (strong scaling):
                config 2 (one Nelder-Mead fit), config 5b (9 009 fits = 1 001 bootstrap rows x 9 split times), config 3
                (basin-hopping walkers, 1 024 per GPU)
@@ -322,6 +323,48 @@ def time_to_fit(args, eng, dev, world, rank, barrier, stream):
     return out
 
 
+def config_sweep(local, stream, B, rank):
+    """Kernel time of one batch of B evaluations for the layouts of the other BASELINE configurations (an engine of its own, so
+    that the bench's model stays registered): config 1 (no migration, reference's default mode, the split times 30..60 interleaved),
+    config 3 (two bands + pulse, --cpfit), config 4 (ancient second genome: sampling date 12, --hetloss rates, unfolded, a band from
+    the sampling date, every split time 30..60 interleaved) and config 2 in the reference's default mode."""
+    import json
+    import numpy as np
+    import misti_b200
+    with open(os.path.join(ROOT, "tests", "golden", "datasets.json")) as f:
+        dss = json.load(f)["datasets"]
+    ds, da = dss["synthetic"], dss["synthetic_ancient"]
+    eng = misti_b200.Engine(local, stream=stream.cuda_stream)
+    g = eng.add_grid(ds["times"], ds["lambdas"])
+    ga = eng.add_grid(da["times"], da["lambdas"])
+    sd = int(da["sampleDate"])
+    rng = np.random.default_rng(77 + rank)
+    grid1 = np.array([eng.add_model(g, st, 0) for st in range(30, 61)], dtype=np.int32)
+    m2 = eng.add_model(g, SPLIT_T, 0, bands=[(BAND[0] - 1, BAND[1], BAND[2], BAND[3], 0)])
+    m3 = eng.add_model(g, 40, 0, bands=[(0, 2, 10, 0.3, 0), (1, 5, 12, 0.8, 1)], pulses=[(0, 7, 0.05, 2)])
+    grid4 = np.array([eng.add_model(ga, st, sd, bands=[(1, sd, sd + 8, 0.5, 0)]) for st in range(30, 61)], dtype=np.int32)
+    F = misti_b200
+    cases = [("config1_no_migration_default_mode_split_grid", ds, dict(model_ids=grid1[np.arange(B) % 31]), np.zeros((B, 1)), F.FLAG_CORRECT | F.FLAG_SMOOTH | F.FLAG_UNFOLDED),
+             ("config2_default_mode", ds, dict(model=m2), rng.uniform(0, 5, (B, 1)), F.FLAG_CORRECT | F.FLAG_SMOOTH | F.FLAG_UNFOLDED),
+             ("config3_two_bands_pulse_cpfit", ds, dict(model=m3), np.column_stack([rng.uniform(0, 5, B), rng.uniform(0, 5, B), rng.uniform(0, 0.5, B)]),
+              F.FLAG_CORRECT | F.FLAG_CPFIT | F.FLAG_SMOOTH | F.FLAG_UNFOLDED),
+             ("config4_ancient_sample_split_grid_cpfit", da, dict(model_ids=grid4[np.arange(B) % 31]), rng.uniform(0, 3, (B, 1)),
+              F.FLAG_CORRECT | F.FLAG_CPFIT | F.FLAG_SMOOTH | F.FLAG_UNFOLDED)]
+    out = {}
+    for name, d, kw, par, flags in cases:
+        par = np.ascontiguousarray(np.pad(par, ((0, 0), (0, 3 - par.shape[1]))))  # P = the largest model's parameter count
+        eng.set_data([d["sfs"]], True)
+        ts = []
+        for _ in range(5):
+            o = eng.evaluate(par, flags=flags, want=("status",), **kw)
+            ts.append(eng.last_kernel_ms())
+        k1, k2 = float(np.median([a for a, _ in ts])), float(np.median([b for _, b in ts]))
+        out[name] = {"B": B, "correction_kernels_ms": k1, "jsfs_likelihood_kernels_ms": k2, "evals_per_s_device": B / ((k1 + k2) * 1e-3),
+                     "ok_fraction": float((o["status"] == 0).mean())}
+    eng.close()
+    return out
+
+
 def run_gpu(args):
     import numpy as np
     import torch
@@ -427,6 +470,9 @@ def run_gpu(args):
         sweep.append({"B_per_gpu": n, "ms_per_step": ms / 10, "evals_per_s": world * n * 10 / (ms * 1e-3),
                       "kernel_ms": {"misti_correct_kernel": sum(a) / len(a), "misti_jsfs_kernel": sum(b) / len(b)}})
 
+    # ---- the other BASELINE configurations at the same batch size (device time of the kernels) ----
+    cfgs = None if args.skip_fits else config_sweep(local, stream, min(B, 65536), rank)
+
     # ---- time to fit ---------------------------------------------------------------------------
     t_fit0 = time.monotonic()
     ttf = None if args.skip_fits else time_to_fit(args, eng, dev, world, rank, barrier, stream)
@@ -514,7 +560,7 @@ def run_gpu(args):
             "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": B * 8, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / args.steps,
                     "returns": "llh of every item of the job (all-gathered at N > 1), expected JSFS [7] and status of this rank's items"},
-            "gpu_launches": launches, "roofline": roofline, "batch_sweep": sweep, "cpu_baseline": cpu, "time_to_fit": ttf, "clocks": clocks}
+            "gpu_launches": launches, "roofline": roofline, "batch_sweep": sweep, "config_sweep": cfgs, "cpu_baseline": cpu, "time_to_fit": ttf, "clocks": clocks}
     _emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -69,6 +69,8 @@ misti_correct_kernel(int B, int P, const double* __restrict__ params, const int*
     // behind a counter) and B is only the capacity the grid was sized for.  regime: 0 = run; 1 / 2 = this launch is one of
     // the pair (four lanes per item | one thread per item) of which only the variant that suits the round's size runs.
     constexpr bool FIT = MODE == 1;
+    const bool defer_seg = (defer_post & 2) != 0;  // the segment pre-pass runs as a kernel of its own (misti_segments_kernel)
+    defer_post &= 1;
     if (FIT && count_ptr) {
         const int n = *count_ptr;
         if ((regime == 1 && n > kCoopMaxItems) || (regime == 2 && n <= kCoopMaxItems)) return;
@@ -154,7 +156,7 @@ misti_correct_kernel(int B, int P, const double* __restrict__ params, const int*
     if (st == MISTI_OK) {
         if (!cp_done) misti::post_split_coeffs(md, tt, lcb, kPitch, stride, cp);
         // all per-interval scalar work of the JSFS stage: the item's segment records
-        st = misti::build_segments_item(md, tt, par, lcb, kPitch, stride, rec + (long)b * seg_cap * misti::kRecSlots, &ns, cls);
+        if (!defer_seg) st = misti::build_segments_item(md, tt, par, lcb, kPitch, stride, rec + (long)b * seg_cap * misti::kRecSlots, &ns, cls);
     }
     nseg[b] = ns;
     cpost[b] = cp[0];
@@ -162,6 +164,24 @@ misti_correct_kernel(int B, int P, const double* __restrict__ params, const int*
     cpost[2 * stride + b] = cp[2];
     status[b] = st;
     nfev[b] = nf;
+}
+
+// The segment pre-pass of a large batch as a kernel of its own: the same function on the same rates, one thread per item like
+// the correction kernel -- but it is 14 % of that kernel's serial chain, needs a third of its registers and a few KB of code,
+// so here the machine runs it with four times the warps per scheduler instead of at the end of a latency-bound chain.
+__global__ void __launch_bounds__(128)
+misti_segments_kernel(int B, int P, const double* __restrict__ params, const int* __restrict__ model_ids, int model_default,
+                      const ModelDesc* __restrict__ models, const double* __restrict__ times, const unsigned* __restrict__ cls_all,
+                      const double* __restrict__ lc, long stride, int* __restrict__ status, double* __restrict__ rec, int seg_cap,
+                      int* __restrict__ nseg) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B || status[b] != MISTI_OK) return;  // (the correction kernel left nseg = 0 for the others)
+    const ModelDesc& md = models[model_ids ? model_ids[b] : model_default];
+    int ns = 0;
+    const int st = misti::build_segments_item(md, times + md.grid_off, params + (long)b * P, lc + b, kPitch, stride,
+                                              rec + (long)b * seg_cap * misti::kRecSlots, &ns, cls_all + md.cls_off);
+    nseg[b] = ns;
+    if (st != MISTI_OK) status[b] = st;
 }
 
 // Where the results of an item go (the optional pointers may be null)
@@ -1163,6 +1183,7 @@ struct misti_ctx {
     int nm_use_graph = 1;                 // tuning knob MISTI_NM_GRAPH
     int nm_rounds_per_graph = 4;          // rounds captured in one graph (tuning knob MISTI_NM_ROUNDS)
     int nm_look_max = kCoopMaxItems;      // look-ahead while a round of look-ahead steps stays below this many items (MISTI_NM_LOOK_MAX)
+    int split_segments = -1;              // segment pre-pass as a kernel of its own (-1 = large plain batches in default mode; knob MISTI_SPLIT_SEGMENTS = 0 / 1)
     int jsfs_pair = -1;                   // JSFS kernel with a pair of lanes per item (-1 = large batches; knob MISTI_JSFS_PAIR = 0 / 1)
     int score_kernel = 1;                 // many data rows: likelihood stage as a kernel of its own (knob MISTI_SCORE_KERNEL)
     int fit_slice_us = 200;               // time slice of a correction chain inside the on-device optimiser (MISTI_FIT_SLICE_US)
@@ -1367,6 +1388,7 @@ int misti_ctx_create(int device, void* stream, misti_ctx** out) {
     if (const char* e = getenv("MISTI_NM_GRAPH")) ctx->nm_use_graph = atoi(e);
     if (const char* e = getenv("MISTI_SCORE_KERNEL")) ctx->score_kernel = atoi(e);
     if (const char* e = getenv("MISTI_JSFS_PAIR")) ctx->jsfs_pair = atoi(e);
+    if (const char* e = getenv("MISTI_SPLIT_SEGMENTS")) ctx->split_segments = atoi(e);
     if (const char* e = getenv("MISTI_NM_LOOK_MAX")) { const int v = atoi(e); if (v >= 64 && v <= kMaxChunk / 2) ctx->nm_look_max = v; }
     if (const char* e = getenv("MISTI_FIT_SLICE_US")) { const int v = atoi(e); if (v >= 0) { ctx->fit_slice_us = v; ctx->fit_slice_forced = true; } }
     if (const char* e = getenv("MISTI_NM_ROUNDS")) { const int v = atoi(e); if (v >= 1 && v <= 64) ctx->nm_rounds_per_graph = v; }
@@ -1570,6 +1592,13 @@ static int eval_chunk(misti_ctx* ctx, int B, int P, const double* d_params, cons
         if (defer_mode < 0 || defer_mode > 2) defer_mode = 0;
     }
     const int defer_post = defer_mode != 0 ? 1 : 0;   // what the correction kernel and the rates-on-request path see
+    // large plain batches in the reference's default mode: the segment pre-pass leaves the correction kernel's serial chain
+    // too (misti_segments_kernel).  Measured at 65 536 items: default mode with migration 3.84 -> 3.53 ms; cpfit mode 0.604 ->
+    // 0.624 ms (the chain is shorter by less than the kernel costs), so there the pre-pass stays where it is.
+    const bool coop_k1 = ctx->correct_coop < 0 ? B <= kCoopMaxItems : ctx->correct_coop != 0;
+    const bool split_seg = !d_count && !d_trace && !coop_k1 &&
+                           (ctx->split_segments < 0 ? (B > kDeferPostMaxItems && !(flags & MISTI_FLAG_CPFIT)) : ctx->split_segments != 0);
+    const int defer_k1 = defer_post | (split_seg ? 2 : 0);  // what the correction kernel is told
     const int defer_lanes = defer_mode == 1 ? 1 : 0;  // the JSFS / stiff kernels run the pass themselves
     CK(cudaEventRecord(ctx->ev[0], ctx->stream));
     // small batches: four lanes per item (see misti_correct_kernel); the knob MISTI_CORRECT_COOP = 0 / 1 forces a variant.
@@ -1581,7 +1610,7 @@ static int eval_chunk(misti_ctx* ctx, int B, int P, const double* d_params, cons
         B, P, d_params, d_model_ids, model_default, ctx->d_models, ctx->d_times, ctx->d_lh, ctx->d_gaux, ctx->d_cls, flags, mixture_th, \
         d_lc_inject, \
         numT_max, ctx->d_lc, stride, ctx->d_cpost, d_pr, ctx->d_status, ctx->d_nfev, ctx->d_rec, ctx->cap_seg, ctx->d_nseg, ctx->d_counts, \
-        defer_post, (int)ctx->h_models.size(), d_trace, d_count, REGIME, d_item_list, d_ckpt, d_slice_ctl, yield_below)
+        defer_k1, (int)ctx->h_models.size(), d_trace, d_count, REGIME, d_item_list, d_ckpt, d_slice_ctl, yield_below)
 #define MISTI_LAUNCH_CORRECT(MINB)                                                                                       \
     if (coop) MISTI_LAUNCH_CORRECT2(MINB, true, 4L * B, 0); else MISTI_LAUNCH_CORRECT2(MINB, false, (long)B, 0)
     if (d_count) {  // the on-device optimiser: the pair of variants, of which the one that suits the round's item count runs
@@ -1602,6 +1631,13 @@ static int eval_chunk(misti_ctx* ctx, int B, int P, const double* d_params, cons
 #undef MISTI_LAUNCH_CORRECT2
 #undef MISTI_LAUNCH_CORRECT3
     CK(cudaGetLastError());
+    if (split_seg) {
+        misti_segments_kernel<<<(unsigned)((B + 127) / 128), 128, 0, ctx->stream>>>(
+            B, P, d_params, d_model_ids, model_default, ctx->d_models, ctx->d_times, ctx->d_cls, ctx->d_lc, stride, ctx->d_status, ctx->d_rec,
+            ctx->cap_seg, ctx->d_nseg);
+        CK(cudaGetLastError());
+        ctx->launches += 1;
+    }
     if (defer_mode == 2) {
         misti_post_split_kernel<<<(unsigned)((16L * B + 127) / 128), 128, 0, ctx->stream>>>(
             B, d_model_ids, model_default, ctx->d_models, ctx->d_status, stride, ctx->d_cpost, ctx->d_post, ctx->d_lh, d_count, d_item_list);
