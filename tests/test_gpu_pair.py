@@ -108,7 +108,7 @@ def test_large_batches_take_the_pair_kernel_and_agree_with_the_16_lane_kernel(go
         # runs of 1 500 items per model (homogeneous warps) followed by items whose models alternate
         mids = np.array(ms, dtype=np.int32)[np.concatenate([np.repeat(np.arange(6), 1500) % 6, np.arange(n - 9000) % 6])]
         outs = {}
-        for R in (1, 5, 70):
+        for R in (1, 5, 40, 70):  # staged stores (<= 32 rows), direct stores, the scoring kernel (>= 64)
             rows = [ds["sfs"]] + [list(r) for r in ds.get("bs_rows", [])]
             while len(rows) < R:
                 rows.append([v * (1.0 + 0.01 * len(rows)) for v in ds["sfs"]])
