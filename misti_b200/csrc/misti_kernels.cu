@@ -833,6 +833,71 @@ misti_post_split_kernel(int B, const int* __restrict__ model_ids, int model_defa
     if (has && g.lane() == 3) cpost[3 * stride + b] = ed_in;
 }
 
+// The same pass for large PLAIN batches with FOUR lanes per item, each on a quarter of the intervals (consecutive slices,
+// read straight from the grid's aux rows), joined by one scan of the survival factors and one sum over the four lanes.
+// The 16-lane form spends two thirds of its 55.6 M warp instructions on slice bookkeeping, the scan and the reductions
+// (5.4 intervals per lane against a fixed cost of ~600 instructions); one thread per item has none of that but is a serial
+// chain of 86 logs at 3.5 warps per scheduler (0.055 ms).  Four lanes: 22 intervals per lane, 55 warps per SM.
+__global__ void __launch_bounds__(128)
+misti_post_split_quad_kernel(int B, const int* __restrict__ model_ids, int model_default, const ModelDesc* __restrict__ models,
+                             const int* __restrict__ status, long stride, double* __restrict__ cpost, const double* __restrict__ times,
+                             const double* __restrict__ gaux, const double* __restrict__ lh) {
+    const int gt = blockIdx.x * blockDim.x + threadIdx.x;
+    const int slot = gt >> 2, q = gt & 3;
+    const bool has = slot < B;
+    const int b = has ? slot : 0;
+    const int st = has ? status[b] : MISTI_SKIPPED;
+    const ModelDesc& md = models[(st == MISTI_SKIPPED || !has) ? 0 : (model_ids ? model_ids[b] : model_default)];
+    const bool act = has && st == MISTI_OK && md.splitT < md.numT;
+    const double ed_in = has ? cpost[b] : 1.0;  // read by every lane before lane 0 overwrites the slot
+    const double ed = act ? ed_in : 1.0, wn = 1.0 / (1.0 + ed);
+    const int n = act ? md.numT - 1 - md.splitT : 0, per = (n + 3) >> 2;
+    const int t0 = md.splitT + q * per, t1 = t0 + per < md.splitT + n ? t0 + per : md.splitT + n;
+    const double* tt = times + md.grid_off;
+    const double* ga0 = gaux + misti::kGridAux * (long)md.grid_off;
+    double c6 = 0, c3 = 0, c1 = 0, e1 = 1.0;  // relative to the start of this lane's slice
+    for (int t = t0; t < t1; ++t) {
+        const double T = tt[t];
+        if (T == 0) continue;
+        const double* ga = ga0 + misti::kGridAux * t;
+        const double u = (ga[0] + ed * ga[1]) * wn;   // exp(-lam T), the fitted non-coalescence probability
+        const double q1 = (ga[2] + ed * ga[3]) * wn;  // 1 - u, free of cancellation
+        const double z = -log(u);
+        const double il = z > 0 ? T / z : 0.0;  // 1 / lam
+        const double e3 = e1 * e1 * e1;
+        const double q3 = q1 * (1.0 + u + u * u), q6 = q3 * (1.0 + u * u * u);  // 1 - u^3, 1 - u^6
+        c1 += z > 0 ? e1 * q1 * il : e1 * T;
+        c3 += z > 0 ? e3 * q3 * (il * (1.0 / 3.0)) : e3 * T;
+        c6 += z > 0 ? (e3 * e3) * q6 * (il * (1.0 / 6.0)) : (e3 * e3) * T;
+        e1 *= u;
+    }
+    // survival factor at the start of the slice: product of e1 over the lower lanes of the quad
+    double v = e1;
+    {
+        double t = __shfl_up_sync(0xffffffffu, v, 1, 4);
+        if (q >= 1) v *= t;
+        t = __shfl_up_sync(0xffffffffu, v, 2, 4);
+        if (q >= 2) v *= t;
+    }
+    const double up = __shfl_up_sync(0xffffffffu, v, 1, 4);
+    const double f1 = q == 0 ? 1.0 : up, f3 = f1 * f1 * f1;
+    c1 *= f1; c3 *= f3; c6 *= f3 * f3;
+    if (act && q == 3) {  // the infinite last interval
+        const double* lh_last = lh + 2 * (long)(md.grid_off + md.numT - 1);
+        const double lam = (1.0 + ed) / (1.0 / lh_last[0] + ed / lh_last[1]);
+        const double il = 1.0 / lam, x1 = f1 * e1, x3 = x1 * x1 * x1;
+        c1 += x1 * il; c3 += x3 * (il * (1.0 / 3.0)); c6 += (x3 * x3) * (il * (1.0 / 6.0));
+    }
+#pragma unroll
+    for (int o = 1; o < 4; o <<= 1) {
+        c1 += __shfl_xor_sync(0xffffffffu, c1, o);
+        c3 += __shfl_xor_sync(0xffffffffu, c3, o);
+        c6 += __shfl_xor_sync(0xffffffffu, c6, o);
+    }
+    if (act && q < 3) cpost[q * stride + b] = q == 0 ? c6 : (q == 1 ? c3 : c1);
+    if (has && q == 3) cpost[3 * stride + b] = ed_in;  // kept for the rates-on-request path
+}
+
 // Reduction over the ITEMS of a batch, per data row: best[r] = max_b llh[b][r] and the item that attains it (the first one,
 // as numpy.argmax) -- what the reference's bootstrap notebook computes from 9 009 result lines (test.bs/bs_conf_int.ipynb:
 // per replicate the split time of the highest likelihood), done where the likelihoods are, so that a sweep returns 2 R
@@ -1184,6 +1249,7 @@ struct misti_ctx {
     int nm_rounds_per_graph = 4;          // rounds captured in one graph (tuning knob MISTI_NM_ROUNDS)
     int nm_look_max = kCoopMaxItems;      // look-ahead while a round of look-ahead steps stays below this many items (MISTI_NM_LOOK_MAX)
     int split_segments = -1;              // segment pre-pass as a kernel of its own (-1 = large plain batches in default mode; knob MISTI_SPLIT_SEGMENTS = 0 / 1)
+    int post_quad = 1;                  // plain batches: the post-split kernel with four lanes per item (knob MISTI_POST_QUAD = 0: 16 lanes)
     int jsfs_pair = -1;                   // JSFS kernel with a pair of lanes per item (-1 = large batches; knob MISTI_JSFS_PAIR = 0 / 1)
     int score_kernel = 1;                 // many data rows: likelihood stage as a kernel of its own (knob MISTI_SCORE_KERNEL)
     int fit_slice_us = 200;               // time slice of a correction chain inside the on-device optimiser (MISTI_FIT_SLICE_US)
@@ -1388,6 +1454,7 @@ int misti_ctx_create(int device, void* stream, misti_ctx** out) {
     if (const char* e = getenv("MISTI_NM_GRAPH")) ctx->nm_use_graph = atoi(e);
     if (const char* e = getenv("MISTI_SCORE_KERNEL")) ctx->score_kernel = atoi(e);
     if (const char* e = getenv("MISTI_JSFS_PAIR")) ctx->jsfs_pair = atoi(e);
+    if (const char* e = getenv("MISTI_POST_QUAD")) ctx->post_quad = atoi(e);
     if (const char* e = getenv("MISTI_SPLIT_SEGMENTS")) ctx->split_segments = atoi(e);
     if (const char* e = getenv("MISTI_NM_LOOK_MAX")) { const int v = atoi(e); if (v >= 64 && v <= kMaxChunk / 2) ctx->nm_look_max = v; }
     if (const char* e = getenv("MISTI_FIT_SLICE_US")) { const int v = atoi(e); if (v >= 0) { ctx->fit_slice_us = v; ctx->fit_slice_forced = true; } }
@@ -1638,7 +1705,12 @@ static int eval_chunk(misti_ctx* ctx, int B, int P, const double* d_params, cons
         CK(cudaGetLastError());
         ctx->launches += 1;
     }
-    if (defer_mode == 2) {
+    if (defer_mode == 2 && !d_count && ctx->post_quad) {
+        misti_post_split_quad_kernel<<<(unsigned)((4L * B + 127) / 128), 128, 0, ctx->stream>>>(
+            B, d_model_ids, model_default, ctx->d_models, ctx->d_status, stride, ctx->d_cpost, ctx->d_times, ctx->d_gaux, ctx->d_lh);
+        CK(cudaGetLastError());
+        ctx->launches += 1;
+    } else if (defer_mode == 2) {
         misti_post_split_kernel<<<(unsigned)((16L * B + 127) / 128), 128, 0, ctx->stream>>>(
             B, d_model_ids, model_default, ctx->d_models, ctx->d_status, stride, ctx->d_cpost, ctx->d_post, ctx->d_lh, d_count, d_item_list);
         CK(cudaGetLastError());

@@ -132,6 +132,41 @@ MISTI_HD inline void post_split_cpfit_item(const ModelDesc& md, const double* ti
     if (cpost) { cpost[0] = c6; cpost[1] = c3; cpost[2] = c1; }
 }
 
+// The coefficients of that pass alone, from ed = exp(nc1 - nc0) (the rates are not needed on the path; the gather kernel
+// computes them on request): the same arithmetic in the same order as post_split_cpfit_item, so the two agree bit for bit.
+// `gaux` = the grid's aux rows (grid_aux_row).  One thread; the intervals are independent of each other given ed, so the
+// loop pipelines (four logs in flight).
+MISTI_HD inline void post_split_cpfit_coeffs(const ModelDesc& md, const double* times, const double* lh, double ed,
+                                             const double* gaux, double* cpost) {
+    const int numT = md.numT, splitT = md.splitT;
+    if (!(splitT < numT)) return;
+    const double wn = 1.0 / (1.0 + ed);
+    double c6 = 0, c3 = 0, c1 = 0, e1 = 1.0;
+#pragma unroll 4
+    for (int t = splitT; t < numT - 1; ++t) {
+        const double T = times[t];
+        if (T == 0) continue;
+        const double* ga = gaux + kGridAux * t;
+        const double u = (ga[0] + ed * ga[1]) * wn;
+        const double q1 = (ga[2] + ed * ga[3]) * wn;
+        const double z = -log(u);
+        const double il = z > 0 ? T / z : 0.0;
+        const double e3 = e1 * e1 * e1;
+        const double q3 = q1 * (1.0 + u + u * u), q6 = q3 * (1.0 + u * u * u);
+        c1 += z > 0 ? e1 * q1 * il : e1 * T;
+        c3 += z > 0 ? e3 * q3 * (il * (1.0 / 3.0)) : e3 * T;
+        c6 += z > 0 ? (e3 * e3) * q6 * (il * (1.0 / 6.0)) : (e3 * e3) * T;
+        e1 *= u;
+    }
+    {
+        const int t = numT - 1;
+        const double lam = (1.0 + ed) / (1.0 / lh[2 * t] + ed / lh[2 * t + 1]);
+        const double il = 1.0 / lam, e3 = e1 * e1 * e1;
+        c1 += e1 * il; c3 += e3 * (il * (1.0 / 3.0)); c6 += (e3 * e3) * (il * (1.0 / 6.0));
+    }
+    cpost[0] = c6; cpost[1] = c3; cpost[2] = c1;
+}
+
 // The finite post-split intervals of a model as the lane groups of the JSFS kernel read them (post_split_cpfit_group in
 // misti_jsfs.cuh): lane l of `lanes` owns the `per` consecutive intervals splitT + l per + j, j < per, and value k
 // (E0, E1, 1 - E0, 1 - E1 of grid_aux_row, and T) of its j-th interval sits at out[(k per + j) lanes + l] -- one coalesced

@@ -584,12 +584,13 @@ def test_post_split_pass_in_the_jsfs_kernel(golden_datasets):
     B = 203
     params = np.column_stack([10 ** rng.uniform(-3, 0.7, B)])
     res = {}
-    for defer in ("0", "1", "2"):
-        os.environ["MISTI_DEFER_POST"] = defer
+    for defer in ("0", "1", "2", "2q"):
+        os.environ["MISTI_DEFER_POST"] = defer[0]
+        os.environ["MISTI_POST_QUAD"] = "1" if defer == "2q" else "0"
         try:
             eng = misti_b200.Engine(0)
         finally:
-            del os.environ["MISTI_DEFER_POST"]
+            del os.environ["MISTI_DEFER_POST"], os.environ["MISTI_POST_QUAD"]
         gid = eng.add_grid(ds["times"], ds["lambdas"])
         numT = len(ds["lambdas"])
         mids = [eng.add_model(gid, st, 0, bands=[(1, 5, min(12, st), 0.8, 0)]) for st in (13, 40, 41, 94, numT - 2, numT - 1)]
@@ -601,17 +602,19 @@ def test_post_split_pass_in_the_jsfs_kernel(golden_datasets):
                       # one model for the whole batch: its table is staged in shared memory
                       eng.evaluate(params, model=mids[1], flags=1 | 2 | 4 | 8, want=("jafs", "lc", "status"))]
         eng.close()
-    for k in (0, 2):
-        a, b = res["0"][k], res["1"][k]
-        assert np.array_equal(a["status"], b["status"])
-        ok = a["status"] == 0
-        assert ok.sum() > B // 2
-        assert relerr(b["jafs"][ok], a["jafs"][ok]) < 1e-13
-        assert relerr(b["llh"][ok], a["llh"][ok]) < 1e-12
-        assert relerr(b["lc"][ok], a["lc"][ok]) < 1e-13
+    for other in ("1", "2q"):  # in the JSFS kernel's lanes; four lanes per item in a kernel of its own (plain large batches)
+        for k in (0, 2):
+            a, b = res["0"][k], res[other][k]
+            assert np.array_equal(a["status"], b["status"])
+            ok = a["status"] == 0
+            assert ok.sum() > B // 2
+            assert relerr(b["jafs"][ok], a["jafs"][ok]) < 1e-13
+            assert relerr(b["llh"][ok], a["llh"][ok]) < 1e-12
+            assert relerr(b["lc"][ok], a["lc"][ok]) < 1e-13
     # asking for the rates does not change the likelihoods
     assert np.array_equal(res["1"][0]["llh"], res["1"][1]["llh"], equal_nan=True)
-    # the pass as a kernel of its own (large batches; knob value 2) is the pass in the JSFS kernel's lanes, bit for bit
+    # the pass as a 16-lane kernel of its own (large rounds of the optimiser; knob value 2 without the four-lane form) is the pass
+    # in the JSFS kernel's lanes, bit for bit
     for k in range(3):
         for key in ("llh", "jafs", "lc", "status"):
             if key in res["1"][k]:
