@@ -501,7 +501,7 @@ def run_gpu(args):
     k1_flops = ex.get("misti_correct_kernel", {}).get("flops_per_item")
     if k1_flops is not None:  # the cpfit post-split pass of a large batch runs as a kernel of its own, inside the same pair of events
         k1_flops += ex.get("misti_post_split_kernel", {}).get("flops_per_item", 0.0)
-    pair_kernel = B > 16384 and os.environ.get("MISTI_JSFS_PAIR", "1") != "0"  # large batches: two lanes per item (csrc/misti_pair.cuh)
+    pair_kernel = B > 6144 and os.environ.get("MISTI_JSFS_PAIR", "1") != "0"  # large batches: two lanes per item (csrc/misti_pair.cuh)
     k2_name = "misti_jsfs_pair_kernel" if pair_kernel and "misti_jsfs_pair_kernel" in ex else "misti_jsfs_kernel"
     k2_flops = ex.get(k2_name, {}).get("flops_per_item")
     src = os.path.relpath(EXEC_FLOPS_FILE, ROOT) if EXEC_FLOPS_FILE else None

@@ -40,7 +40,10 @@ constexpr int kCorrectMinBlocks = 8;
 constexpr int kCoopMaxItems = 4096;  // up to here the four-lane variant of K1 still runs at about one warp per scheduler
 constexpr int kJsfsWarps = 4;      // warps per block of the JSFS kernel (8 items per block)
 constexpr int kJsfsMinBlocks = 3;  // occupancy target: caps the kernel at 168 registers per thread (12 warps per SM)
-constexpr int kDeferPostMaxItems = 16384;  // up to here the post-split pass of cpfit mode runs in the JSFS kernel
+constexpr int kDeferPostMaxItems = 16384;  // inside the optimiser: up to here the post-split pass of cpfit mode runs in the JSFS kernel
+constexpr int kLargeBatchItems = 6144;     // plain batches above this take the large-batch kernels (post-split pass with four lanes per
+                                           // item, JSFS kernel with a pair of lanes per item); measured break-even: equal at 4 096 /
+                                           // 6 144 items, 7 % faster at 8 192, 16 % at 16 384 (tools/midsize_probe.py)
 constexpr int kPostSmemDoubles = 1024;  // shared-memory budget of the JSFS kernel for a model's post-split table (8 KB)
 constexpr int kMaxChunk = 1 << 18;  // items per launch: the machine is full from 65 536 on; scratch is ~6 KB per item (records, rates)
 constexpr int kPitch = 2;  // per interval and item the rate buffer holds la0, la1
@@ -1655,7 +1658,7 @@ static int eval_chunk(misti_ctx* ctx, int B, int P, const double* d_params, cons
     int defer_mode = 0;
     if ((flags & MISTI_FLAG_CPFIT) && !d_lc_inject) {
         const int knob = defer_override >= 0 ? defer_override : ctx->defer_post;
-        defer_mode = knob < 0 ? (B <= kDeferPostMaxItems ? 1 : 2) : knob;
+        defer_mode = knob < 0 ? (B <= (d_count ? kDeferPostMaxItems : kLargeBatchItems) ? 1 : 2) : knob;
         if (defer_mode < 0 || defer_mode > 2) defer_mode = 0;
     }
     const int defer_post = defer_mode != 0 ? 1 : 0;   // what the correction kernel and the rates-on-request path see
@@ -1732,7 +1735,7 @@ static int eval_chunk(misti_ctx* ctx, int B, int P, const double* d_params, cons
     }
     // Large plain batches: the pair-of-lanes kernel takes every item it can (all but those with a stiff segment or an
     // infinite last interval), the 16-lane kernel then runs over the redo list (usually empty: it returns at once).
-    const bool pair_kernel = !d_count && !defer_lanes && (ctx->jsfs_pair < 0 ? B > kDeferPostMaxItems : ctx->jsfs_pair != 0);
+    const bool pair_kernel = !d_count && !defer_lanes && (ctx->jsfs_pair < 0 ? B > kLargeBatchItems : ctx->jsfs_pair != 0);
     if (pair_kernel) {
         int pblocks = (B + 16 * kPairWarps - 1) / (16 * kPairWarps);
         if (pblocks > ctx->sm_count * kPairMinBlocks) pblocks = ctx->sm_count * kPairMinBlocks;

@@ -1,5 +1,5 @@
 """GPU parity of the pair-of-lanes JSFS kernel (misti_jsfs_pair_kernel, csrc/misti_pair.cuh): the kernel large batches
-run (B > 16 384), forced here for single items as well (MISTI_JSFS_PAIR = 1) so that the golden vectors of the unmodified
+run (B > 6 144), forced here for single items as well (MISTI_JSFS_PAIR = 1) so that the golden vectors of the unmodified
 reference can be held against it, and compared on large mixed batches with the 16-lane kernel it replaces.
 Tolerance against the reference: 1e-9 relative on every JSFS entry and on llh (BASELINE.json north_star)."""
 import os
@@ -86,7 +86,7 @@ def test_pair_kernel_golden_end_to_end(pair_engine, golden_datasets, golden_case
 
 
 def test_large_batches_take_the_pair_kernel_and_agree_with_the_16_lane_kernel(golden_datasets):
-    """B > 16 384 with the default knobs against MISTI_JSFS_PAIR = 0: mixed models in one batch (warps whose items differ
+    """B > 6 144 with the default knobs against MISTI_JSFS_PAIR = 0: mixed models in one batch (warps whose items differ
     in model, items with stiff segments and a model without a split inside the grid go to the 16-lane kernel through
     the redo list), negative parameters, few and many data rows.  Same status and term counts; numbers to rounding."""
     ds = golden_datasets["synthetic"]
