@@ -45,5 +45,11 @@ if __name__ == "__main__":
         outs.append((np.load(f), json.load(open(f + ".json"))))
     a = outs[0][0]
     for v, (b, ms) in zip(vals, outs):
-        bad = [k for k in a.files if not np.array_equal(a[k], b[k], equal_nan=True)]
+        bad = {}
+        for k in a.files:
+            if not np.array_equal(a[k], b[k], equal_nan=True):
+                x, y = a[k].astype(float), b[k].astype(float)
+                m = np.isfinite(x) & np.isfinite(y)
+                bad[k] = {"max_rel": float(np.max(np.abs(x[m] - y[m]) / np.maximum(np.abs(x[m]), 1e-300))) if m.any() else None,
+                          "nonfinite_pattern_equal": bool(np.array_equal(np.isfinite(x), np.isfinite(y)))}
         print(knob, "=", v, "kernel ms (K1, K2):", ms, "differs from the first in:", bad)
