@@ -500,7 +500,9 @@ def run_gpu(args):
             ex = json.load(f)
     k1_flops = ex.get("misti_correct_kernel", {}).get("flops_per_item")
     if k1_flops is not None:  # the cpfit post-split pass of a large batch runs as a kernel of its own, inside the same pair of events
-        k1_flops += ex.get("misti_post_split_kernel", {}).get("flops_per_item", 0.0)
+        post = "misti_post_split_quad_kernel" if (B > 6144 and "misti_post_split_quad_kernel" in ex and os.environ.get("MISTI_POST_QUAD", "1") != "0") \
+            else "misti_post_split_kernel"  # plain batches above 6 144 items: four lanes per item
+        k1_flops += ex.get(post, {}).get("flops_per_item", 0.0)
     pair_kernel = B > 6144 and os.environ.get("MISTI_JSFS_PAIR", "1") != "0"  # large batches: two lanes per item (csrc/misti_pair.cuh)
     k2_name = "misti_jsfs_pair_kernel" if pair_kernel and "misti_jsfs_pair_kernel" in ex else "misti_jsfs_kernel"
     k2_flops = ex.get(k2_name, {}).get("flops_per_item")
@@ -511,11 +513,11 @@ def run_gpu(args):
         return {"kernel": name, "ms": ms, "flops_per_eval_executed": flops, "tflops": tf, "frac_of_fp64_peak": None if tf is None else tf / peak,
                 "bound": bound}
     dom_is_k1 = k1 >= k2
-    kernels = {"misti_correct_kernel": kernel_entry("misti_correct_kernel (+ misti_post_split_kernel)", k1, k1_flops,
+    kernels = {"misti_correct_kernel": kernel_entry("misti_correct_kernel (+ misti_post_split_quad_kernel)", k1, k1_flops,
                                                     "latency of one thread's serial FP64 chain (0.86 of one wave, 3.5 warps per scheduler; ncu: "
                                                     "issue slots 35 %, FP64 pipe 27 %, stalls: fixed latency 27 %, long scoreboard 27 % (thread-"
-                                                    "local stack), no instruction 20 % (86 KB of hot code)); the post-split kernel is FP64-bound "
-                                                    "(issue slots 77 %, FP64 pipe 49 %)"),
+                                                    "local stack), no instruction 20 % (78 KB of hot code: the SM's instruction cache hits 78 %, the GPC-level one runs at 69 % "
+                                                    "of its peak request rate)); the post-split kernel is FP64-bound (issue slots 65 %, FP64 pipe 56 %)"),
                "misti_jsfs_kernel": kernel_entry(
                    k2_name + (" (+ misti_jsfs_kernel over an empty redo list, misti_stiff_kernel with nothing parked)" if k2_name != "misti_jsfs_kernel"
                               else " (+ misti_stiff_kernel, nothing parked)"), k2, k2_flops,
