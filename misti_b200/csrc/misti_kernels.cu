@@ -1695,13 +1695,15 @@ static int eval_chunk(misti_ctx* ctx, int B, int P, const double* d_params, cons
         if (coop) MISTI_LAUNCH_CORRECT3(kCorrectMinBlocks, true, 2, 4L * B, 0); else MISTI_LAUNCH_CORRECT3(kCorrectMinBlocks, false, 2, (long)B, 0);
     } else
     if (!coop && ctx->correct_minb == kCorrectMinBlocks && ctx->correct_big_blocks &&
-               (long)B > (long)ctx->sm_count * 384 && (long)B <= (long)ctx->sm_count * 512) {
-        // A batch that is ONE wave of one-thread-per-item warps (up to 16 per SM at 128 registers): one block per SM with all of
-        // the SM's warps instead of seven or eight blocks of two.  The warps of an SM then start in the same cycle and stay close
+               (long)B > (long)ctx->sm_count * 384 && ((long)B <= (long)ctx->sm_count * 512 || (long)B >= (long)ctx->sm_count * 768)) {
+        // A batch that fills the machine with one-thread-per-item warps (up to 16 per SM at 128 registers): one block per SM with
+        // all of the SM's warps instead of seven or eight blocks of two (several waves of such blocks for larger batches).  The warps of an SM then start in the same cycle and stay close
         // to each other in the code, which is what the kernel is short of: it executes 78 KB of distinct code, the SM's
         // instruction cache hits 78 %, and the GPC-level instruction cache runs at 69 % of its peak request rate (ncu).  Measured at
         // 65 408 items: 0.579 -> 0.555 ms (a barrier at every interval on top: 0.543 ms, not taken: items that fail leave the chain
-        // early).  Same code per thread: results do not depend on the block size.
+        // early).  Several waves gain more (131 072 items 1.139 -> 1.065 ms, 262 144 items 2.53 -> 2.08 ms), except between one and
+        // one and a half waves, where the few blocks of the second wave each cost a whole chain (98 304 items 0.953 -> 1.005 ms:
+        // small blocks there).  Same code per thread: results do not depend on the block size.
 #define MISTI_LAUNCH_CORRECT_BIG(T)                                                                                       \
         misti_correct_kernel<1, false, 0, T><<<(unsigned)((B + (T) - 1) / (T)), T, 0, ctx->stream>>>(                      \
             B, P, d_params, d_model_ids, model_default, ctx->d_models, ctx->d_times, ctx->d_lh, ctx->d_gaux, ctx->d_cls, flags, mixture_th, \

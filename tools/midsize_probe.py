@@ -14,7 +14,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "--run":
     eng.set_data([ds["sfs"]], True)
     rng = np.random.default_rng(1)
     out = {}
-    for B in (1024, 2048, 4096, 6144, 8192, 12288, 16384, 24576, 32768):
+    for B in [int(v) for v in os.environ.get('PROBE_SIZES', '1024,2048,4096,6144,8192,12288,16384,24576,32768').split(',')]:
         p = rng.uniform(0, 5, (B, 1))
         ts = []
         for _ in range(9):
@@ -23,6 +23,6 @@ if len(sys.argv) > 1 and sys.argv[1] == "--run":
         out[B] = [round(float(np.median([a for a, _ in ts])), 4), round(float(np.median([b for _, b in ts])), 4)]
     print(json.dumps(out))
     sys.exit(0)
-for env in ({}, {"MISTI_JSFS_PAIR": "1", "MISTI_DEFER_POST": "2"}):
+for env in ([{}, {"MISTI_CORRECT_BIG_BLOCKS": "0"}] if os.environ.get("PROBE_BIG") else [{}, {"MISTI_JSFS_PAIR": "1", "MISTI_DEFER_POST": "2"}]):
     r = subprocess.run([sys.executable, __file__, "--run"], env=dict(os.environ, **env), capture_output=True, text=True)
     print(env, r.stdout.strip(), r.stderr[-300:])
