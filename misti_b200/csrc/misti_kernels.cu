@@ -93,12 +93,36 @@ misti_correct_kernel(int B, int P, const double* __restrict__ params, const int*
         for (int i = threadIdx.x; i < (int)(sizeof(ModelDesc) / sizeof(int)); i += blockDim.x) dst[i] = src[i];
         __syncthreads();
     }
-    if (slot >= B) return;
+    // One-block-per-SM launches (THREADS > kCorrectThreads, plain mode) with regime = 4: every thread of the block arrives
+    // at barrier 1 exactly `align_total` times -- at the top of every interval of its chain (correct_lambdas_item), and here
+    // for the intervals a chain never reached (items that fail, empty slots).  align_total = the block's longest chain.
+    constexpr bool CAN_ALIGN = THREADS > kCorrectThreads && MODE == 0 && !COOP;
+    int align_done = 0, align_total = 0;
+    const bool aligning = CAN_ALIGN && regime == 4;
+    if (aligning) {
+        __shared__ int s_align;
+        if (threadIdx.x == 0) s_align = 0;
+        __syncthreads();
+        int mine = 0;
+        if (slot < B) {
+            const int mid = model_ids ? model_ids[b] : model_default;
+            if ((unsigned)mid < (unsigned)n_models) mine = models[mid].splitT;
+        }
+        atomicMax(&s_align, mine);
+        __syncthreads();
+        align_total = s_align;
+    }
+    auto align_make_up = [&]() {
+        if (aligning)
+            for (; align_done < align_total; ++align_done) asm volatile("barrier.sync 1;" ::: "memory");
+    };
+    if (slot >= B) { align_make_up(); return; }
     if (model_ids && (unsigned)model_ids[b] >= (unsigned)n_models) {  // id -1: an empty slot of the on-device optimiser; any
         // other id outside the registered models (device-pointer calls are not validated on the host) is skipped as well
         nseg[b] = 0;
         status[b] = MISTI_SKIPPED;
         nfev[b] = 0;
+        align_make_up();
         return;
     }
     const ModelDesc& md = model_ids ? models[model_ids[b]] : smd;
@@ -151,7 +175,8 @@ misti_correct_kernel(int B, int P, const double* __restrict__ params, const int*
                                                                 &cp_done, cls, defer_post ? nc : nullptr, trace, nullptr);
         } else {
             st = misti::correct_lambdas_item<COOP, false, false>(md, tt, ll, par, flags, mixtureTH, lcb, kPitch, stride, pr, &nf, ga, cp,
-                                                                 &cp_done, cls, defer_post ? nc : nullptr, nullptr, nullptr);
+                                                                 &cp_done, cls, defer_post ? nc : nullptr, nullptr, nullptr,
+                                                                 aligning ? &align_done : nullptr);
         }
         if (defer_post && cp_done) cp[0] = exp(nc[1] - nc[0]);
     }
@@ -167,6 +192,7 @@ misti_correct_kernel(int B, int P, const double* __restrict__ params, const int*
     cpost[2 * stride + b] = cp[2];
     status[b] = st;
     nfev[b] = nf;
+    align_make_up();
 }
 
 // The segment pre-pass of a large batch as a kernel of its own: the same function on the same rates, one thread per item like
@@ -1254,6 +1280,7 @@ struct misti_ctx {
     int split_segments = -1;              // segment pre-pass as a kernel of its own (-1 = large plain batches in default mode; knob MISTI_SPLIT_SEGMENTS = 0 / 1)
     int post_quad = 1;                  // plain batches: the post-split kernel with four lanes per item (knob MISTI_POST_QUAD = 0: 16 lanes)
     int correct_big_blocks = 1;           // one-wave batches: one block per SM in the correction kernel (knob MISTI_CORRECT_BIG_BLOCKS = 0)
+    int correct_align = 1;                // ... and a barrier at every interval of the chain (knob MISTI_CORRECT_ALIGN = 0)
     int jsfs_pair = -1;                   // JSFS kernel with a pair of lanes per item (-1 = large batches; knob MISTI_JSFS_PAIR = 0 / 1)
     int score_kernel = 1;                 // many data rows: likelihood stage as a kernel of its own (knob MISTI_SCORE_KERNEL)
     int fit_slice_us = 200;               // time slice of a correction chain inside the on-device optimiser (MISTI_FIT_SLICE_US)
@@ -1458,6 +1485,7 @@ int misti_ctx_create(int device, void* stream, misti_ctx** out) {
     if (const char* e = getenv("MISTI_NM_GRAPH")) ctx->nm_use_graph = atoi(e);
     if (const char* e = getenv("MISTI_SCORE_KERNEL")) ctx->score_kernel = atoi(e);
     if (const char* e = getenv("MISTI_JSFS_PAIR")) ctx->jsfs_pair = atoi(e);
+    if (const char* e = getenv("MISTI_CORRECT_ALIGN")) ctx->correct_align = atoi(e);
     if (const char* e = getenv("MISTI_CORRECT_BIG_BLOCKS")) ctx->correct_big_blocks = atoi(e);
     if (const char* e = getenv("MISTI_POST_QUAD")) ctx->post_quad = atoi(e);
     if (const char* e = getenv("MISTI_SPLIT_SEGMENTS")) ctx->split_segments = atoi(e);
@@ -1708,7 +1736,7 @@ static int eval_chunk(misti_ctx* ctx, int B, int P, const double* d_params, cons
         misti_correct_kernel<1, false, 0, T><<<(unsigned)((B + (T) - 1) / (T)), T, 0, ctx->stream>>>(                      \
             B, P, d_params, d_model_ids, model_default, ctx->d_models, ctx->d_times, ctx->d_lh, ctx->d_gaux, ctx->d_cls, flags, mixture_th, \
             d_lc_inject, numT_max, ctx->d_lc, stride, ctx->d_cpost, d_pr, ctx->d_status, ctx->d_nfev, ctx->d_rec, ctx->cap_seg, ctx->d_nseg, \
-            ctx->d_counts, defer_k1, (int)ctx->h_models.size(), d_trace, d_count, 0, d_item_list, d_ckpt, d_slice_ctl, yield_below)
+            ctx->d_counts, defer_k1, (int)ctx->h_models.size(), d_trace, d_count, ctx->correct_align ? 4 : 0, d_item_list, d_ckpt, d_slice_ctl, yield_below)
         if ((long)B <= (long)ctx->sm_count * 448) MISTI_LAUNCH_CORRECT_BIG(448); else MISTI_LAUNCH_CORRECT_BIG(512);
 #undef MISTI_LAUNCH_CORRECT_BIG
     } else

@@ -241,7 +241,7 @@ MISTI_HD inline int correct_lambdas_item(const ModelDesc& md, const double* time
                                          unsigned flags, double mixtureTH, double* lc, int pitch, long stride, double* Pr,
                                          int* nfev_out, const double* gaux = nullptr, double* cpost = nullptr,
                                          bool* cpost_done = nullptr, const unsigned* cls = nullptr, double* nc_out = nullptr,
-                                         int* trace = nullptr, const ChainResume* rs = nullptr) {
+                                         int* trace = nullptr, const ChainResume* rs = nullptr, int* align = nullptr) {
     if (cpost_done) *cpost_done = false;
     const bool correct = flags & MISTI_FLAG_CORRECT, cpfit = flags & MISTI_FLAG_CPFIT;
     int nfev = 0;
@@ -289,6 +289,15 @@ MISTI_HD inline int correct_lambdas_item(const ModelDesc& md, const double* time
         r.time += times[t];
     };
     for (int t = t_first; t < splitT; ++t) {
+#if defined(__CUDA_ARCH__)
+        // `align` (nullable; one-block-per-SM launches of the plain kernel): the threads of the block enter every interval
+        // together, so that the SM's warps share the instruction stream.  An unaligned barrier (threads of a warp may arrive
+        // from different places); the caller makes up the arrivals of a chain that ends early (*align counts them).
+        if (!COOP && !RESUME && !TRACE && align) {
+            asm volatile("barrier.sync 1;" ::: "memory");
+            ++*align;
+        }
+#endif
         if (RESUME && t > t_first && chain_should_yield(rs, COOP)) {  // time slice used up: park the chain at this interval boundary
             ChainCkpt& k = *rs->ck;
             bool writer = true;

@@ -130,3 +130,35 @@ def test_large_batches_take_the_pair_kernel_and_agree_with_the_16_lane_kernel(go
             assert np.array_equal(np.isnan(a[k]), np.isnan(b[k])) and np.array_equal(np.isinf(a[k]), np.isinf(b[k])), (key, k)
             m = np.isfinite(a[k])
             assert float(np.max(np.abs(a[k][m] - b[k][m]) / np.abs(b[k][m]))) < 1e-10, (key, k)
+
+
+def test_one_block_per_sm_launches_of_the_correction_kernel_change_nothing(golden_datasets):
+    """Batches that fill the machine launch the correction kernel as one block per SM with a barrier at every interval of
+    the chain (csrc/misti_kernels.cu: correct_big_blocks / correct_align).  The arithmetic per thread is the same, so the
+    results are those of the two-warp blocks bit for bit -- also when threads leave the chain early (negative parameters,
+    corrections that fail in the reference's default mode), when models of different length share a block, and when the
+    batch is not a multiple of the block."""
+    ds = golden_datasets["synthetic"]
+    numT = len(ds["lambdas"])
+    rng = np.random.default_rng(21)
+    n = 60001
+    p = rng.uniform(0, 5, (n, 1))
+    p[::53, 0] = -1.0
+    pick = rng.integers(0, 5, n)
+    res = []
+    for env in ({}, {"MISTI_CORRECT_BIG_BLOCKS": 0}, {"MISTI_CORRECT_ALIGN": 0}):
+        eng = _engine(**env)
+        gid = eng.add_grid(ds["times"], ds["lambdas"])
+        ms = np.array([eng.add_model(gid, 40, 0, bands=[(1, 5, 12, 0.8, 0)]), eng.add_model(gid, 20, 0, bands=[(1, 5, 12, 0.8, 0)]),
+                       eng.add_model(gid, 90, 0, bands=[(0, 4, 38, 3.0, 0)]), eng.add_model(gid, numT, 0, bands=[(0, 100, numT, 0.5, 0)]),
+                       eng.add_model(gid, 36, 0)], dtype=np.int32)
+        eng.set_data([ds["sfs"]], True)
+        res.append([eng.evaluate(p, model=int(ms[0]), flags=15, want=("jafs", "status", "nfev", "terms")),
+                    eng.evaluate(p, model_ids=ms[pick], flags=15, want=("jafs", "status", "nfev", "terms")),
+                    eng.evaluate(p, model_ids=ms[pick], flags=13, want=("jafs", "status", "nfev", "terms"))])
+        eng.close()
+    for other in res[1:]:
+        for a, b in zip(res[0], other):
+            for k in a:
+                assert np.array_equal(a[k], b[k], equal_nan=True), k
+    assert (res[0][2]["status"] != 0).sum() > 1000 and (res[0][1]["status"] == 0).sum() > 1000
