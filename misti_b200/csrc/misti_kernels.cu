@@ -100,8 +100,8 @@ misti_correct_kernel(int B, int P, const double* __restrict__ params, const int*
     int align_done = 0, align_total = 0;
     const bool aligning = CAN_ALIGN && regime == 4;
     if (aligning) {
-        __shared__ int s_align;
-        if (threadIdx.x == 0) s_align = 0;
+        __shared__ int s_align, s_align_min;
+        if (threadIdx.x == 0) { s_align = 0; s_align_min = INT_MAX; }
         __syncthreads();
         int mine = 0;
         if (slot < B) {
@@ -109,8 +109,14 @@ misti_correct_kernel(int B, int P, const double* __restrict__ params, const int*
             if ((unsigned)mid < (unsigned)n_models) mine = models[mid].splitT;
         }
         atomicMax(&s_align, mine);
+        if (mine > 0) atomicMin(&s_align_min, mine);
         __syncthreads();
         align_total = s_align;
+        // chains of different length in one block: the short ones wait (at their make-up arrivals) for the long ones before
+        // their post-split work.  In cpfit mode that work is deferred or cheap (a split-time grid: +3 %, run-away mixes: -20 %);
+        // in the reference's default mode it is 87 trust-region solves per item and the two phases would add up (a split-time
+        // grid without migration: 1.20 -> 1.63 ms), so there such a block runs without the barriers
+        if (s_align_min != align_total && !(flags & MISTI_FLAG_CPFIT)) align_total = 0;
     }
     auto align_make_up = [&]() {
         if (aligning)
@@ -176,7 +182,7 @@ misti_correct_kernel(int B, int P, const double* __restrict__ params, const int*
         } else {
             st = misti::correct_lambdas_item<COOP, false, false>(md, tt, ll, par, flags, mixtureTH, lcb, kPitch, stride, pr, &nf, ga, cp,
                                                                  &cp_done, cls, defer_post ? nc : nullptr, nullptr, nullptr,
-                                                                 aligning ? &align_done : nullptr);
+                                                                 (aligning && align_total > 0) ? &align_done : nullptr, align_total);
         }
         if (defer_post && cp_done) cp[0] = exp(nc[1] - nc[0]);
     }

@@ -241,7 +241,8 @@ MISTI_HD inline int correct_lambdas_item(const ModelDesc& md, const double* time
                                          unsigned flags, double mixtureTH, double* lc, int pitch, long stride, double* Pr,
                                          int* nfev_out, const double* gaux = nullptr, double* cpost = nullptr,
                                          bool* cpost_done = nullptr, const unsigned* cls = nullptr, double* nc_out = nullptr,
-                                         int* trace = nullptr, const ChainResume* rs = nullptr, int* align = nullptr) {
+                                         int* trace = nullptr, const ChainResume* rs = nullptr, int* align = nullptr,
+                                         int align_total = 0) {
     if (cpost_done) *cpost_done = false;
     const bool correct = flags & MISTI_FLAG_CORRECT, cpfit = flags & MISTI_FLAG_CPFIT;
     int nfev = 0;
@@ -357,6 +358,12 @@ MISTI_HD inline int correct_lambdas_item(const ModelDesc& md, const double* time
         nc0 = (st.P0[0][0] + st.P0[0][1]) + st.P0[0][2];  // reference quirk: a probability used as a log (:353-354)
         nc1 = (st.P0[1][0] + st.P0[1][1]) + st.P0[1][2];
     }
+#if defined(__CUDA_ARCH__)
+    // a chain shorter than the block's longest one makes up its arrivals HERE, before its post-split work: the threads with
+    // longer chains would otherwise wait at their next barrier until this one has finished everything else
+    if (!COOP && !RESUME && !TRACE && align)
+        for (; *align < align_total; ++*align) asm volatile("barrier.sync 1;" ::: "memory");
+#endif
     if (!sr0.done && splitT > sr0.k) {
         const double avg = sr0.nc / sr0.time;
         for (int i = sr0.k; i < splitT; ++i) lc[(pitch * i) * stride] = avg;
