@@ -514,10 +514,10 @@ def run_gpu(args):
                 "bound": bound}
     dom_is_k1 = k1 >= k2
     kernels = {"misti_correct_kernel": kernel_entry("misti_correct_kernel (+ misti_post_split_quad_kernel)", k1, k1_flops,
-                                                    "latency of one thread's serial FP64 chain (0.86 of one wave, 3.5 warps per scheduler; ncu: "
-                                                    "issue slots 35 %, FP64 pipe 27 %, stalls: fixed latency 27 %, long scoreboard 27 % (thread-"
-                                                    "local stack), no instruction 20 % (78 KB of hot code: the SM's instruction cache hits 78 %, the GPC-level one runs at 69 % "
-                                                    "of its peak request rate)); the post-split kernel is FP64-bound (issue slots 65 %, FP64 pipe 56 %)"),
+                                                    "latency of one thread's serial FP64 chain (one block of 14 warps per SM, 3.5 warps per scheduler; ncu r03: issue slots 36 %, "
+                                                    "FP64 pipe 28 %, stalls: long scoreboard 29 % (thread-local stack), fixed latency 26 %, interval barrier 10 %, no "
+                                                    "instruction 7 % (20 % before the SM's warps were launched as one block and kept together: 78 KB of hot code)); the "
+                                                    "post-split kernel is FP64-bound (issue slots 65 %, FP64 pipe 56 %)"),
                "misti_jsfs_kernel": kernel_entry(
                    k2_name + (" (+ misti_jsfs_kernel over an empty redo list, misti_stiff_kernel with nothing parked)" if k2_name != "misti_jsfs_kernel"
                               else " (+ misti_stiff_kernel, nothing parked)"), k2, k2_flops,
