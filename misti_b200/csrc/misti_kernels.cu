@@ -98,7 +98,8 @@ misti_correct_kernel(int B, int P, const double* __restrict__ params, const int*
     // for the intervals a chain never reached (items that fail, empty slots).  align_total = the block's longest chain.
     constexpr bool CAN_ALIGN = THREADS > kCorrectThreads && MODE == 0 && !COOP;
     int align_done = 0, align_total = 0;
-    const bool aligning = CAN_ALIGN && regime == 4;
+    const bool aligning = CAN_ALIGN && (regime & 4) != 0;
+    const int align_every = (regime >> 3) > 0 ? (regime >> 3) : 1;  // a barrier at every align_every-th interval
     if (aligning) {
         __shared__ int s_align, s_align_min;
         if (threadIdx.x == 0) { s_align = 0; s_align_min = INT_MAX; }
@@ -106,7 +107,7 @@ misti_correct_kernel(int B, int P, const double* __restrict__ params, const int*
         int mine = 0;
         if (slot < B) {
             const int mid = model_ids ? model_ids[b] : model_default;
-            if ((unsigned)mid < (unsigned)n_models) mine = models[mid].splitT;
+            if ((unsigned)mid < (unsigned)n_models) mine = (models[mid].splitT + align_every - 1) / align_every;
         }
         atomicMax(&s_align, mine);
         if (mine > 0) atomicMin(&s_align_min, mine);
@@ -182,7 +183,7 @@ misti_correct_kernel(int B, int P, const double* __restrict__ params, const int*
         } else {
             st = misti::correct_lambdas_item<COOP, false, false>(md, tt, ll, par, flags, mixtureTH, lcb, kPitch, stride, pr, &nf, ga, cp,
                                                                  &cp_done, cls, defer_post ? nc : nullptr, nullptr, nullptr,
-                                                                 (aligning && align_total > 0) ? &align_done : nullptr, align_total);
+                                                                 (aligning && align_total > 0) ? &align_done : nullptr, align_total, align_every);
         }
         if (defer_post && cp_done) cp[0] = exp(nc[1] - nc[0]);
     }
@@ -1286,7 +1287,7 @@ struct misti_ctx {
     int split_segments = -1;              // segment pre-pass as a kernel of its own (-1 = large plain batches in default mode; knob MISTI_SPLIT_SEGMENTS = 0 / 1)
     int post_quad = 1;                  // plain batches: the post-split kernel with four lanes per item (knob MISTI_POST_QUAD = 0: 16 lanes)
     int correct_big_blocks = 1;           // one-wave batches: one block per SM in the correction kernel (knob MISTI_CORRECT_BIG_BLOCKS = 0)
-    int correct_align = 1;                // ... and a barrier at every interval of the chain (knob MISTI_CORRECT_ALIGN = 0)
+    int correct_align = 1;                // ... and a barrier at every interval of the chain (knob MISTI_CORRECT_ALIGN = 0 / k: none / at every k-th interval)
     int jsfs_pair = -1;                   // JSFS kernel with a pair of lanes per item (-1 = large batches; knob MISTI_JSFS_PAIR = 0 / 1)
     int score_kernel = 1;                 // many data rows: likelihood stage as a kernel of its own (knob MISTI_SCORE_KERNEL)
     int fit_slice_us = 200;               // time slice of a correction chain inside the on-device optimiser (MISTI_FIT_SLICE_US)
@@ -1491,7 +1492,7 @@ int misti_ctx_create(int device, void* stream, misti_ctx** out) {
     if (const char* e = getenv("MISTI_NM_GRAPH")) ctx->nm_use_graph = atoi(e);
     if (const char* e = getenv("MISTI_SCORE_KERNEL")) ctx->score_kernel = atoi(e);
     if (const char* e = getenv("MISTI_JSFS_PAIR")) ctx->jsfs_pair = atoi(e);
-    if (const char* e = getenv("MISTI_CORRECT_ALIGN")) ctx->correct_align = atoi(e);
+    if (const char* e = getenv("MISTI_CORRECT_ALIGN")) { const int v = atoi(e); if (v >= 0 && v <= 64) ctx->correct_align = v; }
     if (const char* e = getenv("MISTI_CORRECT_BIG_BLOCKS")) ctx->correct_big_blocks = atoi(e);
     if (const char* e = getenv("MISTI_POST_QUAD")) ctx->post_quad = atoi(e);
     if (const char* e = getenv("MISTI_SPLIT_SEGMENTS")) ctx->split_segments = atoi(e);
@@ -1742,7 +1743,7 @@ static int eval_chunk(misti_ctx* ctx, int B, int P, const double* d_params, cons
         misti_correct_kernel<1, false, 0, T><<<(unsigned)((B + (T) - 1) / (T)), T, 0, ctx->stream>>>(                      \
             B, P, d_params, d_model_ids, model_default, ctx->d_models, ctx->d_times, ctx->d_lh, ctx->d_gaux, ctx->d_cls, flags, mixture_th, \
             d_lc_inject, numT_max, ctx->d_lc, stride, ctx->d_cpost, d_pr, ctx->d_status, ctx->d_nfev, ctx->d_rec, ctx->cap_seg, ctx->d_nseg, \
-            ctx->d_counts, defer_k1, (int)ctx->h_models.size(), d_trace, d_count, ctx->correct_align ? 4 : 0, d_item_list, d_ckpt, d_slice_ctl, yield_below)
+            ctx->d_counts, defer_k1, (int)ctx->h_models.size(), d_trace, d_count, ctx->correct_align ? (4 | (ctx->correct_align << 3)) : 0, d_item_list, d_ckpt, d_slice_ctl, yield_below)
         if ((long)B <= (long)ctx->sm_count * 448) MISTI_LAUNCH_CORRECT_BIG(448); else MISTI_LAUNCH_CORRECT_BIG(512);
 #undef MISTI_LAUNCH_CORRECT_BIG
     } else

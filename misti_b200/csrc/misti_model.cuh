@@ -242,7 +242,7 @@ MISTI_HD inline int correct_lambdas_item(const ModelDesc& md, const double* time
                                          int* nfev_out, const double* gaux = nullptr, double* cpost = nullptr,
                                          bool* cpost_done = nullptr, const unsigned* cls = nullptr, double* nc_out = nullptr,
                                          int* trace = nullptr, const ChainResume* rs = nullptr, int* align = nullptr,
-                                         int align_total = 0) {
+                                         int align_total = 0, int align_every = 1) {
     if (cpost_done) *cpost_done = false;
     const bool correct = flags & MISTI_FLAG_CORRECT, cpfit = flags & MISTI_FLAG_CPFIT;
     int nfev = 0;
@@ -294,7 +294,7 @@ MISTI_HD inline int correct_lambdas_item(const ModelDesc& md, const double* time
         // `align` (nullable; one-block-per-SM launches of the plain kernel): the threads of the block enter every interval
         // together, so that the SM's warps share the instruction stream.  An unaligned barrier (threads of a warp may arrive
         // from different places); the caller makes up the arrivals of a chain that ends early (*align counts them).
-        if (!COOP && !RESUME && !TRACE && align) {
+        if (!COOP && !RESUME && !TRACE && align && t % align_every == 0) {
             asm volatile("barrier.sync 1;" ::: "memory");
             ++*align;
         }
