@@ -1730,7 +1730,7 @@ static int eval_chunk(misti_ctx* ctx, int B, int P, const double* d_params, cons
         if (coop) MISTI_LAUNCH_CORRECT3(kCorrectMinBlocks, true, 2, 4L * B, 0); else MISTI_LAUNCH_CORRECT3(kCorrectMinBlocks, false, 2, (long)B, 0);
     } else
     if (!coop && ctx->correct_minb == kCorrectMinBlocks && ctx->correct_big_blocks &&
-               (long)B > (long)ctx->sm_count * 384 && ((long)B <= (long)ctx->sm_count * 512 || (long)B >= (long)ctx->sm_count * 768)) {
+               (((long)B > (long)ctx->sm_count * 384 && (long)B <= (long)ctx->sm_count * 512) || (long)B >= (long)ctx->sm_count * 768)) {
         // A batch that fills the machine with one-thread-per-item warps (up to 16 per SM at 128 registers): one block per SM with
         // all of the SM's warps instead of seven or eight blocks of two (several waves of such blocks for larger batches).  The warps of an SM then start in the same cycle and stay close
         // to each other in the code, which is what the kernel is short of: it executes 78 KB of distinct code, the SM's
@@ -1739,12 +1739,18 @@ static int eval_chunk(misti_ctx* ctx, int B, int P, const double* d_params, cons
         // early).  Several waves gain more (131 072 items 1.139 -> 1.065 ms, 262 144 items 2.53 -> 2.08 ms), except between one and
         // one and a half waves, where the few blocks of the second wave each cost a whole chain (98 304 items 0.953 -> 1.005 ms:
         // small blocks there).  Same code per thread: results do not depend on the block size.
+        // (Only block sizes whose register bound comes out at the 128 of the two-warp blocks: ptxas then generates the same
+        // arithmetic and results do not depend on the size of the batch.  Blocks of 256 / 320 / 384 threads for smaller one-wave
+        // batches were 8 % faster WITH the 255 / 204 / 170 registers their launch bounds allow (30 000 items 0.361 -> 0.333 ms) --
+        // but that code rounds differently (solver evaluation counts of run-away items changed in a test) -- and 3 % slower
+        // with 128 (eight warps per SM do not crowd the instruction cache).)
 #define MISTI_LAUNCH_CORRECT_BIG(T)                                                                                       \
         misti_correct_kernel<1, false, 0, T><<<(unsigned)((B + (T) - 1) / (T)), T, 0, ctx->stream>>>(                      \
             B, P, d_params, d_model_ids, model_default, ctx->d_models, ctx->d_times, ctx->d_lh, ctx->d_gaux, ctx->d_cls, flags, mixture_th, \
             d_lc_inject, numT_max, ctx->d_lc, stride, ctx->d_cpost, d_pr, ctx->d_status, ctx->d_nfev, ctx->d_rec, ctx->cap_seg, ctx->d_nseg, \
             ctx->d_counts, defer_k1, (int)ctx->h_models.size(), d_trace, d_count, ctx->correct_align ? (4 | (ctx->correct_align << 3)) : 0, d_item_list, d_ckpt, d_slice_ctl, yield_below)
-        if ((long)B <= (long)ctx->sm_count * 448) MISTI_LAUNCH_CORRECT_BIG(448); else MISTI_LAUNCH_CORRECT_BIG(512);
+        if ((long)B <= (long)ctx->sm_count * 448) MISTI_LAUNCH_CORRECT_BIG(448);
+        else MISTI_LAUNCH_CORRECT_BIG(512);
 #undef MISTI_LAUNCH_CORRECT_BIG
     } else
     switch (ctx->correct_minb) {  // register budget per thread: 4 -> 255, 8 -> 128, 12 -> 80 (tuning knob MISTI_CORRECT_MINB)

@@ -153,7 +153,8 @@ def test_one_block_per_sm_launches_of_the_correction_kernel_change_nothing(golde
                        eng.add_model(gid, 90, 0, bands=[(0, 4, 38, 3.0, 0)]), eng.add_model(gid, numT, 0, bands=[(0, 100, numT, 0.5, 0)]),
                        eng.add_model(gid, 36, 0)], dtype=np.int32)
         eng.set_data([ds["sfs"]], True)
-        res.append([eng.evaluate(p, model=int(ms[0]), flags=15, want=("jafs", "status", "nfev", "terms")),
+        res.append([eng.evaluate(p[:33000], model_ids=ms[pick[:33000]], flags=15, want=("jafs", "status", "nfev", "terms")),  # blocks of two warps
+                    eng.evaluate(p, model=int(ms[0]), flags=15, want=("jafs", "status", "nfev", "terms")),
                     eng.evaluate(p, model_ids=ms[pick], flags=15, want=("jafs", "status", "nfev", "terms")),
                     eng.evaluate(p, model_ids=ms[pick], flags=13, want=("jafs", "status", "nfev", "terms"))])
         eng.close()
@@ -161,4 +162,4 @@ def test_one_block_per_sm_launches_of_the_correction_kernel_change_nothing(golde
         for a, b in zip(res[0], other):
             for k in a:
                 assert np.array_equal(a[k], b[k], equal_nan=True), k
-    assert (res[0][2]["status"] != 0).sum() > 1000 and (res[0][1]["status"] == 0).sum() > 1000
+    assert (res[0][3]["status"] != 0).sum() > 1000 and (res[0][2]["status"] == 0).sum() > 1000
