@@ -163,3 +163,38 @@ def test_one_block_per_sm_launches_of_the_correction_kernel_change_nothing(golde
             for k in a:
                 assert np.array_equal(a[k], b[k], equal_nan=True), k
     assert (res[0][3]["status"] != 0).sum() > 1000 and (res[0][2]["status"] == 0).sum() > 1000
+
+
+def test_large_batch_path_against_the_oracle(golden_datasets):
+    """The kernels a machine-filling batch runs by default -- correction kernel as one block per SM with interval barriers,
+    four-lane post-split kernel, pair-of-lanes JSFS kernel -- held DIRECTLY against the CPU oracle on items taken from a
+    60 000-item batch of BASELINE config 2 (`-uf -mi 2 5 12 0.8 1 --cpfit`) and of config 3 (two bands + pulse)."""
+    import misti_b200
+    from oracle.misti_oracle import OracleModel
+    ds = golden_datasets["synthetic"]
+    rng = np.random.default_rng(4)
+    n = 60000
+    eng = misti_b200.Engine(0)
+    gid = eng.add_grid(ds["times"], ds["lambdas"])
+    m2 = eng.add_model(gid, 40, 0, bands=[(1, 5, 12, 0.8, 0)])
+    m3 = eng.add_model(gid, 40, 0, bands=[(0, 2, 10, 0.3, 0), (1, 5, 12, 0.8, 1)], pulses=[(0, 7, 0.05, 2)])
+    eng.set_data([ds["sfs"]], True)
+    p2 = np.zeros((n, 3)); p2[:, 0] = rng.uniform(0, 3, n)
+    p3 = np.column_stack([rng.uniform(0, 1.5, n), rng.uniform(0, 1.5, n), rng.uniform(0, 0.3, n)])
+    o2 = eng.evaluate(p2, model=m2, flags=15, want=("jafs", "status"))
+    o3 = eng.evaluate(p3, model=m3, flags=15, want=("jafs", "status"))
+    eng.close()
+    checked = 0
+    for b in rng.choice(n, 6, replace=False):
+        om = OracleModel(ds["times"], ds["lambdas"], ds["sfs"], 40, [[2, 5, 12, 0.8, 1]], [], cpfit=True, smooth=True, unfolded=True)
+        ref = om.likelihood([float(p2[b, 0])])
+        assert o2["status"][b] == 0
+        assert relerr(o2["llh"][b, 0], ref) < TOL and relerr(o2["jafs"][b], om.JAFS) < TOL, b
+        checked += 1
+    for b in np.nonzero(o3["status"] == 0)[0][:6]:
+        om = OracleModel(ds["times"], ds["lambdas"], ds["sfs"], 40, [[1, 2, 10, 0.3, 1], [2, 5, 12, 0.8, 1]], [[1, 7, 0.05, 1]], cpfit=True,
+                         smooth=True, unfolded=True)
+        ref = om.likelihood([float(v) for v in p3[b]])
+        assert relerr(o3["llh"][b, 0], ref) < TOL and relerr(o3["jafs"][b], om.JAFS) < TOL, b
+        checked += 1
+    assert checked == 12
