@@ -216,7 +216,8 @@ MISTI_HD inline void thin_svd(const double* B, int m, const double* f, double* s
     double c1[MR], c2[MR];
     for (int r = 0; r < m; ++r) { c1[r] = B[r]; c2[r] = B[MR + r]; }
     double v00 = 1, v01 = 0, v10 = 0, v11 = 1;  // V columns: (v00,v10) and (v01,v11)
-    for (int sweep = 0; sweep < 3; ++sweep) {
+    for (int sweep = 0; sweep < 2; ++sweep) {  // the first rotation makes the two columns orthogonal to rounding, the second takes
+                                               // the residue out; a third changes nothing but costs two square roots and two divisions
         double a = 0, b = 0, c = 0;
         for (int r = 0; r < m; ++r) { a += c1[r] * c1[r]; b += c1[r] * c2[r]; c += c2[r] * c2[r]; }
         if (b == 0.0) break;
