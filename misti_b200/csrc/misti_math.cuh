@@ -121,7 +121,7 @@ MISTI_HD inline bool mat3_inv(const double* A, double* Ainv) {
 // exp(A) for a 3x3 matrix: Pade [m/m] with m in {3,5,7,9,13} chosen from ||A||_1, scaling and
 // squaring (Higham 2005 thresholds; same algorithm family as scipy.linalg.expm).
 // (inlined into its three callers: the 9-element arrays then live in registers instead of going through the stack)
-MISTI_HD inline void mat3_expm(const double* Ain, double* E) {
+MISTI_HD inline int mat3_pade(const double* Ain, double* U, double* V) {
     double A[9];
     double nrm = 0.0;
     for (int j = 0; j < 3; ++j) {
@@ -136,7 +136,7 @@ MISTI_HD inline void mat3_expm(const double* Ain, double* E) {
     }
     const double sc = ldexp(1.0, -s);
     for (int i = 0; i < 9; ++i) A[i] = Ain[i] * sc;
-    double A2[9], U[9], V[9], T1[9];
+    double A2[9], T1[9];
     mat3_mul(A, A, A2);
     if (s == 0 && nrm <= 1.495585217958292e-2) {
         for (int i = 0; i < 9; ++i) { T1[i] = A2[i]; V[i] = 12.0 * A2[i]; }
@@ -191,6 +191,13 @@ MISTI_HD inline void mat3_expm(const double* Ain, double* E) {
             V[i] = Z[i] + 670442572800.0 * A6[i] + 129060195264000.0 * A4[i] + 7771770303897600.0 * A2[i];
         V[0] += 64764752532480000.0; V[4] += 64764752532480000.0; V[8] += 64764752532480000.0;
     }
+    return s;
+}
+
+MISTI_HD inline void mat3_expm(const double* Ain, double* E) {
+    double U[9], V[9];
+    const int s = mat3_pade(Ain, U, V);
+    double T1[9];
     double Q[9];
     for (int i = 0; i < 9; ++i) { Q[i] = V[i] - U[i]; E[i] = V[i] + U[i]; }
     mat3_solve(Q, E);
@@ -198,6 +205,81 @@ MISTI_HD inline void mat3_expm(const double* Ain, double* E) {
         mat3_mul(E, E, T1);
         for (int i = 0; i < 9; ++i) E[i] = T1[i];
     }
+}
+
+// Solve Q^T z = (1, 1, 1) (partial pivoting on the rows of Q^T, as mat3_solve): z^T = 1^T Q^-1
+MISTI_HD inline bool mat3_solve_ones_t(const double* Q, double* z) {
+    double q[3][3], p[3] = {1.0, 1.0, 1.0};
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) q[i][j] = Q[3 * j + i];
+    {
+        int piv = 0;
+        double best = fabs(q[0][0]);
+        if (fabs(q[1][0]) > best) { best = fabs(q[1][0]); piv = 1; }
+        if (fabs(q[2][0]) > best) { best = fabs(q[2][0]); piv = 2; }
+        if (best == 0.0) return false;
+        for (int j = 0; j < 3; ++j) {
+            const double a0 = q[0][j], a1 = q[1][j], a2 = q[2][j];
+            q[0][j] = piv == 1 ? a1 : (piv == 2 ? a2 : a0);
+            q[1][j] = piv == 1 ? a0 : a1;
+            q[2][j] = piv == 2 ? a0 : a2;
+        }
+        const double inv = 1.0 / q[0][0];
+        for (int i = 1; i < 3; ++i) {
+            const double f = q[i][0] * inv;
+            for (int j = 0; j < 3; ++j) q[i][j] -= f * q[0][j];
+            p[i] -= f * p[0];  // (the right-hand side is all ones: the row exchange leaves it as it is)
+        }
+    }
+    {
+        const bool sw = fabs(q[2][1]) > fabs(q[1][1]);
+        const double best = sw ? fabs(q[2][1]) : fabs(q[1][1]);
+        if (best == 0.0) return false;
+        for (int j = 0; j < 3; ++j) {
+            const double a1 = q[1][j], a2 = q[2][j];
+            q[1][j] = sw ? a2 : a1;
+            q[2][j] = sw ? a1 : a2;
+        }
+        const double b1 = p[1], b2 = p[2];
+        p[1] = sw ? b2 : b1;
+        p[2] = sw ? b1 : b2;
+        const double inv = 1.0 / q[1][1];
+        const double f = q[2][1] * inv;
+        for (int j = 1; j < 3; ++j) q[2][j] -= f * q[1][j];
+        p[2] -= f * p[1];
+    }
+    if (fabs(q[2][2]) == 0.0) return false;
+    for (int k = 2; k >= 0; --k) {
+        double v = p[k];
+        for (int i = k + 1; i < 3; ++i) v -= q[k][i] * p[i];
+        p[k] = v * (1.0 / q[k][k]);
+    }
+    z[0] = p[0]; z[1] = p[1]; z[2] = p[2];
+    return true;
+}
+
+// w = 1^T exp(A): what the cpfit residuals need of the exponential (the probability not to have coalesced, summed over the
+// three states).  Without squarings (||A||_1 <= 5.37, the rule on the stretched unit interval) that is z^T (V + U) with
+// Q^T z = 1, Q = V - U: one right-hand side instead of three and no matrix-vector products afterwards; with squarings the
+// column sums of the full exponential.
+MISTI_HD inline void mat3_expm_ones(const double* Ain, double* w) {
+    double U[9], V[9];
+    const int s = mat3_pade(Ain, U, V);
+    if (s == 0) {
+        double Q[9], Nn[9], z[3];
+        for (int i = 0; i < 9; ++i) { Q[i] = V[i] - U[i]; Nn[i] = V[i] + U[i]; }
+        mat3_solve_ones_t(Q, z);
+        for (int j = 0; j < 3; ++j) w[j] = (z[0] * Nn[j] + z[1] * Nn[3 + j]) + z[2] * Nn[6 + j];
+        return;
+    }
+    double Q[9], E[9], T1[9];
+    for (int i = 0; i < 9; ++i) { Q[i] = V[i] - U[i]; E[i] = V[i] + U[i]; }
+    mat3_solve(Q, E);
+    for (int k = 0; k < s; ++k) {
+        mat3_mul(E, E, T1);
+        for (int i = 0; i < 9; ++i) E[i] = T1[i];
+    }
+    for (int j = 0; j < 3; ++j) w[j] = (E[j] + E[3 + j]) + E[6 + j];
 }
 
 // ------------------------------------------------------------------------------------------
@@ -744,14 +826,12 @@ MISTI_HD inline double one_pop_time_noncond(double lam, double T) {  // CorrectL
 struct ResidualProb {
     const IntervalState* st;
     MISTI_HD MISTI_NOINLINE bool operator()(const double* l, double* out) const {
-        double M[9], E[9];
+        double M[9], w[3];
         corr_matrix(l, st->mu, st->T, M);
-        mat3_expm(M, E);
+        mat3_expm_ones(M, w);
         for (int k = 0; k < 2; ++k) {
             const double* P = st->P0[k];
-            double p[3];
-            mat3_vec(E, P, p);
-            out[k] = ((p[0] + p[1]) + p[2]) - st->nch[k];
+            out[k] = ((w[0] * P[0] + w[1] * P[1]) + w[2] * P[2]) - st->nch[k];
         }
         return true;
     }
