@@ -19,6 +19,7 @@ default_rng(1234 + rank)).  Prints ONE JSON line.
                dense-equivalent figure of SURVEY.md 8d are listed beside it under their own keys
   batch_sweep  evaluations/s at B = 2, 64, 4096, 65536
   config_sweep kernel time of one batch for the layouts of BASELINE configs 1, 3, 4 and config 2 in the reference's default mode
+  likelihood_stage  config 5's bootstrap stage: 65 536 items x 1 001 data rows, HBM write rate against the measured copy rate
   time_to_fit  the second half of the metric, device-timed, fits sharded over the N ranks (strong scaling):
                config 2 (one Nelder-Mead fit), config 5b (9 009 fits = 1 001 bootstrap rows x 9 split times), config 3
                (basin-hopping walkers, 1 024 per GPU)
@@ -365,6 +366,48 @@ def config_sweep(local, stream, B, rank):
     return out
 
 
+def likelihood_stage(local, stream, B):
+    """BASELINE config 5's bootstrap stage: B items scored against the 1 001 rows of data/synthetic/bs.sfs in one call
+    (llh[b, r] = const_r + sum_i d_ri log p_bi: 8 bytes written per (item, row) pair) -- the HBM-bound part of the path.
+    Device-resident buffers; the stage's time = the JSFS + likelihood kernels with 1 001 rows minus the same launch with one row."""
+    import json
+    import numpy as np
+    import torch
+    import misti_b200
+    from misti_b200 import io as mio
+    with open(os.path.join(ROOT, "tests", "golden", "datasets.json")) as f:
+        ds = json.load(f)["datasets"]["synthetic"]
+    bs = mio.read_jafs(os.path.join(ROOT, "data", "synthetic", "bs.sfs")).jafs
+    dev = torch.device("cuda", local)
+    eng = misti_b200.Engine(local, stream=stream.cuda_stream)
+    gid = eng.add_grid(ds["times"], ds["lambdas"])
+    mid = eng.add_model(gid, SPLIT_T, 0, bands=[(BAND[0] - 1, BAND[1], BAND[2], BAND[3], 0)])
+    flags = misti_b200.FLAG_CORRECT | misti_b200.FLAG_CPFIT | misti_b200.FLAG_SMOOTH | misti_b200.FLAG_UNFOLDED
+    p = torch.from_numpy(np.random.default_rng(99).uniform(0, 5, (B, 1))).to(dev)
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+    k2 = {}
+    for R in (1, len(bs)):
+        eng.set_data(bs[:R], True)
+        llh = torch.empty((B, R), dtype=torch.float64, device=dev)
+        ms = []
+        for it in range(7):
+            flush.zero_()
+            eng.evaluate_device(B, 1, p.data_ptr(), llh.data_ptr(), model=mid, flags=flags)
+            if it >= 2:
+                ms.append(eng.last_kernel_ms()[1])
+        k2[R] = float(np.median(ms))
+        finite = bool(torch.isfinite(llh).all().item())
+        del llh
+    eng.close()
+    R = len(bs)
+    extra = k2[R] - k2[1]
+    peak = _measured_hbm()
+    gbs = B * (R - 1) * 8 / (extra * 1e-3) / 1e9
+    return {"items": B, "rows": R, "pairs": B * R, "jsfs_likelihood_kernels_ms": {"1_row": k2[1], "%d_rows" % R: k2[R]}, "stage_ms": extra,
+            "pairs_per_s": B * (R - 1) / (extra * 1e-3), "hbm_write_gbs": gbs, "hbm_peak_gbs": peak, "frac_of_hbm_peak": gbs / peak if peak else None,
+            "finite": finite, "bound": "hbm (8 B written per pair; the 64-byte data rows stay in L2)"}
+
+
 def run_gpu(args):
     import numpy as np
     import torch
@@ -472,6 +515,7 @@ def run_gpu(args):
 
     # ---- the other BASELINE configurations at the same batch size (device time of the kernels) ----
     cfgs = None if args.skip_fits else config_sweep(local, stream, min(B, 65536), rank)
+    lstage = None if args.skip_fits else likelihood_stage(local, stream, min(B, 65536))
 
     # ---- time to fit ---------------------------------------------------------------------------
     t_fit0 = time.monotonic()
@@ -562,7 +606,7 @@ def run_gpu(args):
             "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": B * 8, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / args.steps,
                     "returns": "llh of every item of the job (all-gathered at N > 1), expected JSFS [7] and status of this rank's items"},
-            "gpu_launches": launches, "roofline": roofline, "batch_sweep": sweep, "config_sweep": cfgs, "cpu_baseline": cpu, "time_to_fit": ttf, "clocks": clocks}
+            "gpu_launches": launches, "roofline": roofline, "batch_sweep": sweep, "config_sweep": cfgs, "likelihood_stage": lstage, "cpu_baseline": cpu, "time_to_fit": ttf, "clocks": clocks}
     _emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
