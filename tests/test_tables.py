@@ -206,3 +206,96 @@ def test_sixteen_lane_run_table():
         assert open_row is None
     want = [(r, col[i], ab[i], val[i]) for r in range(44) for i in range(rp[r], rp[r + 1])]
     assert sorted(got) == sorted(want)
+
+
+def test_pair_kernel_code_is_up_to_date_and_equals_the_generator(tmp_path, monkeypatch):
+    """csrc/misti_pair_code.h (the straight-line code of the pair-of-lanes JSFS kernel) is what tools/gen_pair_tables.py
+    generates today -- the generator asserts the deme-exchange symmetry of the generator entries, of the projector products
+    of the zero-migration runs, of StateToJAF and of CollapsePops on the way -- and one term of its sweep, interpreted here
+    for both lanes of a pair, is the mat-vec with A = I + M / q of the oracle's generator."""
+    spec = importlib.util.spec_from_file_location("gen_pair_tables", os.path.join(ROOT, "tools", "gen_pair_tables.py"))
+    gp = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gp)
+    out = tmp_path / "misti_pair_code.h"
+    monkeypatch.setattr(gp, "OUT", str(out))
+    gp.main()
+    code = out.read_text()
+    assert code == open(os.path.join(ROOT, "misti_b200", "csrc", "misti_pair_code.h")).read()
+    # interpret MISTI_PAIR_TERM for the two lanes of a pair
+    rows = eval(re.search(r"#define MISTI_PAIR_ROW_INIT (.*)", code).group(1).replace("{", "[").replace("}", "]"))
+    dcls = eval(re.search(r"#define MISTI_PAIR_DIAG_INIT (.*)", code).group(1).replace("{", "[").replace("}", "]"))
+    body = code[code.index("#define MISTI_PAIR_TERM"):]
+    body = body[body.index("\n") + 1:body.index("} while (0)")]
+    stmts = [ln.strip().rstrip("\\").strip() for ln in body.splitlines() if ln.strip()]
+    rng = np.random.default_rng(8)
+    rate = rng.uniform(0.1, 2.0, 4)  # coalescence in deme 0 / 1, migration out of deme 0 / 1
+    ent, diag = _macro("MISTI_GEN_ENTRIES_INIT"), _macro("MISTI_GEN_DIAG_INIT")
+    q = max(sum(d[k] * rate[k] for k in range(4)) for d in diag)
+    A = np.zeros((44, 44))
+    for r, c, k, n in ent:
+        A[r, c] += n * rate[k] / q
+    for c in range(44):
+        A[c, c] = 1.0 - sum(diag[c][k] * rate[k] for k in range(4)) / q
+    y44 = rng.uniform(0.0, 1.0, 44)
+    want = A @ y44
+    lanes = []
+    for role in (0, 1):
+        rq = [rate[k ^ role] / q for k in range(4)]  # lane 1 reads the rate table with the kinds swapped
+        cf = [(1, 2, 4)[c // 4] * rq[c % 4] for c in range(10)]
+        dg = [max(0.0, 1.0 - sum(t[k] * rq[k] for k in range(4))) for t in dcls]
+        lanes.append({"y": [y44[s] for s in rows[role]], "cf": cf, "dg": dg})
+    new = []
+    for role in (0, 1):
+        me, other = lanes[role], lanes[1 - role]
+        env = {"y": list(me["y"]), "Ia": [0.0] * 23, "P1": [0.0] * 23, "cf": me["cf"], "dg": me["dg"], "tq": 0.0, "p": 1.0,
+               "fma": lambda a, b, c: a * b + c}
+        for st in stmts:
+            st = st.replace("const double ", "").rstrip(";")
+            for part in [x for x in st.split(";") if x.strip()]:
+                part = part.strip()
+                m = re.match(r"(z\d+) = __shfl_xor_sync\(msk, y\[(\d+)\], 1\)", part)
+                if m:
+                    env[m.group(1)] = other["y"][int(m.group(2))]  # the partner's OLD value
+                    continue
+                exec(part, {}, env)
+        new.append(env["y"])
+    for role in (0, 1):
+        for i, s in enumerate(rows[role]):
+            assert abs(new[role][i] - want[s]) < 1e-14, (role, i, s)
+
+
+def test_pair_kernel_run_code_equals_the_projector_table():
+    """MISTI_PAIR_RUN (a run of intervals without migration in the pair kernel), interpreted for both lanes: P <- sum_ab e_ab
+    G_ab P and integral += sum_ab c_ab G_ab P with the projector products of misti_tables.h; lane 1 reads the coefficients
+    with a and b exchanged."""
+    code = open(os.path.join(ROOT, "misti_b200", "csrc", "misti_pair_code.h")).read()
+    rows = eval(re.search(r"#define MISTI_PAIR_ROW_INIT (.*)", code).group(1).replace("{", "[").replace("}", "]"))
+    swap = eval(re.search(r"#define MISTI_PAIR_ABSWAP_INIT (.*)", code).group(1).replace("{", "[").replace("}", "]"))
+    body = code[code.index("#define MISTI_PAIR_RUN"):]
+    body = body[body.index("\n") + 1:body.index("} while (0)")]
+    stmts = [ln.strip().rstrip("\\").strip() for ln in body.splitlines() if ln.strip()]
+    rp, col, ab, val = (_macro("MISTI_NM_ROWPTR_INIT"), _macro("MISTI_NM_COL_INIT"), _macro("MISTI_NM_AB_INIT"), _macro("MISTI_NM_VAL_INIT"))
+    rng = np.random.default_rng(12)
+    e = np.concatenate([[1.0], rng.uniform(0.1, 1.0, 7)])
+    c = rng.uniform(0.1, 2.0, 8)
+    y44 = rng.uniform(0.0, 1.0, 44)
+    want_p, want_i = np.zeros(44), np.zeros(44)
+    for r in range(44):
+        for k in range(rp[r], rp[r + 1]):
+            want_p[r] += e[ab[k]] * val[k] * y44[col[k]]
+            want_i[r] += c[ab[k]] * val[k] * y44[col[k]]
+    lanes = [[y44[s] for s in rows[role]] for role in (0, 1)]
+    for role in (0, 1):
+        env = {"y": list(lanes[role]), "Ia": [0.0] * 23, "fma": lambda a, b, cc: a * b + cc,
+               "E": [e[swap[a] if role else a] for a in range(8)], "C": [c[swap[a] if role else a] for a in range(8)]}
+        for st in stmts:
+            st = st.replace("const double ", "").replace("double ", "").replace("{", "").replace("}", "")
+            for part in [x.strip() for x in st.split(";") if x.strip()]:
+                m = re.match(r"(z\d+) = __shfl_xor_sync\(msk, y\[(\d+)\], 1\)", part)
+                if m:
+                    env[m.group(1)] = lanes[1 - role][int(m.group(2))]
+                    continue
+                for piece in part.split(", ") if re.match(r"pe\d+ = 0.0, ir\d+ = 0.0", part) else [part]:
+                    exec(piece, {}, env)
+        for i, s in enumerate(rows[role]):
+            assert abs(env["y"][i] - want_p[s]) < 1e-13 and abs(env["Ia"][i] - want_i[s]) < 1e-13, (role, i, s)
